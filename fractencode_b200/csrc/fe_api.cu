@@ -1,0 +1,609 @@
+// fe_api.cu -- the extern "C" entry points of include/fractencode_b200.h and the host-side
+// orchestration of one search level / the quadtree / decode on the ctx stream.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <utility>
+
+#include "fe_kernels.cuh"
+
+static std::string g_create_error;
+
+int fe_fail(fe_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define LAUNCH(ctx, kernel, grid, block, ...)                          \
+    do {                                                               \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);    \
+        (ctx)->stats.kernel_launches++;                                \
+        FE_CUDA(ctx, cudaGetLastError());                              \
+    } while (0)
+
+static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// Largest n16 (16 * SSE) whose reference distance double(float(n16/16)) / (S*S) is <= thr, looked
+// for in the exact regime n16 < 2^24 (SURVEY hard part 4).  Returns false when no n16 qualifies.
+static bool threshold_n16(double thr, uint32_t S, uint32_t* out) {
+    auto dist = [&](uint32_t n16) { return (double)(float)((double)n16 / 16.0) / (double)(S * S); };
+    if (!(thr >= 0.0) || dist(0) > thr) return false;
+    uint32_t lo = 0, hi = (1u << 24) - 1; // dist is monotone in n16
+    if (dist(hi) <= thr) { *out = hi; return true; }
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (dist(mid) <= thr) lo = mid; else hi = mid;
+    }
+    *out = lo;
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------------
+// ctx
+// -------------------------------------------------------------------------------------------------
+extern "C" int fe_abi_version(void) { return FE_ABI_VERSION; }
+
+extern "C" const char* fe_last_error(const fe_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int fe_create(fe_ctx** out, int device, void* stream) {
+    if (!out) return fe_fail(nullptr, FE_ERR_INVALID, "fe_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fe_fail(nullptr, FE_ERR_NO_DEVICE, "fe_create: no CUDA device (%s); this library has no CPU path",
+                       e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fe_fail(nullptr, FE_ERR_INVALID, "fe_create: device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fe_fail(nullptr, FE_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fe_fail(nullptr, FE_ERR_NO_DEVICE, "fe_create: device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fe_fail(nullptr, FE_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    fe_ctx* ctx = new fe_ctx();
+    ctx->device = device;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            delete ctx;
+            return fe_fail(nullptr, FE_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        ctx->own_stream = true;
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return FE_OK;
+}
+
+extern "C" void fe_destroy(fe_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->b_src, &ctx->b_tgt, &ctx->b_dom, &ctx->b_rng, &ctx->b_dom_cls, &ctx->b_rng_cls, &ctx->b_dom_order,
+                      &ctx->b_rng_order, &ctx->b_sort_tmp, &ctx->b_keys_tmp, &ctx->b_vals_tmp, &ctx->b_A, &ctx->b_Blo, &ctx->b_Bhi,
+                      &ctx->b_rowc, &ctx->b_coln, &ctx->b_rowbest, &ctx->b_rowhit, &ctx->b_hist, &ctx->b_level_items, &ctx->b_split,
+                      &ctx->b_scan, &ctx->b_scan_tmp, &ctx->b_rng_next, &ctx->b_counters, &ctx->b_A16, &ctx->b_B16, &ctx->b_tmaps,
+                      &ctx->b_items, &ctx->b_dec_a, &ctx->b_dec_b, &ctx->b_dec_items, &ctx->b_dec_sum, &ctx->b_q};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int fe_synchronize(fe_ctx* ctx) {
+    if (!ctx) return FE_ERR_INVALID;
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FE_OK;
+}
+
+extern "C" int fe_get_stats(const fe_ctx* ctx, fe_stats* out) {
+    if (!ctx || !out) return FE_ERR_INVALID;
+    *out = ctx->stats;
+    return FE_OK;
+}
+
+extern "C" int fe_stats_reset(fe_ctx* ctx) {
+    if (!ctx) return FE_ERR_INVALID;
+    ctx->stats = fe_stats{};
+    return FE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// images
+// -------------------------------------------------------------------------------------------------
+static int upload_plane(fe_ctx* ctx, DevBuf& buf, Plane& pl, const void* px, uint32_t w, uint32_t h, uint32_t stride, cudaMemcpyKind kind) {
+    if (!px || !w || !h || stride < w) return fe_fail(ctx, FE_ERR_INVALID, "image: null pixels, zero size or stride < width");
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    FE_CUDA(ctx, buf.ensure((size_t)h * stride + 64));
+    FE_CUDA(ctx, cudaMemcpyAsync(buf.p, px, (size_t)h * stride, kind, ctx->stream));
+    pl.px = buf.as<uint8_t>();
+    pl.w = w; pl.h = h; pl.stride = stride;
+    return FE_OK;
+}
+
+extern "C" int fe_set_image(fe_ctx* ctx, const uint8_t* px, uint32_t w, uint32_t h, uint32_t stride) {
+    if (!ctx) return FE_ERR_INVALID;
+    FE_TRY(upload_plane(ctx, ctx->b_src, ctx->src, px, w, h, stride, cudaMemcpyHostToDevice));
+    ctx->tgt = ctx->src;
+    return FE_OK;
+}
+
+extern "C" int fe_set_images(fe_ctx* ctx, const uint8_t* spx, uint32_t sw, uint32_t sh, uint32_t ss, const uint8_t* tpx,
+                             uint32_t tw, uint32_t th, uint32_t ts) {
+    if (!ctx) return FE_ERR_INVALID;
+    FE_TRY(upload_plane(ctx, ctx->b_src, ctx->src, spx, sw, sh, ss, cudaMemcpyHostToDevice));
+    FE_TRY(upload_plane(ctx, ctx->b_tgt, ctx->tgt, tpx, tw, th, ts, cudaMemcpyHostToDevice));
+    return FE_OK;
+}
+
+extern "C" int fe_set_image_device(fe_ctx* ctx, const void* dpx, uint32_t w, uint32_t h, uint32_t stride) {
+    if (!ctx) return FE_ERR_INVALID;
+    FE_TRY(upload_plane(ctx, ctx->b_src, ctx->src, dpx, w, h, stride, cudaMemcpyDeviceToDevice));
+    ctx->tgt = ctx->src;
+    return FE_OK;
+}
+
+extern "C" int fe_set_synthetic_image(fe_ctx* ctx, uint32_t w, uint32_t h, uint64_t seed, int kind) {
+    if (!ctx || !w || !h || kind < 0 || kind > 2) return fe_fail(ctx, FE_ERR_INVALID, "fe_set_synthetic_image: bad arguments");
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    FE_CUDA(ctx, ctx->b_src.ensure((size_t)h * w + 64));
+    ctx->src.px = ctx->b_src.as<uint8_t>();
+    ctx->src.w = w; ctx->src.h = h; ctx->src.stride = w;
+    ctx->tgt = ctx->src;
+    dim3 block(32, 8), grid(cdiv(w, 32), cdiv(h, 8));
+    LAUNCH(ctx, k_synth, grid, block, ctx->src.px, w, h, w, (unsigned long long)seed, kind);
+    return FE_OK;
+}
+
+extern "C" int fe_get_image(fe_ctx* ctx, uint8_t* out, uint32_t stride) {
+    if (!ctx || !out) return FE_ERR_INVALID;
+    if (!ctx->src.px) return fe_fail(ctx, FE_ERR_STATE, "fe_get_image: no image set");
+    if (stride < ctx->src.w) return fe_fail(ctx, FE_ERR_INVALID, "fe_get_image: stride < width");
+    FE_CUDA(ctx, cudaMemcpy2DAsync(out, stride, ctx->src.px, ctx->src.stride, ctx->src.w, ctx->src.h, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// classification of a host list
+// -------------------------------------------------------------------------------------------------
+extern "C" int fe_classify(fe_ctx* ctx, int which, const fe_grid_item* items, size_t n, int32_t* bins_out) {
+    if (!ctx || !items || !bins_out) return fe_fail(ctx, FE_ERR_INVALID, "fe_classify: null argument");
+    const Plane& pl = which ? ctx->tgt : ctx->src;
+    if (!pl.px) return fe_fail(ctx, FE_ERR_STATE, "fe_classify: no image set");
+    if (n == 0) return FE_OK;
+    for (size_t i = 0; i < n; ++i)
+        if (items[i].w < 2 || items[i].h < 2 || items[i].x + items[i].w > pl.w || items[i].y + items[i].h > pl.h)
+            return fe_fail(ctx, FE_ERR_INVALID, "fe_classify: item %zu outside the image or smaller than 2x2", i);
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    FE_CUDA(ctx, ctx->b_dom.ensure(n * sizeof(fe_grid_item)));
+    FE_CUDA(ctx, ctx->b_dom_cls.ensure(n * sizeof(int32_t)));
+    FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_dom.p, items, n * sizeof(fe_grid_item), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_classify, cdiv(n * 32, 256), 256, pl.px, pl.stride, ctx->b_dom.as<fe_grid_item>(), (uint32_t)n, ctx->b_dom_cls.as<int32_t>(), 1);
+    FE_CUDA(ctx, cudaMemcpyAsync(bins_out, ctx->b_dom_cls.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// one search level on device lists
+// -------------------------------------------------------------------------------------------------
+struct LevelIO {
+    const fe_grid_item* d_dom = nullptr; uint32_t nD = 0;
+    const fe_grid_item* d_rng = nullptr; uint32_t nR = 0;
+    LevelGeom g;
+    fe_encode_item* d_out = nullptr; // [nR], by range index
+    uint32_t* d_split = nullptr;     // [nR] or NULL
+    int can_split = 0;
+    int stat_level = -1;             // quadtree level index for the per-level stats, -1 = none
+};
+
+// Stable bucketing of n items by class (7 buckets: -1, 0..5).  order[pos] = item index, off[c]..off[c+1] = bucket c.
+static int bucket_by_class(fe_ctx* ctx, const int32_t* d_cls, uint32_t n, DevBuf& order, uint32_t off[8]) {
+    FE_CUDA(ctx, order.ensure((size_t)n * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_keys_tmp.ensure((size_t)n * 2 + 64));
+    FE_CUDA(ctx, ctx->b_vals_tmp.ensure((size_t)n * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_hist.ensure(8 * sizeof(uint32_t)));
+    uint8_t* keys_in = ctx->b_keys_tmp.as<uint8_t>();
+    uint8_t* keys_out = keys_in + n;
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_hist.p, 0, 8 * sizeof(uint32_t), ctx->stream));
+    LAUNCH(ctx, k_class_keys, cdiv(n, 256), 256, d_cls, n, keys_in, ctx->b_hist.as<uint32_t>());
+    LAUNCH(ctx, k_iota, cdiv(n, 256), 256, ctx->b_vals_tmp.as<uint32_t>(), n);
+    size_t tmp_bytes = 0;
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, ctx->b_vals_tmp.as<uint32_t>(), order.as<uint32_t>(), (int)n, 0, 3, ctx->stream));
+    FE_CUDA(ctx, ctx->b_sort_tmp.ensure(tmp_bytes));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_bytes, keys_in, keys_out, ctx->b_vals_tmp.as<uint32_t>(), order.as<uint32_t>(), (int)n, 0, 3, ctx->stream));
+    ctx->stats.kernel_launches += 3; // cub: histogram + scan + one onesweep pass
+    uint32_t hist[8];
+    FE_CUDA(ctx, cudaMemcpyAsync(hist, ctx->b_hist.p, sizeof(hist), cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    off[0] = 0;
+    for (int c = 0; c < 7; ++c) off[c + 1] = off[c] + hist[c];
+    return FE_OK;
+}
+
+static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
+    const LevelGeom& g = io.g;
+    const uint32_t nR = io.nR, nD = io.nD;
+    if (nR == 0) return FE_OK;
+    const bool timed = io.stat_level >= 0 && io.stat_level < 8;
+    if (timed) cudaEventRecord(ctx->ev[0], ctx->stream);
+
+    FE_CUDA(ctx, ctx->b_counters.ensure(4 * sizeof(uint32_t)));
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.p, 0, 4 * sizeof(uint32_t), ctx->stream));
+
+    // ---- classes and buckets ----
+    uint32_t doff[8] = {0, nD, nD, nD, nD, nD, nD, nD}, roff[8] = {0, nR, nR, nR, nR, nR, nR, nR};
+    const uint32_t* dom_order = nullptr;
+    const uint32_t* rng_order = nullptr;
+    int nbuckets = 1;
+    if (p.use_classifier && nD) {
+        FE_CUDA(ctx, ctx->b_dom_cls.ensure((size_t)nD * 4));
+        FE_CUDA(ctx, ctx->b_rng_cls.ensure((size_t)nR * 4));
+        LAUNCH(ctx, k_classify, cdiv((uint64_t)nD * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, nD, ctx->b_dom_cls.as<int32_t>(), 0);
+        LAUNCH(ctx, k_classify, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, ctx->b_rng_cls.as<int32_t>(), 0);
+        FE_TRY(bucket_by_class(ctx, ctx->b_dom_cls.as<int32_t>(), nD, ctx->b_dom_order, doff));
+        FE_TRY(bucket_by_class(ctx, ctx->b_rng_cls.as<int32_t>(), nR, ctx->b_rng_order, roff));
+        dom_order = ctx->b_dom_order.as<uint32_t>();
+        rng_order = ctx->b_rng_order.as<uint32_t>();
+        nbuckets = 7;
+    }
+
+    // ---- operands ----
+    const uint32_t npool = g.fast ? 1u : 4u;
+    FE_CUDA(ctx, ctx->b_A.ensure((size_t)nR * 4 * g.Npad));
+    FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)nR * 4));
+    FE_CUDA(ctx, ctx->b_rowbest.ensure((size_t)nR * 4 * 8));
+    FE_CUDA(ctx, ctx->b_rowhit.ensure((size_t)nR * 4 * 4));
+    LAUNCH(ctx, k_build_rows, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, rng_order, nR, g.T, g.Npad,
+           g.fast ? 1 : 0, ctx->b_A.as<uint8_t>(), ctx->b_rowc.as<uint32_t>());
+    if (nD) {
+        FE_CUDA(ctx, ctx->b_Blo.ensure((size_t)nD * npool * g.Npad));
+        FE_CUDA(ctx, ctx->b_Bhi.ensure((size_t)nD * npool * g.Npad));
+        FE_CUDA(ctx, ctx->b_coln.ensure((size_t)nD * npool * 4));
+        LAUNCH(ctx, k_build_pool, cdiv((uint64_t)nD * npool * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, dom_order, nD, npool,
+               g.T, g.rho, g.Npad, ctx->b_Blo.as<uint8_t>(), ctx->b_Bhi.as<uint8_t>(), ctx->b_coln.as<uint32_t>());
+    }
+    LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
+    LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
+    if (timed) cudaEventRecord(ctx->ev[1], ctx->stream);
+
+    // ---- search, one launch per classifier bucket ----
+    uint32_t thr16 = 0;
+    const bool use_thr = threshold_n16(p.rms_threshold, g.S, &thr16);
+    uint64_t matches = 0;
+    for (int c = 0; c < nbuckets; ++c) {
+        const uint32_t rc = roff[c + 1] - roff[c], dc = doff[c + 1] - doff[c];
+        if (!rc || !dc) continue;
+        SearchArgs a{};
+        a.A = ctx->b_A.as<uint8_t>();
+        a.Blo = ctx->b_Blo.as<uint8_t>();
+        a.Bhi = ctx->b_Bhi.as<uint8_t>();
+        a.rowc = ctx->b_rowc.as<uint32_t>();
+        a.coln = ctx->b_coln.as<uint32_t>();
+        a.rowbest = ctx->b_rowbest.as<unsigned long long>();
+        a.rowhit = ctx->b_rowhit.as<uint32_t>();
+        a.row0 = roff[c] * 4; a.nrows = rc * 4;
+        a.col0 = doff[c]; a.ncols = dc;
+        a.Npad = g.Npad;
+        a.pool_stride_cols = g.fast ? 0 : nD;
+        a.thr16 = thr16;
+        a.use_thr = use_thr ? 1u : 0u;
+        FE_CUDA(ctx, launch_search_exact(ctx, a));
+        matches += (uint64_t)rc * dc * 4;
+    }
+    ctx->stats.exact_levels++;
+    ctx->stats.matches += matches;
+    if (timed) cudaEventRecord(ctx->ev[2], ctx->stream);
+
+    // ---- winners ----
+    FinalizeArgs f{};
+    f.src = ctx->src.px; f.src_stride = ctx->src.stride;
+    f.tgt = ctx->tgt.px; f.tgt_stride = ctx->tgt.stride;
+    f.dom = io.d_dom; f.rng = io.d_rng;
+    f.dom_order = dom_order; f.rng_order = rng_order;
+    f.rowbest = ctx->b_rowbest.as<unsigned long long>();
+    f.rowhit = ctx->b_rowhit.as<uint32_t>();
+    f.n = nR;
+    f.use_thr = use_thr ? 1u : 0u;
+    f.thr = p.rms_threshold; f.s_max = p.s_max; f.fma = p.fma;
+    f.can_split = io.can_split;
+    f.thr16 = thr16;
+    f.out = io.d_out; f.split = io.d_split;
+    f.mismatch = ctx->b_counters.as<uint32_t>();
+    f.fp32_regime = ctx->b_counters.as<uint32_t>() + 1;
+    LAUNCH(ctx, k_finalize, cdiv((uint64_t)nR * 32, 256), 256, f);
+    if (timed) cudaEventRecord(ctx->ev[3], ctx->stream);
+
+    uint32_t counters[4];
+    FE_CUDA(ctx, cudaMemcpyAsync(counters, ctx->b_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (counters[0]) return fe_fail(ctx, FE_ERR_CUDA, "internal: %u winners whose search score disagrees with the direct recomputation (T=%u)", counters[0], g.T);
+    ctx->stats.fp32_regime_items += counters[1];
+    if (timed) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.level_prep_ms[io.stat_level] = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.level_search_ms[io.stat_level] = ms;
+        ctx->stats.level_ranges[io.stat_level] = nR;
+        ctx->stats.level_matches[io.stat_level] = matches;
+    }
+    return FE_OK;
+}
+
+static int make_geom(fe_ctx* ctx, uint32_t S, uint32_t T, bool even_origins, LevelGeom* g) {
+    if (T < 2 || S <= T || S % T) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "geometry: need S a multiple of T, S > T >= 2 (got S=%u T=%u)", S, T);
+    if (T > 64) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "geometry: range size %u > 64 (32-bit score arithmetic)", T);
+    g->S = S; g->T = T; g->rho = S / T;
+    g->N = T * T;
+    g->Npad = (g->N + 15u) & ~15u;
+    g->fast = (g->rho == 2) && even_origins;
+    return FE_OK;
+}
+
+extern "C" int fe_encode_level(fe_ctx* ctx, const fe_grid_item* domains, size_t n_dom, const fe_grid_item* ranges, size_t n_rng,
+                               const fe_params* params, fe_encode_item* out) {
+    if (!ctx) return FE_ERR_INVALID;
+    if (!params || (!ranges && n_rng) || (!domains && n_dom) || (!out && n_rng)) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_level: null argument");
+    if (!ctx->src.px) return fe_fail(ctx, FE_ERR_STATE, "fe_encode_level: call fe_set_image first");
+    if (n_rng == 0) return FE_OK;
+    if (n_dom > 0x3FFFFFFFu || n_rng > 0x3FFFFFFFu) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_encode_level: list too long");
+    const uint32_t T = ranges[0].w;
+    for (size_t i = 0; i < n_rng; ++i) {
+        const fe_grid_item& r = ranges[i];
+        if (r.w != T || r.h != T) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_encode_level: range %zu is %ux%u, expected square %u", i, r.w, r.h, T);
+        if (r.x + T > ctx->tgt.w || r.y + T > ctx->tgt.h) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_level: range %zu outside the target image", i);
+    }
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    FE_CUDA(ctx, ctx->b_level_items.ensure(n_rng * sizeof(fe_encode_item)));
+    FE_CUDA(ctx, ctx->b_rng.ensure(n_rng * sizeof(fe_grid_item)));
+    FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_rng.p, ranges, n_rng * sizeof(fe_grid_item), cudaMemcpyHostToDevice, ctx->stream));
+    LevelIO io;
+    io.d_rng = ctx->b_rng.as<fe_grid_item>(); io.nR = (uint32_t)n_rng;
+    io.d_out = ctx->b_level_items.as<fe_encode_item>();
+    if (n_dom) {
+        const uint32_t S = domains[0].w;
+        bool even = true;
+        for (size_t i = 0; i < n_dom; ++i) {
+            const fe_grid_item& d = domains[i];
+            if (d.w != S || d.h != S) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_encode_level: domain %zu is %ux%u, expected square %u", i, d.w, d.h, S);
+            if (d.x + S > ctx->src.w || d.y + S > ctx->src.h) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_level: domain %zu outside the source image", i);
+            even = even && !(d.x & 1) && !(d.y & 1);
+        }
+        FE_TRY(make_geom(ctx, S, T, even, &io.g));
+        FE_CUDA(ctx, ctx->b_dom.ensure(n_dom * sizeof(fe_grid_item)));
+        FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_dom.p, domains, n_dom * sizeof(fe_grid_item), cudaMemcpyHostToDevice, ctx->stream));
+        io.d_dom = ctx->b_dom.as<fe_grid_item>(); io.nD = (uint32_t)n_dom;
+    } else {
+        FE_TRY(make_geom(ctx, 2 * T, T, true, &io.g));
+    }
+    FE_TRY(run_level(ctx, io, *params));
+    FE_CUDA(ctx, cudaMemcpyAsync(out, io.d_out, n_rng * sizeof(fe_encode_item), cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// quadtree
+// -------------------------------------------------------------------------------------------------
+extern "C" int fe_encode_quadtree_device(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params, size_t* n_out) {
+    if (!ctx) return FE_ERR_INVALID;
+    if (!params) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_quadtree: params is NULL");
+    if (!ctx->src.px) return fe_fail(ctx, FE_ERR_STATE, "fe_encode_quadtree: call fe_set_image first");
+    if (ctx->tgt.px != ctx->src.px) return fe_fail(ctx, FE_ERR_STATE, "fe_encode_quadtree: needs a single image (fe_set_image)");
+    const uint32_t W = ctx->src.w, H = ctx->src.h;
+    if (t_min < 2 || t_max < t_min || t_max > 64 || (t_max & (t_max - 1)) || (t_min & (t_min - 1)))
+        return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_encode_quadtree: block sizes must be powers of two, 2 <= t_min <= t_max <= 64");
+    if (W % t_max || H % t_max) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_quadtree: image %ux%u not aligned to %u", W, H, t_max);
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t cap = (size_t)(W / t_min) * (H / t_min);
+    FE_CUDA(ctx, ctx->b_items.ensure(cap * sizeof(fe_encode_item)));
+    size_t n_pending = (size_t)(W / t_max) * (H / t_max);
+    FE_CUDA(ctx, ctx->b_rng.ensure(cap * sizeof(fe_grid_item)));
+    FE_CUDA(ctx, ctx->b_rng_next.ensure(cap * sizeof(fe_grid_item)));
+    LAUNCH(ctx, k_uniform_grid, cdiv(n_pending, 256), 256, ctx->b_rng.as<fe_grid_item>(), W / t_max, (uint32_t)n_pending, t_max, t_max);
+    for (int l = 0; l < 8; ++l) {
+        ctx->stats.level_items[l] = ctx->stats.level_ranges[l] = ctx->stats.level_matches[l] = 0;
+        ctx->stats.level_search_ms[l] = ctx->stats.level_prep_ms[l] = 0.f;
+    }
+    size_t offset = 0;
+    int level = 0;
+    for (uint32_t T = t_max; T >= t_min && n_pending; T /= 2, ++level) {
+        const uint32_t S = 2 * T;
+        const uint32_t dnx = W >= S ? W / T - 1 : 0, dny = H >= S ? H / T - 1 : 0;
+        const size_t nD = (size_t)dnx * dny;
+        LevelIO io;
+        FE_TRY(make_geom(ctx, S, T, true, &io.g));
+        if (nD) {
+            FE_CUDA(ctx, ctx->b_dom.ensure(nD * sizeof(fe_grid_item)));
+            LAUNCH(ctx, k_uniform_grid, cdiv(nD, 256), 256, ctx->b_dom.as<fe_grid_item>(), dnx, (uint32_t)nD, S, T);
+        }
+        FE_CUDA(ctx, ctx->b_level_items.ensure(n_pending * sizeof(fe_encode_item)));
+        FE_CUDA(ctx, ctx->b_split.ensure(n_pending * 4 + 4));
+        io.d_dom = ctx->b_dom.as<fe_grid_item>(); io.nD = (uint32_t)nD;
+        io.d_rng = ctx->b_rng.as<fe_grid_item>(); io.nR = (uint32_t)n_pending;
+        io.d_out = ctx->b_level_items.as<fe_encode_item>();
+        io.can_split = (T / 2 >= t_min) ? 1 : 0;
+        io.d_split = ctx->b_split.as<uint32_t>();
+        io.stat_level = level;
+        FE_TRY(run_level(ctx, io, *params));
+        size_t n_split = 0;
+        if (io.can_split) {
+            FE_CUDA(ctx, ctx->b_scan.ensure(n_pending * 4 + 4));
+            size_t tmp_bytes = 0;
+            FE_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, io.d_split, ctx->b_scan.as<uint32_t>(), (int)n_pending, ctx->stream));
+            FE_CUDA(ctx, ctx->b_scan_tmp.ensure(tmp_bytes));
+            FE_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_scan_tmp.p, tmp_bytes, io.d_split, ctx->b_scan.as<uint32_t>(), (int)n_pending, ctx->stream));
+            ctx->stats.kernel_launches += 2;
+            uint32_t last_scan = 0, last_flag = 0;
+            FE_CUDA(ctx, cudaMemcpyAsync(&last_scan, ctx->b_scan.as<uint32_t>() + (n_pending - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+            FE_CUDA(ctx, cudaMemcpyAsync(&last_flag, io.d_split + (n_pending - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+            FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            n_split = (size_t)last_scan + last_flag;
+            LAUNCH(ctx, k_quadtree_scatter, cdiv(n_pending, 256), 256, ctx->b_rng.as<fe_grid_item>(), io.d_out, io.d_split, ctx->b_scan.as<uint32_t>(),
+                   (uint32_t)n_pending, ctx->b_rng_next.as<fe_grid_item>(), ctx->b_items.as<fe_encode_item>() + offset);
+        } else {
+            FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_items.as<fe_encode_item>() + offset, io.d_out, n_pending * sizeof(fe_encode_item), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        const size_t kept = n_pending - n_split;
+        ctx->stats.level_items[level] = kept;
+        offset += kept;
+        std::swap(ctx->b_rng, ctx->b_rng_next);
+        n_pending = 4 * n_split;
+    }
+    ctx->n_items = offset;
+    if (n_out) *n_out = offset;
+    return FE_OK;
+}
+
+extern "C" int fe_fetch_items(fe_ctx* ctx, fe_encode_item* out, size_t cap, size_t* n_out) {
+    if (!ctx || (!out && ctx->n_items)) return fe_fail(ctx, FE_ERR_INVALID, "fe_fetch_items: null argument");
+    if (cap < ctx->n_items) return fe_fail(ctx, FE_ERR_CAPACITY, "fe_fetch_items: %zu items, capacity %zu", ctx->n_items, cap);
+    if (ctx->n_items) FE_CUDA(ctx, cudaMemcpyAsync(out, ctx->b_items.p, ctx->n_items * sizeof(fe_encode_item), cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_out) *n_out = ctx->n_items;
+    return FE_OK;
+}
+
+extern "C" const void* fe_device_items(const fe_ctx* ctx, size_t* n_out) {
+    if (!ctx) return nullptr;
+    if (n_out) *n_out = ctx->n_items;
+    return ctx->b_items.p;
+}
+
+extern "C" int fe_encode_quadtree(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params, fe_encode_item* out,
+                                  size_t cap, size_t* n_out, size_t* level_counts) {
+    size_t n = 0;
+    FE_TRY(fe_encode_quadtree_device(ctx, t_max, t_min, params, &n));
+    if (level_counts) {
+        int level = 0;
+        for (uint32_t T = t_max; T >= t_min; T /= 2, ++level) level_counts[level] = (size_t)ctx->stats.level_items[level];
+    }
+    FE_TRY(fe_fetch_items(ctx, out, cap, n_out));
+    return FE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// decode
+// -------------------------------------------------------------------------------------------------
+extern "C" int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uint8_t* target, uint32_t width, uint32_t height,
+                         uint32_t stride, int max_iters, double rms_eps, int use_fma, int* iterations, double* rms_out) {
+    if (!ctx) return FE_ERR_INVALID;
+    if ((!items && n) || !target || !width || !height || stride < width) return fe_fail(ctx, FE_ERR_INVALID, "fe_decode: bad arguments");
+    if (n > 0x7FFFFFFFu || (uint64_t)width * height > 0xFFFFFFFFull) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_decode: too large");
+    // validate + layout
+    std::vector<uint32_t> pix_off(n + 1, 0);
+    bool uniform = n > 0, has_default = false;
+    uint64_t area = 0;
+    const uint32_t T0 = n ? items[0].w : 0;
+    for (size_t i = 0; i < n; ++i) {
+        const fe_encode_item& e = items[i];
+        if (!e.w || !e.h || e.x + e.w > width || e.y + e.h > height) return fe_fail(ctx, FE_ERR_INVALID, "fe_decode: item %zu outside the image", i);
+        if (e.src_w && (e.src_w != e.src_h || e.match_x + e.src_w > width || e.match_y + e.src_h > height || e.transform < 0 || e.transform > 7 || e.src_w < 2))
+            return fe_fail(ctx, FE_ERR_INVALID, "fe_decode: item %zu has an invalid source block", i);
+        pix_off[i] = (uint32_t)area;
+        area += (uint64_t)e.w * e.h;
+        uniform = uniform && e.w == T0 && e.h == T0;
+        if (!e.src_w || !e.src_h) has_default = true;
+    }
+    if (area > 0xFFFFFFFFull) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_decode: item areas overflow");
+    pix_off[n] = (uint32_t)area;
+    uniform = uniform && (T0 % 4 == 0);
+    const bool covered = !has_default && area == (uint64_t)width * height; // non-overlapping full cover -> ping-pong needs no copy
+    const int iters = max_iters < 0 ? 300 : max_iters;
+    const size_t bytes = (size_t)height * stride;
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    FE_CUDA(ctx, ctx->b_dec_a.ensure(bytes + 64));
+    FE_CUDA(ctx, ctx->b_dec_b.ensure(bytes + 64));
+    FE_CUDA(ctx, ctx->b_dec_items.ensure(n * sizeof(fe_encode_item) + (n + 1) * 4 + 64));
+    FE_CUDA(ctx, ctx->b_dec_sum.ensure(8));
+    fe_encode_item* d_items = ctx->b_dec_items.as<fe_encode_item>();
+    uint32_t* d_off = reinterpret_cast<uint32_t*>(d_items + n);
+    if (n) {
+        FE_CUDA(ctx, cudaMemcpyAsync(d_items, items, n * sizeof(fe_encode_item), cudaMemcpyHostToDevice, ctx->stream));
+        FE_CUDA(ctx, cudaMemcpyAsync(d_off, pix_off.data(), (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    uint8_t* src = ctx->b_dec_a.as<uint8_t>();
+    uint8_t* dst = ctx->b_dec_b.as<uint8_t>();
+    FE_CUDA(ctx, cudaMemsetAsync(src, 100, bytes, ctx->stream)); // Encoder2.hpp:69
+    FE_CUDA(ctx, cudaMemcpyAsync(dst, target, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    int i = 0;
+    double rms = 0.0;
+    for (; i < iters; ++i) {
+        if (n) {
+            if (uniform)
+                LAUNCH(ctx, k_decode_step_uniform, cdiv((uint64_t)n * T0 * (T0 / 4), 256), 256, src, dst, stride, d_items, (uint32_t)n, T0, use_fma);
+            else
+                LAUNCH(ctx, k_decode_step, cdiv(area, 256), 256, src, dst, stride, d_items, d_off, (uint32_t)n, (uint32_t)area, use_fma);
+        }
+        FE_CUDA(ctx, cudaMemsetAsync(ctx->b_dec_sum.p, 0, 8, ctx->stream));
+        LAUNCH(ctx, k_sqdiff, 148 * 8, 256, src, dst, width, height, stride, ctx->b_dec_sum.as<unsigned long long>());
+        unsigned long long sum64 = 0;
+        FE_CUDA(ctx, cudaMemcpyAsync(&sum64, ctx->b_dec_sum.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const int32_t wrapped = (int32_t)(uint32_t)(sum64 & 0xFFFFFFFFull); // the reference's int32 accumulator (metrics.h:27)
+        rms = (double)wrapped / (double)(uint32_t)(width * height);
+        if (rms < rms_eps) break;
+        if (covered) std::swap(src, dst); // source = target.copy(): every pixel is rewritten next step anyway
+        else FE_CUDA(ctx, cudaMemcpyAsync(src, dst, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    // after a swap the freshest plane is `src` unless we broke out before swapping
+    const uint8_t* result = dst;
+    if (covered && i == iters && iters > 0) result = src;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    FE_CUDA(ctx, cudaMemcpyAsync(target, result, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->stats.last_decode_ms, ctx->ev[0], ctx->ev[1]);
+    if (iterations) *iterations = i;
+    if (rms_out) *rms_out = rms;
+    return FE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// quantizer post-pass
+// -------------------------------------------------------------------------------------------------
+static double key_to_double(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+
+extern "C" int fe_quantize(fe_ctx* ctx, const fe_encode_item* items, size_t n, int bits_s, int bits_o, uint32_t* qs, uint32_t* qo,
+                           double minmax_out[4]) {
+    if (!ctx) return FE_ERR_INVALID;
+    if (!items || !n || !qs || !qo) return fe_fail(ctx, FE_ERR_INVALID, "fe_quantize: null or empty input");
+    if (bits_s < 2 || bits_s > 30 || bits_o < 2 || bits_o > 30) return fe_fail(ctx, FE_ERR_INVALID, "fe_quantize: bits out of range");
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    FE_CUDA(ctx, ctx->b_dec_items.ensure(n * sizeof(fe_encode_item)));
+    FE_CUDA(ctx, ctx->b_q.ensure(64 + n * 8));
+    FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_dec_items.p, items, n * sizeof(fe_encode_item), cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long mm[4] = {FE_INF64, 0, FE_INF64, 0};
+    unsigned long long* d_mm = reinterpret_cast<unsigned long long*>(ctx->b_q.as<uint8_t>());
+    FE_CUDA(ctx, cudaMemcpyAsync(d_mm, mm, sizeof(mm), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_minmax, 148 * 4, 256, ctx->b_dec_items.as<fe_encode_item>(), (uint32_t)n, d_mm);
+    FE_CUDA(ctx, cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // main.cpp:109-118: max starts at -1, min at DBL_MAX
+    const double min_s = std::fmin(1.7976931348623157e308, key_to_double(mm[0])), max_s = std::fmax(-1.0, key_to_double(mm[1]));
+    const double min_o = std::fmin(1.7976931348623157e308, key_to_double(mm[2])), max_o = std::fmax(-1.0, key_to_double(mm[3]));
+    if (minmax_out) { minmax_out[0] = min_s; minmax_out[1] = max_s; minmax_out[2] = min_o; minmax_out[3] = max_o; }
+    if (!(max_s > min_s) || !(max_o > min_o)) return fe_fail(ctx, FE_ERR_INVALID, "fe_quantize: degenerate value range (Quantizer asserts max > min)");
+    uint32_t* d_qs = reinterpret_cast<uint32_t*>(ctx->b_q.as<uint8_t>() + 64);
+    uint32_t* d_qo = d_qs + n;
+    LAUNCH(ctx, k_quantize, cdiv(n, 256), 256, ctx->b_dec_items.as<fe_encode_item>(), (uint32_t)n, min_s, max_s, min_o, max_o, bits_s, bits_o, d_qs, d_qo);
+    FE_CUDA(ctx, cudaMemcpyAsync(qs, d_qs, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaMemcpyAsync(qo, d_qo, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FE_OK;
+}

@@ -1,0 +1,611 @@
+// fe_kernels.cu -- CUDA kernels of the search path except the tcgen05 contraction
+// (fe_search_umma.cu): grids, classification, operand preparation, the exact integer
+// search, winner finalisation (least squares s/o), quadtree bookkeeping, decode gather,
+// quantizer and the synthetic image generator.  sm_100a only.
+//
+// Reference semantics restated here (sebsgit/fractencode, file:line):
+//   sampling        image/sampler.h:22-38, image/transform.h:32-41,96-109
+//   distance        image/metrics.h:37-50  (fp32 running sum of exact 1/16 multiples)
+//   classifier      encode/Classifier2.cpp:8-81
+//   s / o           encode/transformmatcher.h:98-108
+//   decode          encode/DecodeUtils.hpp:9-25, encode/Encoder2.hpp:67-99
+//   quantizer       encode/Quantizer.hpp:13-36
+#include "fe_kernels.cuh"
+
+__device__ __constant__ int8_t kMapDev[8][8] = {
+    {1, 0, 0, 0, 0, 1, 0, 0},   {0, 1, 0, 0, -1, 0, 1, 0}, {-1, 0, 1, 0, 0, -1, 0, 1}, {0, -1, 0, 1, 1, 0, 0, 0},
+    {1, 0, 0, 0, 0, -1, 0, 1},  {0, 1, 0, 0, 1, 0, 0, 0},  {-1, 0, 1, 0, 0, 1, 0, 0},  {0, -1, 0, 1, -1, 0, 1, 0},
+};
+
+// 2x2 box SUM (= 4 * SamplerBilinear::sample) at local (lx,ly) of patch (px,py,ps x ps) under isometry t.
+__device__ __forceinline__ int sample_sum4(const uint8_t* __restrict__ img, uint32_t stride, uint32_t px, uint32_t py,
+                                           uint32_t ps, uint32_t lx, uint32_t ly, int t) {
+    if (lx == ps - 1) --lx; // sampler.h:32-35
+    if (ly == ps - 1) --ly;
+    const int m0 = kMapDev[t][0], m1 = kMapDev[t][1], m4 = kMapDev[t][4], m5 = kMapDev[t][5];
+    const int e = (int)ps - 1;
+    const int gx = (int)px + m0 * (int)lx + m1 * (int)ly + (kMapDev[t][2] + kMapDev[t][3]) * e;
+    const int gy = (int)py + m4 * (int)lx + m5 * (int)ly + (kMapDev[t][6] + kMapDev[t][7]) * e;
+    const uint8_t* p = img + (size_t)gy * stride + gx;
+    const int s = (int)stride;
+    return p[0] + p[m4 * s + m0] + p[m5 * s + m1] + p[(m4 + m5) * s + m0 + m1];
+}
+
+// BrightnessBlocksClassifier2::getCategory (Classifier2.cpp:8-53): class of the strict ordering of the
+// four quadrant sums per the literal table; -1 when any two are equal or for the one ordering the
+// table misses (see below).
+__device__ __forceinline__ int category4(uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4) {
+    if (a1 == a2 || a1 == a3 || a1 == a4 || a2 == a3 || a2 == a4 || a3 == a4) return -1;
+    // rank of each quadrant in descending order (0 = largest)
+    const int r1 = (a2 > a1) + (a3 > a1) + (a4 > a1);
+    const int r2 = (a1 > a2) + (a3 > a2) + (a4 > a2);
+    const int r3 = (a1 > a3) + (a2 > a3) + (a4 > a3);
+    const int r4 = (a1 > a4) + (a2 > a4) + (a3 > a4);
+    // descending order as digits: ord[rank] = quadrant id (1..4)
+    int ord[4];
+    ord[r1] = 1;
+    ord[r2] = 2;
+    ord[r3] = 3;
+    ord[r4] = 4;
+    const int code = ord[0] * 1000 + ord[1] * 100 + ord[2] * 10 + ord[3];
+    switch (code) {
+    case 1234: case 3142: case 4321: case 2413: return 0;
+    case 1324: case 2143: case 4231: case 3412: return 1;
+    case 1432: case 4123: case 3241: case 2314: return 2;
+    case 1243: case 3124: case 4312: case 2431: return 3;
+    case 2134: case 1342: case 3421: case 4213: return 4;
+    case 1423: case 2341: case 3214: return 5;
+    // 4132 (a4 > a1 > a3 > a2) has no row: the reference's fourth class-5 test reads
+    // `a4a1 && a1a3 && a3a4` (Classifier2.cpp:48), which can never hold, so that ordering is -1.
+    }
+    return -1;
+}
+
+__device__ __forceinline__ uint32_t block_sum_dev(const uint8_t* __restrict__ img, uint32_t stride, uint32_t x, uint32_t y,
+                                                  uint32_t w, uint32_t h) {
+    uint32_t s = 0;
+    for (uint32_t j = 0; j < h; ++j) {
+        const uint8_t* row = img + (size_t)(y + j) * stride + x;
+        for (uint32_t i = 0; i < w; ++i) s += row[i];
+    }
+    if (w <= 16) s &= 0xFFFFu; // ImageStatistics2::sum -> sum_u16 (uint16_t) for widths <= 16
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grids (image/partition2.hpp:110-135) and quadtree children (partition2.hpp:18-30)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_uniform_grid(fe_grid_item* out, uint32_t nx, uint32_t n, uint32_t size, uint32_t step) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe_grid_item it;
+    it.x = (i % nx) * step;
+    it.y = (i / nx) * step;
+    it.w = size;
+    it.h = size;
+    it.bin = -1;
+    out[i] = it;
+}
+
+// After an exclusive scan of the split flags: children of split block i go to next[4*scan[i] ..+3]
+// (topLeft, topRight, bottomLeft, bottomRight); kept blocks are copied to items_out[out_base + (i - scan[i])].
+__global__ void k_quadtree_scatter(const fe_grid_item* __restrict__ rng, const fe_encode_item* __restrict__ level_items,
+                                   const uint32_t* __restrict__ split, const uint32_t* __restrict__ scan, uint32_t n,
+                                   fe_grid_item* __restrict__ next, fe_encode_item* __restrict__ items_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = scan[i];
+    if (split[i]) {
+        const fe_grid_item r = rng[i];
+        const uint32_t h = r.w / 2;
+        fe_grid_item c;
+        c.w = h;
+        c.h = h;
+        c.bin = -1;
+        c.x = r.x; c.y = r.y; next[4 * s + 0] = c;
+        c.x = r.x + h; c.y = r.y; next[4 * s + 1] = c;
+        c.x = r.x; c.y = r.y + h; next[4 * s + 2] = c;
+        c.x = r.x + h; c.y = r.y + h; next[4 * s + 3] = c;
+    } else {
+        items_out[i - s] = level_items[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// classification
+// ---------------------------------------------------------------------------------------------
+// One warp per item: quadrant sums by lane-strided rows; class kept as given when bin != -1
+// (Classifier2::compare only recomputes for -1, Classifier2.cpp:70-81).
+__global__ void k_classify(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ items, uint32_t n,
+                           int32_t* __restrict__ cls, int force) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const fe_grid_item it = items[warp];
+    if (!force && it.bin != -1) {
+        if (lane == 0) cls[warp] = it.bin;
+        return;
+    }
+    const uint32_t hw = it.w / 2, hh = it.h / 2;
+    uint32_t a[4] = {0, 0, 0, 0};
+    // quadrant q pixel p: lanes stride over the hw*hh pixels of each quadrant
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t qx = it.x + (q & 1) * hw, qy = it.y + (q >> 1) * hh;
+        uint32_t s = 0;
+        for (uint32_t p = lane; p < hw * hh; p += 32) s += img[(size_t)(qy + p / hw) * stride + qx + p % hw];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        if (hw <= 16) s &= 0xFFFFu;
+        a[q] = s;
+    }
+    if (lane == 0) cls[warp] = category4(a[0], a[1], a[2], a[3]);
+}
+
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_iota(uint32_t* p, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+// sort key = class + 1 (0..6), histogram of keys
+__global__ void k_class_keys(const int32_t* __restrict__ cls, uint32_t n, uint8_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cls[i] + 1;
+    keys[i] = (uint8_t)c;
+    atomicAdd(&hist[c], 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------
+// Range rows.  One warp per range position j (range index order[j]).  Writes the four rows
+// 4j+k: fast geometry -> the range block under the INVERSE of rotation k (so that one unrotated
+// domain pool serves all four isometries); generic geometry -> four copies of the block.
+// Also rowc[j] = 16*sum(r^2).  Optionally the fp16 rows of the tcgen05 path (A16, see fe_search_umma.cu).
+__global__ void k_build_rows(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
+                             const uint32_t* __restrict__ order, uint32_t n, uint32_t T, uint32_t Npad, int fast,
+                             uint8_t* __restrict__ A, uint32_t* __restrict__ rowc) {
+    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= n) return;
+    const fe_grid_item r = rng[order ? order[j] : j];
+    const uint32_t N = T * T;
+    uint8_t* row = A + (size_t)j * 4 * Npad;
+    uint32_t s2 = 0;
+    for (uint32_t e = lane; e < Npad; e += 32) {
+        uint8_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        if (e < N) {
+            const uint32_t Y = e / T, X = e % T;
+            const uint8_t* base = img + (size_t)r.y * stride + r.x;
+            v0 = base[(size_t)Y * stride + X];
+            s2 += (uint32_t)v0 * v0;
+            if (fast) {
+                v1 = base[(size_t)X * stride + (T - 1 - Y)];           // A_1[Y][X] = R[X][T-1-Y]
+                v2 = base[(size_t)(T - 1 - Y) * stride + (T - 1 - X)]; // A_2[Y][X] = R[T-1-Y][T-1-X]
+                v3 = base[(size_t)(T - 1 - X) * stride + Y];           // A_3[Y][X] = R[T-1-X][Y]
+            } else {
+                v1 = v2 = v3 = v0;
+            }
+        }
+        row[e] = v0;
+        row[Npad + e] = v1;
+        row[2 * Npad + e] = v2;
+        row[3 * Npad + e] = v3;
+    }
+    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+    if (lane == 0) rowc[j] = 16u * s2;
+}
+
+// Domain pool.  One warp per (pool k, column c): D[ty][tx] = box sum at local (rho*tx, rho*ty) under
+// isometry k (k = 0 only in the fast geometry).  Split into low/high bytes for the dp4a search;
+// coln = sum(D^2).
+__global__ void k_build_pool(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ dom,
+                             const uint32_t* __restrict__ order, uint32_t n, uint32_t npool, uint32_t T, uint32_t rho,
+                             uint32_t Npad, uint8_t* __restrict__ Blo, uint8_t* __restrict__ Bhi, uint32_t* __restrict__ coln) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n * npool) return;
+    const uint32_t k = w / n, c = w % n;
+    const fe_grid_item d = dom[order ? order[c] : c];
+    const uint32_t N = T * T;
+    uint8_t* lo = Blo + (size_t)w * Npad;
+    uint8_t* hi = Bhi + (size_t)w * Npad;
+    uint32_t s2 = 0;
+    for (uint32_t e = lane; e < Npad; e += 32) {
+        uint32_t D = 0;
+        if (e < N) D = (uint32_t)sample_sum4(img, stride, d.x, d.y, d.w, (e % T) * rho, (e / T) * rho, (int)k);
+        lo[e] = (uint8_t)(D & 255u);
+        hi[e] = (uint8_t)(D >> 8);
+        s2 += D * D;
+    }
+    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+    if (lane == 0) coln[w] = s2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact integer search (CUDA cores, dp4a): n16[row][col] = rowc - 8*sum(r*D) + coln, exact in u32
+// for T <= 64.  Per row: packed-key argmin (n16 << 32 | col) and first col with n16 <= thr16.
+// Tile 128 rows x 64 cols per CTA, 256 threads, 8x4 outputs per thread, K in chunks of 16 words.
+// ---------------------------------------------------------------------------------------------
+#define SX_TM 128
+#define SX_TN 64
+#define SX_KW 16
+#define SX_APAD 132
+
+__global__ void __launch_bounds__(256) k_search_exact(SearchArgs a) {
+    __shared__ __align__(16) uint32_t As[SX_KW][SX_APAD];
+    __shared__ __align__(16) uint32_t Bl[SX_KW][SX_TN];
+    __shared__ __align__(16) uint32_t Bh[SX_KW][SX_TN];
+    const uint32_t tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const uint32_t nw = a.Npad / 4;
+    // a tile never mixes rotations' pools in the generic geometry: blockIdx.y = pool
+    const uint32_t pool = blockIdx.y;
+    const uint32_t row_base = a.row0 + blockIdx.x * SX_TM;
+    const uint32_t rows_here = min((uint32_t)SX_TM, a.row0 + a.nrows - row_base);
+    const uint8_t* Blo = a.Blo + (size_t)pool * a.pool_stride_cols * a.Npad;
+    const uint8_t* Bhi = a.Bhi + (size_t)pool * a.pool_stride_cols * a.Npad;
+    const uint32_t* coln = a.coln + (size_t)pool * a.pool_stride_cols;
+
+    unsigned long long best[8];
+    uint32_t hit[8], rc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        best[i] = FE_INF64;
+        hit[i] = FE_NONE32;
+        const uint32_t r = row_base + ty * 8 + i;
+        rc[i] = (ty * 8 + i < rows_here) ? a.rowc[r >> 2] : 0u;
+    }
+
+    for (uint32_t ct = 0; ct < a.ncols; ct += SX_TN) {
+        uint32_t lo[8][4], hi[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) lo[i][j] = hi[i][j] = 0;
+        for (uint32_t w0 = 0; w0 < nw; w0 += SX_KW) {
+            const uint32_t kw = min((uint32_t)SX_KW, nw - w0);
+            __syncthreads();
+            // A chunk: rows_here x kw words, transposed into As[w][row]
+            for (uint32_t idx = tid; idx < SX_TM * kw; idx += 256) {
+                const uint32_t r = idx / kw, w = idx % kw;
+                uint32_t v = 0;
+                if (r < rows_here) v = *reinterpret_cast<const uint32_t*>(a.A + (size_t)(row_base + r) * a.Npad + (size_t)(w0 + w) * 4);
+                As[w][r] = v;
+            }
+            for (uint32_t idx = tid; idx < SX_TN * kw; idx += 256) {
+                const uint32_t c = idx / kw, w = idx % kw;
+                uint32_t vl = 0, vh = 0;
+                if (ct + c < a.ncols) {
+                    const size_t off = (size_t)(a.col0 + ct + c) * a.Npad + (size_t)(w0 + w) * 4;
+                    vl = *reinterpret_cast<const uint32_t*>(Blo + off);
+                    vh = *reinterpret_cast<const uint32_t*>(Bhi + off);
+                }
+                Bl[w][c] = vl;
+                Bh[w][c] = vh;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (uint32_t w = 0; w < kw; ++w) {
+                const uint4 a0 = *reinterpret_cast<const uint4*>(&As[w][ty * 8]);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(&As[w][ty * 8 + 4]);
+                const uint4 bl = *reinterpret_cast<const uint4*>(&Bl[w][tx * 4]);
+                const uint4 bh = *reinterpret_cast<const uint4*>(&Bh[w][tx * 4]);
+                const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const uint32_t blv[4] = {bl.x, bl.y, bl.z, bl.w};
+                const uint32_t bhv[4] = {bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        lo[i][j] = __dp4a(av[i], blv[j], lo[i][j]);
+                        hi[i][j] = __dp4a(av[i], bhv[j], hi[i][j]);
+                    }
+            }
+        }
+        // epilogue of this column tile
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = ct + tx * 4 + j;
+            if (c < a.ncols) {
+                const uint32_t gc = a.col0 + c;
+                const uint32_t cn = coln[gc];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t cross = lo[i][j] + (hi[i][j] << 8);
+                    const uint32_t n16 = rc[i] - 8u * cross + cn;
+                    const unsigned long long key = ((unsigned long long)n16 << 32) | gc;
+                    best[i] = key < best[i] ? key : best[i];
+                    if (a.use_thr && n16 <= a.thr16) hit[i] = min(hit[i], gc);
+                }
+            }
+        }
+    }
+    // reduce across the 16 threads (tx) sharing the same rows: lanes differ in their low 4 bits
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 8; o; o >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(0xFFFFFFFFu, best[i], o);
+            const uint32_t oh = __shfl_xor_sync(0xFFFFFFFFu, hit[i], o);
+            best[i] = ob < best[i] ? ob : best[i];
+            hit[i] = min(hit[i], oh);
+        }
+        if (tx == 0 && ty * 8 + i < rows_here) {
+            // generic geometry: pool k only answers rows of rotation k
+            const uint32_t r = row_base + ty * 8 + i;
+            if (a.pool_stride_cols == 0 || (r & 3u) == pool) {
+                a.rowbest[r] = best[i];
+                a.rowhit[r] = hit[i];
+            }
+        }
+    }
+}
+
+cudaError_t launch_search_exact(fe_ctx* ctx, const SearchArgs& a) {
+    if (a.nrows == 0 || a.ncols == 0) return cudaSuccess;
+    dim3 grid((a.nrows + SX_TM - 1) / SX_TM, a.pool_stride_cols ? 4 : 1);
+    k_search_exact<<<grid, 256, 0, ctx->stream>>>(a);
+    ctx->stats.kernel_launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// winner finalisation: TransformEstimator2::estimate's net rule over the four
+// rotation rows of a range, then s/o for the winner only (transformmatcher.h:98-108).
+// One warp per range position j.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_finalize(FinalizeArgs f) {
+    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= f.n) return;
+    const uint32_t ri = f.rng_order ? f.rng_order[j] : j;
+    const fe_grid_item r = f.rng[ri];
+    // ---- pick the winner (identical on all lanes) ----
+    int wk = -1;
+    uint32_t wd = 0, wn16 = 0;
+    bool from_min = false;
+    if (f.use_thr) { // first candidate in scan order c = 4*d + k with distance <= threshold
+        unsigned long long bestscan = FE_INF64;
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t h = f.rowhit[4 * j + k];
+            if (h != FE_NONE32) {
+                const uint32_t d = f.dom_order ? f.dom_order[h] : h;
+                const unsigned long long scan = (unsigned long long)d * 4 + k;
+                if (scan < bestscan) bestscan = scan;
+            }
+        }
+        if (bestscan != FE_INF64) {
+            wk = (int)(bestscan & 3);
+            wd = (uint32_t)(bestscan >> 2);
+        }
+    }
+    if (wk < 0) { // minimum n16; ties -> smallest domain index, then LARGEST k
+        uint32_t bn = 0, bd = 0;
+        for (int k = 0; k < 4; ++k) {
+            const unsigned long long key = f.rowbest[4 * j + k];
+            if (key == FE_INF64) continue;
+            const uint32_t n16 = (uint32_t)(key >> 32), col = (uint32_t)key;
+            const uint32_t d = f.dom_order ? f.dom_order[col] : col;
+            if (wk < 0 || n16 < bn || (n16 == bn && d <= bd)) {
+                wk = k;
+                bn = n16;
+                bd = d;
+            }
+        }
+        wd = bd;
+        from_min = true;
+    }
+    fe_encode_item out;
+    out.x = r.x; out.y = r.y; out.w = r.w; out.h = r.h;
+    out.pad_ = 0;
+    if (wk < 0) { // no admissible candidate: default item_match_t (encode/datatypes.h:8-19)
+        out.distance = 100000.0; out.contrast = 0.0; out.brightness = 0.0; out.transform = 0;
+        out.match_x = 0; out.match_y = 0; out.src_w = 0; out.src_h = 0;
+        if (lane == 0) {
+            f.out[ri] = out;
+            if (f.split) f.split[ri] = (f.can_split && !(100000.0 <= f.thr)) ? 1u : 0u;
+        }
+        return;
+    }
+    const fe_grid_item dm = f.dom[wd];
+    // ---- exact sums for the winner ----
+    const uint32_t T = r.w, N = T * T, rho = dm.w / T;
+    uint32_t sA = 0, sA2 = 0, sB = 0, sAB = 0, sB2 = 0;
+    for (uint32_t e = lane; e < N; e += 32) {
+        const uint32_t ty = e / T, tx = e % T;
+        const uint32_t a = f.tgt[(size_t)(r.y + ty) * f.tgt_stride + r.x + tx];
+        const uint32_t D = (uint32_t)sample_sum4(f.src, f.src_stride, dm.x, dm.y, dm.w, tx * rho, ty * rho, wk);
+        sA += a; sA2 += a * a; sB += D; sAB += a * D; sB2 += D * D;
+    }
+    for (int o = 16; o; o >>= 1) {
+        sA += __shfl_xor_sync(0xFFFFFFFFu, sA, o);
+        sA2 += __shfl_xor_sync(0xFFFFFFFFu, sA2, o);
+        sB += __shfl_xor_sync(0xFFFFFFFFu, sB, o);
+        sAB += __shfl_xor_sync(0xFFFFFFFFu, sAB, o);
+        sB2 += __shfl_xor_sync(0xFFFFFFFFu, sB2, o);
+    }
+    wn16 = 16u * sA2 - 8u * sAB + sB2; // exact for T <= 64
+    if (lane != 0) return;
+    // self-check of the search kernel's arithmetic against the direct recomputation
+    if (from_min) {
+        const unsigned long long key = f.rowbest[4 * j + wk];
+        if ((uint32_t)(key >> 32) != wn16) atomicAdd(f.mismatch, 1u);
+    } else if (wn16 > f.thr16) {
+        atomicAdd(f.mismatch, 1u);
+    }
+    double distance;
+    if (wn16 < (1u << 24)) {
+        distance = ((double)wn16 / 16.0) / (double)(dm.w * dm.h);
+    } else { // reference fp32 running sum rounds (metrics.h:38-49): emulate it, row-major
+        float sum = 0.0f;
+        for (uint32_t ty = 0; ty < T; ++ty)
+            for (uint32_t tx = 0; tx < T; ++tx) {
+                const float a = (float)f.tgt[(size_t)(r.y + ty) * f.tgt_stride + r.x + tx];
+                const float d = (float)sample_sum4(f.src, f.src_stride, dm.x, dm.y, dm.w, tx * rho, ty * rho, wk) * 0.25f;
+                const float v = __fsub_rn(a, d);
+                sum = __fadd_rn(sum, __fmul_rn(v, v));
+            }
+        distance = (double)sum / (double)(dm.w * dm.h);
+        atomicAdd(f.fp32_regime, 1u);
+    }
+    // least squares exactly as transformmatcher.h:98-108 (A = range, B = decimated domain)
+    const double Nd = (double)N, sumA = (double)sA, sumA2 = (double)sA2;
+    const double sumB = (double)sB * 0.25, sumAB = (double)sAB * 0.25;
+    const double tmp = __dsub_rn(__dmul_rn(Nd, sumA2), __dmul_rn(sumA - 1.0, sumA));
+    double s = fabs(tmp) < 0.00001 ? 0.0 : __ddiv_rn(__dsub_rn(__dmul_rn(Nd, sumAB), __dmul_rn(sumA, sumB)), tmp);
+    if (f.s_max > 0.0) s = s > f.s_max ? f.s_max : (s < -f.s_max ? -f.s_max : s);
+    const double o = f.fma ? __ddiv_rn(__fma_rn(-s, sumA, sumB), Nd) : __ddiv_rn(__dsub_rn(sumB, __dmul_rn(s, sumA)), Nd);
+    out.distance = distance;
+    out.contrast = s;
+    out.brightness = o;
+    out.transform = wk;
+    out.match_x = dm.x; out.match_y = dm.y; out.src_w = dm.w; out.src_h = dm.h;
+    f.out[ri] = out;
+    if (f.split) f.split[ri] = (f.can_split && !(distance <= f.thr)) ? 1u : 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode (Frac::copy as a gather kernel) + convergence sum
+// ---------------------------------------------------------------------------------------------
+// One thread per target pixel of an item list with prefix offsets (pix_off[i] = first pixel id of item i).
+__global__ void k_decode_step(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t stride,
+                              const fe_encode_item* __restrict__ items, const uint32_t* __restrict__ pix_off, uint32_t n_items,
+                              uint32_t total_pix, int use_fma) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total_pix) return;
+    // binary search the owning item
+    uint32_t lo = 0, hi = n_items;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pix_off[mid] <= p) lo = mid; else hi = mid;
+    }
+    const fe_encode_item e = items[lo];
+    if (e.src_w == 0 || e.src_h == 0) return; // default item: nothing to sample (see oracle/frac_oracle.c)
+    const uint32_t q = p - pix_off[lo], x = q % e.w, y = q / e.w;
+    const uint32_t sx = (x * e.src_w) / e.w, sy = (y * e.src_h) / e.h;
+    const double smp = (double)sample_sum4(src, stride, e.match_x, e.match_y, e.src_w, sx, sy, e.transform) * 0.25;
+    const double v = use_fma ? __fma_rn(e.contrast, smp, e.brightness) : __dadd_rn(__dmul_rn(e.contrast, smp), e.brightness);
+    dst[(size_t)(e.y + y) * stride + e.x + x] = v < 0.0 ? 0 : (v > 255.0 ? 255 : (uint8_t)v);
+}
+
+// Uniform square items of size T (every item T x T): one thread per 4 horizontal pixels, no search.
+__global__ void k_decode_step_uniform(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t stride,
+                                      const fe_encode_item* __restrict__ items, uint32_t n_items, uint32_t T, int use_fma) {
+    const uint32_t segs = T / 4, per_item = T * segs;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items * per_item) return;
+    const uint32_t i = t / per_item, q = t % per_item, y = q / segs, x0 = (q % segs) * 4;
+    const fe_encode_item e = items[i];
+    if (e.src_w == 0 || e.src_h == 0) return;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = x0 + k;
+        const uint32_t sx = (x * e.src_w) / T, sy = (y * e.src_h) / T;
+        const double smp = (double)sample_sum4(src, stride, e.match_x, e.match_y, e.src_w, sx, sy, e.transform) * 0.25;
+        const double v = use_fma ? __fma_rn(e.contrast, smp, e.brightness) : __dadd_rn(__dmul_rn(e.contrast, smp), e.brightness);
+        const uint32_t b = v < 0.0 ? 0u : (v > 255.0 ? 255u : (uint32_t)(uint8_t)v);
+        packed |= b << (8 * k);
+    }
+    uint8_t* o = dst + (size_t)(e.y + y) * stride + e.x + x0;
+    if ((reinterpret_cast<uintptr_t>(o) & 3u) == 0) *reinterpret_cast<uint32_t*>(o) = packed;
+    else { o[0] = packed & 255; o[1] = (packed >> 8) & 255; o[2] = (packed >> 16) & 255; o[3] = packed >> 24; }
+}
+
+// sum over the plane of (a-b)^2 as uint64 (the reference accumulates in int32, metrics.h:27; the
+// host wraps the 64-bit sum to int32 to reproduce it).
+__global__ void k_sqdiff(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t w, uint32_t h, uint32_t stride,
+                         unsigned long long* __restrict__ out) {
+    unsigned long long s = 0;
+    const size_t n = (size_t)w * h;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t off = (i / w) * stride + (i % w);
+        const int d = (int)a[off] - (int)b[off];
+        s += (unsigned long long)(d * d);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    __shared__ unsigned long long ws[32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0ull;
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        if (threadIdx.x == 0) atomicAdd(out, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// quantizer (Quantizer.hpp:13-36) : min/max then quantized()
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dbl_key(double v) { // order-preserving map double -> u64
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void k_minmax(const fe_encode_item* __restrict__ items, uint32_t n, unsigned long long* __restrict__ mm) {
+    // mm[0]=min key s, mm[1]=max key s, mm[2]=min key o, mm[3]=max key o
+    unsigned long long mns = FE_INF64, mxs = 0, mno = FE_INF64, mxo = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long ks = dbl_key(items[i].contrast), ko = dbl_key(items[i].brightness);
+        mns = ks < mns ? ks : mns; mxs = ks > mxs ? ks : mxs;
+        mno = ko < mno ? ko : mno; mxo = ko > mxo ? ko : mxo;
+    }
+    for (int o = 16; o; o >>= 1) {
+        unsigned long long t;
+        t = __shfl_xor_sync(0xFFFFFFFFu, mns, o); mns = t < mns ? t : mns;
+        t = __shfl_xor_sync(0xFFFFFFFFu, mxs, o); mxs = t > mxs ? t : mxs;
+        t = __shfl_xor_sync(0xFFFFFFFFu, mno, o); mno = t < mno ? t : mno;
+        t = __shfl_xor_sync(0xFFFFFFFFu, mxo, o); mxo = t > mxo ? t : mxo;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[0], mns); atomicMax(&mm[1], mxs); atomicMin(&mm[2], mno); atomicMax(&mm[3], mxo);
+    }
+}
+__global__ void k_quantize(const fe_encode_item* __restrict__ items, uint32_t n, double min_s, double max_s, double min_o,
+                           double max_o, int bits_s, int bits_o, uint32_t* __restrict__ qs, uint32_t* __restrict__ qo) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double step_s = __ddiv_rn(fabs(__dsub_rn(max_s, min_s)), (double)(1 << bits_s));
+    const double step_o = __ddiv_rn(fabs(__dsub_rn(max_o, min_o)), (double)(1 << bits_o));
+    const unsigned long long mq_s = (1ull << bits_s) - 1, mq_o = (1ull << bits_o) - 1;
+    const unsigned long long a = (unsigned long long)floor(__ddiv_rn(__dsub_rn(items[i].contrast, min_s), step_s));
+    const unsigned long long b = (unsigned long long)floor(__ddiv_rn(__dsub_rn(items[i].brightness, min_o), step_o));
+    qs[i] = (uint32_t)(a < mq_s ? a : mq_s);
+    qo[i] = (uint32_t)(b < mq_o ? b : mq_o);
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthetic images: same integer formulas as oracle/frac_oracle.c:fo_synth_image
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint32_t lattice(unsigned long long seed, unsigned long long i, unsigned long long j, unsigned long long o) {
+    return (uint32_t)(splitmix64(seed ^ (o * 0xD6E8FEB86659FD93ull) ^ (i * 0x9E3779B97F4A7C15ull) ^ (j * 0xC2B2AE3D27D4EB4Full)) >> 56);
+}
+__global__ void k_synth(uint8_t* out, uint32_t w, uint32_t h, uint32_t stride, unsigned long long seed, int kind) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    uint32_t v;
+    if (kind == 2) {
+        v = (11u * x + 43u * y + 124u) % 256u;
+    } else if (kind == 1) {
+        v = (uint32_t)(splitmix64(seed ^ ((unsigned long long)x * 0x9E3779B97F4A7C15ull) ^ ((unsigned long long)y * 0xC2B2AE3D27D4EB4Full)) >> 56);
+    } else {
+        const uint32_t cell[4] = {64, 16, 4, 1}, wt[4] = {4, 2, 1, 1};
+        uint32_t acc = 0;
+        for (int o = 0; o < 4; ++o) {
+            const uint32_t c = cell[o], i = x / c, j = y / c, fx = x % c, fy = y % c;
+            const uint32_t vo = ((c - fx) * (c - fy) * lattice(seed, i, j, o) + fx * (c - fy) * lattice(seed, i + 1, j, o) +
+                                 (c - fx) * fy * lattice(seed, i, j + 1, o) + fx * fy * lattice(seed, i + 1, j + 1, o)) / (c * c);
+            acc += wt[o] * vo;
+        }
+        v = acc / 8;
+    }
+    out[(size_t)y * stride + x] = (uint8_t)v;
+}

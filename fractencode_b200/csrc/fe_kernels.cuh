@@ -1,0 +1,47 @@
+// fe_kernels.cuh -- kernel declarations shared by fe_kernels.cu and fe_api.cu.
+#pragma once
+#include "fe_internal.cuh"
+
+struct FinalizeArgs {
+    const uint8_t* src; uint32_t src_stride;
+    const uint8_t* tgt; uint32_t tgt_stride;
+    const fe_grid_item* dom;        // original (unsorted) domain list
+    const fe_grid_item* rng;        // original range list
+    const uint32_t* dom_order;      // column -> domain index (NULL: identity)
+    const uint32_t* rng_order;      // range position -> range index (NULL: identity)
+    const unsigned long long* rowbest;
+    const uint32_t* rowhit;
+    uint32_t n;                     // ranges
+    uint32_t use_thr;
+    double thr, s_max;
+    int fma;
+    int can_split;                  // quadtree: T > t_min
+    uint32_t thr16;
+    fe_encode_item* out;            // [range index]
+    uint32_t* split;                // NULL or per-range-index split flag
+    uint32_t* mismatch;             // device counter: search n16 != recomputed n16
+    uint32_t* fp32_regime;          // device counter: winners with SSE >= 2^20
+};
+
+__global__ void k_uniform_grid(fe_grid_item* out, uint32_t nx, uint32_t n, uint32_t size, uint32_t step);
+__global__ void k_quadtree_scatter(const fe_grid_item* rng, const fe_encode_item* level_items, const uint32_t* split,
+                                   const uint32_t* scan, uint32_t n, fe_grid_item* next, fe_encode_item* items_out);
+__global__ void k_classify(const uint8_t* img, uint32_t stride, const fe_grid_item* items, uint32_t n, int32_t* cls, int force);
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n);
+__global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n);
+__global__ void k_iota(uint32_t* p, uint32_t n);
+__global__ void k_class_keys(const int32_t* cls, uint32_t n, uint8_t* keys, uint32_t* hist);
+__global__ void k_build_rows(const uint8_t* img, uint32_t stride, const fe_grid_item* rng, const uint32_t* order, uint32_t n,
+                             uint32_t T, uint32_t Npad, int fast, uint8_t* A, uint32_t* rowc);
+__global__ void k_build_pool(const uint8_t* img, uint32_t stride, const fe_grid_item* dom, const uint32_t* order, uint32_t n,
+                             uint32_t npool, uint32_t T, uint32_t rho, uint32_t Npad, uint8_t* Blo, uint8_t* Bhi, uint32_t* coln);
+__global__ void k_finalize(FinalizeArgs f);
+__global__ void k_decode_step(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items,
+                              const uint32_t* pix_off, uint32_t n_items, uint32_t total_pix, int use_fma);
+__global__ void k_decode_step_uniform(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items,
+                                      uint32_t n_items, uint32_t T, int use_fma);
+__global__ void k_sqdiff(const uint8_t* a, const uint8_t* b, uint32_t w, uint32_t h, uint32_t stride, unsigned long long* out);
+__global__ void k_minmax(const fe_encode_item* items, uint32_t n, unsigned long long* mm);
+__global__ void k_quantize(const fe_encode_item* items, uint32_t n, double min_s, double max_s, double min_o, double max_o,
+                           int bits_s, int bits_o, uint32_t* qs, uint32_t* qo);
+__global__ void k_synth(uint8_t* out, uint32_t w, uint32_t h, uint32_t stride, unsigned long long seed, int kind);

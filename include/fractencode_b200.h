@@ -1,0 +1,176 @@
+/*
+ * fractencode_b200.h -- C ABI of the B200-native fractal-encoding search.
+ *
+ * This is the drop-in boundary for the reference's encode/ hot path
+ * (sebsgit/fractencode; file:line citations are into that repository).  A
+ * reference maintainer binds these entry points from a
+ * Frac2::AbstractEncodingEngine2 subclass (encode/EncodingEngine2.hpp:50-85;
+ * the slot left open at encode/EncodingEngine2.cpp:21-26) -- see INTEGRATION.md
+ * and fractencode_b200/host/ for that subclass.  Plain pointers and sizes only;
+ * no C++ or torch types cross this boundary; no exceptions; every function
+ * returns FE_OK (0) or a negative fe_status and records a message readable
+ * with fe_last_error().
+ *
+ * Threading: one fe_ctx per device and per host thread (the reference runs one
+ * thread per engine, encode/EncodingEngine2.hpp:126-155).  A ctx is not
+ * thread-safe.  All work is issued on the ctx's CUDA stream.
+ *
+ * There is NO CPU fallback: fe_create fails when no sm_100 device is present.
+ */
+#ifndef FRACTENCODE_B200_H
+#define FRACTENCODE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FE_ABI_VERSION 1
+
+typedef enum {
+    FE_OK = 0,
+    FE_ERR_INVALID = -1,     /* bad argument (null pointer, zero size, unaligned image ...) */
+    FE_ERR_UNSUPPORTED = -2, /* geometry outside the supported family (see fe_encode_level) */
+    FE_ERR_CUDA = -3,        /* CUDA runtime error; message holds cudaGetErrorString */
+    FE_ERR_NO_DEVICE = -4,   /* no sm_100 GPU: the product has no CPU path */
+    FE_ERR_CAPACITY = -5,    /* caller buffer too small */
+    FE_ERR_STATE = -6        /* call order (e.g. encode before fe_set_image) */
+} fe_status;
+
+/* Frac2::UniformGridItem = GridItemBase{origin,size} + GridItemData{bb_classifierBin}
+ * (image/partition2.hpp:13-16, 88-99): 20 bytes, same layout. */
+typedef struct {
+    uint32_t x, y, w, h;
+    int32_t bin; /* -1 = not classified; the engine classifies it like Classifier2::compare does */
+} fe_grid_item;
+
+/* Frac::encode_item_t (encode/datatypes.h:8-23): 64 bytes, same layout
+ * (x,y,w,h | transform_score_t{distance,contrast,brightness,transform} | match x,y | sourceItemSize). */
+typedef struct {
+    uint32_t x, y, w, h;
+    double distance, contrast, brightness;
+    int32_t transform; /* Frac::TransformType, image/transform.h:16-25 */
+    int32_t pad_;
+    uint32_t match_x, match_y;
+    uint32_t src_w, src_h;
+} fe_encode_item;
+
+/* Search engine selection (diagnostics / A-B parity; FE_SEARCH_AUTO in production). */
+typedef enum {
+    FE_SEARCH_AUTO = 0,  /* tcgen05 path where its exactness proof holds, exact integer path otherwise */
+    FE_SEARCH_EXACT = 1, /* CUDA-core integer (dp4a) search, any geometry */
+    FE_SEARCH_UMMA = 2   /* force the tcgen05/TMEM path; FE_ERR_UNSUPPORTED when not applicable */
+} fe_search_impl;
+
+/* Frac::encode_parameters_t (encode/encode_parameters.h:5-14) + TransformMatcher(rmsThreshold, sMax)
+ * (encode/transformmatcher.h:20-34) + the classifier choice of main.cpp:152-154. */
+typedef struct {
+    double rms_threshold; /* checkDistance: d <= rms_threshold; reference default 0 */
+    double s_max;         /* truncateSMax: clamp contrast to +-s_max when > 0; default -1 */
+    int32_t use_classifier; /* 0 = DummyClassifier, 1 = BrightnessBlocksClassifier2 */
+    int32_t fma;          /* 0: brightness = (sumB - s*sumA)/N with separate roundings (reference built
+                             without FMA); 1: fused, as GCC emits for the reference's -march=native
+                             build.  Same switch for decode's s*v+o. */
+    int32_t search_impl;  /* fe_search_impl */
+    int32_t reserved_;
+} fe_params;
+
+typedef struct {
+    uint64_t matches;          /* (range, domain, rotation) candidates evaluated = admissible pairs x 4 */
+    uint64_t kernel_launches;  /* kernels launched by this ctx since fe_stats_reset */
+    uint64_t fp32_regime_items;/* items whose best SSE >= 2^20 (reference fp32 sum rounds; distance emulated) */
+    uint64_t umma_levels;      /* levels searched on the tcgen05 path */
+    uint64_t exact_levels;     /* levels searched on the exact integer path */
+    uint64_t level_items[8];   /* last quadtree: items emitted per level */
+    uint64_t level_ranges[8];  /* last quadtree: range blocks searched per level */
+    uint64_t level_matches[8]; /* last quadtree: matches per level */
+    float level_search_ms[8];  /* last quadtree: search-kernel time per level (CUDA events on the ctx stream) */
+    float level_prep_ms[8];    /* last quadtree: pool/range prep + classify time per level */
+    float last_decode_ms;
+} fe_stats;
+
+typedef struct fe_ctx fe_ctx;
+
+/* Replaces: construction of an engine for EncodingEngineCore2's engine list
+ * (encode/EncodingEngine2.cpp:12-29).  `stream` is a cudaStream_t to issue on
+ * (e.g. the caller's current stream) or NULL for a ctx-owned stream. */
+int fe_create(fe_ctx** out, int device, void* stream);
+void fe_destroy(fe_ctx* ctx);
+const char* fe_last_error(const fe_ctx* ctx); /* ctx may be NULL: error of the last failed fe_create */
+int fe_abi_version(void);
+
+/* Replaces: the `const ImagePlane& sourceImage` the engine/estimator constructors
+ * capture (encode/EncodingEngine2.hpp:52-59, encode/TransformEstimator2.hpp:14-27).
+ * Host pixels are copied to the device; the caller keeps ownership.  `px` has
+ * height*stride bytes, stride >= width (image/Image2.hpp:84-111). */
+int fe_set_image(fe_ctx* ctx, const uint8_t* px, uint32_t width, uint32_t height, uint32_t stride);
+/* Separate source (domain) and target (range) planes, as TransformEstimator2's
+ * (sourceImage, targetImage) pair allows (tests/TransformEstimatorTest.cpp:13-47). */
+int fe_set_images(fe_ctx* ctx, const uint8_t* src_px, uint32_t src_w, uint32_t src_h, uint32_t src_stride,
+                  const uint8_t* tgt_px, uint32_t tgt_w, uint32_t tgt_h, uint32_t tgt_stride);
+/* Same, but `dev_px` already lives in this device's memory (copied device-to-device). */
+int fe_set_image_device(fe_ctx* ctx, const void* dev_px, uint32_t width, uint32_t height, uint32_t stride);
+
+/* Replaces: BrightnessBlocksClassifier2::preclassify / getCategory
+ * (encode/Classifier2.cpp:55-68) over a list.  which: 0 = source image, 1 = target image.
+ * bins_out[i] in {-1, 0..5}. */
+int fe_classify(fe_ctx* ctx, int which, const fe_grid_item* items, size_t n, int32_t* bins_out);
+
+/* Replaces: init() + encode(item) x n + finalize() of an AbstractEncodingEngine2
+ * (encode/EncodingEngine2.hpp:63-72,100-109), i.e. TransformEstimator2::estimate
+ * (encode/TransformEstimator2.hpp:29-48) for every range item against the domain
+ * list in list order.  out[i] corresponds to ranges[i].
+ * Supported family: all domains one square size S, all ranges one square size T,
+ * S a multiple of T, S > T, T <= 64, blocks inside their image.  The tcgen05 path
+ * additionally needs S == 2T and even domain origins (true for createUniformGrid
+ * lattices with step S/2, main.cpp:145-162); other geometries (e.g. the
+ * reference's default 16->4) run on the exact integer path. */
+int fe_encode_level(fe_ctx* ctx, const fe_grid_item* domains, size_t n_domains,
+                    const fe_grid_item* ranges, size_t n_ranges, const fe_params* params,
+                    fe_encode_item* out);
+
+/* Quadtree partition (image/partition2.hpp:18-30 children + transformmatcher.h:32-34
+ * checkDistance; the reference parses --quadtree but never implements it).
+ * Level T (t_max, t_max/2, ..., t_min): domains = createUniformGrid(size 2T, step T),
+ * a block is emitted when checkDistance(best) or T == t_min, else replaced by its
+ * topLeft, topRight, bottomLeft, bottomRight children.  Items are written level by
+ * level, in pending-list order.  level_counts (may be NULL) gets items per level. */
+int fe_encode_quadtree(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params,
+                       fe_encode_item* out, size_t cap, size_t* n_out, size_t* level_counts);
+/* Same search, results left in device memory (for device-resident pipelines and
+ * kernel-only timing); fetch with fe_fetch_items. */
+int fe_encode_quadtree_device(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params,
+                              size_t* n_out);
+int fe_fetch_items(fe_ctx* ctx, fe_encode_item* out, size_t cap, size_t* n_out);
+/* Device pointer to the last result list (n items of 64 bytes), valid until the next encode. */
+const void* fe_device_items(const fe_ctx* ctx, size_t* n_out);
+
+/* Replaces: Decoder2::decode (encode/Encoder2.hpp:54-99) with Frac::copy
+ * (encode/DecodeUtils.hpp:9-25) as a gather kernel.  `target` (height*stride bytes)
+ * is in/out like Decoder2's ImagePlane&; the iteration source starts at 100.
+ * max_iters < 0 -> 300.  Returns Decoder2::decode_stats_t in *iterations / *rms. */
+int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uint8_t* target, uint32_t width,
+              uint32_t height, uint32_t stride, int max_iters, double rms_eps, int fma,
+              int* iterations, double* rms);
+
+/* Replaces: the Quantizer post-pass of main.cpp:106-140 (encode/Quantizer.hpp:13-36):
+ * min/max over the list, then quantized(contrast) with bits_s bits and
+ * quantized(brightness) with bits_o bits.  minmax_out = {min_s, max_s, min_o, max_o}. */
+int fe_quantize(fe_ctx* ctx, const fe_encode_item* items, size_t n, int bits_s, int bits_o,
+                uint32_t* q_s_out, uint32_t* q_o_out, double minmax_out[4]);
+
+int fe_get_stats(const fe_ctx* ctx, fe_stats* out);
+int fe_stats_reset(fe_ctx* ctx);
+int fe_synchronize(fe_ctx* ctx);
+
+/* Synthetic inputs of the benchmark, generated on the device into
+ * the ctx's image: kind 0 natural, 1 noise, 2 pattern. */
+int fe_set_synthetic_image(fe_ctx* ctx, uint32_t width, uint32_t height, uint64_t seed, int kind);
+int fe_get_image(fe_ctx* ctx, uint8_t* out, uint32_t stride); /* copy the ctx's source image back */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRACTENCODE_B200_H */

@@ -238,7 +238,8 @@ size_t fr_encode_quadtree(const fo_plane* img, uint32_t t_max, uint32_t t_min, c
         return d;
     };
     std::vector<fo_grid_item> pending;
-    for (const auto& it : createUniformGrid(isz, Size32u(t_max, t_max), Size32u(t_max, t_max)).items())
+    const UniformGrid top = createUniformGrid(isz, Size32u(t_max, t_max), Size32u(t_max, t_max));
+    for (const auto& it : top.items())
         pending.push_back(fo_grid_item{it.origin.x(), it.origin.y(), it.size.x(), it.size.y(), -1});
     size_t n_out = 0;
     int level = 0;
