@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- fractal-encoding search throughput on N B200s of one node, or the reference CPU arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path over one synthetic image per GPU: the whole quadtree encode
+(BASELINE config 3: 4096x4096 "natural" image, quadtree 32->4, full search) -- operand preparation,
+the (range, domain x rotation) search on every level, winner finalisation with the least-squares
+(s, o), and the split/compaction between levels.  `value` times it with the image already in HBM and
+the transform list left in HBM (+ the NCCL gather of the per-rank lists for N > 1); `e2e` times the
+reference-facing C-ABI call with HOST buffers (pinned image in, transform list out).
+
+matches = sum over levels of (range blocks searched) x (domains) x 4 rotations: the FULL candidate
+count of the workload, identical for both arms, so matches/s ratios are time ratios.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "range_block_matches_per_s"
+UNIT = "matches/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--tmax", type=int, default=32)
+    ap.add_argument("--tmin", type=int, default=4)
+    ap.add_argument("--thr", type=float, default=float(os.environ.get("FE_BENCH_THR", "12")))
+    ap.add_argument("--classifier", type=int, default=0)
+    ap.add_argument("--search", type=int, default=0, help="0 auto, 1 exact integer path, 2 tcgen05 path")
+    ap.add_argument("--cpu-blocks", type=int, default=0, help="range blocks per level in the CPU sample (0: 2 x cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "natural %dx%d u8 (SURVEY 8d generator, seed 1234+rank), quadtree %d->%d, %s, rms_threshold %g" % (
+        a.size, a.size, a.tmax, a.tmin, "Classifier2" if a.classifier else "full search (DummyClassifier)", a.thr)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "tflops_burst": d.get("bf16_tflops", 1590.0),
+                "tflops_sustained": d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0)), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: the real reference (oracle/_ref) when it was compiled, else the oracle port.
+# Hierarchical bounded sample: m blocks of the top level against the FULL domain grid; the children of
+# the sampled blocks that split are the sample of the next level; per-level cost and split fraction are
+# scaled to the whole image.  Cost per block is independent of the other blocks.
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(a, img, blocks_per_level=0):
+    from oracle import pyoracle as po
+    lib, kind = po.reference(fma=False), "reference"
+    if lib is None:
+        lib, kind = po.restatement(), "port"
+    cores = lib.hardware_threads()
+    m = blocks_per_level or 2 * cores
+    W = H = a.size
+    p = lib.params(a.thr, -1.0, bool(a.classifier), False)
+    top = lib.uniform_grid(W, H, a.tmax, a.tmax)
+    sample = top[:: max(1, len(top) // m)][:m]
+    pending_est = float(len(top))
+    tot_time = tot_matches = 0.0
+    per_level = []
+    T = a.tmax
+    cpu_work = 0.0
+    while T >= a.tmin and len(sample):
+        dom = lib.uniform_grid(W, H, 2 * T, T)
+        if a.classifier:
+            dom, sample = lib.preclassify(img, dom), lib.preclassify(img, sample)
+        t0 = time.perf_counter()
+        out = lib.encode_level(img, img, dom, sample, p, 0, 1)
+        dt = time.perf_counter() - t0
+        cpu_work += dt
+        if a.classifier:
+            cand = float(np.mean([np.count_nonzero(dom["bin"] == b) for b in sample["bin"]])) * 4
+        else:
+            cand = len(dom) * 4.0
+        tot_time += pending_est * dt / len(sample)
+        tot_matches += pending_est * cand
+        split = (out["distance"] > a.thr) if T // 2 >= a.tmin else np.zeros(len(out), bool)
+        per_level.append({"T": T, "sampled": int(len(sample)), "sec": round(dt, 3), "split_frac": float(split.mean()),
+                          "pending_est": pending_est})
+        pending_est = pending_est * float(split.mean()) * 4
+        kids = []
+        for r in sample[split]:
+            h = T // 2
+            for dx, dy in ((0, 0), (h, 0), (0, h), (h, h)):
+                kids.append((r["x"] + dx, r["y"] + dy, h, h, -1))
+        sample = np.array(kids, po.GRID_ITEM) if kids else np.zeros(0, po.GRID_ITEM)
+        if len(sample) > m:
+            sample = sample[:: len(sample) // m][:m]
+        T //= 2
+    value = tot_matches / tot_time if tot_time > 0 else 0.0
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d range blocks per quadtree level vs the full domain grid, children of split sampled blocks feed the next level; "
+                      "scaled per level by (estimated pending blocks)/(sampled blocks); %.1f s of CPU wall on %d threads" % (m, cpu_work, cores),
+            "est_image_seconds": tot_time, "est_mpix_per_s": W * H / 1e6 / tot_time if tot_time > 0 else 0.0, "levels": per_level}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    po.build(ref=os.path.isdir("/root/reference/encode"))
+    fo = po.restatement()
+    img = fo.synth_image(a.size, a.size, 1234, 0)
+    res = []
+    for step in range(a.warmup + a.steps):
+        r = cpu_sample(a, img, a.cpu_blocks)
+        if step >= a.warmup:
+            res.append(r)
+    vals = [r["value"] for r in res]
+    v = float(np.mean(vals))
+    last = res[-1]
+    ms = float(np.mean([r["est_image_seconds"] for r in res])) * 1e3
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32 (CPU scalar+SSE)",
+            "data": "synthetic", "config": {"workload": workload_name(a), "note": "whole-image time extrapolated from a bounded sample; ms_per_step is that estimate"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "mpix_per_s": last["est_mpix_per_s"], "levels": last["levels"], "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+class DevArray:
+    """__cuda_array_interface__ view of a raw device pointer (the library's result list)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def run_b200(a):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import fractencode_b200 as fb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not os.path.exists(fb.library_path()):
+        raise SystemExit("libfractencode_b200.so missing: run __graft_entry__.build() (no fallback path exists)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    ctx = fb.Context(local, stream.cuda_stream)
+    lib = ctx.lib
+    W = H = a.size
+    params = fb.Params(a.thr, -1.0, bool(a.classifier), False, a.search)
+    cap = (W // a.tmin) * (H // a.tmin)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    host_img = torch.empty((H, W), dtype=torch.uint8).pin_memory()
+    host_items = torch.empty(cap * 64, dtype=torch.uint8).pin_memory()
+    counts_t = torch.zeros(world, dtype=torch.int64, device="cuda")
+    gather_buf = torch.empty(world * cap * 64, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    ctx.set_synthetic_image(W, H, 1234 + rank, 0)
+    host_img.copy_(torch.from_numpy(ctx.get_image()))
+
+    def step_resident():
+        n = ctx.encode_quadtree_device(a.tmax, a.tmin, params)
+        if world > 1:  # gather the per-rank transform lists (the only collective of the path)
+            mine = torch.tensor([n], dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(counts_t, mine)
+            nptr = C.c_size_t(0)
+            ptr = lib.fe_device_items(ctx.h, C.byref(nptr))
+            items = torch.as_tensor(DevArray(ptr, cap * 64), device="cuda")
+            dist.all_gather_into_tensor(gather_buf, items)
+        return n
+
+    def step_e2e():
+        ctx.set_image(host_img.numpy())  # pinned host -> device on the ctx stream
+        n = C.c_size_t(0)
+        rc = lib.fe_encode_quadtree(ctx.h, a.tmax, a.tmin, C.byref(params), host_items.data_ptr(), cap, C.byref(n), None)
+        if rc != 0:
+            raise fb.FractencodeError(rc, lib.fe_last_error(ctx.h).decode())
+        return n.value
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps):
+        times = []
+        n = 0
+        for _ in range(steps):
+            flush.fill_(1)  # evict L2 between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            n = fn()
+            e1.record(stream)
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        return times, n
+
+    for _ in range(a.warmup):
+        step_resident()
+    sync_all()
+    ctx.stats_reset()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    times, n_items = timed(step_resident, a.steps)
+    sync_all()
+    wall = time.perf_counter() - t_wall0
+    sampler.stop_flag = True
+    st = ctx.stats()
+    launches = int(st.kernel_launches)
+    matches_step = sum(int(x) for x in st.level_matches)
+    nlev = int(np.log2(a.tmax // a.tmin)) + 1
+    levels = []
+    flops = 0.0
+    search_ms = 0.0
+    for l in range(nlev):
+        T = a.tmax >> l
+        lm, ms = int(st.level_matches[l]), float(st.level_search_ms[l])
+        lf = 2.0 * T * T * lm
+        flops += lf
+        search_ms += ms
+        levels.append({"T": T, "ranges": int(st.level_ranges[l]), "items": int(st.level_items[l]), "matches": lm, "search_ms": round(ms, 3),
+                       "prep_ms": round(float(st.level_prep_ms[l]), 3), "tflops": round(lf / (ms * 1e-3) / 1e12, 2) if ms > 0 else None})
+    # e2e through the C ABI with host buffers
+    for _ in range(max(1, a.warmup // 2)):
+        step_e2e()
+    sync_all()
+    e_times, e_items = timed(step_e2e, a.steps)
+    sync_all()
+
+    my = torch.tensor([sum(times), sum(e_times), float(matches_step), float(n_items)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = my.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = my.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tot_ms, e_ms, all_matches, all_items = tmax[0].item(), tmax[1].item(), tsum[2].item(), tsum[3].item()
+    else:
+        tot_ms, e_ms, all_matches, all_items = my[0].item(), my[1].item(), my[2].item(), my[3].item()
+    if rank == 0:
+        pk = peaks()
+        ms_per_step = tot_ms / a.steps
+        value = all_matches / (ms_per_step * 1e-3)
+        e_value = all_matches / (e_ms / a.steps * 1e-3)
+        ach = flops / (search_ms * 1e-3) / 1e12 if search_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 in, fp16 operands / fp32 (integer-exact) accumulate, int32 scores, f64 s/o",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "images_per_step": world, "l2": "flushed between timed steps (512 MiB fill)",
+                       "search_impl": ["auto", "exact-int (dp4a)", "tcgen05"][a.search]},
+            "mpix_per_s": world * W * H / 1e6 / (ms_per_step * 1e-3),
+            "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": W * H, "d2h_bytes_per_step": int(e_items) * 64,
+                    "ms_per_step": e_ms / a.steps, "mpix_per_s": world * W * H / 1e6 / (e_ms / a.steps * 1e-3)},
+            "gpu_launches": launches,
+            "items_per_step": all_items,
+            "levels": levels,
+            "umma_levels": int(st.umma_levels), "exact_levels": int(st.exact_levels),
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": ach / pk["tflops_sustained"], "traffic": None,
+                         "kernel": "search (all levels, rank 0): 2*T^2 FLOP per match / summed CUDA-event search time; peak = sustained bf16, " + pk["source"]},
+            "clocks": sampler.summary(),
+            "wall_s_timed_region": wall,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            from oracle import pyoracle as po
+            po.build(ref=os.path.isdir("/root/reference/encode"))
+            cb = cpu_sample(a, host_img.numpy(), a.cpu_blocks)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["est_mpix_per_s"] = cb["est_mpix_per_s"]
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

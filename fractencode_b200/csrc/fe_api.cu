@@ -10,6 +10,7 @@
 #include <utility>
 
 #include "fe_kernels.cuh"
+#include "fe_umma.cuh"
 
 static std::string g_create_error;
 
@@ -259,50 +260,69 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
         nbuckets = 7;
     }
 
-    // ---- operands ----
-    const uint32_t npool = g.fast ? 1u : 4u;
-    FE_CUDA(ctx, ctx->b_A.ensure((size_t)nR * 4 * g.Npad));
-    FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)nR * 4));
-    FE_CUDA(ctx, ctx->b_rowbest.ensure((size_t)nR * 4 * 8));
-    FE_CUDA(ctx, ctx->b_rowhit.ensure((size_t)nR * 4 * 4));
-    LAUNCH(ctx, k_build_rows, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, rng_order, nR, g.T, g.Npad,
-           g.fast ? 1 : 0, ctx->b_A.as<uint8_t>(), ctx->b_rowc.as<uint32_t>());
-    if (nD) {
-        FE_CUDA(ctx, ctx->b_Blo.ensure((size_t)nD * npool * g.Npad));
-        FE_CUDA(ctx, ctx->b_Bhi.ensure((size_t)nD * npool * g.Npad));
-        FE_CUDA(ctx, ctx->b_coln.ensure((size_t)nD * npool * 4));
-        LAUNCH(ctx, k_build_pool, cdiv((uint64_t)nD * npool * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, dom_order, nD, npool,
-               g.T, g.rho, g.Npad, ctx->b_Blo.as<uint8_t>(), ctx->b_Bhi.as<uint8_t>(), ctx->b_coln.as<uint32_t>());
-    }
-    LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
-    LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
-    if (timed) cudaEventRecord(ctx->ev[1], ctx->stream);
-
-    // ---- search, one launch per classifier bucket ----
     uint32_t thr16 = 0;
     const bool use_thr = threshold_n16(p.rms_threshold, g.S, &thr16);
     uint64_t matches = 0;
-    for (int c = 0; c < nbuckets; ++c) {
-        const uint32_t rc = roff[c + 1] - roff[c], dc = doff[c + 1] - doff[c];
-        if (!rc || !dc) continue;
-        SearchArgs a{};
-        a.A = ctx->b_A.as<uint8_t>();
-        a.Blo = ctx->b_Blo.as<uint8_t>();
-        a.Bhi = ctx->b_Bhi.as<uint8_t>();
-        a.rowc = ctx->b_rowc.as<uint32_t>();
-        a.coln = ctx->b_coln.as<uint32_t>();
-        a.rowbest = ctx->b_rowbest.as<unsigned long long>();
-        a.rowhit = ctx->b_rowhit.as<uint32_t>();
-        a.row0 = roff[c] * 4; a.nrows = rc * 4;
-        a.col0 = doff[c]; a.ncols = dc;
-        a.Npad = g.Npad;
-        a.pool_stride_cols = g.fast ? 0 : nD;
-        a.thr16 = thr16;
-        a.use_thr = use_thr ? 1u : 0u;
-        FE_CUDA(ctx, launch_search_exact(ctx, a));
-        matches += (uint64_t)rc * dc * 4;
+    for (int c = 0; c < nbuckets; ++c) matches += (uint64_t)(roff[c + 1] - roff[c]) * (doff[c + 1] - doff[c]) * 4;
+    FE_CUDA(ctx, ctx->b_rowbest.ensure((size_t)nR * 4 * 8));
+    FE_CUDA(ctx, ctx->b_rowhit.ensure((size_t)nR * 4 * 4));
+    FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)nR * 4));
+
+    bool use_umma = p.search_impl != FE_SEARCH_EXACT && nD && umma_level_supported(g);
+    if (p.search_impl == FE_SEARCH_UMMA && nD && !umma_level_supported(g))
+        return fe_fail(ctx, FE_ERR_UNSUPPORTED, "tcgen05 path needs S == 2T, even domain origins and T in {4, 8} (got S=%u T=%u)", g.S, g.T);
+    bool searched = false;
+    if (use_umma) {
+        // ---- tcgen05 path: fp16 operand blobs + fused contraction/argmin ----
+        LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
+        LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
+        bool inexact = false;
+        FE_TRY(umma_prepare_and_search(ctx, g, io.d_dom, io.d_rng, dom_order, rng_order, doff, roff, nbuckets, thr16, use_thr, &inexact,
+                                       timed ? ctx->ev[1] : nullptr));
+        if (!inexact) {
+            searched = true;
+            ctx->stats.umma_levels++;
+        } else if (p.search_impl == FE_SEARCH_UMMA) {
+            return fe_fail(ctx, FE_ERR_UNSUPPORTED, "tcgen05 path: a winner lies in the fp32-inexact band (V >= 2^24 - 64); use FE_SEARCH_AUTO");
+        }
     }
-    ctx->stats.exact_levels++;
+    if (!searched) {
+        // ---- exact integer path: u8 rows, low/high byte pools, dp4a ----
+        const uint32_t npool = g.fast ? 1u : 4u;
+        FE_CUDA(ctx, ctx->b_A.ensure((size_t)nR * 4 * g.Npad));
+        LAUNCH(ctx, k_build_rows, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, rng_order, nR, g.T, g.Npad,
+               g.fast ? 1 : 0, ctx->b_A.as<uint8_t>(), ctx->b_rowc.as<uint32_t>());
+        if (nD) {
+            FE_CUDA(ctx, ctx->b_Blo.ensure((size_t)nD * npool * g.Npad));
+            FE_CUDA(ctx, ctx->b_Bhi.ensure((size_t)nD * npool * g.Npad));
+            FE_CUDA(ctx, ctx->b_coln.ensure((size_t)nD * npool * 4));
+            LAUNCH(ctx, k_build_pool, cdiv((uint64_t)nD * npool * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, dom_order, nD, npool,
+                   g.T, g.rho, g.Npad, ctx->b_Blo.as<uint8_t>(), ctx->b_Bhi.as<uint8_t>(), ctx->b_coln.as<uint32_t>());
+        }
+        LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
+        LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
+        if (timed) cudaEventRecord(ctx->ev[1], ctx->stream);
+        for (int c = 0; c < nbuckets; ++c) {
+            const uint32_t rc = roff[c + 1] - roff[c], dc = doff[c + 1] - doff[c];
+            if (!rc || !dc) continue;
+            SearchArgs a{};
+            a.A = ctx->b_A.as<uint8_t>();
+            a.Blo = ctx->b_Blo.as<uint8_t>();
+            a.Bhi = ctx->b_Bhi.as<uint8_t>();
+            a.rowc = ctx->b_rowc.as<uint32_t>();
+            a.coln = ctx->b_coln.as<uint32_t>();
+            a.rowbest = ctx->b_rowbest.as<unsigned long long>();
+            a.rowhit = ctx->b_rowhit.as<uint32_t>();
+            a.row0 = roff[c] * 4; a.nrows = rc * 4;
+            a.col0 = doff[c]; a.ncols = dc;
+            a.Npad = g.Npad;
+            a.pool_stride_cols = g.fast ? 0 : nD;
+            a.thr16 = thr16;
+            a.use_thr = use_thr ? 1u : 0u;
+            FE_CUDA(ctx, launch_search_exact(ctx, a));
+        }
+        ctx->stats.exact_levels++;
+    }
     ctx->stats.matches += matches;
     if (timed) cudaEventRecord(ctx->ev[2], ctx->stream);
 

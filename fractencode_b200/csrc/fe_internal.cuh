@@ -103,4 +103,3 @@ int fe_fail(fe_ctx* ctx, int code, const char* fmt, ...);
 cudaError_t launch_search_exact(fe_ctx* ctx, const SearchArgs& a);
 // tcgen05 path (fe_search_umma.cu). Returns FE_OK / FE_ERR_*.
 int umma_level_supported(const LevelGeom& g);
-int launch_search_umma(fe_ctx* ctx, const LevelGeom& g, const SearchArgs& a, const void* A16, const void* B16);

@@ -1,7 +1,522 @@
-// fe_search_umma.cu -- tcgen05/TMEM contraction path (placeholder until the kernel lands).
-#include "fe_internal.cuh"
+// fe_search_umma.cu -- the (range x rotation) x domain cross-correlation as a grouped dense
+// contraction on tcgen05 tensor cores with TMEM accumulators, fused with the argmin epilogue.
+// sm_100a only (tcgen05.mma / tcgen05.ld / cp.async.bulk / mbarrier, hand-written PTX).
+//
+// Formulation (fast geometry S = 2T):
+//   a = 4 r - 510   (range pixel, inverse-rotated per row)        |a| <= 510
+//   b = D   - 510   (domain 2x2 box sum)                          |b| <= 510
+//   n16 = sum (a - b)^2 = sum a^2 + 2 V + p,   V = h - sum a b,   sum b^2 = 2 h + p,  p in {0,1}
+// For a fixed row, argmin n16 == argmin (V, p, column).  The MMA computes V directly:
+//   A row  = [ -a_0 .. -a_{N-1} | 1 | 2048 | 2048 | 0 .. ]          (fp16, all exact integers <= 2048)
+//   B col  = [  b_0 ..  b_{N-1} | h0 | h1 | 2048*h2 | 0 .. ]        h = h0 + 2048 h1 + 2048^2 h2
+// so the fp32 accumulator holds the INTEGER V.  Exactness: every product and every partial sum is an
+// integer of magnitude < 2^24 whenever the final V is (|sum a b| <= N * 510^2 <= 16,646,400 for
+// N <= 64), hence exact in fp32.  A winner with V >= 2^24 - 64 raises `inexact` and the host reruns
+// the level on the exact integer kernel (only pathological images: best match worse than ~180 grey
+// levels rms).  tests/test_gpu_umma.py holds the max-magnitude known-answer test.
+//
+// Kernel anatomy (one CTA per SM, persistent over work items = (row tile, column chunk)):
+//   warp 0     : bulk-async (TMA engine, cp.async.bulk) producer: A blob per work item, B blob per tile
+//   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer, 2 accumulators x 256 columns
+//   warps 2..9 : two epilogue warpgroups, one per accumulator: tcgen05.ld -> FMNMX3 row minimum;
+//                only when a tile can improve a row (or cross the threshold) is it re-read to find the column.
+// Operands are pre-laid-out in global memory in the no-swizzle K-major core-matrix order, one
+// contiguous blob per tile, so a stage is ONE bulk copy and needs no tensor map.
+#include <cuda_fp16.h>
 
-int umma_level_supported(const LevelGeom&) { return 0; }
-int launch_search_umma(fe_ctx* ctx, const LevelGeom&, const SearchArgs&, const void*, const void*) {
-    return fe_fail(ctx, FE_ERR_UNSUPPORTED, "tcgen05 search path not built");
+#include "fe_umma.cuh"
+
+namespace {
+
+constexpr uint32_t kStagesMaxBytes = 200 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU -- trap after ~2 s instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int KIND>  // 0: kind::f16, 1: kind::i8
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == 0) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// K-major, no swizzle: core matrices of 8 rows x 16 bytes; LBO = byte stride between the K chunks,
+// SBO = byte stride between 8-row groups (cute/atom/mma_traits_sm100.hpp, LayoutType::INTERLEAVE).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+    const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); // version = 1 (Blackwell), layout_type = 0
+    return ((uint64_t)hi << 32) | lo;
+}
+
+#define TMEM_LD32(taddr, v)                                                                                                   \
+    asm volatile(                                                                                                             \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                             \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                             \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                             \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),         \
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), \
+          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),             \
+          "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                        \
+        : "r"(taddr)                                                                                                          \
+        : "memory")
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float min32(const uint32_t (&v)[32], float m) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) m = fmin3(m, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+    return m;
+}
+
+struct WorkItem {
+    uint32_t a_blob;   // row-tile index (A blob)
+    uint32_t row0;     // first global row of the tile
+    uint32_t nrows;    // valid rows in the tile (<= 128)
+    uint32_t t0, t1;   // column-tile range [t0, t1)
+    uint32_t col0;     // global (sorted) column index of tile t0's first column
+    uint32_t cols_left;// valid columns from tile t0 to the end of the bucket
+};
+
+__device__ __forceinline__ WorkItem decode_item(const UmmaArgs& a, uint32_t w) {
+    WorkItem it{};
+    for (int bi = 0; bi < a.nb; ++bi) {
+        const UmmaBucket& b = a.b[bi];
+        const uint32_t items = b.n_row_tiles * b.chunks;
+        if (w < items) {
+            const uint32_t rt = w / b.chunks, q = w % b.chunks;
+            it.a_blob = b.row_tile0 + rt;
+            it.row0 = b.row0 + rt * UM_ROWS;
+            it.nrows = min((uint32_t)UM_ROWS, b.nrows - rt * UM_ROWS);
+            const uint32_t lt0 = (uint32_t)(((uint64_t)q * b.n_col_tiles) / b.chunks);
+            const uint32_t lt1 = (uint32_t)(((uint64_t)(q + 1) * b.n_col_tiles) / b.chunks);
+            it.t0 = b.col_tile0 + lt0;
+            it.t1 = b.col_tile0 + lt1;
+            it.col0 = b.col0 + lt0 * UM_NT;
+            it.cols_left = b.ncols - lt0 * UM_NT;
+            return it;
+        }
+        w -= items;
+    }
+    return it;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bytesA = UM_ROWS * a.Kpad * 2, bytesB = UM_NT * a.Kpad * 2;
+    const uint32_t S = a.stages;
+    uint8_t* sA = smem;                     // 2 buffers
+    uint8_t* sB = smem + 2 * bytesA;        // S stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)S * bytesB);
+    // barrier indices
+    const uint32_t bar0 = smem_u32(bars);
+    auto A_FULL = [&](uint32_t i) { return bar0 + 8 * (0 + i); };
+    auto A_EMPTY = [&](uint32_t i) { return bar0 + 8 * (2 + i); };
+    auto ACC_FULL = [&](uint32_t i) { return bar0 + 8 * (4 + i); };
+    auto ACC_EMPTY = [&](uint32_t i) { return bar0 + 8 * (6 + i); };
+    auto B_FULL = [&](uint32_t i) { return bar0 + 8 * (8 + i); };
+    auto B_EMPTY = [&](uint32_t i) { return bar0 + 8 * (8 + UM_MAX_STAGES + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * UM_MAX_STAGES);
+
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < 2; ++i) {
+            mbar_init(A_FULL(i), 1);
+            mbar_init(A_EMPTY(i), 1);
+            mbar_init(ACC_FULL(i), 1);
+            mbar_init(ACC_EMPTY(i), 4);
+        }
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(B_FULL(i), 1);
+            mbar_init(B_EMPTY(i), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= producer =================
+        if (lane == 0) {
+            uint32_t it = 0, wi = 0;
+            for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x, ++wi) {
+                const WorkItem item = decode_item(a, w);
+                const uint32_t ab = wi & 1;
+                mbar_wait(A_EMPTY(ab), ((wi >> 1) & 1) ^ 1);
+                mbar_expect_tx(A_FULL(ab), bytesA);
+                bulk_g2s(smem_u32(sA + ab * bytesA), reinterpret_cast<const uint8_t*>(a.A16) + (size_t)item.a_blob * bytesA, bytesA, A_FULL(ab));
+                for (uint32_t t = item.t0; t < item.t1; ++t, ++it) {
+                    const uint32_t s = it % S;
+                    mbar_wait(B_EMPTY(s), ((it / S) & 1) ^ 1);
+                    mbar_expect_tx(B_FULL(s), bytesB);
+                    bulk_g2s(smem_u32(sB + (size_t)s * bytesB), reinterpret_cast<const uint8_t*>(a.B16) + (size_t)t * bytesB, bytesB, B_FULL(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor: D = F32 (f16 kind) / S32 (i8 kind), A/B format 0 (F16 / U8), K-major both, N = 256, M = 128
+            const uint32_t idesc = ((KIND == 0 ? 1u : 2u) << 4) | ((uint32_t)(UM_NT >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
+            const uint32_t nk = a.Kpad / 16;  // K = 16 elements of 2 bytes per instruction = 2 core-matrix chunks
+            uint32_t it = 0, wi = 0;
+            for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x, ++wi) {
+                const WorkItem item = decode_item(a, w);
+                const uint32_t ab = wi & 1;
+                mbar_wait(A_FULL(ab), (wi >> 1) & 1);
+                const uint32_t a_addr = smem_u32(sA + ab * bytesA);
+                for (uint32_t t = item.t0; t < item.t1; ++t, ++it) {
+                    const uint32_t s = it % S, acc = it & 1;
+                    mbar_wait(ACC_EMPTY(acc), ((it >> 1) & 1) ^ 1);
+                    mbar_wait(B_FULL(s), (it / S) & 1);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(sB + (size_t)s * bytesB);
+                    for (uint32_t kk = 0; kk < nk; ++kk) {
+                        // chunk-major blobs: K chunk c (8 elements = 16 bytes) of all rows is contiguous
+                        const uint64_t adesc = make_desc(a_addr + kk * 2 * (UM_ROWS * 16), UM_ROWS * 16, 128);
+                        const uint64_t bdesc = make_desc(b_addr + kk * 2 * (UM_NT * 16), UM_NT * 16, 128);
+                        tc_mma<KIND>(tmem_base + acc * UM_NT, adesc, bdesc, idesc, kk > 0 ? 1u : 0u);
+                    }
+                    tc_commit(B_EMPTY(s));
+                    tc_commit(ACC_FULL(acc));
+                }
+                tc_commit(A_EMPTY(ab));
+            }
+        }
+    } else {
+        // ================= epilogue: warpgroup g drains accumulator g =================
+        const uint32_t g = (warp - 2) >> 2;
+        const uint32_t sp = warp & 3;                 // TMEM sub-partition this warp may read
+        const uint32_t lrow = sp * 32 + lane;         // row inside the tile == TMEM lane
+        const uint32_t taddr = tmem_base + ((sp * 32u) << 16) + g * UM_NT;
+        uint32_t it = 0;
+        for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x) {
+            const WorkItem item = decode_item(a, w);
+            const bool row_ok = lrow < item.nrows;
+            const uint32_t grow = item.row0 + lrow;
+            const uint32_t a2 = row_ok ? a.rowA2[grow >> 2] : 0u;
+            // n16 <= thr16  <=>  V <= floor((thr16 - a2 - p) / 2)
+            float vthr0 = -3.0e38f, vthr1 = -3.0e38f;
+            if (a.use_thr && row_ok) {
+                const long long tt = (long long)a.thr16 - (long long)a2;
+                long long f0 = tt >= 0 ? tt / 2 : -((-tt + 1) / 2);
+                long long f1 = (tt - 1) >= 0 ? (tt - 1) / 2 : -((-(tt - 1) + 1) / 2);
+                f0 = max(-16777216ll, min(16777215ll, f0));
+                f1 = max(-16777216ll, min(16777215ll, f1));
+                vthr0 = (float)f0;
+                vthr1 = (float)f1;
+            }
+            float bestV = 3.0e38f;
+            uint32_t bestp = 0, bestcol = FE_NONE32, hit = FE_NONE32;
+            const uint32_t n = item.t1 - item.t0;
+            for (uint32_t u = 0; u < n; ++u) {
+                if (((it + u) & 1) != g) continue;
+                const uint32_t parity = ((it + u) >> 1) & 1;
+                mbar_wait(ACC_FULL(g), parity);
+                tc_fence_after();
+                const uint32_t colbase = u * UM_NT;                          // local column of this tile inside the item
+                const uint32_t nvalid = min((uint32_t)UM_NT, item.cols_left - colbase);
+                float tmin = 3.0e38f;
+                if (nvalid == UM_NT) {
+#pragma unroll 1
+                    for (uint32_t c = 0; c < UM_NT; c += 64) {
+                        uint32_t v0[32], v1[32];
+                        TMEM_LD32(taddr + c, v0);
+                        TMEM_LD32(taddr + c + 32, v1);
+                        tmem_wait_ld();
+                        tmin = min32(v0, tmin);
+                        tmin = min32(v1, tmin);
+                    }
+                } else {
+#pragma unroll 1
+                    for (uint32_t c = 0; c < UM_NT; c += 32) {
+                        uint32_t v0[32];
+                        TMEM_LD32(taddr + c, v0);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c + i < nvalid) tmin = fminf(tmin, __uint_as_float(v0[i]));
+                    }
+                }
+                const bool need_best = row_ok && (tmin < bestV || (tmin == bestV && bestp == 1));
+                const bool need_hit = row_ok && hit == FE_NONE32 && tmin <= vthr0;
+                if (__any_sync(0xFFFFFFFFu, need_best || need_hit)) {
+                    // rare path: re-read the tile to locate columns (first column of the best (V, p); first hit)
+                    const uint32_t* par = a.colpar + (size_t)(item.t0 + u) * (UM_NT / 32);
+                    float cx = 3.0e38f;
+                    uint32_t cp = 1, ccol = FE_NONE32, chit = FE_NONE32;
+#pragma unroll 1
+                    for (uint32_t c = 0; c < UM_NT; c += 32) {
+                        uint32_t v0[32];
+                        TMEM_LD32(taddr + c, v0);
+                        tmem_wait_ld();
+                        const uint32_t pw = par[c >> 5];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (c + i < nvalid) {
+                                const float x = __uint_as_float(v0[i]);
+                                const uint32_t p = (pw >> i) & 1u;
+                                if (x < cx || (x == cx && p < cp)) { cx = x; cp = p; ccol = colbase + c + i; }
+                                if (chit == FE_NONE32 && x <= (p ? vthr1 : vthr0)) chit = colbase + c + i;
+                            }
+                        }
+                    }
+                    if (need_best && (cx < bestV || (cx == bestV && cp < bestp))) { bestV = cx; bestp = cp; bestcol = ccol; }
+                    if (need_hit && chit != FE_NONE32) hit = chit;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ACC_EMPTY(g));
+            }
+            it += n;
+            if (row_ok) {
+                if (bestcol != FE_NONE32) {
+                    const long long n16 = (long long)a2 + 2ll * (long long)bestV + (long long)bestp;
+                    const unsigned long long key = ((unsigned long long)(uint32_t)n16 << 32) | (unsigned long long)(item.col0 + bestcol);
+                    atomicMin(&a.rowbest[grow], key);
+                    if (bestV >= 16777216.0f - 64.0f) atomicOr(a.flags, 1u);
+                }
+                if (hit != FE_NONE32) atomicMin(&a.rowhit[grow], item.col0 + hit);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// operand blobs
+// ---------------------------------------------------------------------------------------------------
+// A rows: one warp per range position j of bucket-local order.  Row (4*lr + k) of blob `tile`:
+// element kidx -> blob + (kidx/8)*(128*8) + row*8 + kidx%8   (halves).
+__global__ void k_build_rows16(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
+                               const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
+                               __half* __restrict__ A16, uint32_t* __restrict__ rowA2) {
+    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= bk.n_ranges) return;
+    int bi = 0;
+    while (bi + 1 < bk.nb && j >= bk.range_off[bi + 1]) ++bi;
+    const uint32_t lj = j - bk.range_off[bi];
+    const uint32_t tile = bk.row_tile0[bi] + lj / 32, lr = lj % 32;
+    const fe_grid_item r = rng[order ? order[j] : j];
+    const uint32_t N = T * T;
+    __half* blob = A16 + (size_t)tile * UM_ROWS * Kpad;
+    const uint8_t* base = img + (size_t)r.y * stride + r.x;
+    uint32_t s2 = 0;
+    for (uint32_t e = lane; e < Kpad; e += 32) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (e < N) {
+            const uint32_t Y = e / T, X = e % T;
+            const int p0 = base[(size_t)Y * stride + X];
+            const int p1 = base[(size_t)X * stride + (T - 1 - Y)];
+            const int p2 = base[(size_t)(T - 1 - Y) * stride + (T - 1 - X)];
+            const int p3 = base[(size_t)(T - 1 - X) * stride + Y];
+            const int a0 = 4 * p0 - 510;
+            s2 += (uint32_t)(a0 * a0);
+            v[0] = (float)(510 - 4 * p0); v[1] = (float)(510 - 4 * p1); v[2] = (float)(510 - 4 * p2); v[3] = (float)(510 - 4 * p3);
+        } else if (e == N) {
+            v[0] = v[1] = v[2] = v[3] = 1.0f;
+        } else if (e == N + 1 || e == N + 2) {
+            v[0] = v[1] = v[2] = v[3] = 2048.0f;
+        }
+        __half* dst = blob + (size_t)(e / 8) * (UM_ROWS * 8) + (e % 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[(4 * lr + k) * 8] = __float2half_rn(v[k]);
+    }
+    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+    if (lane == 0) rowA2[j] = s2;
+}
+
+// B columns: one warp per sorted column.  b = D - 510; limbs of h = floor(sum b^2 / 2); parity bit.
+__global__ void k_build_pool16(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ dom,
+                               const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
+                               __half* __restrict__ B16, uint32_t* __restrict__ colpar) {
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= bk.n_domains) return;
+    int bi = 0;
+    while (bi + 1 < bk.nb && c >= bk.dom_off[bi + 1]) ++bi;
+    const uint32_t lc = c - bk.dom_off[bi];
+    const uint32_t tile = bk.col_tile0[bi] + lc / UM_NT, l = lc % UM_NT;
+    const fe_grid_item d = dom[order ? order[c] : c];
+    const uint32_t N = T * T;
+    __half* blob = B16 + (size_t)tile * UM_NT * Kpad;
+    const uint8_t* base = img + (size_t)d.y * stride + d.x;
+    uint32_t s2 = 0;
+    for (uint32_t e = lane; e < N; e += 32) {
+        const uint32_t ty = e / T, tx = e % T;
+        const uint8_t* p = base + (size_t)(2 * ty) * stride + 2 * tx;
+        const int D = p[0] + p[1] + p[stride] + p[stride + 1];
+        const int b = D - 510;
+        s2 += (uint32_t)(b * b);
+        blob[(size_t)(e / 8) * (UM_NT * 8) + l * 8 + (e % 8)] = __float2half_rn((float)b);
+    }
+    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+    if (lane == 0) {
+        const uint32_t h = s2 >> 1, p = s2 & 1u;
+        const float limb[3] = {(float)(h & 2047u), (float)((h >> 11) & 2047u), (float)((h >> 22) * 2048u)};
+        for (uint32_t q = 0; q < 3; ++q) {
+            const uint32_t e = N + q;
+            blob[(size_t)(e / 8) * (UM_NT * 8) + l * 8 + (e % 8)] = __float2half_rn(limb[q]);
+        }
+        if (p) atomicOr(&colpar[(size_t)tile * (UM_NT / 32) + (l >> 5)], 1u << (l & 31));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+int umma_level_supported(const LevelGeom& g) { return g.fast && (g.T == 4 || g.T == 8); }
+
+uint32_t umma_kpad(const LevelGeom& g) { return (g.N + 3 + 15u) & ~15u; }
+
+int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng,
+                            const uint32_t* dom_order, const uint32_t* rng_order, const uint32_t doff[8], const uint32_t roff[8],
+                            int nbuckets, uint32_t thr16, bool use_thr, bool* inexact, cudaEvent_t prep_done) {
+    const uint32_t Kpad = umma_kpad(g);
+    UmmaBuckets bk{};
+    UmmaArgs a{};
+    uint32_t rt = 0, ct = 0, nb = 0;
+    uint64_t total_items = 0;
+    for (int c = 0; c < nbuckets; ++c) {
+        const uint32_t rc = roff[c + 1] - roff[c], dc = doff[c + 1] - doff[c];
+        // buckets keep their slot in the operand layout even when they have no partner (their rows stay at INF)
+        bk.range_off[nb] = roff[c];
+        bk.dom_off[nb] = doff[c];
+        bk.row_tile0[nb] = rt;
+        bk.col_tile0[nb] = ct;
+        UmmaBucket& b = a.b[nb];
+        b.row_tile0 = rt; b.n_row_tiles = (rc + 31) / 32;
+        b.col_tile0 = ct; b.n_col_tiles = (dc + UM_NT - 1) / UM_NT;
+        b.row0 = roff[c] * 4; b.nrows = rc * 4;
+        b.col0 = doff[c]; b.ncols = dc;
+        rt += b.n_row_tiles;
+        ct += b.n_col_tiles;
+        ++nb;
+    }
+    bk.nb = (int)nb;
+    bk.range_off[nb] = roff[nbuckets];
+    bk.dom_off[nb] = doff[nbuckets];
+    bk.n_ranges = roff[nbuckets];
+    bk.n_domains = doff[nbuckets];
+    // column chunking: aim at >= 2 work items per SM when there are few row tiles
+    uint32_t live_row_tiles = 0;
+    for (uint32_t i = 0; i < nb; ++i)
+        if (a.b[i].n_col_tiles) live_row_tiles += a.b[i].n_row_tiles;
+    const uint32_t want_chunks = live_row_tiles ? (2 * 148 + live_row_tiles - 1) / live_row_tiles : 1;
+    for (uint32_t i = 0; i < nb; ++i) {
+        UmmaBucket& b = a.b[i];
+        b.chunks = b.n_col_tiles ? std::max(1u, std::min(want_chunks, b.n_col_tiles)) : 0;
+        if (!b.n_row_tiles) b.chunks = 0;
+        total_items += (uint64_t)b.n_row_tiles * b.chunks;
+    }
+    if (total_items == 0) { *inexact = false; if (prep_done) cudaEventRecord(prep_done, ctx->stream); return FE_OK; }
+    if (total_items > 0x7FFFFFFFull) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "umma: too many work items");
+
+    const size_t bytesA = (size_t)rt * UM_ROWS * Kpad * 2, bytesB = (size_t)ct * UM_NT * Kpad * 2;
+    FE_CUDA(ctx, ctx->b_A16.ensure(bytesA + 256));
+    FE_CUDA(ctx, ctx->b_B16.ensure(bytesB + 256));
+    FE_CUDA(ctx, ctx->b_tmaps.ensure((size_t)ct * (UM_NT / 32) * 4 + 64));
+    FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)bk.n_ranges * 4 + 4));
+    uint32_t* flags = ctx->b_counters.as<uint32_t>() + 2;
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_A16.p, 0, bytesA, ctx->stream));
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_B16.p, 0, bytesB, ctx->stream));
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_tmaps.p, 0, (size_t)ct * (UM_NT / 32) * 4, ctx->stream));
+    k_build_rows16<<<(unsigned)(((uint64_t)bk.n_ranges * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, g.T, Kpad, ctx->b_A16.as<__half>(), ctx->b_rowc.as<uint32_t>());
+    FE_CUDA(ctx, cudaGetLastError());
+    k_build_pool16<<<(unsigned)(((uint64_t)bk.n_domains * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, g.T, Kpad, ctx->b_B16.as<__half>(), ctx->b_tmaps.as<uint32_t>());
+    FE_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 2;
+    if (prep_done) cudaEventRecord(prep_done, ctx->stream);
+
+    a.A16 = ctx->b_A16.p;
+    a.B16 = ctx->b_B16.p;
+    a.colpar = ctx->b_tmaps.as<uint32_t>();
+    a.rowA2 = ctx->b_rowc.as<uint32_t>();
+    a.rowbest = ctx->b_rowbest.as<unsigned long long>();
+    a.rowhit = ctx->b_rowhit.as<uint32_t>();
+    a.flags = flags;
+    a.nb = (int)nb;
+    a.Kpad = Kpad;
+    a.total_items = (uint32_t)total_items;
+    a.thr16 = thr16;
+    a.use_thr = use_thr ? 1u : 0u;
+    const uint32_t stage_bytes = UM_NT * Kpad * 2, a_bytes = 2 * UM_ROWS * Kpad * 2;
+    uint32_t stages = (kStagesMaxBytes - a_bytes) / stage_bytes;
+    stages = std::max(2u, std::min((uint32_t)UM_MAX_STAGES, stages));
+    a.stages = stages;
+    const size_t smem = (size_t)a_bytes + (size_t)stages * stage_bytes + (8 + 2 * UM_MAX_STAGES) * 8 + 16;
+    FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(total_items, 148);
+    k_search_umma<0><<<grid, UM_THREADS, smem, ctx->stream>>>(a);
+    FE_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    uint32_t f = 0;
+    FE_CUDA(ctx, cudaMemcpyAsync(&f, flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *inexact = f != 0;
+    return FE_OK;
 }

@@ -1,0 +1,41 @@
+// fe_umma.cuh -- declarations of the tcgen05 search path (fe_search_umma.cu).
+#pragma once
+#include <algorithm>
+
+#include "fe_internal.cuh"
+
+constexpr int UM_NT = 256;         // domain columns per tile (UMMA N)
+constexpr int UM_ROWS = 128;       // rows per tile = 32 ranges x 4 rotations (UMMA M)
+constexpr int UM_THREADS = 320;    // producer warp, MMA warp, two epilogue warpgroups
+constexpr int UM_MAX_STAGES = 8;
+
+struct UmmaBucket {
+    uint32_t row_tile0, n_row_tiles; // A blobs of this classifier bucket
+    uint32_t col_tile0, n_col_tiles; // B blobs
+    uint32_t row0, nrows;            // first global row (= 4 * first range position), valid rows
+    uint32_t col0, ncols;            // first global sorted column, valid columns
+    uint32_t chunks;                 // column chunks per row tile (work items = n_row_tiles * chunks)
+};
+
+struct UmmaArgs {
+    const void* A16;
+    const void* B16;
+    const uint32_t* colpar;          // [col tiles][UM_NT/32] parity of sum(b^2) per column
+    const uint32_t* rowA2;           // [range position] sum(a^2)
+    unsigned long long* rowbest;
+    uint32_t* rowhit;
+    uint32_t* flags;                 // bit 0: a winner sits in the fp32-inexact band
+    UmmaBucket b[7];
+    int nb;
+    uint32_t Kpad, stages, total_items, thr16, use_thr;
+};
+
+struct UmmaBuckets {                 // operand-layout view for the blob builders
+    uint32_t range_off[8], dom_off[8], row_tile0[7], col_tile0[7];
+    uint32_t n_ranges, n_domains;
+    int nb;
+};
+
+int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng,
+                            const uint32_t* dom_order, const uint32_t* rng_order, const uint32_t doff[8], const uint32_t roff[8],
+                            int nbuckets, uint32_t thr16, bool use_thr, bool* inexact, cudaEvent_t prep_done);
