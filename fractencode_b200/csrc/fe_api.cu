@@ -240,8 +240,8 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     const bool timed = io.stat_level >= 0 && io.stat_level < 8;
     if (timed) cudaEventRecord(ctx->ev[0], ctx->stream);
 
-    FE_CUDA(ctx, ctx->b_counters.ensure(4 * sizeof(uint32_t)));
-    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.p, 0, 4 * sizeof(uint32_t), ctx->stream));
+    FE_CUDA(ctx, ctx->b_counters.ensure(16 * sizeof(uint32_t)));
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.p, 0, 16 * sizeof(uint32_t), ctx->stream));
 
     // ---- classes and buckets ----
     uint32_t doff[8] = {0, nD, nD, nD, nD, nD, nD, nD}, roff[8] = {0, nR, nR, nR, nR, nR, nR, nR};

@@ -24,7 +24,14 @@
 // contiguous blob per tile, so a stage is ONE bulk copy and needs no tensor map.
 #include <cuda_fp16.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "fe_umma.cuh"
+
+#ifndef FE_USE_FMNMX3
+#define FE_USE_FMNMX3 0
+#endif
 
 namespace {
 
@@ -150,6 +157,101 @@ __device__ __forceinline__ WorkItem decode_item(const UmmaArgs& a, uint32_t w) {
     return it;
 }
 
+// 128 accumulator values of one row -> running (bestV, bestp, bestcol) and first threshold hit.
+// Fast path: FMNMX3 tree for the tile minimum; the per-column scan only runs for lanes whose tile
+// minimum can improve their row (or cross the threshold) and works on the registers already loaded.
+struct RowState {
+    float bestV;
+    uint32_t bestp, bestcol, hit;
+    float vthr0, vthr1;
+    uint32_t n_improve, n_full, n_warp_events; // tuning counters (FE_UMMA_DBG & 16)
+};
+
+// Exhaustive scan of the tile held in registers (rare: exact ties, threshold crossings).
+__device__ __forceinline__ void scan_tile_full(const uint32_t (&v)[UM_NT], RowState& st, bool need_best, bool need_hit, uint32_t colbase,
+                                            const uint32_t* __restrict__ par) {
+    float cx = 3.0e38f;
+    uint32_t cp = 1, ccol = FE_NONE32, chit = FE_NONE32;
+#pragma unroll
+    for (int wd = 0; wd < UM_NT / 32; ++wd) {
+        const uint32_t pw = par[wd];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const int i = wd * 32 + b;
+            const float x = __uint_as_float(v[i]);
+            const uint32_t p = (pw >> b) & 1u;
+            if (x < cx || (x == cx && p < cp)) { cx = x; cp = p; ccol = colbase + i; }
+            if (chit == FE_NONE32 && x <= (p ? st.vthr1 : st.vthr0)) chit = colbase + i;
+        }
+    }
+    if (need_best && (cx < st.bestV || (cx == st.bestV && cp < st.bestp))) { st.bestV = cx; st.bestp = cp; st.bestcol = ccol; }
+    if (need_hit && chit != FE_NONE32) st.hit = chit;
+}
+
+__device__ __forceinline__ void process_tile(uint32_t (&v)[UM_NT], RowState& st, bool row_ok, uint32_t colbase, uint32_t nvalid,
+                                             const uint32_t* __restrict__ par) {
+    if (nvalid < UM_NT) {
+#pragma unroll
+        for (int i = 0; i < UM_NT; ++i)
+            if ((uint32_t)i >= nvalid) v[i] = 0x7F61B1E6u; // 3.0e38f
+    }
+    // minimum of every group of 8 columns, then of the tile
+    float grp[UM_NT / 8];
+#pragma unroll
+    for (int k = 0; k < UM_NT / 8; ++k) {
+        const int i = 8 * k;
+        float m = fmin3(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]));
+        m = fmin3(m, __uint_as_float(v[i + 3]), __uint_as_float(v[i + 4]));
+        m = fmin3(m, __uint_as_float(v[i + 5]), __uint_as_float(v[i + 6]));
+        grp[k] = fminf(m, __uint_as_float(v[i + 7]));
+    }
+    float t0 = 3.0e38f, t1 = 3.0e38f;
+#pragma unroll
+    for (int k = 0; k < UM_NT / 8; k += 4) {
+        t0 = fmin3(t0, grp[k], grp[k + 1]);
+        t1 = fmin3(t1, grp[k + 2], grp[k + 3]);
+    }
+    const float tmin = fminf(t0, t1);
+    const bool improve = row_ok && tmin < st.bestV;
+    const bool tie = row_ok && tmin == st.bestV && st.bestp == 1;   // an equal V with even parity would win
+    const bool need_hit = row_ok && st.hit == FE_NONE32 && tmin <= st.vthr0;
+    if (__any_sync(__activemask(), improve | tie | need_hit)) ++st.n_warp_events;
+    if (improve | tie | need_hit) {
+        ++st.n_improve;
+        bool full = tie | need_hit;
+        if (!full) {
+            // common case: locate the first column holding the tile minimum through its group
+            int gi = UM_NT / 8 - 1, ng = 0;
+#pragma unroll
+            for (int k = UM_NT / 8 - 1; k >= 0; --k) {
+                const bool e = grp[k] == tmin;
+                gi = e ? k : gi;
+                ng += e ? 1 : 0;
+            }
+            int ei = 7, ne = 0;
+#pragma unroll
+            for (int k = 0; k < UM_NT / 8; ++k) {
+                if (k == gi) {
+#pragma unroll
+                    for (int e = 7; e >= 0; --e) {
+                        const bool q = __uint_as_float(v[8 * k + e]) == tmin;
+                        ei = q ? e : ei;
+                        ne += q ? 1 : 0;
+                    }
+                }
+            }
+            const uint32_t c = (uint32_t)(gi * 8 + ei);
+            const uint32_t p = (par[c >> 5] >> (c & 31)) & 1u;
+            if (p == 0 || (ng == 1 && ne == 1)) { // nothing in this tile can beat (tmin, p, c)
+                st.bestV = tmin; st.bestp = p; st.bestcol = colbase + c;
+            } else {
+                full = true;                       // several columns tie on V and the first has odd parity
+            }
+        }
+        if (full) { ++st.n_full; scan_tile_full(v, st, improve | tie, need_hit, colbase, par); }
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -159,12 +261,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
     uint8_t* sA = smem;                     // 2 buffers
     uint8_t* sB = smem + 2 * bytesA;        // S stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)S * bytesB);
-    // barrier indices
     const uint32_t bar0 = smem_u32(bars);
     auto A_FULL = [&](uint32_t i) { return bar0 + 8 * (0 + i); };
     auto A_EMPTY = [&](uint32_t i) { return bar0 + 8 * (2 + i); };
-    auto ACC_FULL = [&](uint32_t i) { return bar0 + 8 * (4 + i); };
-    auto ACC_EMPTY = [&](uint32_t i) { return bar0 + 8 * (6 + i); };
+    auto ACC_FULL = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (4 + 2 * g + b); };
     auto B_FULL = [&](uint32_t i) { return bar0 + 8 * (8 + i); };
     auto B_EMPTY = [&](uint32_t i) { return bar0 + 8 * (8 + UM_MAX_STAGES + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * UM_MAX_STAGES);
@@ -172,17 +272,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < 2; ++i) {
             mbar_init(A_FULL(i), 1);
-            mbar_init(A_EMPTY(i), 1);
-            mbar_init(ACC_FULL(i), 1);
-            mbar_init(ACC_EMPTY(i), 4);
+            mbar_init(A_EMPTY(i), UM_WGS);
         }
+        for (uint32_t i = 0; i < 4; ++i) mbar_init(bar0 + 8 * (4 + i), 1);
         for (uint32_t i = 0; i < S; ++i) {
             mbar_init(B_FULL(i), 1);
             mbar_init(B_EMPTY(i), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -192,7 +291,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= producer =================
+        // ================= producer: bulk async copies (TMA engine) =================
         if (lane == 0) {
             uint32_t it = 0, wi = 0;
             for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x, ++wi) {
@@ -204,141 +303,124 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
                 for (uint32_t t = item.t0; t < item.t1; ++t, ++it) {
                     const uint32_t s = it % S;
                     mbar_wait(B_EMPTY(s), ((it / S) & 1) ^ 1);
+                    if (a.dbg & 4) { mbar_arrive(B_FULL(s)); continue; }
                     mbar_expect_tx(B_FULL(s), bytesB);
                     bulk_g2s(smem_u32(sB + (size_t)s * bytesB), reinterpret_cast<const uint8_t*>(a.B16) + (size_t)t * bytesB, bytesB, B_FULL(s));
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            // instruction descriptor: D = F32 (f16 kind) / S32 (i8 kind), A/B format 0 (F16 / U8), K-major both, N = 256, M = 128
-            const uint32_t idesc = ((KIND == 0 ? 1u : 2u) << 4) | ((uint32_t)(UM_NT >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
-            const uint32_t nk = a.Kpad / 16;  // K = 16 elements of 2 bytes per instruction = 2 core-matrix chunks
-            uint32_t it = 0, wi = 0;
-            for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x, ++wi) {
-                const WorkItem item = decode_item(a, w);
-                const uint32_t ab = wi & 1;
-                mbar_wait(A_FULL(ab), (wi >> 1) & 1);
-                const uint32_t a_addr = smem_u32(sA + ab * bytesA);
-                for (uint32_t t = item.t0; t < item.t1; ++t, ++it) {
-                    const uint32_t s = it % S, acc = it & 1;
-                    mbar_wait(ACC_EMPTY(acc), ((it >> 1) & 1) ^ 1);
-                    mbar_wait(B_FULL(s), (it / S) & 1);
-                    tc_fence_after();
-                    const uint32_t b_addr = smem_u32(sB + (size_t)s * bytesB);
-                    for (uint32_t kk = 0; kk < nk; ++kk) {
-                        // chunk-major blobs: K chunk c (8 elements = 16 bytes) of all rows is contiguous
-                        const uint64_t adesc = make_desc(a_addr + kk * 2 * (UM_ROWS * 16), UM_ROWS * 16, 128);
-                        const uint64_t bdesc = make_desc(b_addr + kk * 2 * (UM_NT * 16), UM_NT * 16, 128);
-                        tc_mma<KIND>(tmem_base + acc * UM_NT, adesc, bdesc, idesc, kk > 0 ? 1u : 0u);
-                    }
-                    tc_commit(B_EMPTY(s));
-                    tc_commit(ACC_FULL(acc));
-                }
-                tc_commit(A_EMPTY(ab));
-            }
-        }
     } else {
-        // ================= epilogue: warpgroup g drains accumulator g =================
-        const uint32_t g = (warp - 2) >> 2;
+        // ================= compute warpgroups =================
+        // Warpgroup g owns accumulators (g,0) and (g,1) (128 TMEM columns each) and the tiles with
+        // (global tile counter % UM_WGS) == g.  Its elected thread issues the tcgen05.mma of the tile two
+        // steps ahead as soon as all four warps have copied the current accumulator to registers, so the
+        // tensor pipe works on tile t+1/t+2 while the warpgroup reduces tile t.  No separate MMA warp and
+        // no accumulator-empty barrier: the handoff latency is off the critical path.
+        const uint32_t g = (warp - 1) >> 2;
         const uint32_t sp = warp & 3;                 // TMEM sub-partition this warp may read
         const uint32_t lrow = sp * 32 + lane;         // row inside the tile == TMEM lane
-        const uint32_t taddr = tmem_base + ((sp * 32u) << 16) + g * UM_NT;
-        uint32_t it = 0;
-        for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x) {
+        const bool elected = ((warp - 1) & 3) == 0 && lane == 0;
+        const uint32_t idesc = ((KIND == 0 ? 1u : 2u) << 4) | ((uint32_t)(UM_NT >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
+        const uint32_t nk = (a.dbg & 2) ? 0u : a.Kpad / 16;
+        uint32_t it0 = 0, wi = 0;   // global tile counter at the start of the item, item counter
+        uint32_t nfull[2] = {0, 0}; // completed uses of accumulator (g, b) -> mbarrier parity
+        for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x, ++wi) {
             const WorkItem item = decode_item(a, w);
+            const uint32_t ab = wi & 1;
+            const uint32_t n = item.t1 - item.t0;
             const bool row_ok = lrow < item.nrows;
             const uint32_t grow = item.row0 + lrow;
             const uint32_t a2 = row_ok ? a.rowA2[grow >> 2] : 0u;
-            // n16 <= thr16  <=>  V <= floor((thr16 - a2 - p) / 2)
-            float vthr0 = -3.0e38f, vthr1 = -3.0e38f;
-            if (a.use_thr && row_ok) {
+            RowState st;
+            st.bestV = 3.0e38f; st.bestp = 0; st.bestcol = FE_NONE32; st.hit = FE_NONE32;
+            st.n_improve = st.n_full = st.n_warp_events = 0;
+            st.vthr0 = -3.0e38f; st.vthr1 = -3.0e38f;
+            if (a.use_thr && row_ok) { // n16 <= thr16  <=>  V <= floor((thr16 - a2 - p) / 2)
                 const long long tt = (long long)a.thr16 - (long long)a2;
                 long long f0 = tt >= 0 ? tt / 2 : -((-tt + 1) / 2);
                 long long f1 = (tt - 1) >= 0 ? (tt - 1) / 2 : -((-(tt - 1) + 1) / 2);
                 f0 = max(-16777216ll, min(16777215ll, f0));
                 f1 = max(-16777216ll, min(16777215ll, f1));
-                vthr0 = (float)f0;
-                vthr1 = (float)f1;
+                st.vthr0 = (float)f0;
+                st.vthr1 = (float)f1;
             }
-            float bestV = 3.0e38f;
-            uint32_t bestp = 0, bestcol = FE_NONE32, hit = FE_NONE32;
-            const uint32_t n = item.t1 - item.t0;
-            for (uint32_t u = 0; u < n; ++u) {
-                if (((it + u) & 1) != g) continue;
-                const uint32_t parity = ((it + u) >> 1) & 1;
-                mbar_wait(ACC_FULL(g), parity);
+            // local tile indices of this warpgroup inside the item: u = first, first + UM_WGS, ...
+            const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
+            const uint32_t a_addr = smem_u32(sA + ab * bytesA);
+            auto issue = [&](uint32_t u, uint32_t buf) { // elected thread only
+                const uint32_t gi = it0 + u, s = gi % S;
+                mbar_wait(B_FULL(s), (gi / S) & 1);
                 tc_fence_after();
-                const uint32_t colbase = u * UM_NT;                          // local column of this tile inside the item
-                const uint32_t nvalid = min((uint32_t)UM_NT, item.cols_left - colbase);
-                float tmin = 3.0e38f;
-                if (nvalid == UM_NT) {
-#pragma unroll 1
-                    for (uint32_t c = 0; c < UM_NT; c += 64) {
-                        uint32_t v0[32], v1[32];
-                        TMEM_LD32(taddr + c, v0);
-                        TMEM_LD32(taddr + c + 32, v1);
-                        tmem_wait_ld();
-                        tmin = min32(v0, tmin);
-                        tmin = min32(v1, tmin);
-                    }
-                } else {
-#pragma unroll 1
-                    for (uint32_t c = 0; c < UM_NT; c += 32) {
-                        uint32_t v0[32];
-                        TMEM_LD32(taddr + c, v0);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c + i < nvalid) tmin = fminf(tmin, __uint_as_float(v0[i]));
-                    }
+                const uint32_t b_addr = smem_u32(sB + (size_t)s * bytesB);
+                const uint32_t d_tmem = tmem_base + (g * 2 + buf) * UM_NT;
+                for (uint32_t kk = 0; kk < nk; ++kk) {
+                    // chunk-major blobs: K chunk c (8 halves = 16 bytes) of all rows is contiguous
+                    const uint64_t adesc = make_desc(a_addr + kk * 2 * (UM_ROWS * 16), UM_ROWS * 16, 128);
+                    const uint64_t bdesc = make_desc(b_addr + kk * 2 * (UM_NT * 16), UM_NT * 16, 128);
+                    tc_mma<KIND>(d_tmem, adesc, bdesc, idesc, kk > 0 ? 1u : 0u);
                 }
-                const bool need_best = row_ok && (tmin < bestV || (tmin == bestV && bestp == 1));
-                const bool need_hit = row_ok && hit == FE_NONE32 && tmin <= vthr0;
-                if (__any_sync(0xFFFFFFFFu, need_best || need_hit)) {
-                    // rare path: re-read the tile to locate columns (first column of the best (V, p); first hit)
-                    const uint32_t* par = a.colpar + (size_t)(item.t0 + u) * (UM_NT / 32);
-                    float cx = 3.0e38f;
-                    uint32_t cp = 1, ccol = FE_NONE32, chit = FE_NONE32;
-#pragma unroll 1
-                    for (uint32_t c = 0; c < UM_NT; c += 32) {
-                        uint32_t v0[32];
-                        TMEM_LD32(taddr + c, v0);
-                        tmem_wait_ld();
-                        const uint32_t pw = par[c >> 5];
+                tc_commit(B_EMPTY(s));
+                tc_commit(ACC_FULL(g, buf));
+            };
+            uint32_t my_tiles = first < n ? (n - first + UM_WGS - 1) / UM_WGS : 0;
+            if (elected) {
+                mbar_wait(A_FULL(ab), (wi >> 1) & 1);
+                if (my_tiles > 0) issue(first, 0);
+            }
+            // buffer sequence inside an item always starts at 0: both buffers are idle at item boundaries
+            if (elected && my_tiles > 1) issue(first + UM_WGS, 1);
+            for (uint32_t j = 0; j < my_tiles; ++j) {
+                const uint32_t u = first + j * UM_WGS, buf = j & 1;
+                mbar_wait(ACC_FULL(g, buf), nfull[buf] & 1);
+                ++nfull[buf];
+                tc_fence_after();
+                uint32_t v[UM_NT];
+                if (!(a.dbg & 1)) {
+                    const uint32_t taddr = tmem_base + ((sp * 32u) << 16) + (g * 2 + buf) * UM_NT;
+                    TMEM_LD32(taddr, (v + 0));
+                    TMEM_LD32(taddr + 32, (v + 32));
+                    TMEM_LD32(taddr + 64, (v + 64));
+                    TMEM_LD32(taddr + 96, (v + 96));
+                    tmem_wait_ld();
+                } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (c + i < nvalid) {
-                                const float x = __uint_as_float(v0[i]);
-                                const uint32_t p = (pw >> i) & 1u;
-                                if (x < cx || (x == cx && p < cp)) { cx = x; cp = p; ccol = colbase + c + i; }
-                                if (chit == FE_NONE32 && x <= (p ? vthr1 : vthr0)) chit = colbase + c + i;
-                            }
-                        }
-                    }
-                    if (need_best && (cx < bestV || (cx == bestV && cp < bestp))) { bestV = cx; bestp = cp; bestcol = ccol; }
-                    if (need_hit && chit != FE_NONE32) hit = chit;
+                    for (int i = 0; i < UM_NT; ++i) v[i] = 0;
                 }
                 tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ACC_EMPTY(g));
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); // all four warps hold the tile in registers
+                if (elected && j + 2 < my_tiles) issue(u + 2 * UM_WGS, buf);
+                const uint32_t colbase = u * UM_NT;
+                const uint32_t nvalid = min((uint32_t)UM_NT, item.cols_left - colbase);
+                if (a.dbg & 8) {
+                    uint32_t x = 0;
+#pragma unroll
+                    for (int i = 0; i < UM_NT; ++i) x ^= v[i];
+                    if (x == 0x12345u) st.bestcol = 0; // keep the loads alive
+                } else if (!(a.dbg & 1)) process_tile(v, st, row_ok, colbase, nvalid, a.colpar + (size_t)(item.t0 + u) * (UM_NT / 32));
             }
-            it += n;
+            // this warpgroup is done with the A buffer once its last MMAs have completed
+            if (elected) {
+                if (my_tiles > 0) tc_commit(A_EMPTY(ab)); else mbar_arrive(A_EMPTY(ab));
+            }
+            it0 += n;
+            if (a.dbg & 16) {
+                atomicAdd(a.flags + 4, st.n_improve); atomicAdd(a.flags + 5, st.n_full);
+                if (lane == 0) { atomicAdd(a.flags + 6, st.n_warp_events); atomicAdd(a.flags + 7, my_tiles); }
+            }
             if (row_ok) {
-                if (bestcol != FE_NONE32) {
-                    const long long n16 = (long long)a2 + 2ll * (long long)bestV + (long long)bestp;
-                    const unsigned long long key = ((unsigned long long)(uint32_t)n16 << 32) | (unsigned long long)(item.col0 + bestcol);
+                if (st.bestcol != FE_NONE32) {
+                    const long long n16 = (long long)a2 + 2ll * (long long)st.bestV + (long long)st.bestp;
+                    const unsigned long long key = ((unsigned long long)(uint32_t)n16 << 32) | (unsigned long long)(item.col0 + st.bestcol);
                     atomicMin(&a.rowbest[grow], key);
-                    if (bestV >= 16777216.0f - 64.0f) atomicOr(a.flags, 1u);
+                    if (st.bestV >= 16777216.0f - 64.0f) atomicOr(a.flags, 1u);
                 }
-                if (hit != FE_NONE32) atomicMin(&a.rowhit[grow], item.col0 + hit);
+                if (st.hit != FE_NONE32) atomicMin(&a.rowhit[grow], item.col0 + st.hit);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -504,6 +586,7 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     a.total_items = (uint32_t)total_items;
     a.thr16 = thr16;
     a.use_thr = use_thr ? 1u : 0u;
+    { const char* e = getenv("FE_UMMA_DBG"); a.dbg = e ? (uint32_t)atoi(e) : 0u; }
     const uint32_t stage_bytes = UM_NT * Kpad * 2, a_bytes = 2 * UM_ROWS * Kpad * 2;
     uint32_t stages = (kStagesMaxBytes - a_bytes) / stage_bytes;
     stages = std::max(2u, std::min((uint32_t)UM_MAX_STAGES, stages));
@@ -517,6 +600,11 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     uint32_t f = 0;
     FE_CUDA(ctx, cudaMemcpyAsync(&f, flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *inexact = f != 0;
+    *inexact = (f & 1u) != 0;
+    if (a.dbg & 16) {
+        uint32_t c[8];
+        cudaMemcpy(c, ctx->b_counters.p, sizeof(c), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[umma dbg] T=%u lane-improvements=%u full-scans=%u warp-events=%u warp-tiles=%u\n", g.T, c[4 + 2], c[5 + 2], c[6 + 2], c[7 + 2]);
+    }
     return FE_OK;
 }

@@ -4,9 +4,10 @@
 
 #include "fe_internal.cuh"
 
-constexpr int UM_NT = 256;         // domain columns per tile (UMMA N)
+constexpr int UM_NT = 128;         // domain columns per tile (UMMA N)
 constexpr int UM_ROWS = 128;       // rows per tile = 32 ranges x 4 rotations (UMMA M)
-constexpr int UM_THREADS = 320;    // producer warp, MMA warp, two epilogue warpgroups
+constexpr int UM_WGS = 2;          // compute warpgroups (each owns 2 TMEM accumulators of UM_NT columns)
+constexpr int UM_THREADS = 32 + 128 * UM_WGS; // producer warp + compute warpgroups
 constexpr int UM_MAX_STAGES = 8;
 
 struct UmmaBucket {
@@ -28,6 +29,7 @@ struct UmmaArgs {
     UmmaBucket b[7];
     int nb;
     uint32_t Kpad, stages, total_items, thr16, use_thr;
+    uint32_t dbg;                    // tuning probes (FE_UMMA_DBG): 1 skip TMEM drain, 2 skip MMA issue, 4 skip B copies
 };
 
 struct UmmaBuckets {                 // operand-layout view for the blob builders
