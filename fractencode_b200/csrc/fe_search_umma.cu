@@ -29,6 +29,9 @@
 
 #include "fe_umma.cuh"
 
+#ifndef FE_UMMA_PROF
+#define FE_UMMA_PROF 0
+#endif
 #ifndef FE_USE_FMNMX3
 #define FE_USE_FMNMX3 0
 #endif
@@ -71,6 +74,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
                  : "memory");
+}
+// plain shared-memory flags: ~30-cycle polls instead of ~200-cycle mbarrier probes
+__device__ __forceinline__ void flag_add_release(uint32_t addr, uint32_t v) {
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void flag_store_release(uint32_t addr, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t flag_load_acquire(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void flag_wait_ge(uint32_t addr, uint32_t want) {
+    if ((int32_t)(flag_load_acquire(addr) - want) >= 0) return;
+    const long long t0 = clock64();
+    while ((int32_t)(flag_load_acquire(addr) - want) < 0) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -162,18 +184,20 @@ __device__ __forceinline__ WorkItem decode_item(const UmmaArgs& a, uint32_t w) {
 // minimum can improve their row (or cross the threshold) and works on the registers already loaded.
 struct RowState {
     float bestV;
-    uint32_t bestp, bestcol, hit;
+    uint32_t bestp;            // parity of sum(b^2) of the best column; 2 = not looked up yet
+    uint32_t bestcol, hit;
     float vthr0, vthr1;
-    uint32_t n_improve, n_full, n_warp_events; // tuning counters (FE_UMMA_DBG & 16)
+    const uint32_t* par_item;  // parity words of the item's first tile (columns are contiguous from there)
 };
+__device__ __forceinline__ uint32_t row_parity(const RowState& st, uint32_t col) { return (st.par_item[col >> 5] >> (col & 31)) & 1u; }
 
-// Exhaustive scan of the tile held in registers (rare: exact ties, threshold crossings).
-__device__ __forceinline__ void scan_tile_full(const uint32_t (&v)[UM_NT], RowState& st, bool need_best, bool need_hit, uint32_t colbase,
-                                            const uint32_t* __restrict__ par) {
+// Exhaustive scan of a half tile held in registers (rare: exact ties, threshold crossings).
+__device__ __forceinline__ void scan_half_full(const uint32_t (&v)[UM_HALF], RowState& st, bool need_best, bool need_hit, uint32_t colbase,
+                                               const uint32_t* __restrict__ par) {
     float cx = 3.0e38f;
     uint32_t cp = 1, ccol = FE_NONE32, chit = FE_NONE32;
 #pragma unroll
-    for (int wd = 0; wd < UM_NT / 32; ++wd) {
+    for (int wd = 0; wd < UM_HALF / 32; ++wd) {
         const uint32_t pw = par[wd];
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
@@ -188,49 +212,53 @@ __device__ __forceinline__ void scan_tile_full(const uint32_t (&v)[UM_NT], RowSt
     if (need_hit && chit != FE_NONE32) st.hit = chit;
 }
 
-__device__ __forceinline__ void process_tile(uint32_t (&v)[UM_NT], RowState& st, bool row_ok, uint32_t colbase, uint32_t nvalid,
+// UM_HALF accumulator values of one row (columns colbase .. colbase+UM_HALF-1 of the work item).
+__device__ __forceinline__ void process_half(uint32_t (&v)[UM_HALF], RowState& st, bool row_ok, uint32_t colbase, uint32_t nvalid,
                                              const uint32_t* __restrict__ par) {
-    if (nvalid < UM_NT) {
+    if (nvalid < UM_HALF) {
 #pragma unroll
-        for (int i = 0; i < UM_NT; ++i)
+        for (int i = 0; i < UM_HALF; ++i)
             if ((uint32_t)i >= nvalid) v[i] = 0x7F61B1E6u; // 3.0e38f
     }
-    // minimum of every group of 8 columns, then of the tile
-    float grp[UM_NT / 8];
+    float grp[UM_HALF / 8]; // minimum of every group of 8 columns; written level by level for ILP (8 independent chains)
+    float ga[UM_HALF / 8], gb[UM_HALF / 8];
 #pragma unroll
-    for (int k = 0; k < UM_NT / 8; ++k) {
-        const int i = 8 * k;
-        float m = fmin3(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]));
-        m = fmin3(m, __uint_as_float(v[i + 3]), __uint_as_float(v[i + 4]));
-        m = fmin3(m, __uint_as_float(v[i + 5]), __uint_as_float(v[i + 6]));
-        grp[k] = fminf(m, __uint_as_float(v[i + 7]));
-    }
+    for (int k = 0; k < UM_HALF / 8; ++k) ga[k] = fmin3(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1]), __uint_as_float(v[8 * k + 2]));
+#pragma unroll
+    for (int k = 0; k < UM_HALF / 8; ++k) gb[k] = fmin3(__uint_as_float(v[8 * k + 3]), __uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5]));
+#pragma unroll
+    for (int k = 0; k < UM_HALF / 8; ++k) ga[k] = fmin3(ga[k], __uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7]));
+#pragma unroll
+    for (int k = 0; k < UM_HALF / 8; ++k) grp[k] = fminf(ga[k], gb[k]);
     float t0 = 3.0e38f, t1 = 3.0e38f;
 #pragma unroll
-    for (int k = 0; k < UM_NT / 8; k += 4) {
+    for (int k = 0; k < UM_HALF / 8; k += 4) {
         t0 = fmin3(t0, grp[k], grp[k + 1]);
         t1 = fmin3(t1, grp[k + 2], grp[k + 3]);
     }
     const float tmin = fminf(t0, t1);
     const bool improve = row_ok && tmin < st.bestV;
-    const bool tie = row_ok && tmin == st.bestV && st.bestp == 1;   // an equal V with even parity would win
+    const bool tie = row_ok && tmin == st.bestV;                     // an equal V with even parity could win
     const bool need_hit = row_ok && st.hit == FE_NONE32 && tmin <= st.vthr0;
-    if (__any_sync(__activemask(), improve | tie | need_hit)) ++st.n_warp_events;
     if (improve | tie | need_hit) {
-        ++st.n_improve;
-        bool full = tie | need_hit;
-        if (!full) {
-            // common case: locate the first column holding the tile minimum through its group
-            int gi = UM_NT / 8 - 1, ng = 0;
+        bool full = need_hit;
+        if (tie) {
+            if (st.bestp == 2) st.bestp = row_parity(st, st.bestcol);
+            full = full | (st.bestp == 1);
+        }
+        if (improve && !full) {
+            // common case: the minimum is held by exactly one column -> it is the best of these columns
+            // whatever its parity (looked up lazily); locate it through its group of 8
+            int gi = UM_HALF / 8 - 1, ng = 0;
 #pragma unroll
-            for (int k = UM_NT / 8 - 1; k >= 0; --k) {
+            for (int k = UM_HALF / 8 - 1; k >= 0; --k) {
                 const bool e = grp[k] == tmin;
                 gi = e ? k : gi;
                 ng += e ? 1 : 0;
             }
             int ei = 7, ne = 0;
 #pragma unroll
-            for (int k = 0; k < UM_NT / 8; ++k) {
+            for (int k = 0; k < UM_HALF / 8; ++k) {
                 if (k == gi) {
 #pragma unroll
                     for (int e = 7; e >= 0; --e) {
@@ -240,15 +268,16 @@ __device__ __forceinline__ void process_tile(uint32_t (&v)[UM_NT], RowState& st,
                     }
                 }
             }
-            const uint32_t c = (uint32_t)(gi * 8 + ei);
-            const uint32_t p = (par[c >> 5] >> (c & 31)) & 1u;
-            if (p == 0 || (ng == 1 && ne == 1)) { // nothing in this tile can beat (tmin, p, c)
-                st.bestV = tmin; st.bestp = p; st.bestcol = colbase + c;
+            if (ng == 1 && ne == 1) {
+                st.bestV = tmin; st.bestp = 2; st.bestcol = colbase + (uint32_t)(gi * 8 + ei);
             } else {
-                full = true;                       // several columns tie on V and the first has odd parity
+                full = true;                       // several columns tie on V: parity decides
             }
         }
-        if (full) { ++st.n_full; scan_tile_full(v, st, improve | tie, need_hit, colbase, par); }
+        if (full) {
+            if (st.bestp == 2 && st.bestcol != FE_NONE32) st.bestp = row_parity(st, st.bestcol);
+            scan_half_full(v, st, improve | tie, need_hit, colbase, par);
+        }
     }
 }
 
@@ -257,7 +286,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bytesA = UM_ROWS * a.Kpad * 2, bytesB = UM_NT * a.Kpad * 2;
-    const uint32_t S = a.stages;
+    const uint32_t S = UM_STAGES;
     uint8_t* sA = smem;                     // 2 buffers
     uint8_t* sB = smem + 2 * bytesA;        // S stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)S * bytesB);
@@ -265,20 +294,24 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
     auto A_FULL = [&](uint32_t i) { return bar0 + 8 * (0 + i); };
     auto A_EMPTY = [&](uint32_t i) { return bar0 + 8 * (2 + i); };
     auto ACC_FULL = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (4 + 2 * g + b); };
-    auto B_FULL = [&](uint32_t i) { return bar0 + 8 * (8 + i); };
-    auto B_EMPTY = [&](uint32_t i) { return bar0 + 8 * (8 + UM_MAX_STAGES + i); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * UM_MAX_STAGES);
+    auto ACC_EMPTY = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (8 + 2 * g + b); };
+    auto B_FULL = [&](uint32_t i) { return bar0 + 8 * (12 + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * UM_MAX_STAGES);
+    const uint32_t flag0 = smem_u32(tmem_slot + 4);   // [0..3] accumulator releases (one per compute warp), [4] B tiles landed
+    auto ACC_FREE = [&](uint32_t g, uint32_t b) { return flag0 + 4 * (2 * g + b); };
+    const uint32_t B_READY = flag0 + 16;
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < 2; ++i) {
             mbar_init(A_FULL(i), 1);
             mbar_init(A_EMPTY(i), UM_WGS);
         }
-        for (uint32_t i = 0; i < 4; ++i) mbar_init(bar0 + 8 * (4 + i), 1);
-        for (uint32_t i = 0; i < S; ++i) {
-            mbar_init(B_FULL(i), 1);
-            mbar_init(B_EMPTY(i), 1);
+        for (uint32_t i = 0; i < 4; ++i) {
+            mbar_init(bar0 + 8 * (4 + i), 1);  // ACC_FULL: one tcgen05.commit
+            mbar_init(bar0 + 8 * (8 + i), 8);  // ACC_EMPTY: one arrive per compute warp of the warpgroup
         }
+        for (uint32_t i = 0; i < S; ++i) mbar_init(B_FULL(i), 1);
+        for (uint32_t i = 0; i < 5; ++i) tmem_slot[4 + i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -301,40 +334,83 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
                 mbar_expect_tx(A_FULL(ab), bytesA);
                 bulk_g2s(smem_u32(sA + ab * bytesA), reinterpret_cast<const uint8_t*>(a.A16) + (size_t)item.a_blob * bytesA, bytesA, A_FULL(ab));
                 for (uint32_t t = item.t0; t < item.t1; ++t, ++it) {
-                    const uint32_t s = it % S;
-                    mbar_wait(B_EMPTY(s), ((it / S) & 1) ^ 1);
+                    const uint32_t s = it & (UM_STAGES - 1);
+                    if (it >= UM_STAGES) {
+                        // the stage was last read by tile q = it - 4; its MMAs are done when its accumulator is full
+                        // (tile q belongs to warpgroup q & 1, is that group's (q >> 1)-th tile, buffer (q >> 1) & 1)
+                        const uint32_t q = it - UM_STAGES, jq = q >> 1;
+                        mbar_wait(ACC_FULL(q & 1, jq & 1), (jq >> 1) & 1);
+                    }
                     if (a.dbg & 4) { mbar_arrive(B_FULL(s)); continue; }
                     mbar_expect_tx(B_FULL(s), bytesB);
                     bulk_g2s(smem_u32(sB + (size_t)s * bytesB), reinterpret_cast<const uint8_t*>(a.B16) + (size_t)t * bytesB, bytesB, B_FULL(s));
                 }
             }
         }
+    } else if (warp <= UM_WGS) {
+        // ================= MMA issuer of warpgroup g = warp - 1 (one thread) =================
+        // Tiles with (global tile counter % UM_WGS) == g go to accumulators (g, 0) and (g, 1) alternately.
+        if (lane == 0) {
+            const uint32_t g = warp - 1;
+            const uint32_t idesc = ((KIND == 0 ? 1u : 2u) << 4) | ((uint32_t)(UM_NT >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
+            const uint32_t nk = (a.dbg & 2) ? 0u : a.Kpad / 16;
+            uint32_t it0 = 0, wi = 0, jb = 0; // jb: tiles this warpgroup has been given so far
+            for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x, ++wi) {
+                const WorkItem item = decode_item(a, w);
+                const uint32_t ab = wi & 1, n = item.t1 - item.t0;
+                const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
+                mbar_wait(A_FULL(ab), (wi >> 1) & 1);
+                const uint32_t a_addr = smem_u32(sA + ab * bytesA);
+                bool any = false;
+                // descriptors of the A tile for every K step (constant over the item)
+                uint64_t adesc[UM_MAX_NK];
+#pragma unroll
+                for (uint32_t kk = 0; kk < UM_MAX_NK; ++kk) adesc[kk] = make_desc(a_addr + kk * 2 * (UM_ROWS * 16), UM_ROWS * 16, 128);
+                for (uint32_t u = first; u < n; u += UM_WGS, ++jb) {
+                    const uint32_t gi = it0 + u, s = gi & (UM_STAGES - 1), buf = jb & 1;
+                    mbar_wait(ACC_EMPTY(g, buf), ((jb >> 1) & 1) ^ 1);   // all four warps have copied the previous use to registers
+                    mbar_wait(B_FULL(s), (gi / UM_STAGES) & 1);          // the tile's B stage has landed
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(sB + (size_t)s * bytesB);
+                    const uint32_t d_tmem = tmem_base + (g * 2 + buf) * UM_NT;
+#pragma unroll
+                    for (uint32_t kk = 0; kk < UM_MAX_NK; ++kk) {
+                        if (kk < nk) {
+                            // chunk-major blobs: K chunk c (8 halves = 16 bytes) of all rows is contiguous
+                            const uint64_t bdesc = make_desc(b_addr + kk * 2 * (UM_NT * 16), UM_NT * 16, 128);
+                            tc_mma<KIND>(d_tmem, adesc[kk], bdesc, idesc, kk > 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(ACC_FULL(g, buf)); // also tells the producer that stage s can be refilled
+                    any = true;
+                }
+                if (any) tc_commit(A_EMPTY(ab)); else mbar_arrive(A_EMPTY(ab));
+                it0 += n;
+            }
+        }
     } else {
-        // ================= compute warpgroups =================
-        // Warpgroup g owns accumulators (g,0) and (g,1) (128 TMEM columns each) and the tiles with
-        // (global tile counter % UM_WGS) == g.  Its elected thread issues the tcgen05.mma of the tile two
-        // steps ahead as soon as all four warps have copied the current accumulator to registers, so the
-        // tensor pipe works on tile t+1/t+2 while the warpgroup reduces tile t.  No separate MMA warp and
-        // no accumulator-empty barrier: the handoff latency is off the critical path.
-        const uint32_t g = (warp - 1) >> 2;
+        // ================= compute warps: TMEM -> registers -> row argmin =================
+        // Warpgroup g = 8 warps: warp (sp, h) reads TMEM lanes 32*sp..+31 (the sub-partition its warp id maps
+        // to) and columns h*64..+63 of the group's accumulators, i.e. every thread owns one row x 64 columns of a
+        // tile.  Four compute warps per SM sub-partition hide the TMEM-load and FMNMX3 latencies of each other;
+        // an accumulator goes back to the issuer as soon as all eight warps hold their part in registers.
+        const uint32_t cw = warp - 1 - UM_WGS;
+        const uint32_t g = cw >> 3;
+        const uint32_t h = (cw >> 2) & 1;             // column half
         const uint32_t sp = warp & 3;                 // TMEM sub-partition this warp may read
         const uint32_t lrow = sp * 32 + lane;         // row inside the tile == TMEM lane
-        const bool elected = ((warp - 1) & 3) == 0 && lane == 0;
-        const uint32_t idesc = ((KIND == 0 ? 1u : 2u) << 4) | ((uint32_t)(UM_NT >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
-        const uint32_t nk = (a.dbg & 2) ? 0u : a.Kpad / 16;
-        uint32_t it0 = 0, wi = 0;   // global tile counter at the start of the item, item counter
-        uint32_t nfull[2] = {0, 0}; // completed uses of accumulator (g, b) -> mbarrier parity
-        for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x, ++wi) {
+        const uint32_t lane_addr = tmem_base + ((sp * 32u) << 16) + h * UM_HALF;
+        uint32_t it0 = 0, jb = 0;
+        for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x) {
             const WorkItem item = decode_item(a, w);
-            const uint32_t ab = wi & 1;
             const uint32_t n = item.t1 - item.t0;
             const bool row_ok = lrow < item.nrows;
             const uint32_t grow = item.row0 + lrow;
             const uint32_t a2 = row_ok ? a.rowA2[grow >> 2] : 0u;
             RowState st;
             st.bestV = 3.0e38f; st.bestp = 0; st.bestcol = FE_NONE32; st.hit = FE_NONE32;
-            st.n_improve = st.n_full = st.n_warp_events = 0;
             st.vthr0 = -3.0e38f; st.vthr1 = -3.0e38f;
+            st.par_item = a.colpar + (size_t)item.t0 * (UM_NT / 32);
             if (a.use_thr && row_ok) { // n16 <= thr16  <=>  V <= floor((thr16 - a2 - p) / 2)
                 const long long tt = (long long)a.thr16 - (long long)a2;
                 long long f0 = tt >= 0 ? tt / 2 : -((-tt + 1) / 2);
@@ -344,71 +420,32 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
                 st.vthr0 = (float)f0;
                 st.vthr1 = (float)f1;
             }
-            // local tile indices of this warpgroup inside the item: u = first, first + UM_WGS, ...
             const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
-            const uint32_t a_addr = smem_u32(sA + ab * bytesA);
-            auto issue = [&](uint32_t u, uint32_t buf) { // elected thread only
-                const uint32_t gi = it0 + u, s = gi % S;
-                mbar_wait(B_FULL(s), (gi / S) & 1);
+            const uint32_t my_tiles = first < n ? (n - first + UM_WGS - 1) / UM_WGS : 0;
+            for (uint32_t j = 0; j < my_tiles; ++j, ++jb) {
+                const uint32_t u = first + j * UM_WGS, buf = jb & 1;
+                const uint32_t colbase = u * UM_NT + h * UM_HALF;
+                const uint32_t tile_valid = min((uint32_t)UM_NT, item.cols_left - u * UM_NT);
+                const uint32_t nvalid = tile_valid > h * UM_HALF ? min((uint32_t)UM_HALF, tile_valid - h * UM_HALF) : 0u;
+                const uint32_t* par = a.colpar + (size_t)(item.t0 + u) * (UM_NT / 32) + h * (UM_HALF / 32);
+                uint32_t v[UM_HALF];
+                mbar_wait(ACC_FULL(g, buf), (jb >> 1) & 1);
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(sB + (size_t)s * bytesB);
-                const uint32_t d_tmem = tmem_base + (g * 2 + buf) * UM_NT;
-                for (uint32_t kk = 0; kk < nk; ++kk) {
-                    // chunk-major blobs: K chunk c (8 halves = 16 bytes) of all rows is contiguous
-                    const uint64_t adesc = make_desc(a_addr + kk * 2 * (UM_ROWS * 16), UM_ROWS * 16, 128);
-                    const uint64_t bdesc = make_desc(b_addr + kk * 2 * (UM_NT * 16), UM_NT * 16, 128);
-                    tc_mma<KIND>(d_tmem, adesc, bdesc, idesc, kk > 0 ? 1u : 0u);
-                }
-                tc_commit(B_EMPTY(s));
-                tc_commit(ACC_FULL(g, buf));
-            };
-            uint32_t my_tiles = first < n ? (n - first + UM_WGS - 1) / UM_WGS : 0;
-            if (elected) {
-                mbar_wait(A_FULL(ab), (wi >> 1) & 1);
-                if (my_tiles > 0) issue(first, 0);
-            }
-            // buffer sequence inside an item always starts at 0: both buffers are idle at item boundaries
-            if (elected && my_tiles > 1) issue(first + UM_WGS, 1);
-            for (uint32_t j = 0; j < my_tiles; ++j) {
-                const uint32_t u = first + j * UM_WGS, buf = j & 1;
-                mbar_wait(ACC_FULL(g, buf), nfull[buf] & 1);
-                ++nfull[buf];
-                tc_fence_after();
-                uint32_t v[UM_NT];
                 if (!(a.dbg & 1)) {
-                    const uint32_t taddr = tmem_base + ((sp * 32u) << 16) + (g * 2 + buf) * UM_NT;
+                    const uint32_t taddr = lane_addr + (g * 2 + buf) * UM_NT;
                     TMEM_LD32(taddr, (v + 0));
                     TMEM_LD32(taddr + 32, (v + 32));
-                    TMEM_LD32(taddr + 64, (v + 64));
-                    TMEM_LD32(taddr + 96, (v + 96));
                     tmem_wait_ld();
-                } else {
-#pragma unroll
-                    for (int i = 0; i < UM_NT; ++i) v[i] = 0;
                 }
                 tc_fence_before();
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); // all four warps hold the tile in registers
-                if (elected && j + 2 < my_tiles) issue(u + 2 * UM_WGS, buf);
-                const uint32_t colbase = u * UM_NT;
-                const uint32_t nvalid = min((uint32_t)UM_NT, item.cols_left - colbase);
-                if (a.dbg & 8) {
-                    uint32_t x = 0;
-#pragma unroll
-                    for (int i = 0; i < UM_NT; ++i) x ^= v[i];
-                    if (x == 0x12345u) st.bestcol = 0; // keep the loads alive
-                } else if (!(a.dbg & 1)) process_tile(v, st, row_ok, colbase, nvalid, a.colpar + (size_t)(item.t0 + u) * (UM_NT / 32));
-            }
-            // this warpgroup is done with the A buffer once its last MMAs have completed
-            if (elected) {
-                if (my_tiles > 0) tc_commit(A_EMPTY(ab)); else mbar_arrive(A_EMPTY(ab));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ACC_EMPTY(g, buf));
+                if (!(a.dbg & 1)) process_half(v, st, row_ok, colbase, nvalid, par);
             }
             it0 += n;
-            if (a.dbg & 16) {
-                atomicAdd(a.flags + 4, st.n_improve); atomicAdd(a.flags + 5, st.n_full);
-                if (lane == 0) { atomicAdd(a.flags + 6, st.n_warp_events); atomicAdd(a.flags + 7, my_tiles); }
-            }
             if (row_ok) {
                 if (st.bestcol != FE_NONE32) {
+                    if (st.bestp == 2) st.bestp = row_parity(st, st.bestcol);
                     const long long n16 = (long long)a2 + 2ll * (long long)st.bestV + (long long)st.bestp;
                     const unsigned long long key = ((unsigned long long)(uint32_t)n16 << 32) | (unsigned long long)(item.col0 + st.bestcol);
                     atomicMin(&a.rowbest[grow], key);
@@ -588,10 +625,10 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     a.use_thr = use_thr ? 1u : 0u;
     { const char* e = getenv("FE_UMMA_DBG"); a.dbg = e ? (uint32_t)atoi(e) : 0u; }
     const uint32_t stage_bytes = UM_NT * Kpad * 2, a_bytes = 2 * UM_ROWS * Kpad * 2;
-    uint32_t stages = (kStagesMaxBytes - a_bytes) / stage_bytes;
-    stages = std::max(2u, std::min((uint32_t)UM_MAX_STAGES, stages));
+    const uint32_t stages = UM_STAGES;
     a.stages = stages;
-    const size_t smem = (size_t)a_bytes + (size_t)stages * stage_bytes + (8 + 2 * UM_MAX_STAGES) * 8 + 16;
+    if (Kpad / 16 > UM_MAX_NK) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "umma: K too large");
+    const size_t smem = (size_t)a_bytes + (size_t)stages * stage_bytes + (12 + 2 * UM_MAX_STAGES) * 8 + 64;
     FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const uint32_t grid = (uint32_t)std::min<uint64_t>(total_items, 148);
     k_search_umma<0><<<grid, UM_THREADS, smem, ctx->stream>>>(a);
@@ -601,10 +638,12 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     FE_CUDA(ctx, cudaMemcpyAsync(&f, flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *inexact = (f & 1u) != 0;
-    if (a.dbg & 16) {
-        uint32_t c[8];
-        cudaMemcpy(c, ctx->b_counters.p, sizeof(c), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[umma dbg] T=%u lane-improvements=%u full-scans=%u warp-events=%u warp-tiles=%u\n", g.T, c[4 + 2], c[5 + 2], c[6 + 2], c[7 + 2]);
+    if (a.dbg & 32) {
+        unsigned long long c[6];
+        cudaMemcpy(c, flags + 2, sizeof(c), cudaMemcpyDeviceToHost);
+        const double nt = (double)std::max<unsigned long long>(1, c[5]);
+        fprintf(stderr, "[umma prof] T=%u per warp-tile cycles: wait_ldA %.0f  procA %.0f  wait_ldB %.0f  release+wait_full+issue %.0f  procB %.0f  (tiles %.0f)\n",
+                g.T, c[0] / nt, c[1] / nt, c[2] / nt, c[3] / nt, c[4] / nt, nt);
     }
     return FE_OK;
 }

@@ -7,8 +7,11 @@
 constexpr int UM_NT = 128;         // domain columns per tile (UMMA N)
 constexpr int UM_ROWS = 128;       // rows per tile = 32 ranges x 4 rotations (UMMA M)
 constexpr int UM_WGS = 2;          // compute warpgroups (each owns 2 TMEM accumulators of UM_NT columns)
-constexpr int UM_THREADS = 32 + 128 * UM_WGS; // producer warp + compute warpgroups
+constexpr int UM_HALF = UM_NT / 2;   // columns a compute thread holds per register set
+constexpr int UM_THREADS = 32 + 32 * UM_WGS + 256 * UM_WGS; // producer warp, one MMA-issuer warp per group, 8 compute warps per group
 constexpr int UM_MAX_STAGES = 8;
+constexpr int UM_STAGES = 4;       // B stages: tile t reuses the stage of tile t-4, freed by that tile's accumulator-full commit
+constexpr int UM_MAX_NK = 5;       // K steps of 16 per tile: T=4 -> 2, T=8 -> 5
 
 struct UmmaBucket {
     uint32_t row_tile0, n_row_tiles; // A blobs of this classifier bucket
