@@ -61,7 +61,7 @@ _LIB = None
 EXPORTS = [
     "fe_abi_version", "fe_create", "fe_destroy", "fe_last_error", "fe_set_image", "fe_set_images", "fe_set_image_device",
     "fe_classify", "fe_encode_level", "fe_encode_quadtree", "fe_encode_quadtree_device", "fe_fetch_items", "fe_device_items",
-    "fe_decode", "fe_quantize", "fe_get_stats", "fe_stats_reset", "fe_synchronize", "fe_set_synthetic_image", "fe_get_image",
+    "fe_decode", "fe_copy_items", "fe_quantize", "fe_get_stats", "fe_stats_reset", "fe_synchronize", "fe_set_synthetic_image", "fe_get_image",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library():
         "fe_fetch_items": (i32, [vp, vp, sz, C.POINTER(sz)]),
         "fe_device_items": (vp, [vp, C.POINTER(sz)]),
         "fe_decode": (i32, [vp, vp, sz, vp, u32, u32, u32, i32, dbl, i32, C.POINTER(C.c_int), C.POINTER(dbl)]),
+        "fe_copy_items": (i32, [vp, vp, vp, u32, u32, u32, vp, sz, i32]),
         "fe_quantize": (i32, [vp, vp, sz, i32, i32, vp, vp, vp]),
         "fe_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "fe_stats_reset": (i32, [vp]),
@@ -228,6 +229,15 @@ class Context:
         self._check(self.lib.fe_decode(self.h, items.ctypes.data, len(items), tgt.ctypes.data, W, H, stride, max_iters, eps,
                                        int(fma), C.byref(it), C.byref(rms)))
         return tgt[:, :W], it.value, rms.value
+
+    def copy_items(self, source: np.ndarray, target: np.ndarray, items: np.ndarray, fma: bool = False) -> np.ndarray:
+        """One Decoder2::decodeStep: target[item] = clamp(trunc(s * sample(source) + o)); returns the new target."""
+        items = np.ascontiguousarray(items, ENCODE_ITEM)
+        source = np.ascontiguousarray(source, np.uint8)
+        out = np.ascontiguousarray(target, np.uint8).copy()
+        H, W = out.shape
+        self._check(self.lib.fe_copy_items(self.h, source.ctypes.data, out.ctypes.data, W, H, W, items.ctypes.data, len(items), int(fma)))
+        return out
 
     def quantize(self, items: np.ndarray, bits_s: int = 5, bits_o: int = 7):
         items = np.ascontiguousarray(items, ENCODE_ITEM)

@@ -589,6 +589,43 @@ extern "C" int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uin
     return FE_OK;
 }
 
+extern "C" int fe_copy_items(fe_ctx* ctx, const uint8_t* source, uint8_t* target, uint32_t width, uint32_t height, uint32_t stride,
+                             const fe_encode_item* items, size_t n, int use_fma) {
+    if (!ctx) return FE_ERR_INVALID;
+    if (!source || !target || (!items && n) || !width || !height || stride < width) return fe_fail(ctx, FE_ERR_INVALID, "fe_copy_items: bad arguments");
+    if (n > 0x7FFFFFFFu) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_copy_items: too many items");
+    std::vector<uint32_t> pix_off(n + 1, 0);
+    uint64_t area = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const fe_encode_item& e = items[i];
+        if (!e.w || !e.h || e.x + e.w > width || e.y + e.h > height) return fe_fail(ctx, FE_ERR_INVALID, "fe_copy_items: item %zu outside the image", i);
+        if (e.src_w && (e.src_w != e.src_h || e.match_x + e.src_w > width || e.match_y + e.src_h > height || e.transform < 0 || e.transform > 7 || e.src_w < 2))
+            return fe_fail(ctx, FE_ERR_INVALID, "fe_copy_items: item %zu has an invalid source block", i);
+        pix_off[i] = (uint32_t)area;
+        area += (uint64_t)e.w * e.h;
+    }
+    if (area > 0xFFFFFFFFull) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_copy_items: item areas overflow");
+    pix_off[n] = (uint32_t)area;
+    const size_t bytes = (size_t)height * stride;
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    FE_CUDA(ctx, ctx->b_dec_a.ensure(bytes + 64));
+    FE_CUDA(ctx, ctx->b_dec_b.ensure(bytes + 64));
+    FE_CUDA(ctx, ctx->b_dec_items.ensure(n * sizeof(fe_encode_item) + (n + 1) * 4 + 64));
+    fe_encode_item* d_items = ctx->b_dec_items.as<fe_encode_item>();
+    uint32_t* d_off = reinterpret_cast<uint32_t*>(d_items + n);
+    FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_dec_a.p, source, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_dec_b.p, target, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+        FE_CUDA(ctx, cudaMemcpyAsync(d_items, items, n * sizeof(fe_encode_item), cudaMemcpyHostToDevice, ctx->stream));
+        FE_CUDA(ctx, cudaMemcpyAsync(d_off, pix_off.data(), (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(ctx, k_decode_step, cdiv(area, 256), 256, ctx->b_dec_a.as<uint8_t>(), ctx->b_dec_b.as<uint8_t>(), stride, d_items, d_off, (uint32_t)n,
+               (uint32_t)area, use_fma);
+    }
+    FE_CUDA(ctx, cudaMemcpyAsync(target, ctx->b_dec_b.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FE_OK;
+}
+
 // -------------------------------------------------------------------------------------------------
 // quantizer post-pass
 // -------------------------------------------------------------------------------------------------

@@ -1,0 +1,3 @@
+// Drop-in forwarding header: same include path as the reference's encode/Encoder2.hpp; the implementation lives in frac_b200/encode.hpp.
+#pragma once
+#include "frac_b200/encode.hpp"

@@ -155,6 +155,12 @@ int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uint8_t* targe
               uint32_t height, uint32_t stride, int max_iters, double rms_eps, int fma,
               int* iterations, double* rms);
 
+/* Replaces: Frac::copy (encode/DecodeUtils.hpp:9-25) / Decoder2::decodeStep (encode/Encoder2.hpp:91-99):
+ * one pass target[item] = clamp(trunc(s * sample(source, item) + o)) over n items with an explicit
+ * source plane.  `source` and `target` are host planes of the same width/height/stride; target is in/out. */
+int fe_copy_items(fe_ctx* ctx, const uint8_t* source, uint8_t* target, uint32_t width, uint32_t height,
+                  uint32_t stride, const fe_encode_item* items, size_t n, int fma);
+
 /* Replaces: the Quantizer post-pass of main.cpp:106-140 (encode/Quantizer.hpp:13-36):
  * min/max over the list, then quantized(contrast) with bits_s bits and
  * quantized(brightness) with bits_o bits.  minmax_out = {min_s, max_s, min_o, max_o}. */
