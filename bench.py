@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--tmax", type=int, default=32)
     ap.add_argument("--tmin", type=int, default=4)
-    ap.add_argument("--thr", type=float, default=float(os.environ.get("FE_BENCH_THR", "12")))
+    ap.add_argument("--thr", type=float, default=float(os.environ.get("FE_BENCH_THR", "25")))
     ap.add_argument("--classifier", type=int, default=0)
     ap.add_argument("--search", type=int, default=0, help="0 auto, 1 exact integer path, 2 tcgen05 path")
     ap.add_argument("--cpu-blocks", type=int, default=0, help="range blocks per level in the CPU sample (0: 2 x cores)")
