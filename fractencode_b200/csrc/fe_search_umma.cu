@@ -62,12 +62,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU -- trap after ~2 s instead.
+// Bounded wait: a protocol bug must not hang the GPU -- trap after ~2^26 probes (each probe suspends the warp in
+// hardware for up to the mbarrier time limit) instead of spinning forever.  No clock reads in the loop: the
+// spinning producer/issuer warps share their SM sub-partition's ALU pipe with the compute warps.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t probes = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();
+        if (++probes > (1u << 26)) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
