@@ -233,6 +233,93 @@ static int bucket_by_class(fe_ctx* ctx, const int32_t* d_cls, uint32_t n, DevBuf
     return FE_OK;
 }
 
+// fp32-regime re-rank (SURVEY hard part 2): ranges whose best SSE is >= 2^20 are re-scored with the reference's
+// rounded fp32 running sum over every candidate inside the rounding band of the exact minimum.  Rare (noise-like or
+// saturated blocks at T >= 16); runs the exact integer kernel on the flagged ranges only.
+static int rerank_fp32_regime(fe_ctx* ctx, const LevelIO& io, const fe_params& p, const uint32_t* dom_order, const uint32_t* rng_order,
+                              const uint32_t doff[8], const uint32_t roff[8], int nbuckets) {
+    const LevelGeom& g = io.g;
+    const uint32_t nR = io.nR, nD = io.nD;
+    std::vector<uint32_t> bound(nR), order;
+    FE_CUDA(ctx, cudaMemcpyAsync(bound.data(), ctx->b_bound.p, (size_t)nR * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rng_order) {
+        order.resize(nR);
+        FE_CUDA(ctx, cudaMemcpyAsync(order.data(), rng_order, (size_t)nR * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> flag_idx, flag_bound;
+    uint32_t foff[8] = {0};
+    for (int c = 0; c < nbuckets; ++c) {
+        for (uint32_t j = roff[c]; j < roff[c + 1]; ++j)
+            if (bound[j]) {
+                flag_idx.push_back(rng_order ? order[j] : j);
+                flag_bound.push_back(bound[j]);
+            }
+        foff[c + 1] = (uint32_t)flag_idx.size();
+    }
+    const uint32_t nF = (uint32_t)flag_idx.size();
+    if (!nF) return FE_OK;
+    const uint32_t npool = g.fast ? 1u : 4u;
+    FE_CUDA(ctx, ctx->b_flag_idx.ensure((size_t)nF * 8 + 16));
+    uint32_t* d_idx = ctx->b_flag_idx.as<uint32_t>();
+    uint32_t* d_bound = d_idx + nF;
+    FE_CUDA(ctx, cudaMemcpyAsync(d_idx, flag_idx.data(), (size_t)nF * 4, cudaMemcpyHostToDevice, ctx->stream));
+    FE_CUDA(ctx, cudaMemcpyAsync(d_bound, flag_bound.data(), (size_t)nF * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // exact-path operands: rows of the flagged ranges only, the whole (sorted) pool
+    FE_CUDA(ctx, ctx->b_A.ensure((size_t)nF * 4 * g.Npad));
+    FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)std::max(nF, nR) * 4));
+    FE_CUDA(ctx, ctx->b_Blo.ensure((size_t)nD * npool * g.Npad));
+    FE_CUDA(ctx, ctx->b_Bhi.ensure((size_t)nD * npool * g.Npad));
+    FE_CUDA(ctx, ctx->b_coln.ensure((size_t)nD * npool * 4));
+    LAUNCH(ctx, k_build_rows, cdiv((uint64_t)nF * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, d_idx, nF, g.T, g.Npad, g.fast ? 1 : 0,
+           ctx->b_A.as<uint8_t>(), ctx->b_rowc.as<uint32_t>());
+    LAUNCH(ctx, k_build_pool, cdiv((uint64_t)nD * npool * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, dom_order, nD, npool, g.T, g.rho,
+           g.Npad, ctx->b_Blo.as<uint8_t>(), ctx->b_Bhi.as<uint8_t>(), ctx->b_coln.as<uint32_t>());
+    LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nF * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nF * 4);
+    for (int c = 0; c < nbuckets; ++c) {
+        const uint32_t rc = foff[c + 1] - foff[c], dc = doff[c + 1] - doff[c];
+        if (!rc || !dc) continue;
+        SearchArgs a{};
+        a.A = ctx->b_A.as<uint8_t>();
+        a.Blo = ctx->b_Blo.as<uint8_t>();
+        a.Bhi = ctx->b_Bhi.as<uint8_t>();
+        a.rowc = ctx->b_rowc.as<uint32_t>();
+        a.coln = ctx->b_coln.as<uint32_t>();
+        a.rowbest = ctx->b_rowbest.as<unsigned long long>();
+        a.rowhit = ctx->b_rowhit.as<uint32_t>();
+        a.row0 = foff[c] * 4; a.nrows = rc * 4;
+        a.col0 = doff[c]; a.ncols = dc;
+        a.Npad = g.Npad;
+        a.pool_stride_cols = g.fast ? 0 : nD;
+        a.rowbound = d_bound;
+        a.src = ctx->src.px; a.src_stride = ctx->src.stride;
+        a.tgt = ctx->tgt.px; a.tgt_stride = ctx->tgt.stride;
+        a.dom = io.d_dom; a.dom_order = dom_order;
+        a.rng = io.d_rng; a.row_range = d_idx;
+        a.rho = g.rho;
+        FE_CUDA(ctx, launch_search_exact(ctx, a, true));
+    }
+    FinalizeArgs f{};
+    f.src = ctx->src.px; f.src_stride = ctx->src.stride;
+    f.tgt = ctx->tgt.px; f.tgt_stride = ctx->tgt.stride;
+    f.dom = io.d_dom; f.rng = io.d_rng;
+    f.dom_order = dom_order; f.rng_order = d_idx;
+    f.rowbest = ctx->b_rowbest.as<unsigned long long>();
+    f.rowhit = ctx->b_rowhit.as<uint32_t>();
+    f.n = nF;
+    f.use_thr = 0;
+    f.thr = p.rms_threshold; f.s_max = p.s_max; f.fma = p.fma;
+    f.can_split = io.can_split;
+    f.out = io.d_out; f.split = io.d_split;
+    f.mismatch = ctx->b_counters.as<uint32_t>() + 8;
+    f.fp32_regime = ctx->b_counters.as<uint32_t>() + 9;
+    f.bound_out = nullptr;
+    f.rerank = 1;
+    LAUNCH(ctx, k_finalize, cdiv((uint64_t)nF * 32, 256), 256, f);
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FE_OK;
+}
+
 static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     const LevelGeom& g = io.g;
     const uint32_t nR = io.nR, nD = io.nD;
@@ -260,6 +347,8 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
         nbuckets = 7;
     }
 
+    if (p.rms_threshold * (double)(g.S * g.S) >= 1048576.0)
+        return fe_fail(ctx, FE_ERR_UNSUPPORTED, "rms_threshold %g reaches the fp32-rounding regime of the reference distance (SSE >= 2^20) at S=%u", p.rms_threshold, g.S);
     uint32_t thr16 = 0;
     const bool use_thr = threshold_n16(p.rms_threshold, g.S, &thr16);
     uint64_t matches = 0;
@@ -268,23 +357,30 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     FE_CUDA(ctx, ctx->b_rowhit.ensure((size_t)nR * 4 * 4));
     FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)nR * 4));
 
-    bool use_umma = p.search_impl != FE_SEARCH_EXACT && nD && umma_level_supported(g);
-    if (p.search_impl == FE_SEARCH_UMMA && nD && !umma_level_supported(g))
-        return fe_fail(ctx, FE_ERR_UNSUPPORTED, "tcgen05 path needs S == 2T, even domain origins and T in {4, 8} (got S=%u T=%u)", g.S, g.T);
+    const bool f16_ok = nD && umma_level_supported(g), i8_ok = nD && umma_i8_level_supported(g);
+    if (p.search_impl == FE_SEARCH_UMMA && nD && !f16_ok && !i8_ok)
+        return fe_fail(ctx, FE_ERR_UNSUPPORTED, "tcgen05 paths need S == 2T, even domain origins and T <= 32 (got S=%u T=%u)", g.S, g.T);
     bool searched = false;
-    if (use_umma) {
-        // ---- tcgen05 path: fp16 operand blobs + fused contraction/argmin ----
+    if (p.search_impl != FE_SEARCH_EXACT && (f16_ok || i8_ok)) {
         LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
         LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
-        bool inexact = false;
-        FE_TRY(umma_prepare_and_search(ctx, g, io.d_dom, io.d_rng, dom_order, rng_order, doff, roff, nbuckets, thr16, use_thr, &inexact,
-                                       timed ? ctx->ev[1] : nullptr));
-        if (!inexact) {
-            searched = true;
-            ctx->stats.umma_levels++;
-        } else if (p.search_impl == FE_SEARCH_UMMA) {
-            return fe_fail(ctx, FE_ERR_UNSUPPORTED, "tcgen05 path: a winner lies in the fp32-inexact band (V >= 2^24 - 64); use FE_SEARCH_AUTO");
+        bool inexact = !f16_ok;
+        if (f16_ok) {
+            // ---- tcgen05 kind::f16 (T = 4, 8): fp16 operand blobs, integer-exact fp32 accumulators, fused argmin ----
+            FE_TRY(umma_prepare_and_search(ctx, g, io.d_dom, io.d_rng, dom_order, rng_order, doff, roff, nbuckets, thr16, use_thr, &inexact,
+                                           timed ? ctx->ev[1] : nullptr));
+            if (inexact) { // a winner in the fp32-inexact band: redo the level on the always-exact int8 kind
+                LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
+                LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
+            }
         }
+        if (inexact) {
+            // ---- tcgen05 kind::i8 (T >= 16, or the fallback above): u8 operands, exact s32 accumulators ----
+            FE_TRY(umma_i8_prepare_and_search(ctx, g, io.d_dom, io.d_rng, dom_order, rng_order, doff, roff, nbuckets, thr16, use_thr,
+                                              timed ? ctx->ev[1] : nullptr));
+        }
+        searched = true;
+        ctx->stats.umma_levels++;
     }
     if (!searched) {
         // ---- exact integer path: u8 rows, low/high byte pools, dp4a ----
@@ -342,6 +438,9 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     f.out = io.d_out; f.split = io.d_split;
     f.mismatch = ctx->b_counters.as<uint32_t>();
     f.fp32_regime = ctx->b_counters.as<uint32_t>() + 1;
+    FE_CUDA(ctx, ctx->b_bound.ensure((size_t)nR * 4 + 4));
+    f.bound_out = ctx->b_bound.as<uint32_t>();
+    f.rerank = 0;
     LAUNCH(ctx, k_finalize, cdiv((uint64_t)nR * 32, 256), 256, f);
     if (timed) cudaEventRecord(ctx->ev[3], ctx->stream);
 
@@ -350,6 +449,7 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (counters[0]) return fe_fail(ctx, FE_ERR_CUDA, "internal: %u winners whose search score disagrees with the direct recomputation (T=%u)", counters[0], g.T);
     ctx->stats.fp32_regime_items += counters[1];
+    if (counters[1]) FE_TRY(rerank_fp32_regime(ctx, io, p, dom_order, rng_order, doff, roff, nbuckets));
     if (timed) {
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.level_prep_ms[io.stat_level] = ms;

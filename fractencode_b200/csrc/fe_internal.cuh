@@ -62,6 +62,14 @@ struct SearchArgs {
     uint32_t pool_stride_cols; // columns per rotation pool (generic geometry: 4 pools), 0 when fast
     uint32_t thr16;
     uint32_t use_thr;
+    // fp32-regime re-rank pass (reference distance = fp32 running sum, image/metrics.h:38-49): candidates with
+    // n16 <= rowbound[row >> 2] are scored by the emulated float sum instead (key = float bits << 32 | column)
+    const uint32_t* rowbound;
+    const uint8_t* src; uint32_t src_stride;
+    const uint8_t* tgt; uint32_t tgt_stride;
+    const fe_grid_item* dom; const uint32_t* dom_order; // column -> domain item
+    const fe_grid_item* rng; const uint32_t* row_range; // row >> 2 -> range item index
+    uint32_t rho;
 };
 
 struct fe_ctx {
@@ -74,7 +82,7 @@ struct fe_ctx {
     // level scratch
     DevBuf b_dom, b_rng, b_dom_cls, b_rng_cls, b_dom_order, b_rng_order, b_sort_tmp, b_keys_tmp, b_vals_tmp;
     DevBuf b_A, b_Blo, b_Bhi, b_rowc, b_coln, b_rowbest, b_rowhit, b_hist, b_level_items, b_split, b_scan, b_scan_tmp;
-    DevBuf b_rng_next, b_counters;
+    DevBuf b_rng_next, b_counters, b_bound, b_flag_idx;
     // tcgen05 path operands
     DevBuf b_A16, b_B16, b_tmaps;
     // results
@@ -100,6 +108,6 @@ int fe_fail(fe_ctx* ctx, int code, const char* fmt, ...);
     } while (0)
 
 // ---- kernels' host launchers (each returns a cudaError_t from cudaGetLastError) ----
-cudaError_t launch_search_exact(fe_ctx* ctx, const SearchArgs& a);
+cudaError_t launch_search_exact(fe_ctx* ctx, const SearchArgs& a, bool rerank = false);
 // tcgen05 path (fe_search_umma.cu). Returns FE_OK / FE_ERR_*.
 int umma_level_supported(const LevelGeom& g);

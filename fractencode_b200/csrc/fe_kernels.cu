@@ -230,11 +230,28 @@ __global__ void k_build_pool(const uint8_t* __restrict__ img, uint32_t stride, c
 // for T <= 64.  Per row: packed-key argmin (n16 << 32 | col) and first col with n16 <= thr16.
 // Tile 128 rows x 64 cols per CTA, 256 threads, 8x4 outputs per thread, K in chunks of 16 words.
 // ---------------------------------------------------------------------------------------------
+// The reference's distance for one (range, domain, rotation): fp32 running sum over the block, row-major
+// (image/metrics.h:38-49); v*v is exact in fp32 so only the additions round.
+__device__ float float_seq_sse(const uint8_t* __restrict__ tgt, uint32_t tstride, const fe_grid_item& r, const uint8_t* __restrict__ src,
+                               uint32_t sstride, const fe_grid_item& dm, uint32_t rho, int k) {
+    float sum = 0.0f;
+    const uint32_t T = r.w;
+    for (uint32_t ty = 0; ty < T; ++ty)
+        for (uint32_t tx = 0; tx < T; ++tx) {
+            const float a = (float)tgt[(size_t)(r.y + ty) * tstride + r.x + tx];
+            const float d = (float)sample_sum4(src, sstride, dm.x, dm.y, dm.w, tx * rho, ty * rho, k) * 0.25f;
+            const float v = __fsub_rn(a, d);
+            sum = __fadd_rn(sum, __fmul_rn(v, v));
+        }
+    return sum;
+}
+
 #define SX_TM 128
 #define SX_TN 64
 #define SX_KW 16
 #define SX_APAD 132
 
+template <bool RERANK>
 __global__ void __launch_bounds__(256) k_search_exact(SearchArgs a) {
     __shared__ __align__(16) uint32_t As[SX_KW][SX_APAD];
     __shared__ __align__(16) uint32_t Bl[SX_KW][SX_TN];
@@ -250,13 +267,15 @@ __global__ void __launch_bounds__(256) k_search_exact(SearchArgs a) {
     const uint32_t* coln = a.coln + (size_t)pool * a.pool_stride_cols;
 
     unsigned long long best[8];
-    uint32_t hit[8], rc[8];
+    uint32_t hit[8], rc[8], bound[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         best[i] = FE_INF64;
         hit[i] = FE_NONE32;
         const uint32_t r = row_base + ty * 8 + i;
-        rc[i] = (ty * 8 + i < rows_here) ? a.rowc[r >> 2] : 0u;
+        const bool ok = ty * 8 + i < rows_here;
+        rc[i] = ok ? a.rowc[r >> 2] : 0u;
+        bound[i] = (RERANK && ok) ? a.rowbound[r >> 2] : 0u;
     }
 
     for (uint32_t ct = 0; ct < a.ncols; ct += SX_TN) {
@@ -316,9 +335,21 @@ __global__ void __launch_bounds__(256) k_search_exact(SearchArgs a) {
                 for (int i = 0; i < 8; ++i) {
                     const uint32_t cross = lo[i][j] + (hi[i][j] << 8);
                     const uint32_t n16 = rc[i] - 8u * cross + cn;
-                    const unsigned long long key = ((unsigned long long)n16 << 32) | gc;
-                    best[i] = key < best[i] ? key : best[i];
-                    if (a.use_thr && n16 <= a.thr16) hit[i] = min(hit[i], gc);
+                    if (RERANK) {
+                        if (ty * 8 + i < rows_here && n16 <= bound[i]) { // near-minimal candidate: score it like the reference does
+                            const uint32_t r = row_base + ty * 8 + i;
+                            const fe_grid_item rg = a.rng[a.row_range[r >> 2]];
+                            const fe_grid_item dm = a.dom[a.dom_order ? a.dom_order[gc] : gc];
+                            const int k = a.pool_stride_cols ? (int)pool : (int)(r & 3u);
+                            const float f = float_seq_sse(a.tgt, a.tgt_stride, rg, a.src, a.src_stride, dm, a.rho, k);
+                            const unsigned long long key = ((unsigned long long)__float_as_uint(f) << 32) | gc;
+                            best[i] = key < best[i] ? key : best[i];
+                        }
+                    } else {
+                        const unsigned long long key = ((unsigned long long)n16 << 32) | gc;
+                        best[i] = key < best[i] ? key : best[i];
+                        if (a.use_thr && n16 <= a.thr16) hit[i] = min(hit[i], gc);
+                    }
                 }
             }
         }
@@ -344,10 +375,11 @@ __global__ void __launch_bounds__(256) k_search_exact(SearchArgs a) {
     }
 }
 
-cudaError_t launch_search_exact(fe_ctx* ctx, const SearchArgs& a) {
+cudaError_t launch_search_exact(fe_ctx* ctx, const SearchArgs& a, bool rerank) {
     if (a.nrows == 0 || a.ncols == 0) return cudaSuccess;
     dim3 grid((a.nrows + SX_TM - 1) / SX_TM, a.pool_stride_cols ? 4 : 1);
-    k_search_exact<<<grid, 256, 0, ctx->stream>>>(a);
+    if (rerank) k_search_exact<true><<<grid, 256, 0, ctx->stream>>>(a);
+    else k_search_exact<false><<<grid, 256, 0, ctx->stream>>>(a);
     ctx->stats.kernel_launches++;
     return cudaGetLastError();
 }
@@ -386,6 +418,7 @@ __global__ void k_finalize(FinalizeArgs f) {
         for (int k = 0; k < 4; ++k) {
             const unsigned long long key = f.rowbest[4 * j + k];
             if (key == FE_INF64) continue;
+            // normal pass: n16; re-rank pass: bits of the emulated fp32 sum (monotone for non-negative floats)
             const uint32_t n16 = (uint32_t)(key >> 32), col = (uint32_t)key;
             const uint32_t d = f.dom_order ? f.dom_order[col] : col;
             if (wk < 0 || n16 < bn || (n16 == bn && d <= bd)) {
@@ -429,11 +462,27 @@ __global__ void k_finalize(FinalizeArgs f) {
     wn16 = 16u * sA2 - 8u * sAB + sB2; // exact for T <= 64
     if (lane != 0) return;
     // self-check of the search kernel's arithmetic against the direct recomputation
-    if (from_min) {
+    if (f.rerank) {
+        // keys are float sums here; nothing to cross-check against the integer recomputation
+    } else if (from_min) {
         const unsigned long long key = f.rowbest[4 * j + wk];
         if ((uint32_t)(key >> 32) != wn16) atomicAdd(f.mismatch, 1u);
     } else if (wn16 > f.thr16) {
         atomicAdd(f.mismatch, 1u);
+    }
+    if (f.bound_out) {
+        // fp32 regime (SSE >= 2^20): the reference ranks candidates by a ROUNDED running sum, so every candidate whose
+        // exact score lies within the worst-case rounding band of the exact minimum must be re-scored.
+        // |fl_seq(S) - S| <= N * ulp(S) / 2; band = 2 * N * ulp(S_min) in SSE units = 32 * N * ulp in n16 units.
+        uint32_t b = 0;
+        if (wn16 >= (1u << 24) && from_min) {
+            const float smin = (float)(wn16 >> 4);
+            const float ulp = __uint_as_float((__float_as_uint(smin) & 0x7F800000u) - (23u << 23));
+            const double band = 32.0 * (double)N * (double)ulp;
+            const double bb = (double)wn16 + band;
+            b = bb >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)bb;
+        }
+        f.bound_out[j] = b;
     }
     double distance;
     if (wn16 < (1u << 24)) {

@@ -21,6 +21,8 @@ struct FinalizeArgs {
     uint32_t* split;                // NULL or per-range-index split flag
     uint32_t* mismatch;             // device counter: search n16 != recomputed n16
     uint32_t* fp32_regime;          // device counter: winners with SSE >= 2^20
+    uint32_t* bound_out;            // NULL or [range position]: 0, or the n16 bound of the re-rank band for fp32-regime ranges
+    int rerank;                     // rowbest keys hold float bits (re-rank pass)
 };
 
 __global__ void k_uniform_grid(fe_grid_item* out, uint32_t nx, uint32_t n, uint32_t size, uint32_t step);

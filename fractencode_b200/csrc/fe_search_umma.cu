@@ -15,11 +15,12 @@
 // the level on the exact integer kernel (only pathological images: best match worse than ~180 grey
 // levels rms).  tests/test_gpu_umma.py holds the max-magnitude known-answer test.
 //
-// Kernel anatomy (one CTA per SM, persistent over work items = (row tile, column chunk)):
-//   warp 0     : bulk-async (TMA engine, cp.async.bulk) producer: A blob per work item, B blob per tile
-//   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer, 2 accumulators x 256 columns
-//   warps 2..9 : two epilogue warpgroups, one per accumulator: tcgen05.ld -> FMNMX3 row minimum;
-//                only when a tile can improve a row (or cross the threshold) is it re-read to find the column.
+// Kernel anatomy (one persistent CTA per SM, 608 threads; work item = (row tile, column chunk)):
+//   warp 0      : TMEM allocator + bulk-async (TMA engine, cp.async.bulk) producer: A blob per work item, B blob per tile
+//   warps 1-2   : one tcgen05.mma issuer thread per warpgroup; 4 accumulators x 128 TMEM columns; one tcgen05.commit per
+//                 tile, which also tells the producer that the tile's B stage can be refilled
+//   warps 3-18  : two compute warpgroups of 8 warps; thread = one row x 64 columns: tcgen05.ld -> accumulator released ->
+//                 FMNMX3 tree; the column is only located (in registers, through groups of 8) when the row improves
 // Operands are pre-laid-out in global memory in the no-swizzle K-major core-matrix order, one
 // contiguous blob per tile, so a stage is ONE bulk copy and needs no tensor map.
 #include <cuda_fp16.h>
@@ -27,7 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "fe_umma.cuh"
+#include "fe_umma_dev.cuh"
 
 #ifndef FE_UMMA_PROF
 #define FE_UMMA_PROF 0
@@ -40,146 +41,7 @@ namespace {
 
 constexpr uint32_t kStagesMaxBytes = 200 * 1024;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must not hang the GPU -- trap after ~2^26 probes (each probe suspends the warp in
-// hardware for up to the mbarrier time limit) instead of spinning forever.  No clock reads in the loop: the
-// spinning producer/issuer warps share their SM sub-partition's ALU pipe with the compute warps.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    uint32_t probes = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++probes > (1u << 26)) __trap();
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-// plain shared-memory flags: ~30-cycle polls instead of ~200-cycle mbarrier probes
-__device__ __forceinline__ void flag_add_release(uint32_t addr, uint32_t v) {
-    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void flag_store_release(uint32_t addr, uint32_t v) {
-    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t flag_load_acquire(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void flag_wait_ge(uint32_t addr, uint32_t want) {
-    if ((int32_t)(flag_load_acquire(addr) - want) >= 0) return;
-    const long long t0 = clock64();
-    while ((int32_t)(flag_load_acquire(addr) - want) < 0) {
-        if (clock64() - t0 > 4000000000ll) __trap();
-    }
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-template <int KIND>  // 0: kind::f16, 1: kind::i8
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (KIND == 0) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    }
-}
-// K-major, no swizzle: core matrices of 8 rows x 16 bytes; LBO = byte stride between the K chunks,
-// SBO = byte stride between 8-row groups (cute/atom/mma_traits_sm100.hpp, LayoutType::INTERLEAVE).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
-    const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); // version = 1 (Blackwell), layout_type = 0
-    return ((uint64_t)hi << 32) | lo;
-}
-
-#define TMEM_LD32(taddr, v)                                                                                                   \
-    asm volatile(                                                                                                             \
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                             \
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                             \
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                             \
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),         \
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), \
-          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),             \
-          "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                        \
-        : "r"(taddr)                                                                                                          \
-        : "memory")
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float fmin3(float a, float b, float c) {
-    float r;
-    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
-__device__ __forceinline__ float min32(const uint32_t (&v)[32], float m) {
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) m = fmin3(m, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-    return m;
-}
-
-struct WorkItem {
-    uint32_t a_blob;   // row-tile index (A blob)
-    uint32_t row0;     // first global row of the tile
-    uint32_t nrows;    // valid rows in the tile (<= 128)
-    uint32_t t0, t1;   // column-tile range [t0, t1)
-    uint32_t col0;     // global (sorted) column index of tile t0's first column
-    uint32_t cols_left;// valid columns from tile t0 to the end of the bucket
-};
-
-__device__ __forceinline__ WorkItem decode_item(const UmmaArgs& a, uint32_t w) {
-    WorkItem it{};
-    for (int bi = 0; bi < a.nb; ++bi) {
-        const UmmaBucket& b = a.b[bi];
-        const uint32_t items = b.n_row_tiles * b.chunks;
-        if (w < items) {
-            const uint32_t rt = w / b.chunks, q = w % b.chunks;
-            it.a_blob = b.row_tile0 + rt;
-            it.row0 = b.row0 + rt * UM_ROWS;
-            it.nrows = min((uint32_t)UM_ROWS, b.nrows - rt * UM_ROWS);
-            const uint32_t lt0 = (uint32_t)(((uint64_t)q * b.n_col_tiles) / b.chunks);
-            const uint32_t lt1 = (uint32_t)(((uint64_t)(q + 1) * b.n_col_tiles) / b.chunks);
-            it.t0 = b.col_tile0 + lt0;
-            it.t1 = b.col_tile0 + lt1;
-            it.col0 = b.col0 + lt0 * UM_NT;
-            it.cols_left = b.ncols - lt0 * UM_NT;
-            return it;
-        }
-        w -= items;
-    }
-    return it;
-}
+using namespace umma_dev;
 
 // 128 accumulator values of one row -> running (bestV, bestp, bestcol) and first threshold hit.
 // Fast path: FMNMX3 tree for the tile minimum; the per-column scan only runs for lanes whose tile
@@ -625,6 +487,7 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     a.total_items = (uint32_t)total_items;
     a.thr16 = thr16;
     a.use_thr = use_thr ? 1u : 0u;
+    a.nt = UM_NT;
     { const char* e = getenv("FE_UMMA_DBG"); a.dbg = e ? (uint32_t)atoi(e) : 0u; }
     const uint32_t stage_bytes = UM_NT * Kpad * 2, a_bytes = 2 * UM_ROWS * Kpad * 2;
     const uint32_t stages = UM_STAGES;

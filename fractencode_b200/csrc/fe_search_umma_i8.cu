@@ -1,0 +1,374 @@
+// fe_search_umma_i8.cu -- tcgen05 search for large blocks (T >= 16): kind::i8 MMAs with exact s32 accumulators.
+//
+// fp32 accumulation stops being integer-exact when K = T^2 grows (sum r*D reaches 2.7e8 at T=32), so the large levels
+// use the integer tensor path of sm_100a:  A = range pixels r (u8, inverse-rotated rows), B = the domain box sums D
+// split into a low-byte plane and a high-byte plane (D <= 1020 -> high byte 0..3), two s32 accumulators per tile:
+//     cross = acc_lo + 256 * acc_hi,      n16 = 16 sum r^2 - 8 cross + sum D^2      (exact, any input)
+// Two planes at the 2x int8 rate cost the same tensor time as one fp16 pass.  Tile = 128 rows x 64 domain columns
+// (2 x 64 TMEM columns per buffer, two buffers per warpgroup, two warpgroups = all 512 columns); K is streamed in
+// stages of 256 bytes (32 KB per stage: both planes), the A tile (128 x K bytes, up to 128 KB at T=32) stays in
+// shared memory for the whole work item.  Same warp roles as the fp16 kernel (fe_search_umma.cu).
+#include <cstdio>
+#include <cstdlib>
+
+#include "fe_kernels.cuh"
+#include "fe_umma_dev.cuh"
+
+using namespace umma_dev;
+
+namespace {
+
+template <int DUMMY>
+__global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma_i8(const UmmaArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t Kpad = a.Kpad;
+    const uint32_t kc = min(Kpad, (uint32_t)I8_KC);          // bytes of K per stage
+    const uint32_t nch = Kpad / kc;                          // stages per tile
+    const uint32_t bytesA = UM_ROWS * Kpad, bytesB = 2 * I8_NT * kc;
+    const uint32_t S = a.stages, NA = a.n_abuf;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + NA * bytesA;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)S * bytesB);
+    const uint32_t bar0 = smem_u32(bars);
+    auto A_FULL = [&](uint32_t i) { return bar0 + 8 * (0 + i); };
+    auto A_EMPTY = [&](uint32_t i) { return bar0 + 8 * (2 + i); };
+    auto ACC_FULL = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (4 + 2 * g + b); };
+    auto ACC_EMPTY = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (8 + 2 * g + b); };
+    auto B_FULL = [&](uint32_t i) { return bar0 + 8 * (12 + i); };
+    auto B_EMPTY = [&](uint32_t i) { return bar0 + 8 * (12 + I8_MAX_STAGES + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * I8_MAX_STAGES);
+    const uint32_t B_LANDED = smem_u32(tmem_slot + 4); // number of B stages that have landed, published in order by the forwarder lane
+
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < 2; ++i) {
+            mbar_init(A_FULL(i), 1);
+            mbar_init(A_EMPTY(i), UM_WGS);
+        }
+        for (uint32_t i = 0; i < 4; ++i) {
+            mbar_init(bar0 + 8 * (4 + i), 1);
+            mbar_init(bar0 + 8 * (8 + i), 8);
+        }
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(B_FULL(i), 1);
+            mbar_init(B_EMPTY(i), 1);
+        }
+        tmem_slot[4] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= producer =================
+        if (lane == 0) {
+            uint32_t ic = 0, wi = 0; // running stage counter, item counter
+            for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x, ++wi) {
+                const WorkItem item = decode_item(a, w);
+                const uint32_t ab = wi % NA;
+                mbar_wait(A_EMPTY(ab), ((wi / NA) & 1) ^ 1);
+                mbar_expect_tx(A_FULL(ab), bytesA);
+                // the bulk copy engine takes at most ~1 MB per request; 128 KB tiles go as 32 KB pieces
+                for (uint32_t off = 0; off < bytesA; off += 32768) {
+                    const uint32_t n = min(32768u, bytesA - off);
+                    bulk_g2s(smem_u32(sA + ab * bytesA + off), reinterpret_cast<const uint8_t*>(a.A16) + (size_t)item.a_blob * bytesA + off, n, A_FULL(ab));
+                }
+                for (uint32_t t = item.t0; t < item.t1; ++t)
+                    for (uint32_t c = 0; c < nch; ++c, ++ic) {
+                        const uint32_t s = ic % S;
+                        mbar_wait(B_EMPTY(s), ((ic / S) & 1) ^ 1);
+                        mbar_expect_tx(B_FULL(s), bytesB);
+                        bulk_g2s(smem_u32(sB + (size_t)s * bytesB), reinterpret_cast<const uint8_t*>(a.B16) + ((size_t)t * nch + c) * bytesB, bytesB, B_FULL(s));
+                    }
+            }
+        } else if (lane == 1) {
+            // forwarder: a stage ring shared by two issuers means an issuer may look at a stage barrier that is still
+            // TWO phases behind the one it needs, which a parity wait cannot tell from "done".  This lane observes
+            // every phase in order (never ambiguous) and publishes the count of landed stages.
+            uint32_t ic = 0;
+            for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x) {
+                const WorkItem item = decode_item(a, w);
+                const uint32_t total = (item.t1 - item.t0) * nch;
+                for (uint32_t q = 0; q < total; ++q, ++ic) {
+                    mbar_wait(B_FULL(ic % S), (ic / S) & 1);
+                    flag_store_release(B_LANDED, ic + 1);
+                }
+            }
+        }
+    } else if (warp <= UM_WGS) {
+        // ================= MMA issuer of warpgroup g =================
+        if (lane == 0) {
+            const uint32_t g = warp - 1;
+            // D = S32, A = B = unsigned 8 bit, K-major both, N = 64, M = 128
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(I8_NT >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
+            const uint32_t nj = kc / 32; // MMAs (K = 32 bytes) per stage and plane
+            uint32_t it0 = 0, wi = 0, jb = 0;
+            for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x, ++wi) {
+                const WorkItem item = decode_item(a, w);
+                const uint32_t ab = wi % NA, n = item.t1 - item.t0;
+                const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
+                mbar_wait(A_FULL(ab), (wi / NA) & 1);
+                const uint32_t a_addr = smem_u32(sA + ab * bytesA);
+                bool any = false;
+                for (uint32_t u = first; u < n; u += UM_WGS, ++jb) {
+                    const uint32_t gi = it0 + u, buf = jb & 1;
+                    const uint32_t d_lo = tmem_base + (g * 2 + buf) * 2 * I8_NT, d_hi = d_lo + I8_NT;
+                    mbar_wait(ACC_EMPTY(g, buf), ((jb >> 1) & 1) ^ 1);
+                    for (uint32_t c = 0; c < nch; ++c) {
+                        const uint32_t ic = gi * nch + c, s = ic % S;
+                        flag_wait_ge(B_LANDED, ic + 1);       // the barrier has reached the phase we need ...
+                        mbar_wait(B_FULL(s), (ic / S) & 1);   // ... so this parity probe is unambiguous (and is the formal acquire)
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(sB + (size_t)s * bytesB);
+                        for (uint32_t j = 0; j < nj; ++j) {
+                            // chunk-major blobs: a 16-byte K chunk of all rows is contiguous (rows * 16 bytes)
+                            const uint64_t adesc = make_desc(a_addr + (c * (kc / 16) + 2 * j) * (UM_ROWS * 16), UM_ROWS * 16, 128);
+                            const uint64_t blo = make_desc(b_addr + (2 * j) * (I8_NT * 16), I8_NT * 16, 128);
+                            const uint64_t bhi = make_desc(b_addr + I8_NT * kc + (2 * j) * (I8_NT * 16), I8_NT * 16, 128);
+                            const uint32_t acc = (c | j) ? 1u : 0u;
+                            tc_mma<1>(d_lo, adesc, blo, idesc, acc);
+                            tc_mma<1>(d_hi, adesc, bhi, idesc, acc);
+                        }
+                        tc_commit(B_EMPTY(s));
+                    }
+                    tc_commit(ACC_FULL(g, buf));
+                    any = true;
+                }
+                if (any) tc_commit(A_EMPTY(ab)); else mbar_arrive(A_EMPTY(ab));
+                it0 += n;
+            }
+        }
+    } else {
+        // ================= compute warps: thread = one row x 32 columns =================
+        const uint32_t cw = warp - 1 - UM_WGS;
+        const uint32_t g = cw >> 3;
+        const uint32_t h = (cw >> 2) & 1;             // column half (32 columns)
+        const uint32_t sp = warp & 3;
+        const uint32_t lrow = sp * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((sp * 32u) << 16) + h * 32;
+        uint32_t it0 = 0, jb = 0;
+        for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x) {
+            const WorkItem item = decode_item(a, w);
+            const uint32_t n = item.t1 - item.t0;
+            const bool row_ok = lrow < item.nrows;
+            const uint32_t grow = item.row0 + lrow;
+            const uint32_t rc = row_ok ? a.rowA2[grow >> 2] : 0u;       // 16 * sum r^2
+            // w = sum D^2 - 8 cross (signed); n16 = rc + w;  n16 <= thr16  <=>  w <= thr16 - rc
+            long long wt = (long long)a.thr16 - (long long)rc;
+            wt = max(-2147483647ll, min(2147483646ll, wt));                  // INT_MAX is the padding columns' score
+            const int wthr = (a.use_thr && row_ok) ? (int)wt : (int)0x80000000;
+            int bestw = 0x7FFFFFFF;
+            uint32_t bestcol = FE_NONE32, hit = FE_NONE32;
+            const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
+            const uint32_t my_tiles = first < n ? (n - first + UM_WGS - 1) / UM_WGS : 0;
+            for (uint32_t j = 0; j < my_tiles; ++j, ++jb) {
+                const uint32_t u = first + j * UM_WGS, buf = jb & 1;
+                const uint32_t colbase = u * I8_NT + h * 32;             // column inside the item
+                const uint32_t taddr = lane_addr + (g * 2 + buf) * 2 * I8_NT;
+                uint32_t lo[32], hi[32];
+                mbar_wait(ACC_FULL(g, buf), (jb >> 1) & 1);
+                tc_fence_after();
+                TMEM_LD32(taddr, lo);
+                TMEM_LD32(taddr + I8_NT, hi);
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ACC_EMPTY(g, buf));
+                // sum(D^2) per column, stored by padded (tile, column) position so the 16-byte loads stay aligned
+                const uint4* cn4 = reinterpret_cast<const uint4*>(a.coln + (size_t)(item.t0 + u) * I8_NT + h * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint4 cn = __ldg(cn4 + q);
+                    const uint32_t cnv[4] = {cn.x, cn.y, cn.z, cn.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = 4 * q + e;
+                        const int cross = (int)(lo[i] + (hi[i] << 8));
+                        const int wv = (int)cnv[e] - 8 * cross;
+                        const uint32_t col = colbase + i;
+                        if (wv < bestw) { bestw = wv; bestcol = col; }
+                        if (wv <= wthr && hit == FE_NONE32) hit = col;
+                    }
+                }
+            }
+            it0 += n;
+            if (row_ok) {
+                if (bestcol != FE_NONE32) {
+                    const uint32_t n16 = rc + (uint32_t)bestw;
+                    const unsigned long long key = ((unsigned long long)n16 << 32) | (unsigned long long)(item.col0 + bestcol);
+                    atomicMin(&a.rowbest[grow], key);
+                }
+                if (hit != FE_NONE32) atomicMin(&a.rowhit[grow], item.col0 + hit);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// operand blobs (u8).  A: [row tile][K/16][128 rows][16 B].  B: [col tile][K stage][plane lo,hi][kc/16][64 cols][16 B].
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_build_rows_i8(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
+                                const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
+                                uint8_t* __restrict__ A8, uint32_t* __restrict__ rowc) {
+    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= bk.n_ranges) return;
+    int bi = 0;
+    while (bi + 1 < bk.nb && j >= bk.range_off[bi + 1]) ++bi;
+    const uint32_t lj = j - bk.range_off[bi];
+    const uint32_t tile = bk.row_tile0[bi] + lj / 32, lr = lj % 32;
+    const fe_grid_item r = rng[order ? order[j] : j];
+    const uint32_t N = T * T;
+    uint8_t* blob = A8 + (size_t)tile * UM_ROWS * Kpad;
+    const uint8_t* base = img + (size_t)r.y * stride + r.x;
+    uint32_t s2 = 0;
+    for (uint32_t e = lane; e < N; e += 32) {
+        const uint32_t Y = e / T, X = e % T;
+        const uint8_t p0 = base[(size_t)Y * stride + X];
+        const uint8_t p1 = base[(size_t)X * stride + (T - 1 - Y)];
+        const uint8_t p2 = base[(size_t)(T - 1 - Y) * stride + (T - 1 - X)];
+        const uint8_t p3 = base[(size_t)(T - 1 - X) * stride + Y];
+        s2 += (uint32_t)p0 * p0;
+        uint8_t* dst = blob + (size_t)(e / 16) * (UM_ROWS * 16) + (e % 16);
+        dst[(4 * lr + 0) * 16] = p0;
+        dst[(4 * lr + 1) * 16] = p1;
+        dst[(4 * lr + 2) * 16] = p2;
+        dst[(4 * lr + 3) * 16] = p3;
+    }
+    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+    if (lane == 0) rowc[j] = 16u * s2;
+}
+
+__global__ void k_build_pool_i8(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ dom,
+                                const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad, uint32_t kc,
+                                uint8_t* __restrict__ B8, uint32_t* __restrict__ coln_tiles) {
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= bk.n_domains) return;
+    int bi = 0;
+    while (bi + 1 < bk.nb && c >= bk.dom_off[bi + 1]) ++bi;
+    const uint32_t lc = c - bk.dom_off[bi];
+    const uint32_t tile = bk.col_tile0[bi] + lc / I8_NT, l = lc % I8_NT;
+    const fe_grid_item d = dom[order ? order[c] : c];
+    const uint32_t N = T * T;
+    uint8_t* blob = B8 + (size_t)tile * 2 * I8_NT * Kpad;
+    const uint8_t* base = img + (size_t)d.y * stride + d.x;
+    uint32_t s2 = 0;
+    for (uint32_t e = lane; e < N; e += 32) {
+        const uint32_t ty = e / T, tx = e % T;
+        const uint8_t* p = base + (size_t)(2 * ty) * stride + 2 * tx;
+        const uint32_t D = p[0] + p[1] + p[stride] + p[stride + 1];
+        s2 += D * D;
+        const uint32_t st = e / kc, ek = e % kc;                       // K stage, byte inside the stage
+        uint8_t* sb = blob + (size_t)st * (2 * I8_NT * kc);
+        const size_t off = (size_t)(ek / 16) * (I8_NT * 16) + l * 16 + (ek % 16);
+        sb[off] = (uint8_t)(D & 255u);
+        sb[(size_t)I8_NT * kc + off] = (uint8_t)(D >> 8);
+    }
+    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+    if (lane == 0) coln_tiles[(size_t)tile * I8_NT + l] = s2;          // indexed by padded (tile, column) position
+}
+
+int umma_i8_level_supported(const LevelGeom& g) { return g.fast && g.T >= 4 && g.T <= 32; }
+
+static uint32_t i8_kpad(const LevelGeom& g) { return g.N <= (uint32_t)I8_KC ? ((g.N + 31u) & ~31u) : ((g.N + I8_KC - 1) / I8_KC) * I8_KC; }
+
+int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng,
+                               const uint32_t* dom_order, const uint32_t* rng_order, const uint32_t doff[8], const uint32_t roff[8],
+                               int nbuckets, uint32_t thr16, bool use_thr, cudaEvent_t prep_done) {
+    const uint32_t Kpad = i8_kpad(g), kc = std::min(Kpad, (uint32_t)I8_KC);
+    UmmaBuckets bk{};
+    UmmaArgs a{};
+    uint32_t rt = 0, ct = 0, nb = 0;
+    uint64_t total_items = 0;
+    for (int c = 0; c < nbuckets; ++c) {
+        const uint32_t rc = roff[c + 1] - roff[c], dc = doff[c + 1] - doff[c];
+        bk.range_off[nb] = roff[c];
+        bk.dom_off[nb] = doff[c];
+        bk.row_tile0[nb] = rt;
+        bk.col_tile0[nb] = ct;
+        UmmaBucket& b = a.b[nb];
+        b.row_tile0 = rt; b.n_row_tiles = (rc + 31) / 32;
+        b.col_tile0 = ct; b.n_col_tiles = (dc + I8_NT - 1) / I8_NT;
+        b.row0 = roff[c] * 4; b.nrows = rc * 4;
+        b.col0 = doff[c]; b.ncols = dc;
+        rt += b.n_row_tiles;
+        ct += b.n_col_tiles;
+        ++nb;
+    }
+    bk.nb = (int)nb;
+    bk.range_off[nb] = roff[nbuckets];
+    bk.dom_off[nb] = doff[nbuckets];
+    bk.n_ranges = roff[nbuckets];
+    bk.n_domains = doff[nbuckets];
+    uint32_t live_row_tiles = 0;
+    for (uint32_t i = 0; i < nb; ++i)
+        if (a.b[i].n_col_tiles) live_row_tiles += a.b[i].n_row_tiles;
+    const uint32_t want_chunks = live_row_tiles ? (2 * 148 + live_row_tiles - 1) / live_row_tiles : 1;
+    for (uint32_t i = 0; i < nb; ++i) {
+        UmmaBucket& b = a.b[i];
+        b.chunks = (b.n_col_tiles && b.n_row_tiles) ? std::max(1u, std::min(want_chunks, b.n_col_tiles)) : 0;
+        total_items += (uint64_t)b.n_row_tiles * b.chunks;
+    }
+    if (total_items == 0) { if (prep_done) cudaEventRecord(prep_done, ctx->stream); return FE_OK; }
+    if (total_items > 0x7FFFFFFFull) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "umma i8: too many work items");
+
+    const size_t bytesA = (size_t)rt * UM_ROWS * Kpad, bytesB = (size_t)ct * 2 * I8_NT * Kpad;
+    FE_CUDA(ctx, ctx->b_A16.ensure(bytesA + 256));
+    FE_CUDA(ctx, ctx->b_B16.ensure(bytesB + 256));
+    FE_CUDA(ctx, ctx->b_coln.ensure((size_t)ct * I8_NT * 4 + 64));
+    FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)bk.n_ranges * 4 + 4));
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_A16.p, 0, bytesA, ctx->stream));
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_B16.p, 0, bytesB, ctx->stream));
+    k_fill_u32<<<(unsigned)(((size_t)ct * I8_NT + 255) / 256), 256, 0, ctx->stream>>>(ctx->b_coln.as<uint32_t>(), 0x7FFFFFFFu, (size_t)ct * I8_NT);
+    FE_CUDA(ctx, cudaGetLastError()); // INT_MAX: padding columns can never be a strict minimum nor pass the threshold
+    k_build_rows_i8<<<(unsigned)(((uint64_t)bk.n_ranges * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, g.T, Kpad, ctx->b_A16.as<uint8_t>(), ctx->b_rowc.as<uint32_t>());
+    FE_CUDA(ctx, cudaGetLastError());
+    k_build_pool_i8<<<(unsigned)(((uint64_t)bk.n_domains * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, g.T, Kpad, kc, ctx->b_B16.as<uint8_t>(), ctx->b_coln.as<uint32_t>());
+    FE_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 3;
+    if (prep_done) cudaEventRecord(prep_done, ctx->stream);
+
+    a.A16 = ctx->b_A16.p;
+    a.B16 = ctx->b_B16.p;
+    a.colpar = nullptr;
+    a.coln = ctx->b_coln.as<uint32_t>();
+    a.rowA2 = ctx->b_rowc.as<uint32_t>();
+    a.rowbest = ctx->b_rowbest.as<unsigned long long>();
+    a.rowhit = ctx->b_rowhit.as<uint32_t>();
+    a.flags = ctx->b_counters.as<uint32_t>() + 2;
+    a.nb = (int)nb;
+    a.Kpad = Kpad;
+    a.total_items = (uint32_t)total_items;
+    a.thr16 = thr16;
+    a.use_thr = use_thr ? 1u : 0u;
+    a.nt = I8_NT;
+    const uint32_t stage_bytes = 2 * I8_NT * kc, a_bytes = UM_ROWS * Kpad;
+    const uint32_t budget = 226 * 1024 - 512;
+    a.n_abuf = (2 * a_bytes + 2 * stage_bytes <= budget) ? 2 : 1;
+    uint32_t stages = (budget - a.n_abuf * a_bytes) / stage_bytes;
+    stages = std::min((uint32_t)I8_MAX_STAGES, stages);
+    if (stages < 2) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "umma i8: operands do not fit shared memory (T=%u)", g.T);
+    a.stages = stages;
+    const size_t smem = (size_t)a.n_abuf * a_bytes + (size_t)stages * stage_bytes + (12 + 2 * I8_MAX_STAGES) * 8 + 128;
+    FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma_i8<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(total_items, 148);
+    k_search_umma_i8<0><<<grid, UM_THREADS, smem, ctx->stream>>>(a);
+    FE_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    return FE_OK;
+}

@@ -11,7 +11,10 @@ constexpr int UM_HALF = UM_NT / 2;   // columns a compute thread holds per regis
 constexpr int UM_THREADS = 32 + 32 * UM_WGS + 256 * UM_WGS; // producer warp, one MMA-issuer warp per group, 8 compute warps per group
 constexpr int UM_MAX_STAGES = 8;
 constexpr int UM_STAGES = 4;       // B stages: tile t reuses the stage of tile t-4, freed by that tile's accumulator-full commit
-constexpr int UM_MAX_NK = 5;       // K steps of 16 per tile: T=4 -> 2, T=8 -> 5
+constexpr int UM_MAX_NK = 5;
+constexpr int I8_NT = 64;          // i8 kind: domain columns per tile (two s32 accumulators, low/high byte plane, of 64 columns)
+constexpr int I8_KC = 256;         // i8 kind: bytes of K per shared-memory stage
+constexpr int I8_MAX_STAGES = 4;       // K steps of 16 per tile: T=4 -> 2, T=8 -> 5
 
 struct UmmaBucket {
     uint32_t row_tile0, n_row_tiles; // A blobs of this classifier bucket
@@ -32,6 +35,9 @@ struct UmmaArgs {
     UmmaBucket b[7];
     int nb;
     uint32_t Kpad, stages, total_items, thr16, use_thr;
+    uint32_t nt;                     // domain columns per tile (UM_NT for the f16 kind, I8_NT for the i8 kind)
+    const uint32_t* coln;            // i8 kind: [sorted column] sum(D^2) (0x3FFFFFFF for padding columns)
+    uint32_t n_abuf;                 // i8 kind: A buffers in shared memory (2, or 1 when the tile is 128 KB)
     uint32_t dbg;                    // tuning probes (FE_UMMA_DBG): 1 skip TMEM drain, 2 skip MMA issue, 4 skip B copies
 };
 
@@ -41,6 +47,10 @@ struct UmmaBuckets {                 // operand-layout view for the blob builder
     int nb;
 };
 
+int umma_i8_level_supported(const LevelGeom& g);
+int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng,
+                               const uint32_t* dom_order, const uint32_t* rng_order, const uint32_t doff[8], const uint32_t roff[8],
+                               int nbuckets, uint32_t thr16, bool use_thr, cudaEvent_t prep_done);
 int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng,
                             const uint32_t* dom_order, const uint32_t* rng_order, const uint32_t doff[8], const uint32_t roff[8],
                             int nbuckets, uint32_t thr16, bool use_thr, bool* inexact, cudaEvent_t prep_done);
