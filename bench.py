@@ -196,6 +196,7 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
     import fractencode_b200 as fb
+    from fractencode_b200.dist import gather_item_lists
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,12 +224,10 @@ def run_b200(a):
     def step_resident():
         n = ctx.encode_quadtree_device(a.tmax, a.tmin, params)
         if world > 1:  # gather the per-rank transform lists (the only collective of the path)
-            mine = torch.tensor([n], dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(counts_t, mine)
             nptr = C.c_size_t(0)
             ptr = lib.fe_device_items(ctx.h, C.byref(nptr))
             items = torch.as_tensor(DevArray(ptr, cap * 64), device="cuda")
-            dist.all_gather_into_tensor(gather_buf, items)
+            gather_item_lists(items, n, cap, counts_t, gather_buf)
         return n
 
     def step_e2e():
