@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma_i8(const UmmaArgs
                 if (lane == 0) mbar_arrive(ACC_EMPTY(g, buf));
                 // sum(D^2) per column, stored by padded (tile, column) position so the 16-byte loads stay aligned
                 const uint4* cn4 = reinterpret_cast<const uint4*>(a.coln + (size_t)(item.t0 + u) * I8_NT + h * 32);
+                // w = sum D^2 - 8 (lo + 256 hi): two IMADs per column (FMA pipe), written over the low-plane registers
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const uint4 cn = __ldg(cn4 + q);
@@ -189,12 +190,28 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma_i8(const UmmaArgs
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int i = 4 * q + e;
-                        const int cross = (int)(lo[i] + (hi[i] << 8));
-                        const int wv = (int)cnv[e] - 8 * cross;
-                        const uint32_t col = colbase + i;
-                        if (wv < bestw) { bestw = wv; bestcol = col; }
-                        if (wv <= wthr && hit == FE_NONE32) hit = col;
+                        lo[i] = (uint32_t)((int)cnv[e] - 8 * (int)lo[i] - 2048 * (int)hi[i]);
                     }
+                }
+                // tile minimum through 3-input integer minima (VIMNMX3), column located only when the row improves
+                int m0 = 0x7FFFFFFF, m1 = 0x7FFFFFFF;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    m0 = min(min(m0, (int)lo[i]), (int)lo[i + 1]);
+                    m1 = min(min(m1, (int)lo[i + 2]), (int)lo[i + 3]);
+                }
+                const int tmin = min(m0, m1);
+                const bool improve = row_ok && tmin < bestw;
+                const bool need_hit = row_ok && hit == FE_NONE32 && tmin <= wthr;
+                if (improve | need_hit) {
+                    uint32_t c_best = FE_NONE32, c_hit = FE_NONE32;
+#pragma unroll
+                    for (int i = 31; i >= 0; --i) {       // descending: the smallest qualifying column survives
+                        c_best = ((int)lo[i] == tmin) ? (uint32_t)i : c_best;
+                        c_hit = ((int)lo[i] <= wthr) ? (uint32_t)i : c_hit;
+                    }
+                    if (improve) { bestw = tmin; bestcol = colbase + c_best; }
+                    if (need_hit && c_hit != FE_NONE32) hit = colbase + c_hit;
                 }
             }
             it0 += n;
