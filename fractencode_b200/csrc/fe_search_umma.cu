@@ -332,79 +332,118 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
 // ---------------------------------------------------------------------------------------------------
 // operand blobs
 // ---------------------------------------------------------------------------------------------------
-// A rows: one warp per range position j of bucket-local order.  Row (4*lr + k) of blob `tile`:
-// element kidx -> blob + (kidx/8)*(128*8) + row*8 + kidx%8   (halves).
-__global__ void k_build_rows16(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
-                               const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
-                               __half* __restrict__ A16, uint32_t* __restrict__ rowA2) {
-    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (j >= bk.n_ranges) return;
-    int bi = 0;
-    while (bi + 1 < bk.nb && j >= bk.range_off[bi + 1]) ++bi;
-    const uint32_t lj = j - bk.range_off[bi];
-    const uint32_t tile = bk.row_tile0[bi] + lj / 32, lr = lj % 32;
-    const fe_grid_item r = rng[order ? order[j] : j];
+__global__ void k_block_norms(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ items,
+                              const uint32_t* __restrict__ order, uint32_t n, uint32_t T, int mode, uint32_t* __restrict__ out) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n) return;
+    const fe_grid_item it = items[order ? order[p] : p];
+    const uint8_t* base = img + (size_t)it.y * stride + it.x;
     const uint32_t N = T * T;
-    __half* blob = A16 + (size_t)tile * UM_ROWS * Kpad;
-    const uint8_t* base = img + (size_t)r.y * stride + r.x;
-    uint32_t s2 = 0;
-    for (uint32_t e = lane; e < Kpad; e += 32) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (e < N) {
-            const uint32_t Y = e / T, X = e % T;
-            const int p0 = base[(size_t)Y * stride + X];
-            const int p1 = base[(size_t)X * stride + (T - 1 - Y)];
-            const int p2 = base[(size_t)(T - 1 - Y) * stride + (T - 1 - X)];
-            const int p3 = base[(size_t)(T - 1 - X) * stride + Y];
-            const int a0 = 4 * p0 - 510;
-            s2 += (uint32_t)(a0 * a0);
-            v[0] = (float)(510 - 4 * p0); v[1] = (float)(510 - 4 * p1); v[2] = (float)(510 - 4 * p2); v[3] = (float)(510 - 4 * p3);
-        } else if (e == N) {
-            v[0] = v[1] = v[2] = v[3] = 1.0f;
-        } else if (e == N + 1 || e == N + 2) {
-            v[0] = v[1] = v[2] = v[3] = 2048.0f;
-        }
-        __half* dst = blob + (size_t)(e / 8) * (UM_ROWS * 8) + (e % 8);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dst[(4 * lr + k) * 8] = __float2half_rn(v[k]);
-    }
-    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
-    if (lane == 0) rowA2[j] = s2;
-}
-
-// B columns: one warp per sorted column.  b = D - 510; limbs of h = floor(sum b^2 / 2); parity bit.
-__global__ void k_build_pool16(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ dom,
-                               const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
-                               __half* __restrict__ B16, uint32_t* __restrict__ colpar) {
-    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= bk.n_domains) return;
-    int bi = 0;
-    while (bi + 1 < bk.nb && c >= bk.dom_off[bi + 1]) ++bi;
-    const uint32_t lc = c - bk.dom_off[bi];
-    const uint32_t tile = bk.col_tile0[bi] + lc / UM_NT, l = lc % UM_NT;
-    const fe_grid_item d = dom[order ? order[c] : c];
-    const uint32_t N = T * T;
-    __half* blob = B16 + (size_t)tile * UM_NT * Kpad;
-    const uint8_t* base = img + (size_t)d.y * stride + d.x;
     uint32_t s2 = 0;
     for (uint32_t e = lane; e < N; e += 32) {
-        const uint32_t ty = e / T, tx = e % T;
-        const uint8_t* p = base + (size_t)(2 * ty) * stride + 2 * tx;
-        const int D = p[0] + p[1] + p[stride] + p[stride + 1];
-        const int b = D - 510;
-        s2 += (uint32_t)(b * b);
-        blob[(size_t)(e / 8) * (UM_NT * 8) + l * 8 + (e % 8)] = __float2half_rn((float)b);
+        int v;
+        if (mode < 2) {
+            const int r = base[(size_t)(e / T) * stride + (e % T)];
+            v = mode == 0 ? 4 * r - 510 : 4 * r;              // (4r)^2 = 16 r^2
+        } else {
+            const uint8_t* q = base + (size_t)(2 * (e / T)) * stride + 2 * (e % T);
+            const int D = (int)q[0] + (int)q[1] + (int)q[stride] + (int)q[stride + 1];
+            v = mode == 2 ? D - 510 : D;
+        }
+        s2 += (uint32_t)(v * v);
     }
     for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
-    if (lane == 0) {
-        const uint32_t h = s2 >> 1, p = s2 & 1u;
-        const float limb[3] = {(float)(h & 2047u), (float)((h >> 11) & 2047u), (float)((h >> 22) * 2048u)};
-        for (uint32_t q = 0; q < 3; ++q) {
-            const uint32_t e = N + q;
-            blob[(size_t)(e / 8) * (UM_NT * 8) + l * 8 + (e % 8)] = __float2half_rn(limb[q]);
+    if (lane == 0) out[p] = s2;
+}
+
+// Both builders: one thread per 16-byte store (8 halves = one K chunk of one row / column), consecutive threads ->
+// consecutive rows of the same chunk, so every warp writes 512 contiguous bytes; every byte of every blob (padding rows,
+// columns and K included) is written exactly once -- no memset, write traffic = blob size.  Reads are u8 gathers from the
+// L2-resident image.
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// A rows.  Row (4*lr + k) of row tile `tile`: range lr of the tile under the inverse of rotation k, value 510 - 4 r, then
+// the constant columns [1, 2048, 2048].
+__global__ void k_build_rows16(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
+                               const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
+                               uint4* __restrict__ A16) {
+    const uint32_t nch = Kpad / 8;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)bk.row_tile0[bk.nb] * nch * UM_ROWS) return;
+    const uint32_t row = (uint32_t)(idx % UM_ROWS), ch = (uint32_t)((idx / UM_ROWS) % nch), tile = (uint32_t)(idx / ((uint64_t)UM_ROWS * nch));
+    int bi = 0;
+    while (bi + 1 < bk.nb && tile >= bk.row_tile0[bi + 1]) ++bi;
+    const uint32_t j = bk.range_off[bi] + (tile - bk.row_tile0[bi]) * 32 + row / 4, k = row & 3;
+    const uint32_t N = T * T;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+    if (j < bk.range_off[bi + 1]) {
+        const fe_grid_item r = rng[order ? order[j] : j];
+        const uint8_t* base = img + (size_t)r.y * stride + r.x;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t e = ch * 8 + q;
+            if (e < N) {
+                const uint32_t Y = e / T, X = e % T;
+                uint32_t py, px;
+                if (k == 0) { py = Y; px = X; }
+                else if (k == 1) { py = X; px = T - 1 - Y; }
+                else if (k == 2) { py = T - 1 - Y; px = T - 1 - X; }
+                else { py = T - 1 - X; px = Y; }
+                v[q] = (float)(510 - 4 * (int)base[(size_t)py * stride + px]);
+            } else if (e == N) {
+                v[q] = 1.0f;
+            } else if (e == N + 1 || e == N + 2) {
+                v[q] = 2048.0f;
+            }
         }
-        if (p) atomicOr(&colpar[(size_t)tile * (UM_NT / 32) + (l >> 5)], 1u << (l & 31));
     }
+    A16[idx] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+}
+
+// B columns.  b = D - 510; limbs of h = floor(sum b^2 / 2) in the three columns after the data; parity bit.
+__global__ void k_build_pool16(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ dom,
+                               const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
+                               const uint32_t* __restrict__ colS2, uint4* __restrict__ B16, uint32_t* __restrict__ colpar) {
+    const uint32_t nch = Kpad / 8;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)bk.col_tile0[bk.nb] * nch * UM_NT) return;
+    const uint32_t l = (uint32_t)(idx % UM_NT), ch = (uint32_t)((idx / UM_NT) % nch), tile = (uint32_t)(idx / ((uint64_t)UM_NT * nch));
+    int bi = 0;
+    while (bi + 1 < bk.nb && tile >= bk.col_tile0[bi + 1]) ++bi;
+    const uint32_t c = bk.dom_off[bi] + (tile - bk.col_tile0[bi]) * UM_NT + l;
+    const uint32_t N = T * T;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+    if (c < bk.dom_off[bi + 1]) {
+        const fe_grid_item d = dom[order ? order[c] : c];
+        const uint8_t* base = img + (size_t)d.y * stride + d.x;
+        auto boxsum = [&](uint32_t e) {
+            const uint8_t* p = base + (size_t)(2 * (e / T)) * stride + 2 * (e % T);
+            return (int)p[0] + (int)p[1] + (int)p[stride] + (int)p[stride + 1];
+        };
+        const bool has_limbs = ch * 8 + 7 >= N && ch * 8 <= N + 2;
+        uint32_t h = 0;
+        if (has_limbs) {
+            const uint32_t s2 = colS2[c];
+            h = s2 >> 1;
+            if ((s2 & 1u) && ch * 8 <= N && N <= ch * 8 + 7) atomicOr(&colpar[(size_t)tile * (UM_NT / 32) + (l >> 5)], 1u << (l & 31));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t e = ch * 8 + q;
+            if (e < N) v[q] = (float)(boxsum(e) - 510);
+            else if (e == N) v[q] = (float)(h & 2047u);
+            else if (e == N + 1) v[q] = (float)((h >> 11) & 2047u);
+            else if (e == N + 2) v[q] = (float)((h >> 22) * 2048u);
+        }
+    }
+    B16[idx] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -441,6 +480,8 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     bk.nb = (int)nb;
     bk.range_off[nb] = roff[nbuckets];
     bk.dom_off[nb] = doff[nbuckets];
+    bk.row_tile0[nb] = rt;
+    bk.col_tile0[nb] = ct;
     bk.n_ranges = roff[nbuckets];
     bk.n_domains = doff[nbuckets];
     // column chunking: aim at >= 2 work items per SM when there are few row tiles
@@ -463,16 +504,19 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     FE_CUDA(ctx, ctx->b_tmaps.ensure((size_t)ct * (UM_NT / 32) * 4 + 64));
     FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)bk.n_ranges * 4 + 4));
     uint32_t* flags = ctx->b_counters.as<uint32_t>() + 2;
-    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_A16.p, 0, bytesA, ctx->stream));
-    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_B16.p, 0, bytesB, ctx->stream));
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_tmaps.p, 0, (size_t)ct * (UM_NT / 32) * 4, ctx->stream));
-    k_build_rows16<<<(unsigned)(((uint64_t)bk.n_ranges * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, g.T, Kpad, ctx->b_A16.as<__half>(), ctx->b_rowc.as<uint32_t>());
+    FE_CUDA(ctx, ctx->b_coln.ensure((size_t)bk.n_domains * 4 + 4));
+    k_block_norms<<<(unsigned)(((uint64_t)bk.n_ranges * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order,
+                                                                                               bk.n_ranges, g.T, 0, ctx->b_rowc.as<uint32_t>());
+    k_block_norms<<<(unsigned)(((uint64_t)bk.n_domains * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order,
+                                                                                                bk.n_domains, g.T, 2, ctx->b_coln.as<uint32_t>());
+    k_build_rows16<<<(unsigned)((bytesA / 16 + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, g.T, Kpad, ctx->b_A16.as<uint4>());
     FE_CUDA(ctx, cudaGetLastError());
-    k_build_pool16<<<(unsigned)(((uint64_t)bk.n_domains * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, g.T, Kpad, ctx->b_B16.as<__half>(), ctx->b_tmaps.as<uint32_t>());
+    k_build_pool16<<<(unsigned)((bytesB / 16 + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, g.T, Kpad, ctx->b_coln.as<uint32_t>(), ctx->b_B16.as<uint4>(), ctx->b_tmaps.as<uint32_t>());
     FE_CUDA(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches += 2;
+    ctx->stats.kernel_launches += 4;
     if (prep_done) cudaEventRecord(prep_done, ctx->stream);
 
     a.A16 = ctx->b_A16.p;

@@ -238,64 +238,76 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma_i8(const UmmaArgs
 // ---------------------------------------------------------------------------------------------------
 // operand blobs (u8).  A: [row tile][K/16][128 rows][16 B].  B: [col tile][K stage][plane lo,hi][kc/16][64 cols][16 B].
 // ---------------------------------------------------------------------------------------------------
+// One thread per 16-byte store (16 K bytes of one row / column); every byte of every blob is written once, no memset.
 __global__ void k_build_rows_i8(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
                                 const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
-                                uint8_t* __restrict__ A8, uint32_t* __restrict__ rowc) {
-    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (j >= bk.n_ranges) return;
+                                uint4* __restrict__ A8) {
+    const uint32_t nch = Kpad / 16;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)bk.row_tile0[bk.nb] * nch * UM_ROWS) return;
+    const uint32_t row = (uint32_t)(idx % UM_ROWS), ch = (uint32_t)((idx / UM_ROWS) % nch), tile = (uint32_t)(idx / ((uint64_t)UM_ROWS * nch));
     int bi = 0;
-    while (bi + 1 < bk.nb && j >= bk.range_off[bi + 1]) ++bi;
-    const uint32_t lj = j - bk.range_off[bi];
-    const uint32_t tile = bk.row_tile0[bi] + lj / 32, lr = lj % 32;
-    const fe_grid_item r = rng[order ? order[j] : j];
+    while (bi + 1 < bk.nb && tile >= bk.row_tile0[bi + 1]) ++bi;
+    const uint32_t j = bk.range_off[bi] + (tile - bk.row_tile0[bi]) * 32 + row / 4, k = row & 3;
     const uint32_t N = T * T;
-    uint8_t* blob = A8 + (size_t)tile * UM_ROWS * Kpad;
-    const uint8_t* base = img + (size_t)r.y * stride + r.x;
-    uint32_t s2 = 0;
-    for (uint32_t e = lane; e < N; e += 32) {
-        const uint32_t Y = e / T, X = e % T;
-        const uint8_t p0 = base[(size_t)Y * stride + X];
-        const uint8_t p1 = base[(size_t)X * stride + (T - 1 - Y)];
-        const uint8_t p2 = base[(size_t)(T - 1 - Y) * stride + (T - 1 - X)];
-        const uint8_t p3 = base[(size_t)(T - 1 - X) * stride + Y];
-        s2 += (uint32_t)p0 * p0;
-        uint8_t* dst = blob + (size_t)(e / 16) * (UM_ROWS * 16) + (e % 16);
-        dst[(4 * lr + 0) * 16] = p0;
-        dst[(4 * lr + 1) * 16] = p1;
-        dst[(4 * lr + 2) * 16] = p2;
-        dst[(4 * lr + 3) * 16] = p3;
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (j < bk.range_off[bi + 1]) {
+        const fe_grid_item r = rng[order ? order[j] : j];
+        const uint8_t* base = img + (size_t)r.y * stride + r.x;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const uint32_t e = ch * 16 + q;
+            if (e < N) {
+                const uint32_t Y = e / T, X = e % T;
+                uint32_t py, px;
+                if (k == 0) { py = Y; px = X; }
+                else if (k == 1) { py = X; px = T - 1 - Y; }
+                else if (k == 2) { py = T - 1 - Y; px = T - 1 - X; }
+                else { py = T - 1 - X; px = Y; }
+                w[q >> 2] |= (uint32_t)base[(size_t)py * stride + px] << (8 * (q & 3));
+            }
+        }
     }
-    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
-    if (lane == 0) rowc[j] = 16u * s2;
+    A8[idx] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// B: [col tile][K stage][plane lo,hi][kc/16][64 cols][16 B].  Thread -> (tile, stage, 16-byte K chunk, column): writes the
+// low-plane and the high-plane 16 bytes.  coln (by padded position): sum D^2, INT_MAX for padding columns.
 __global__ void k_build_pool_i8(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ dom,
                                 const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad, uint32_t kc,
-                                uint8_t* __restrict__ B8, uint32_t* __restrict__ coln_tiles) {
-    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= bk.n_domains) return;
+                                const uint32_t* __restrict__ colS2, uint4* __restrict__ B8, uint32_t* __restrict__ coln_tiles) {
+    const uint32_t nst = Kpad / kc, ncs = kc / 16;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)bk.col_tile0[bk.nb] * nst * ncs * I8_NT) return;
+    const uint32_t l = (uint32_t)(idx % I8_NT), cs = (uint32_t)((idx / I8_NT) % ncs), st = (uint32_t)((idx / ((uint64_t)I8_NT * ncs)) % nst);
+    const uint32_t tile = (uint32_t)(idx / ((uint64_t)I8_NT * ncs * nst));
     int bi = 0;
-    while (bi + 1 < bk.nb && c >= bk.dom_off[bi + 1]) ++bi;
-    const uint32_t lc = c - bk.dom_off[bi];
-    const uint32_t tile = bk.col_tile0[bi] + lc / I8_NT, l = lc % I8_NT;
-    const fe_grid_item d = dom[order ? order[c] : c];
+    while (bi + 1 < bk.nb && tile >= bk.col_tile0[bi + 1]) ++bi;
+    const uint32_t c = bk.dom_off[bi] + (tile - bk.col_tile0[bi]) * I8_NT + l;
     const uint32_t N = T * T;
-    uint8_t* blob = B8 + (size_t)tile * 2 * I8_NT * Kpad;
-    const uint8_t* base = img + (size_t)d.y * stride + d.x;
-    uint32_t s2 = 0;
-    for (uint32_t e = lane; e < N; e += 32) {
-        const uint32_t ty = e / T, tx = e % T;
-        const uint8_t* p = base + (size_t)(2 * ty) * stride + 2 * tx;
-        const uint32_t D = p[0] + p[1] + p[stride] + p[stride + 1];
-        s2 += D * D;
-        const uint32_t st = e / kc, ek = e % kc;                       // K stage, byte inside the stage
-        uint8_t* sb = blob + (size_t)st * (2 * I8_NT * kc);
-        const size_t off = (size_t)(ek / 16) * (I8_NT * 16) + l * 16 + (ek % 16);
-        sb[off] = (uint8_t)(D & 255u);
-        sb[(size_t)I8_NT * kc + off] = (uint8_t)(D >> 8);
+    uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    const bool valid = c < bk.dom_off[bi + 1];
+    if (valid) {
+        const fe_grid_item d = dom[order ? order[c] : c];
+        const uint8_t* base = img + (size_t)d.y * stride + d.x;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const uint32_t e = st * kc + cs * 16 + q;
+            if (e < N) {
+                const uint8_t* p = base + (size_t)(2 * (e / T)) * stride + 2 * (e % T);
+                const uint32_t D = (uint32_t)p[0] + p[1] + p[stride] + p[stride + 1];
+                lo[q >> 2] |= (D & 255u) << (8 * (q & 3));
+                hi[q >> 2] |= (D >> 8) << (8 * (q & 3));
+            }
+        }
+        if (st == 0 && cs == 0) coln_tiles[(size_t)tile * I8_NT + l] = colS2[c];
+    } else if (st == 0 && cs == 0) {
+        coln_tiles[(size_t)tile * I8_NT + l] = 0x7FFFFFFFu; // padding columns can never be a strict minimum nor pass the threshold
     }
-    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
-    if (lane == 0) coln_tiles[(size_t)tile * I8_NT + l] = s2;          // indexed by padded (tile, column) position
+    // stage blob = [plane][kc/16][64][16 B]: in uint4 units plane stride = ncs * 64
+    const size_t stage_base = ((size_t)tile * nst + st) * 2 * ncs * I8_NT;
+    B8[stage_base + (size_t)cs * I8_NT + l] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    B8[stage_base + (size_t)ncs * I8_NT + (size_t)cs * I8_NT + l] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
 }
 
 int umma_i8_level_supported(const LevelGeom& g) { return g.fast && g.T >= 4 && g.T <= 32; }
@@ -328,6 +340,8 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     bk.nb = (int)nb;
     bk.range_off[nb] = roff[nbuckets];
     bk.dom_off[nb] = doff[nbuckets];
+    bk.row_tile0[nb] = rt;
+    bk.col_tile0[nb] = ct;
     bk.n_ranges = roff[nbuckets];
     bk.n_domains = doff[nbuckets];
     uint32_t live_row_tiles = 0;
@@ -347,17 +361,18 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     FE_CUDA(ctx, ctx->b_B16.ensure(bytesB + 256));
     FE_CUDA(ctx, ctx->b_coln.ensure((size_t)ct * I8_NT * 4 + 64));
     FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)bk.n_ranges * 4 + 4));
-    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_A16.p, 0, bytesA, ctx->stream));
-    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_B16.p, 0, bytesB, ctx->stream));
-    k_fill_u32<<<(unsigned)(((size_t)ct * I8_NT + 255) / 256), 256, 0, ctx->stream>>>(ctx->b_coln.as<uint32_t>(), 0x7FFFFFFFu, (size_t)ct * I8_NT);
-    FE_CUDA(ctx, cudaGetLastError()); // INT_MAX: padding columns can never be a strict minimum nor pass the threshold
-    k_build_rows_i8<<<(unsigned)(((uint64_t)bk.n_ranges * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, g.T, Kpad, ctx->b_A16.as<uint8_t>(), ctx->b_rowc.as<uint32_t>());
+    FE_CUDA(ctx, ctx->b_tmaps.ensure((size_t)bk.n_domains * 4 + 64));
+    k_block_norms<<<(unsigned)(((uint64_t)bk.n_ranges * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order,
+                                                                                               bk.n_ranges, g.T, 1, ctx->b_rowc.as<uint32_t>());
+    k_block_norms<<<(unsigned)(((uint64_t)bk.n_domains * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order,
+                                                                                                bk.n_domains, g.T, 3, ctx->b_tmaps.as<uint32_t>());
+    k_build_rows_i8<<<(unsigned)((bytesA / 16 + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, g.T, Kpad, ctx->b_A16.as<uint4>());
     FE_CUDA(ctx, cudaGetLastError());
-    k_build_pool_i8<<<(unsigned)(((uint64_t)bk.n_domains * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, g.T, Kpad, kc, ctx->b_B16.as<uint8_t>(), ctx->b_coln.as<uint32_t>());
+    k_build_pool_i8<<<(unsigned)((bytesB / 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, g.T, Kpad, kc, ctx->b_tmaps.as<uint32_t>(), ctx->b_B16.as<uint4>(), ctx->b_coln.as<uint32_t>());
     FE_CUDA(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches += 3;
+    ctx->stats.kernel_launches += 4;
     if (prep_done) cudaEventRecord(prep_done, ctx->stream);
 
     a.A16 = ctx->b_A16.p;

@@ -42,7 +42,7 @@ struct UmmaArgs {
 };
 
 struct UmmaBuckets {                 // operand-layout view for the blob builders
-    uint32_t range_off[8], dom_off[8], row_tile0[7], col_tile0[7];
+    uint32_t range_off[8], dom_off[8], row_tile0[8], col_tile0[8]; // [nb] entries are the totals
     uint32_t n_ranges, n_domains;
     int nb;
 };

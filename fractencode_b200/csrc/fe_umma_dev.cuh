@@ -147,3 +147,9 @@ __device__ __forceinline__ WorkItem decode_item(const UmmaArgs& a, uint32_t w) {
 
 
 } // namespace umma_dev
+
+// Per-block second moments for the operand builders, one warp per block (sorted position p -> item order[p]).
+// mode 0: range, sum (4 r - 510)^2   mode 1: range, 16 sum r^2   mode 2: domain, sum (D - 510)^2   mode 3: domain, sum D^2
+__global__ void k_block_norms(const uint8_t* img, uint32_t stride, const fe_grid_item* items, const uint32_t* order, uint32_t n, uint32_t T,
+                              int mode, uint32_t* out);
+
