@@ -289,6 +289,18 @@ def run_b200(a):
     e_times, e_items = timed(step_e2e, a.steps)
     sync_all()
 
+    # HBM-bound side of the path, measured once on rank 0: the decode gather (Decoder2's fixed-point iteration)
+    decode_info = None
+    if rank == 0:
+        items_host = np.frombuffer(host_items.numpy()[: int(e_items) * 64].tobytes(), dtype=fb.ENCODE_ITEM)
+        dec_iters = 8
+        ctx.decode(items_host, W, H, max_iters=dec_iters, eps=-1e9)  # warm-up (allocations)
+        ctx.decode(items_host, W, H, max_iters=dec_iters, eps=-1e9)
+        dms = float(ctx.stats().last_decode_ms) / dec_iters
+        dbytes = 2.0 * W * H + 64.0 * len(items_host)       # read plane + write plane + item records per iteration
+        decode_info = {"ms_per_iteration": dms, "algorithmic_bytes": dbytes, "achieved_gbs": dbytes / (dms * 1e-3) / 1e9,
+                       "note": "k_decode_step + k_sqdiff (convergence sum re-reads both planes: +2*W*H real traffic) + 8-byte D2H per iteration"}
+
     my = torch.tensor([sum(times), sum(e_times), float(matches_step), float(n_items)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = my.clone()
@@ -304,6 +316,11 @@ def run_b200(a):
         value = all_matches / (ms_per_step * 1e-3)
         e_value = all_matches / (e_ms / a.steps * 1e-3)
         ach = flops / (search_ms * 1e-3) / 1e12 if search_ms > 0 else 0.0
+        # dominant kernel = the search launch with the largest share of the step
+        dom = max(levels, key=lambda l: l["search_ms"])
+        dom_ach = 2.0 * dom["T"] ** 2 * dom["matches"] / (dom["search_ms"] * 1e-3) / 1e12 if dom["search_ms"] > 0 else 0.0
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of this workload (profiles/search_kernels_r1.md)
+        traffic_by_T = {32: 105.5e6, 16: 109.8e6, 8: 245.9e6, 4: 804.4e6} if (a.size, a.tmax, a.tmin, a.thr, a.classifier) == (4096, 32, 4, 25.0, 0) else {}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -318,9 +335,14 @@ def run_b200(a):
             "items_per_step": all_items,
             "levels": levels,
             "umma_levels": int(st.umma_levels), "exact_levels": int(st.exact_levels),
-            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": ach / pk["tflops_sustained"], "traffic": None,
-                         "kernel": "search (all levels, rank 0): 2*T^2 FLOP per match / summed CUDA-event search time; peak = sustained bf16, " + pk["source"]},
+            "roofline": {"bound": "tensor", "achieved": dom_ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": dom_ach / pk["tflops_sustained"], "traffic": traffic_by_T.get(dom["T"]),
+                         "kernel": "%s, level T=%d: 2*T^2 FLOP x %d matches per launch / CUDA-event launch time (ctx stream); peak = sustained bf16 (kernel timed inside a long step), %s" % (
+                             "k_search_umma<f16>" if dom["T"] <= 8 else "k_search_umma_i8", dom["T"], dom["matches"], pk["source"]),
+                         "all_levels": {"achieved": ach, "frac": ach / pk["tflops_sustained"]},
+                         "peak_burst": pk["tflops_burst"]},
+            "hbm_kernels": {"peak_gbs": pk["hbm_gbs"], "decode": decode_info,
+                            "prep_ms_per_level": {str(l["T"]): l["prep_ms"] for l in levels}},
             "clocks": sampler.summary(),
             "wall_s_timed_region": wall,
         }

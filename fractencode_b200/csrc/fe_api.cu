@@ -3,6 +3,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -620,37 +621,62 @@ extern "C" int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uin
     if (!ctx) return FE_ERR_INVALID;
     if ((!items && n) || !target || !width || !height || stride < width) return fe_fail(ctx, FE_ERR_INVALID, "fe_decode: bad arguments");
     if (n > 0x7FFFFFFFu || (uint64_t)width * height > 0xFFFFFFFFull) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_decode: too large");
-    // validate + layout
-    std::vector<uint32_t> pix_off(n + 1, 0);
-    bool uniform = n > 0, has_default = false;
+    // validate; group the items by block size: every group of square blocks with T % 4 == 0 runs on the 4-pixels-per-thread
+    // kernel, the rest (odd sizes, non-square) on the per-pixel kernel with prefix offsets
+    bool has_default = false;
     uint64_t area = 0;
-    const uint32_t T0 = n ? items[0].w : 0;
+    std::vector<uint32_t> sizes;   // distinct fast sizes
     for (size_t i = 0; i < n; ++i) {
         const fe_encode_item& e = items[i];
         if (!e.w || !e.h || e.x + e.w > width || e.y + e.h > height) return fe_fail(ctx, FE_ERR_INVALID, "fe_decode: item %zu outside the image", i);
         if (e.src_w && (e.src_w != e.src_h || e.match_x + e.src_w > width || e.match_y + e.src_h > height || e.transform < 0 || e.transform > 7 || e.src_w < 2))
             return fe_fail(ctx, FE_ERR_INVALID, "fe_decode: item %zu has an invalid source block", i);
-        pix_off[i] = (uint32_t)area;
         area += (uint64_t)e.w * e.h;
-        uniform = uniform && e.w == T0 && e.h == T0;
         if (!e.src_w || !e.src_h) has_default = true;
+        if (e.w == e.h && e.w % 4 == 0 && std::find(sizes.begin(), sizes.end(), e.w) == sizes.end() && sizes.size() < 8) sizes.push_back(e.w);
     }
     if (area > 0xFFFFFFFFull) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_decode: item areas overflow");
-    pix_off[n] = (uint32_t)area;
-    uniform = uniform && (T0 % 4 == 0);
+    std::vector<fe_encode_item> grouped;
+    grouped.reserve(n);
+    std::vector<size_t> goff{0};
+    std::vector<char> tiled;       // per size: every item has a 2T source block at a 4-byte aligned origin inside aligned rows
+    for (uint32_t T : sizes) {
+        bool ok = (stride % 4 == 0) && T <= 32;
+        for (size_t i = 0; i < n; ++i)
+            if (items[i].w == T && items[i].h == T) {
+                const fe_encode_item& e = items[i];
+                grouped.push_back(e);
+                ok = ok && e.src_w == 2 * T && e.src_h == 2 * T && e.match_x % 4 == 0 && e.match_y % 2 == 0 && e.x % 4 == 0;
+            }
+        goff.push_back(grouped.size());
+        tiled.push_back(ok ? 1 : 0);
+    }
+    const size_t n_fast = grouped.size();
+    std::vector<uint32_t> pix_off;
+    uint64_t slow_area = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const fe_encode_item& e = items[i];
+        if (e.w == e.h && std::find(sizes.begin(), sizes.end(), e.w) != sizes.end()) continue;
+        grouped.push_back(e);
+        pix_off.push_back((uint32_t)slow_area);
+        slow_area += (uint64_t)e.w * e.h;
+    }
+    pix_off.push_back((uint32_t)slow_area);
+    const size_t n_slow = n - n_fast;
     const bool covered = !has_default && area == (uint64_t)width * height; // non-overlapping full cover -> ping-pong needs no copy
+    const bool fused_sq = covered && n_slow == 0;                          // convergence sum inside the gather kernel
     const int iters = max_iters < 0 ? 300 : max_iters;
     const size_t bytes = (size_t)height * stride;
     FE_CUDA(ctx, cudaSetDevice(ctx->device));
     FE_CUDA(ctx, ctx->b_dec_a.ensure(bytes + 64));
     FE_CUDA(ctx, ctx->b_dec_b.ensure(bytes + 64));
-    FE_CUDA(ctx, ctx->b_dec_items.ensure(n * sizeof(fe_encode_item) + (n + 1) * 4 + 64));
-    FE_CUDA(ctx, ctx->b_dec_sum.ensure(8));
+    FE_CUDA(ctx, ctx->b_dec_items.ensure(n * sizeof(fe_encode_item) + (n_slow + 1) * 4 + 64));
+    FE_CUDA(ctx, ctx->b_dec_sum.ensure(64 * 8));
     fe_encode_item* d_items = ctx->b_dec_items.as<fe_encode_item>();
     uint32_t* d_off = reinterpret_cast<uint32_t*>(d_items + n);
     if (n) {
-        FE_CUDA(ctx, cudaMemcpyAsync(d_items, items, n * sizeof(fe_encode_item), cudaMemcpyHostToDevice, ctx->stream));
-        FE_CUDA(ctx, cudaMemcpyAsync(d_off, pix_off.data(), (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        FE_CUDA(ctx, cudaMemcpyAsync(d_items, grouped.data(), n * sizeof(fe_encode_item), cudaMemcpyHostToDevice, ctx->stream));
+        FE_CUDA(ctx, cudaMemcpyAsync(d_off, pix_off.data(), (n_slow + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     uint8_t* src = ctx->b_dec_a.as<uint8_t>();
     uint8_t* dst = ctx->b_dec_b.as<uint8_t>();
@@ -659,18 +685,31 @@ extern "C" int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uin
     cudaEventRecord(ctx->ev[0], ctx->stream);
     int i = 0;
     double rms = 0.0;
+    unsigned long long* d_sum = ctx->b_dec_sum.as<unsigned long long>();
     for (; i < iters; ++i) {
-        if (n) {
-            if (uniform)
-                LAUNCH(ctx, k_decode_step_uniform, cdiv((uint64_t)n * T0 * (T0 / 4), 256), 256, src, dst, stride, d_items, (uint32_t)n, T0, use_fma);
-            else
-                LAUNCH(ctx, k_decode_step, cdiv(area, 256), 256, src, dst, stride, d_items, d_off, (uint32_t)n, (uint32_t)area, use_fma);
+        FE_CUDA(ctx, cudaMemsetAsync(d_sum, 0, 64 * 8, ctx->stream));
+        for (size_t gidx = 0; gidx < sizes.size(); ++gidx) {
+            const uint32_t T = sizes[gidx];
+            const size_t cnt = goff[gidx + 1] - goff[gidx];
+            if (!cnt) continue;
+            if (tiled[gidx]) {
+                k_decode_step_tiled<<<cdiv(cnt, 8), 256, 8 * T * T * sizeof(uint16_t), ctx->stream>>>(src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T,
+                                                                                                    use_fma, fused_sq ? d_sum : nullptr);
+                ctx->stats.kernel_launches++;
+                FE_CUDA(ctx, cudaGetLastError());
+            } else {
+                LAUNCH(ctx, k_decode_step_uniform, cdiv((uint64_t)cnt * T * (T / 4), 256), 256, src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T,
+                       use_fma, fused_sq ? d_sum : nullptr);
+            }
         }
-        FE_CUDA(ctx, cudaMemsetAsync(ctx->b_dec_sum.p, 0, 8, ctx->stream));
-        LAUNCH(ctx, k_sqdiff, 148 * 8, 256, src, dst, width, height, stride, ctx->b_dec_sum.as<unsigned long long>());
-        unsigned long long sum64 = 0;
-        FE_CUDA(ctx, cudaMemcpyAsync(&sum64, ctx->b_dec_sum.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (n_slow)
+            LAUNCH(ctx, k_decode_step, cdiv(slow_area, 256), 256, src, dst, stride, d_items + n_fast, d_off, (uint32_t)n_slow, (uint32_t)slow_area, use_fma);
+        if (!fused_sq) LAUNCH(ctx, k_sqdiff, 148 * 8, 256, src, dst, width, height, stride, d_sum);
+        unsigned long long slots[64];
+        FE_CUDA(ctx, cudaMemcpyAsync(slots, d_sum, sizeof(slots), cudaMemcpyDeviceToHost, ctx->stream));
         FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        unsigned long long sum64 = 0;
+        for (unsigned long long v : slots) sum64 += v;
         const int32_t wrapped = (int32_t)(uint32_t)(sum64 & 0xFFFFFFFFull); // the reference's int32 accumulator (metrics.h:27)
         rms = (double)wrapped / (double)(uint32_t)(width * height);
         if (rms < rms_eps) break;

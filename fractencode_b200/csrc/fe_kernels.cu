@@ -539,28 +539,122 @@ __global__ void k_decode_step(const uint8_t* __restrict__ src, uint8_t* __restri
     dst[(size_t)(e.y + y) * stride + e.x + x] = v < 0.0 ? 0 : (v > 255.0 ? 255 : (uint8_t)v);
 }
 
-// Uniform square items of size T (every item T x T): one thread per 4 horizontal pixels, no search.
+// Square items of one size T (T % 4 == 0): one thread per 4 horizontal pixels, packed 4-byte store.  When `sq_out` is
+// given the thread also accumulates (old - new)^2 of its pixels (old = source at the same position): the convergence sum
+// of Decoder2 (metrics.h:26-36) without a second pass over both planes -- valid when the items tile the plane.
 __global__ void k_decode_step_uniform(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t stride,
-                                      const fe_encode_item* __restrict__ items, uint32_t n_items, uint32_t T, int use_fma) {
+                                      const fe_encode_item* __restrict__ items, uint32_t n_items, uint32_t T, int use_fma,
+                                      unsigned long long* __restrict__ sq_out) {
     const uint32_t segs = T / 4, per_item = T * segs;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_items * per_item) return;
-    const uint32_t i = t / per_item, q = t % per_item, y = q / segs, x0 = (q % segs) * 4;
-    const fe_encode_item e = items[i];
-    if (e.src_w == 0 || e.src_h == 0) return;
-    uint32_t packed = 0;
+    unsigned long long sq = 0;
+    if (t < n_items * per_item) {
+        const uint32_t i = t / per_item, q = t % per_item, y = q / segs, x0 = (q % segs) * 4;
+        const fe_encode_item e = items[i];
+        if (e.src_w != 0 && e.src_h != 0) {
+            uint32_t packed = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t x = x0 + k;
-        const uint32_t sx = (x * e.src_w) / T, sy = (y * e.src_h) / T;
-        const double smp = (double)sample_sum4(src, stride, e.match_x, e.match_y, e.src_w, sx, sy, e.transform) * 0.25;
-        const double v = use_fma ? __fma_rn(e.contrast, smp, e.brightness) : __dadd_rn(__dmul_rn(e.contrast, smp), e.brightness);
-        const uint32_t b = v < 0.0 ? 0u : (v > 255.0 ? 255u : (uint32_t)(uint8_t)v);
-        packed |= b << (8 * k);
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t x = x0 + k;
+                const uint32_t sx = (x * e.src_w) / T, sy = (y * e.src_h) / T;
+                const double smp = (double)sample_sum4(src, stride, e.match_x, e.match_y, e.src_w, sx, sy, e.transform) * 0.25;
+                const double v = use_fma ? __fma_rn(e.contrast, smp, e.brightness) : __dadd_rn(__dmul_rn(e.contrast, smp), e.brightness);
+                const uint32_t b = v < 0.0 ? 0u : (v > 255.0 ? 255u : (uint32_t)(uint8_t)v);
+                packed |= b << (8 * k);
+            }
+            const size_t off = (size_t)(e.y + y) * stride + e.x + x0;
+            uint8_t* o = dst + off;
+            if ((reinterpret_cast<uintptr_t>(o) & 3u) == 0) *reinterpret_cast<uint32_t*>(o) = packed;
+            else { o[0] = packed & 255; o[1] = (packed >> 8) & 255; o[2] = (packed >> 16) & 255; o[3] = packed >> 24; }
+            if (sq_out) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int d = (int)src[off + k] - (int)((packed >> (8 * k)) & 255u);
+                    sq += (unsigned long long)(d * d);
+                }
+            }
+        }
     }
-    uint8_t* o = dst + (size_t)(e.y + y) * stride + e.x + x0;
-    if ((reinterpret_cast<uintptr_t>(o) & 3u) == 0) *reinterpret_cast<uint32_t*>(o) = packed;
-    else { o[0] = packed & 255; o[1] = (packed >> 8) & 255; o[2] = (packed >> 16) & 255; o[3] = packed >> 24; }
+    if (sq_out) {
+        __shared__ unsigned long long wsum[32];
+        for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long tot = 0;
+            for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) tot += wsum[w];
+            if (tot) atomicAdd(sq_out + (blockIdx.x & 63u), tot);
+        }
+    }
+}
+
+// Decode gather for the encoder's own geometry (square T x T item, 2T x 2T source block, even origin, T % 4 == 0,
+// 4-byte aligned rows): one warp per item.  The source block is read once with coalesced 4-byte loads and reduced to the
+// T x T grid of 2x2 box sums in shared memory; every output pixel is then one shared-memory read under the item's isometry,
+// s * (D/4) + o in fp64 (the reference's arithmetic), and the row is written back as packed 4-byte stores.  Traffic per
+// iteration = one read of every source block (4x the item area, served by L2: the plane is re-read 4x but fits) + one
+// write of the plane (+ one read of the old plane for the fused convergence sum).
+__global__ void __launch_bounds__(256) k_decode_step_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t stride,
+                                                           const fe_encode_item* __restrict__ items, uint32_t n_items, uint32_t T, int use_fma,
+                                                           unsigned long long* __restrict__ sq_out) {
+    extern __shared__ uint16_t sh_box[];                       // [warps per block][T*T]
+    const uint32_t warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+    unsigned long long sq = 0;
+    if (i < n_items) {
+        const fe_encode_item e = items[i];
+        uint16_t* box = sh_box + (size_t)warp_in_block * T * T;
+        const uint32_t S = 2 * T, wpr = S / 4;                  // 4-byte words per source row
+        // pairs of source rows -> one row of box sums; a lane handles one word (4 pixels -> 2 boxes) of a row pair
+        for (uint32_t w = lane; w < T * wpr; w += 32) {
+            const uint32_t Y = w / wpr, xw = w % wpr;
+            const uint8_t* p = src + (size_t)(e.match_y + 2 * Y) * stride + e.match_x + 4 * xw;
+            const uint32_t r0 = *reinterpret_cast<const uint32_t*>(p), r1 = *reinterpret_cast<const uint32_t*>(p + stride);
+            const uint32_t b0 = (r0 & 255u) + ((r0 >> 8) & 255u) + (r1 & 255u) + ((r1 >> 8) & 255u);
+            const uint32_t b1 = ((r0 >> 16) & 255u) + (r0 >> 24) + ((r1 >> 16) & 255u) + (r1 >> 24);
+            *reinterpret_cast<uint32_t*>(box + Y * T + 2 * xw) = b0 | (b1 << 16);
+        }
+        __syncwarp();
+        const int t = e.transform;
+        const int m0 = kMapDev[t][0], m1 = kMapDev[t][1], m4 = kMapDev[t][4], m5 = kMapDev[t][5];
+        const int cx = (kMapDev[t][2] + kMapDev[t][3]) * ((int)S - 1), cy = (kMapDev[t][6] + kMapDev[t][7]) * ((int)S - 1);
+        const int ax = (m0 + m1) < 0 ? -1 : 0, ay = (m4 + m5) < 0 ? -1 : 0;     // min corner of the mapped 2x2 box
+        const uint32_t segs = T / 4;
+        for (uint32_t q = lane; q < T * segs; q += 32) {
+            const uint32_t y = q / segs, x0 = (q % segs) * 4;
+            uint32_t packed = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int lx = 2 * (int)(x0 + k), ly = 2 * (int)y;
+                const int gx = m0 * lx + m1 * ly + cx + ax, gy = m4 * lx + m5 * ly + cy + ay;
+                const double smp = (double)box[(gy >> 1) * (int)T + (gx >> 1)] * 0.25;
+                const double v = use_fma ? __fma_rn(e.contrast, smp, e.brightness) : __dadd_rn(__dmul_rn(e.contrast, smp), e.brightness);
+                const uint32_t b = v < 0.0 ? 0u : (v > 255.0 ? 255u : (uint32_t)(uint8_t)v);
+                packed |= b << (8 * k);
+            }
+            const size_t off = (size_t)(e.y + y) * stride + e.x + x0;
+            *reinterpret_cast<uint32_t*>(dst + off) = packed;
+            if (sq_out) {
+                const uint32_t old = *reinterpret_cast<const uint32_t*>(src + off);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int d = (int)((old >> (8 * k)) & 255u) - (int)((packed >> (8 * k)) & 255u);
+                    sq += (unsigned long long)(d * d);
+                }
+            }
+        }
+    }
+    if (sq_out) { // one atomic per block, spread over 64 slots: a single hot address would serialise the whole grid
+        __shared__ unsigned long long wsum[8];
+        for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+        if (lane == 0) wsum[warp_in_block] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long tot = 0;
+            for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) tot += wsum[w];
+            if (tot) atomicAdd(sq_out + (blockIdx.x & 63u), tot);
+        }
+    }
 }
 
 // sum over the plane of (a-b)^2 as uint64 (the reference accumulates in int32, metrics.h:27; the
@@ -581,7 +675,7 @@ __global__ void k_sqdiff(const uint8_t* __restrict__ a, const uint8_t* __restric
     if (threadIdx.x < 32) {
         s = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0ull;
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-        if (threadIdx.x == 0) atomicAdd(out, s);
+        if (threadIdx.x == 0) atomicAdd(out + (blockIdx.x & 63u), s);
     }
 }
 

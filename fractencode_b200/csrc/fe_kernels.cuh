@@ -41,7 +41,9 @@ __global__ void k_finalize(FinalizeArgs f);
 __global__ void k_decode_step(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items,
                               const uint32_t* pix_off, uint32_t n_items, uint32_t total_pix, int use_fma);
 __global__ void k_decode_step_uniform(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items,
-                                      uint32_t n_items, uint32_t T, int use_fma);
+                                      uint32_t n_items, uint32_t T, int use_fma, unsigned long long* sq_out);
+__global__ void k_decode_step_tiled(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items, uint32_t n_items,
+                                    uint32_t T, int use_fma, unsigned long long* sq_out);
 __global__ void k_sqdiff(const uint8_t* a, const uint8_t* b, uint32_t w, uint32_t h, uint32_t stride, unsigned long long* out);
 __global__ void k_minmax(const fe_encode_item* items, uint32_t n, unsigned long long* mm);
 __global__ void k_quantize(const fe_encode_item* items, uint32_t n, double min_s, double max_s, double min_o, double max_o,
