@@ -146,7 +146,7 @@ __device__ __forceinline__ void process_half(uint32_t (&v)[UM_HALF], RowState& s
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a) {
+__global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bytesA = UM_ROWS * a.Kpad * 2, bytesB = UM_NT * a.Kpad * 2;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < 2; ++i) {
             mbar_init(A_FULL(i), 1);
-            mbar_init(A_EMPTY(i), UM_WGS);
+            mbar_init(A_EMPTY(i), UM_ISSUERS_F16);
         }
         for (uint32_t i = 0; i < 4; ++i) {
             mbar_init(bar0 + 8 * (4 + i), 1);  // ACC_FULL: one tcgen05.commit
@@ -211,11 +211,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
                 }
             }
         }
-    } else if (warp <= UM_WGS) {
-        // ================= MMA issuer of warpgroup g = warp - 1 (one thread) =================
-        // Tiles with (global tile counter % UM_WGS) == g go to accumulators (g, 0) and (g, 1) alternately.
+    } else if (warp <= UM_ISSUERS_F16) {
+        // ================= MMA issuers: one thread per accumulator buffer (g, ib) =================
+        // Tiles with (global tile counter % UM_WGS) == g go to accumulators (g, 0) and (g, 1) alternately; the issue loop
+        // of one tile (two ~200-cycle barrier probes, the MMAs, a ~170-cycle commit) is latency bound, so each buffer has
+        // its own issuer thread and the four loops overlap.
         if (lane == 0) {
-            const uint32_t g = warp - 1;
+            const uint32_t g = UM_ISSUERS_F16 == UM_WGS ? warp - 1 : (warp - 1) >> 1;
+            const uint32_t ib = (warp - 1) & 1;
             const uint32_t idesc = ((KIND == 0 ? 1u : 2u) << 4) | ((uint32_t)(UM_NT >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
             const uint32_t nk = (a.dbg & 2) ? 0u : a.Kpad / 16;
             uint32_t it0 = 0, wi = 0, jb = 0; // jb: tiles this warpgroup has been given so far
@@ -232,7 +235,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
                 for (uint32_t kk = 0; kk < UM_MAX_NK; ++kk) adesc[kk] = make_desc(a_addr + kk * 2 * (UM_ROWS * 16), UM_ROWS * 16, 128);
                 for (uint32_t u = first; u < n; u += UM_WGS, ++jb) {
                     const uint32_t gi = it0 + u, s = gi & (UM_STAGES - 1), buf = jb & 1;
-                    mbar_wait(ACC_EMPTY(g, buf), ((jb >> 1) & 1) ^ 1);   // all four warps have copied the previous use to registers
+                    if (UM_ISSUERS_F16 != UM_WGS && buf != ib) continue;  // (with one issuer per buffer) the other issuer owns that buffer
+                    mbar_wait(ACC_EMPTY(g, buf), ((jb >> 1) & 1) ^ 1);   // all eight warps have copied the previous use to registers
                     mbar_wait(B_FULL(s), (gi / UM_STAGES) & 1);          // the tile's B stage has landed
                     tc_fence_after();
                     const uint32_t b_addr = smem_u32(sB + (size_t)s * bytesB);
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma(const UmmaArgs a)
         // to) and columns h*64..+63 of the group's accumulators, i.e. every thread owns one row x 64 columns of a
         // tile.  Four compute warps per SM sub-partition hide the TMEM-load and FMNMX3 latencies of each other;
         // an accumulator goes back to the issuer as soon as all eight warps hold their part in registers.
-        const uint32_t cw = warp - 1 - UM_WGS;
+        const uint32_t cw = warp - 1 - UM_ISSUERS_F16;
         const uint32_t g = cw >> 3;
         const uint32_t h = (cw >> 2) & 1;             // column half
         const uint32_t sp = warp & 3;                 // TMEM sub-partition this warp may read
@@ -540,7 +544,7 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     const size_t smem = (size_t)a_bytes + (size_t)stages * stage_bytes + (12 + 2 * UM_MAX_STAGES) * 8 + 64;
     FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const uint32_t grid = (uint32_t)std::min<uint64_t>(total_items, 148);
-    k_search_umma<0><<<grid, UM_THREADS, smem, ctx->stream>>>(a);
+    k_search_umma<0><<<grid, UM_THREADS_F16, smem, ctx->stream>>>(a);
     FE_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches++;
     uint32_t f = 0;

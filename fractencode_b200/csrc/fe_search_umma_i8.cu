@@ -19,7 +19,7 @@ using namespace umma_dev;
 namespace {
 
 template <int DUMMY>
-__global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma_i8(const UmmaArgs a) {
+__global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_umma_i8(const UmmaArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t Kpad = a.Kpad;
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma_i8(const UmmaArgs
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < 2; ++i) {
             mbar_init(A_FULL(i), 1);
-            mbar_init(A_EMPTY(i), UM_WGS);
+            mbar_init(A_EMPTY(i), UM_ISSUERS_I8);
         }
         for (uint32_t i = 0; i < 4; ++i) {
             mbar_init(bar0 + 8 * (4 + i), 1);
@@ -101,10 +101,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma_i8(const UmmaArgs
                 }
             }
         }
-    } else if (warp <= UM_WGS) {
-        // ================= MMA issuer of warpgroup g =================
+    } else if (warp <= UM_ISSUERS_I8) {
+        // ================= MMA issuers: one thread per accumulator buffer (g, ib) =================
         if (lane == 0) {
-            const uint32_t g = warp - 1;
+            const uint32_t g = (warp - 1) >> 1, ib = (warp - 1) & 1;
             // D = S32, A = B = unsigned 8 bit, K-major both, N = 64, M = 128
             const uint32_t idesc = (2u << 4) | ((uint32_t)(I8_NT >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
             const uint32_t nj = kc / 32; // MMAs (K = 32 bytes) per stage and plane
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma_i8(const UmmaArgs
                 bool any = false;
                 for (uint32_t u = first; u < n; u += UM_WGS, ++jb) {
                     const uint32_t gi = it0 + u, buf = jb & 1;
+                    if (buf != ib) continue;
                     const uint32_t d_lo = tmem_base + (g * 2 + buf) * 2 * I8_NT, d_hi = d_lo + I8_NT;
                     mbar_wait(ACC_EMPTY(g, buf), ((jb >> 1) & 1) ^ 1);
                     for (uint32_t c = 0; c < nch; ++c) {
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_search_umma_i8(const UmmaArgs
         }
     } else {
         // ================= compute warps: thread = one row x 32 columns =================
-        const uint32_t cw = warp - 1 - UM_WGS;
+        const uint32_t cw = warp - 1 - UM_ISSUERS_I8;
         const uint32_t g = cw >> 3;
         const uint32_t h = (cw >> 2) & 1;             // column half (32 columns)
         const uint32_t sp = warp & 3;
@@ -399,7 +400,7 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     const size_t smem = (size_t)a.n_abuf * a_bytes + (size_t)stages * stage_bytes + (12 + 2 * I8_MAX_STAGES) * 8 + 128;
     FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma_i8<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const uint32_t grid = (uint32_t)std::min<uint64_t>(total_items, 148);
-    k_search_umma_i8<0><<<grid, UM_THREADS, smem, ctx->stream>>>(a);
+    k_search_umma_i8<0><<<grid, UM_THREADS_I8, smem, ctx->stream>>>(a);
     FE_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches++;
     return FE_OK;
