@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bytesA = UM_ROWS * a.Kpad * 2, bytesB = UM_NT * a.Kpad * 2;
-    const uint32_t S = UM_STAGES;
+    const uint32_t S = 2 * UM_ISSUERS_F16;   // two B stages per issuer
     uint8_t* sA = smem;                     // 2 buffers
     uint8_t* sB = smem + 2 * bytesA;        // S stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)S * bytesB);
@@ -187,73 +187,106 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ================= producer: bulk async copies (TMA engine) =================
+    if (warp < UM_ISSUERS_F16) {
+        // ================= issuers: one thread per accumulator buffer (g, ib), each also its own producer =================
+        // Issuer (g, ib) owns accumulator (g, ib), the two B stages 2*(2g+ib), 2*(2g+ib)+1 and every tile whose global
+        // counter is congruent to g + 2*ib modulo 4.  Per tile it (1) waits for the MMAs of its previous tile (its own
+        // commit barrier) and refills that tile's stage with the bulk copy of the tile two steps ahead, (2) waits for this
+        // tile's stage and for the compute warps to have drained the accumulator, (3) issues the MMAs and one commit.  The
+        // four latency-bound loops overlap; there is no separate producer warp (20 warps = 5 per SM sub-partition keeps
+        // the 96 registers the compute threads need).  Issuer (0,0) additionally keeps the two A buffers filled.
         if (lane == 0) {
-            uint32_t it = 0, wi = 0;
-            for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x, ++wi) {
-                const WorkItem item = decode_item(a, w);
-                const uint32_t ab = wi & 1;
-                mbar_wait(A_EMPTY(ab), ((wi >> 1) & 1) ^ 1);
-                mbar_expect_tx(A_FULL(ab), bytesA);
-                bulk_g2s(smem_u32(sA + ab * bytesA), reinterpret_cast<const uint8_t*>(a.A16) + (size_t)item.a_blob * bytesA, bytesA, A_FULL(ab));
-                for (uint32_t t = item.t0; t < item.t1; ++t, ++it) {
-                    const uint32_t s = it & (UM_STAGES - 1);
-                    if (it >= UM_STAGES) {
-                        // the stage was last read by tile q = it - 4; its MMAs are done when its accumulator is full
-                        // (tile q belongs to warpgroup q & 1, is that group's (q >> 1)-th tile, buffer (q >> 1) & 1)
-                        const uint32_t q = it - UM_STAGES, jq = q >> 1;
-                        mbar_wait(ACC_FULL(q & 1, jq & 1), (jq >> 1) & 1);
-                    }
-                    if (a.dbg & 4) { mbar_arrive(B_FULL(s)); continue; }
-                    mbar_expect_tx(B_FULL(s), bytesB);
-                    bulk_g2s(smem_u32(sB + (size_t)s * bytesB), reinterpret_cast<const uint8_t*>(a.B16) + (size_t)t * bytesB, bytesB, B_FULL(s));
-                }
-            }
-        }
-    } else if (warp <= UM_ISSUERS_F16) {
-        // ================= MMA issuers: one thread per accumulator buffer (g, ib) =================
-        // Tiles with (global tile counter % UM_WGS) == g go to accumulators (g, 0) and (g, 1) alternately; the issue loop
-        // of one tile (two ~200-cycle barrier probes, the MMAs, a ~170-cycle commit) is latency bound, so each buffer has
-        // its own issuer thread and the four loops overlap.
-        if (lane == 0) {
-            const uint32_t g = UM_ISSUERS_F16 == UM_WGS ? warp - 1 : (warp - 1) >> 1;
-            const uint32_t ib = (warp - 1) & 1;
-            const uint32_t idesc = ((KIND == 0 ? 1u : 2u) << 4) | ((uint32_t)(UM_NT >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
+            const uint32_t g = warp >> 1, ib = warp & 1, res = g + 2 * ib;
+            const uint32_t sb = 2 * warp;                                  // first of this issuer's two stages
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(UM_NT >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
             const uint32_t nk = (a.dbg & 2) ? 0u : a.Kpad / 16;
-            uint32_t it0 = 0, wi = 0, jb = 0; // jb: tiles this warpgroup has been given so far
-            for (uint32_t w = blockIdx.x; w < a.total_items; w += gridDim.x, ++wi) {
-                const WorkItem item = decode_item(a, w);
-                const uint32_t ab = wi & 1, n = item.t1 - item.t0;
-                const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
-                mbar_wait(A_FULL(ab), (wi >> 1) & 1);
-                const uint32_t a_addr = smem_u32(sA + ab * bytesA);
-                bool any = false;
-                // descriptors of the A tile for every K step (constant over the item)
-                uint64_t adesc[UM_MAX_NK];
-#pragma unroll
-                for (uint32_t kk = 0; kk < UM_MAX_NK; ++kk) adesc[kk] = make_desc(a_addr + kk * 2 * (UM_ROWS * 16), UM_ROWS * 16, 128);
-                for (uint32_t u = first; u < n; u += UM_WGS, ++jb) {
-                    const uint32_t gi = it0 + u, s = gi & (UM_STAGES - 1), buf = jb & 1;
-                    if (UM_ISSUERS_F16 != UM_WGS && buf != ib) continue;  // (with one issuer per buffer) the other issuer owns that buffer
-                    mbar_wait(ACC_EMPTY(g, buf), ((jb >> 1) & 1) ^ 1);   // all eight warps have copied the previous use to registers
-                    mbar_wait(B_FULL(s), (gi / UM_STAGES) & 1);          // the tile's B stage has landed
-                    tc_fence_after();
-                    const uint32_t b_addr = smem_u32(sB + (size_t)s * bytesB);
-                    const uint32_t d_tmem = tmem_base + (g * 2 + buf) * UM_NT;
-#pragma unroll
-                    for (uint32_t kk = 0; kk < UM_MAX_NK; ++kk) {
-                        if (kk < nk) {
-                            // chunk-major blobs: K chunk c (8 halves = 16 bytes) of all rows is contiguous
-                            const uint64_t bdesc = make_desc(b_addr + kk * 2 * (UM_NT * 16), UM_NT * 16, 128);
-                            tc_mma<KIND>(d_tmem, adesc[kk], bdesc, idesc, kk > 0 ? 1u : 0u);
-                        }
-                    }
-                    tc_commit(ACC_FULL(g, buf)); // also tells the producer that stage s can be refilled
-                    any = true;
+            struct Cursor {
+                uint32_t w, wi, it0, u, n;
+                WorkItem item;
+                bool valid;
+            };
+            auto load_item = [&](Cursor& c) {
+                c.valid = c.w < a.total_items;
+                if (c.valid) { c.item = decode_item(a, c.w); c.n = c.item.t1 - c.item.t0; }
+            };
+            Cursor ld, mm;
+            ld.w = mm.w = blockIdx.x; ld.wi = mm.wi = 0; ld.it0 = mm.it0 = 0;
+            load_item(ld);
+            mm = ld;
+            // ---- A tiles (issuer 0 only): A(wi) lives in buffer wi & 1 ----
+            auto load_A = [&](uint32_t wi_load) {
+                const uint32_t wl = blockIdx.x + wi_load * gridDim.x;
+                if (wl >= a.total_items) return;
+                const WorkItem it = decode_item(a, wl);
+                const uint32_t ab = wi_load & 1;
+                if (wi_load >= 2) mbar_wait(A_EMPTY(ab), ((wi_load >> 1) & 1) ^ 1);   // all four issuers are done with A(wi_load - 2)
+                mbar_expect_tx(A_FULL(ab), bytesA);
+                bulk_g2s(smem_u32(sA + ab * bytesA), reinterpret_cast<const uint8_t*>(a.A16) + (size_t)it.a_blob * bytesA, bytesA, A_FULL(ab));
+            };
+            if (warp == 0) { load_A(0); load_A(1); }
+            // ---- cursor movement; the MMA cursor signs off every item it leaves (A_EMPTY needs all four issuers) ----
+            bool mm_had_tiles = false;
+            auto next_item = [&](Cursor& c, bool is_mm) {
+                if (is_mm) {
+                    if (mm_had_tiles) tc_commit(A_EMPTY(c.wi & 1)); else mbar_arrive(A_EMPTY(c.wi & 1));
+                    mm_had_tiles = false;
+                    if (warp == 0) load_A(c.wi + 2);
                 }
-                if (any) tc_commit(A_EMPTY(ab)); else mbar_arrive(A_EMPTY(ab));
-                it0 += n;
+                c.it0 += c.n; c.w += gridDim.x; ++c.wi;
+                load_item(c);
+            };
+            auto seek = [&](Cursor& c, bool is_mm) {
+                while (c.valid) {
+                    c.u = (res + 4 - (c.it0 & 3)) & 3;
+                    if (c.u < c.n) return;
+                    next_item(c, is_mm);
+                }
+            };
+            auto advance = [&](Cursor& c, bool is_mm) {
+                c.u += 4;
+                if (c.u >= c.n) { next_item(c, is_mm); seek(c, is_mm); }
+            };
+            seek(ld, false);
+            seek(mm, true);
+            uint32_t m_ld = 0, m = 0;      // tiles loaded / issued by this issuer so far
+            auto load_B = [&]() {           // bulk copy of the load cursor's tile into stage sb + (m_ld & 1)
+                const uint32_t s = sb + (m_ld & 1);
+                if (m_ld >= 2) mbar_wait(ACC_FULL(g, ib), (m_ld - 2) & 1);   // the stage's previous tile: its MMAs have completed
+                if (a.dbg & 4) mbar_arrive(B_FULL(s));
+                else {
+                    mbar_expect_tx(B_FULL(s), bytesB);
+                    bulk_g2s(smem_u32(sB + (size_t)s * bytesB), reinterpret_cast<const uint8_t*>(a.B16) + (size_t)(ld.item.t0 + ld.u) * bytesB, bytesB, B_FULL(s));
+                }
+                ++m_ld;
+                advance(ld, false);
+            };
+            if (ld.valid) load_B();
+            if (ld.valid) load_B();
+            uint32_t cur_wi = 0xFFFFFFFFu, a_addr = 0;
+            while (mm.valid) {
+                // refill: tile m+1 goes into the stage of tile m-1, whose MMAs were issued one iteration ago
+                if (m >= 1 && ld.valid) load_B();
+                if (mm.wi != cur_wi) {       // first tile of this issuer in a new item: its A tile must have landed
+                    cur_wi = mm.wi;
+                    mbar_wait(A_FULL(cur_wi & 1), (cur_wi >> 1) & 1);
+                    a_addr = smem_u32(sA + (cur_wi & 1) * bytesA);
+                }
+                const uint32_t s = sb + (m & 1);
+                mbar_wait(B_FULL(s), (m >> 1) & 1);
+                mbar_wait(ACC_EMPTY(g, ib), (m & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(sB + (size_t)s * bytesB);
+                const uint32_t d_tmem = tmem_base + (g * 2 + ib) * UM_NT;
+                for (uint32_t kk = 0; kk < nk; ++kk) {
+                    // chunk-major blobs: K chunk c (8 halves = 16 bytes) of all rows is contiguous
+                    const uint64_t adesc = make_desc(a_addr + kk * 2 * (UM_ROWS * 16), UM_ROWS * 16, 128);
+                    const uint64_t bdesc = make_desc(b_addr + kk * 2 * (UM_NT * 16), UM_NT * 16, 128);
+                    tc_mma<KIND>(d_tmem, adesc, bdesc, idesc, kk > 0 ? 1u : 0u);
+                }
+                tc_commit(ACC_FULL(g, ib));
+                mm_had_tiles = true;
+                ++m;
+                advance(mm, true);
             }
         }
     } else {
@@ -262,7 +295,7 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
         // to) and columns h*64..+63 of the group's accumulators, i.e. every thread owns one row x 64 columns of a
         // tile.  Four compute warps per SM sub-partition hide the TMEM-load and FMNMX3 latencies of each other;
         // an accumulator goes back to the issuer as soon as all eight warps hold their part in registers.
-        const uint32_t cw = warp - 1 - UM_ISSUERS_F16;
+        const uint32_t cw = warp - UM_ISSUERS_F16;
         const uint32_t g = cw >> 3;
         const uint32_t h = (cw >> 2) & 1;             // column half
         const uint32_t sp = warp & 3;                 // TMEM sub-partition this warp may read
@@ -538,7 +571,7 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     a.nt = UM_NT;
     { const char* e = getenv("FE_UMMA_DBG"); a.dbg = e ? (uint32_t)atoi(e) : 0u; }
     const uint32_t stage_bytes = UM_NT * Kpad * 2, a_bytes = 2 * UM_ROWS * Kpad * 2;
-    const uint32_t stages = UM_STAGES;
+    const uint32_t stages = 2 * UM_ISSUERS_F16;
     a.stages = stages;
     if (Kpad / 16 > UM_MAX_NK) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "umma: K too large");
     const size_t smem = (size_t)a_bytes + (size_t)stages * stage_bytes + (12 + 2 * UM_MAX_STAGES) * 8 + 64;

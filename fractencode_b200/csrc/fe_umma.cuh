@@ -9,11 +9,12 @@ constexpr int UM_ROWS = 128;       // rows per tile = 32 ranges x 4 rotations (U
 constexpr int UM_WGS = 2;          // compute warpgroups (each owns 2 TMEM accumulators of UM_NT columns)
 constexpr int UM_HALF = UM_NT / 2;   // columns a compute thread holds per register set
 // MMA-issuer warps.  kind::i8 kernel: one issuer thread per accumulator buffer (4): the issue loop of a tile is latency bound
-// (barrier probes ~200 cycles, commit ~170) and four loops overlap.  kind::f16 kernel: one per warpgroup (2) -- its compute
-// threads need 96 registers, and a 21st warp would put six warps on one SM sub-partition (16384 registers) and cap them at 80.
-constexpr int UM_ISSUERS_F16 = UM_WGS;
+// (barrier probes ~200 cycles, commit ~170) and four loops overlap.  The kind::f16 kernel's compute threads need 96 registers:
+// a 21st warp would put six warps on one SM sub-partition (16384 registers) and cap them at 80, so there the four issuers
+// are also their own producers and no producer warp exists (20 warps).
+constexpr int UM_ISSUERS_F16 = 2 * UM_WGS;
 constexpr int UM_ISSUERS_I8 = 2 * UM_WGS;
-constexpr int UM_THREADS_F16 = 32 + 32 * UM_ISSUERS_F16 + 256 * UM_WGS; // producer warp, issuer warps, 8 compute warps per group
+constexpr int UM_THREADS_F16 = 32 * UM_ISSUERS_F16 + 256 * UM_WGS;      // issuer warps (each its own producer), 8 compute warps per group
 constexpr int UM_THREADS_I8 = 32 + 32 * UM_ISSUERS_I8 + 256 * UM_WGS;
 constexpr int UM_MAX_STAGES = 8;
 constexpr int UM_STAGES = 4;       // B stages: tile t reuses the stage of tile t-4, freed by that tile's accumulator-full commit

@@ -33,7 +33,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t probes = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++probes > (1u << 26)) __trap();
+        if (++probes > (1u << 24)) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
