@@ -101,14 +101,33 @@ __device__ __forceinline__ void process_half(uint32_t (&v)[UM_HALF], RowState& s
         t1 = fmin3(t1, grp[k + 2], grp[k + 3]);
     }
     const float tmin = fminf(t0, t1);
-    const bool improve = row_ok && tmin < st.bestV;
-    const bool tie = row_ok && tmin == st.bestV;                     // an equal V with even parity could win
-    const bool need_hit = row_ok && st.hit == FE_NONE32 && tmin <= st.vthr0;
+    // A row that already crossed the threshold is finished for this work item: its range is decided by the first hit in
+    // scan order, and no later column can come earlier (columns are visited in increasing order).
+    const bool live = row_ok && st.hit == FE_NONE32;
+    const bool improve = live && tmin < st.bestV;
+    const bool tie = live && tmin == st.bestV;                       // an equal V with even parity could win
+    const bool need_hit = live && tmin <= st.vthr0;
     if (improve | tie | need_hit) {
-        bool full = need_hit;
+        if (need_hit) {
+            // first column with V <= vthr(parity): walk the groups of 8 in order, look inside the first that can hold one
+            uint32_t chit = FE_NONE32;
+#pragma unroll
+            for (int k = 0; k < UM_HALF / 8; ++k) {
+                if (chit == FE_NONE32 && grp[k] <= st.vthr0) {
+                    const uint32_t pw = par[(8 * k) >> 5] >> ((8 * k) & 31);
+#pragma unroll
+                    for (int e = 7; e >= 0; --e) {
+                        const float x = __uint_as_float(v[8 * k + e]);
+                        if (x <= (((pw >> e) & 1u) ? st.vthr1 : st.vthr0)) chit = (uint32_t)(8 * k + e);
+                    }
+                }
+            }
+            if (chit != FE_NONE32) { st.hit = colbase + chit; return; }
+        }
+        bool full = false;
         if (tie) {
             if (st.bestp == 2) st.bestp = row_parity(st, st.bestcol);
-            full = full | (st.bestp == 1);
+            full = st.bestp == 1;
         }
         if (improve && !full) {
             // common case: the minimum is held by exactly one column -> it is the best of these columns
@@ -140,12 +159,13 @@ __device__ __forceinline__ void process_half(uint32_t (&v)[UM_HALF], RowState& s
         }
         if (full) {
             if (st.bestp == 2 && st.bestcol != FE_NONE32) st.bestp = row_parity(st, st.bestcol);
-            scan_half_full(v, st, improve | tie, need_hit, colbase, par);
+            scan_half_full(v, st, true, false, colbase, par);
         }
     }
 }
 
-template <int KIND>
+// RETIRE: retire quads of rows after their first threshold hit (extra per-thread state: worth it on the ALU-bound T=4 level)
+template <int KIND, bool RETIRE>
 __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -323,6 +343,11 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
             }
             const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
             const uint32_t my_tiles = first < n ? (n - first + UM_WGS - 1) / UM_WGS : 0;
+            // Threshold runs: a range is decided by its first hit in scan order, so once any of its four rotation rows
+            // (four adjacent lanes) has crossed the threshold the whole quad is retired for the rest of the item, and a
+            // warp whose 32 rows are all retired only keeps the accumulator hand-shake going.
+            bool retired = !row_ok;
+            bool warp_done = false;
             for (uint32_t j = 0; j < my_tiles; ++j, ++jb) {
                 const uint32_t u = first + j * UM_WGS, buf = jb & 1;
                 const uint32_t colbase = u * UM_NT + h * UM_HALF;
@@ -332,7 +357,7 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                 uint32_t v[UM_HALF];
                 mbar_wait(ACC_FULL(g, buf), (jb >> 1) & 1);
                 tc_fence_after();
-                if (!(a.dbg & 1)) {
+                if (!(a.dbg & 1) && !(RETIRE && warp_done)) {
                     const uint32_t taddr = lane_addr + (g * 2 + buf) * UM_NT;
                     TMEM_LD32(taddr, (v + 0));
                     TMEM_LD32(taddr + 32, (v + 32));
@@ -341,7 +366,15 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ACC_EMPTY(g, buf));
-                if (!(a.dbg & 1)) process_half(v, st, row_ok, colbase, nvalid, par);
+                if (!(a.dbg & 1) && !(RETIRE && warp_done)) {
+                    process_half(v, st, RETIRE ? !retired : row_ok, colbase, nvalid, par);
+                    if (RETIRE && (j & 3) == 3) {   // every 4th tile is enough: retirement only saves work
+                        uint32_t hm = __ballot_sync(0xFFFFFFFFu, st.hit != FE_NONE32);
+                        hm = (hm | (hm >> 1) | (hm >> 2) | (hm >> 3)) & 0x11111111u;   // one bit per quad of lanes
+                        retired = retired || (((hm * 15u) >> lane) & 1u);
+                        warp_done = __all_sync(0xFFFFFFFFu, retired);
+                    }
+                }
             }
             it0 += n;
             if (row_ok) {
@@ -575,9 +608,12 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     a.stages = stages;
     if (Kpad / 16 > UM_MAX_NK) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "umma: K too large");
     const size_t smem = (size_t)a_bytes + (size_t)stages * stage_bytes + (12 + 2 * UM_MAX_STAGES) * 8 + 64;
-    FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const bool retire = use_thr && g.T == 4;
+    FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const uint32_t grid = (uint32_t)std::min<uint64_t>(total_items, 148);
-    k_search_umma<0><<<grid, UM_THREADS_F16, smem, ctx->stream>>>(a);
+    if (retire) k_search_umma<0, true><<<grid, UM_THREADS_F16, smem, ctx->stream>>>(a);
+    else k_search_umma<0, false><<<grid, UM_THREADS_F16, smem, ctx->stream>>>(a);
     FE_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches++;
     uint32_t f = 0;
