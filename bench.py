@@ -320,7 +320,7 @@ def run_b200(a):
         dom = max(levels, key=lambda l: l["search_ms"])
         dom_ach = 2.0 * dom["T"] ** 2 * dom["matches"] / (dom["search_ms"] * 1e-3) / 1e12 if dom["search_ms"] > 0 else 0.0
         # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of this workload (profiles/search_kernels_r1.md)
-        traffic_by_T = {32: 105.5e6, 16: 109.8e6, 8: 245.9e6, 4: 804.4e6} if (a.size, a.tmax, a.tmin, a.thr, a.classifier) == (4096, 32, 4, 25.0, 0) else {}
+        traffic_by_T = {32: 107.1e6, 16: 109.6e6, 8: 245.9e6, 4: 3425.8e6} if (a.size, a.tmax, a.tmin, a.thr, a.classifier) == (4096, 32, 4, 25.0, 0) else {}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -39,8 +39,6 @@
 
 namespace {
 
-constexpr uint32_t kStagesMaxBytes = 200 * 1024;
-
 using namespace umma_dev;
 
 // 128 accumulator values of one row -> running (bestV, bestp, bestcol) and first threshold hit.
@@ -181,9 +179,6 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
     auto ACC_EMPTY = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (8 + 2 * g + b); };
     auto B_FULL = [&](uint32_t i) { return bar0 + 8 * (12 + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * UM_MAX_STAGES);
-    const uint32_t flag0 = smem_u32(tmem_slot + 4);   // [0..3] accumulator releases (one per compute warp), [4] B tiles landed
-    auto ACC_FREE = [&](uint32_t g, uint32_t b) { return flag0 + 4 * (2 * g + b); };
-    const uint32_t B_READY = flag0 + 16;
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < 2; ++i) {
@@ -195,7 +190,6 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
             mbar_init(bar0 + 8 * (8 + i), 8);  // ACC_EMPTY: one arrive per compute warp of the warpgroup
         }
         for (uint32_t i = 0; i < S; ++i) mbar_init(B_FULL(i), 1);
-        for (uint32_t i = 0; i < 5; ++i) tmem_slot[4 + i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {

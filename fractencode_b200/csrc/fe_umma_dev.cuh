@@ -107,11 +107,6 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
-__device__ __forceinline__ float min32(const uint32_t (&v)[32], float m) {
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) m = fmin3(m, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-    return m;
-}
 
 struct WorkItem {
     uint32_t a_blob;   // row-tile index (A blob)
