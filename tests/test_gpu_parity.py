@@ -175,3 +175,42 @@ def test_error_codes(ctx):
     assert e.value.code == -1  # FE_ERR_INVALID: outside the image
     with pytest.raises(fb.FractencodeError):
         ctx.encode_quadtree(24, 4, fb.Params())  # not a power of two
+
+
+def test_empty_and_degenerate_inputs(ctx, fo):
+    """Empty range list, empty domain list (default items), a single range, image smaller than one domain."""
+    import fractencode_b200 as fb
+    img = fo.synth_image(64, 64, 3, 0)
+    ctx.set_image(img)
+    dom, rng = fb.uniform_grid(64, 64, 16, 8), fb.uniform_grid(64, 64, 8, 8)
+    assert len(ctx.encode_level(dom, rng[:0], fb.Params())) == 0
+    out = ctx.encode_level(dom[:0], rng, fb.Params(0.0, -1.0, True))
+    assert (out["distance"] == 100000.0).all() and (out["src_w"] == 0).all() and (out["x"] == rng["x"]).all()
+    one = ctx.encode_level(dom, rng[5:6], fb.Params())
+    assert_items_equal(one, fo.encode_level(img, img, dom, rng[5:6], fo.params()))
+    # quadtree on an image with no room for a 2T domain at the top level: the top level yields default items and splits
+    small = fo.synth_image(32, 32, 3, 0)
+    ctx.set_image(small)
+    got, counts = ctx.encode_quadtree(32, 8, fb.Params(5.0))
+    want, wcounts = fo.encode_quadtree(small, 32, 8, fo.params(5.0))
+    assert counts == wcounts
+    assert_items_equal(got, want)
+
+
+def test_largest_block_size_and_padded_stride_quadtree(ctx, fo):
+    """T = 64 (largest supported range block, exact integer path) and a quadtree on a plane with stride > width."""
+    import fractencode_b200 as fb
+    buf = np.zeros((256, 256 + 64), np.uint8)
+    buf[:, :256] = fo.synth_image(256, 256, 11, 0)
+    img = buf[:, :256]
+    ctx.set_image(img)
+    dom, rng = fb.uniform_grid(256, 256, 128, 64), fb.uniform_grid(256, 256, 64, 64)
+    got = ctx.encode_level(dom, rng, fb.Params(0.0))
+    assert_items_equal(got, fo.encode_level(img, img, dom, rng, fo.params(0.0)), "T=64")
+    got, counts = ctx.encode_quadtree(32, 4, fb.Params(40.0, 1.5, True))
+    want, wcounts = fo.encode_quadtree(img, 32, 4, fo.params(40.0, 1.5, True))
+    assert counts == wcounts
+    assert_items_equal(got, want, "padded-stride quadtree")
+    with pytest.raises(fb.FractencodeError) as e:
+        ctx.encode_level(fb.uniform_grid(256, 256, 256, 128), fb.uniform_grid(256, 256, 128, 128), fb.Params())
+    assert e.value.code == -2  # T = 128 > 64
