@@ -61,7 +61,7 @@ _LIB = None
 EXPORTS = [
     "fe_abi_version", "fe_create", "fe_destroy", "fe_last_error", "fe_set_image", "fe_set_images", "fe_set_image_device",
     "fe_classify", "fe_encode_level", "fe_encode_quadtree", "fe_encode_quadtree_device", "fe_fetch_items", "fe_device_items",
-    "fe_decode", "fe_copy_items", "fe_quantize", "fe_get_stats", "fe_stats_reset", "fe_synchronize", "fe_set_synthetic_image", "fe_get_image",
+    "fe_decode", "fe_copy_items", "fe_quantize", "fe_pack_items", "fe_unpack_items", "fe_get_stats", "fe_stats_reset", "fe_synchronize", "fe_set_synthetic_image", "fe_get_image",
 ]
 
 
@@ -93,6 +93,8 @@ def load_library():
         "fe_decode": (i32, [vp, vp, sz, vp, u32, u32, u32, i32, dbl, i32, C.POINTER(C.c_int), C.POINTER(dbl)]),
         "fe_copy_items": (i32, [vp, vp, vp, u32, u32, u32, vp, sz, i32]),
         "fe_quantize": (i32, [vp, vp, sz, i32, i32, vp, vp, vp]),
+        "fe_pack_items": (i32, [vp, vp, sz, u32, i32, i32, vp, vp]),
+        "fe_unpack_items": (i32, [vp, vp, sz, u32, i32, i32, vp, i32, vp]),
         "fe_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "fe_stats_reset": (i32, [vp]),
         "fe_synchronize": (i32, [vp]),
@@ -246,6 +248,21 @@ class Context:
         mm = np.zeros(4, np.float64)
         self._check(self.lib.fe_quantize(self.h, items.ctypes.data, len(items), bits_s, bits_o, qs.ctypes.data, qo.ctypes.data, mm.ctypes.data))
         return qs, qo, mm
+
+    def pack_items(self, items: np.ndarray, t_max: int, bits_s: int = 5, bits_o: int = 7):
+        """64-bit packed quantised records + the (min_s, max_s, min_o, max_o) header."""
+        items = np.ascontiguousarray(items, ENCODE_ITEM)
+        packed = np.zeros(len(items), np.uint64)
+        mm = np.zeros(4, np.float64)
+        self._check(self.lib.fe_pack_items(self.h, items.ctypes.data, len(items), t_max, bits_s, bits_o, packed.ctypes.data, mm.ctypes.data))
+        return packed, mm
+
+    def unpack_items(self, packed: np.ndarray, t_max: int, mm: np.ndarray, bits_s: int = 5, bits_o: int = 7, fma: bool = False) -> np.ndarray:
+        packed = np.ascontiguousarray(packed, np.uint64)
+        mm = np.ascontiguousarray(mm, np.float64)
+        out = np.zeros(len(packed), ENCODE_ITEM)
+        self._check(self.lib.fe_unpack_items(self.h, packed.ctypes.data, len(packed), t_max, bits_s, bits_o, mm.ctypes.data, int(fma), out.ctypes.data))
+        return out
 
     # ---- misc ----
     def stats(self) -> Stats:

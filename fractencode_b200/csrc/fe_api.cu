@@ -803,3 +803,64 @@ extern "C" int fe_quantize(fe_ctx* ctx, const fe_encode_item* items, size_t n, i
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FE_OK;
 }
+
+// -------------------------------------------------------------------------------------------------
+// packed quantised records
+// -------------------------------------------------------------------------------------------------
+static int list_minmax(fe_ctx* ctx, const fe_encode_item* d_items, size_t n, double mm_out[4]) {
+    unsigned long long mm[4] = {FE_INF64, 0, FE_INF64, 0};
+    unsigned long long* d_mm = reinterpret_cast<unsigned long long*>(ctx->b_q.as<uint8_t>());
+    FE_CUDA(ctx, cudaMemcpyAsync(d_mm, mm, sizeof(mm), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_minmax, 148 * 4, 256, d_items, (uint32_t)n, d_mm);
+    FE_CUDA(ctx, cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    mm_out[0] = std::fmin(1.7976931348623157e308, key_to_double(mm[0]));
+    mm_out[1] = std::fmax(-1.0, key_to_double(mm[1]));
+    mm_out[2] = std::fmin(1.7976931348623157e308, key_to_double(mm[2]));
+    mm_out[3] = std::fmax(-1.0, key_to_double(mm[3]));
+    return FE_OK;
+}
+
+extern "C" int fe_pack_items(fe_ctx* ctx, const fe_encode_item* items, size_t n, uint32_t t_max, int bits_s, int bits_o,
+                             uint64_t* packed_out, double minmax_out[4]) {
+    if (!ctx) return FE_ERR_INVALID;
+    if (!items || !n || !packed_out || !minmax_out) return fe_fail(ctx, FE_ERR_INVALID, "fe_pack_items: null or empty input");
+    if (bits_s < 2 || bits_s > 5 || bits_o < 2 || bits_o > 7) return fe_fail(ctx, FE_ERR_INVALID, "fe_pack_items: bits_s in 2..5, bits_o in 2..7");
+    if (!t_max || (t_max & (t_max - 1)) || n > 0x7FFFFFFFu) return fe_fail(ctx, FE_ERR_INVALID, "fe_pack_items: t_max must be a power of two");
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    FE_CUDA(ctx, ctx->b_dec_items.ensure(n * sizeof(fe_encode_item)));
+    FE_CUDA(ctx, ctx->b_q.ensure(128 + n * 8));
+    FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_dec_items.p, items, n * sizeof(fe_encode_item), cudaMemcpyHostToDevice, ctx->stream));
+    FE_TRY(list_minmax(ctx, ctx->b_dec_items.as<fe_encode_item>(), n, minmax_out));
+    if (!(minmax_out[1] > minmax_out[0]) || !(minmax_out[3] > minmax_out[2]))
+        return fe_fail(ctx, FE_ERR_INVALID, "fe_pack_items: degenerate value range (Quantizer asserts max > min)");
+    uint32_t* d_bad = reinterpret_cast<uint32_t*>(ctx->b_q.as<uint8_t>() + 64);
+    unsigned long long* d_out = reinterpret_cast<unsigned long long*>(ctx->b_q.as<uint8_t>() + 128);
+    FE_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    LAUNCH(ctx, k_pack, cdiv(n, 256), 256, ctx->b_dec_items.as<fe_encode_item>(), (uint32_t)n, t_max, minmax_out[0], minmax_out[1], minmax_out[2],
+           minmax_out[3], bits_s, bits_o, d_out, d_bad);
+    uint32_t bad = 0;
+    FE_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaMemcpyAsync(packed_out, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_pack_items: %u items are not power-of-two lattice blocks with S = 2T below t_max=%u", bad, t_max);
+    return FE_OK;
+}
+
+extern "C" int fe_unpack_items(fe_ctx* ctx, const uint64_t* packed, size_t n, uint32_t t_max, int bits_s, int bits_o, const double minmax[4],
+                               int use_fma, fe_encode_item* items_out) {
+    if (!ctx) return FE_ERR_INVALID;
+    if (!packed || !n || !items_out || !minmax) return fe_fail(ctx, FE_ERR_INVALID, "fe_unpack_items: null or empty input");
+    if (bits_s < 2 || bits_s > 5 || bits_o < 2 || bits_o > 7 || !t_max || (t_max & (t_max - 1)) || n > 0x7FFFFFFFu)
+        return fe_fail(ctx, FE_ERR_INVALID, "fe_unpack_items: bad header");
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    FE_CUDA(ctx, ctx->b_dec_items.ensure(n * sizeof(fe_encode_item)));
+    FE_CUDA(ctx, ctx->b_q.ensure(128 + n * 8));
+    unsigned long long* d_in = reinterpret_cast<unsigned long long*>(ctx->b_q.as<uint8_t>() + 128);
+    FE_CUDA(ctx, cudaMemcpyAsync(d_in, packed, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_unpack, cdiv(n, 256), 256, d_in, (uint32_t)n, t_max, minmax[0], minmax[1], minmax[2], minmax[3], bits_s, bits_o, use_fma,
+           ctx->b_dec_items.as<fe_encode_item>());
+    FE_CUDA(ctx, cudaMemcpyAsync(items_out, ctx->b_dec_items.p, n * sizeof(fe_encode_item), cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FE_OK;
+}

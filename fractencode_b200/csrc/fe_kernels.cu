@@ -718,6 +718,62 @@ __global__ void k_quantize(const fe_encode_item* __restrict__ items, uint32_t n,
     qo[i] = (uint32_t)(b < mq_o ? b : mq_o);
 }
 
+// packed 64-bit records (layout in include/fractencode_b200.h)
+__global__ void k_pack(const fe_encode_item* __restrict__ items, uint32_t n, uint32_t t_max, double min_s, double max_s, double min_o,
+                       double max_o, int bits_s, int bits_o, unsigned long long* __restrict__ out, uint32_t* __restrict__ bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fe_encode_item e = items[i];
+    const uint32_t T = e.w;
+    uint32_t level = 0;
+    while ((t_max >> level) > T && level < 4) ++level;
+    const bool has = e.src_w != 0;
+    const bool ok = T && e.w == e.h && (t_max >> level) == T && level < 4 && e.x % T == 0 && e.y % T == 0 && e.x / T < 2048 && e.y / T < 2048 &&
+                    (!has || (e.src_w == 2 * T && e.src_h == 2 * T && e.match_x % T == 0 && e.match_y % T == 0 && e.match_x / T < 2048 &&
+                              e.match_y / T < 2048 && e.transform >= 0 && e.transform < 8));
+    if (!ok) { atomicAdd(bad, 1u); out[i] = 0; return; }
+    unsigned long long w = (unsigned long long)(e.x / T) | ((unsigned long long)(e.y / T) << 11) | ((unsigned long long)level << 44);
+    if (has) {
+        const double step_s = __ddiv_rn(fabs(__dsub_rn(max_s, min_s)), (double)(1 << bits_s));
+        const double step_o = __ddiv_rn(fabs(__dsub_rn(max_o, min_o)), (double)(1 << bits_o));
+        const unsigned long long mq_s = (1ull << bits_s) - 1, mq_o = (1ull << bits_o) - 1;
+        unsigned long long qs = (unsigned long long)floor(__ddiv_rn(__dsub_rn(e.contrast, min_s), step_s));
+        unsigned long long qo = (unsigned long long)floor(__ddiv_rn(__dsub_rn(e.brightness, min_o), step_o));
+        qs = qs < mq_s ? qs : mq_s;
+        qo = qo < mq_o ? qo : mq_o;
+        w |= ((unsigned long long)(e.match_x / T) << 22) | ((unsigned long long)(e.match_y / T) << 33) | ((unsigned long long)e.transform << 46) |
+             (qs << 49) | (qo << 54);
+    } else {
+        w |= 1ull << 63;
+    }
+    out[i] = w;
+}
+
+__global__ void k_unpack(const unsigned long long* __restrict__ in, uint32_t n, uint32_t t_max, double min_s, double max_s, double min_o,
+                         double max_o, int bits_s, int bits_o, int use_fma, fe_encode_item* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long w = in[i];
+    const uint32_t level = (uint32_t)((w >> 44) & 3), T = t_max >> level;
+    fe_encode_item e;
+    e.x = (uint32_t)(w & 2047) * T; e.y = (uint32_t)((w >> 11) & 2047) * T; e.w = T; e.h = T;
+    e.distance = 0.0; e.pad_ = 0;
+    if (w >> 63) {
+        e.distance = 100000.0; e.contrast = 0.0; e.brightness = 0.0; e.transform = 0; e.match_x = e.match_y = e.src_w = e.src_h = 0;
+    } else {
+        const double step_s = __ddiv_rn(fabs(__dsub_rn(max_s, min_s)), (double)(1 << bits_s));
+        const double step_o = __ddiv_rn(fabs(__dsub_rn(max_o, min_o)), (double)(1 << bits_o));
+        const double qs = (double)((w >> 49) & 31), qo = (double)((w >> 54) & 127);
+        // Quantizer::value: quant * step + min + step / 2 (Quantizer.hpp:31-35)
+        e.contrast = __dadd_rn(use_fma ? __fma_rn(qs, step_s, min_s) : __dadd_rn(__dmul_rn(qs, step_s), min_s), __dmul_rn(step_s, 0.5));
+        e.brightness = __dadd_rn(use_fma ? __fma_rn(qo, step_o, min_o) : __dadd_rn(__dmul_rn(qo, step_o), min_o), __dmul_rn(step_o, 0.5));
+        e.transform = (int32_t)((w >> 46) & 7);
+        e.match_x = (uint32_t)((w >> 22) & 2047) * T; e.match_y = (uint32_t)((w >> 33) & 2047) * T;
+        e.src_w = e.src_h = 2 * T;
+    }
+    out[i] = e;
+}
+
 // ---------------------------------------------------------------------------------------------
 // synthetic images: same integer formulas as oracle/frac_oracle.c:fo_synth_image
 // ---------------------------------------------------------------------------------------------

@@ -49,3 +49,7 @@ __global__ void k_minmax(const fe_encode_item* items, uint32_t n, unsigned long 
 __global__ void k_quantize(const fe_encode_item* items, uint32_t n, double min_s, double max_s, double min_o, double max_o,
                            int bits_s, int bits_o, uint32_t* qs, uint32_t* qo);
 __global__ void k_synth(uint8_t* out, uint32_t w, uint32_t h, uint32_t stride, unsigned long long seed, int kind);
+__global__ void k_pack(const fe_encode_item* items, uint32_t n, uint32_t t_max, double min_s, double max_s, double min_o, double max_o,
+                       int bits_s, int bits_o, unsigned long long* out, uint32_t* bad);
+__global__ void k_unpack(const unsigned long long* in, uint32_t n, uint32_t t_max, double min_s, double max_s, double min_o, double max_o,
+                         int bits_s, int bits_o, int use_fma, fe_encode_item* out);

@@ -167,6 +167,22 @@ int fe_copy_items(fe_ctx* ctx, const uint8_t* source, uint8_t* target, uint32_t 
 int fe_quantize(fe_ctx* ctx, const fe_encode_item* items, size_t n, int bits_s, int bits_o,
                 uint32_t* q_s_out, uint32_t* q_o_out, double minmax_out[4]);
 
+/* Packed, quantised transform records (ours: the reference has no serialised format; built from its
+ * Quantizer, encode/Quantizer.hpp:13-36, with the bit widths of main.cpp:120-121).  One 64-bit word per item:
+ *   bits  0..10  range  x / T        bits 11..21  range  y / T        (T = t_max >> level)
+ *   bits 22..32  domain x / T        bits 33..43  domain y / T        (domain origins are multiples of T)
+ *   bits 44..45  level               bits 46..48  transform
+ *   bits 49..53  quantized(contrast), bits_s <= 5 bits     bits 54..60  quantized(brightness), bits_o <= 7 bits
+ *   bit  63      item has no match (default item_match_t)
+ * minmax = {min_s, max_s, min_o, max_o} over the list as main.cpp:109-118 computes them; it is the stream header
+ * together with (t_max, bits_s, bits_o).  Requires square power-of-two blocks with S = 2T on their lattice. */
+int fe_pack_items(fe_ctx* ctx, const fe_encode_item* items, size_t n, uint32_t t_max, int bits_s, int bits_o,
+                  uint64_t* packed_out, double minmax_out[4]);
+/* Inverse: contrast = Quantizer::value(q_s), brightness = Quantizer::value(q_o) (fma: q*step+min fused as an
+ * FMA-contracting build of the reference would), distance = 0.  The result feeds fe_decode. */
+int fe_unpack_items(fe_ctx* ctx, const uint64_t* packed, size_t n, uint32_t t_max, int bits_s, int bits_o,
+                    const double minmax[4], int fma, fe_encode_item* items_out);
+
 int fe_get_stats(const fe_ctx* ctx, fe_stats* out);
 int fe_stats_reset(fe_ctx* ctx);
 int fe_synchronize(fe_ctx* ctx);

@@ -214,3 +214,33 @@ def test_largest_block_size_and_padded_stride_quadtree(ctx, fo):
     with pytest.raises(fb.FractencodeError) as e:
         ctx.encode_level(fb.uniform_grid(256, 256, 256, 128), fb.uniform_grid(256, 256, 128, 128), fb.Params())
     assert e.value.code == -2  # T = 128 > 64
+
+
+def test_packed_quantised_records_roundtrip(ctx, fo, lenna):
+    """fe_pack_items / fe_unpack_items: q values and dequantised values equal the reference Quantizer's
+    (oracle restatement of encode/Quantizer.hpp), geometry survives the 64-bit packing, and the unpacked list decodes."""
+    z = np.load(os.path.join(GOLDEN, "items_lenna_qt_16_4_cls_thr5.npz"))["items"]
+    packed, mm = ctx.pack_items(z, 16, 5, 7)
+    assert packed.dtype == np.uint64 and len(packed) == len(z)
+    assert mm[0] == z["contrast"].min() and mm[1] == max(z["contrast"].max(), -1.0)
+    un = ctx.unpack_items(packed, 16, mm, 5, 7)
+    for f in ("x", "y", "w", "h", "match_x", "match_y", "src_w", "src_h", "transform"):
+        assert (un[f] == z[f]).all(), f
+    qs, qo, mm2 = ctx.quantize(z, 5, 7)
+    assert (mm2 == mm).all()
+    assert (((packed >> np.uint64(49)) & np.uint64(31)) == qs).all() and (((packed >> np.uint64(54)) & np.uint64(127)) == qo).all()
+    for i in range(0, len(z), 53):
+        assert qs[i] == fo.quantize(z["contrast"][i], mm[0], mm[1], 5)
+        assert un["contrast"][i] == fo.dequantize(int(qs[i]), mm[0], mm[1], 5)
+        assert un["brightness"][i] == fo.dequantize(int(qo[i]), mm[2], mm[3], 7)
+    # the quantised stream still decodes to something close to the image (5/7-bit coefficients)
+    dec_q, _, _ = ctx.decode(un, 512, 512, max_iters=16)
+    dec, _, _ = ctx.decode(z, 512, 512, max_iters=16)
+    assert np.abs(dec_q.astype(int) - lenna.astype(int)).mean() < np.abs(dec.astype(int) - lenna.astype(int)).mean() + 4.0
+    # items off the power-of-two lattice are refused
+    bad = z[:4].copy()
+    bad["x"] += 1
+    import fractencode_b200 as fb
+    with pytest.raises(fb.FractencodeError) as e:
+        ctx.pack_items(bad, 16)
+    assert e.value.code == -2
