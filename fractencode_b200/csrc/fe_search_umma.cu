@@ -420,94 +420,146 @@ __global__ void k_block_norms(const uint8_t* __restrict__ img, uint32_t stride, 
     if (lane == 0) out[p] = s2;
 }
 
-// Both builders: one thread per 16-byte store (8 halves = one K chunk of one row / column), consecutive threads ->
-// consecutive rows of the same chunk, so every warp writes 512 contiguous bytes; every byte of every blob (padding rows,
-// columns and K included) is written exactly once -- no memset, write traffic = blob size.  Reads are u8 gathers from the
-// L2-resident image.
+// Both builders: one thread per block (range / domain).  The thread reads its block with T-byte vector loads (byte loads
+// when the origin is not T-aligned), forms every K chunk (8 halves = 16 bytes) of its rows / column in registers and stores
+// them; consecutive threads own consecutive rows / columns, so each store instruction of a warp covers one contiguous run
+// of the blob.  The block norm falls out of the same registers (no separate norm pass) and every byte of every blob
+// (padding rows, columns and K included) is written exactly once -- no memset, write traffic = blob size.
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     const __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// A rows.  Row (4*lr + k) of row tile `tile`: range lr of the tile under the inverse of rotation k, value 510 - 4 r, then
-// the constant columns [1, 2048, 2048].
-__global__ void k_build_rows16(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
-                               const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
-                               uint4* __restrict__ A16) {
-    const uint32_t nch = Kpad / 8;
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint64_t)bk.row_tile0[bk.nb] * nch * UM_ROWS) return;
-    const uint32_t row = (uint32_t)(idx % UM_ROWS), ch = (uint32_t)((idx / UM_ROWS) % nch), tile = (uint32_t)(idx / ((uint64_t)UM_ROWS * nch));
-    int bi = 0;
-    while (bi + 1 < bk.nb && tile >= bk.row_tile0[bi + 1]) ++bi;
-    const uint32_t j = bk.range_off[bi] + (tile - bk.row_tile0[bi]) * 32 + row / 4, k = row & 3;
-    const uint32_t N = T * T;
-    float v[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = 0.f;
-    if (j < bk.range_off[bi + 1]) {
-        const fe_grid_item r = rng[order ? order[j] : j];
-        const uint8_t* base = img + (size_t)r.y * stride + r.x;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const uint32_t e = ch * 8 + q;
-            if (e < N) {
-                const uint32_t Y = e / T, X = e % T;
-                uint32_t py, px;
-                if (k == 0) { py = Y; px = X; }
-                else if (k == 1) { py = X; px = T - 1 - Y; }
-                else if (k == 2) { py = T - 1 - Y; px = T - 1 - X; }
-                else { py = T - 1 - X; px = Y; }
-                v[q] = (float)(510 - 4 * (int)base[(size_t)py * stride + px]);
-            } else if (e == N) {
-                v[q] = 1.0f;
-            } else if (e == N + 1 || e == N + 2) {
-                v[q] = 2048.0f;
-            }
+// T bytes at p as T/4 little-endian words
+template <int T>
+__device__ __forceinline__ void load_px(const uint8_t* __restrict__ p, uint32_t (&w)[T / 4]) {
+    if ((reinterpret_cast<uintptr_t>(p) & (T - 1)) == 0) {
+        if constexpr (T == 4) {
+            w[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+        } else {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+            w[0] = v.x; w[1] = v.y;
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < T / 4; ++i)
+            w[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
     }
-    A16[idx] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
 }
 
-// B columns.  b = D - 510; limbs of h = floor(sum b^2 / 2) in the three columns after the data; parity bit.
-__global__ void k_build_pool16(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ dom,
-                               const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
-                               const uint32_t* __restrict__ colS2, uint4* __restrict__ B16, uint32_t* __restrict__ colpar) {
-    const uint32_t nch = Kpad / 8;
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint64_t)bk.col_tile0[bk.nb] * nch * UM_NT) return;
-    const uint32_t l = (uint32_t)(idx % UM_NT), ch = (uint32_t)((idx / UM_NT) % nch), tile = (uint32_t)(idx / ((uint64_t)UM_NT * nch));
+// A rows.  Row (4*lr + k) of row tile `tile`: range lr of the tile under the inverse of rotation k, value 510 - 4 r, then
+// the constant columns [1, 2048, 2048].  rowA2[j] = sum (4r - 510)^2.
+template <int T>
+__global__ void __launch_bounds__(128) k_build_rows16(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
+                                                      const uint32_t* __restrict__ order, UmmaBuckets bk, uint4* __restrict__ A16,
+                                                      uint32_t* __restrict__ rowA2) {
+    constexpr int N = T * T, KPAD = (N + 3 + 15) & ~15, NCH = KPAD / 8, W = T / 4;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= bk.row_tile0[bk.nb] * 32u) return;
+    const uint32_t tile = idx / 32, lr = idx % 32;
+    int bi = 0;
+    while (bi + 1 < bk.nb && tile >= bk.row_tile0[bi + 1]) ++bi;
+    const uint32_t j = bk.range_off[bi] + (tile - bk.row_tile0[bi]) * 32 + lr;
+    uint4* out = A16 + (size_t)tile * NCH * UM_ROWS + 4 * lr;
+    if (j >= bk.range_off[bi + 1]) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[ch * UM_ROWS + k] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const fe_grid_item r = rng[order ? order[j] : j];
+    const uint8_t* base = img + (size_t)r.y * stride + r.x;
+    uint32_t w[T][W];
+#pragma unroll
+    for (int y = 0; y < T; ++y) load_px<T>(base + (size_t)y * stride, w[y]);
+    auto px = [&](int py, int pxx) { return (int)((w[py][pxx >> 2] >> (8 * (pxx & 3))) & 255u); };
+    uint32_t s2 = 0;
+#pragma unroll
+    for (int y = 0; y < T; ++y)
+#pragma unroll
+        for (int x = 0; x < T; ++x) { const int a = 4 * px(y, x) - 510; s2 += (uint32_t)(a * a); }
+    rowA2[j] = s2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int e = ch * 8 + q;
+                if (e < N) {
+                    const int Y = e / T, X = e % T;
+                    const int py = k == 0 ? Y : k == 1 ? X : k == 2 ? T - 1 - Y : T - 1 - X;
+                    const int pxx = k == 0 ? X : k == 1 ? T - 1 - Y : k == 2 ? T - 1 - X : Y;
+                    v[q] = (float)(510 - 4 * px(py, pxx));
+                } else {
+                    v[q] = e == N ? 1.0f : (e == N + 1 || e == N + 2) ? 2048.0f : 0.0f;
+                }
+            }
+            out[ch * UM_ROWS + k] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+        }
+    }
+}
+
+// B columns.  b = D - 510; limbs of h = floor(sum b^2 / 2) in the three columns after the data; parity bit per column
+// (one ballot word per 32 columns).
+template <int T>
+__global__ void __launch_bounds__(128) k_build_pool16(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ dom,
+                                                      const uint32_t* __restrict__ order, UmmaBuckets bk, uint4* __restrict__ B16,
+                                                      uint32_t* __restrict__ colpar) {
+    constexpr int N = T * T, KPAD = (N + 3 + 15) & ~15, NCH = KPAD / 8, W = T / 4;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= bk.col_tile0[bk.nb] * (uint32_t)UM_NT) return;          // whole warps: UM_NT is a multiple of 32
+    const uint32_t tile = idx / UM_NT, l = idx % UM_NT;
     int bi = 0;
     while (bi + 1 < bk.nb && tile >= bk.col_tile0[bi + 1]) ++bi;
     const uint32_t c = bk.dom_off[bi] + (tile - bk.col_tile0[bi]) * UM_NT + l;
-    const uint32_t N = T * T;
-    float v[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = 0.f;
-    if (c < bk.dom_off[bi + 1]) {
+    uint4* out = B16 + (size_t)tile * NCH * UM_NT + l;
+    const bool live = c < bk.dom_off[bi + 1];
+    uint32_t s2 = 0;
+    if (live) {
         const fe_grid_item d = dom[order ? order[c] : c];
         const uint8_t* base = img + (size_t)d.y * stride + d.x;
-        auto boxsum = [&](uint32_t e) {
-            const uint8_t* p = base + (size_t)(2 * (e / T)) * stride + 2 * (e % T);
-            return (int)p[0] + (int)p[1] + (int)p[stride] + (int)p[stride + 1];
-        };
-        const bool has_limbs = ch * 8 + 7 >= N && ch * 8 <= N + 2;
-        uint32_t h = 0;
-        if (has_limbs) {
-            const uint32_t s2 = colS2[c];
-            h = s2 >> 1;
-            if ((s2 & 1u) && ch * 8 <= N && N <= ch * 8 + 7) atomicOr(&colpar[(size_t)tile * (UM_NT / 32) + (l >> 5)], 1u << (l & 31));
-        }
+        float v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const uint32_t e = ch * 8 + q;
-            if (e < N) v[q] = (float)(boxsum(e) - 510);
-            else if (e == N) v[q] = (float)(h & 2047u);
-            else if (e == N + 1) v[q] = (float)((h >> 11) & 2047u);
-            else if (e == N + 2) v[q] = (float)((h >> 22) * 2048u);
+        for (int Y = 0; Y < T; ++Y) {
+            uint32_t top[2 * W], bot[2 * W];
+            {
+                uint32_t lo[W], hi[W];
+                load_px<T>(base + (size_t)(2 * Y) * stride, lo);
+                load_px<T>(base + (size_t)(2 * Y) * stride + T, hi);
+#pragma unroll
+                for (int i = 0; i < W; ++i) { top[i] = lo[i]; top[W + i] = hi[i]; }
+                load_px<T>(base + (size_t)(2 * Y + 1) * stride, lo);
+                load_px<T>(base + (size_t)(2 * Y + 1) * stride + T, hi);
+#pragma unroll
+                for (int i = 0; i < W; ++i) { bot[i] = lo[i]; bot[W + i] = hi[i]; }
+            }
+#pragma unroll
+            for (int i = 0; i < 2 * W; ++i) {
+                // two box sums per word pair: horizontal byte pairs in 16-bit lanes, then the two rows
+                const uint32_t t = (top[i] & 0x00FF00FFu) + ((top[i] >> 8) & 0x00FF00FFu);
+                const uint32_t b = (bot[i] & 0x00FF00FFu) + ((bot[i] >> 8) & 0x00FF00FFu);
+                const uint32_t dd = t + b;
+                const int d0 = (int)(dd & 0xFFFFu) - 510, d1 = (int)(dd >> 16) - 510;
+                s2 += (uint32_t)(d0 * d0) + (uint32_t)(d1 * d1);
+                v[(Y * T + 2 * i) & 7] = (float)d0;
+                v[(Y * T + 2 * i + 1) & 7] = (float)d1;
+            }
+            if (((Y + 1) * T) % 8 == 0)
+                out[(((Y + 1) * T) / 8 - 1) * UM_NT] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
         }
+        const uint32_t h = s2 >> 1;
+        out[(N / 8) * UM_NT] = make_uint4(pack_half2((float)(h & 2047u), (float)((h >> 11) & 2047u)), pack_half2((float)((h >> 22) * 2048u), 0.f), 0, 0);
+#pragma unroll
+        for (int ch = N / 8 + 1; ch < NCH; ++ch) out[ch * UM_NT] = make_uint4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) out[ch * UM_NT] = make_uint4(0, 0, 0, 0);
     }
-    B16[idx] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+    const uint32_t par = __ballot_sync(0xFFFFFFFFu, live && (s2 & 1u));
+    if ((l & 31) == 0) colpar[(size_t)tile * (UM_NT / 32) + (l >> 5)] = par;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -568,19 +620,22 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     FE_CUDA(ctx, ctx->b_tmaps.ensure((size_t)ct * (UM_NT / 32) * 4 + 64));
     FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)bk.n_ranges * 4 + 4));
     uint32_t* flags = ctx->b_counters.as<uint32_t>() + 2;
-    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_tmaps.p, 0, (size_t)ct * (UM_NT / 32) * 4, ctx->stream));
-    FE_CUDA(ctx, ctx->b_coln.ensure((size_t)bk.n_domains * 4 + 4));
-    k_block_norms<<<(unsigned)(((uint64_t)bk.n_ranges * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order,
-                                                                                               bk.n_ranges, g.T, 0, ctx->b_rowc.as<uint32_t>());
-    k_block_norms<<<(unsigned)(((uint64_t)bk.n_domains * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order,
-                                                                                                bk.n_domains, g.T, 2, ctx->b_coln.as<uint32_t>());
-    k_build_rows16<<<(unsigned)((bytesA / 16 + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, g.T, Kpad, ctx->b_A16.as<uint4>());
-    FE_CUDA(ctx, cudaGetLastError());
-    k_build_pool16<<<(unsigned)((bytesB / 16 + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, g.T, Kpad, ctx->b_coln.as<uint32_t>(), ctx->b_B16.as<uint4>(), ctx->b_tmaps.as<uint32_t>());
-    FE_CUDA(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches += 4;
+    {
+        const unsigned gr = (rt * 32 + 127) / 128, gc = (ct * UM_NT + 127) / 128;
+        uint4* A16 = ctx->b_A16.as<uint4>();
+        uint4* B16 = ctx->b_B16.as<uint4>();
+        uint32_t* rowA2 = ctx->b_rowc.as<uint32_t>();
+        uint32_t* colpar = ctx->b_tmaps.as<uint32_t>();
+        if (g.T == 4) {
+            k_build_rows16<4><<<gr, 128, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, A16, rowA2);
+            k_build_pool16<4><<<gc, 128, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, B16, colpar);
+        } else {
+            k_build_rows16<8><<<gr, 128, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, A16, rowA2);
+            k_build_pool16<8><<<gc, 128, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, B16, colpar);
+        }
+        FE_CUDA(ctx, cudaGetLastError());
+    }
+    ctx->stats.kernel_launches += 2;
     if (prep_done) cudaEventRecord(prep_done, ctx->stream);
 
     a.A16 = ctx->b_A16.p;
