@@ -11,7 +11,10 @@ the transform list left in HBM (+ the NCCL gather of the per-rank lists for N > 
 reference-facing C-ABI call with HOST buffers (pinned image in, transform list out).
 
 matches = sum over levels of (range blocks searched) x (domains) x 4 rotations: the FULL candidate
-count of the workload, identical for both arms, so matches/s ratios are time ratios.
+count of the workload, identical for both arms, so matches/s ratios are time ratios.  With a
+threshold both arms stop a range block at its first candidate under it (the reference's `break`,
+TransformEstimator2.hpp:40-41; here at pass granularity), so fewer candidates are actually scored:
+`evaluated` counts those, and every roofline figure is computed from `evaluated`, never from `matches`.
 """
 from __future__ import annotations
 
@@ -26,6 +29,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+# dram bytes (read + write) of all search launches of a level of the default workload, from ncu (None: not captured yet)
+TRAFFIC_BY_T = {}
 
 METRIC = "range_block_matches_per_s"
 UNIT = "matches/s"
@@ -270,18 +276,20 @@ def run_b200(a):
     st = ctx.stats()
     launches = int(st.kernel_launches)
     matches_step = sum(int(x) for x in st.level_matches)
+    evaluated_step = sum(int(x) for x in st.level_evaluated)
     nlev = int(np.log2(a.tmax // a.tmin)) + 1
     levels = []
     flops = 0.0
     search_ms = 0.0
     for l in range(nlev):
         T = a.tmax >> l
-        lm, ms = int(st.level_matches[l]), float(st.level_search_ms[l])
-        lf = 2.0 * T * T * lm
+        lm, le, ms = int(st.level_matches[l]), int(st.level_evaluated[l]), float(st.level_search_ms[l])
+        lf = 2.0 * T * T * le
         flops += lf
         search_ms += ms
-        levels.append({"T": T, "ranges": int(st.level_ranges[l]), "items": int(st.level_items[l]), "matches": lm, "search_ms": round(ms, 3),
-                       "prep_ms": round(float(st.level_prep_ms[l]), 3), "tflops": round(lf / (ms * 1e-3) / 1e12, 2) if ms > 0 else None})
+        levels.append({"T": T, "ranges": int(st.level_ranges[l]), "items": int(st.level_items[l]), "matches": lm, "evaluated": le,
+                       "passes": int(st.level_passes[l]), "search_ms": round(ms, 3), "prep_ms": round(float(st.level_prep_ms[l]), 3),
+                       "tflops": round(lf / (ms * 1e-3) / 1e12, 2) if ms > 0 else None})
     # e2e through the C ABI with host buffers
     for _ in range(max(1, a.warmup // 2)):
         step_e2e()
@@ -318,9 +326,10 @@ def run_b200(a):
         ach = flops / (search_ms * 1e-3) / 1e12 if search_ms > 0 else 0.0
         # dominant kernel = the search launch with the largest share of the step
         dom = max(levels, key=lambda l: l["search_ms"])
-        dom_ach = 2.0 * dom["T"] ** 2 * dom["matches"] / (dom["search_ms"] * 1e-3) / 1e12 if dom["search_ms"] > 0 else 0.0
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of this workload (profiles/search_kernels_r1.md)
-        traffic_by_T = {32: 107.1e6, 16: 109.6e6, 8: 245.9e6, 4: 3425.8e6} if (a.size, a.tmax, a.tmin, a.thr, a.classifier) == (4096, 32, 4, 25.0, 0) else {}
+        dom_ach = 2.0 * dom["T"] ** 2 * dom["evaluated"] / (dom["search_ms"] * 1e-3) / 1e12 if dom["search_ms"] > 0 else 0.0
+        # dram__bytes_read.sum + dram__bytes_write.sum summed over the level's search launches, ncu --set full of this workload
+        # (profiles/search_kernels_r1.md)
+        traffic_by_T = TRAFFIC_BY_T if (a.size, a.tmax, a.tmin, a.thr, a.classifier) == (4096, 32, 4, 25.0, 0) else {}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -333,12 +342,14 @@ def run_b200(a):
                     "ms_per_step": e_ms / a.steps, "mpix_per_s": world * W * H / 1e6 / (e_ms / a.steps * 1e-3)},
             "gpu_launches": launches,
             "items_per_step": all_items,
+            "evaluated_matches_per_step": evaluated_step,
             "levels": levels,
             "umma_levels": int(st.umma_levels), "exact_levels": int(st.exact_levels),
             "roofline": {"bound": "tensor", "achieved": dom_ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                          "frac": dom_ach / pk["tflops_sustained"], "traffic": traffic_by_T.get(dom["T"]),
-                         "kernel": "%s, level T=%d: 2*T^2 FLOP x %d matches per launch / CUDA-event launch time (ctx stream); peak = sustained bf16 (kernel timed inside a long step), %s" % (
-                             "k_search_umma<f16>" if dom["T"] <= 8 else "k_search_umma_i8", dom["T"], dom["matches"], pk["source"]),
+                         "kernel": "%s, level T=%d: 2*T^2 FLOP x %d candidates scored by the level's %d search launches / their summed CUDA-event "
+                                   "durations (ctx stream); peak = sustained bf16 (kernel timed inside a long step), %s" % (
+                             "k_search_umma<f16>" if dom["T"] <= 8 else "k_search_umma_i8", dom["T"], dom["evaluated"], dom["passes"], pk["source"]),
                          "all_levels": {"achieved": ach, "frac": ach / pk["tflops_sustained"]},
                          "peak_burst": pk["tflops_burst"]},
             "hbm_kernels": {"peak_gbs": pk["hbm_gbs"], "decode": decode_info,

@@ -38,7 +38,8 @@ class Stats(C.Structure):
     _fields_ = [("matches", C.c_uint64), ("kernel_launches", C.c_uint64), ("fp32_regime_items", C.c_uint64),
                 ("umma_levels", C.c_uint64), ("exact_levels", C.c_uint64),
                 ("level_items", C.c_uint64 * 8), ("level_ranges", C.c_uint64 * 8), ("level_matches", C.c_uint64 * 8),
-                ("level_search_ms", C.c_float * 8), ("level_prep_ms", C.c_float * 8), ("last_decode_ms", C.c_float)]
+                ("level_search_ms", C.c_float * 8), ("level_prep_ms", C.c_float * 8), ("last_decode_ms", C.c_float), ("reserved_", C.c_uint32),
+                ("evaluated", C.c_uint64), ("level_evaluated", C.c_uint64 * 8), ("level_passes", C.c_uint64 * 8)]
 
 
 class FractencodeError(RuntimeError):

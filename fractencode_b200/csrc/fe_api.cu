@@ -2,6 +2,8 @@
 // orchestration of one search level / the quadtree / decode on the ctx stream.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 #include <cmath>
@@ -83,6 +85,7 @@ extern "C" int fe_create(fe_ctx** out, int device, void* stream) {
         ctx->own_stream = true;
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto& ev : ctx->ev_pass) cudaEventCreate(&ev);
     *out = ctx;
     return FE_OK;
 }
@@ -95,9 +98,11 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
                       &ctx->b_rng_order, &ctx->b_sort_tmp, &ctx->b_keys_tmp, &ctx->b_vals_tmp, &ctx->b_A, &ctx->b_Blo, &ctx->b_Bhi,
                       &ctx->b_rowc, &ctx->b_coln, &ctx->b_rowbest, &ctx->b_rowhit, &ctx->b_hist, &ctx->b_level_items, &ctx->b_split,
                       &ctx->b_scan, &ctx->b_scan_tmp, &ctx->b_rng_next, &ctx->b_counters, &ctx->b_A16, &ctx->b_B16, &ctx->b_tmaps,
-                      &ctx->b_items, &ctx->b_dec_a, &ctx->b_dec_b, &ctx->b_dec_items, &ctx->b_dec_sum, &ctx->b_q};
+                      &ctx->b_items, &ctx->b_dec_a, &ctx->b_dec_b, &ctx->b_dec_items, &ctx->b_dec_sum, &ctx->b_q, &ctx->b_bound,
+                      &ctx->b_flag_idx, &ctx->b_act[0], &ctx->b_act[1], &ctx->b_act_items, &ctx->b_act_flags, &ctx->b_act_tmp};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_pass) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -321,6 +326,142 @@ static int rerank_fp32_regime(fe_ctx* ctx, const LevelIO& io, const fe_params& p
     return FE_OK;
 }
 
+// tcgen05 search of one level (kind 0: f16 operands, T = 4, 8; kind 1: i8 operands, T <= 32).
+// Without a threshold: one pass, every range against every admissible domain.  With a threshold the scan is cut into
+// growing slices of the domain order; after each slice the ranges that met the threshold are final (their first hit in
+// scan order lies in the slices searched so far -- the reference stops there too, TransformEstimator2.hpp:40-41) and
+// only the survivors go on, compacted into fresh row tiles.  Results land in the level's row slots through
+// UmmaArgs::rowslot, so the winner rules of k_finalize see exactly what a single full pass would have left for every
+// range that matters: first hits for the resolved ranges, the complete minimum for the ranges that never hit.
+struct TcSearchResult {
+    bool inexact = false;      // kind 0 only: a winner sits in the fp32-inexact band, redo on kind 1
+    uint64_t evaluated = 0;    // (range, domain, rotation) candidates actually scored
+    uint32_t passes = 0;
+    float kernel_ms = 0.f;     // search launches only (CUDA events), when timed
+};
+
+static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const uint32_t* dom_order, const uint32_t* rng_order, const uint32_t doff[8],
+                     const uint32_t roff[8], int nbuckets, uint32_t thr16, bool use_thr, bool timed, TcSearchResult* res) {
+    const LevelGeom& g = io.g;
+    const uint32_t nR = io.nR, nD = io.nD;
+    static const bool single_pass = getenv("FE_SINGLE_PASS") != nullptr;   // tuning / A-B switch: never slice the scan
+    const bool multipass = use_thr && !single_pass;
+    const uint32_t GR = 128;                                              // slice granularity: whole column tiles of both kinds
+    LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
+    LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));
+    FE_CUDA(ctx, ctx->b_hist.ensure(8 * sizeof(uint32_t)));
+
+    uint32_t dc[7], done[7], aoff[8];
+    for (int c = 0; c < 7; ++c) { dc[c] = c < nbuckets ? doff[c + 1] - doff[c] : 0; done[c] = 0; }
+    for (int c = 0; c <= 7; ++c) aoff[c] = roff[std::min(c, nbuckets)];
+    const uint32_t* items = rng_order;   // range position of the pass -> range item
+    const uint32_t* slots = nullptr;     // range position of the pass -> range position of the level
+    uint32_t nA = nR;
+    int gen = 0;
+    double F = multipass ? 1.0 / 128.0 : 1.0;   // cumulative fraction of each bucket's scan after this pass
+    bool reuse_rows = false;             // the operand rows of the current range list are already built
+    *res = TcSearchResult{};
+    for (;;) {
+        if (res->passes >= (uint32_t)FE_MAX_PASSES - 1) F = 1.0;
+        SearchPass sp{};
+        sp.dom_order = dom_order; sp.rng_items = items; sp.rowslot = slots;
+        sp.nbuckets = nbuckets; sp.n_dom = nD;
+        sp.reuse_rows = reuse_rows; sp.reuse_dom_norms = res->passes > 0;
+        bool all_done = true, any_work = false;
+        for (int c = 0; c < nbuckets; ++c) {
+            const uint32_t rc = aoff[c + 1] - aoff[c];
+            uint32_t hi = dc[c];
+            if (rc && F < 1.0) {
+                const uint64_t want = std::max<uint64_t>(16 * GR, (uint64_t)std::ceil((double)dc[c] * F));
+                const uint64_t up = (want + GR - 1) / GR * GR;
+                hi = (uint32_t)std::min<uint64_t>(dc[c], std::max<uint64_t>(up, (uint64_t)done[c] + 16 * GR));   // every pass advances
+                if (dc[c] - hi < 8 * GR) hi = dc[c];                      // no slivers at the end of the scan
+            }
+            sp.dbeg[c] = doff[c] + done[c];
+            sp.dend[c] = doff[c] + (rc ? hi : done[c]);
+            res->evaluated += (uint64_t)rc * (rc ? hi - done[c] : 0) * 4;
+            if (rc && hi > done[c]) any_work = true;
+            done[c] = hi;
+            if (hi < dc[c]) all_done = false;
+        }
+        for (int c = 0; c <= nbuckets; ++c) sp.roff[c] = aoff[c];
+        if (timed) { sp.ev0 = ctx->ev_pass[2 * res->passes]; sp.ev1 = ctx->ev_pass[2 * res->passes + 1]; }
+        if (!any_work) {                                                   // nothing left to scan for the surviving buckets
+            if (all_done) break;
+            F *= 2.0;
+            continue;
+        }
+        if (kind == 0) FE_TRY(umma_prepare_and_search(ctx, g, io.d_dom, io.d_rng, sp, thr16, use_thr));
+        else FE_TRY(umma_i8_prepare_and_search(ctx, g, io.d_dom, io.d_rng, sp, thr16, use_thr));
+        ++res->passes;
+        reuse_rows = true;
+
+        // survivors + the inexact flag in one round trip
+        uint32_t host[8 + 1] = {0};
+        if (!all_done) {
+            FE_CUDA(ctx, ctx->b_act_flags.ensure((size_t)nA + 16));
+            FE_CUDA(ctx, cudaMemsetAsync(ctx->b_hist.p, 0, 8 * sizeof(uint32_t), ctx->stream));
+            Off8 o8;
+            for (int c = 0; c <= 7; ++c) o8.v[c] = aoff[c];
+            LAUNCH(ctx, k_unresolved, cdiv(nA, 256), 256, slots, ctx->b_rowhit.as<uint32_t>(), nA, o8, nbuckets, ctx->b_act_flags.as<uint8_t>(),
+                   ctx->b_hist.as<uint32_t>());
+            FE_CUDA(ctx, cudaMemcpyAsync(host, ctx->b_hist.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (kind == 0 || !all_done) {
+            FE_CUDA(ctx, cudaMemcpyAsync(host + 8, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        if (kind == 0 && (host[8] & 1u)) { res->inexact = true; break; }
+        if (all_done) break;
+        uint32_t S = 0;
+        for (int c = 0; c < nbuckets; ++c) S += host[c];
+        if (S == 0) break;                                                // every range has its first hit
+        const double resolved = 1.0 - (double)S / (double)nA;
+        if (S < nA) {
+            // stable compaction of the surviving positions (bucket grouping is kept), then their item indices
+            DevBuf& out = ctx->b_act[gen];
+            FE_CUDA(ctx, out.ensure((size_t)S * 4 + 16));
+            FE_CUDA(ctx, ctx->b_act_items.ensure((size_t)S * 4 + 16));
+            uint32_t* d_nsel = ctx->b_hist.as<uint32_t>() + 7;
+            size_t tmp_bytes = 0;
+            if (slots) {
+                FE_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, slots, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
+                FE_CUDA(ctx, ctx->b_act_tmp.ensure(tmp_bytes));
+                FE_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_act_tmp.p, tmp_bytes, slots, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
+            } else {
+                thrust::counting_iterator<uint32_t> iota(0u);
+                FE_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
+                FE_CUDA(ctx, ctx->b_act_tmp.ensure(tmp_bytes));
+                FE_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_act_tmp.p, tmp_bytes, iota, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
+            }
+            ctx->stats.kernel_launches += 2;
+            slots = out.as<uint32_t>();
+            gen ^= 1;
+            if (rng_order) {
+                LAUNCH(ctx, k_gather_u32, cdiv(S, 256), 256, slots, rng_order, S, ctx->b_act_items.as<uint32_t>());
+                items = ctx->b_act_items.as<uint32_t>();
+            } else {
+                items = slots;
+            }
+            aoff[0] = 0;
+            for (int c = 0; c < 7; ++c) aoff[c + 1] = aoff[c] + (c < nbuckets ? host[c] : 0);
+            nA = S;
+            reuse_rows = false;
+        }
+        F *= resolved >= 0.03 ? 2.0 : 4.0;
+    }
+    if (timed && res->passes) {
+        cudaEventSynchronize(ctx->ev_pass[2 * res->passes - 1]);
+        for (uint32_t i = 0; i < res->passes; ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev_pass[2 * i], ctx->ev_pass[2 * i + 1]);
+            res->kernel_ms += ms;
+        }
+    }
+    return FE_OK;
+}
+
 static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     const LevelGeom& g = io.g;
     const uint32_t nR = io.nR, nD = io.nD;
@@ -362,23 +503,22 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     if (p.search_impl == FE_SEARCH_UMMA && nD && !f16_ok && !i8_ok)
         return fe_fail(ctx, FE_ERR_UNSUPPORTED, "tcgen05 paths need S == 2T, even domain origins and T <= 32 (got S=%u T=%u)", g.S, g.T);
     bool searched = false;
+    uint64_t evaluated = matches;
+    uint32_t passes = 1;
+    float kernel_ms = -1.f;
     if (p.search_impl != FE_SEARCH_EXACT && (f16_ok || i8_ok)) {
-        LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
-        LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
-        bool inexact = !f16_ok;
+        TcSearchResult r{};
+        r.inexact = !f16_ok;
+        evaluated = 0; passes = 0; kernel_ms = 0.f;
         if (f16_ok) {
             // ---- tcgen05 kind::f16 (T = 4, 8): fp16 operand blobs, integer-exact fp32 accumulators, fused argmin ----
-            FE_TRY(umma_prepare_and_search(ctx, g, io.d_dom, io.d_rng, dom_order, rng_order, doff, roff, nbuckets, thr16, use_thr, &inexact,
-                                           timed ? ctx->ev[1] : nullptr));
-            if (inexact) { // a winner in the fp32-inexact band: redo the level on the always-exact int8 kind
-                LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
-                LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
-            }
+            FE_TRY(search_tc(ctx, io, 0, dom_order, rng_order, doff, roff, nbuckets, thr16, use_thr, timed, &r));
+            evaluated += r.evaluated; passes += r.passes; kernel_ms += r.kernel_ms;
         }
-        if (inexact) {
-            // ---- tcgen05 kind::i8 (T >= 16, or the fallback above): u8 operands, exact s32 accumulators ----
-            FE_TRY(umma_i8_prepare_and_search(ctx, g, io.d_dom, io.d_rng, dom_order, rng_order, doff, roff, nbuckets, thr16, use_thr,
-                                              timed ? ctx->ev[1] : nullptr));
+        if (r.inexact) {
+            // ---- tcgen05 kind::i8 (T >= 16, or a winner of the f16 kind in the fp32-inexact band): exact s32 accumulators ----
+            FE_TRY(search_tc(ctx, io, 1, dom_order, rng_order, doff, roff, nbuckets, thr16, use_thr, timed, &r));
+            evaluated += r.evaluated; passes += r.passes; kernel_ms += r.kernel_ms;
         }
         searched = true;
         ctx->stats.umma_levels++;
@@ -421,6 +561,7 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
         ctx->stats.exact_levels++;
     }
     ctx->stats.matches += matches;
+    ctx->stats.evaluated += evaluated;
     if (timed) cudaEventRecord(ctx->ev[2], ctx->stream);
 
     // ---- winners ----
@@ -453,10 +594,18 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     if (counters[1]) FE_TRY(rerank_fp32_regime(ctx, io, p, dom_order, rng_order, doff, roff, nbuckets));
     if (timed) {
         float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.level_prep_ms[io.stat_level] = ms;
-        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.level_search_ms[io.stat_level] = ms;
+        if (kernel_ms >= 0.f) { // tcgen05 path: the search launches were timed one by one; the rest of the level is preparation
+            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]);
+            ctx->stats.level_search_ms[io.stat_level] = kernel_ms;
+            ctx->stats.level_prep_ms[io.stat_level] = ms - kernel_ms;
+        } else {
+            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.level_prep_ms[io.stat_level] = ms;
+            cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.level_search_ms[io.stat_level] = ms;
+        }
         ctx->stats.level_ranges[io.stat_level] = nR;
         ctx->stats.level_matches[io.stat_level] = matches;
+        ctx->stats.level_evaluated[io.stat_level] = evaluated;
+        ctx->stats.level_passes[io.stat_level] = passes;
     }
     return FE_OK;
 }

@@ -72,6 +72,8 @@ struct SearchArgs {
     uint32_t rho;
 };
 
+constexpr int FE_MAX_PASSES = 32;
+
 struct fe_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -83,6 +85,9 @@ struct fe_ctx {
     DevBuf b_dom, b_rng, b_dom_cls, b_rng_cls, b_dom_order, b_rng_order, b_sort_tmp, b_keys_tmp, b_vals_tmp;
     DevBuf b_A, b_Blo, b_Bhi, b_rowc, b_coln, b_rowbest, b_rowhit, b_hist, b_level_items, b_split, b_scan, b_scan_tmp;
     DevBuf b_rng_next, b_counters, b_bound, b_flag_idx;
+    // multi-pass search: range positions still without a candidate under the threshold (two generations), their item
+    // indices, survivor flags, select scratch
+    DevBuf b_act[2], b_act_items, b_act_flags, b_act_tmp;
     // tcgen05 path operands
     DevBuf b_A16, b_B16, b_tmaps;
     // results
@@ -92,6 +97,7 @@ struct fe_ctx {
     DevBuf b_dec_a, b_dec_b, b_dec_items, b_dec_sum, b_q;
     fe_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_pass[2 * FE_MAX_PASSES] = {}; // start/stop around each search launch of a level
 };
 
 int fe_fail(fe_ctx* ctx, int code, const char* fmt, ...);

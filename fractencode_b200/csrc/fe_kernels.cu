@@ -147,6 +147,34 @@ __global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
+// Multi-pass search: flags[i] = 1 when none of the four rotation rows of range position i (result slot slots[i]) has met the
+// threshold yet; cnt[b] += survivors of bucket b (roff = prefix offsets of the pass's positions).
+__global__ void k_unresolved(const uint32_t* __restrict__ slots, const uint32_t* __restrict__ rowhit, uint32_t n, Off8 roff, int nb,
+                             uint8_t* __restrict__ flags, uint32_t* __restrict__ cnt) {
+    __shared__ uint32_t sc[8];
+    if (threadIdx.x < 8) sc[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t s = slots ? slots[i] : i;
+        const uint4 h = reinterpret_cast<const uint4*>(rowhit)[s];
+        const bool alive = (h.x & h.y & h.z & h.w) == FE_NONE32;
+        flags[i] = alive ? 1 : 0;
+        if (alive) {
+            int b = 0;
+            while (b + 1 < nb && i >= roff.v[b + 1]) ++b;
+            atomicAdd(&sc[b], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && sc[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], sc[threadIdx.x]);
+}
+
+__global__ void k_gather_u32(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ table, uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = table ? table[idx[i]] : idx[i];
+}
+
 __global__ void k_iota(uint32_t* p, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;

@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
             const bool row_ok = lrow < item.nrows;
             const uint32_t grow = item.row0 + lrow;
             const uint32_t a2 = row_ok ? a.rowA2[grow >> 2] : 0u;
+            const uint32_t srow = (row_ok && a.rowslot) ? 4u * a.rowslot[grow >> 2] + (grow & 3u) : grow;   // result slot of the level
             RowState st;
             st.bestV = 3.0e38f; st.bestp = 0; st.bestcol = FE_NONE32; st.hit = FE_NONE32;
             st.vthr0 = -3.0e38f; st.vthr1 = -3.0e38f;
@@ -376,10 +377,10 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                     if (st.bestp == 2) st.bestp = row_parity(st, st.bestcol);
                     const long long n16 = (long long)a2 + 2ll * (long long)st.bestV + (long long)st.bestp;
                     const unsigned long long key = ((unsigned long long)(uint32_t)n16 << 32) | (unsigned long long)(item.col0 + st.bestcol);
-                    atomicMin(&a.rowbest[grow], key);
+                    atomicMin(&a.rowbest[srow], key);
                     if (st.bestV >= 16777216.0f - 64.0f) atomicOr(a.flags, 1u);
                 }
-                if (st.hit != FE_NONE32) atomicMin(&a.rowhit[grow], item.col0 + st.hit);
+                if (st.hit != FE_NONE32) atomicMin(&a.rowhit[srow], item.col0 + st.hit);
             }
         }
     }
@@ -516,7 +517,7 @@ __global__ void __launch_bounds__(128) k_build_pool16(const uint8_t* __restrict_
     while (bi + 1 < bk.nb && tile >= bk.col_tile0[bi + 1]) ++bi;
     const uint32_t c = bk.dom_off[bi] + (tile - bk.col_tile0[bi]) * UM_NT + l;
     uint4* out = B16 + (size_t)tile * NCH * UM_NT + l;
-    const bool live = c < bk.dom_off[bi + 1];
+    const bool live = c < bk.dom_end[bi];
     uint32_t s2 = 0;
     if (live) {
         const fe_grid_item d = dom[order ? order[c] : c];
@@ -569,37 +570,39 @@ int umma_level_supported(const LevelGeom& g) { return g.fast && (g.T == 4 || g.T
 
 uint32_t umma_kpad(const LevelGeom& g) { return (g.N + 3 + 15u) & ~15u; }
 
-int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng,
-                            const uint32_t* dom_order, const uint32_t* rng_order, const uint32_t doff[8], const uint32_t roff[8],
-                            int nbuckets, uint32_t thr16, bool use_thr, bool* inexact, cudaEvent_t prep_done) {
+int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng, const SearchPass& sp,
+                            uint32_t thr16, bool use_thr) {
     const uint32_t Kpad = umma_kpad(g);
+    const int nbuckets = sp.nbuckets;
+    const uint32_t* dom_order = sp.dom_order;
+    const uint32_t* rng_order = sp.rng_items;
     UmmaBuckets bk{};
     UmmaArgs a{};
     uint32_t rt = 0, ct = 0, nb = 0;
     uint64_t total_items = 0;
     for (int c = 0; c < nbuckets; ++c) {
-        const uint32_t rc = roff[c + 1] - roff[c], dc = doff[c + 1] - doff[c];
+        const uint32_t rc = sp.roff[c + 1] - sp.roff[c], dc = rc ? sp.dend[c] - sp.dbeg[c] : 0u;
         // buckets keep their slot in the operand layout even when they have no partner (their rows stay at INF)
-        bk.range_off[nb] = roff[c];
-        bk.dom_off[nb] = doff[c];
+        bk.range_off[nb] = sp.roff[c];
+        bk.dom_off[nb] = sp.dbeg[c];
+        bk.dom_end[nb] = sp.dbeg[c] + dc;
         bk.row_tile0[nb] = rt;
         bk.col_tile0[nb] = ct;
         UmmaBucket& b = a.b[nb];
         b.row_tile0 = rt; b.n_row_tiles = (rc + 31) / 32;
         b.col_tile0 = ct; b.n_col_tiles = (dc + UM_NT - 1) / UM_NT;
-        b.row0 = roff[c] * 4; b.nrows = rc * 4;
-        b.col0 = doff[c]; b.ncols = dc;
+        b.row0 = sp.roff[c] * 4; b.nrows = rc * 4;
+        b.col0 = sp.dbeg[c]; b.ncols = dc;
         rt += b.n_row_tiles;
         ct += b.n_col_tiles;
         ++nb;
     }
     bk.nb = (int)nb;
-    bk.range_off[nb] = roff[nbuckets];
-    bk.dom_off[nb] = doff[nbuckets];
+    bk.range_off[nb] = sp.roff[nbuckets];
     bk.row_tile0[nb] = rt;
     bk.col_tile0[nb] = ct;
-    bk.n_ranges = roff[nbuckets];
-    bk.n_domains = doff[nbuckets];
+    bk.n_ranges = sp.roff[nbuckets];
+    bk.n_domains = sp.n_dom;
     // column chunking: aim at >= 2 work items per SM when there are few row tiles
     uint32_t live_row_tiles = 0;
     for (uint32_t i = 0; i < nb; ++i)
@@ -611,7 +614,10 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
         if (!b.n_row_tiles) b.chunks = 0;
         total_items += (uint64_t)b.n_row_tiles * b.chunks;
     }
-    if (total_items == 0) { *inexact = false; if (prep_done) cudaEventRecord(prep_done, ctx->stream); return FE_OK; }
+    if (total_items == 0) {
+        if (sp.ev0) { cudaEventRecord(sp.ev0, ctx->stream); cudaEventRecord(sp.ev1, ctx->stream); }
+        return FE_OK;
+    }
     if (total_items > 0x7FFFFFFFull) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "umma: too many work items");
 
     const size_t bytesA = (size_t)rt * UM_ROWS * Kpad * 2, bytesB = (size_t)ct * UM_NT * Kpad * 2;
@@ -627,16 +633,15 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
         uint32_t* rowA2 = ctx->b_rowc.as<uint32_t>();
         uint32_t* colpar = ctx->b_tmaps.as<uint32_t>();
         if (g.T == 4) {
-            k_build_rows16<4><<<gr, 128, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, A16, rowA2);
+            if (!sp.reuse_rows) k_build_rows16<4><<<gr, 128, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, A16, rowA2);
             k_build_pool16<4><<<gc, 128, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, B16, colpar);
         } else {
-            k_build_rows16<8><<<gr, 128, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, A16, rowA2);
+            if (!sp.reuse_rows) k_build_rows16<8><<<gr, 128, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, A16, rowA2);
             k_build_pool16<8><<<gc, 128, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, B16, colpar);
         }
         FE_CUDA(ctx, cudaGetLastError());
     }
-    ctx->stats.kernel_launches += 2;
-    if (prep_done) cudaEventRecord(prep_done, ctx->stream);
+    ctx->stats.kernel_launches += sp.reuse_rows ? 1 : 2;
 
     a.A16 = ctx->b_A16.p;
     a.B16 = ctx->b_B16.p;
@@ -651,6 +656,7 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     a.thr16 = thr16;
     a.use_thr = use_thr ? 1u : 0u;
     a.nt = UM_NT;
+    a.rowslot = sp.rowslot;
     { const char* e = getenv("FE_UMMA_DBG"); a.dbg = e ? (uint32_t)atoi(e) : 0u; }
     const uint32_t stage_bytes = UM_NT * Kpad * 2, a_bytes = 2 * UM_ROWS * Kpad * 2;
     const uint32_t stages = 2 * UM_ISSUERS_F16;
@@ -661,16 +667,15 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const uint32_t grid = (uint32_t)std::min<uint64_t>(total_items, 148);
+    if (sp.ev0) cudaEventRecord(sp.ev0, ctx->stream);
     if (retire) k_search_umma<0, true><<<grid, UM_THREADS_F16, smem, ctx->stream>>>(a);
     else k_search_umma<0, false><<<grid, UM_THREADS_F16, smem, ctx->stream>>>(a);
     FE_CUDA(ctx, cudaGetLastError());
+    if (sp.ev1) cudaEventRecord(sp.ev1, ctx->stream);
     ctx->stats.kernel_launches++;
-    uint32_t f = 0;
-    FE_CUDA(ctx, cudaMemcpyAsync(&f, flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *inexact = (f & 1u) != 0;
     if (a.dbg & 32) {
         unsigned long long c[6];
+        cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(c, flags + 2, sizeof(c), cudaMemcpyDeviceToHost);
         const double nt = (double)std::max<unsigned long long>(1, c[5]);
         fprintf(stderr, "[umma prof] T=%u per warp-tile cycles: wait_ldA %.0f  procA %.0f  wait_ldB %.0f  release+wait_full+issue %.0f  procB %.0f  (tiles %.0f)\n",

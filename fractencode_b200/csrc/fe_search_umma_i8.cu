@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_umma_i8(const UmmaA
             const bool row_ok = lrow < item.nrows;
             const uint32_t grow = item.row0 + lrow;
             const uint32_t rc = row_ok ? a.rowA2[grow >> 2] : 0u;       // 16 * sum r^2
+            const uint32_t srow = (row_ok && a.rowslot) ? 4u * a.rowslot[grow >> 2] + (grow & 3u) : grow;   // result slot of the level
             // w = sum D^2 - 8 cross (signed); n16 = rc + w;  n16 <= thr16  <=>  w <= thr16 - rc
             long long wt = (long long)a.thr16 - (long long)rc;
             wt = max(-2147483647ll, min(2147483646ll, wt));                  // INT_MAX is the padding columns' score
@@ -220,9 +221,9 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_umma_i8(const UmmaA
                 if (bestcol != FE_NONE32) {
                     const uint32_t n16 = rc + (uint32_t)bestw;
                     const unsigned long long key = ((unsigned long long)n16 << 32) | (unsigned long long)(item.col0 + bestcol);
-                    atomicMin(&a.rowbest[grow], key);
+                    atomicMin(&a.rowbest[srow], key);
                 }
-                if (hit != FE_NONE32) atomicMin(&a.rowhit[grow], item.col0 + hit);
+                if (hit != FE_NONE32) atomicMin(&a.rowhit[srow], item.col0 + hit);
             }
         }
     }
@@ -287,7 +288,7 @@ __global__ void k_build_pool_i8(const uint8_t* __restrict__ img, uint32_t stride
     const uint32_t c = bk.dom_off[bi] + (tile - bk.col_tile0[bi]) * I8_NT + l;
     const uint32_t N = T * T;
     uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
-    const bool valid = c < bk.dom_off[bi + 1];
+    const bool valid = c < bk.dom_end[bi];
     if (valid) {
         const fe_grid_item d = dom[order ? order[c] : c];
         const uint8_t* base = img + (size_t)d.y * stride + d.x;
@@ -315,36 +316,38 @@ int umma_i8_level_supported(const LevelGeom& g) { return g.fast && g.T >= 4 && g
 
 static uint32_t i8_kpad(const LevelGeom& g) { return g.N <= (uint32_t)I8_KC ? ((g.N + 31u) & ~31u) : ((g.N + I8_KC - 1) / I8_KC) * I8_KC; }
 
-int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng,
-                               const uint32_t* dom_order, const uint32_t* rng_order, const uint32_t doff[8], const uint32_t roff[8],
-                               int nbuckets, uint32_t thr16, bool use_thr, cudaEvent_t prep_done) {
+int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng, const SearchPass& sp,
+                               uint32_t thr16, bool use_thr) {
     const uint32_t Kpad = i8_kpad(g), kc = std::min(Kpad, (uint32_t)I8_KC);
+    const int nbuckets = sp.nbuckets;
+    const uint32_t* dom_order = sp.dom_order;
+    const uint32_t* rng_order = sp.rng_items;
     UmmaBuckets bk{};
     UmmaArgs a{};
     uint32_t rt = 0, ct = 0, nb = 0;
     uint64_t total_items = 0;
     for (int c = 0; c < nbuckets; ++c) {
-        const uint32_t rc = roff[c + 1] - roff[c], dc = doff[c + 1] - doff[c];
-        bk.range_off[nb] = roff[c];
-        bk.dom_off[nb] = doff[c];
+        const uint32_t rc = sp.roff[c + 1] - sp.roff[c], dc = rc ? sp.dend[c] - sp.dbeg[c] : 0u;
+        bk.range_off[nb] = sp.roff[c];
+        bk.dom_off[nb] = sp.dbeg[c];
+        bk.dom_end[nb] = sp.dbeg[c] + dc;
         bk.row_tile0[nb] = rt;
         bk.col_tile0[nb] = ct;
         UmmaBucket& b = a.b[nb];
         b.row_tile0 = rt; b.n_row_tiles = (rc + 31) / 32;
         b.col_tile0 = ct; b.n_col_tiles = (dc + I8_NT - 1) / I8_NT;
-        b.row0 = roff[c] * 4; b.nrows = rc * 4;
-        b.col0 = doff[c]; b.ncols = dc;
+        b.row0 = sp.roff[c] * 4; b.nrows = rc * 4;
+        b.col0 = sp.dbeg[c]; b.ncols = dc;
         rt += b.n_row_tiles;
         ct += b.n_col_tiles;
         ++nb;
     }
     bk.nb = (int)nb;
-    bk.range_off[nb] = roff[nbuckets];
-    bk.dom_off[nb] = doff[nbuckets];
+    bk.range_off[nb] = sp.roff[nbuckets];
     bk.row_tile0[nb] = rt;
     bk.col_tile0[nb] = ct;
-    bk.n_ranges = roff[nbuckets];
-    bk.n_domains = doff[nbuckets];
+    bk.n_ranges = sp.roff[nbuckets];
+    bk.n_domains = sp.n_dom;
     uint32_t live_row_tiles = 0;
     for (uint32_t i = 0; i < nb; ++i)
         if (a.b[i].n_col_tiles) live_row_tiles += a.b[i].n_row_tiles;
@@ -354,7 +357,10 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
         b.chunks = (b.n_col_tiles && b.n_row_tiles) ? std::max(1u, std::min(want_chunks, b.n_col_tiles)) : 0;
         total_items += (uint64_t)b.n_row_tiles * b.chunks;
     }
-    if (total_items == 0) { if (prep_done) cudaEventRecord(prep_done, ctx->stream); return FE_OK; }
+    if (total_items == 0) {
+        if (sp.ev0) { cudaEventRecord(sp.ev0, ctx->stream); cudaEventRecord(sp.ev1, ctx->stream); }
+        return FE_OK;
+    }
     if (total_items > 0x7FFFFFFFull) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "umma i8: too many work items");
 
     const size_t bytesA = (size_t)rt * UM_ROWS * Kpad, bytesB = (size_t)ct * 2 * I8_NT * Kpad;
@@ -363,18 +369,23 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     FE_CUDA(ctx, ctx->b_coln.ensure((size_t)ct * I8_NT * 4 + 64));
     FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)bk.n_ranges * 4 + 4));
     FE_CUDA(ctx, ctx->b_tmaps.ensure((size_t)bk.n_domains * 4 + 64));
-    k_block_norms<<<(unsigned)(((uint64_t)bk.n_ranges * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order,
-                                                                                               bk.n_ranges, g.T, 1, ctx->b_rowc.as<uint32_t>());
-    k_block_norms<<<(unsigned)(((uint64_t)bk.n_domains * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order,
-                                                                                                bk.n_domains, g.T, 3, ctx->b_tmaps.as<uint32_t>());
-    k_build_rows_i8<<<(unsigned)((bytesA / 16 + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, g.T, Kpad, ctx->b_A16.as<uint4>());
+    if (!sp.reuse_rows) {
+        k_block_norms<<<(unsigned)(((uint64_t)bk.n_ranges * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order,
+                                                                                                   bk.n_ranges, g.T, 1, ctx->b_rowc.as<uint32_t>());
+        k_build_rows_i8<<<(unsigned)((bytesA / 16 + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, g.T, Kpad, ctx->b_A16.as<uint4>());
+        ctx->stats.kernel_launches += 2;
+    }
+    if (!sp.reuse_dom_norms) {
+        k_block_norms<<<(unsigned)(((uint64_t)bk.n_domains * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order,
+                                                                                                    bk.n_domains, g.T, 3, ctx->b_tmaps.as<uint32_t>());
+        ctx->stats.kernel_launches++;
+    }
     FE_CUDA(ctx, cudaGetLastError());
     k_build_pool_i8<<<(unsigned)((bytesB / 32 + 255) / 256), 256, 0, ctx->stream>>>(
         ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, g.T, Kpad, kc, ctx->b_tmaps.as<uint32_t>(), ctx->b_B16.as<uint4>(), ctx->b_coln.as<uint32_t>());
     FE_CUDA(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches += 4;
-    if (prep_done) cudaEventRecord(prep_done, ctx->stream);
+    ctx->stats.kernel_launches++;
 
     a.A16 = ctx->b_A16.p;
     a.B16 = ctx->b_B16.p;
@@ -390,6 +401,7 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     a.thr16 = thr16;
     a.use_thr = use_thr ? 1u : 0u;
     a.nt = I8_NT;
+    a.rowslot = sp.rowslot;
     const uint32_t stage_bytes = 2 * I8_NT * kc, a_bytes = UM_ROWS * Kpad;
     const uint32_t budget = 226 * 1024 - 512;
     a.n_abuf = (2 * a_bytes + 2 * stage_bytes <= budget) ? 2 : 1;
@@ -400,8 +412,10 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     const size_t smem = (size_t)a.n_abuf * a_bytes + (size_t)stages * stage_bytes + (12 + 2 * I8_MAX_STAGES) * 8 + 128;
     FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma_i8<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const uint32_t grid = (uint32_t)std::min<uint64_t>(total_items, 148);
+    if (sp.ev0) cudaEventRecord(sp.ev0, ctx->stream);
     k_search_umma_i8<0><<<grid, UM_THREADS_I8, smem, ctx->stream>>>(a);
     FE_CUDA(ctx, cudaGetLastError());
+    if (sp.ev1) cudaEventRecord(sp.ev1, ctx->stream);
     ctx->stats.kernel_launches++;
     return FE_OK;
 }

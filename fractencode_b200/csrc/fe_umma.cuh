@@ -46,18 +46,37 @@ struct UmmaArgs {
     const uint32_t* coln;            // i8 kind: [sorted column] sum(D^2) (0x3FFFFFFF for padding columns)
     uint32_t n_abuf;                 // i8 kind: A buffers in shared memory (2, or 1 when the tile is 128 KB)
     uint32_t dbg;                    // tuning probes (FE_UMMA_DBG): 1 skip TMEM drain, 2 skip MMA issue, 4 skip B copies
+    const uint32_t* rowslot;         // [range position of this pass] -> range position of the level (result slot); NULL = identity
 };
 
 struct UmmaBuckets {                 // operand-layout view for the blob builders
-    uint32_t range_off[8], dom_off[8], row_tile0[8], col_tile0[8]; // [nb] entries are the totals
+    uint32_t range_off[8], row_tile0[8], col_tile0[8]; // [nb] entries are the totals
+    uint32_t dom_off[8], dom_end[8];                   // slice of domain positions of each bucket
     uint32_t n_ranges, n_domains;
     int nb;
 };
 
+// One search pass of a level: every range position of the pass (grouped by classifier bucket) against a slice of the
+// bucket's domain positions.  A level is one pass over everything, or -- with a threshold -- several passes over growing
+// slices of the scan, each over the ranges that have not met the threshold yet (the reference's `break` at the first
+// candidate under the threshold, TransformEstimator2.hpp:40-41, at pass granularity).
+struct SearchPass {
+    const uint32_t* dom_order;       // domain position -> domain item index (NULL = identity)
+    const uint32_t* rng_items;       // range position of this pass -> range item index (NULL = identity)
+    const uint32_t* rowslot;         // range position of this pass -> range position of the level (NULL = identity)
+    uint32_t dbeg[7], dend[7];       // per bucket: domain positions searched in this pass
+    uint32_t roff[8];                // per bucket: range positions of this pass (prefix offsets)
+    int nbuckets;
+    uint32_t n_dom;                  // all domain positions of the level
+    bool reuse_rows;                 // the A blob and row norms built by the previous pass are still valid
+    bool reuse_dom_norms;            // i8 kind: the per-position domain norms of the level are already built
+    cudaEvent_t ev0, ev1;            // recorded around the search launch (NULL: not timed)
+};
+
 int umma_i8_level_supported(const LevelGeom& g);
-int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng,
-                               const uint32_t* dom_order, const uint32_t* rng_order, const uint32_t doff[8], const uint32_t roff[8],
-                               int nbuckets, uint32_t thr16, bool use_thr, cudaEvent_t prep_done);
-int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng,
-                            const uint32_t* dom_order, const uint32_t* rng_order, const uint32_t doff[8], const uint32_t roff[8],
-                            int nbuckets, uint32_t thr16, bool use_thr, bool* inexact, cudaEvent_t prep_done);
+// Both enqueue the operand builders and the search kernel on the ctx stream and return without synchronising; the f16
+// kind raises bit 0 of ctx->b_counters[2] when a winner sits in the fp32-inexact band (the caller re-runs on the i8 kind).
+int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng, const SearchPass& sp,
+                               uint32_t thr16, bool use_thr);
+int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const fe_grid_item* d_rng, const SearchPass& sp,
+                            uint32_t thr16, bool use_thr);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FE_ABI_VERSION 1
+#define FE_ABI_VERSION 2
 
 typedef enum {
     FE_OK = 0,
@@ -78,7 +78,8 @@ typedef struct {
 } fe_params;
 
 typedef struct {
-    uint64_t matches;          /* (range, domain, rotation) candidates evaluated = admissible pairs x 4 */
+    uint64_t matches;          /* (range, domain, rotation) candidates of the workload = admissible pairs x 4: what a scan
+                                * without early-out scores (the figure BASELINE.md calls "matches") */
     uint64_t kernel_launches;  /* kernels launched by this ctx since fe_stats_reset */
     uint64_t fp32_regime_items;/* items whose best SSE >= 2^20 (reference fp32 sum rounds; distance emulated) */
     uint64_t umma_levels;      /* levels searched on the tcgen05 path */
@@ -89,6 +90,11 @@ typedef struct {
     float level_search_ms[8];  /* last quadtree: search-kernel time per level (CUDA events on the ctx stream) */
     float level_prep_ms[8];    /* last quadtree: pool/range prep + classify time per level */
     float last_decode_ms;
+    uint32_t reserved_;
+    uint64_t evaluated;        /* candidates the search kernels actually scored: < matches when a threshold lets range
+                                * blocks stop at their first hit (the reference's break, TransformEstimator2.hpp:40-41) */
+    uint64_t level_evaluated[8]; /* last quadtree: evaluated per level */
+    uint64_t level_passes[8];  /* last quadtree: search passes (kernel launches) per level */
 } fe_stats;
 
 typedef struct fe_ctx fe_ctx;
