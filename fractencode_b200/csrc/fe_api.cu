@@ -344,7 +344,7 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const uint32_t* d
                      const uint32_t roff[8], int nbuckets, uint32_t thr16, bool use_thr, bool timed, TcSearchResult* res) {
     const LevelGeom& g = io.g;
     const uint32_t nR = io.nR, nD = io.nD;
-    static const bool single_pass = getenv("FE_SINGLE_PASS") != nullptr;   // tuning / A-B switch: never slice the scan
+    const bool single_pass = getenv("FE_SINGLE_PASS") != nullptr;   // tuning / A-B switch: never slice the scan
     const bool multipass = use_thr && !single_pass;
     const uint32_t GR = 128;                                              // slice granularity: whole column tiles of both kinds
     LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
@@ -391,6 +391,13 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const uint32_t* d
             if (all_done) break;
             F *= 2.0;
             continue;
+        }
+        const bool pass_dbg = getenv("FE_PASS_DBG") != nullptr;
+        if (pass_dbg) {
+            uint64_t cols = 0;
+            for (int c = 0; c < nbuckets; ++c) cols += sp.dend[c] - sp.dbeg[c];
+            fprintf(stderr, "[pass] T=%u kind=%d pass=%u ranges=%u cols=%llu (scan fraction so far %.4f) rebuild_rows=%d\n", g.T, kind, res->passes, nA,
+                    (unsigned long long)cols, F, reuse_rows ? 0 : 1);
         }
         if (kind == 0) FE_TRY(umma_prepare_and_search(ctx, g, io.d_dom, io.d_rng, sp, thr16, use_thr));
         else FE_TRY(umma_i8_prepare_and_search(ctx, g, io.d_dom, io.d_rng, sp, thr16, use_thr));
@@ -457,6 +464,7 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const uint32_t* d
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->ev_pass[2 * i], ctx->ev_pass[2 * i + 1]);
             res->kernel_ms += ms;
+            if (getenv("FE_PASS_DBG")) fprintf(stderr, "[pass] T=%u kind=%d pass=%u kernel %.3f ms\n", g.T, kind, i, ms);
         }
     }
     return FE_OK;

@@ -55,7 +55,7 @@ __device__ __forceinline__ uint32_t row_parity(const RowState& st, uint32_t col)
 
 // Exhaustive scan of a half tile held in registers (rare: exact ties, threshold crossings).
 __device__ __forceinline__ void scan_half_full(const uint32_t (&v)[UM_HALF], RowState& st, bool need_best, bool need_hit, uint32_t colbase,
-                                               const uint32_t* __restrict__ par) {
+                                               const uint32_t (&par)[UM_HALF / 32]) {
     float cx = 3.0e38f;
     uint32_t cp = 1, ccol = FE_NONE32, chit = FE_NONE32;
 #pragma unroll
@@ -76,7 +76,7 @@ __device__ __forceinline__ void scan_half_full(const uint32_t (&v)[UM_HALF], Row
 
 // UM_HALF accumulator values of one row (columns colbase .. colbase+UM_HALF-1 of the work item).
 __device__ __forceinline__ void process_half(uint32_t (&v)[UM_HALF], RowState& st, bool row_ok, uint32_t colbase, uint32_t nvalid,
-                                             const uint32_t* __restrict__ par) {
+                                             const uint32_t (&par)[UM_HALF / 32]) {
     if (nvalid < UM_HALF) {
 #pragma unroll
         for (int i = 0; i < UM_HALF; ++i)
@@ -336,6 +336,17 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                 st.vthr0 = (float)f0;
                 st.vthr1 = (float)f1;
             }
+            if (row_ok) {
+                // Seed the running minimum with what earlier passes / column chunks already found for this row, plus one:
+                // anything this item finds at or below the recorded score still gets written (ties are settled by the
+                // column index inside the 64-bit key), everything above it is rejected by the cheap tile-minimum test.
+                const unsigned long long seen = __ldcg(&a.rowbest[srow]);
+                if (seen != FE_INF64) {
+                    const long long d = (long long)(uint32_t)(seen >> 32) + 1ll - (long long)a2;   // = 2 V + p
+                    const long long V = d >= 0 ? d / 2 : -((-d + 1) / 2);
+                    if (V > -16777216ll && V < 16777216ll) { st.bestV = (float)V; st.bestp = (uint32_t)(d - 2 * V); }
+                }
+            }
             const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
             const uint32_t my_tiles = first < n ? (n - first + UM_WGS - 1) / UM_WGS : 0;
             // Threshold runs: a range is decided by its first hit in scan order, so once any of its four rotation rows
@@ -348,7 +359,10 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                 const uint32_t colbase = u * UM_NT + h * UM_HALF;
                 const uint32_t tile_valid = min((uint32_t)UM_NT, item.cols_left - u * UM_NT);
                 const uint32_t nvalid = tile_valid > h * UM_HALF ? min((uint32_t)UM_HALF, tile_valid - h * UM_HALF) : 0u;
-                const uint32_t* par = a.colpar + (size_t)(item.t0 + u) * (UM_NT / 32) + h * (UM_HALF / 32);
+                // parity words of this half tile, fetched ahead of the accumulator wait (one 8-byte broadcast load per warp)
+                static_assert(UM_HALF == 64, "two parity words per half tile");
+                const uint2 pw2 = __ldg(reinterpret_cast<const uint2*>(a.colpar + (size_t)(item.t0 + u) * (UM_NT / 32) + h * (UM_HALF / 32)));
+                const uint32_t par[2] = {pw2.x, pw2.y};
                 uint32_t v[UM_HALF];
                 mbar_wait(ACC_FULL(g, buf), (jb >> 1) & 1);
                 tc_fence_after();
