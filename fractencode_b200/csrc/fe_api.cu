@@ -327,146 +327,256 @@ static int rerank_fp32_regime(fe_ctx* ctx, const LevelIO& io, const fe_params& p
 }
 
 // tcgen05 search of one level (kind 0: f16 operands, T = 4, 8; kind 1: i8 operands, T <= 32).
-// Without a threshold: one pass, every range against every admissible domain.  With a threshold the scan is cut into
-// growing slices of the domain order; after each slice the ranges that met the threshold are final (their first hit in
-// scan order lies in the slices searched so far -- the reference stops there too, TransformEstimator2.hpp:40-41) and
-// only the survivors go on, compacted into fresh row tiles.  Results land in the level's row slots through
-// UmmaArgs::rowslot, so the winner rules of k_finalize see exactly what a single full pass would have left for every
-// range that matters: first hits for the resolved ranges, the complete minimum for the ranges that never hit.
+//
+// Without a threshold: one pass, every range against every admissible domain.
+//
+// With a threshold two exact prunings apply, both leaving k_finalize with what it needs to reproduce the reference's
+// estimate() (TransformEstimator2.hpp:29-47): the first candidate in scan order under the threshold, else the minimum.
+//  * Early-out: the scan is cut into growing slices of the domain order; after each slice the ranges whose first hit is
+//    known are final (the reference breaks there too, :40-41) and only the survivors go on, compacted into fresh row tiles.
+//  * Brightness bins (no classifier): by Cauchy-Schwarz (sum(4r) - sum(D))^2 <= N * n16, so a candidate can only be under the
+//    threshold when the two block sums differ by at most R = floor(sqrt(N * thr16)).  Blocks are bucketed by sum / width with
+//    width > R, so a range of bin c finds every possible hit in the domain bins c-1, c, c+1 (three launches per slice over
+//    the same rows).  Ranges that never hit get their minimum from one plain pass over all domains at the end -- unless the
+//    level can split, where a range without a hit is split and its minimum is never looked at (Encoder2 quadtree rule).
+// Hits are recorded as DOMAIN indices (atomicMin), so "first in scan order" holds across bins, slices and column chunks.
+struct TcBuckets {
+    int nb = 1;
+    const uint32_t* dom_order = nullptr;   // position -> domain index, ascending inside a bucket
+    const uint32_t* rng_order = nullptr;   // position -> range index
+    uint32_t doff[FE_MAX_BUCKETS + 1] = {0}, roff[FE_MAX_BUCKETS + 1] = {0};
+    bool bins = false;                     // brightness bins: range bucket c pairs with domain buckets c-1, c, c+1
+    uint32_t cut[8] = {0};                 // bins: domain-index cutoffs of the slice schedule (fractions 2^k / 128 of the scan)
+    uint32_t pre[FE_MAX_BUCKETS][8] = {};  // bins: positions of bucket b below cut[k]
+};
+
 struct TcSearchResult {
     bool inexact = false;      // kind 0 only: a winner sits in the fp32-inexact band, redo on kind 1
     uint64_t evaluated = 0;    // (range, domain, rotation) candidates actually scored
-    uint32_t passes = 0;
+    uint32_t passes = 0;       // slices
+    uint32_t launches = 0;     // search kernel launches
     float kernel_ms = 0.f;     // search launches only (CUDA events), when timed
 };
 
-static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const uint32_t* dom_order, const uint32_t* rng_order, const uint32_t doff[8],
-                     const uint32_t roff[8], int nbuckets, uint32_t thr16, bool use_thr, bool timed, TcSearchResult* res) {
+static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& tb, uint32_t thr16, bool use_thr, bool need_min, bool timed,
+                     TcSearchResult* res) {
     const LevelGeom& g = io.g;
     const uint32_t nR = io.nR, nD = io.nD;
-    const bool single_pass = getenv("FE_SINGLE_PASS") != nullptr;   // tuning / A-B switch: never slice the scan
+    const int nb = tb.nb;
+    const bool single_pass = getenv("FE_SINGLE_PASS") != nullptr;         // tuning / A-B switch: never slice the scan
+    const bool pass_dbg = getenv("FE_PASS_DBG") != nullptr;
     const bool multipass = use_thr && !single_pass;
     const uint32_t GR = 128;                                              // slice granularity: whole column tiles of both kinds
     LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
     LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));
-    FE_CUDA(ctx, ctx->b_hist.ensure(8 * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_hist.ensure(64 * sizeof(uint32_t)));
+    uint32_t* d_cnt = ctx->b_hist.as<uint32_t>();
+    uint32_t* d_nsel = d_cnt + 40;
 
-    uint32_t dc[7], done[7], aoff[8];
-    for (int c = 0; c < 7; ++c) { dc[c] = c < nbuckets ? doff[c + 1] - doff[c] : 0; done[c] = 0; }
-    for (int c = 0; c <= 7; ++c) aoff[c] = roff[std::min(c, nbuckets)];
-    const uint32_t* items = rng_order;   // range position of the pass -> range item
-    const uint32_t* slots = nullptr;     // range position of the pass -> range position of the level
+    uint32_t dc[FE_MAX_BUCKETS], done[FE_MAX_BUCKETS], aoff[FE_MAX_BUCKETS + 1];
+    for (int c = 0; c < nb; ++c) { dc[c] = tb.doff[c + 1] - tb.doff[c]; done[c] = 0; }
+    for (int c = 0; c <= nb; ++c) aoff[c] = tb.roff[c];
+    const uint32_t* items = tb.rng_order; // range position of the pass -> range item
+    const uint32_t* slots = nullptr;      // range position of the pass -> range position of the level
     uint32_t nA = nR;
-    int gen = 0;
-    double F = multipass ? 1.0 / 128.0 : 1.0;   // cumulative fraction of each bucket's scan after this pass
-    bool reuse_rows = false;             // the operand rows of the current range list are already built
+    int gen = 0, kF = 0;                  // F = 2^kF / 128: cumulative fraction of the scan after this pass
+    double F = multipass ? 1.0 / 128.0 : 1.0;
+    bool reuse_rows = false;              // the operand rows of the current range list are already built
+    bool open_left = true;                // some range may still be without a hit
     *res = TcSearchResult{};
-    for (;;) {
-        if (res->passes >= (uint32_t)FE_MAX_PASSES - 1) F = 1.0;
-        SearchPass sp{};
-        sp.dom_order = dom_order; sp.rng_items = items; sp.rowslot = slots;
-        sp.nbuckets = nbuckets; sp.n_dom = nD;
-        sp.reuse_rows = reuse_rows; sp.reuse_dom_norms = res->passes > 0;
-        bool all_done = true, any_work = false;
-        for (int c = 0; c < nbuckets; ++c) {
-            const uint32_t rc = aoff[c + 1] - aoff[c];
-            uint32_t hi = dc[c];
-            if (rc && F < 1.0) {
-                const uint64_t want = std::max<uint64_t>(16 * GR, (uint64_t)std::ceil((double)dc[c] * F));
-                const uint64_t up = (want + GR - 1) / GR * GR;
-                hi = (uint32_t)std::min<uint64_t>(dc[c], std::max<uint64_t>(up, (uint64_t)done[c] + 16 * GR));   // every pass advances
-                if (dc[c] - hi < 8 * GR) hi = dc[c];                      // no slivers at the end of the scan
-            }
-            sp.dbeg[c] = doff[c] + done[c];
-            sp.dend[c] = doff[c] + (rc ? hi : done[c]);
-            res->evaluated += (uint64_t)rc * (rc ? hi - done[c] : 0) * 4;
-            if (rc && hi > done[c]) any_work = true;
-            done[c] = hi;
-            if (hi < dc[c]) all_done = false;
+    uint32_t host[FE_MAX_BUCKETS + 1];
+
+    // survivors of the current list (positions whose best hit is not below `cutoff`), compacted; updates the list state
+    auto survivors = [&](uint32_t cutoff, bool read_inexact, bool* inexact, uint32_t* n_left) -> int {
+        FE_CUDA(ctx, ctx->b_act_flags.ensure((size_t)nA + 16));
+        FE_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, FE_MAX_BUCKETS * sizeof(uint32_t), ctx->stream));
+        BucketOff o;
+        for (int c = 0; c <= FE_MAX_BUCKETS; ++c) o.v[c] = aoff[std::min(c, nb)];
+        LAUNCH(ctx, k_unresolved, cdiv(nA, 256), 256, slots, ctx->b_rowhit.as<uint32_t>(), nA, o, nb, cutoff, ctx->b_act_flags.as<uint8_t>(), d_cnt);
+        FE_CUDA(ctx, cudaMemcpyAsync(host, d_cnt, FE_MAX_BUCKETS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (read_inexact)
+            FE_CUDA(ctx, cudaMemcpyAsync(host + FE_MAX_BUCKETS, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *inexact = read_inexact && (host[FE_MAX_BUCKETS] & 1u);
+        uint32_t S = 0;
+        for (int c = 0; c < nb; ++c) S += host[c];
+        *n_left = S;
+        if (*inexact || S == 0 || S == nA) return FE_OK;
+        // stable compaction of the surviving positions (bucket grouping is kept), then their item indices
+        DevBuf& out = ctx->b_act[gen];
+        FE_CUDA(ctx, out.ensure((size_t)S * 4 + 16));
+        FE_CUDA(ctx, ctx->b_act_items.ensure((size_t)S * 4 + 16));
+        size_t tmp_bytes = 0;
+        if (slots) {
+            FE_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, slots, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
+            FE_CUDA(ctx, ctx->b_act_tmp.ensure(tmp_bytes));
+            FE_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_act_tmp.p, tmp_bytes, slots, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
+        } else {
+            thrust::counting_iterator<uint32_t> iota(0u);
+            FE_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
+            FE_CUDA(ctx, ctx->b_act_tmp.ensure(tmp_bytes));
+            FE_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_act_tmp.p, tmp_bytes, iota, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
         }
-        for (int c = 0; c <= nbuckets; ++c) sp.roff[c] = aoff[c];
-        if (timed) { sp.ev0 = ctx->ev_pass[2 * res->passes]; sp.ev1 = ctx->ev_pass[2 * res->passes + 1]; }
-        if (!any_work) {                                                   // nothing left to scan for the surviving buckets
-            if (all_done) break;
-            F *= 2.0;
-            continue;
+        ctx->stats.kernel_launches += 2;
+        slots = out.as<uint32_t>();
+        gen ^= 1;
+        if (tb.rng_order) {
+            LAUNCH(ctx, k_gather_u32, cdiv(S, 256), 256, slots, tb.rng_order, S, ctx->b_act_items.as<uint32_t>());
+            items = ctx->b_act_items.as<uint32_t>();
+        } else {
+            items = slots;
         }
-        const bool pass_dbg = getenv("FE_PASS_DBG") != nullptr;
-        if (pass_dbg) {
-            uint64_t cols = 0;
-            for (int c = 0; c < nbuckets; ++c) cols += sp.dend[c] - sp.dbeg[c];
-            fprintf(stderr, "[pass] T=%u kind=%d pass=%u ranges=%u cols=%llu (scan fraction so far %.4f) rebuild_rows=%d\n", g.T, kind, res->passes, nA,
-                    (unsigned long long)cols, F, reuse_rows ? 0 : 1);
-        }
+        aoff[0] = 0;
+        for (int c = 0; c < nb; ++c) aoff[c + 1] = aoff[c] + host[c];
+        nA = S;
+        reuse_rows = false;
+        return FE_OK;
+    };
+    auto launch = [&](SearchPass& sp) -> int {
+        if (res->launches >= (uint32_t)FE_MAX_LAUNCHES) return fe_fail(ctx, FE_ERR_CUDA, "internal: search launch budget exceeded");
+        if (timed) { sp.ev0 = ctx->ev_pass[2 * res->launches]; sp.ev1 = ctx->ev_pass[2 * res->launches + 1]; }
+        sp.reuse_rows = reuse_rows;
         if (kind == 0) FE_TRY(umma_prepare_and_search(ctx, g, io.d_dom, io.d_rng, sp, thr16, use_thr));
         else FE_TRY(umma_i8_prepare_and_search(ctx, g, io.d_dom, io.d_rng, sp, thr16, use_thr));
-        ++res->passes;
+        ++res->launches;
         reuse_rows = true;
+        return FE_OK;
+    };
 
-        // survivors + the inexact flag in one round trip
-        uint32_t host[8 + 1] = {0};
-        if (!all_done) {
-            FE_CUDA(ctx, ctx->b_act_flags.ensure((size_t)nA + 16));
-            FE_CUDA(ctx, cudaMemsetAsync(ctx->b_hist.p, 0, 8 * sizeof(uint32_t), ctx->stream));
-            Off8 o8;
-            for (int c = 0; c <= 7; ++c) o8.v[c] = aoff[c];
-            LAUNCH(ctx, k_unresolved, cdiv(nA, 256), 256, slots, ctx->b_rowhit.as<uint32_t>(), nA, o8, nbuckets, ctx->b_act_flags.as<uint8_t>(),
-                   ctx->b_hist.as<uint32_t>());
-            FE_CUDA(ctx, cudaMemcpyAsync(host, ctx->b_hist.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    for (;;) {
+        if (res->passes >= (uint32_t)FE_MAX_PASSES - 2) F = 1.0;
+        // ---- domain slice of every bucket for this pass ----
+        uint32_t lo[FE_MAX_BUCKETS], hi[FE_MAX_BUCKETS];
+        bool all_done = true, any_work = false;
+        for (int b = 0; b < nb; ++b) {
+            bool wanted = aoff[b + 1] > aoff[b];
+            if (tb.bins) {
+                if (b > 0 && aoff[b] > aoff[b - 1]) wanted = true;
+                if (b + 1 < nb && aoff[b + 2] > aoff[b + 1]) wanted = true;
+            }
+            lo[b] = done[b];
+            hi[b] = dc[b];
+            if (!wanted) { lo[b] = hi[b] = done[b] = dc[b]; continue; }   // its ranges are all closed: never needed again
+            if (F < 1.0) {
+                const uint64_t target = tb.bins ? tb.pre[b][kF] : (uint64_t)std::ceil((double)dc[b] * F);
+                const uint64_t up = (std::max<uint64_t>(16 * GR, target) + GR - 1) / GR * GR;
+                hi[b] = (uint32_t)std::min<uint64_t>(dc[b], std::max<uint64_t>(up, (uint64_t)done[b] + 16 * GR));   // every pass advances
+                if (dc[b] - hi[b] < 8 * GR) hi[b] = dc[b];                // no slivers at the end of the scan
+            }
+            if (hi[b] > lo[b]) any_work = true;
+            if (hi[b] < dc[b]) all_done = false;
         }
-        if (kind == 0 || !all_done) {
-            FE_CUDA(ctx, cudaMemcpyAsync(host + 8, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-            FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!any_work) break;
+        // every admissible domain with an index below `cutoff` has been scored once this pass is through
+        const uint32_t cutoff = (tb.bins && !all_done) ? tb.cut[kF] : FE_NONE32;
+        for (int shift = tb.bins ? -1 : 0; shift <= (tb.bins ? 1 : 0); ++shift) {
+            SearchPass sp{};
+            sp.dom_order = tb.dom_order; sp.rng_items = items; sp.rowslot = slots;
+            sp.nbuckets = nb; sp.n_dom = nD;
+            sp.reuse_dom_norms = res->launches > 0;
+            uint64_t cols = 0, work = 0;
+            for (int c = 0; c < nb; ++c) {
+                const int b = c + shift;
+                const uint32_t rc = aoff[c + 1] - aoff[c];
+                sp.dbeg[c] = sp.dend[c] = 0;
+                if (rc && b >= 0 && b < nb && hi[b] > lo[b]) {
+                    sp.dbeg[c] = tb.doff[b] + lo[b];
+                    sp.dend[c] = tb.doff[b] + hi[b];
+                    cols += hi[b] - lo[b];
+                    work += (uint64_t)rc * (hi[b] - lo[b]) * 4;
+                }
+            }
+            for (int c = 0; c <= nb; ++c) sp.roff[c] = aoff[c];
+            if (!work) continue;
+            if (pass_dbg)
+                fprintf(stderr, "[pass] T=%u kind=%d pass=%u shift=%d ranges=%u cols=%llu candidates=%.3e (scan fraction %.4f) rebuild_rows=%d\n", g.T, kind,
+                        res->passes, shift, nA, (unsigned long long)cols, (double)work, F, reuse_rows ? 0 : 1);
+            FE_TRY(launch(sp));
+            res->evaluated += work;
         }
-        if (kind == 0 && (host[8] & 1u)) { res->inexact = true; break; }
-        if (all_done) break;
+        for (int b = 0; b < nb; ++b) done[b] = hi[b];
+        ++res->passes;
+
+        if (all_done) {
+            if (kind == 0) {
+                FE_CUDA(ctx, cudaMemcpyAsync(host + FE_MAX_BUCKETS, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                res->inexact = (host[FE_MAX_BUCKETS] & 1u) != 0;
+            }
+            break;
+        }
+        const uint32_t before = nA;
         uint32_t S = 0;
-        for (int c = 0; c < nbuckets; ++c) S += host[c];
-        if (S == 0) break;                                                // every range has its first hit
-        const double resolved = 1.0 - (double)S / (double)nA;
-        if (S < nA) {
-            // stable compaction of the surviving positions (bucket grouping is kept), then their item indices
-            DevBuf& out = ctx->b_act[gen];
-            FE_CUDA(ctx, out.ensure((size_t)S * 4 + 16));
-            FE_CUDA(ctx, ctx->b_act_items.ensure((size_t)S * 4 + 16));
-            uint32_t* d_nsel = ctx->b_hist.as<uint32_t>() + 7;
-            size_t tmp_bytes = 0;
-            if (slots) {
-                FE_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, slots, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
-                FE_CUDA(ctx, ctx->b_act_tmp.ensure(tmp_bytes));
-                FE_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_act_tmp.p, tmp_bytes, slots, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
-            } else {
-                thrust::counting_iterator<uint32_t> iota(0u);
-                FE_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
-                FE_CUDA(ctx, ctx->b_act_tmp.ensure(tmp_bytes));
-                FE_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_act_tmp.p, tmp_bytes, iota, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
-            }
-            ctx->stats.kernel_launches += 2;
-            slots = out.as<uint32_t>();
-            gen ^= 1;
-            if (rng_order) {
-                LAUNCH(ctx, k_gather_u32, cdiv(S, 256), 256, slots, rng_order, S, ctx->b_act_items.as<uint32_t>());
-                items = ctx->b_act_items.as<uint32_t>();
-            } else {
-                items = slots;
-            }
-            aoff[0] = 0;
-            for (int c = 0; c < 7; ++c) aoff[c + 1] = aoff[c] + (c < nbuckets ? host[c] : 0);
-            nA = S;
-            reuse_rows = false;
-        }
-        F *= resolved >= 0.03 ? 2.0 : 4.0;
+        FE_TRY(survivors(cutoff, kind == 0, &res->inexact, &S));
+        if (res->inexact) break;
+        if (S == 0) { open_left = false; break; }                         // every range has its first hit
+        const double resolved = 1.0 - (double)S / (double)before;
+        const int step = resolved >= 0.03 ? 1 : 2;
+        kF += step;
+        F *= step == 1 ? 2.0 : 4.0;
+        if (kF > 7) { kF = 7; F = 1.0; }
     }
-    if (timed && res->passes) {
-        cudaEventSynchronize(ctx->ev_pass[2 * res->passes - 1]);
-        for (uint32_t i = 0; i < res->passes; ++i) {
+
+    if (tb.bins && need_min && open_left && !res->inexact) {
+        // ---- ranges without any hit: their minimum over ALL domains, one plain pass in scan order ----
+        uint32_t S = 0;
+        bool inex = false;
+        FE_TRY(survivors(FE_NONE32, false, &inex, &S));
+        if (S) {
+            LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
+            SearchPass sp{};
+            sp.dom_order = nullptr; sp.rng_items = items; sp.rowslot = slots;
+            sp.nbuckets = 1; sp.n_dom = nD;
+            sp.reuse_dom_norms = false;
+            sp.dbeg[0] = 0; sp.dend[0] = nD;
+            sp.roff[0] = 0; sp.roff[1] = S;
+            reuse_rows = false;                                           // one bucket now: different row tiles
+            if (pass_dbg) fprintf(stderr, "[pass] T=%u kind=%d minimum pass: ranges=%u cols=%u\n", g.T, kind, S, nD);
+            FE_TRY(launch(sp));
+            res->evaluated += (uint64_t)S * nD * 4;
+            ++res->passes;
+            if (kind == 0) {
+                FE_CUDA(ctx, cudaMemcpyAsync(host + FE_MAX_BUCKETS, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                res->inexact = (host[FE_MAX_BUCKETS] & 1u) != 0;
+            }
+        }
+    }
+    if (timed && res->launches) {
+        cudaEventSynchronize(ctx->ev_pass[2 * res->launches - 1]);
+        for (uint32_t i = 0; i < res->launches; ++i) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->ev_pass[2 * i], ctx->ev_pass[2 * i + 1]);
             res->kernel_ms += ms;
-            if (getenv("FE_PASS_DBG")) fprintf(stderr, "[pass] T=%u kind=%d pass=%u kernel %.3f ms\n", g.T, kind, i, ms);
+            if (pass_dbg) fprintf(stderr, "[pass] T=%u kind=%d launch=%u kernel %.3f ms\n", g.T, kind, i, ms);
         }
     }
+    return FE_OK;
+}
+
+// Stable bucketing of a uniform block list by brightness bin (see search_tc); order[pos] = item index.
+static int bucket_by_brightness(fe_ctx* ctx, const Plane& pl, const fe_grid_item* d_items, uint32_t n, uint32_t edge, uint32_t mul, uint32_t width,
+                                int nbins, DevBuf& order, uint32_t off[FE_MAX_BUCKETS + 1]) {
+    FE_CUDA(ctx, order.ensure((size_t)n * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_keys_tmp.ensure((size_t)n * 2 + 64));
+    FE_CUDA(ctx, ctx->b_vals_tmp.ensure((size_t)n * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_hist.ensure(64 * sizeof(uint32_t)));
+    uint8_t* keys_in = ctx->b_keys_tmp.as<uint8_t>();
+    uint8_t* keys_out = keys_in + n;
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_hist.p, 0, FE_MAX_BUCKETS * sizeof(uint32_t), ctx->stream));
+    LAUNCH(ctx, k_brightness_bins, cdiv((uint64_t)n * 32, 256), 256, pl.px, pl.stride, d_items, n, edge, mul, width, keys_in, ctx->b_hist.as<uint32_t>());
+    LAUNCH(ctx, k_iota, cdiv(n, 256), 256, ctx->b_vals_tmp.as<uint32_t>(), n);
+    size_t tmp_bytes = 0;
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, ctx->b_vals_tmp.as<uint32_t>(), order.as<uint32_t>(), (int)n, 0, 5, ctx->stream));
+    FE_CUDA(ctx, ctx->b_sort_tmp.ensure(tmp_bytes));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_bytes, keys_in, keys_out, ctx->b_vals_tmp.as<uint32_t>(), order.as<uint32_t>(), (int)n, 0, 5, ctx->stream));
+    ctx->stats.kernel_launches += 3;
+    uint32_t hist[FE_MAX_BUCKETS];
+    FE_CUDA(ctx, cudaMemcpyAsync(hist, ctx->b_hist.p, sizeof(hist), cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    off[0] = 0;
+    for (int c = 0; c < nbins; ++c) off[c + 1] = off[c] + hist[c];
     return FE_OK;
 }
 
@@ -514,19 +624,57 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     uint64_t evaluated = matches;
     uint32_t passes = 1;
     float kernel_ms = -1.f;
+    bool bins = false;
     if (p.search_impl != FE_SEARCH_EXACT && (f16_ok || i8_ok)) {
+        TcBuckets tb;
+        tb.nb = nbuckets;
+        tb.dom_order = dom_order; tb.rng_order = rng_order;
+        for (int c = 0; c <= nbuckets; ++c) { tb.doff[c] = doff[c]; tb.roff[c] = roff[c]; }
+        // ---- brightness bins (threshold, no classifier): see search_tc ----
+        if (use_thr && !p.use_classifier && nD && !getenv("FE_NO_BINS") && !getenv("FE_SINGLE_PASS")) {
+            const uint64_t nt = (uint64_t)g.N * thr16;
+            uint64_t R = (uint64_t)std::sqrt((double)nt);
+            while (R * R > nt) --R;
+            while ((R + 1) * (R + 1) <= nt) ++R;
+            const uint64_t maxsum = 1020ull * g.N;
+            const uint64_t width = std::max<uint64_t>(R + 1, (maxsum + FE_MAX_BUCKETS) / FE_MAX_BUCKETS);
+            const int nbins = (int)(maxsum / width) + 1;
+            if (nbins >= 4 && nbins <= FE_MAX_BUCKETS) {
+                FE_TRY(bucket_by_brightness(ctx, ctx->src, io.d_dom, nD, g.S, 1, (uint32_t)width, nbins, ctx->b_dom_order, tb.doff));
+                FE_TRY(bucket_by_brightness(ctx, ctx->tgt, io.d_rng, nR, g.T, 4, (uint32_t)width, nbins, ctx->b_rng_order, tb.roff));
+                tb.nb = nbins;
+                tb.dom_order = ctx->b_dom_order.as<uint32_t>();
+                tb.rng_order = ctx->b_rng_order.as<uint32_t>();
+                tb.bins = bins = true;
+                for (int k = 0; k < 8; ++k) tb.cut[k] = k == 7 ? nD : (uint32_t)(((uint64_t)nD << k) / 128 + 1);
+                FE_CUDA(ctx, ctx->b_scan_tmp.ensure((8 + FE_MAX_BUCKETS * 8) * sizeof(uint32_t)));
+                uint32_t* d_cut = ctx->b_scan_tmp.as<uint32_t>();
+                FE_CUDA(ctx, cudaMemcpyAsync(d_cut, tb.cut, sizeof(tb.cut), cudaMemcpyHostToDevice, ctx->stream));
+                BucketOff o;
+                for (int c = 0; c <= FE_MAX_BUCKETS; ++c) o.v[c] = tb.doff[std::min(c, nbins)];
+                LAUNCH(ctx, k_bin_prefix, cdiv((uint64_t)nbins * 8, 128), 128, tb.dom_order, o, nbins, d_cut, 8, d_cut + 8);
+                uint32_t pre[FE_MAX_BUCKETS * 8];
+                FE_CUDA(ctx, cudaMemcpyAsync(pre, d_cut + 8, (size_t)nbins * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                for (int b = 0; b < nbins; ++b)
+                    for (int k = 0; k < 8; ++k) tb.pre[b][k] = pre[b * 8 + k];
+                dom_order = nullptr;                 // results come back as domain indices
+                rng_order = tb.rng_order;            // row slots follow the binned range order
+            }
+        }
+        const bool need_min = !io.can_split;
         TcSearchResult r{};
         r.inexact = !f16_ok;
         evaluated = 0; passes = 0; kernel_ms = 0.f;
         if (f16_ok) {
             // ---- tcgen05 kind::f16 (T = 4, 8): fp16 operand blobs, integer-exact fp32 accumulators, fused argmin ----
-            FE_TRY(search_tc(ctx, io, 0, dom_order, rng_order, doff, roff, nbuckets, thr16, use_thr, timed, &r));
-            evaluated += r.evaluated; passes += r.passes; kernel_ms += r.kernel_ms;
+            FE_TRY(search_tc(ctx, io, 0, tb, thr16, use_thr, need_min, timed, &r));
+            evaluated += r.evaluated; passes += r.launches; kernel_ms += r.kernel_ms;
         }
         if (r.inexact) {
             // ---- tcgen05 kind::i8 (T >= 16, or a winner of the f16 kind in the fp32-inexact band): exact s32 accumulators ----
-            FE_TRY(search_tc(ctx, io, 1, dom_order, rng_order, doff, roff, nbuckets, thr16, use_thr, timed, &r));
-            evaluated += r.evaluated; passes += r.passes; kernel_ms += r.kernel_ms;
+            FE_TRY(search_tc(ctx, io, 1, tb, thr16, use_thr, need_min, timed, &r));
+            evaluated += r.evaluated; passes += r.launches; kernel_ms += r.kernel_ms;
         }
         searched = true;
         ctx->stats.umma_levels++;
@@ -591,6 +739,8 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     FE_CUDA(ctx, ctx->b_bound.ensure((size_t)nR * 4 + 4));
     f.bound_out = ctx->b_bound.as<uint32_t>();
     f.rerank = 0;
+    f.hit_is_domain = searched ? 1 : 0;
+    f.no_min = (bins && io.can_split) ? 1 : 0;
     LAUNCH(ctx, k_finalize, cdiv((uint64_t)nR * 32, 256), 256, f);
     if (timed) cudaEventRecord(ctx->ev[3], ctx->stream);
 
@@ -599,7 +749,14 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (counters[0]) return fe_fail(ctx, FE_ERR_CUDA, "internal: %u winners whose search score disagrees with the direct recomputation (T=%u)", counters[0], g.T);
     ctx->stats.fp32_regime_items += counters[1];
-    if (counters[1]) FE_TRY(rerank_fp32_regime(ctx, io, p, dom_order, rng_order, doff, roff, nbuckets));
+    if (counters[1]) {
+        if (bins) { // every domain is admissible for the minimum: one bucket in scan order, rows in the binned range order
+            const uint32_t d1[8] = {0, nD, nD, nD, nD, nD, nD, nD}, r1[8] = {0, nR, nR, nR, nR, nR, nR, nR};
+            FE_TRY(rerank_fp32_regime(ctx, io, p, nullptr, rng_order, d1, r1, 1));
+        } else {
+            FE_TRY(rerank_fp32_regime(ctx, io, p, dom_order, rng_order, doff, roff, nbuckets));
+        }
+    }
     if (timed) {
         float ms = 0;
         if (kernel_ms >= 0.f) { // tcgen05 path: the search launches were timed one by one; the rest of the level is preparation

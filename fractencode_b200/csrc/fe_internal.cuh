@@ -73,6 +73,8 @@ struct SearchArgs {
 };
 
 constexpr int FE_MAX_PASSES = 32;
+constexpr int FE_MAX_LAUNCHES = 3 * FE_MAX_PASSES + 4;   // search launches of one level (three brightness-bin shifts per slice)
+constexpr int FE_MAX_BUCKETS = 32;   // classifier buckets (7) or brightness bins of the threshold pruning (<= 32)
 
 struct fe_ctx {
     int device = 0;
@@ -97,7 +99,7 @@ struct fe_ctx {
     DevBuf b_dec_a, b_dec_b, b_dec_items, b_dec_sum, b_q;
     fe_stats stats{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_pass[2 * FE_MAX_PASSES] = {}; // start/stop around each search launch of a level
+    cudaEvent_t ev_pass[2 * FE_MAX_LAUNCHES] = {}; // start/stop around each search launch of a level
 };
 
 int fe_fail(fe_ctx* ctx, int code, const char* fmt, ...);

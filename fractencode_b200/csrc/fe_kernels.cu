@@ -147,18 +147,20 @@ __global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-// Multi-pass search: flags[i] = 1 when none of the four rotation rows of range position i (result slot slots[i]) has met the
-// threshold yet; cnt[b] += survivors of bucket b (roff = prefix offsets of the pass's positions).
-__global__ void k_unresolved(const uint32_t* __restrict__ slots, const uint32_t* __restrict__ rowhit, uint32_t n, Off8 roff, int nb,
-                             uint8_t* __restrict__ flags, uint32_t* __restrict__ cnt) {
-    __shared__ uint32_t sc[8];
-    if (threadIdx.x < 8) sc[threadIdx.x] = 0;
+// Multi-pass search: flags[i] = 1 when the range at position i (result slot slots[i]) is still open: none of its four rotation
+// rows has a candidate under the threshold at a domain index below `cutoff` (every admissible domain below the cutoff has
+// been scored, so a recorded hit below it is the first in scan order; 0xFFFFFFFF = "any hit closes the range").
+// cnt[b] += survivors of bucket b (roff = prefix offsets of the pass's positions).
+__global__ void k_unresolved(const uint32_t* __restrict__ slots, const uint32_t* __restrict__ rowhit, uint32_t n, BucketOff roff, int nb,
+                             uint32_t cutoff, uint8_t* __restrict__ flags, uint32_t* __restrict__ cnt) {
+    __shared__ uint32_t sc[FE_MAX_BUCKETS];
+    if (threadIdx.x < FE_MAX_BUCKETS) sc[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const uint32_t s = slots ? slots[i] : i;
         const uint4 h = reinterpret_cast<const uint4*>(rowhit)[s];
-        const bool alive = (h.x & h.y & h.z & h.w) == FE_NONE32;
+        const bool alive = min(min(h.x, h.y), min(h.z, h.w)) >= cutoff;
         flags[i] = alive ? 1 : 0;
         if (alive) {
             int b = 0;
@@ -167,7 +169,56 @@ __global__ void k_unresolved(const uint32_t* __restrict__ slots, const uint32_t*
         }
     }
     __syncthreads();
-    if (threadIdx.x < 8 && sc[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], sc[threadIdx.x]);
+    if (threadIdx.x < FE_MAX_BUCKETS && sc[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], sc[threadIdx.x]);
+}
+
+// Brightness bin of every block of a uniform list: key = (mul * sum of the block's edge x edge pixels) / width, one warp per
+// block.  For a range block mul = 4 (sum of 4 r); for a domain block mul = 1 and edge = S (the sum of its 2x2 box sums D is the
+// sum of its pixels).  hist[key] counts.
+__global__ void k_brightness_bins(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ items, uint32_t n,
+                                  uint32_t edge, uint32_t mul, uint32_t width, uint8_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[FE_MAX_BUCKETS];
+    if (threadIdx.x < FE_MAX_BUCKETS) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p < n) {
+        const fe_grid_item it = items[p];
+        const uint8_t* base = img + (size_t)it.y * stride + it.x;
+        uint32_t s = 0;
+        if ((edge & 3u) == 0 && ((reinterpret_cast<uintptr_t>(base) | stride) & 3u) == 0) {
+            const uint32_t wpr = edge / 4, nw = wpr * edge;   // 4-byte words per row / per block
+            for (uint32_t e = lane; e < nw; e += 32) {
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)(e / wpr) * stride) + (e % wpr));
+                s += __dp4a(v, 0x01010101u, 0u);
+            }
+        } else {
+            for (uint32_t e = lane; e < edge * edge; e += 32) s += base[(size_t)(e / edge) * stride + (e % edge)];
+        }
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        if (lane == 0) {
+            const uint32_t k = min((mul * s) / width, (uint32_t)FE_MAX_BUCKETS - 1);
+            keys[p] = (uint8_t)k;
+            atomicAdd(&sh[k], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < FE_MAX_BUCKETS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// out[b * ncut + k] = number of positions of bucket b whose domain index is below cutoffs[k] (positions of a bucket are in
+// ascending domain index, so these are prefix lengths).  One thread per (b, k).
+__global__ void k_bin_prefix(const uint32_t* __restrict__ dom_order, BucketOff doff, int nb, const uint32_t* __restrict__ cutoffs, int ncut,
+                             uint32_t* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb * ncut) return;
+    const int b = t / ncut, k = t % ncut;
+    const uint32_t c = cutoffs[k];
+    uint32_t lo = doff.v[b], hi = doff.v[b + 1];
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (dom_order[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    out[t] = lo - doff.v[b];
 }
 
 __global__ void k_gather_u32(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ table, uint32_t n, uint32_t* __restrict__ out) {
@@ -431,7 +482,7 @@ __global__ void k_finalize(FinalizeArgs f) {
         for (int k = 0; k < 4; ++k) {
             const uint32_t h = f.rowhit[4 * j + k];
             if (h != FE_NONE32) {
-                const uint32_t d = f.dom_order ? f.dom_order[h] : h;
+                const uint32_t d = (f.dom_order && !f.hit_is_domain) ? f.dom_order[h] : h;
                 const unsigned long long scan = (unsigned long long)d * 4 + k;
                 if (scan < bestscan) bestscan = scan;
             }
@@ -441,7 +492,7 @@ __global__ void k_finalize(FinalizeArgs f) {
             wd = (uint32_t)(bestscan >> 2);
         }
     }
-    if (wk < 0) { // minimum n16; ties -> smallest domain index, then LARGEST k
+    if (wk < 0 && !f.no_min) { // minimum n16; ties -> smallest domain index, then LARGEST k
         uint32_t bn = 0, bd = 0;
         for (int k = 0; k < 4; ++k) {
             const unsigned long long key = f.rowbest[4 * j + k];
@@ -467,6 +518,7 @@ __global__ void k_finalize(FinalizeArgs f) {
         if (lane == 0) {
             f.out[ri] = out;
             if (f.split) f.split[ri] = (f.can_split && !(100000.0 <= f.thr)) ? 1u : 0u;
+            if (f.bound_out) f.bound_out[j] = 0;
         }
         return;
     }

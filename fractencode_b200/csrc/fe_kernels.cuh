@@ -23,6 +23,8 @@ struct FinalizeArgs {
     uint32_t* fp32_regime;          // device counter: winners with SSE >= 2^20
     uint32_t* bound_out;            // NULL or [range position]: 0, or the n16 bound of the re-rank band for fp32-regime ranges
     int rerank;                     // rowbest keys hold float bits (re-rank pass)
+    int no_min;                     // the minimum is not wanted: a range without a hit gets the default item (and splits)
+    int hit_is_domain;              // rowhit holds domain indices (tcgen05 paths), not sorted column positions (exact path)
 };
 
 __global__ void k_uniform_grid(fe_grid_item* out, uint32_t nx, uint32_t n, uint32_t size, uint32_t step);
@@ -32,8 +34,12 @@ __global__ void k_classify(const uint8_t* img, uint32_t stride, const fe_grid_it
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n);
 __global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n);
 __global__ void k_iota(uint32_t* p, uint32_t n);
-struct Off8 { uint32_t v[8]; };
-__global__ void k_unresolved(const uint32_t* slots, const uint32_t* rowhit, uint32_t n, Off8 roff, int nb, uint8_t* flags, uint32_t* cnt);
+struct BucketOff { uint32_t v[FE_MAX_BUCKETS + 1]; };
+__global__ void k_unresolved(const uint32_t* slots, const uint32_t* rowhit, uint32_t n, BucketOff roff, int nb, uint32_t cutoff, uint8_t* flags,
+                             uint32_t* cnt);
+__global__ void k_brightness_bins(const uint8_t* img, uint32_t stride, const fe_grid_item* items, uint32_t n, uint32_t edge, uint32_t mul,
+                                  uint32_t width, uint8_t* keys, uint32_t* hist);
+__global__ void k_bin_prefix(const uint32_t* dom_order, BucketOff doff, int nb, const uint32_t* cutoffs, int ncut, uint32_t* out);
 __global__ void k_gather_u32(const uint32_t* idx, const uint32_t* table, uint32_t n, uint32_t* out);
 __global__ void k_class_keys(const int32_t* cls, uint32_t n, uint8_t* keys, uint32_t* hist);
 __global__ void k_build_rows(const uint8_t* img, uint32_t stride, const fe_grid_item* rng, const uint32_t* order, uint32_t n,

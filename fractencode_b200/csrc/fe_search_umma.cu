@@ -394,7 +394,10 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                     atomicMin(&a.rowbest[srow], key);
                     if (st.bestV >= 16777216.0f - 64.0f) atomicOr(a.flags, 1u);
                 }
-                if (st.hit != FE_NONE32) atomicMin(&a.rowhit[srow], item.col0 + st.hit);
+                if (st.hit != FE_NONE32) {
+                    const uint32_t hc = item.col0 + st.hit;
+                    atomicMin(&a.rowhit[srow], a.dom_order ? a.dom_order[hc] : hc);
+                }
             }
         }
     }
@@ -671,6 +674,7 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     a.use_thr = use_thr ? 1u : 0u;
     a.nt = UM_NT;
     a.rowslot = sp.rowslot;
+    a.dom_order = sp.dom_order;
     { const char* e = getenv("FE_UMMA_DBG"); a.dbg = e ? (uint32_t)atoi(e) : 0u; }
     const uint32_t stage_bytes = UM_NT * Kpad * 2, a_bytes = 2 * UM_ROWS * Kpad * 2;
     const uint32_t stages = 2 * UM_ISSUERS_F16;

@@ -223,7 +223,10 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_umma_i8(const UmmaA
                     const unsigned long long key = ((unsigned long long)n16 << 32) | (unsigned long long)(item.col0 + bestcol);
                     atomicMin(&a.rowbest[srow], key);
                 }
-                if (hit != FE_NONE32) atomicMin(&a.rowhit[srow], item.col0 + hit);
+                if (hit != FE_NONE32) {
+                    const uint32_t hc = item.col0 + hit;
+                    atomicMin(&a.rowhit[srow], a.dom_order ? a.dom_order[hc] : hc);
+                }
             }
         }
     }
@@ -402,6 +405,7 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     a.use_thr = use_thr ? 1u : 0u;
     a.nt = I8_NT;
     a.rowslot = sp.rowslot;
+    a.dom_order = sp.dom_order;
     const uint32_t stage_bytes = 2 * I8_NT * kc, a_bytes = UM_ROWS * Kpad;
     const uint32_t budget = 226 * 1024 - 512;
     a.n_abuf = (2 * a_bytes + 2 * stage_bytes <= budget) ? 2 : 1;

@@ -39,7 +39,7 @@ struct UmmaArgs {
     unsigned long long* rowbest;
     uint32_t* rowhit;
     uint32_t* flags;                 // bit 0: a winner sits in the fp32-inexact band
-    UmmaBucket b[7];
+    UmmaBucket b[FE_MAX_BUCKETS];
     int nb;
     uint32_t Kpad, stages, total_items, thr16, use_thr;
     uint32_t nt;                     // domain columns per tile (UM_NT for the f16 kind, I8_NT for the i8 kind)
@@ -47,11 +47,13 @@ struct UmmaArgs {
     uint32_t n_abuf;                 // i8 kind: A buffers in shared memory (2, or 1 when the tile is 128 KB)
     uint32_t dbg;                    // tuning probes (FE_UMMA_DBG): 1 skip TMEM drain, 2 skip MMA issue, 4 skip B copies
     const uint32_t* rowslot;         // [range position of this pass] -> range position of the level (result slot); NULL = identity
+    const uint32_t* dom_order;       // sorted column -> domain index (NULL = identity): rowhit holds DOMAIN indices, so hits found
+                                     // in different buckets / slices of the same row compare in scan order
 };
 
 struct UmmaBuckets {                 // operand-layout view for the blob builders
-    uint32_t range_off[8], row_tile0[8], col_tile0[8]; // [nb] entries are the totals
-    uint32_t dom_off[8], dom_end[8];                   // slice of domain positions of each bucket
+    uint32_t range_off[FE_MAX_BUCKETS + 1], row_tile0[FE_MAX_BUCKETS + 1], col_tile0[FE_MAX_BUCKETS + 1]; // [nb] entries are the totals
+    uint32_t dom_off[FE_MAX_BUCKETS + 1], dom_end[FE_MAX_BUCKETS + 1];   // slice of domain positions of each bucket
     uint32_t n_ranges, n_domains;
     int nb;
 };
@@ -64,8 +66,8 @@ struct SearchPass {
     const uint32_t* dom_order;       // domain position -> domain item index (NULL = identity)
     const uint32_t* rng_items;       // range position of this pass -> range item index (NULL = identity)
     const uint32_t* rowslot;         // range position of this pass -> range position of the level (NULL = identity)
-    uint32_t dbeg[7], dend[7];       // per bucket: domain positions searched in this pass
-    uint32_t roff[8];                // per bucket: range positions of this pass (prefix offsets)
+    uint32_t dbeg[FE_MAX_BUCKETS], dend[FE_MAX_BUCKETS]; // per bucket: domain positions searched in this pass
+    uint32_t roff[FE_MAX_BUCKETS + 1];                   // per bucket: range positions of this pass (prefix offsets)
     int nbuckets;
     uint32_t n_dom;                  // all domain positions of the level
     bool reuse_rows;                 // the A blob and row norms built by the previous pass are still valid
