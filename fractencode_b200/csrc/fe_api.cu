@@ -99,7 +99,7 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
                       &ctx->b_rowc, &ctx->b_coln, &ctx->b_rowbest, &ctx->b_rowhit, &ctx->b_hist, &ctx->b_level_items, &ctx->b_split,
                       &ctx->b_scan, &ctx->b_scan_tmp, &ctx->b_rng_next, &ctx->b_counters, &ctx->b_A16, &ctx->b_B16, &ctx->b_tmaps,
                       &ctx->b_items, &ctx->b_dec_a, &ctx->b_dec_b, &ctx->b_dec_items, &ctx->b_dec_sum, &ctx->b_q, &ctx->b_bound,
-                      &ctx->b_flag_idx, &ctx->b_act[0], &ctx->b_act[1], &ctx->b_act_items, &ctx->b_act_flags, &ctx->b_act_tmp};
+                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_act[0], &ctx->b_act[1], &ctx->b_act_items, &ctx->b_act_flags, &ctx->b_act_tmp};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_pass) if (ev) cudaEventDestroy(ev);
@@ -367,6 +367,8 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
     const bool pass_dbg = getenv("FE_PASS_DBG") != nullptr;
     const bool multipass = use_thr && !single_pass;
     const uint32_t GR = 128;                                              // slice granularity: whole column tiles of both kinds
+    const uint32_t min_step = (tb.bins ? 6 : 16) * GR;                    // columns a bucket advances per pass at least (a work item
+                                                                          // spans three buckets with bins)
     LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
     LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));
@@ -384,6 +386,7 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
     double F = multipass ? 1.0 / 128.0 : 1.0;
     bool reuse_rows = false;              // the operand rows of the current range list are already built
     bool open_left = true;                // some range may still be without a hit
+    uint32_t done_cutoff = 0;             // every admissible domain below this index has been scored for the ranges still listed
     *res = TcSearchResult{};
     uint32_t host[FE_MAX_BUCKETS + 1];
 
@@ -460,9 +463,9 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
             if (!wanted) { lo[b] = hi[b] = done[b] = dc[b]; continue; }   // its ranges are all closed: never needed again
             if (F < 1.0) {
                 const uint64_t target = tb.bins ? tb.pre[b][kF] : (uint64_t)std::ceil((double)dc[b] * F);
-                const uint64_t up = (std::max<uint64_t>(16 * GR, target) + GR - 1) / GR * GR;
-                hi[b] = (uint32_t)std::min<uint64_t>(dc[b], std::max<uint64_t>(up, (uint64_t)done[b] + 16 * GR));   // every pass advances
-                if (dc[b] - hi[b] < 8 * GR) hi[b] = dc[b];                // no slivers at the end of the scan
+                const uint64_t up = (std::max<uint64_t>(min_step, target) + GR - 1) / GR * GR;
+                hi[b] = (uint32_t)std::min<uint64_t>(dc[b], std::max<uint64_t>(up, (uint64_t)done[b] + min_step));   // every pass advances
+                if (dc[b] - hi[b] < min_step / 2) hi[b] = dc[b];         // no slivers at the end of the scan
             }
             if (hi[b] > lo[b]) any_work = true;
             if (hi[b] < dc[b]) all_done = false;
@@ -470,33 +473,33 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
         if (!any_work) break;
         // every admissible domain with an index below `cutoff` has been scored once this pass is through
         const uint32_t cutoff = (tb.bins && !all_done) ? tb.cut[kF] : FE_NONE32;
-        for (int shift = tb.bins ? -1 : 0; shift <= (tb.bins ? 1 : 0); ++shift) {
+        {
             SearchPass sp{};
             sp.dom_order = tb.dom_order; sp.rng_items = items; sp.rowslot = slots;
             sp.nbuckets = nb; sp.n_dom = nD;
+            sp.span = tb.bins ? 1 : 0;
+            sp.no_min = use_thr && !need_min;
             sp.reuse_dom_norms = res->launches > 0;
             uint64_t cols = 0, work = 0;
+            for (int b = 0; b < nb; ++b) {
+                sp.dbeg[b] = tb.doff[b] + lo[b];
+                sp.dend[b] = tb.doff[b] + hi[b];
+                cols += hi[b] - lo[b];
+            }
             for (int c = 0; c < nb; ++c) {
-                const int b = c + shift;
                 const uint32_t rc = aoff[c + 1] - aoff[c];
-                sp.dbeg[c] = sp.dend[c] = 0;
-                if (rc && b >= 0 && b < nb && hi[b] > lo[b]) {
-                    sp.dbeg[c] = tb.doff[b] + lo[b];
-                    sp.dend[c] = tb.doff[b] + hi[b];
-                    cols += hi[b] - lo[b];
-                    work += (uint64_t)rc * (hi[b] - lo[b]) * 4;
-                }
+                for (int b = std::max(0, c - sp.span); b <= std::min(nb - 1, c + sp.span); ++b) work += (uint64_t)rc * (hi[b] - lo[b]) * 4;
             }
             for (int c = 0; c <= nb; ++c) sp.roff[c] = aoff[c];
-            if (!work) continue;
             if (pass_dbg)
-                fprintf(stderr, "[pass] T=%u kind=%d pass=%u shift=%d ranges=%u cols=%llu candidates=%.3e (scan fraction %.4f) rebuild_rows=%d\n", g.T, kind,
-                        res->passes, shift, nA, (unsigned long long)cols, (double)work, F, reuse_rows ? 0 : 1);
+                fprintf(stderr, "[pass] T=%u kind=%d pass=%u ranges=%u cols=%llu candidates=%.3e (scan fraction %.4f) rebuild_rows=%d\n", g.T, kind,
+                        res->passes, nA, (unsigned long long)cols, (double)work, F, reuse_rows ? 0 : 1);
             FE_TRY(launch(sp));
             res->evaluated += work;
         }
         for (int b = 0; b < nb; ++b) done[b] = hi[b];
         ++res->passes;
+        done_cutoff = cutoff;
 
         if (all_done) {
             if (kind == 0) {
@@ -512,6 +515,9 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
         if (res->inexact) break;
         if (S == 0) { open_left = false; break; }                         // every range has its first hit
         const double resolved = 1.0 - (double)S / (double)before;
+        // Bins only pay when most ranges end on a hit: a range without one still needs the plain pass over every domain for
+        // its minimum.  Hits come early in the scan where they come at all -- a slice that closes few ranges says go plain now.
+        if (tb.bins && need_min && resolved < 0.25) break;
         const int step = resolved >= 0.03 ? 1 : 2;
         kF += step;
         F *= step == 1 ? 2.0 : 4.0;
@@ -519,10 +525,10 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
     }
 
     if (tb.bins && need_min && open_left && !res->inexact) {
-        // ---- ranges without any hit: their minimum over ALL domains, one plain pass in scan order ----
+        // ---- ranges whose first hit is not known yet: one plain pass over ALL domains in scan order (first hit and minimum) ----
         uint32_t S = 0;
         bool inex = false;
-        FE_TRY(survivors(FE_NONE32, false, &inex, &S));
+        FE_TRY(survivors(done_cutoff, false, &inex, &S));
         if (S) {
             LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
             SearchPass sp{};
@@ -740,7 +746,8 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     f.bound_out = ctx->b_bound.as<uint32_t>();
     f.rerank = 0;
     f.hit_is_domain = searched ? 1 : 0;
-    f.no_min = (bins && io.can_split) ? 1 : 0;
+    if (searched) f.dom_order = nullptr;   // the tcgen05 paths report domain indices (keys and hits), not sorted columns
+    f.no_min = (searched && use_thr && io.can_split) ? 1 : 0;   // a range without a hit splits: its minimum was not even tracked
     LAUNCH(ctx, k_finalize, cdiv((uint64_t)nR * 32, 256), 256, f);
     if (timed) cudaEventRecord(ctx->ev[3], ctx->stream);
 

@@ -91,7 +91,7 @@ struct fe_ctx {
     // indices, survivor flags, select scratch
     DevBuf b_act[2], b_act_items, b_act_flags, b_act_tmp;
     // tcgen05 path operands
-    DevBuf b_A16, b_B16, b_tmaps;
+    DevBuf b_A16, b_B16, b_tmaps, b_blob_dom, b_tileseg;
     // results
     DevBuf b_items;
     size_t n_items = 0;

@@ -49,9 +49,11 @@ struct RowState {
     uint32_t bestp;            // parity of sum(b^2) of the best column; 2 = not looked up yet
     uint32_t bestcol, hit;
     float vthr0, vthr1;
-    const uint32_t* par_item;  // parity words of the item's first tile (columns are contiguous from there)
+    const uint32_t* par_item;  // tile metadata of the item's first tile (4 words per half tile: parity lo, parity hi, valid, bucket)
 };
-__device__ __forceinline__ uint32_t row_parity(const RowState& st, uint32_t col) { return (st.par_item[col >> 5] >> (col & 31)) & 1u; }
+__device__ __forceinline__ uint32_t row_parity(const RowState& st, uint32_t col) {
+    return (st.par_item[(col >> 6) * 4 + ((col >> 5) & 1u)] >> (col & 31)) & 1u;
+}
 
 // Exhaustive scan of a half tile held in registers (rare: exact ties, threshold crossings).
 __device__ __forceinline__ void scan_half_full(const uint32_t (&v)[UM_HALF], RowState& st, bool need_best, bool need_hit, uint32_t colbase,
@@ -76,7 +78,7 @@ __device__ __forceinline__ void scan_half_full(const uint32_t (&v)[UM_HALF], Row
 
 // UM_HALF accumulator values of one row (columns colbase .. colbase+UM_HALF-1 of the work item).
 __device__ __forceinline__ void process_half(uint32_t (&v)[UM_HALF], RowState& st, bool row_ok, uint32_t colbase, uint32_t nvalid,
-                                             const uint32_t (&par)[UM_HALF / 32]) {
+                                             const uint32_t (&par)[UM_HALF / 32], bool want_min) {
     if (nvalid < UM_HALF) {
 #pragma unroll
         for (int i = 0; i < UM_HALF; ++i)
@@ -102,8 +104,8 @@ __device__ __forceinline__ void process_half(uint32_t (&v)[UM_HALF], RowState& s
     // A row that already crossed the threshold is finished for this work item: its range is decided by the first hit in
     // scan order, and no later column can come earlier (columns are visited in increasing order).
     const bool live = row_ok && st.hit == FE_NONE32;
-    const bool improve = live && tmin < st.bestV;
-    const bool tie = live && tmin == st.bestV;                       // an equal V with even parity could win
+    const bool improve = want_min && live && tmin < st.bestV;
+    const bool tie = want_min && live && tmin == st.bestV;           // an equal V with even parity could win
     const bool need_hit = live && tmin <= st.vthr0;
     if (improve | tie | need_hit) {
         if (need_hit) {
@@ -326,7 +328,8 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
             RowState st;
             st.bestV = 3.0e38f; st.bestp = 0; st.bestcol = FE_NONE32; st.hit = FE_NONE32;
             st.vthr0 = -3.0e38f; st.vthr1 = -3.0e38f;
-            st.par_item = a.colpar + (size_t)item.t0 * (UM_NT / 32);
+            st.par_item = reinterpret_cast<const uint32_t*>(a.colmeta + (size_t)item.t0 * 2);
+            uint32_t cur_seg = FE_NONE32;       // domain bucket of the tiles this thread is scanning
             if (a.use_thr && row_ok) { // n16 <= thr16  <=>  V <= floor((thr16 - a2 - p) / 2)
                 const long long tt = (long long)a.thr16 - (long long)a2;
                 long long f0 = tt >= 0 ? tt / 2 : -((-tt + 1) / 2);
@@ -357,12 +360,21 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
             for (uint32_t j = 0; j < my_tiles; ++j, ++jb) {
                 const uint32_t u = first + j * UM_WGS, buf = jb & 1;
                 const uint32_t colbase = u * UM_NT + h * UM_HALF;
-                const uint32_t tile_valid = min((uint32_t)UM_NT, item.cols_left - u * UM_NT);
-                const uint32_t nvalid = tile_valid > h * UM_HALF ? min((uint32_t)UM_HALF, tile_valid - h * UM_HALF) : 0u;
-                // parity words of this half tile, fetched ahead of the accumulator wait (one 8-byte broadcast load per warp)
+                // metadata of this half tile, fetched ahead of the accumulator wait (one 16-byte broadcast load per warp)
                 static_assert(UM_HALF == 64, "two parity words per half tile");
-                const uint2 pw2 = __ldg(reinterpret_cast<const uint2*>(a.colpar + (size_t)(item.t0 + u) * (UM_NT / 32) + h * (UM_HALF / 32)));
-                const uint32_t par[2] = {pw2.x, pw2.y};
+                const uint4 meta = __ldg(a.colmeta + (size_t)(item.t0 + u) * 2 + h);
+                const uint32_t par[2] = {meta.x, meta.y};
+                const uint32_t nvalid = meta.z;
+                if (meta.w != cur_seg) {
+                    // The item moves into another domain bucket: columns restart at low domain indices there, so the first
+                    // hit found so far is only the first of the bucket behind us -- bank it and start over.
+                    if (st.hit != FE_NONE32) {
+                        atomicMin(&a.rowhit[srow], a.blob_dom[(size_t)item.t0 * UM_NT + st.hit]);
+                        st.hit = FE_NONE32;
+                    }
+                    cur_seg = meta.w;
+                    if (RETIRE) { retired = !row_ok; warp_done = false; }
+                }
                 uint32_t v[UM_HALF];
                 mbar_wait(ACC_FULL(g, buf), (jb >> 1) & 1);
                 tc_fence_after();
@@ -376,7 +388,7 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ACC_EMPTY(g, buf));
                 if (!(a.dbg & 1) && !(RETIRE && warp_done)) {
-                    process_half(v, st, RETIRE ? !retired : row_ok, colbase, nvalid, par);
+                    process_half(v, st, RETIRE ? !retired : row_ok, colbase, nvalid, par, a.no_min == 0);
                     if (RETIRE && (j & 3) == 3) {   // every 4th tile is enough: retirement only saves work
                         uint32_t hm = __ballot_sync(0xFFFFFFFFu, st.hit != FE_NONE32);
                         hm = (hm | (hm >> 1) | (hm >> 2) | (hm >> 3)) & 0x11111111u;   // one bit per quad of lanes
@@ -390,14 +402,11 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                 if (st.bestcol != FE_NONE32) {
                     if (st.bestp == 2) st.bestp = row_parity(st, st.bestcol);
                     const long long n16 = (long long)a2 + 2ll * (long long)st.bestV + (long long)st.bestp;
-                    const unsigned long long key = ((unsigned long long)(uint32_t)n16 << 32) | (unsigned long long)(item.col0 + st.bestcol);
+                    const unsigned long long key = ((unsigned long long)(uint32_t)n16 << 32) | (unsigned long long)a.blob_dom[(size_t)item.t0 * UM_NT + st.bestcol];
                     atomicMin(&a.rowbest[srow], key);
                     if (st.bestV >= 16777216.0f - 64.0f) atomicOr(a.flags, 1u);
                 }
-                if (st.hit != FE_NONE32) {
-                    const uint32_t hc = item.col0 + st.hit;
-                    atomicMin(&a.rowhit[srow], a.dom_order ? a.dom_order[hc] : hc);
-                }
+                if (st.hit != FE_NONE32) atomicMin(&a.rowhit[srow], a.blob_dom[(size_t)item.t0 * UM_NT + st.hit]);
             }
         }
     }
@@ -525,7 +534,7 @@ __global__ void __launch_bounds__(128) k_build_rows16(const uint8_t* __restrict_
 template <int T>
 __global__ void __launch_bounds__(128) k_build_pool16(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ dom,
                                                       const uint32_t* __restrict__ order, UmmaBuckets bk, uint4* __restrict__ B16,
-                                                      uint32_t* __restrict__ colpar) {
+                                                      uint32_t* __restrict__ colmeta, uint32_t* __restrict__ blob_dom) {
     constexpr int N = T * T, KPAD = (N + 3 + 15) & ~15, NCH = KPAD / 8, W = T / 4;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= bk.col_tile0[bk.nb] * (uint32_t)UM_NT) return;          // whole warps: UM_NT is a multiple of 32
@@ -536,8 +545,10 @@ __global__ void __launch_bounds__(128) k_build_pool16(const uint8_t* __restrict_
     uint4* out = B16 + (size_t)tile * NCH * UM_NT + l;
     const bool live = c < bk.dom_end[bi];
     uint32_t s2 = 0;
+    const uint32_t di = live ? (order ? order[c] : c) : FE_NONE32;
+    blob_dom[idx] = di;
     if (live) {
-        const fe_grid_item d = dom[order ? order[c] : c];
+        const fe_grid_item d = dom[di];
         const uint8_t* base = img + (size_t)d.y * stride + d.x;
         float v[8];
 #pragma unroll
@@ -576,8 +587,17 @@ __global__ void __launch_bounds__(128) k_build_pool16(const uint8_t* __restrict_
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) out[ch * UM_NT] = make_uint4(0, 0, 0, 0);
     }
+    // tile metadata, 4 words per half tile: parity of columns 0-31, 32-63, valid columns of the half, domain bucket
     const uint32_t par = __ballot_sync(0xFFFFFFFFu, live && (s2 & 1u));
-    if ((l & 31) == 0) colpar[(size_t)tile * (UM_NT / 32) + (l >> 5)] = par;
+    if ((l & 31) == 0) {
+        uint32_t* m = colmeta + ((size_t)tile * 2 + (l >> 6)) * 4;
+        m[(l >> 5) & 1u] = par;
+        if ((l & 63) == 0) {
+            const uint32_t end = bk.dom_end[bi];
+            m[2] = c >= end ? 0u : min(end - c, (uint32_t)UM_HALF);
+            m[3] = (uint32_t)bi;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -597,27 +617,34 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     UmmaArgs a{};
     uint32_t rt = 0, ct = 0, nb = 0;
     uint64_t total_items = 0;
+    // B blob: the slices of the domain buckets, one after the other (whole column tiles each)
+    uint32_t nct[FE_MAX_BUCKETS];
+    for (int b = 0; b < nbuckets; ++b) {
+        const uint32_t dc = sp.dend[b] - sp.dbeg[b];
+        bk.dom_off[b] = sp.dbeg[b];
+        bk.dom_end[b] = sp.dend[b];
+        bk.col_tile0[b] = ct;
+        nct[b] = (dc + UM_NT - 1) / UM_NT;
+        ct += nct[b];
+    }
+    bk.col_tile0[nbuckets] = ct;
+    // A blob: the range buckets; bucket c meets the column tiles of the domain buckets c-span .. c+span (adjacent in the blob)
     for (int c = 0; c < nbuckets; ++c) {
-        const uint32_t rc = sp.roff[c + 1] - sp.roff[c], dc = rc ? sp.dend[c] - sp.dbeg[c] : 0u;
-        // buckets keep their slot in the operand layout even when they have no partner (their rows stay at INF)
+        const uint32_t rc = sp.roff[c + 1] - sp.roff[c];
         bk.range_off[nb] = sp.roff[c];
-        bk.dom_off[nb] = sp.dbeg[c];
-        bk.dom_end[nb] = sp.dbeg[c] + dc;
         bk.row_tile0[nb] = rt;
-        bk.col_tile0[nb] = ct;
         UmmaBucket& b = a.b[nb];
         b.row_tile0 = rt; b.n_row_tiles = (rc + 31) / 32;
-        b.col_tile0 = ct; b.n_col_tiles = (dc + UM_NT - 1) / UM_NT;
+        const int b0 = std::max(0, c - sp.span), b1 = std::min(nbuckets - 1, c + sp.span);
+        b.col_tile0 = bk.col_tile0[b0];
+        b.n_col_tiles = bk.col_tile0[b1 + 1] - bk.col_tile0[b0];
         b.row0 = sp.roff[c] * 4; b.nrows = rc * 4;
-        b.col0 = sp.dbeg[c]; b.ncols = dc;
         rt += b.n_row_tiles;
-        ct += b.n_col_tiles;
         ++nb;
     }
     bk.nb = (int)nb;
     bk.range_off[nb] = sp.roff[nbuckets];
     bk.row_tile0[nb] = rt;
-    bk.col_tile0[nb] = ct;
     bk.n_ranges = sp.roff[nbuckets];
     bk.n_domains = sp.n_dom;
     // column chunking: aim at >= 2 work items per SM when there are few row tiles
@@ -640,7 +667,8 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     const size_t bytesA = (size_t)rt * UM_ROWS * Kpad * 2, bytesB = (size_t)ct * UM_NT * Kpad * 2;
     FE_CUDA(ctx, ctx->b_A16.ensure(bytesA + 256));
     FE_CUDA(ctx, ctx->b_B16.ensure(bytesB + 256));
-    FE_CUDA(ctx, ctx->b_tmaps.ensure((size_t)ct * (UM_NT / 32) * 4 + 64));
+    FE_CUDA(ctx, ctx->b_tmaps.ensure((size_t)ct * 32 + 64));
+    FE_CUDA(ctx, ctx->b_blob_dom.ensure((size_t)ct * UM_NT * 4 + 64));
     FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)bk.n_ranges * 4 + 4));
     uint32_t* flags = ctx->b_counters.as<uint32_t>() + 2;
     {
@@ -648,13 +676,14 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
         uint4* A16 = ctx->b_A16.as<uint4>();
         uint4* B16 = ctx->b_B16.as<uint4>();
         uint32_t* rowA2 = ctx->b_rowc.as<uint32_t>();
-        uint32_t* colpar = ctx->b_tmaps.as<uint32_t>();
+        uint32_t* colmeta = ctx->b_tmaps.as<uint32_t>();
+        uint32_t* blob_dom = ctx->b_blob_dom.as<uint32_t>();
         if (g.T == 4) {
             if (!sp.reuse_rows) k_build_rows16<4><<<gr, 128, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, A16, rowA2);
-            k_build_pool16<4><<<gc, 128, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, B16, colpar);
+            k_build_pool16<4><<<gc, 128, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, B16, colmeta, blob_dom);
         } else {
             if (!sp.reuse_rows) k_build_rows16<8><<<gr, 128, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, A16, rowA2);
-            k_build_pool16<8><<<gc, 128, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, B16, colpar);
+            k_build_pool16<8><<<gc, 128, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, B16, colmeta, blob_dom);
         }
         FE_CUDA(ctx, cudaGetLastError());
     }
@@ -662,7 +691,8 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
 
     a.A16 = ctx->b_A16.p;
     a.B16 = ctx->b_B16.p;
-    a.colpar = ctx->b_tmaps.as<uint32_t>();
+    a.colmeta = ctx->b_tmaps.as<uint4>();
+    a.blob_dom = ctx->b_blob_dom.as<uint32_t>();
     a.rowA2 = ctx->b_rowc.as<uint32_t>();
     a.rowbest = ctx->b_rowbest.as<unsigned long long>();
     a.rowhit = ctx->b_rowhit.as<uint32_t>();
@@ -674,7 +704,7 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     a.use_thr = use_thr ? 1u : 0u;
     a.nt = UM_NT;
     a.rowslot = sp.rowslot;
-    a.dom_order = sp.dom_order;
+    a.no_min = sp.no_min ? 1u : 0u;
     { const char* e = getenv("FE_UMMA_DBG"); a.dbg = e ? (uint32_t)atoi(e) : 0u; }
     const uint32_t stage_bytes = UM_NT * Kpad * 2, a_bytes = 2 * UM_ROWS * Kpad * 2;
     const uint32_t stages = 2 * UM_ISSUERS_F16;

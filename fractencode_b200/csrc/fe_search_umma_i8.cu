@@ -167,12 +167,23 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_umma_i8(const UmmaA
             const int wthr = (a.use_thr && row_ok) ? (int)wt : (int)0x80000000;
             int bestw = 0x7FFFFFFF;
             uint32_t bestcol = FE_NONE32, hit = FE_NONE32;
+            uint32_t cur_seg = FE_NONE32;       // domain bucket of the tiles this thread is scanning
             const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
             const uint32_t my_tiles = first < n ? (n - first + UM_WGS - 1) / UM_WGS : 0;
             for (uint32_t j = 0; j < my_tiles; ++j, ++jb) {
                 const uint32_t u = first + j * UM_WGS, buf = jb & 1;
                 const uint32_t colbase = u * I8_NT + h * 32;             // column inside the item
                 const uint32_t taddr = lane_addr + (g * 2 + buf) * 2 * I8_NT;
+                const uint32_t seg = __ldg(a.tileseg + item.t0 + u);
+                if (seg != cur_seg) {
+                    // another domain bucket: its columns restart at low domain indices, so bank the first hit of the bucket
+                    // behind us and look for this bucket's
+                    if (hit != FE_NONE32) {
+                        atomicMin(&a.rowhit[srow], a.blob_dom[(size_t)item.t0 * I8_NT + hit]);
+                        hit = FE_NONE32;
+                    }
+                    cur_seg = seg;
+                }
                 uint32_t lo[32], hi[32];
                 mbar_wait(ACC_FULL(g, buf), (jb >> 1) & 1);
                 tc_fence_after();
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_umma_i8(const UmmaA
                     m1 = min(min(m1, (int)lo[i + 2]), (int)lo[i + 3]);
                 }
                 const int tmin = min(m0, m1);
-                const bool improve = row_ok && tmin < bestw;
+                const bool improve = row_ok && !a.no_min && tmin < bestw;
                 const bool need_hit = row_ok && hit == FE_NONE32 && tmin <= wthr;
                 if (improve | need_hit) {
                     uint32_t c_best = FE_NONE32, c_hit = FE_NONE32;
@@ -220,13 +231,10 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_umma_i8(const UmmaA
             if (row_ok) {
                 if (bestcol != FE_NONE32) {
                     const uint32_t n16 = rc + (uint32_t)bestw;
-                    const unsigned long long key = ((unsigned long long)n16 << 32) | (unsigned long long)(item.col0 + bestcol);
+                    const unsigned long long key = ((unsigned long long)n16 << 32) | (unsigned long long)a.blob_dom[(size_t)item.t0 * I8_NT + bestcol];
                     atomicMin(&a.rowbest[srow], key);
                 }
-                if (hit != FE_NONE32) {
-                    const uint32_t hc = item.col0 + hit;
-                    atomicMin(&a.rowhit[srow], a.dom_order ? a.dom_order[hc] : hc);
-                }
+                if (hit != FE_NONE32) atomicMin(&a.rowhit[srow], a.blob_dom[(size_t)item.t0 * I8_NT + hit]);
             }
         }
     }
@@ -280,7 +288,8 @@ __global__ void k_build_rows_i8(const uint8_t* __restrict__ img, uint32_t stride
 // low-plane and the high-plane 16 bytes.  coln (by padded position): sum D^2, INT_MAX for padding columns.
 __global__ void k_build_pool_i8(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ dom,
                                 const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad, uint32_t kc,
-                                const uint32_t* __restrict__ colS2, uint4* __restrict__ B8, uint32_t* __restrict__ coln_tiles) {
+                                const uint32_t* __restrict__ colS2, uint4* __restrict__ B8, uint32_t* __restrict__ coln_tiles,
+                                uint32_t* __restrict__ blob_dom, uint32_t* __restrict__ tileseg) {
     const uint32_t nst = Kpad / kc, ncs = kc / 16;
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint64_t)bk.col_tile0[bk.nb] * nst * ncs * I8_NT) return;
@@ -292,8 +301,13 @@ __global__ void k_build_pool_i8(const uint8_t* __restrict__ img, uint32_t stride
     const uint32_t N = T * T;
     uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
     const bool valid = c < bk.dom_end[bi];
+    const uint32_t di = valid ? (order ? order[c] : c) : FE_NONE32;
+    if (st == 0 && cs == 0) {
+        blob_dom[(size_t)tile * I8_NT + l] = di;
+        if (l == 0) tileseg[tile] = (uint32_t)bi;
+    }
     if (valid) {
-        const fe_grid_item d = dom[order ? order[c] : c];
+        const fe_grid_item d = dom[di];
         const uint8_t* base = img + (size_t)d.y * stride + d.x;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
@@ -329,26 +343,32 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     UmmaArgs a{};
     uint32_t rt = 0, ct = 0, nb = 0;
     uint64_t total_items = 0;
+    // B blob: the slices of the domain buckets, one after the other (whole column tiles each)
+    for (int b = 0; b < nbuckets; ++b) {
+        const uint32_t dc = sp.dend[b] - sp.dbeg[b];
+        bk.dom_off[b] = sp.dbeg[b];
+        bk.dom_end[b] = sp.dend[b];
+        bk.col_tile0[b] = ct;
+        ct += (dc + I8_NT - 1) / I8_NT;
+    }
+    bk.col_tile0[nbuckets] = ct;
+    // A blob: the range buckets; bucket c meets the column tiles of the domain buckets c-span .. c+span (adjacent in the blob)
     for (int c = 0; c < nbuckets; ++c) {
-        const uint32_t rc = sp.roff[c + 1] - sp.roff[c], dc = rc ? sp.dend[c] - sp.dbeg[c] : 0u;
+        const uint32_t rc = sp.roff[c + 1] - sp.roff[c];
         bk.range_off[nb] = sp.roff[c];
-        bk.dom_off[nb] = sp.dbeg[c];
-        bk.dom_end[nb] = sp.dbeg[c] + dc;
         bk.row_tile0[nb] = rt;
-        bk.col_tile0[nb] = ct;
         UmmaBucket& b = a.b[nb];
         b.row_tile0 = rt; b.n_row_tiles = (rc + 31) / 32;
-        b.col_tile0 = ct; b.n_col_tiles = (dc + I8_NT - 1) / I8_NT;
+        const int b0 = std::max(0, c - sp.span), b1 = std::min(nbuckets - 1, c + sp.span);
+        b.col_tile0 = bk.col_tile0[b0];
+        b.n_col_tiles = bk.col_tile0[b1 + 1] - bk.col_tile0[b0];
         b.row0 = sp.roff[c] * 4; b.nrows = rc * 4;
-        b.col0 = sp.dbeg[c]; b.ncols = dc;
         rt += b.n_row_tiles;
-        ct += b.n_col_tiles;
         ++nb;
     }
     bk.nb = (int)nb;
     bk.range_off[nb] = sp.roff[nbuckets];
     bk.row_tile0[nb] = rt;
-    bk.col_tile0[nb] = ct;
     bk.n_ranges = sp.roff[nbuckets];
     bk.n_domains = sp.n_dom;
     uint32_t live_row_tiles = 0;
@@ -370,6 +390,8 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     FE_CUDA(ctx, ctx->b_A16.ensure(bytesA + 256));
     FE_CUDA(ctx, ctx->b_B16.ensure(bytesB + 256));
     FE_CUDA(ctx, ctx->b_coln.ensure((size_t)ct * I8_NT * 4 + 64));
+    FE_CUDA(ctx, ctx->b_blob_dom.ensure((size_t)ct * I8_NT * 4 + 64));
+    FE_CUDA(ctx, ctx->b_tileseg.ensure((size_t)ct * 4 + 64));
     FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)bk.n_ranges * 4 + 4));
     FE_CUDA(ctx, ctx->b_tmaps.ensure((size_t)bk.n_domains * 4 + 64));
     if (!sp.reuse_rows) {
@@ -386,13 +408,16 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     }
     FE_CUDA(ctx, cudaGetLastError());
     k_build_pool_i8<<<(unsigned)((bytesB / 32 + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, g.T, Kpad, kc, ctx->b_tmaps.as<uint32_t>(), ctx->b_B16.as<uint4>(), ctx->b_coln.as<uint32_t>());
+        ctx->src.px, ctx->src.stride, d_dom, dom_order, bk, g.T, Kpad, kc, ctx->b_tmaps.as<uint32_t>(), ctx->b_B16.as<uint4>(), ctx->b_coln.as<uint32_t>(),
+        ctx->b_blob_dom.as<uint32_t>(), ctx->b_tileseg.as<uint32_t>());
     FE_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches++;
 
     a.A16 = ctx->b_A16.p;
     a.B16 = ctx->b_B16.p;
-    a.colpar = nullptr;
+    a.colmeta = nullptr;
+    a.tileseg = ctx->b_tileseg.as<uint32_t>();
+    a.blob_dom = ctx->b_blob_dom.as<uint32_t>();
     a.coln = ctx->b_coln.as<uint32_t>();
     a.rowA2 = ctx->b_rowc.as<uint32_t>();
     a.rowbest = ctx->b_rowbest.as<unsigned long long>();
@@ -405,7 +430,7 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     a.use_thr = use_thr ? 1u : 0u;
     a.nt = I8_NT;
     a.rowslot = sp.rowslot;
-    a.dom_order = sp.dom_order;
+    a.no_min = sp.no_min ? 1u : 0u;
     const uint32_t stage_bytes = 2 * I8_NT * kc, a_bytes = UM_ROWS * Kpad;
     const uint32_t budget = 226 * 1024 - 512;
     a.n_abuf = (2 * a_bytes + 2 * stage_bytes <= budget) ? 2 : 1;

@@ -27,14 +27,16 @@ struct UmmaBucket {
     uint32_t row_tile0, n_row_tiles; // A blobs of this classifier bucket
     uint32_t col_tile0, n_col_tiles; // B blobs
     uint32_t row0, nrows;            // first global row (= 4 * first range position), valid rows
-    uint32_t col0, ncols;            // first global sorted column, valid columns
     uint32_t chunks;                 // column chunks per row tile (work items = n_row_tiles * chunks)
 };
 
 struct UmmaArgs {
     const void* A16;
     const void* B16;
-    const uint32_t* colpar;          // [col tiles][UM_NT/32] parity of sum(b^2) per column
+    const uint4* colmeta;            // f16 kind: [col tile][2 halves] {parity of sum(b^2) of columns 0-31, 32-63, valid columns of
+                                     // the half, domain bucket of the tile}
+    const uint32_t* tileseg;         // i8 kind: [col tile] domain bucket of the tile
+    const uint32_t* blob_dom;        // [col tile][nt] domain index of every blob column (FE_NONE32: padding)
     const uint32_t* rowA2;           // [range position] sum(a^2)
     unsigned long long* rowbest;
     uint32_t* rowhit;
@@ -47,8 +49,8 @@ struct UmmaArgs {
     uint32_t n_abuf;                 // i8 kind: A buffers in shared memory (2, or 1 when the tile is 128 KB)
     uint32_t dbg;                    // tuning probes (FE_UMMA_DBG): 1 skip TMEM drain, 2 skip MMA issue, 4 skip B copies
     const uint32_t* rowslot;         // [range position of this pass] -> range position of the level (result slot); NULL = identity
-    const uint32_t* dom_order;       // sorted column -> domain index (NULL = identity): rowhit holds DOMAIN indices, so hits found
-                                     // in different buckets / slices of the same row compare in scan order
+    uint32_t no_min;                 // only threshold hits are wanted (levels that split: a range without a hit is split and its
+                                     // minimum never read) -- skip the running-minimum bookkeeping
 };
 
 struct UmmaBuckets {                 // operand-layout view for the blob builders
@@ -66,10 +68,12 @@ struct SearchPass {
     const uint32_t* dom_order;       // domain position -> domain item index (NULL = identity)
     const uint32_t* rng_items;       // range position of this pass -> range item index (NULL = identity)
     const uint32_t* rowslot;         // range position of this pass -> range position of the level (NULL = identity)
-    uint32_t dbeg[FE_MAX_BUCKETS], dend[FE_MAX_BUCKETS]; // per bucket: domain positions searched in this pass
+    uint32_t dbeg[FE_MAX_BUCKETS], dend[FE_MAX_BUCKETS]; // per DOMAIN bucket: domain positions searched in this pass
+    int span;                        // range bucket c meets the domain buckets c-span .. c+span (0: its own; 1: brightness bins)
     uint32_t roff[FE_MAX_BUCKETS + 1];                   // per bucket: range positions of this pass (prefix offsets)
     int nbuckets;
     uint32_t n_dom;                  // all domain positions of the level
+    bool no_min;                     // only threshold hits are wanted
     bool reuse_rows;                 // the A blob and row norms built by the previous pass are still valid
     bool reuse_dom_norms;            // i8 kind: the per-position domain norms of the level are already built
     cudaEvent_t ev0, ev1;            // recorded around the search launch (NULL: not timed)

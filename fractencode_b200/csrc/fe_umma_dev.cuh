@@ -112,9 +112,7 @@ struct WorkItem {
     uint32_t a_blob;   // row-tile index (A blob)
     uint32_t row0;     // first global row of the tile
     uint32_t nrows;    // valid rows in the tile (<= 128)
-    uint32_t t0, t1;   // column-tile range [t0, t1)
-    uint32_t col0;     // global (sorted) column index of tile t0's first column
-    uint32_t cols_left;// valid columns from tile t0 to the end of the bucket
+    uint32_t t0, t1;   // column-tile range [t0, t1) of the B blob (may run over several adjacent domain buckets)
 };
 
 __device__ __forceinline__ WorkItem decode_item(const UmmaArgs& a, uint32_t w) {
@@ -131,8 +129,6 @@ __device__ __forceinline__ WorkItem decode_item(const UmmaArgs& a, uint32_t w) {
             const uint32_t lt1 = (uint32_t)(((uint64_t)(q + 1) * b.n_col_tiles) / b.chunks);
             it.t0 = b.col_tile0 + lt0;
             it.t1 = b.col_tile0 + lt1;
-            it.col0 = b.col0 + lt0 * a.nt;
-            it.cols_left = b.ncols - lt0 * a.nt;
             return it;
         }
         w -= items;
