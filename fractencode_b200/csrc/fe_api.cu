@@ -515,12 +515,13 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
         if (res->inexact) break;
         if (S == 0) { open_left = false; break; }                         // every range has its first hit
         const double resolved = 1.0 - (double)S / (double)before;
-        // Bins only pay when most ranges end on a hit: a range without one still needs the plain pass over every domain for
-        // its minimum.  Hits come early in the scan where they come at all -- a slice that closes few ranges says go plain now.
-        if (tb.bins && need_min && resolved < 0.25) break;
-        const int step = resolved >= 0.03 ? 1 : 2;
+        // Bins only pay when ranges end on a hit: a range without one still needs the plain pass over every domain for its
+        // minimum, and the bins (about a third of the scan) come on top.  Hits come early in the scan where they come at
+        // all -- first slices that close next to nothing say "no hits on this level": go plain now.
+        if (tb.bins && need_min && res->passes <= 2 && resolved < 0.05) break;
+        const int step = resolved >= 0.03 ? 1 : (resolved >= 0.002 ? 2 : 3);   // slices that close nothing: grow faster
         kF += step;
-        F *= step == 1 ? 2.0 : 4.0;
+        F *= (double)(1 << step);
         if (kF > 7) { kF = 7; F = 1.0; }
     }
 
@@ -561,28 +562,43 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
     return FE_OK;
 }
 
-// Stable bucketing of a uniform block list by brightness bin (see search_tc); order[pos] = item index.
-static int bucket_by_brightness(fe_ctx* ctx, const Plane& pl, const fe_grid_item* d_items, uint32_t n, uint32_t edge, uint32_t mul, uint32_t width,
-                                int nbins, DevBuf& order, uint32_t off[FE_MAX_BUCKETS + 1]) {
-    FE_CUDA(ctx, order.ensure((size_t)n * sizeof(uint32_t)));
-    FE_CUDA(ctx, ctx->b_keys_tmp.ensure((size_t)n * 2 + 64));
-    FE_CUDA(ctx, ctx->b_vals_tmp.ensure((size_t)n * sizeof(uint32_t)));
-    FE_CUDA(ctx, ctx->b_hist.ensure(64 * sizeof(uint32_t)));
-    uint8_t* keys_in = ctx->b_keys_tmp.as<uint8_t>();
-    uint8_t* keys_out = keys_in + n;
-    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_hist.p, 0, FE_MAX_BUCKETS * sizeof(uint32_t), ctx->stream));
-    LAUNCH(ctx, k_brightness_bins, cdiv((uint64_t)n * 32, 256), 256, pl.px, pl.stride, d_items, n, edge, mul, width, keys_in, ctx->b_hist.as<uint32_t>());
-    LAUNCH(ctx, k_iota, cdiv(n, 256), 256, ctx->b_vals_tmp.as<uint32_t>(), n);
-    size_t tmp_bytes = 0;
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, ctx->b_vals_tmp.as<uint32_t>(), order.as<uint32_t>(), (int)n, 0, 5, ctx->stream));
-    FE_CUDA(ctx, ctx->b_sort_tmp.ensure(tmp_bytes));
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_bytes, keys_in, keys_out, ctx->b_vals_tmp.as<uint32_t>(), order.as<uint32_t>(), (int)n, 0, 5, ctx->stream));
-    ctx->stats.kernel_launches += 3;
-    uint32_t hist[FE_MAX_BUCKETS];
-    FE_CUDA(ctx, cudaMemcpyAsync(hist, ctx->b_hist.p, sizeof(hist), cudaMemcpyDeviceToHost, ctx->stream));
+// Stable bucketing of the level's two uniform block lists by brightness bin (see search_tc); order[pos] = item index.
+// Keys and histograms of both lists first, ONE host round trip for the two histograms, then the two sorts.
+static int bucket_by_brightness(fe_ctx* ctx, const LevelIO& io, uint32_t width, int nbins, uint32_t doff[FE_MAX_BUCKETS + 1],
+                                uint32_t roff[FE_MAX_BUCKETS + 1], const uint32_t cut[8], uint32_t pre[FE_MAX_BUCKETS][8]) {
+    const uint32_t nD = io.nD, nR = io.nR;
+    const size_t n = (size_t)nD + nR;
+    FE_CUDA(ctx, ctx->b_dom_order.ensure((size_t)nD * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_rng_order.ensure((size_t)nR * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_keys_tmp.ensure(n * 2 + 64));
+    FE_CUDA(ctx, ctx->b_vals_tmp.ensure((size_t)std::max(nD, nR) * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_hist.ensure((64 + FE_MAX_BUCKETS * 8) * sizeof(uint32_t)));
+    uint8_t* dkeys = ctx->b_keys_tmp.as<uint8_t>();
+    uint8_t* rkeys = dkeys + nD;
+    uint8_t* keys_out = dkeys + n;
+    uint32_t* hist = ctx->b_hist.as<uint32_t>();
+    FE_CUDA(ctx, cudaMemsetAsync(hist, 0, 64 * sizeof(uint32_t), ctx->stream));
+    LAUNCH(ctx, k_brightness_bins, cdiv((uint64_t)nD * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, nD, io.g.S, 1u, width, dkeys, hist);
+    LAUNCH(ctx, k_brightness_bins, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, io.g.T, 4u, width, rkeys, hist + 32);
+    LAUNCH(ctx, k_iota, cdiv(std::max(nD, nR), 256), 256, ctx->b_vals_tmp.as<uint32_t>(), std::max(nD, nR));
+    size_t tmp_d = 0, tmp_r = 0;
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_d, dkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order.as<uint32_t>(), (int)nD, 0, 5, ctx->stream));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_r, rkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order.as<uint32_t>(), (int)nR, 0, 5, ctx->stream));
+    FE_CUDA(ctx, ctx->b_sort_tmp.ensure(std::max(tmp_d, tmp_r)));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_d, dkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order.as<uint32_t>(), (int)nD, 0, 5, ctx->stream));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_r, rkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order.as<uint32_t>(), (int)nR, 0, 5, ctx->stream));
+    ctx->stats.kernel_launches += 6;
+    // prefix lengths of every domain bucket at the slice cutoffs (device-side offsets: no host round trip in between)
+    BucketOff c8{};
+    for (int k = 0; k < 8; ++k) c8.v[k] = cut[k];
+    LAUNCH(ctx, k_bin_prefix, cdiv((uint64_t)nbins * 8, 128), 128, ctx->b_dom_order.as<uint32_t>(), hist, nbins, c8, hist + 64);
+    uint32_t h[64 + FE_MAX_BUCKETS * 8];
+    FE_CUDA(ctx, cudaMemcpyAsync(h, hist, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    off[0] = 0;
-    for (int c = 0; c < nbins; ++c) off[c + 1] = off[c] + hist[c];
+    doff[0] = roff[0] = 0;
+    for (int c = 0; c < nbins; ++c) { doff[c + 1] = doff[c] + h[c]; roff[c + 1] = roff[c] + h[32 + c]; }
+    for (int b = 0; b < nbins; ++b)
+        for (int k = 0; k < 8; ++k) pre[b][k] = h[64 + b * 8 + k];
     return FE_OK;
 }
 
@@ -646,24 +662,12 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
             const uint64_t width = std::max<uint64_t>(R + 1, (maxsum + FE_MAX_BUCKETS) / FE_MAX_BUCKETS);
             const int nbins = (int)(maxsum / width) + 1;
             if (nbins >= 4 && nbins <= FE_MAX_BUCKETS) {
-                FE_TRY(bucket_by_brightness(ctx, ctx->src, io.d_dom, nD, g.S, 1, (uint32_t)width, nbins, ctx->b_dom_order, tb.doff));
-                FE_TRY(bucket_by_brightness(ctx, ctx->tgt, io.d_rng, nR, g.T, 4, (uint32_t)width, nbins, ctx->b_rng_order, tb.roff));
+                for (int k = 0; k < 8; ++k) tb.cut[k] = k == 7 ? nD : (uint32_t)(((uint64_t)nD << k) / 128 + 1);
+                FE_TRY(bucket_by_brightness(ctx, io, (uint32_t)width, nbins, tb.doff, tb.roff, tb.cut, tb.pre));
                 tb.nb = nbins;
                 tb.dom_order = ctx->b_dom_order.as<uint32_t>();
                 tb.rng_order = ctx->b_rng_order.as<uint32_t>();
                 tb.bins = bins = true;
-                for (int k = 0; k < 8; ++k) tb.cut[k] = k == 7 ? nD : (uint32_t)(((uint64_t)nD << k) / 128 + 1);
-                FE_CUDA(ctx, ctx->b_scan_tmp.ensure((8 + FE_MAX_BUCKETS * 8) * sizeof(uint32_t)));
-                uint32_t* d_cut = ctx->b_scan_tmp.as<uint32_t>();
-                FE_CUDA(ctx, cudaMemcpyAsync(d_cut, tb.cut, sizeof(tb.cut), cudaMemcpyHostToDevice, ctx->stream));
-                BucketOff o;
-                for (int c = 0; c <= FE_MAX_BUCKETS; ++c) o.v[c] = tb.doff[std::min(c, nbins)];
-                LAUNCH(ctx, k_bin_prefix, cdiv((uint64_t)nbins * 8, 128), 128, tb.dom_order, o, nbins, d_cut, 8, d_cut + 8);
-                uint32_t pre[FE_MAX_BUCKETS * 8];
-                FE_CUDA(ctx, cudaMemcpyAsync(pre, d_cut + 8, (size_t)nbins * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-                FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                for (int b = 0; b < nbins; ++b)
-                    for (int k = 0; k < 8; ++k) tb.pre[b][k] = pre[b * 8 + k];
                 dom_order = nullptr;                 // results come back as domain indices
                 rng_order = tb.rng_order;            // row slots follow the binned range order
             }

@@ -205,20 +205,23 @@ __global__ void k_brightness_bins(const uint8_t* __restrict__ img, uint32_t stri
     if (threadIdx.x < FE_MAX_BUCKETS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
-// out[b * ncut + k] = number of positions of bucket b whose domain index is below cutoffs[k] (positions of a bucket are in
-// ascending domain index, so these are prefix lengths).  One thread per (b, k).
-__global__ void k_bin_prefix(const uint32_t* __restrict__ dom_order, BucketOff doff, int nb, const uint32_t* __restrict__ cutoffs, int ncut,
+// out[b * 8 + k] = number of positions of domain bucket b whose domain index is below cut.v[k] (positions of a bucket are
+// in ascending domain index, so these are prefix lengths).  hist = bucket sizes; one thread per (b, k).
+__global__ void k_bin_prefix(const uint32_t* __restrict__ dom_order, const uint32_t* __restrict__ hist, int nb, BucketOff cut,
                              uint32_t* __restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nb * ncut) return;
-    const int b = t / ncut, k = t % ncut;
-    const uint32_t c = cutoffs[k];
-    uint32_t lo = doff.v[b], hi = doff.v[b + 1];
+    if (t >= nb * 8) return;
+    const int b = t / 8, k = t % 8;
+    uint32_t lo = 0;
+    for (int i = 0; i < b; ++i) lo += hist[i];
+    const uint32_t beg = lo;
+    uint32_t hi = lo + hist[b];
+    const uint32_t c = cut.v[k];
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
         if (dom_order[mid] < c) lo = mid + 1; else hi = mid;
     }
-    out[t] = lo - doff.v[b];
+    out[t] = lo - beg;
 }
 
 __global__ void k_gather_u32(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ table, uint32_t n, uint32_t* __restrict__ out) {
