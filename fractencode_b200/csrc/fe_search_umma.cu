@@ -230,23 +230,33 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
             load_item(ld);
             mm = ld;
             // ---- A tiles (issuer 0 only): A(wi) lives in buffer wi & 1 ----
-            auto load_A = [&](uint32_t wi_load) {
-                const uint32_t wl = blockIdx.x + wi_load * gridDim.x;
-                if (wl >= a.total_items) return;
+            // The refill of a buffer has to wait until all four issuers' MMAs of the item two back are complete; issuer 0
+            // must not sit in that wait (its accumulator would idle once per item -- with short items, e.g. a slice of
+            // three brightness bins, that is most of the time), so the refill is posted and polled from the tile loop.
+            uint32_t pend_A = FE_NONE32;
+            auto load_A = [&](bool block) {
+                if (pend_A == FE_NONE32) return;
+                const uint32_t wl = blockIdx.x + pend_A * gridDim.x;
+                if (wl >= a.total_items) { pend_A = FE_NONE32; return; }
+                const uint32_t ab = pend_A & 1;
+                if (pend_A >= 2) {                                              // all four issuers are done with A(pend_A - 2)
+                    const uint32_t par = ((pend_A >> 1) & 1) ^ 1;
+                    if (block) mbar_wait(A_EMPTY(ab), par);
+                    else if (!mbar_try_wait(A_EMPTY(ab), par)) return;
+                }
                 const WorkItem it = decode_item(a, wl);
-                const uint32_t ab = wi_load & 1;
-                if (wi_load >= 2) mbar_wait(A_EMPTY(ab), ((wi_load >> 1) & 1) ^ 1);   // all four issuers are done with A(wi_load - 2)
                 mbar_expect_tx(A_FULL(ab), bytesA);
                 bulk_g2s(smem_u32(sA + ab * bytesA), reinterpret_cast<const uint8_t*>(a.A16) + (size_t)it.a_blob * bytesA, bytesA, A_FULL(ab));
+                pend_A = FE_NONE32;
             };
-            if (warp == 0) { load_A(0); load_A(1); }
+            if (warp == 0) { pend_A = 0; load_A(true); pend_A = 1; load_A(true); }
             // ---- cursor movement; the MMA cursor signs off every item it leaves (A_EMPTY needs all four issuers) ----
             bool mm_had_tiles = false;
             auto next_item = [&](Cursor& c, bool is_mm) {
                 if (is_mm) {
                     if (mm_had_tiles) tc_commit(A_EMPTY(c.wi & 1)); else mbar_arrive(A_EMPTY(c.wi & 1));
                     mm_had_tiles = false;
-                    if (warp == 0) load_A(c.wi + 2);
+                    if (warp == 0) { load_A(true); pend_A = c.wi + 2; }         // (an older refill still posted: finish it first)
                 }
                 c.it0 += c.n; c.w += gridDim.x; ++c.wi;
                 load_item(c);
@@ -282,8 +292,10 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
             while (mm.valid) {
                 // refill: tile m+1 goes into the stage of tile m-1, whose MMAs were issued one iteration ago
                 if (m >= 1 && ld.valid) load_B();
+                if (warp == 0) load_A(false);
                 if (mm.wi != cur_wi) {       // first tile of this issuer in a new item: its A tile must have landed
                     cur_wi = mm.wi;
+                    if (warp == 0 && pend_A == cur_wi) load_A(true);
                     mbar_wait(A_FULL(cur_wi & 1), (cur_wi >> 1) & 1);
                     a_addr = smem_u32(sA + (cur_wi & 1) * bytesA);
                 }
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                 st.vthr0 = (float)f0;
                 st.vthr1 = (float)f1;
             }
-            if (row_ok) {
+            if (row_ok && !a.no_min) {
                 // Seed the running minimum with what earlier passes / column chunks already found for this row, plus one:
                 // anything this item finds at or below the recorded score still gets written (ties are settled by the
                 // column index inside the 64-bit key), everything above it is rejected by the cheap tile-minimum test.
