@@ -221,9 +221,14 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                 WorkItem item;
                 bool valid;
             };
+            uint32_t memo_w = FE_NONE32;     // the two cursors visit the same items a tile or two apart: decode each once
+            WorkItem memo{};
             auto load_item = [&](Cursor& c) {
                 c.valid = c.w < a.total_items;
-                if (c.valid) { c.item = decode_item(a, c.w); c.n = c.item.t1 - c.item.t0; }
+                if (c.valid) {
+                    if (c.w != memo_w) { memo = decode_item(a, c.w); memo_w = c.w; }
+                    c.item = memo; c.n = c.item.t1 - c.item.t0;
+                }
             };
             Cursor ld, mm;
             ld.w = mm.w = blockIdx.x; ld.wi = mm.wi = 0; ld.it0 = mm.it0 = 0;
@@ -335,8 +340,8 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
             const uint32_t n = item.t1 - item.t0;
             const bool row_ok = lrow < item.nrows;
             const uint32_t grow = item.row0 + lrow;
-            const uint32_t a2 = row_ok ? a.rowA2[grow >> 2] : 0u;
-            const uint32_t srow = (row_ok && a.rowslot) ? 4u * a.rowslot[grow >> 2] + (grow & 3u) : grow;   // result slot of the level
+            const uint32_t a2 = (row_ok && !(a.dbg & 8)) ? a.rowA2[grow >> 2] : 0u;
+            const uint32_t srow = (row_ok && a.rowslot && !(a.dbg & 8)) ? 4u * a.rowslot[grow >> 2] + (grow & 3u) : grow;   // result slot of the level
             RowState st;
             st.bestV = 3.0e38f; st.bestp = 0; st.bestcol = FE_NONE32; st.hit = FE_NONE32;
             st.vthr0 = -3.0e38f; st.vthr1 = -3.0e38f;
@@ -410,7 +415,7 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                 }
             }
             it0 += n;
-            if (row_ok) {
+            if (row_ok && !(a.dbg & 16)) {
                 if (st.bestcol != FE_NONE32) {
                     if (st.bestp == 2) st.bestp = row_parity(st, st.bestcol);
                     const long long n16 = (long long)a2 + 2ll * (long long)st.bestV + (long long)st.bestp;
@@ -669,6 +674,7 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
         b.chunks = b.n_col_tiles ? std::max(1u, std::min(want_chunks, b.n_col_tiles)) : 0;
         if (!b.n_row_tiles) b.chunks = 0;
         total_items += (uint64_t)b.n_row_tiles * b.chunks;
+        a.item_end[i] = (uint32_t)std::min<uint64_t>(total_items, 0xFFFFFFFFull);
     }
     if (total_items == 0) {
         if (sp.ev0) { cudaEventRecord(sp.ev0, ctx->stream); cudaEventRecord(sp.ev1, ctx->stream); }

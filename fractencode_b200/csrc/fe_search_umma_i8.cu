@@ -379,6 +379,7 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
         UmmaBucket& b = a.b[i];
         b.chunks = (b.n_col_tiles && b.n_row_tiles) ? std::max(1u, std::min(want_chunks, b.n_col_tiles)) : 0;
         total_items += (uint64_t)b.n_row_tiles * b.chunks;
+        a.item_end[i] = (uint32_t)std::min<uint64_t>(total_items, 0xFFFFFFFFull);
     }
     if (total_items == 0) {
         if (sp.ev0) { cudaEventRecord(sp.ev0, ctx->stream); cudaEventRecord(sp.ev1, ctx->stream); }

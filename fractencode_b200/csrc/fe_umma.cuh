@@ -42,6 +42,7 @@ struct UmmaArgs {
     uint32_t* rowhit;
     uint32_t* flags;                 // bit 0: a winner sits in the fp32-inexact band
     UmmaBucket b[FE_MAX_BUCKETS];
+    uint32_t item_end[FE_MAX_BUCKETS]; // work items of the buckets 0..i (running total)
     int nb;
     uint32_t Kpad, stages, total_items, thr16, use_thr;
     uint32_t nt;                     // domain columns per tile (UM_NT for the f16 kind, I8_NT for the i8 kind)

@@ -117,22 +117,22 @@ struct WorkItem {
 
 __device__ __forceinline__ WorkItem decode_item(const UmmaArgs& a, uint32_t w) {
     WorkItem it{};
-    for (int bi = 0; bi < a.nb; ++bi) {
-        const UmmaBucket& b = a.b[bi];
-        const uint32_t items = b.n_row_tiles * b.chunks;
-        if (w < items) {
-            const uint32_t rt = w / b.chunks, q = w % b.chunks;
-            it.a_blob = b.row_tile0 + rt;
-            it.row0 = b.row0 + rt * UM_ROWS;
-            it.nrows = min((uint32_t)UM_ROWS, b.nrows - rt * UM_ROWS);
-            const uint32_t lt0 = (uint32_t)(((uint64_t)q * b.n_col_tiles) / b.chunks);
-            const uint32_t lt1 = (uint32_t)(((uint64_t)(q + 1) * b.n_col_tiles) / b.chunks);
-            it.t0 = b.col_tile0 + lt0;
-            it.t1 = b.col_tile0 + lt1;
-            return it;
-        }
-        w -= items;
+    int bi = 0;
+    while (bi + 1 < a.nb && w >= a.item_end[bi]) ++bi;       // running totals: two instructions per bucket passed
+    if (bi) w -= a.item_end[bi - 1];
+    const UmmaBucket& b = a.b[bi];
+    uint32_t rt = w, lt0 = 0, lt1 = b.n_col_tiles;
+    if (b.chunks != 1) {                                      // column chunking (few row tiles): divisions only here
+        rt = w / b.chunks;
+        const uint32_t q = w - rt * b.chunks;
+        lt0 = (uint32_t)(((uint64_t)q * b.n_col_tiles) / b.chunks);
+        lt1 = (uint32_t)(((uint64_t)(q + 1) * b.n_col_tiles) / b.chunks);
     }
+    it.a_blob = b.row_tile0 + rt;
+    it.row0 = b.row0 + rt * UM_ROWS;
+    it.nrows = min((uint32_t)UM_ROWS, b.nrows - rt * UM_ROWS);
+    it.t0 = b.col_tile0 + lt0;
+    it.t1 = b.col_tile0 + lt1;
     return it;
 }
 
