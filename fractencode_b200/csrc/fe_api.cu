@@ -345,7 +345,8 @@ struct TcBuckets {
     const uint32_t* dom_order = nullptr;   // position -> domain index, ascending inside a bucket
     const uint32_t* rng_order = nullptr;   // position -> range index
     uint32_t doff[FE_MAX_BUCKETS + 1] = {0}, roff[FE_MAX_BUCKETS + 1] = {0};
-    bool bins = false;                     // brightness bins: range bucket c pairs with domain buckets c-1, c, c+1
+    bool bins = false;                     // brightness bins: range bucket c pairs with the domain buckets c-span .. c+span
+    int span = 0;
     uint32_t cut[8] = {0};                 // bins: domain-index cutoffs of the slice schedule (fractions 2^k / 128 of the scan)
     uint32_t pre[FE_MAX_BUCKETS][8] = {};  // bins: positions of bucket b below cut[k]
 };
@@ -367,14 +368,14 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
     const bool pass_dbg = getenv("FE_PASS_DBG") != nullptr;
     const bool multipass = use_thr && !single_pass;
     const uint32_t GR = 128;                                              // slice granularity: whole column tiles of both kinds
-    const uint32_t min_step = (tb.bins ? 6 : 16) * GR;                    // columns a bucket advances per pass at least (a work item
-                                                                          // spans three buckets with bins)
+    const uint32_t min_step = (tb.bins ? std::max(3, 16 / (2 * tb.span + 1)) : 16) * GR;   // columns a bucket advances per pass at
+                                                                          // least (a work item spans 2*span+1 buckets with bins)
     LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
     LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));
-    FE_CUDA(ctx, ctx->b_hist.ensure(64 * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_hist.ensure((FE_MAX_BUCKETS + 8) * sizeof(uint32_t)));
     uint32_t* d_cnt = ctx->b_hist.as<uint32_t>();
-    uint32_t* d_nsel = d_cnt + 40;
+    uint32_t* d_nsel = d_cnt + FE_MAX_BUCKETS;
 
     uint32_t dc[FE_MAX_BUCKETS], done[FE_MAX_BUCKETS], aoff[FE_MAX_BUCKETS + 1];
     for (int c = 0; c < nb; ++c) { dc[c] = tb.doff[c + 1] - tb.doff[c]; done[c] = 0; }
@@ -454,10 +455,8 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
         bool all_done = true, any_work = false;
         for (int b = 0; b < nb; ++b) {
             bool wanted = aoff[b + 1] > aoff[b];
-            if (tb.bins) {
-                if (b > 0 && aoff[b] > aoff[b - 1]) wanted = true;
-                if (b + 1 < nb && aoff[b + 2] > aoff[b + 1]) wanted = true;
-            }
+            for (int c = std::max(0, b - tb.span); c <= std::min(nb - 1, b + tb.span); ++c)
+                if (aoff[c + 1] > aoff[c]) wanted = true;                 // some range bucket that meets this domain bucket is alive
             lo[b] = done[b];
             hi[b] = dc[b];
             if (!wanted) { lo[b] = hi[b] = done[b] = dc[b]; continue; }   // its ranges are all closed: never needed again
@@ -477,7 +476,7 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
             SearchPass sp{};
             sp.dom_order = tb.dom_order; sp.rng_items = items; sp.rowslot = slots;
             sp.nbuckets = nb; sp.n_dom = nD;
-            sp.span = tb.bins ? 1 : 0;
+            sp.span = tb.span;
             sp.no_min = use_thr && !need_min;
             sp.reuse_dom_norms = res->launches > 0;
             uint64_t cols = 0, work = 0;
@@ -572,33 +571,33 @@ static int bucket_by_brightness(fe_ctx* ctx, const LevelIO& io, uint32_t width, 
     FE_CUDA(ctx, ctx->b_rng_order.ensure((size_t)nR * sizeof(uint32_t)));
     FE_CUDA(ctx, ctx->b_keys_tmp.ensure(n * 2 + 64));
     FE_CUDA(ctx, ctx->b_vals_tmp.ensure((size_t)std::max(nD, nR) * sizeof(uint32_t)));
-    FE_CUDA(ctx, ctx->b_hist.ensure((64 + FE_MAX_BUCKETS * 8) * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_hist.ensure((size_t)FE_MAX_BUCKETS * 10 * sizeof(uint32_t)));
     uint8_t* dkeys = ctx->b_keys_tmp.as<uint8_t>();
     uint8_t* rkeys = dkeys + nD;
     uint8_t* keys_out = dkeys + n;
     uint32_t* hist = ctx->b_hist.as<uint32_t>();
-    FE_CUDA(ctx, cudaMemsetAsync(hist, 0, 64 * sizeof(uint32_t), ctx->stream));
+    FE_CUDA(ctx, cudaMemsetAsync(hist, 0, 2 * FE_MAX_BUCKETS * sizeof(uint32_t), ctx->stream));
     LAUNCH(ctx, k_brightness_bins, cdiv((uint64_t)nD * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, nD, io.g.S, 1u, width, dkeys, hist);
-    LAUNCH(ctx, k_brightness_bins, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, io.g.T, 4u, width, rkeys, hist + 32);
+    LAUNCH(ctx, k_brightness_bins, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, io.g.T, 4u, width, rkeys, hist + FE_MAX_BUCKETS);
     LAUNCH(ctx, k_iota, cdiv(std::max(nD, nR), 256), 256, ctx->b_vals_tmp.as<uint32_t>(), std::max(nD, nR));
     size_t tmp_d = 0, tmp_r = 0;
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_d, dkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order.as<uint32_t>(), (int)nD, 0, 5, ctx->stream));
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_r, rkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order.as<uint32_t>(), (int)nR, 0, 5, ctx->stream));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_d, dkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order.as<uint32_t>(), (int)nD, 0, 6, ctx->stream));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_r, rkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order.as<uint32_t>(), (int)nR, 0, 6, ctx->stream));
     FE_CUDA(ctx, ctx->b_sort_tmp.ensure(std::max(tmp_d, tmp_r)));
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_d, dkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order.as<uint32_t>(), (int)nD, 0, 5, ctx->stream));
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_r, rkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order.as<uint32_t>(), (int)nR, 0, 5, ctx->stream));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_d, dkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order.as<uint32_t>(), (int)nD, 0, 6, ctx->stream));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_r, rkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order.as<uint32_t>(), (int)nR, 0, 6, ctx->stream));
     ctx->stats.kernel_launches += 6;
     // prefix lengths of every domain bucket at the slice cutoffs (device-side offsets: no host round trip in between)
     BucketOff c8{};
     for (int k = 0; k < 8; ++k) c8.v[k] = cut[k];
-    LAUNCH(ctx, k_bin_prefix, cdiv((uint64_t)nbins * 8, 128), 128, ctx->b_dom_order.as<uint32_t>(), hist, nbins, c8, hist + 64);
-    uint32_t h[64 + FE_MAX_BUCKETS * 8];
+    LAUNCH(ctx, k_bin_prefix, cdiv((uint64_t)nbins * 8, 128), 128, ctx->b_dom_order.as<uint32_t>(), hist, nbins, c8, hist + 2 * FE_MAX_BUCKETS);
+    uint32_t h[FE_MAX_BUCKETS * 10];
     FE_CUDA(ctx, cudaMemcpyAsync(h, hist, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     doff[0] = roff[0] = 0;
-    for (int c = 0; c < nbins; ++c) { doff[c + 1] = doff[c] + h[c]; roff[c + 1] = roff[c] + h[32 + c]; }
+    for (int c = 0; c < nbins; ++c) { doff[c + 1] = doff[c] + h[c]; roff[c + 1] = roff[c] + h[FE_MAX_BUCKETS + c]; }
     for (int b = 0; b < nbins; ++b)
-        for (int k = 0; k < 8; ++k) pre[b][k] = h[64 + b * 8 + k];
+        for (int k = 0; k < 8; ++k) pre[b][k] = h[2 * FE_MAX_BUCKETS + b * 8 + k];
     return FE_OK;
 }
 
@@ -659,9 +658,13 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
             while (R * R > nt) --R;
             while ((R + 1) * (R + 1) <= nt) ++R;
             const uint64_t maxsum = 1020ull * g.N;
-            const uint64_t width = std::max<uint64_t>(R + 1, (maxsum + FE_MAX_BUCKETS) / FE_MAX_BUCKETS);
+            // bins half as wide as the radius (a range then meets 5 bins = 2.5 radii instead of 3 bins = 3 radii), as long as
+            // 64 bins cover the value range; |sumA - sumB| <= R  =>  |binA - binB| <= floor(R / width) + 1
+            const uint64_t width = std::max<uint64_t>((R + 2) / 2, (maxsum + FE_MAX_BUCKETS) / FE_MAX_BUCKETS);
             const int nbins = (int)(maxsum / width) + 1;
-            if (nbins >= 4 && nbins <= FE_MAX_BUCKETS) {
+            const int span = (int)(R / width) + 1;
+            if (nbins >= 2 * (2 * span + 1) && nbins <= FE_MAX_BUCKETS) {
+                tb.span = span;
                 for (int k = 0; k < 8; ++k) tb.cut[k] = k == 7 ? nD : (uint32_t)(((uint64_t)nD << k) / 128 + 1);
                 FE_TRY(bucket_by_brightness(ctx, io, (uint32_t)width, nbins, tb.doff, tb.roff, tb.cut, tb.pre));
                 tb.nb = nbins;

@@ -74,7 +74,7 @@ struct SearchArgs {
 
 constexpr int FE_MAX_PASSES = 32;
 constexpr int FE_MAX_LAUNCHES = 3 * FE_MAX_PASSES + 4;   // search launches of one level (three brightness-bin shifts per slice)
-constexpr int FE_MAX_BUCKETS = 32;   // classifier buckets (7) or brightness bins of the threshold pruning (<= 32)
+constexpr int FE_MAX_BUCKETS = 64;   // classifier buckets (7) or brightness bins of the threshold pruning (<= 64)
 
 struct fe_ctx {
     int device = 0;

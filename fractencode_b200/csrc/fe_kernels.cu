@@ -213,7 +213,7 @@ __global__ void k_bin_prefix(const uint32_t* __restrict__ dom_order, const uint3
     if (t >= nb * 8) return;
     const int b = t / 8, k = t % 8;
     uint32_t lo = 0;
-    for (int i = 0; i < b; ++i) lo += hist[i];
+    for (int i = 0; i < b; ++i) lo += hist[i];   // (<= 63 adds)
     const uint32_t beg = lo;
     uint32_t hi = lo + hist[b];
     const uint32_t c = cut.v[k];
