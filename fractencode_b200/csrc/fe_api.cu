@@ -577,8 +577,10 @@ static int bucket_by_brightness(fe_ctx* ctx, const LevelIO& io, uint32_t width, 
     uint8_t* keys_out = dkeys + n;
     uint32_t* hist = ctx->b_hist.as<uint32_t>();
     FE_CUDA(ctx, cudaMemsetAsync(hist, 0, 2 * FE_MAX_BUCKETS * sizeof(uint32_t), ctx->stream));
-    LAUNCH(ctx, k_brightness_bins, cdiv((uint64_t)nD * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, nD, io.g.S, 1u, width, dkeys, hist);
-    LAUNCH(ctx, k_brightness_bins, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, io.g.T, 4u, width, rkeys, hist + FE_MAX_BUCKETS);
+    launch_brightness_bins(ctx->stream, ctx->src.px, ctx->src.stride, io.d_dom, nD, io.g.S, 1u, width, dkeys, hist);
+    launch_brightness_bins(ctx->stream, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, io.g.T, 4u, width, rkeys, hist + FE_MAX_BUCKETS);
+    FE_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 2;
     LAUNCH(ctx, k_iota, cdiv(std::max(nD, nR), 256), 256, ctx->b_vals_tmp.as<uint32_t>(), std::max(nD, nR));
     size_t tmp_d = 0, tmp_r = 0;
     FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_d, dkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order.as<uint32_t>(), (int)nD, 0, 6, ctx->stream));

@@ -172,29 +172,33 @@ __global__ void k_unresolved(const uint32_t* __restrict__ slots, const uint32_t*
     if (threadIdx.x < FE_MAX_BUCKETS && sc[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], sc[threadIdx.x]);
 }
 
-// Brightness bin of every block of a uniform list: key = (mul * sum of the block's edge x edge pixels) / width, one warp per
-// block.  For a range block mul = 4 (sum of 4 r); for a domain block mul = 1 and edge = S (the sum of its 2x2 box sums D is the
-// sum of its pixels).  hist[key] counts.
-__global__ void k_brightness_bins(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ items, uint32_t n,
-                                  uint32_t edge, uint32_t mul, uint32_t width, uint8_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+// Brightness bin of every block of a uniform list: key = (mul * sum of the block's edge x edge pixels) / width.  For a range
+// block mul = 4 (sum of 4 r); for a domain block mul = 1 and edge = S (the sum of its 2x2 box sums D is the sum of its pixels).
+// hist[key] counts.  WARP = true: one warp per block (large blocks); false: one thread per block (edge <= 16; neighbouring
+// threads read neighbouring, for domains overlapping, blocks).
+template <bool WARP>
+__global__ void k_brightness_bins_t(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ items, uint32_t n,
+                                    uint32_t edge, uint32_t mul, uint32_t width, uint8_t* __restrict__ keys, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[FE_MAX_BUCKETS];
     if (threadIdx.x < FE_MAX_BUCKETS) sh[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = WARP ? t >> 5 : t, lane = WARP ? threadIdx.x & 31 : 0, step = WARP ? 32 : 1;
     if (p < n) {
         const fe_grid_item it = items[p];
         const uint8_t* base = img + (size_t)it.y * stride + it.x;
         uint32_t s = 0;
         if ((edge & 3u) == 0 && ((reinterpret_cast<uintptr_t>(base) | stride) & 3u) == 0) {
             const uint32_t wpr = edge / 4, nw = wpr * edge;   // 4-byte words per row / per block
-            for (uint32_t e = lane; e < nw; e += 32) {
+            for (uint32_t e = lane; e < nw; e += step) {
                 const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)(e / wpr) * stride) + (e % wpr));
                 s += __dp4a(v, 0x01010101u, 0u);
             }
         } else {
-            for (uint32_t e = lane; e < edge * edge; e += 32) s += base[(size_t)(e / edge) * stride + (e % edge)];
+            for (uint32_t e = lane; e < edge * edge; e += step) s += base[(size_t)(e / edge) * stride + (e % edge)];
         }
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        if (WARP)
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
         if (lane == 0) {
             const uint32_t k = min((mul * s) / width, (uint32_t)FE_MAX_BUCKETS - 1);
             keys[p] = (uint8_t)k;
@@ -203,6 +207,13 @@ __global__ void k_brightness_bins(const uint8_t* __restrict__ img, uint32_t stri
     }
     __syncthreads();
     if (threadIdx.x < FE_MAX_BUCKETS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+void launch_brightness_bins(cudaStream_t stream, const uint8_t* img, uint32_t stride, const fe_grid_item* items, uint32_t n, uint32_t edge,
+                            uint32_t mul, uint32_t width, uint8_t* keys, uint32_t* hist) {
+    if (!n) return;
+    if (edge <= 16) k_brightness_bins_t<false><<<(n + 127) / 128, 128, 0, stream>>>(img, stride, items, n, edge, mul, width, keys, hist);
+    else k_brightness_bins_t<true><<<(unsigned)(((uint64_t)n * 32 + 255) / 256), 256, 0, stream>>>(img, stride, items, n, edge, mul, width, keys, hist);
 }
 
 // out[b * 8 + k] = number of positions of domain bucket b whose domain index is below cut.v[k] (positions of a bucket are

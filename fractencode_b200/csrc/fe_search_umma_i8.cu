@@ -251,37 +251,84 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_umma_i8(const UmmaA
 // ---------------------------------------------------------------------------------------------------
 // operand blobs (u8).  A: [row tile][K/16][128 rows][16 B].  B: [col tile][K stage][plane lo,hi][kc/16][64 cols][16 B].
 // ---------------------------------------------------------------------------------------------------
-// One thread per 16-byte store (16 K bytes of one row / column); every byte of every blob is written once, no memset.
-__global__ void k_build_rows_i8(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
-                                const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
-                                uint4* __restrict__ A8) {
-    const uint32_t nch = Kpad / 16;
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint64_t)bk.row_tile0[bk.nb] * nch * UM_ROWS) return;
-    const uint32_t row = (uint32_t)(idx % UM_ROWS), ch = (uint32_t)((idx / UM_ROWS) % nch), tile = (uint32_t)(idx / ((uint64_t)UM_ROWS * nch));
+// A: one CTA per row tile (32 ranges).  The 32 blocks are staged in shared memory with coalesced word loads (their
+// 16 * sum r^2 falls out on the way), then every thread assembles 16-byte K chunks of the four rotations from shared memory
+// -- rotations 0 and 2 are straight / reversed 16-byte runs, 1 and 3 are strided byte gathers that never leave the SM.
+// Every byte of the blob is written exactly once (padding rows as zeros): no memset.
+__global__ void __launch_bounds__(256) k_build_rows_i8(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
+                                                       const uint32_t* __restrict__ order, UmmaBuckets bk, uint32_t T, uint32_t Kpad,
+                                                       uint4* __restrict__ A8, uint32_t* __restrict__ rowc) {
+    extern __shared__ __align__(16) uint8_t sblk[];            // [32][N]
+    __shared__ uint32_t s2[32];
+    __shared__ fe_grid_item sit[32];
+    const uint32_t tile = blockIdx.x, N = T * T, nch = Kpad / 16;
     int bi = 0;
     while (bi + 1 < bk.nb && tile >= bk.row_tile0[bi + 1]) ++bi;
-    const uint32_t j = bk.range_off[bi] + (tile - bk.row_tile0[bi]) * 32 + row / 4, k = row & 3;
-    const uint32_t N = T * T;
-    uint32_t w[4] = {0, 0, 0, 0};
-    if (j < bk.range_off[bi + 1]) {
-        const fe_grid_item r = rng[order ? order[j] : j];
-        const uint8_t* base = img + (size_t)r.y * stride + r.x;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const uint32_t e = ch * 16 + q;
-            if (e < N) {
-                const uint32_t Y = e / T, X = e % T;
-                uint32_t py, px;
-                if (k == 0) { py = Y; px = X; }
-                else if (k == 1) { py = X; px = T - 1 - Y; }
-                else if (k == 2) { py = T - 1 - Y; px = T - 1 - X; }
-                else { py = T - 1 - X; px = Y; }
-                w[q >> 2] |= (uint32_t)base[(size_t)py * stride + px] << (8 * (q & 3));
-            }
+    const uint32_t j0 = bk.range_off[bi] + (tile - bk.row_tile0[bi]) * 32;
+    const uint32_t jend = bk.range_off[bi + 1];
+    const uint32_t nvalid = j0 < jend ? min(32u, jend - j0) : 0u;
+    if (threadIdx.x < 32) {
+        s2[threadIdx.x] = 0;
+        if (threadIdx.x < nvalid) sit[threadIdx.x] = rng[order ? order[j0 + threadIdx.x] : j0 + threadIdx.x];
+    }
+    __syncthreads();
+    // ---- stage the blocks ----
+    const bool words = (T & 3u) == 0 && (stride & 3u) == 0 && (reinterpret_cast<uintptr_t>(img) & 3u) == 0;
+    if (words) {
+        const uint32_t wpr = T / 4, wpb = N / 4;              // words per block row / per block
+        for (uint32_t idx = threadIdx.x; idx < nvalid * wpb; idx += blockDim.x) {
+            const uint32_t lr = idx / wpb, e = idx - lr * wpb, y = e / wpr, xw = e - y * wpr;
+            const fe_grid_item it = sit[lr];
+            const uint8_t* p = img + (size_t)(it.y + y) * stride + it.x + 4 * xw;
+            uint32_t v;
+            if ((it.x & 3u) == 0) v = __ldg(reinterpret_cast<const uint32_t*>(p));
+            else v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+            reinterpret_cast<uint32_t*>(sblk)[lr * wpb + e] = v;
+            atomicAdd(&s2[lr], __dp4a(v, v, 0u));
+        }
+    } else {
+        for (uint32_t idx = threadIdx.x; idx < nvalid * N; idx += blockDim.x) {
+            const uint32_t lr = idx / N, e = idx - lr * N, y = e / T, x = e - y * T;
+            const fe_grid_item it = sit[lr];
+            const uint32_t v = img[(size_t)(it.y + y) * stride + it.x + x];
+            sblk[lr * N + e] = (uint8_t)v;
+            atomicAdd(&s2[lr], v * v);
         }
     }
-    A8[idx] = make_uint4(w[0], w[1], w[2], w[3]);
+    __syncthreads();
+    if (threadIdx.x < nvalid) rowc[j0 + threadIdx.x] = 16u * s2[threadIdx.x];
+    // ---- chunks: [K/16][128 rows][16 B] ----
+    uint4* out = A8 + (size_t)tile * nch * UM_ROWS;
+    for (uint32_t idx = threadIdx.x; idx < nch * UM_ROWS; idx += blockDim.x) {
+        const uint32_t row = idx % UM_ROWS, ch = idx / UM_ROWS, lr = row >> 2, k = row & 3u;
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (lr < nvalid && ch * 16 < N) {
+            const uint8_t* sb = sblk + lr * N;
+            if (k == 0 && (N & 15u) == 0) {
+                const uint4 v = *reinterpret_cast<const uint4*>(sb + ch * 16);
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            } else if (k == 2 && (N & 15u) == 0) {             // element e of the rotated block = element N-1-e of the block
+                const uint4 v = *reinterpret_cast<const uint4*>(sb + N - 16 - ch * 16);
+                w[0] = __byte_perm(v.w, 0, 0x0123); w[1] = __byte_perm(v.z, 0, 0x0123);
+                w[2] = __byte_perm(v.y, 0, 0x0123); w[3] = __byte_perm(v.x, 0, 0x0123);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const uint32_t e = ch * 16 + q;
+                    if (e < N) {
+                        const uint32_t Y = e / T, X = e - Y * T;
+                        uint32_t py, px;
+                        if (k == 0) { py = Y; px = X; }
+                        else if (k == 1) { py = X; px = T - 1 - Y; }
+                        else if (k == 2) { py = T - 1 - Y; px = T - 1 - X; }
+                        else { py = T - 1 - X; px = Y; }
+                        w[q >> 2] |= (uint32_t)sb[py * T + px] << (8 * (q & 3));
+                    }
+                }
+            }
+        }
+        out[idx] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
 }
 
 // B: [col tile][K stage][plane lo,hi][kc/16][64 cols][16 B].  Thread -> (tile, stage, 16-byte K chunk, column): writes the
@@ -306,7 +353,32 @@ __global__ void k_build_pool_i8(const uint8_t* __restrict__ img, uint32_t stride
         blob_dom[(size_t)tile * I8_NT + l] = di;
         if (l == 0) tileseg[tile] = (uint32_t)bi;
     }
-    if (valid) {
+    const uint32_t e0 = st * kc + cs * 16;
+    bool done = false;
+    if (valid && (T & 15u) == 0 && e0 < N) {
+        // 16 box sums = 16 consecutive values of one decimated row: two source rows of 32 pixels, as 16-byte loads when aligned
+        const fe_grid_item d = dom[di];
+        const uint32_t Y = e0 / T, X0 = e0 - Y * T;
+        const uint8_t* p0 = img + (size_t)(d.y + 2 * Y) * stride + d.x + 2 * X0;
+        if (((reinterpret_cast<uintptr_t>(p0) | stride) & 15u) == 0) {
+            const uint4* r0 = reinterpret_cast<const uint4*>(p0);
+            const uint4* r1 = reinterpret_cast<const uint4*>(p0 + stride);
+            const uint4 ta = __ldg(r0), tb = __ldg(r0 + 1), ba = __ldg(r1), bb = __ldg(r1 + 1);
+            const uint32_t top[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+            const uint32_t bot[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+            uint32_t dd[8];                                   // two box sums per word, 16 bits each
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                dd[i] = (top[i] & 0x00FF00FFu) + ((top[i] >> 8) & 0x00FF00FFu) + (bot[i] & 0x00FF00FFu) + ((bot[i] >> 8) & 0x00FF00FFu);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                lo[i] = __byte_perm(dd[2 * i], dd[2 * i + 1], 0x6420);
+                hi[i] = __byte_perm(dd[2 * i], dd[2 * i + 1], 0x7531);
+            }
+            done = true;
+        }
+    }
+    if (valid && !done) {
         const fe_grid_item d = dom[di];
         const uint8_t* base = img + (size_t)d.y * stride + d.x;
 #pragma unroll
@@ -319,10 +391,9 @@ __global__ void k_build_pool_i8(const uint8_t* __restrict__ img, uint32_t stride
                 hi[q >> 2] |= (D >> 8) << (8 * (q & 3));
             }
         }
-        if (st == 0 && cs == 0) coln_tiles[(size_t)tile * I8_NT + l] = colS2[c];
-    } else if (st == 0 && cs == 0) {
-        coln_tiles[(size_t)tile * I8_NT + l] = 0x7FFFFFFFu; // padding columns can never be a strict minimum nor pass the threshold
     }
+    if (st == 0 && cs == 0) // padding columns can never be a strict minimum nor pass the threshold
+        coln_tiles[(size_t)tile * I8_NT + l] = valid ? colS2[c] : 0x7FFFFFFFu;
     // stage blob = [plane][kc/16][64][16 B]: in uint4 units plane stride = ncs * 64
     const size_t stage_base = ((size_t)tile * nst + st) * 2 * ncs * I8_NT;
     B8[stage_base + (size_t)cs * I8_NT + l] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -396,11 +467,9 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)bk.n_ranges * 4 + 4));
     FE_CUDA(ctx, ctx->b_tmaps.ensure((size_t)bk.n_domains * 4 + 64));
     if (!sp.reuse_rows) {
-        k_block_norms<<<(unsigned)(((uint64_t)bk.n_ranges * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order,
-                                                                                                   bk.n_ranges, g.T, 1, ctx->b_rowc.as<uint32_t>());
-        k_build_rows_i8<<<(unsigned)((bytesA / 16 + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, g.T, Kpad, ctx->b_A16.as<uint4>());
-        ctx->stats.kernel_launches += 2;
+        k_build_rows_i8<<<rt, 256, 32 * g.N, ctx->stream>>>(ctx->tgt.px, ctx->tgt.stride, d_rng, rng_order, bk, g.T, Kpad, ctx->b_A16.as<uint4>(),
+                                                           ctx->b_rowc.as<uint32_t>());
+        ctx->stats.kernel_launches++;
     }
     if (!sp.reuse_dom_norms) {
         k_block_norms<<<(unsigned)(((uint64_t)bk.n_domains * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order,
