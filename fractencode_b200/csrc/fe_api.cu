@@ -518,9 +518,17 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
         // minimum, and the bins (about a third of the scan) come on top.  Hits come early in the scan where they come at
         // all -- first slices that close next to nothing say "no hits on this level": go plain now.
         if (tb.bins && need_min && res->passes <= 2 && resolved < 0.05) break;
-        const int step = resolved >= 0.03 ? 1 : (resolved >= 0.002 ? 2 : 3);   // slices that close nothing: grow faster
+        // slices that close little grow faster; one that closes nothing at all says early-out will not pay: finish in one go
+        const int step = resolved >= 0.03 ? 1 : (resolved >= 0.002 ? 2 : 8);
         kF += step;
         F *= (double)(1 << step);
+        // what is left is small: one more launch for all of it costs less than the round trips of several slices
+        uint64_t left = 0;
+        for (int c = 0; c < nb; ++c) {
+            const uint64_t rc = aoff[c + 1] - aoff[c];
+            for (int b = std::max(0, c - tb.span); rc && b <= std::min(nb - 1, c + tb.span); ++b) left += rc * (dc[b] - done[b]) * 4;
+        }
+        if ((double)left * 2.0 * g.N <= 1.5e11) F = 1.0;
         if (kF > 7) { kF = 7; F = 1.0; }
     }
 
