@@ -85,6 +85,8 @@ extern "C" int fe_create(fe_ctx** out, int device, void* stream) {
         ctx->own_stream = true;
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
     for (auto& ev : ctx->ev_pass) cudaEventCreate(&ev);
     *out = ctx;
     return FE_OK;
@@ -102,6 +104,8 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
                       &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_act[0], &ctx->b_act[1], &ctx->b_act_items, &ctx->b_act_flags, &ctx->b_act_tmp};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& ev : ctx->ev_pass) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -915,6 +919,14 @@ extern "C" int fe_encode_quadtree_device(fe_ctx* ctx, uint32_t t_max, uint32_t t
         }
         const size_t kept = n_pending - n_split;
         ctx->stats.level_items[level] = kept;
+        if (ctx->host_out && kept && offset + kept <= ctx->host_cap && ctx->host_copied == offset) {
+            // the level's items are final: send them to the caller's buffer behind the next level's work
+            FE_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
+            FE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+            FE_CUDA(ctx, cudaMemcpyAsync(ctx->host_out + offset, ctx->b_items.as<fe_encode_item>() + offset, kept * sizeof(fe_encode_item),
+                                         cudaMemcpyDeviceToHost, ctx->copy_stream));
+            ctx->host_copied = offset + kept;
+        }
         offset += kept;
         std::swap(ctx->b_rng, ctx->b_rng_next);
         n_pending = 4 * n_split;
@@ -942,10 +954,20 @@ extern "C" const void* fe_device_items(const fe_ctx* ctx, size_t* n_out) {
 extern "C" int fe_encode_quadtree(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params, fe_encode_item* out,
                                   size_t cap, size_t* n_out, size_t* level_counts) {
     size_t n = 0;
-    FE_TRY(fe_encode_quadtree_device(ctx, t_max, t_min, params, &n));
+    if (!ctx) return FE_ERR_INVALID;
+    ctx->host_out = out; ctx->host_cap = out ? cap : 0; ctx->host_copied = 0;
+    const int rc = fe_encode_quadtree_device(ctx, t_max, t_min, params, &n);
+    ctx->host_out = nullptr;
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (rc != FE_OK) return rc;
     if (level_counts) {
         int level = 0;
         for (uint32_t T = t_max; T >= t_min; T /= 2, ++level) level_counts[level] = (size_t)ctx->stats.level_items[level];
+    }
+    if (ctx->host_copied == n && n <= cap) { // everything already went out level by level
+        FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (n_out) *n_out = n;
+        return FE_OK;
     }
     FE_TRY(fe_fetch_items(ctx, out, cap, n_out));
     return FE_OK;

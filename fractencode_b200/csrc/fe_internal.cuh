@@ -98,6 +98,11 @@ struct fe_ctx {
     // decode scratch
     DevBuf b_dec_a, b_dec_b, b_dec_items, b_dec_sum, b_q;
     fe_stats stats{};
+    // fe_encode_quadtree with a host buffer: the items of a level go out on a second stream while the next level runs
+    fe_encode_item* host_out = nullptr;
+    size_t host_cap = 0, host_copied = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_pass[2 * FE_MAX_LAUNCHES] = {}; // start/stop around each search launch of a level
 };
