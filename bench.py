@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram bytes (read + write) of all search launches of a level of the default workload, from ncu (None: not captured yet)
-TRAFFIC_BY_T = {}
+TRAFFIC_BY_T = {32: 176.1e6, 16: 175.3e6, 8: 732.5e6, 4: 166.6e6}   # profiles/search_kernels_r1b.md
 
 METRIC = "range_block_matches_per_s"
 UNIT = "matches/s"
@@ -57,6 +57,11 @@ def parse():
 def workload_name(a):
     return "natural %dx%d u8 (SURVEY 8d generator, seed 1234+rank), quadtree %d->%d, %s, rms_threshold %g" % (
         a.size, a.size, a.tmax, a.tmin, "Classifier2" if a.classifier else "full search (DummyClassifier)", a.thr)
+
+
+PRUNING_NOTE = ("exact: range blocks stop at their first candidate under the threshold (slices of the scan, reference break semantics) and, "
+                "without classifier, meet only domains whose pixel sum can satisfy the threshold (Cauchy-Schwarz bins); "
+                "`matches` is the nominal candidate count, `evaluated` what the kernels scored")
 
 
 def peaks():
@@ -297,6 +302,24 @@ def run_b200(a):
     e_times, e_items = timed(step_e2e, a.steps)
     sync_all()
 
+    # The dominant search kernel at steady state: the same level scanned in ONE pass (no slices, no bins: every range block
+    # against every domain, long work items) -- what the kernel does when the pruning of the step cannot shorten the scan.
+    steady = None
+    if rank == 0 and os.environ.get("FE_BENCH_STEADY", "1") != "0":
+        dom_T = max(range(nlev), key=lambda l: float(st.level_search_ms[l]))
+        Ts = a.tmax >> dom_T
+        os.environ["FE_SINGLE_PASS"] = "1"
+        try:
+            for _ in range(2):
+                ctx.stats_reset()
+                ctx.encode_quadtree_device(Ts, Ts, params)
+            s2 = ctx.stats()
+            ms2, ev2 = float(s2.level_search_ms[0]), int(s2.level_evaluated[0])
+            steady = {"T": Ts, "candidates": ev2, "search_ms": ms2, "achieved": 2.0 * Ts * Ts * ev2 / (ms2 * 1e-3) / 1e12 if ms2 > 0 else 0.0,
+                      "note": "one-pass scan of the whole level (FE_SINGLE_PASS=1): all %d-pixel range blocks of the image x every domain x 4" % Ts}
+        finally:
+            del os.environ["FE_SINGLE_PASS"]
+
     # HBM-bound side of the path, measured once on rank 0: the decode gather (Decoder2's fixed-point iteration)
     decode_info = None
     if rank == 0:
@@ -336,7 +359,7 @@ def run_b200(a):
             "dtype": "u8 in, fp16 operands / fp32 (integer-exact) accumulate, int32 scores, f64 s/o",
             "data": "synthetic",
             "config": {"workload": workload_name(a), "images_per_step": world, "l2": "flushed between timed steps (512 MiB fill)",
-                       "search_impl": ["auto", "exact-int (dp4a)", "tcgen05"][a.search]},
+                       "search_impl": ["auto", "exact-int (dp4a)", "tcgen05"][a.search], "pruning": PRUNING_NOTE},
             "mpix_per_s": world * W * H / 1e6 / (ms_per_step * 1e-3),
             "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": W * H, "d2h_bytes_per_step": int(e_items) * 64,
                     "ms_per_step": e_ms / a.steps, "mpix_per_s": world * W * H / 1e6 / (e_ms / a.steps * 1e-3)},
@@ -351,6 +374,7 @@ def run_b200(a):
                                    "durations (ctx stream); peak = sustained bf16 (kernel timed inside a long step), %s" % (
                              "k_search_umma<f16>" if dom["T"] <= 8 else "k_search_umma_i8", dom["T"], dom["evaluated"], dom["passes"], pk["source"]),
                          "all_levels": {"achieved": ach, "frac": ach / pk["tflops_sustained"]},
+                         "steady_state": dict(steady, frac=steady["achieved"] / pk["tflops_sustained"]) if steady else None,
                          "peak_burst": pk["tflops_burst"]},
             "hbm_kernels": {"peak_gbs": pk["hbm_gbs"], "decode": decode_info,
                             "prep_ms_per_level": {str(l["T"]): l["prep_ms"] for l in levels}},
