@@ -56,13 +56,23 @@ __device__ __forceinline__ uint32_t row_parity(const RowState& st, uint32_t col)
 }
 
 // Exhaustive scan of a half tile held in registers (rare: exact ties, threshold crossings).
+// Parity words of a half tile: held in registers when the tile metadata is read anyway (META), else fetched from the
+// metadata record only on the rare paths that need them.
+struct ParitySrc {
+    uint32_t reg[UM_HALF / 32];
+    const uint32_t* ptr;
+};
+template <bool META>
+__device__ __forceinline__ uint32_t par_word(const ParitySrc& p, int wd) { return META ? p.reg[wd] : __ldg(p.ptr + wd); }
+
+template <bool META>
 __device__ __forceinline__ void scan_half_full(const uint32_t (&v)[UM_HALF], RowState& st, bool need_best, bool need_hit, uint32_t colbase,
-                                               const uint32_t (&par)[UM_HALF / 32]) {
+                                               const ParitySrc& par) {
     float cx = 3.0e38f;
     uint32_t cp = 1, ccol = FE_NONE32, chit = FE_NONE32;
 #pragma unroll
     for (int wd = 0; wd < UM_HALF / 32; ++wd) {
-        const uint32_t pw = par[wd];
+        const uint32_t pw = par_word<META>(par, wd);
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
             const int i = wd * 32 + b;
@@ -77,8 +87,9 @@ __device__ __forceinline__ void scan_half_full(const uint32_t (&v)[UM_HALF], Row
 }
 
 // UM_HALF accumulator values of one row (columns colbase .. colbase+UM_HALF-1 of the work item).
+template <bool META>
 __device__ __forceinline__ void process_half(uint32_t (&v)[UM_HALF], RowState& st, bool row_ok, uint32_t colbase, uint32_t nvalid,
-                                             const uint32_t (&par)[UM_HALF / 32], bool want_min) {
+                                             const ParitySrc& par, bool want_min) {
     if (nvalid < UM_HALF) {
 #pragma unroll
         for (int i = 0; i < UM_HALF; ++i)
@@ -114,7 +125,7 @@ __device__ __forceinline__ void process_half(uint32_t (&v)[UM_HALF], RowState& s
 #pragma unroll
             for (int k = 0; k < UM_HALF / 8; ++k) {
                 if (chit == FE_NONE32 && grp[k] <= st.vthr0) {
-                    const uint32_t pw = par[(8 * k) >> 5] >> ((8 * k) & 31);
+                    const uint32_t pw = par_word<META>(par, (8 * k) >> 5) >> ((8 * k) & 31);
 #pragma unroll
                     for (int e = 7; e >= 0; --e) {
                         const float x = __uint_as_float(v[8 * k + e]);
@@ -159,13 +170,16 @@ __device__ __forceinline__ void process_half(uint32_t (&v)[UM_HALF], RowState& s
         }
         if (full) {
             if (st.bestp == 2 && st.bestcol != FE_NONE32) st.bestp = row_parity(st, st.bestcol);
-            scan_half_full(v, st, true, false, colbase, par);
+            scan_half_full<META>(v, st, true, false, colbase, par);
         }
     }
 }
 
 // RETIRE: retire quads of rows after their first threshold hit (extra per-thread state: worth it on the ALU-bound T=4 level)
-template <int KIND, bool RETIRE>
+// META: work items may run over several domain buckets (brightness bins): per-tile metadata (valid columns, bucket id,
+// parity words) is read for every tile.  Otherwise a work item lies inside one bucket, only its last tile can be partial and
+// nothing is loaded per tile.
+template <int KIND, bool RETIRE, bool META>
 __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -377,21 +391,35 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
             for (uint32_t j = 0; j < my_tiles; ++j, ++jb) {
                 const uint32_t u = first + j * UM_WGS, buf = jb & 1;
                 const uint32_t colbase = u * UM_NT + h * UM_HALF;
-                // metadata of this half tile, fetched ahead of the accumulator wait (one 16-byte broadcast load per warp)
+                // metadata of this half tile (META: one 16-byte broadcast load per warp, issued ahead of the accumulator wait)
                 static_assert(UM_HALF == 64, "two parity words per half tile");
-                const uint4 meta = __ldg(a.colmeta + (size_t)(item.t0 + u) * 2 + h);
-                const uint32_t par[2] = {meta.x, meta.y};
-                const uint32_t nvalid = meta.z;
-                if (meta.w != cur_seg) {
-                    // The item moves into another domain bucket: columns restart at low domain indices there, so the first
-                    // hit found so far is only the first of the bucket behind us -- bank it and start over.
-                    if (st.hit != FE_NONE32) {
-                        atomicMin(&a.rowhit[srow], a.blob_dom[(size_t)item.t0 * UM_NT + st.hit]);
-                        st.hit = FE_NONE32;
-                    }
-                    cur_seg = meta.w;
-                    if (RETIRE) { retired = !row_ok; warp_done = false; }
+                const uint4* meta_p = a.colmeta + (size_t)(item.t0 + u) * 2 + h;
+                uint4 meta = make_uint4(0, 0, 0, 0);
+                ParitySrc par;
+                par.ptr = reinterpret_cast<const uint32_t*>(meta_p);
+                uint32_t nvalid;
+                if (META) {
+                    meta = __ldg(meta_p);
+                    par.reg[0] = meta.x; par.reg[1] = meta.y;
+                    nvalid = meta.z;
+                } else {
+                    const uint32_t tile_valid = min((uint32_t)UM_NT, item.cols_left - u * UM_NT);
+                    nvalid = tile_valid > h * UM_HALF ? min((uint32_t)UM_HALF, tile_valid - h * UM_HALF) : 0u;
                 }
+                // The item moves into another domain bucket: columns restart at low domain indices there, so the first hit
+                // found so far is only the first of the bucket behind us -- bank it and start over.  (Looked at after the
+                // accumulator has been read, when the metadata load has long landed; the retiring kernel needs it earlier.)
+                auto bucket_change = [&]() {
+                    if (META && meta.w != cur_seg) {
+                        if (st.hit != FE_NONE32) {
+                            atomicMin(&a.rowhit[srow], a.blob_dom[(size_t)item.t0 * UM_NT + st.hit]);
+                            st.hit = FE_NONE32;
+                        }
+                        cur_seg = meta.w;
+                        if (RETIRE) { retired = !row_ok; warp_done = false; }
+                    }
+                };
+                if (RETIRE) bucket_change();
                 uint32_t v[UM_HALF];
                 mbar_wait(ACC_FULL(g, buf), (jb >> 1) & 1);
                 tc_fence_after();
@@ -404,8 +432,9 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ACC_EMPTY(g, buf));
+                if (!RETIRE) bucket_change();
                 if (!(a.dbg & 1) && !(RETIRE && warp_done)) {
-                    process_half(v, st, RETIRE ? !retired : row_ok, colbase, nvalid, par, a.no_min == 0);
+                    process_half<META>(v, st, RETIRE ? !retired : row_ok, colbase, nvalid, par, a.no_min == 0);
                     if (RETIRE && (j & 3) == 3) {   // every 4th tile is enough: retirement only saves work
                         uint32_t hm = __ballot_sync(0xFFFFFFFFu, st.hit != FE_NONE32);
                         hm = (hm | (hm >> 1) | (hm >> 2) | (hm >> 3)) & 0x11111111u;   // one bit per quad of lanes
@@ -656,6 +685,7 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
         b.col_tile0 = bk.col_tile0[b0];
         b.n_col_tiles = bk.col_tile0[b1 + 1] - bk.col_tile0[b0];
         b.row0 = sp.roff[c] * 4; b.nrows = rc * 4;
+        b.ncols = sp.dend[b0] - sp.dbeg[b0];
         rt += b.n_row_tiles;
         ++nb;
     }
@@ -730,12 +760,13 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     if (Kpad / 16 > UM_MAX_NK) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "umma: K too large");
     const size_t smem = (size_t)a_bytes + (size_t)stages * stage_bytes + (12 + 2 * UM_MAX_STAGES) * 8 + 64;
     const bool retire = use_thr && g.T == 4;
-    FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FE_CUDA(ctx, cudaFuncSetAttribute(k_search_umma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const bool meta = sp.span > 0;
+    auto kern = retire ? (meta ? k_search_umma<0, true, true> : k_search_umma<0, true, false>)
+                       : (meta ? k_search_umma<0, false, true> : k_search_umma<0, false, false>);
+    FE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const uint32_t grid = (uint32_t)std::min<uint64_t>(total_items, 148);
     if (sp.ev0) cudaEventRecord(sp.ev0, ctx->stream);
-    if (retire) k_search_umma<0, true><<<grid, UM_THREADS_F16, smem, ctx->stream>>>(a);
-    else k_search_umma<0, false><<<grid, UM_THREADS_F16, smem, ctx->stream>>>(a);
+    kern<<<grid, UM_THREADS_F16, smem, ctx->stream>>>(a);
     FE_CUDA(ctx, cudaGetLastError());
     if (sp.ev1) cudaEventRecord(sp.ev1, ctx->stream);
     ctx->stats.kernel_launches++;

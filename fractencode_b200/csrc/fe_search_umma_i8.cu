@@ -434,6 +434,7 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
         b.col_tile0 = bk.col_tile0[b0];
         b.n_col_tiles = bk.col_tile0[b1 + 1] - bk.col_tile0[b0];
         b.row0 = sp.roff[c] * 4; b.nrows = rc * 4;
+        b.ncols = sp.dend[b0] - sp.dbeg[b0];
         rt += b.n_row_tiles;
         ++nb;
     }

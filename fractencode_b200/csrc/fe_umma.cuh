@@ -27,6 +27,7 @@ struct UmmaBucket {
     uint32_t row_tile0, n_row_tiles; // A blobs of this classifier bucket
     uint32_t col_tile0, n_col_tiles; // B blobs
     uint32_t row0, nrows;            // first global row (= 4 * first range position), valid rows
+    uint32_t ncols;                  // valid columns of the bucket's column tiles (meaningful when it meets one domain bucket)
     uint32_t chunks;                 // column chunks per row tile (work items = n_row_tiles * chunks)
 };
 

@@ -113,6 +113,7 @@ struct WorkItem {
     uint32_t row0;     // first global row of the tile
     uint32_t nrows;    // valid rows in the tile (<= 128)
     uint32_t t0, t1;   // column-tile range [t0, t1) of the B blob (may run over several adjacent domain buckets)
+    uint32_t cols_left;// span 0 only: valid columns from tile t0 to the end of the bucket's slice
 };
 
 __device__ __forceinline__ WorkItem decode_item(const UmmaArgs& a, uint32_t w) {
@@ -133,6 +134,7 @@ __device__ __forceinline__ WorkItem decode_item(const UmmaArgs& a, uint32_t w) {
     it.nrows = min((uint32_t)UM_ROWS, b.nrows - rt * UM_ROWS);
     it.t0 = b.col_tile0 + lt0;
     it.t1 = b.col_tile0 + lt1;
+    it.cols_left = b.ncols - lt0 * a.nt;
     return it;
 }
 
