@@ -752,6 +752,7 @@ int umma_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item*
     a.use_thr = use_thr ? 1u : 0u;
     a.nt = UM_NT;
     a.rowslot = sp.rowslot;
+    a.meta = sp.span > 0 ? 1u : 0u;
     a.no_min = sp.no_min ? 1u : 0u;
     { const char* e = getenv("FE_UMMA_DBG"); a.dbg = e ? (uint32_t)atoi(e) : 0u; }
     const uint32_t stage_bytes = UM_NT * Kpad * 2, a_bytes = 2 * UM_ROWS * Kpad * 2;

@@ -174,16 +174,9 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_umma_i8(const UmmaA
                 const uint32_t u = first + j * UM_WGS, buf = jb & 1;
                 const uint32_t colbase = u * I8_NT + h * 32;             // column inside the item
                 const uint32_t taddr = lane_addr + (g * 2 + buf) * 2 * I8_NT;
-                const uint32_t seg = __ldg(a.tileseg + item.t0 + u);
-                if (seg != cur_seg) {
-                    // another domain bucket: its columns restart at low domain indices, so bank the first hit of the bucket
-                    // behind us and look for this bucket's
-                    if (hit != FE_NONE32) {
-                        atomicMin(&a.rowhit[srow], a.blob_dom[(size_t)item.t0 * I8_NT + hit]);
-                        hit = FE_NONE32;
-                    }
-                    cur_seg = seg;
-                }
+                // work items that run over several domain buckets (brightness bins): bucket id of the tile, loaded ahead of the
+                // accumulator wait and looked at after the accumulator has been read
+                const uint32_t seg = a.meta ? __ldg(a.tileseg + item.t0 + u) : 0u;
                 uint32_t lo[32], hi[32];
                 mbar_wait(ACC_FULL(g, buf), (jb >> 1) & 1);
                 tc_fence_after();
@@ -193,6 +186,15 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_umma_i8(const UmmaA
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ACC_EMPTY(g, buf));
+                if (a.meta && seg != cur_seg) {
+                    // another domain bucket: its columns restart at low domain indices, so bank the first hit of the bucket
+                    // behind us and look for this bucket's
+                    if (hit != FE_NONE32) {
+                        atomicMin(&a.rowhit[srow], a.blob_dom[(size_t)item.t0 * I8_NT + hit]);
+                        hit = FE_NONE32;
+                    }
+                    cur_seg = seg;
+                }
                 // sum(D^2) per column, stored by padded (tile, column) position so the 16-byte loads stay aligned
                 const uint4* cn4 = reinterpret_cast<const uint4*>(a.coln + (size_t)(item.t0 + u) * I8_NT + h * 32);
                 // w = sum D^2 - 8 (lo + 256 hi): two IMADs per column (FMA pipe), written over the low-plane registers
@@ -501,6 +503,7 @@ int umma_i8_prepare_and_search(fe_ctx* ctx, const LevelGeom& g, const fe_grid_it
     a.use_thr = use_thr ? 1u : 0u;
     a.nt = I8_NT;
     a.rowslot = sp.rowslot;
+    a.meta = sp.span > 0 ? 1u : 0u;
     a.no_min = sp.no_min ? 1u : 0u;
     const uint32_t stage_bytes = 2 * I8_NT * kc, a_bytes = UM_ROWS * Kpad;
     const uint32_t budget = 226 * 1024 - 512;

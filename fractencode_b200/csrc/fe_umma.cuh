@@ -51,6 +51,7 @@ struct UmmaArgs {
     uint32_t n_abuf;                 // i8 kind: A buffers in shared memory (2, or 1 when the tile is 128 KB)
     uint32_t dbg;                    // tuning probes (FE_UMMA_DBG): 1 skip TMEM drain, 2 skip MMA issue, 4 skip B copies
     const uint32_t* rowslot;         // [range position of this pass] -> range position of the level (result slot); NULL = identity
+    uint32_t meta;                   // work items may cross domain buckets: per-tile bucket ids matter
     uint32_t no_min;                 // only threshold hits are wanted (levels that split: a range without a hit is split and its
                                      // minimum never read) -- skip the running-minimum bookkeeping
 };
