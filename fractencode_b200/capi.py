@@ -42,6 +42,20 @@ class Stats(C.Structure):
                 ("evaluated", C.c_uint64), ("level_evaluated", C.c_uint64 * 8), ("level_passes", C.c_uint64 * 8)]
 
 
+class ThresholdPlan(C.Structure):
+    """fe_threshold_plan: how a threshold search is pruned (host-only planning, no GPU needed)."""
+    _fields_ = [("use_threshold", C.c_int32), ("thr16", C.c_uint32), ("radius", C.c_uint64), ("bin_width", C.c_uint32),
+                ("n_bins", C.c_uint32), ("bin_span", C.c_uint32)]
+
+
+def plan_threshold(rms_threshold: float, S: int, T: int) -> ThresholdPlan:
+    pl = ThresholdPlan()
+    rc = load_library().fe_plan_threshold(float(rms_threshold), int(S), int(T), C.byref(pl))
+    if rc != 0:
+        raise FractencodeError(rc, "fe_plan_threshold(%g, %d, %d)" % (rms_threshold, S, T))
+    return pl
+
+
 class FractencodeError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("fractencode_b200 error %d: %s" % (code, msg))
@@ -62,7 +76,7 @@ _LIB = None
 EXPORTS = [
     "fe_abi_version", "fe_create", "fe_destroy", "fe_last_error", "fe_set_image", "fe_set_images", "fe_set_image_device",
     "fe_classify", "fe_encode_level", "fe_encode_quadtree", "fe_encode_quadtree_device", "fe_fetch_items", "fe_device_items",
-    "fe_decode", "fe_copy_items", "fe_quantize", "fe_pack_items", "fe_unpack_items", "fe_get_stats", "fe_stats_reset", "fe_synchronize", "fe_set_synthetic_image", "fe_get_image",
+    "fe_decode", "fe_copy_items", "fe_quantize", "fe_pack_items", "fe_unpack_items", "fe_get_stats", "fe_stats_reset", "fe_synchronize", "fe_set_synthetic_image", "fe_get_image", "fe_plan_threshold",
 ]
 
 
@@ -101,6 +115,7 @@ def load_library():
         "fe_synchronize": (i32, [vp]),
         "fe_set_synthetic_image": (i32, [vp, u32, u32, C.c_uint64, i32]),
         "fe_get_image": (i32, [vp, vp, u32]),
+        "fe_plan_threshold": (i32, [C.c_double, u32, u32, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)

@@ -51,6 +51,36 @@ static bool threshold_n16(double thr, uint32_t S, uint32_t* out) {
     return true;
 }
 
+// Brightness bins of a threshold search (search_tc): radius of the Cauchy-Schwarz bound, bin width, bins, span.
+static void plan_bins(uint32_t N, uint32_t thr16, fe_threshold_plan* pl) {
+    const uint64_t nt = (uint64_t)N * thr16;
+    uint64_t R = (uint64_t)std::sqrt((double)nt);
+    while (R * R > nt) --R;
+    while ((R + 1) * (R + 1) <= nt) ++R;
+    const uint64_t maxsum = 1020ull * N;
+    // bins half as wide as the radius (a range then meets 5 bins = 2.5 radii instead of 3 bins = 3 radii), as long as
+    // FE_MAX_BUCKETS bins cover the value range; |sumA - sumB| <= R  =>  |binA - binB| <= floor(R / width) + 1
+    const uint64_t width = std::max<uint64_t>((R + 2) / 2, (maxsum + FE_MAX_BUCKETS) / FE_MAX_BUCKETS);
+    const int nbins = (int)(maxsum / width) + 1;
+    const int span = (int)(R / width) + 1;
+    pl->radius = R;
+    pl->bin_width = (uint32_t)width;
+    pl->bin_span = (uint32_t)span;
+    pl->n_bins = (nbins >= 2 * (2 * span + 1) && nbins <= FE_MAX_BUCKETS) ? (uint32_t)nbins : 0u;
+}
+
+extern "C" int fe_plan_threshold(double rms_threshold, uint32_t S, uint32_t T, fe_threshold_plan* out) {
+    if (!out || T < 2 || S <= T || S % T || T > 64) return FE_ERR_INVALID;
+    *out = fe_threshold_plan{};
+    if (rms_threshold * (double)(S * S) >= 1048576.0) return FE_ERR_UNSUPPORTED;   // fp32-rounding regime of the reference distance
+    uint32_t thr16 = 0;
+    if (!threshold_n16(rms_threshold, S, &thr16)) return FE_OK;
+    out->use_threshold = 1;
+    out->thr16 = thr16;
+    plan_bins(T * T, thr16, out);
+    return FE_OK;
+}
+
 // -------------------------------------------------------------------------------------------------
 // ctx
 // -------------------------------------------------------------------------------------------------
@@ -667,17 +697,11 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
         for (int c = 0; c <= nbuckets; ++c) { tb.doff[c] = doff[c]; tb.roff[c] = roff[c]; }
         // ---- brightness bins (threshold, no classifier): see search_tc ----
         if (use_thr && !p.use_classifier && nD && !getenv("FE_NO_BINS") && !getenv("FE_SINGLE_PASS")) {
-            const uint64_t nt = (uint64_t)g.N * thr16;
-            uint64_t R = (uint64_t)std::sqrt((double)nt);
-            while (R * R > nt) --R;
-            while ((R + 1) * (R + 1) <= nt) ++R;
-            const uint64_t maxsum = 1020ull * g.N;
-            // bins half as wide as the radius (a range then meets 5 bins = 2.5 radii instead of 3 bins = 3 radii), as long as
-            // 64 bins cover the value range; |sumA - sumB| <= R  =>  |binA - binB| <= floor(R / width) + 1
-            const uint64_t width = std::max<uint64_t>((R + 2) / 2, (maxsum + FE_MAX_BUCKETS) / FE_MAX_BUCKETS);
-            const int nbins = (int)(maxsum / width) + 1;
-            const int span = (int)(R / width) + 1;
-            if (nbins >= 2 * (2 * span + 1) && nbins <= FE_MAX_BUCKETS) {
+            fe_threshold_plan pl{};
+            plan_bins(g.N, thr16, &pl);
+            const uint64_t width = pl.bin_width;
+            const int nbins = (int)pl.n_bins, span = (int)pl.bin_span;
+            if (nbins) {
                 tb.span = span;
                 for (int k = 0; k < 8; ++k) tb.cut[k] = k == 7 ? nD : (uint32_t)(((uint64_t)nD << k) / 128 + 1);
                 FE_TRY(bucket_by_brightness(ctx, io, (uint32_t)width, nbins, tb.doff, tb.roff, tb.cut, tb.pre));

@@ -189,6 +189,19 @@ int fe_pack_items(fe_ctx* ctx, const fe_encode_item* items, size_t n, uint32_t t
 int fe_unpack_items(fe_ctx* ctx, const uint64_t* packed, size_t n, uint32_t t_max, int bits_s, int bits_o,
                     const double minmax[4], int fma, fe_encode_item* items_out);
 
+/* Host-only (no GPU, no ctx): how a threshold search of T x T range blocks against S x S domain blocks is planned.
+ * thr16 = the largest integer n16 = 16 * SSE whose reference distance double(float(n16 / 16)) / (S * S)
+ * (image/metrics.h:38-49) is <= rms_threshold (use_threshold = 0 when none is).  A candidate with n16 <= thr16 has
+ * |sum(4 r) - sum(D)| <= radius (Cauchy-Schwarz over the T*T pixels), so with blocks keyed by sum / bin_width it lies
+ * within bin_span bins of the range block's bin; n_bins = 0 when the bins would not prune (then they are not used). */
+typedef struct {
+    int32_t use_threshold;
+    uint32_t thr16;
+    uint64_t radius;
+    uint32_t bin_width, n_bins, bin_span;
+} fe_threshold_plan;
+int fe_plan_threshold(double rms_threshold, uint32_t S, uint32_t T, fe_threshold_plan* out);
+
 int fe_get_stats(const fe_ctx* ctx, fe_stats* out);
 int fe_stats_reset(fe_ctx* ctx);
 int fe_synchronize(fe_ctx* ctx);
