@@ -286,7 +286,13 @@ __global__ void __launch_bounds__(256) k_build_rows_i8(const uint8_t* __restrict
             if ((it.x & 3u) == 0) v = __ldg(reinterpret_cast<const uint32_t*>(p));
             else v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
             reinterpret_cast<uint32_t*>(sblk)[lr * wpb + e] = v;
-            atomicAdd(&s2[lr], __dp4a(v, v, 0u));
+            uint32_t q = __dp4a(v, v, 0u);
+            if ((wpb & 31u) == 0 && (nvalid * wpb) % blockDim.x == 0) {   // a warp lies inside one block: one atomic per warp
+                for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
+                if ((threadIdx.x & 31u) == 0) atomicAdd(&s2[lr], q);
+            } else {
+                atomicAdd(&s2[lr], q);
+            }
         }
     } else {
         for (uint32_t idx = threadIdx.x; idx < nvalid * N; idx += blockDim.x) {
