@@ -216,6 +216,7 @@ def run_b200(a):
         raise SystemExit("libfractencode_b200.so missing: run __graft_entry__.build() (no fallback path exists)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.current_stream()
     ctx = fb.Context(local, stream.cuda_stream)
