@@ -354,8 +354,8 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
             const uint32_t n = item.t1 - item.t0;
             const bool row_ok = lrow < item.nrows;
             const uint32_t grow = item.row0 + lrow;
-            const uint32_t a2 = (row_ok && !(a.dbg & 8)) ? a.rowA2[grow >> 2] : 0u;
-            const uint32_t srow = (row_ok && a.rowslot && !(a.dbg & 8)) ? 4u * a.rowslot[grow >> 2] + (grow & 3u) : grow;   // result slot of the level
+            const uint32_t a2 = row_ok ? a.rowA2[grow >> 2] : 0u;
+            const uint32_t srow = (row_ok && a.rowslot) ? 4u * a.rowslot[grow >> 2] + (grow & 3u) : grow;   // result slot of the level
             RowState st;
             st.bestV = 3.0e38f; st.bestp = 0; st.bestcol = FE_NONE32; st.hit = FE_NONE32;
             st.vthr0 = -3.0e38f; st.vthr1 = -3.0e38f;
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
                 }
             }
             it0 += n;
-            if (row_ok && !(a.dbg & 16)) {
+            if (row_ok) {
                 if (st.bestcol != FE_NONE32) {
                     if (st.bestp == 2) st.bestp = row_parity(st, st.bestcol);
                     const long long n16 = (long long)a2 + 2ll * (long long)st.bestV + (long long)st.bestp;
