@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--search", type=int, default=0, help="0 auto, 1 exact integer path, 2 tcgen05 path")
     ap.add_argument("--cpu-blocks", type=int, default=0, help="range blocks per level in the CPU sample (0: 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="images", choices=["images", "ranges"],
+                    help="N > 1: one image per GPU (weak scaling, default) or the range blocks of ONE image sharded over the GPUs "
+                         "(strong scaling, BASELINE config 4 in shape; the domain pool is rebuilt on every GPU)")
     return ap.parse_args()
 
 
@@ -207,7 +210,7 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
     import fractencode_b200 as fb
-    from fractencode_b200.dist import gather_item_lists
+    from fractencode_b200.dist import gather_item_lists, shard_slice
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -230,22 +233,37 @@ def run_b200(a):
     counts_t = torch.zeros(world, dtype=torch.int64, device="cuda")
     gather_buf = torch.empty(world * cap * 64, dtype=torch.uint8, device="cuda") if world > 1 else None
 
-    ctx.set_synthetic_image(W, H, 1234 + rank, 0)
+    by_ranges = a.shard == "ranges" and world > 1
+    ctx.set_synthetic_image(W, H, 1234 + (0 if by_ranges else rank), 0)
     host_img.copy_(torch.from_numpy(ctx.get_image()))
+    n_top = (W // a.tmax) * (H // a.tmax)
+    mine = shard_slice(n_top, rank, world)          # this rank's top-level range blocks when sharding by ranges
+    my_items = torch.empty(cap * 64, dtype=torch.uint8, device="cuda") if by_ranges else None
 
     def step_resident():
-        n = ctx.encode_quadtree_device(a.tmax, a.tmin, params)
+        if by_ranges:
+            n = ctx.encode_quadtree_slice_device(a.tmax, a.tmin, params, mine.start, mine.stop - mine.start)
+        else:
+            n = ctx.encode_quadtree_device(a.tmax, a.tmin, params)
         if world > 1:  # gather the per-rank transform lists (the only collective of the path)
             nptr = C.c_size_t(0)
             ptr = lib.fe_device_items(ctx.h, C.byref(nptr))
-            items = torch.as_tensor(DevArray(ptr, cap * 64), device="cuda")
+            if by_ranges:   # the shard's list lives in a buffer sized for the shard: stage it in a full-capacity one
+                my_items[: n * 64].copy_(torch.as_tensor(DevArray(ptr, max(n, 1) * 64), device="cuda")[: n * 64])
+                items = my_items
+            else:
+                items = torch.as_tensor(DevArray(ptr, cap * 64), device="cuda")
             gather_item_lists(items, n, cap, counts_t, gather_buf)
         return n
 
     def step_e2e():
         ctx.set_image(host_img.numpy())  # pinned host -> device on the ctx stream
         n = C.c_size_t(0)
-        rc = lib.fe_encode_quadtree(ctx.h, a.tmax, a.tmin, C.byref(params), host_items.data_ptr(), cap, C.byref(n), None)
+        if by_ranges:
+            n = C.c_size_t(ctx.encode_quadtree_slice_device(a.tmax, a.tmin, params, mine.start, mine.stop - mine.start))
+            rc = lib.fe_fetch_items(ctx.h, host_items.data_ptr(), cap, C.byref(n))
+        else:
+            rc = lib.fe_encode_quadtree(ctx.h, a.tmax, a.tmin, C.byref(params), host_items.data_ptr(), cap, C.byref(n), None)
         if rc != 0:
             raise fb.FractencodeError(rc, lib.fe_last_error(ctx.h).decode())
         return n.value
@@ -356,14 +374,16 @@ def run_b200(a):
         traffic_by_T = TRAFFIC_BY_T if (a.size, a.tmax, a.tmin, a.thr, a.classifier) == (4096, 32, 4, 25.0, 0) else {}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if by_ranges else "weak", "vs_baseline": None,
             "dtype": "u8 in, fp16 operands / fp32 (integer-exact) accumulate, int32 scores, f64 s/o",
             "data": "synthetic",
-            "config": {"workload": workload_name(a), "images_per_step": world, "l2": "flushed between timed steps (512 MiB fill)",
+            "config": {"workload": workload_name(a), "images_per_step": 1 if by_ranges else world,
+                       "sharding": "top-level range blocks of one image over the GPUs, pool rebuilt per GPU" if by_ranges else "one image per GPU",
+                       "l2": "flushed between timed steps (512 MiB fill)",
                        "search_impl": ["auto", "exact-int (dp4a)", "tcgen05"][a.search], "pruning": PRUNING_NOTE},
-            "mpix_per_s": world * W * H / 1e6 / (ms_per_step * 1e-3),
+            "mpix_per_s": (1 if by_ranges else world) * W * H / 1e6 / (ms_per_step * 1e-3),
             "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": W * H, "d2h_bytes_per_step": int(e_items) * 64,
-                    "ms_per_step": e_ms / a.steps, "mpix_per_s": world * W * H / 1e6 / (e_ms / a.steps * 1e-3)},
+                    "ms_per_step": e_ms / a.steps, "mpix_per_s": (1 if by_ranges else world) * W * H / 1e6 / (e_ms / a.steps * 1e-3)},
             "gpu_launches": launches,
             "items_per_step": all_items,
             "evaluated_matches_per_step": evaluated_step,

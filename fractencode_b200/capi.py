@@ -75,7 +75,7 @@ def build_library() -> str:
 _LIB = None
 EXPORTS = [
     "fe_abi_version", "fe_create", "fe_destroy", "fe_last_error", "fe_set_image", "fe_set_images", "fe_set_image_device",
-    "fe_classify", "fe_encode_level", "fe_encode_quadtree", "fe_encode_quadtree_device", "fe_fetch_items", "fe_device_items",
+    "fe_classify", "fe_encode_level", "fe_encode_quadtree", "fe_encode_quadtree_device", "fe_encode_quadtree_slice_device", "fe_fetch_items", "fe_device_items",
     "fe_decode", "fe_copy_items", "fe_quantize", "fe_pack_items", "fe_unpack_items", "fe_get_stats", "fe_stats_reset", "fe_synchronize", "fe_set_synthetic_image", "fe_get_image", "fe_plan_threshold",
 ]
 
@@ -103,6 +103,7 @@ def load_library():
         "fe_encode_level": (i32, [vp, vp, sz, vp, sz, C.POINTER(Params), vp]),
         "fe_encode_quadtree": (i32, [vp, u32, u32, C.POINTER(Params), vp, sz, C.POINTER(sz), vp]),
         "fe_encode_quadtree_device": (i32, [vp, u32, u32, C.POINTER(Params), C.POINTER(sz)]),
+        "fe_encode_quadtree_slice_device": (i32, [vp, u32, u32, C.POINTER(Params), sz, sz, C.POINTER(sz)]),
         "fe_fetch_items": (i32, [vp, vp, sz, C.POINTER(sz)]),
         "fe_device_items": (vp, [vp, C.POINTER(sz)]),
         "fe_decode": (i32, [vp, vp, sz, vp, u32, u32, u32, i32, dbl, i32, C.POINTER(C.c_int), C.POINTER(dbl)]),
@@ -227,6 +228,12 @@ class Context:
     def encode_quadtree_device(self, t_max: int, t_min: int, params: Params) -> int:
         n = C.c_size_t(0)
         self._check(self.lib.fe_encode_quadtree_device(self.h, t_max, t_min, C.byref(params), C.byref(n)))
+        return n.value
+
+    def encode_quadtree_slice_device(self, t_max: int, t_min: int, params: Params, first_block: int, n_blocks: int) -> int:
+        """One shard of the quadtree encode: top-level range blocks first_block..+n_blocks of the whole image's grid."""
+        n = C.c_size_t(0)
+        self._check(self.lib.fe_encode_quadtree_slice_device(self.h, t_max, t_min, C.byref(params), first_block, n_blocks, C.byref(n)))
         return n.value
 
     def fetch_items(self, out: np.ndarray | None = None) -> np.ndarray:

@@ -883,6 +883,11 @@ extern "C" int fe_encode_level(fe_ctx* ctx, const fe_grid_item* domains, size_t 
 // quadtree
 // -------------------------------------------------------------------------------------------------
 extern "C" int fe_encode_quadtree_device(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params, size_t* n_out) {
+    return fe_encode_quadtree_slice_device(ctx, t_max, t_min, params, 0, (size_t)-1, n_out);
+}
+
+extern "C" int fe_encode_quadtree_slice_device(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params, size_t first_block,
+                                               size_t n_blocks, size_t* n_out) {
     if (!ctx) return FE_ERR_INVALID;
     if (!params) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_quadtree: params is NULL");
     if (!ctx->src.px) return fe_fail(ctx, FE_ERR_STATE, "fe_encode_quadtree: call fe_set_image first");
@@ -892,12 +897,19 @@ extern "C" int fe_encode_quadtree_device(fe_ctx* ctx, uint32_t t_max, uint32_t t
         return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_encode_quadtree: block sizes must be powers of two, 2 <= t_min <= t_max <= 64");
     if (W % t_max || H % t_max) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_quadtree: image %ux%u not aligned to %u", W, H, t_max);
     FE_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t cap = (size_t)(W / t_min) * (H / t_min);
+    const size_t n_top = (size_t)(W / t_max) * (H / t_max);
+    if (n_blocks == (size_t)-1) n_blocks = first_block <= n_top ? n_top - first_block : 0;
+    if (first_block > n_top || n_blocks > n_top - first_block)
+        return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_quadtree_slice: blocks %zu..+%zu outside the %zu top-level blocks", first_block, n_blocks, n_top);
+    const size_t per_top = (size_t)(t_max / t_min) * (t_max / t_min);
+    const size_t cap = std::max<size_t>(n_blocks * per_top, 1);
     FE_CUDA(ctx, ctx->b_items.ensure(cap * sizeof(fe_encode_item)));
-    size_t n_pending = (size_t)(W / t_max) * (H / t_max);
+    size_t n_pending = n_blocks;
     FE_CUDA(ctx, ctx->b_rng.ensure(cap * sizeof(fe_grid_item)));
     FE_CUDA(ctx, ctx->b_rng_next.ensure(cap * sizeof(fe_grid_item)));
-    LAUNCH(ctx, k_uniform_grid, cdiv(n_pending, 256), 256, ctx->b_rng.as<fe_grid_item>(), W / t_max, (uint32_t)n_pending, t_max, t_max);
+    if (n_pending)
+        LAUNCH(ctx, k_uniform_grid, cdiv(n_pending, 256), 256, ctx->b_rng.as<fe_grid_item>(), W / t_max, (uint32_t)n_pending, t_max, t_max,
+               (uint32_t)first_block);
     for (int l = 0; l < 8; ++l) {
         ctx->stats.level_items[l] = ctx->stats.level_ranges[l] = ctx->stats.level_matches[l] = 0;
         ctx->stats.level_search_ms[l] = ctx->stats.level_prep_ms[l] = 0.f;
@@ -912,7 +924,7 @@ extern "C" int fe_encode_quadtree_device(fe_ctx* ctx, uint32_t t_max, uint32_t t
         FE_TRY(make_geom(ctx, S, T, true, &io.g));
         if (nD) {
             FE_CUDA(ctx, ctx->b_dom.ensure(nD * sizeof(fe_grid_item)));
-            LAUNCH(ctx, k_uniform_grid, cdiv(nD, 256), 256, ctx->b_dom.as<fe_grid_item>(), dnx, (uint32_t)nD, S, T);
+            LAUNCH(ctx, k_uniform_grid, cdiv(nD, 256), 256, ctx->b_dom.as<fe_grid_item>(), dnx, (uint32_t)nD, S, T, 0u);
         }
         FE_CUDA(ctx, ctx->b_level_items.ensure(n_pending * sizeof(fe_encode_item)));
         FE_CUDA(ctx, ctx->b_split.ensure(n_pending * 4 + 4));

@@ -75,12 +75,12 @@ __device__ __forceinline__ uint32_t block_sum_dev(const uint8_t* __restrict__ im
 // ---------------------------------------------------------------------------------------------
 // grids (image/partition2.hpp:110-135) and quadtree children (partition2.hpp:18-30)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_uniform_grid(fe_grid_item* out, uint32_t nx, uint32_t n, uint32_t size, uint32_t step) {
+__global__ void k_uniform_grid(fe_grid_item* out, uint32_t nx, uint32_t n, uint32_t size, uint32_t step, uint32_t first) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fe_grid_item it;
-    it.x = (i % nx) * step;
-    it.y = (i / nx) * step;
+    it.x = ((first + i) % nx) * step;
+    it.y = ((first + i) / nx) * step;
     it.w = size;
     it.h = size;
     it.bin = -1;

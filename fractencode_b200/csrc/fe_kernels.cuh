@@ -27,7 +27,7 @@ struct FinalizeArgs {
     int hit_is_domain;              // rowhit holds domain indices (tcgen05 paths), not sorted column positions (exact path)
 };
 
-__global__ void k_uniform_grid(fe_grid_item* out, uint32_t nx, uint32_t n, uint32_t size, uint32_t step);
+__global__ void k_uniform_grid(fe_grid_item* out, uint32_t nx, uint32_t n, uint32_t size, uint32_t step, uint32_t first);
 __global__ void k_quadtree_scatter(const fe_grid_item* rng, const fe_encode_item* level_items, const uint32_t* split,
                                    const uint32_t* scan, uint32_t n, fe_grid_item* next, fe_encode_item* items_out);
 __global__ void k_classify(const uint8_t* img, uint32_t stride, const fe_grid_item* items, uint32_t n, int32_t* cls, int force);

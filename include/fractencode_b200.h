@@ -149,6 +149,12 @@ int fe_encode_quadtree(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_par
  * kernel-only timing); fetch with fe_fetch_items. */
 int fe_encode_quadtree_device(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params,
                               size_t* n_out);
+/* One shard of the same search (range blocks sharded across GPUs, pool replicated): only the top-level range
+ * blocks first_block .. first_block + n_blocks - 1 of createUniformGrid(t_max, t_max) order (x fastest) are encoded -- they
+ * and their descendants, against the domains of the WHOLE image.  The shards of a partition of the top-level grid together
+ * give exactly the transform list of fe_encode_quadtree (range blocks are independent). */
+int fe_encode_quadtree_slice_device(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params,
+                                    size_t first_block, size_t n_blocks, size_t* n_out);
 int fe_fetch_items(fe_ctx* ctx, fe_encode_item* out, size_t cap, size_t* n_out);
 /* Device pointer to the last result list (n items of 64 bytes), valid until the next encode. */
 const void* fe_device_items(const fe_ctx* ctx, size_t* n_out);

@@ -101,3 +101,28 @@ def test_first_hit_is_first_in_scan_order_across_bins(ctx, fo):
     want = fo.encode_level(img, img, dom, rng, fo.params(100.0))
     assert_items_equal(got, want, "flat image")
     assert (got["match_x"] == 0).all() and (got["match_y"] == 0).all() and (got["transform"] == 0).all()
+
+
+@pytest.mark.parametrize("cls", [False, True])
+def test_quadtree_slices_give_the_whole_transform_list(ctx, cls):
+    """Range sharding: the shards of a partition of the top-level grid, each searched against the domains of the
+    whole image, together are exactly the transform list of the whole image."""
+    import fractencode_b200 as fb
+    from fractencode_b200.dist import shard_slice
+    W, H = 1024, 512
+    ctx.set_synthetic_image(W, H, 99, 0)
+    p = fb.Params(20.0, -1.0, cls)
+    whole, counts = ctx.encode_quadtree(32, 4, p)
+    n_top = (W // 32) * (H // 32)
+    parts = []
+    for r in range(3):
+        sl = shard_slice(n_top, r, 3)
+        n = ctx.encode_quadtree_slice_device(32, 4, p, sl.start, sl.stop - sl.start)
+        got = ctx.fetch_items()
+        assert len(got) == n
+        parts.append(got.copy())
+    assert sum(len(x) for x in parts) == len(whole)
+    assert_items_equal(np.concatenate(parts), whole, "union of three shards")
+    assert ctx.encode_quadtree_slice_device(32, 4, p, n_top, 0) == 0
+    with pytest.raises(fb.FractencodeError):
+        ctx.encode_quadtree_slice_device(32, 4, p, n_top - 1, 2)
