@@ -402,7 +402,8 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
     const bool pass_dbg = getenv("FE_PASS_DBG") != nullptr;
     const bool multipass = use_thr && !single_pass;
     const uint32_t GR = 128;                                              // slice granularity: whole column tiles of both kinds
-    const uint32_t min_step = (tb.bins ? std::max(3, 16 / (2 * tb.span + 1)) : 16) * GR;   // columns a bucket advances per pass at
+    const char* ms_env = getenv("FE_MIN_STEP");                          // tuning: column tiles a bucket advances per pass at least
+    const uint32_t min_step = (ms_env ? (uint32_t)std::max(1, atoi(ms_env)) : (tb.bins ? std::max(2, 10 / (2 * tb.span + 1)) : 16)) * GR;   // columns a bucket advances per pass at
                                                                           // least (a work item spans 2*span+1 buckets with bins)
     LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
     LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
