@@ -1090,8 +1090,9 @@ extern "C" int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uin
             const size_t cnt = goff[gidx + 1] - goff[gidx];
             if (!cnt) continue;
             if (tiled[gidx]) {
-                k_decode_step_tiled<<<cdiv(cnt, 8), 256, 8 * T * T * sizeof(uint16_t), ctx->stream>>>(src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T,
-                                                                                                    use_fma, fused_sq ? d_sum : nullptr);
+                if (!launch_decode_step_small(ctx->stream, src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T, use_fma, fused_sq ? d_sum : nullptr))
+                    k_decode_step_tiled<<<cdiv(cnt, 8), 256, 8 * T * T * sizeof(uint16_t), ctx->stream>>>(src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T,
+                                                                                                        use_fma, fused_sq ? d_sum : nullptr);
                 ctx->stats.kernel_launches++;
                 FE_CUDA(ctx, cudaGetLastError());
             } else {

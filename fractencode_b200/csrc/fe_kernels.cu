@@ -751,6 +751,104 @@ __global__ void __launch_bounds__(256) k_decode_step_tiled(const uint8_t* __rest
     }
 }
 
+// Same gather for the small blocks (T = 4: eight items per warp, T = 8: four): a warp per item leaves most lanes idle there and
+// chains item load -> source loads -> store once per item; here a warp fetches IPW item records with one coalesced read,
+// issues all its source loads before it touches any of them, and every lane has output work.
+template <int T, int IPW>
+__global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t stride,
+                                                           const fe_encode_item* __restrict__ items, uint32_t n_items, int use_fma,
+                                                           unsigned long long* __restrict__ sq_out) {
+    constexpr int N = T * T, S = 2 * T, WPR = S / 4, UNITS = T * WPR;       // row-pair words per item
+    constexpr int U = (IPW * UNITS + 31) / 32;                                // load units per lane
+    constexpr int SEGS = T / 4, OUT = T * SEGS, Q = (IPW * OUT + 31) / 32;    // 4-pixel output segments per item / per lane
+    __shared__ __align__(16) fe_encode_item sitem[8][IPW];
+    __shared__ __align__(16) uint16_t sbox[8][IPW][N];
+    const uint32_t warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t first = (blockIdx.x * 8 + warp_in_block) * IPW;
+    unsigned long long sq = 0;
+    if (first < n_items) {
+        const uint32_t cnt = min((uint32_t)IPW, n_items - first);
+        // item records: 4 x 16 bytes each, one coalesced read
+        for (uint32_t q = lane; q < cnt * 4; q += 32)
+            reinterpret_cast<uint4*>(&sitem[warp_in_block][0])[q] = __ldg(reinterpret_cast<const uint4*>(items + first) + q);
+        __syncwarp();
+        // all source loads first, then the box sums
+        uint32_t r0[U], r1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t idx = lane + 32 * u, k = idx / UNITS, w = idx % UNITS;
+            r0[u] = r1[u] = 0;
+            if (k < cnt) {
+                const fe_encode_item& e = sitem[warp_in_block][k];
+                const uint8_t* p = src + (size_t)(e.match_y + 2 * (w / WPR)) * stride + e.match_x + 4 * (w % WPR);
+                r0[u] = __ldg(reinterpret_cast<const uint32_t*>(p));
+                r1[u] = __ldg(reinterpret_cast<const uint32_t*>(p + stride));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t idx = lane + 32 * u, k = idx / UNITS, w = idx % UNITS;
+            if (k < cnt) {
+                const uint32_t dd = (r0[u] & 0x00FF00FFu) + ((r0[u] >> 8) & 0x00FF00FFu) + (r1[u] & 0x00FF00FFu) + ((r1[u] >> 8) & 0x00FF00FFu);
+                *reinterpret_cast<uint32_t*>(&sbox[warp_in_block][k][(w / WPR) * T + 2 * (w % WPR)]) = dd;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int qq = 0; qq < Q; ++qq) {
+            const uint32_t idx = lane + 32 * qq, k = idx / OUT, q = idx % OUT;
+            if (k >= cnt) continue;
+            const fe_encode_item& e = sitem[warp_in_block][k];
+            const uint16_t* box = sbox[warp_in_block][k];
+            const int t = e.transform;
+            const int m0 = kMapDev[t][0], m1 = kMapDev[t][1], m4 = kMapDev[t][4], m5 = kMapDev[t][5];
+            const int cx = (kMapDev[t][2] + kMapDev[t][3]) * (S - 1), cy = (kMapDev[t][6] + kMapDev[t][7]) * (S - 1);
+            const int ax = (m0 + m1) < 0 ? -1 : 0, ay = (m4 + m5) < 0 ? -1 : 0;     // min corner of the mapped 2x2 box
+            const uint32_t y = q / SEGS, x0 = (q % SEGS) * 4;
+            const double cs = e.contrast, br = e.brightness;
+            uint32_t packed = 0;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int lx = 2 * (int)(x0 + kk), ly = 2 * (int)y;
+                const int gx = m0 * lx + m1 * ly + cx + ax, gy = m4 * lx + m5 * ly + cy + ay;
+                const double smp = (double)box[(gy >> 1) * T + (gx >> 1)] * 0.25;
+                const double v = use_fma ? __fma_rn(cs, smp, br) : __dadd_rn(__dmul_rn(cs, smp), br);
+                const uint32_t b = v < 0.0 ? 0u : (v > 255.0 ? 255u : (uint32_t)(uint8_t)v);
+                packed |= b << (8 * kk);
+            }
+            const size_t off = (size_t)(e.y + y) * stride + e.x + x0;
+            *reinterpret_cast<uint32_t*>(dst + off) = packed;
+            if (sq_out) {
+                const uint32_t old = __ldg(reinterpret_cast<const uint32_t*>(src + off));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int d = (int)((old >> (8 * kk)) & 255u) - (int)((packed >> (8 * kk)) & 255u);
+                    sq += (unsigned long long)(d * d);
+                }
+            }
+        }
+    }
+    if (sq_out) { // one atomic per block, spread over 64 slots
+        __shared__ unsigned long long wsum[8];
+        for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+        if (lane == 0) wsum[warp_in_block] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long tot = 0;
+            for (uint32_t w = 0; w < 8; ++w) tot += wsum[w];
+            if (tot) atomicAdd(sq_out + (blockIdx.x & 63u), tot);
+        }
+    }
+}
+
+bool launch_decode_step_small(cudaStream_t stream, const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items, uint32_t n,
+                              uint32_t T, int use_fma, unsigned long long* sq_out) {
+    if (T == 4) k_decode_step_small<4, 8><<<(n + 63) / 64, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out);
+    else if (T == 8) k_decode_step_small<8, 4><<<(n + 31) / 32, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out);
+    else return false;
+    return true;
+}
+
 // sum over the plane of (a-b)^2 as uint64 (the reference accumulates in int32, metrics.h:27; the
 // host wraps the 64-bit sum to int32 to reproduce it).
 __global__ void k_sqdiff(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t w, uint32_t h, uint32_t stride,

@@ -51,6 +51,8 @@ __global__ void k_decode_step(const uint8_t* src, uint8_t* dst, uint32_t stride,
                               const uint32_t* pix_off, uint32_t n_items, uint32_t total_pix, int use_fma);
 __global__ void k_decode_step_uniform(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items,
                                       uint32_t n_items, uint32_t T, int use_fma, unsigned long long* sq_out);
+bool launch_decode_step_small(cudaStream_t stream, const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items, uint32_t n,
+                              uint32_t T, int use_fma, unsigned long long* sq_out);
 __global__ void k_decode_step_tiled(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items, uint32_t n_items,
                                     uint32_t T, int use_fma, unsigned long long* sq_out);
 __global__ void k_sqdiff(const uint8_t* a, const uint8_t* b, uint32_t w, uint32_t h, uint32_t stride, unsigned long long* out);
