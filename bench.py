@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram bytes (read + write) of all search launches of a level of the default workload, from ncu (None: not captured yet)
-TRAFFIC_BY_T = {32: 176.1e6, 16: 175.3e6, 8: 732.5e6, 4: 166.6e6}   # profiles/search_kernels_r1b.md
+TRAFFIC_BY_T = {32: 178.5e6, 16: 177.8e6, 8: 735.0e6, 4: 166.9e6}   # profiles/search_kernels_r1b.md
 
 METRIC = "range_block_matches_per_s"
 UNIT = "matches/s"
@@ -40,7 +40,7 @@ UNIT = "matches/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=4096)
