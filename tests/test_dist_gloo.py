@@ -25,13 +25,14 @@ WORKER = textwrap.dedent("""
     mine["x"] = units[sl] * 4
     mine["y"] = rank
     mine["distance"] = units[sl] * 0.5
-    cap = 32
+    cap = 2048
     buf = torch.zeros(cap * 64, dtype=torch.uint8)
     buf[: mine.nbytes] = torch.from_numpy(np.frombuffer(mine.tobytes(), np.uint8).copy())
     counts, gathered = gather_item_lists(buf, len(mine), cap)
     lists = unpack_gathered(counts, gathered, ENCODE_ITEM)
     allitems = np.concatenate(lists)
     assert counts.tolist() == [19, 18], counts
+    assert tuple(gathered.shape) == (2, 1024 * 64), gathered.shape   # blocks of the largest count (rounded), not of the capacity
     assert (allitems["x"] == units * 4).all()
     assert (allitems["distance"] == units * 0.5).all()
     assert [int(l["y"][0]) for l in lists] == [0, 1]
