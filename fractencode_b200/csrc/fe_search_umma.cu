@@ -273,6 +273,11 @@ __global__ void __launch_bounds__(UM_THREADS_F16, 1) k_search_umma(const UmmaArg
             bool mm_had_tiles = false;
             auto next_item = [&](Cursor& c, bool is_mm) {
                 if (is_mm) {
+                    // An issuer without a tile in this item (fewer than four column tiles) must not sign it off before the
+                    // item's A tile has even been loaded: it could run two items ahead and arrive twice on the same
+                    // A_EMPTY phase, releasing a buffer whose MMAs are still in flight.  Waiting for A_FULL of the item
+                    // orders it behind the completion of the item two back, like the issuers that do have tiles.
+                    if (!mm_had_tiles) mbar_wait(A_FULL(c.wi & 1), (c.wi >> 1) & 1);
                     if (mm_had_tiles) tc_commit(A_EMPTY(c.wi & 1)); else mbar_arrive(A_EMPTY(c.wi & 1));
                     mm_had_tiles = false;
                     if (warp == 0) { load_A(true); pend_A = c.wi + 2; }         // (an older refill still posted: finish it first)
