@@ -126,3 +126,18 @@ def test_quadtree_slices_give_the_whole_transform_list(ctx, cls):
     assert ctx.encode_quadtree_slice_device(32, 4, p, n_top, 0) == 0
     with pytest.raises(fb.FractencodeError):
         ctx.encode_quadtree_slice_device(32, 4, p, n_top - 1, 2)
+
+
+def test_short_work_items_many_small_buckets(ctx):
+    """Classifier buckets with fewer than four column tiles: work items in which some MMA issuers have no tile at all (a
+    release/reuse race of the A-tile buffers showed up here as winners that failed the self-check, found by
+    tools/stress_pruning.py).  Repeated, because a race does not fail every time."""
+    import fractencode_b200 as fb
+    W, H = 512, 768
+    ctx.set_synthetic_image(W, H, 434051177, 0)
+    p = fb.Params(31.10872017449507, -1.0, True)
+    with _Env(FE_SINGLE_PASS="1"):
+        want, _ = ctx.encode_quadtree(32, 8, p)
+    for rep in range(12):
+        got, _ = ctx.encode_quadtree(32, 8, p)
+        assert_items_equal(got, want, "repetition %d" % rep)
