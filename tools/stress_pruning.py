@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised A/B of the pruned threshold search against the plain one-pass search (FE_SINGLE_PASS=1) and, on small images,
 against the exact integer (dp4a) kernel, bit for bit.
-usage: stress_pruning.py [seconds] [seed]"""
+usage: stress_pruning.py [seconds] [seed] [max edge / 64]"""
 import os
 import sys
 import time
@@ -14,13 +14,14 @@ from oracle import pyoracle as po  # noqa: E402  (sort_items only)
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 rs = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+max_blocks = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 FIELDS = ("x", "y", "w", "h", "match_x", "match_y", "src_w", "src_h", "transform")
 t0 = time.time()
 runs = 0
 with fb.Context(0) as ctx:
     while time.time() - t0 < budget:
-        W = int(rs.integers(2, 17)) * 64
-        H = int(rs.integers(2, 17)) * 64
+        W = int(rs.integers(2, max_blocks + 1)) * 64
+        H = int(rs.integers(2, max_blocks + 1)) * 64
         kind = int(rs.integers(0, 3))
         tmax = int(rs.choice([8, 16, 32, 64]))
         tmin = int(rs.choice([t for t in (4, 8, 16, 32) if t <= tmax]))
