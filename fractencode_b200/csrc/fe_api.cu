@@ -131,7 +131,7 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
                       &ctx->b_rowc, &ctx->b_coln, &ctx->b_rowbest, &ctx->b_rowhit, &ctx->b_hist, &ctx->b_level_items, &ctx->b_split,
                       &ctx->b_scan, &ctx->b_scan_tmp, &ctx->b_rng_next, &ctx->b_counters, &ctx->b_A16, &ctx->b_B16, &ctx->b_tmaps,
                       &ctx->b_items, &ctx->b_dec_a, &ctx->b_dec_b, &ctx->b_dec_items, &ctx->b_dec_sum, &ctx->b_q, &ctx->b_bound,
-                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_act[0], &ctx->b_act[1], &ctx->b_act_items, &ctx->b_act_flags, &ctx->b_act_tmp};
+                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_act[0], &ctx->b_act[1], &ctx->b_act_items, &ctx->b_act_flags, &ctx->b_act_tmp, &ctx->b_dom_order2, &ctx->b_rng_order2};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
@@ -375,14 +375,18 @@ static int rerank_fp32_regime(fe_ctx* ctx, const LevelIO& io, const fe_params& p
 //    level can split, where a range without a hit is split and its minimum is never looked at (Encoder2 quadtree rule).
 // Hits are recorded as DOMAIN indices (atomicMin), so "first in scan order" holds across bins, slices and column chunks.
 struct TcBuckets {
-    int nb = 1;
+    int nb = 1;                            // buckets of one group (one search launch)
+    int ngroups = 1;                       // groups: 1, or the classifier classes when brightness bins run inside every class
     const uint32_t* dom_order = nullptr;   // position -> domain index, ascending inside a bucket
     const uint32_t* rng_order = nullptr;   // position -> range index
-    uint32_t doff[FE_MAX_BUCKETS + 1] = {0}, roff[FE_MAX_BUCKETS + 1] = {0};
-    bool bins = false;                     // brightness bins: range bucket c pairs with the domain buckets c-span .. c+span
+    uint32_t doff[FE_MAX_TOTAL + 1] = {0}, roff[FE_MAX_TOTAL + 1] = {0};   // bucket (group g, c) = entry g * nb + c
+    bool bins = false;                     // brightness bins: range bucket c pairs with the domain buckets c-span .. c+span of its group
     int span = 0;
     uint32_t cut[8] = {0};                 // bins: domain-index cutoffs of the slice schedule (fractions 2^k / 128 of the scan)
-    uint32_t pre[FE_MAX_BUCKETS][8] = {};  // bins: positions of bucket b below cut[k]
+    uint32_t pre[FE_MAX_TOTAL][8] = {};    // bins: positions of a bucket below cut[k]
+    // bins inside classifier classes: the class-only order (domain index ascending inside a class) for the minimum pass
+    const uint32_t* grp_dom_order = nullptr;
+    uint32_t grp_doff[FE_MAX_GROUPS + 1] = {0};
 };
 
 struct TcSearchResult {
@@ -397,7 +401,7 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
                      TcSearchResult* res) {
     const LevelGeom& g = io.g;
     const uint32_t nR = io.nR, nD = io.nD;
-    const int nb = tb.nb;
+    const int nb = tb.nb, nbt = tb.nb * tb.ngroups;                      // buckets per group / of the level
     const bool single_pass = getenv("FE_SINGLE_PASS") != nullptr;         // tuning / A-B switch: never slice the scan
     const bool pass_dbg = getenv("FE_PASS_DBG") != nullptr;
     const bool multipass = use_thr && !single_pass;
@@ -408,13 +412,16 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
     LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
     LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));
-    FE_CUDA(ctx, ctx->b_hist.ensure((FE_MAX_BUCKETS + 8) * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_hist.ensure((FE_MAX_TOTAL + 8) * sizeof(uint32_t)));
     uint32_t* d_cnt = ctx->b_hist.as<uint32_t>();
-    uint32_t* d_nsel = d_cnt + FE_MAX_BUCKETS;
+    uint32_t* d_nsel = d_cnt + FE_MAX_TOTAL;
 
-    uint32_t dc[FE_MAX_BUCKETS], done[FE_MAX_BUCKETS], aoff[FE_MAX_BUCKETS + 1];
-    for (int c = 0; c < nb; ++c) { dc[c] = tb.doff[c + 1] - tb.doff[c]; done[c] = 0; }
-    for (int c = 0; c <= nb; ++c) aoff[c] = tb.roff[c];
+    std::vector<uint32_t> dc(nbt), done(nbt, 0), aoff(nbt + 1), lo(nbt), hi(nbt), host(FE_MAX_TOTAL + 1);
+    for (int c = 0; c < nbt; ++c) dc[c] = tb.doff[c + 1] - tb.doff[c];
+    for (int c = 0; c <= nbt; ++c) aoff[c] = tb.roff[c];
+    // neighbours of bucket idx inside its group: [nlo(idx), nhi(idx)]
+    auto nlo = [&](int idx) { return (idx / nb) * nb + std::max(0, idx % nb - tb.span); };
+    auto nhi = [&](int idx) { return (idx / nb) * nb + std::min(nb - 1, idx % nb + tb.span); };
     const uint32_t* items = tb.rng_order; // range position of the pass -> range item
     const uint32_t* slots = nullptr;      // range position of the pass -> range position of the level
     uint32_t nA = nR;
@@ -424,22 +431,21 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
     bool open_left = true;                // some range may still be without a hit
     uint32_t done_cutoff = 0;             // every admissible domain below this index has been scored for the ranges still listed
     *res = TcSearchResult{};
-    uint32_t host[FE_MAX_BUCKETS + 1];
 
     // survivors of the current list (positions whose best hit is not below `cutoff`), compacted; updates the list state
     auto survivors = [&](uint32_t cutoff, bool read_inexact, bool* inexact, uint32_t* n_left) -> int {
         FE_CUDA(ctx, ctx->b_act_flags.ensure((size_t)nA + 16));
-        FE_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, FE_MAX_BUCKETS * sizeof(uint32_t), ctx->stream));
-        BucketOff o;
-        for (int c = 0; c <= FE_MAX_BUCKETS; ++c) o.v[c] = aoff[std::min(c, nb)];
-        LAUNCH(ctx, k_unresolved, cdiv(nA, 256), 256, slots, ctx->b_rowhit.as<uint32_t>(), nA, o, nb, cutoff, ctx->b_act_flags.as<uint8_t>(), d_cnt);
-        FE_CUDA(ctx, cudaMemcpyAsync(host, d_cnt, FE_MAX_BUCKETS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        FE_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)nbt * sizeof(uint32_t), ctx->stream));
+        TotalOff o;
+        for (int c = 0; c <= FE_MAX_TOTAL; ++c) o.v[c] = aoff[std::min(c, nbt)];
+        LAUNCH(ctx, k_unresolved, cdiv(nA, 256), 256, slots, ctx->b_rowhit.as<uint32_t>(), nA, o, nbt, cutoff, ctx->b_act_flags.as<uint8_t>(), d_cnt);
+        FE_CUDA(ctx, cudaMemcpyAsync(host.data(), d_cnt, (size_t)nbt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (read_inexact)
-            FE_CUDA(ctx, cudaMemcpyAsync(host + FE_MAX_BUCKETS, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            FE_CUDA(ctx, cudaMemcpyAsync(host.data() + FE_MAX_TOTAL, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        *inexact = read_inexact && (host[FE_MAX_BUCKETS] & 1u);
+        *inexact = read_inexact && (host[FE_MAX_TOTAL] & 1u);
         uint32_t S = 0;
-        for (int c = 0; c < nb; ++c) S += host[c];
+        for (int c = 0; c < nbt; ++c) S += host[c];
         *n_left = S;
         if (*inexact || S == 0 || S == nA) return FE_OK;
         // stable compaction of the surviving positions (bucket grouping is kept), then their item indices
@@ -467,7 +473,7 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
             items = slots;
         }
         aoff[0] = 0;
-        for (int c = 0; c < nb; ++c) aoff[c + 1] = aoff[c] + host[c];
+        for (int c = 0; c < nbt; ++c) aoff[c + 1] = aoff[c] + host[c];
         nA = S;
         reuse_rows = false;
         return FE_OK;
@@ -486,11 +492,10 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
     for (;;) {
         if (res->passes >= (uint32_t)FE_MAX_PASSES - 2) F = 1.0;
         // ---- domain slice of every bucket for this pass ----
-        uint32_t lo[FE_MAX_BUCKETS], hi[FE_MAX_BUCKETS];
         bool all_done = true, any_work = false;
-        for (int b = 0; b < nb; ++b) {
-            bool wanted = aoff[b + 1] > aoff[b];
-            for (int c = std::max(0, b - tb.span); c <= std::min(nb - 1, b + tb.span); ++c)
+        for (int b = 0; b < nbt; ++b) {
+            bool wanted = false;
+            for (int c = nlo(b); c <= nhi(b); ++c)
                 if (aoff[c + 1] > aoff[c]) wanted = true;                 // some range bucket that meets this domain bucket is alive
             lo[b] = done[b];
             hi[b] = dc[b];
@@ -507,7 +512,8 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
         if (!any_work) break;
         // every admissible domain with an index below `cutoff` has been scored once this pass is through
         const uint32_t cutoff = (tb.bins && !all_done) ? tb.cut[kF] : FE_NONE32;
-        {
+        for (int grp = 0; grp < tb.ngroups; ++grp) {                      // one launch per group, back to back (no round trip between)
+            const int g0 = grp * nb;
             SearchPass sp{};
             sp.dom_order = tb.dom_order; sp.rng_items = items; sp.rowslot = slots;
             sp.nbuckets = nb; sp.n_dom = nD;
@@ -516,30 +522,32 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
             sp.reuse_dom_norms = res->launches > 0;
             uint64_t cols = 0, work = 0;
             for (int b = 0; b < nb; ++b) {
-                sp.dbeg[b] = tb.doff[b] + lo[b];
-                sp.dend[b] = tb.doff[b] + hi[b];
-                cols += hi[b] - lo[b];
+                sp.dbeg[b] = tb.doff[g0 + b] + lo[g0 + b];
+                sp.dend[b] = tb.doff[g0 + b] + hi[g0 + b];
+                cols += hi[g0 + b] - lo[g0 + b];
             }
             for (int c = 0; c < nb; ++c) {
-                const uint32_t rc = aoff[c + 1] - aoff[c];
-                for (int b = std::max(0, c - sp.span); b <= std::min(nb - 1, c + sp.span); ++b) work += (uint64_t)rc * (hi[b] - lo[b]) * 4;
+                const uint32_t rc = aoff[g0 + c + 1] - aoff[g0 + c];
+                for (int b = nlo(g0 + c); rc && b <= nhi(g0 + c); ++b) work += (uint64_t)rc * (hi[b] - lo[b]) * 4;
             }
-            for (int c = 0; c <= nb; ++c) sp.roff[c] = aoff[c];
+            for (int c = 0; c <= nb; ++c) sp.roff[c] = aoff[g0 + c];
+            if (!work) continue;
+            if (tb.ngroups > 1) reuse_rows = false;                       // the groups share the operand buffers
             if (pass_dbg)
-                fprintf(stderr, "[pass] T=%u kind=%d pass=%u ranges=%u cols=%llu candidates=%.3e (scan fraction %.4f) rebuild_rows=%d\n", g.T, kind,
-                        res->passes, nA, (unsigned long long)cols, (double)work, F, reuse_rows ? 0 : 1);
+                fprintf(stderr, "[pass] T=%u kind=%d pass=%u group=%d ranges=%u of %u cols=%llu candidates=%.3e (scan fraction %.4f) rebuild_rows=%d\n", g.T,
+                        kind, res->passes, grp, aoff[g0 + nb] - aoff[g0], nA, (unsigned long long)cols, (double)work, F, reuse_rows ? 0 : 1);
             FE_TRY(launch(sp));
             res->evaluated += work;
         }
-        for (int b = 0; b < nb; ++b) done[b] = hi[b];
+        for (int b = 0; b < nbt; ++b) done[b] = hi[b];
         ++res->passes;
         done_cutoff = cutoff;
 
         if (all_done) {
             if (kind == 0) {
-                FE_CUDA(ctx, cudaMemcpyAsync(host + FE_MAX_BUCKETS, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                FE_CUDA(ctx, cudaMemcpyAsync(host.data() + FE_MAX_TOTAL, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
                 FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                res->inexact = (host[FE_MAX_BUCKETS] & 1u) != 0;
+                res->inexact = (host[FE_MAX_TOTAL] & 1u) != 0;
             }
             break;
         }
@@ -559,9 +567,9 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
         F *= (double)(1 << step);
         // what is left is small: one more launch for all of it costs less than the round trips of several slices
         uint64_t left = 0;
-        for (int c = 0; c < nb; ++c) {
+        for (int c = 0; c < nbt; ++c) {
             const uint64_t rc = aoff[c + 1] - aoff[c];
-            for (int b = std::max(0, c - tb.span); rc && b <= std::min(nb - 1, c + tb.span); ++b) left += rc * (dc[b] - done[b]) * 4;
+            for (int b = nlo(c); rc && b <= nhi(c); ++b) left += rc * (dc[b] - done[b]) * 4;
         }
         if ((double)left * 2.0 * g.N <= 1.5e11) F = 1.0;
         if (kF > 7) { kF = 7; F = 1.0; }
@@ -575,20 +583,35 @@ static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& 
         if (S) {
             LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
             SearchPass sp{};
-            sp.dom_order = nullptr; sp.rng_items = items; sp.rowslot = slots;
-            sp.nbuckets = 1; sp.n_dom = nD;
+            sp.rng_items = items; sp.rowslot = slots;
+            sp.n_dom = nD;
             sp.reuse_dom_norms = false;
-            sp.dbeg[0] = 0; sp.dend[0] = nD;
-            sp.roff[0] = 0; sp.roff[1] = S;
-            reuse_rows = false;                                           // one bucket now: different row tiles
-            if (pass_dbg) fprintf(stderr, "[pass] T=%u kind=%d minimum pass: ranges=%u cols=%u\n", g.T, kind, S, nD);
+            uint64_t work = 0;
+            if (tb.ngroups == 1) {
+                sp.dom_order = nullptr;
+                sp.nbuckets = 1;
+                sp.dbeg[0] = 0; sp.dend[0] = nD;
+                sp.roff[0] = 0; sp.roff[1] = S;
+                work = (uint64_t)S * nD * 4;
+            } else {                                                      // every class against its own domains, in scan order
+                sp.dom_order = tb.grp_dom_order;
+                sp.nbuckets = tb.ngroups;
+                for (int grp = 0; grp < tb.ngroups; ++grp) {
+                    sp.dbeg[grp] = tb.grp_doff[grp]; sp.dend[grp] = tb.grp_doff[grp + 1];
+                    sp.roff[grp] = aoff[grp * nb];
+                    work += (uint64_t)(aoff[(grp + 1) * nb] - aoff[grp * nb]) * (tb.grp_doff[grp + 1] - tb.grp_doff[grp]) * 4;
+                }
+                sp.roff[tb.ngroups] = aoff[nbt];
+            }
+            reuse_rows = false;                                           // other buckets now: different row tiles
+            if (pass_dbg) fprintf(stderr, "[pass] T=%u kind=%d minimum pass: ranges=%u candidates=%.3e\n", g.T, kind, S, (double)work);
             FE_TRY(launch(sp));
-            res->evaluated += (uint64_t)S * nD * 4;
+            res->evaluated += work;
             ++res->passes;
             if (kind == 0) {
-                FE_CUDA(ctx, cudaMemcpyAsync(host + FE_MAX_BUCKETS, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                FE_CUDA(ctx, cudaMemcpyAsync(host.data() + FE_MAX_TOTAL, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
                 FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                res->inexact = (host[FE_MAX_BUCKETS] & 1u) != 0;
+                res->inexact = (host[FE_MAX_TOTAL] & 1u) != 0;
             }
         }
     }
@@ -646,6 +669,50 @@ static int bucket_by_brightness(fe_ctx* ctx, const LevelIO& io, uint32_t width, 
     return FE_OK;
 }
 
+// Classifier classes x brightness bins (a threshold search with the classifier on): both lists are ordered by
+// (class, bin, index); bucket (class c, bin b) = entry (c + 1) * nbins + b of the offset arrays.  The class-only orders
+// (bucket_by_class) must already sit in b_dom_order / b_rng_order with the classes in b_dom_cls / b_rng_cls.
+static int bucket_by_class_and_brightness(fe_ctx* ctx, const LevelIO& io, uint32_t width, int nbins, TcBuckets* tb) {
+    const uint32_t nD = io.nD, nR = io.nR;
+    const int nbt = 7 * nbins;
+    const size_t n = (size_t)nD + nR;
+    FE_CUDA(ctx, ctx->b_dom_order2.ensure((size_t)nD * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_rng_order2.ensure((size_t)nR * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_keys_tmp.ensure(n * 7 + 256));
+    FE_CUDA(ctx, ctx->b_vals_tmp.ensure((size_t)std::max(nD, nR) * sizeof(uint32_t)));
+    FE_CUDA(ctx, ctx->b_hist.ensure((size_t)FE_MAX_TOTAL * 10 * sizeof(uint32_t)));
+    uint8_t* bins8 = ctx->b_keys_tmp.as<uint8_t>();                              // [nD + nR] brightness bins
+    uint16_t* keys = reinterpret_cast<uint16_t*>(bins8 + ((n + 63) & ~(size_t)63)); // [nD + nR] composite keys, then the sorted copies
+    uint16_t* keys_out = keys + n;
+    uint32_t* hist = ctx->b_hist.as<uint32_t>();                                 // [FE_MAX_TOTAL] domains, [FE_MAX_TOTAL] ranges, [FE_MAX_TOTAL * 8] prefixes
+    FE_CUDA(ctx, cudaMemsetAsync(hist, 0, 2 * FE_MAX_TOTAL * sizeof(uint32_t), ctx->stream));
+    uint32_t* scratch = hist + 2 * FE_MAX_TOTAL;                                 // bin histograms nobody reads (filled before the prefixes)
+    FE_CUDA(ctx, cudaMemsetAsync(scratch, 0, 2 * FE_MAX_BUCKETS * sizeof(uint32_t), ctx->stream));
+    launch_brightness_bins(ctx->stream, ctx->src.px, ctx->src.stride, io.d_dom, nD, io.g.S, 1u, width, bins8, scratch);
+    launch_brightness_bins(ctx->stream, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, io.g.T, 4u, width, bins8 + nD, scratch + FE_MAX_BUCKETS);
+    LAUNCH(ctx, k_composite_keys, cdiv(nD, 256), 256, ctx->b_dom_cls.as<int32_t>(), bins8, nD, (uint32_t)nbins, keys, hist);
+    LAUNCH(ctx, k_composite_keys, cdiv(nR, 256), 256, ctx->b_rng_cls.as<int32_t>(), bins8 + nD, nR, (uint32_t)nbins, keys + nD, hist + FE_MAX_TOTAL);
+    LAUNCH(ctx, k_iota, cdiv(std::max(nD, nR), 256), 256, ctx->b_vals_tmp.as<uint32_t>(), std::max(nD, nR));
+    size_t tmp_d = 0, tmp_r = 0;
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_d, keys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order2.as<uint32_t>(), (int)nD, 0, 9, ctx->stream));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_r, keys + nD, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order2.as<uint32_t>(), (int)nR, 0, 9, ctx->stream));
+    FE_CUDA(ctx, ctx->b_sort_tmp.ensure(std::max(tmp_d, tmp_r)));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_d, keys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order2.as<uint32_t>(), (int)nD, 0, 9, ctx->stream));
+    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_r, keys + nD, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order2.as<uint32_t>(), (int)nR, 0, 9, ctx->stream));
+    ctx->stats.kernel_launches += 10;
+    BucketOff c8{};
+    for (int k = 0; k < 8; ++k) c8.v[k] = tb->cut[k];
+    LAUNCH(ctx, k_bin_prefix, cdiv((uint64_t)nbt * 8, 128), 128, ctx->b_dom_order2.as<uint32_t>(), hist, nbt, c8, hist + 2 * FE_MAX_TOTAL);
+    std::vector<uint32_t> h((size_t)FE_MAX_TOTAL * 10);
+    FE_CUDA(ctx, cudaMemcpyAsync(h.data(), hist, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tb->doff[0] = tb->roff[0] = 0;
+    for (int c = 0; c < nbt; ++c) { tb->doff[c + 1] = tb->doff[c] + h[c]; tb->roff[c + 1] = tb->roff[c] + h[FE_MAX_TOTAL + c]; }
+    for (int b = 0; b < nbt; ++b)
+        for (int k = 0; k < 8; ++k) tb->pre[b][k] = h[2 * FE_MAX_TOTAL + b * 8 + k];
+    return FE_OK;
+}
+
 static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     const LevelGeom& g = io.g;
     const uint32_t nR = io.nR, nD = io.nD;
@@ -691,24 +758,42 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     uint32_t passes = 1;
     float kernel_ms = -1.f;
     bool bins = false;
+    const uint32_t* cls_dom_order = nullptr;   // bins inside classifier classes: class-only domain order and class offsets of the
+    uint32_t cls_roff[8] = {0};                // (class, bin)-ordered range list, for the re-rank
     if (p.search_impl != FE_SEARCH_EXACT && (f16_ok || i8_ok)) {
         TcBuckets tb;
         tb.nb = nbuckets;
         tb.dom_order = dom_order; tb.rng_order = rng_order;
         for (int c = 0; c <= nbuckets; ++c) { tb.doff[c] = doff[c]; tb.roff[c] = roff[c]; }
-        // ---- brightness bins (threshold, no classifier): see search_tc ----
-        if (use_thr && !p.use_classifier && nD && !getenv("FE_NO_BINS") && !getenv("FE_SINGLE_PASS")) {
+        // ---- brightness bins (threshold): see search_tc; with the classifier on they run inside every class ----
+        if (use_thr && nD && !getenv("FE_NO_BINS") && !getenv("FE_SINGLE_PASS")) {
             fe_threshold_plan pl{};
             plan_bins(g.N, thr16, &pl);
             const uint64_t width = pl.bin_width;
             const int nbins = (int)pl.n_bins, span = (int)pl.bin_span;
-            if (nbins) {
+            // Inside classifier classes the bins cost seven launches per slice (the classes share the operand buffers): only
+            // worth it when the level is big -- below ~7 TFLOP of nominal work the plain class buckets finish sooner.
+            // On the last level most ranges close in the first slice anyway (everything that did not match further up ends
+            // there), so the extra launches buy little: levels that split only.
+            const bool cls_bins_pay = ((double)matches * 2.0 * g.N >= 7e12 && io.can_split) || getenv("FE_CLASS_BINS") != nullptr;
+            if (nbins && (!p.use_classifier || cls_bins_pay)) {
                 tb.span = span;
                 for (int k = 0; k < 8; ++k) tb.cut[k] = k == 7 ? nD : (uint32_t)(((uint64_t)nD << k) / 128 + 1);
-                FE_TRY(bucket_by_brightness(ctx, io, (uint32_t)width, nbins, tb.doff, tb.roff, tb.cut, tb.pre));
+                if (p.use_classifier) {
+                    tb.grp_dom_order = dom_order;                    // class-only order: the minimum pass and the re-rank use it
+                    for (int c = 0; c <= 7; ++c) tb.grp_doff[c] = doff[c];
+                    FE_TRY(bucket_by_class_and_brightness(ctx, io, (uint32_t)width, nbins, &tb));
+                    tb.ngroups = 7;
+                    tb.dom_order = ctx->b_dom_order2.as<uint32_t>();
+                    tb.rng_order = ctx->b_rng_order2.as<uint32_t>();
+                    for (int c = 0; c <= 7; ++c) cls_roff[c] = tb.roff[c * nbins];
+                    cls_dom_order = dom_order;
+                } else {
+                    FE_TRY(bucket_by_brightness(ctx, io, (uint32_t)width, nbins, tb.doff, tb.roff, tb.cut, tb.pre));
+                    tb.dom_order = ctx->b_dom_order.as<uint32_t>();
+                    tb.rng_order = ctx->b_rng_order.as<uint32_t>();
+                }
                 tb.nb = nbins;
-                tb.dom_order = ctx->b_dom_order.as<uint32_t>();
-                tb.rng_order = ctx->b_rng_order.as<uint32_t>();
                 tb.bins = bins = true;
                 dom_order = nullptr;                 // results come back as domain indices
                 rng_order = tb.rng_order;            // row slots follow the binned range order
@@ -803,7 +888,9 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     if (counters[0]) return fe_fail(ctx, FE_ERR_CUDA, "internal: %u winners whose search score disagrees with the direct recomputation (T=%u)", counters[0], g.T);
     ctx->stats.fp32_regime_items += counters[1];
     if (counters[1]) {
-        if (bins) { // every domain is admissible for the minimum: one bucket in scan order, rows in the binned range order
+        if (bins && cls_dom_order) { // bins inside classes: a class's domains in scan order, rows in the (class, bin) range order
+            FE_TRY(rerank_fp32_regime(ctx, io, p, cls_dom_order, rng_order, doff, cls_roff, 7));
+        } else if (bins) { // every domain is admissible for the minimum: one bucket in scan order, rows in the binned range order
             const uint32_t d1[8] = {0, nD, nD, nD, nD, nD, nD, nD}, r1[8] = {0, nR, nR, nR, nR, nR, nR, nR};
             FE_TRY(rerank_fp32_regime(ctx, io, p, nullptr, rng_order, d1, r1, 1));
         } else {

@@ -74,7 +74,9 @@ struct SearchArgs {
 
 constexpr int FE_MAX_PASSES = 32;
 constexpr int FE_MAX_LAUNCHES = 3 * FE_MAX_PASSES + 4;   // search launches of one level (three brightness-bin shifts per slice)
-constexpr int FE_MAX_BUCKETS = 64;   // classifier buckets (7) or brightness bins of the threshold pruning (<= 64)
+constexpr int FE_MAX_BUCKETS = 64;   // buckets of one search launch: classifier classes (7) or brightness bins (<= 64)
+constexpr int FE_MAX_GROUPS = 8;     // groups of buckets searched by separate launches of a slice: classifier classes when bins are on
+constexpr int FE_MAX_TOTAL = FE_MAX_GROUPS * FE_MAX_BUCKETS;
 
 struct fe_ctx {
     int device = 0;
@@ -90,6 +92,8 @@ struct fe_ctx {
     // multi-pass search: range positions still without a candidate under the threshold (two generations), their item
     // indices, survivor flags, select scratch
     DevBuf b_act[2], b_act_items, b_act_flags, b_act_tmp;
+    // classifier classes x brightness bins: the composite orders (the class-only orders stay in b_dom_order / b_rng_order)
+    DevBuf b_dom_order2, b_rng_order2;
     // tcgen05 path operands
     DevBuf b_A16, b_B16, b_tmaps, b_blob_dom, b_tileseg;
     // results

@@ -151,10 +151,10 @@ __global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n
 // rows has a candidate under the threshold at a domain index below `cutoff` (every admissible domain below the cutoff has
 // been scored, so a recorded hit below it is the first in scan order; 0xFFFFFFFF = "any hit closes the range").
 // cnt[b] += survivors of bucket b (roff = prefix offsets of the pass's positions).
-__global__ void k_unresolved(const uint32_t* __restrict__ slots, const uint32_t* __restrict__ rowhit, uint32_t n, BucketOff roff, int nb,
+__global__ void k_unresolved(const uint32_t* __restrict__ slots, const uint32_t* __restrict__ rowhit, uint32_t n, TotalOff roff, int nb,
                              uint32_t cutoff, uint8_t* __restrict__ flags, uint32_t* __restrict__ cnt) {
-    __shared__ uint32_t sc[FE_MAX_BUCKETS];
-    if (threadIdx.x < FE_MAX_BUCKETS) sc[threadIdx.x] = 0;
+    __shared__ uint32_t sc[FE_MAX_TOTAL];
+    for (uint32_t i = threadIdx.x; i < (uint32_t)nb; i += blockDim.x) sc[i] = 0;
     __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -163,13 +163,27 @@ __global__ void k_unresolved(const uint32_t* __restrict__ slots, const uint32_t*
         const bool alive = min(min(h.x, h.y), min(h.z, h.w)) >= cutoff;
         flags[i] = alive ? 1 : 0;
         if (alive) {
-            int b = 0;
-            while (b + 1 < nb && i >= roff.v[b + 1]) ++b;
-            atomicAdd(&sc[b], 1u);
+            int lo = 0, hi = nb - 1;                       // bucket b with roff[b] <= i < roff[b + 1]
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (roff.v[mid] <= i) lo = mid; else hi = mid - 1;
+            }
+            atomicAdd(&sc[lo], 1u);
         }
     }
     __syncthreads();
-    if (threadIdx.x < FE_MAX_BUCKETS && sc[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], sc[threadIdx.x]);
+    for (uint32_t b = threadIdx.x; b < (uint32_t)nb; b += blockDim.x)
+        if (sc[b]) atomicAdd(&cnt[b], sc[b]);
+}
+
+// Classifier classes x brightness bins: key = (class + 1) * nbins + bin, hist[key] counts.
+__global__ void k_composite_keys(const int32_t* __restrict__ cls, const uint8_t* __restrict__ bins, uint32_t n, uint32_t nbins,
+                                 uint16_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = (uint32_t)(cls[i] + 1) * nbins + bins[i];
+    keys[i] = (uint16_t)k;
+    atomicAdd(&hist[k], 1u);
 }
 
 // Brightness bin of every block of a uniform list: key = (mul * sum of the block's edge x edge pixels) / width.  For a range

@@ -31,7 +31,8 @@ class _Env:
                 os.environ[k] = v
 
 
-MODES = {"pruned": {}, "slices_only": {"FE_NO_BINS": "1"}, "one_pass": {"FE_SINGLE_PASS": "1"}}
+# FE_CLASS_BINS forces the brightness bins inside classifier classes on levels too small for them to pay
+MODES = {"pruned": {"FE_CLASS_BINS": "1"}, "slices_only": {"FE_NO_BINS": "1"}, "one_pass": {"FE_SINGLE_PASS": "1"}}
 
 
 @pytest.mark.parametrize("kind,cls,thr", [(0, False, 25.0), (0, False, 6.0), (0, True, 25.0), (1, False, 40.0), (2, False, 25.0)])
