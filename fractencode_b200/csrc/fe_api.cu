@@ -775,7 +775,10 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
             // worth it when the level is big -- below ~7 TFLOP of nominal work the plain class buckets finish sooner.
             // On the last level most ranges close in the first slice anyway (everything that did not match further up ends
             // there), so the extra launches buy little: levels that split only.
-            const bool cls_bins_pay = ((double)matches * 2.0 * g.N >= 7e12 && io.can_split) || getenv("FE_CLASS_BINS") != nullptr;
+            // Levels of small blocks run many slices (seven launches each): they need more work to pay (measured on config 4,
+            // whole and sharded over 8 GPUs).
+            const double nominal = (double)matches * 2.0 * g.N;
+            const bool cls_bins_pay = (io.can_split && nominal >= (g.T >= 16 ? 7e12 : 3e13)) || getenv("FE_CLASS_BINS") != nullptr;
             if (nbins && (!p.use_classifier || cls_bins_pay)) {
                 tb.span = span;
                 for (int k = 0; k < 8; ++k) tb.cut[k] = k == 7 ? nD : (uint32_t)(((uint64_t)nD << k) / 128 + 1);
