@@ -368,11 +368,13 @@ static int rerank_fp32_regime(fe_ctx* ctx, const LevelIO& io, const fe_params& p
 // estimate() (TransformEstimator2.hpp:29-47): the first candidate in scan order under the threshold, else the minimum.
 //  * Early-out: the scan is cut into growing slices of the domain order; after each slice the ranges whose first hit is
 //    known are final (the reference breaks there too, :40-41) and only the survivors go on, compacted into fresh row tiles.
-//  * Brightness bins (no classifier): by Cauchy-Schwarz (sum(4r) - sum(D))^2 <= N * n16, so a candidate can only be under the
-//    threshold when the two block sums differ by at most R = floor(sqrt(N * thr16)).  Blocks are bucketed by sum / width with
-//    width > R, so a range of bin c finds every possible hit in the domain bins c-1, c, c+1 (three launches per slice over
-//    the same rows).  Ranges that never hit get their minimum from one plain pass over all domains at the end -- unless the
-//    level can split, where a range without a hit is split and its minimum is never looked at (Encoder2 quadtree rule).
+//  * Brightness bins: by Cauchy-Schwarz (sum(4r) - sum(D))^2 <= N * n16, so a candidate can only be under the threshold
+//    when the two block sums differ by at most R = floor(sqrt(N * thr16)).  Blocks are bucketed by sum / width (width about
+//    R / 2, plan_bins), so a range of bin c finds every possible hit in the domain bins c-span .. c+span: adjacent in the
+//    operand blob, one work item per row tile.  With the classifier on the bins run inside every class (groups): one
+//    launch per class and slice, back to back.  Ranges that never hit get their minimum from one plain pass over all their
+//    admissible domains at the end -- unless the level can split, where a range without a hit is split and its minimum is
+//    never looked at (Encoder2 quadtree rule): those levels do not even track it (no_min).
 // Hits are recorded as DOMAIN indices (atomicMin), so "first in scan order" holds across bins, slices and column chunks.
 struct TcBuckets {
     int nb = 1;                            // buckets of one group (one search launch)
