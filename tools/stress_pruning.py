@@ -30,6 +30,11 @@ with fb.Context(0) as ctx:
         seed = int(rs.integers(0, 1 << 30))
         single = bool(rs.integers(0, 4) == 0)       # sometimes a single level through fe_encode_level (minimum always wanted)
         ctx.set_synthetic_image(W, H, seed, kind)
+        if rs.integers(0, 3) == 0:                  # same pixels through a host plane with an odd stride (unaligned rows)
+            img = ctx.get_image()
+            pad = np.zeros((H, W + int(rs.integers(1, 9))), np.uint8)
+            pad[:, :W] = img
+            ctx.set_image(pad[:, :W])
         p = fb.Params(thr, -1.0, cls)
         out = {}
         modes = ("pruned", "one_pass", "exact") if W * H <= 512 * 512 else ("pruned", "one_pass")   # exact = dp4a integer kernel
