@@ -13,9 +13,10 @@
 #include <utility>
 
 #include "fe_kernels.cuh"
+#include "fe_plan.cuh"
 #include "fe_umma.cuh"
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;   // error of the last failed fe_create on this thread
 
 int fe_fail(fe_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];
@@ -52,7 +53,7 @@ static bool threshold_n16(double thr, uint32_t S, uint32_t* out) {
 }
 
 // Brightness bins of a threshold search (search_tc): radius of the Cauchy-Schwarz bound, bin width, bins, span.
-static void plan_bins(uint32_t N, uint32_t thr16, fe_threshold_plan* pl) {
+void fe_plan_bins(uint32_t N, uint32_t thr16, fe_threshold_plan* pl) {
     const uint64_t nt = (uint64_t)N * thr16;
     uint64_t R = (uint64_t)std::sqrt((double)nt);
     while (R * R > nt) --R;
@@ -77,7 +78,7 @@ extern "C" int fe_plan_threshold(double rms_threshold, uint32_t S, uint32_t T, f
     if (!threshold_n16(rms_threshold, S, &thr16)) return FE_OK;
     out->use_threshold = 1;
     out->thr16 = thr16;
-    plan_bins(T * T, thr16, out);
+    fe_plan_bins(T * T, thr16, out);
     return FE_OK;
 }
 
@@ -114,10 +115,18 @@ extern "C" int fe_create(fe_ctx** out, int device, void* stream) {
         }
         ctx->own_stream = true;
     }
-    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
-    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
-    for (auto& ev : ctx->ev_pass) cudaEventCreate(&ev);
+    ctx->n_sm = prop.multiProcessorCount;
+    e = cudaSuccess;
+    for (auto& ev : ctx->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
+    for (auto& ev : ctx->ev_pass) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_summary, 256, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        fe_fail(nullptr, FE_ERR_CUDA, "fe_create: %s", cudaGetErrorString(e));
+        fe_destroy(ctx);
+        return FE_ERR_CUDA;
+    }
     *out = ctx;
     return FE_OK;
 }
@@ -125,8 +134,9 @@ extern "C" int fe_create(fe_ctx** out, int device, void* stream) {
 extern "C" void fe_destroy(fe_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->b_src, &ctx->b_tgt, &ctx->b_dom, &ctx->b_rng, &ctx->b_dom_cls, &ctx->b_rng_cls, &ctx->b_dom_order,
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->b_plan, &ctx->b_ctl, &ctx->b_list[0], &ctx->b_list[1], &ctx->b_itemrec, &ctx->b_posb, &ctx->b_summary,
+                      &ctx->b_src, &ctx->b_tgt, &ctx->b_dom, &ctx->b_rng, &ctx->b_dom_cls, &ctx->b_rng_cls, &ctx->b_dom_order,
                       &ctx->b_rng_order, &ctx->b_sort_tmp, &ctx->b_keys_tmp, &ctx->b_vals_tmp, &ctx->b_A, &ctx->b_Blo, &ctx->b_Bhi,
                       &ctx->b_rowc, &ctx->b_coln, &ctx->b_rowbest, &ctx->b_rowhit, &ctx->b_hist, &ctx->b_level_items, &ctx->b_split,
                       &ctx->b_scan, &ctx->b_scan_tmp, &ctx->b_rng_next, &ctx->b_counters, &ctx->b_A16, &ctx->b_B16, &ctx->b_tmaps,
@@ -137,7 +147,8 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& ev : ctx->ev_pass) if (ev) cudaEventDestroy(ev);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h_summary) cudaFreeHost(ctx->h_summary);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -715,7 +726,7 @@ static int bucket_by_class_and_brightness(fe_ctx* ctx, const LevelIO& io, uint32
     return FE_OK;
 }
 
-static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
+static int run_level_host(fe_ctx* ctx, const LevelIO& io, const fe_params& p, bool skip_f16 = false) {
     const LevelGeom& g = io.g;
     const uint32_t nR = io.nR, nD = io.nD;
     if (nR == 0) return FE_OK;
@@ -752,7 +763,7 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     FE_CUDA(ctx, ctx->b_rowhit.ensure((size_t)nR * 4 * 4));
     FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)nR * 4));
 
-    const bool f16_ok = nD && umma_level_supported(g), i8_ok = nD && umma_i8_level_supported(g);
+    const bool f16_ok = nD && umma_level_supported(g) && !skip_f16, i8_ok = nD && umma_i8_level_supported(g);
     if (p.search_impl == FE_SEARCH_UMMA && nD && !f16_ok && !i8_ok)
         return fe_fail(ctx, FE_ERR_UNSUPPORTED, "tcgen05 paths need S == 2T, even domain origins and T <= 32 (got S=%u T=%u)", g.S, g.T);
     bool searched = false;
@@ -770,7 +781,7 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
         // ---- brightness bins (threshold): see search_tc; with the classifier on they run inside every class ----
         if (use_thr && nD && !getenv("FE_NO_BINS") && !getenv("FE_SINGLE_PASS")) {
             fe_threshold_plan pl{};
-            plan_bins(g.N, thr16, &pl);
+            fe_plan_bins(g.N, thr16, &pl);
             const uint64_t width = pl.bin_width;
             const int nbins = (int)pl.n_bins, span = (int)pl.bin_span;
             // Inside classifier classes the bins cost seven launches per slice (the classes share the operand buffers): only
@@ -920,6 +931,144 @@ static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     return FE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// A level in two halves: everything is enqueued, then ONE synchronisation reads the level's summary back (together with
+// the quadtree's split count).  Levels of the device-scheduled tcgen05 path (fe_plan.cu) never synchronise in between;
+// the other paths (exact integer search, host-scheduled i8 kind) still run to completion inside the first half.
+// ---------------------------------------------------------------------------------------------------
+struct LevelPending {
+    bool device = false;
+    DeviceLevelState st;
+    uint32_t thr16 = 0;
+    bool use_thr = false, timed = false;
+};
+
+static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p, LevelPending* lp) {
+    const LevelGeom& g = io.g;
+    const uint32_t nR = io.nR, nD = io.nD;
+    *lp = LevelPending{};
+    if (nR == 0) return FE_OK;
+    const bool device = nD && umma_level_supported(g) && p.search_impl != FE_SEARCH_EXACT && !getenv("FE_HOST_SLICES");
+    if (!device) return run_level_host(ctx, io, p);
+    if (p.rms_threshold * (double)(g.S * g.S) >= 1048576.0)
+        return fe_fail(ctx, FE_ERR_UNSUPPORTED, "rms_threshold %g reaches the fp32-rounding regime of the reference distance (SSE >= 2^20) at S=%u", p.rms_threshold, g.S);
+    lp->device = true;
+    lp->timed = io.stat_level >= 0 && io.stat_level < 8;
+    lp->use_thr = threshold_n16(p.rms_threshold, g.S, &lp->thr16);
+    if (lp->timed) cudaEventRecord(ctx->ev[0], ctx->stream);
+    FE_CUDA(ctx, ctx->b_counters.ensure(16 * sizeof(uint32_t)));
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.p, 0, 16 * sizeof(uint32_t), ctx->stream));
+    FE_CUDA(ctx, ctx->b_rowbest.ensure((size_t)nR * 4 * 8));
+    FE_CUDA(ctx, ctx->b_rowhit.ensure((size_t)nR * 4 * 4));
+    DeviceLevel lv{};
+    lv.d_dom = io.d_dom; lv.nD = nD; lv.d_rng = io.d_rng; lv.nR = nR; lv.g = g;
+    if (p.use_classifier) {
+        FE_CUDA(ctx, ctx->b_dom_cls.ensure((size_t)nD * 4));
+        FE_CUDA(ctx, ctx->b_rng_cls.ensure((size_t)nR * 4));
+        LAUNCH(ctx, k_classify, cdiv((uint64_t)nD * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, nD, ctx->b_dom_cls.as<int32_t>(), 0);
+        LAUNCH(ctx, k_classify, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, ctx->b_rng_cls.as<int32_t>(), 0);
+        lv.dom_cls = ctx->b_dom_cls.as<int32_t>();
+        lv.rng_cls = ctx->b_rng_cls.as<int32_t>();
+    }
+    lv.thr16 = lp->thr16; lv.use_thr = lp->use_thr; lv.need_min = !io.can_split; lv.timed = lp->timed;
+    FE_TRY(search_level_device(ctx, lv, 0, &lp->st));
+    if (lp->timed) cudaEventRecord(ctx->ev[2], ctx->stream);
+    FinalizeArgs f{};
+    f.src = ctx->src.px; f.src_stride = ctx->src.stride;
+    f.tgt = ctx->tgt.px; f.tgt_stride = ctx->tgt.stride;
+    f.dom = io.d_dom; f.rng = io.d_rng;
+    f.dom_order = nullptr; f.rng_order = lp->st.rng_order;        // keys and hits are domain indices
+    f.rowbest = ctx->b_rowbest.as<unsigned long long>();
+    f.rowhit = ctx->b_rowhit.as<uint32_t>();
+    f.n = nR;
+    f.use_thr = lp->use_thr ? 1u : 0u;
+    f.thr = p.rms_threshold; f.s_max = p.s_max; f.fma = p.fma;
+    f.can_split = io.can_split;
+    f.thr16 = lp->thr16;
+    f.out = io.d_out; f.split = io.d_split;
+    f.mismatch = ctx->b_counters.as<uint32_t>();
+    f.fp32_regime = ctx->b_counters.as<uint32_t>() + 1;
+    FE_CUDA(ctx, ctx->b_bound.ensure((size_t)nR * 4 + 4));
+    f.bound_out = ctx->b_bound.as<uint32_t>();
+    f.rerank = 0;
+    f.hit_is_domain = 1;
+    f.no_min = (lp->use_thr && io.can_split) ? 1 : 0;   // a range without a hit splits: its minimum was not even tracked
+    LAUNCH(ctx, k_finalize, cdiv((uint64_t)nR * 32, 256), 256, f);
+    if (lp->timed) cudaEventRecord(ctx->ev[3], ctx->stream);
+    return FE_OK;
+}
+
+// Second half: one D2H copy + synchronisation.  scan_last / split_last (device, may be NULL): last entries of the quadtree's
+// exclusive scan of the split flags and of the flags; *n_split gets their sum.  *redo is set when the level's items were
+// rewritten after the scan had been enqueued (rare paths: inexact fp16 band, fp32-regime re-rank).
+static int run_level_complete(fe_ctx* ctx, const LevelIO& io, const fe_params& p, LevelPending* lp, const uint32_t* scan_last,
+                              const uint32_t* split_last, size_t* n_split, bool* redo) {
+    *redo = false;
+    if (io.nR == 0) { if (n_split) *n_split = 0; return FE_OK; }
+    FE_CUDA(ctx, ctx->b_summary.ensure(sizeof(LevelSummary)));
+    FE_CUDA(ctx, ctx->b_counters.ensure(16 * sizeof(uint32_t)));
+    LevelSummary* hs = reinterpret_cast<LevelSummary*>(ctx->h_summary);
+    LAUNCH(ctx, k_level_summary, 1, 1, lp->device ? ctx->b_ctl.as<SliceCtl>() : nullptr, lp->device ? ctx->b_plan.as<LevelPlan>() : nullptr,
+           ctx->b_counters.as<uint32_t>(), scan_last, split_last, ctx->b_summary.as<LevelSummary>());
+    FE_CUDA(ctx, cudaMemcpyAsync(hs, ctx->b_summary.p, sizeof(LevelSummary), cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_split) *n_split = (size_t)hs->last_scan + hs->last_flag;
+    if (!lp->device) return FE_OK;
+    const LevelGeom& g = io.g;
+    if (hs->overflow) return fe_fail(ctx, FE_ERR_CUDA, "internal: work-item buffer of the level too small (T=%u)", g.T);
+    if (hs->flags & 1u) {
+        // a winner of the kind::f16 search sits in the fp32-inexact band: the level is searched again on the integer kind
+        *redo = true;
+        return run_level_host(ctx, io, p, true);
+    }
+    if (hs->mismatch) return fe_fail(ctx, FE_ERR_CUDA, "internal: %u winners whose search score disagrees with the direct recomputation (T=%u)", hs->mismatch, g.T);
+    ctx->stats.matches += hs->matches;
+    ctx->stats.evaluated += hs->evaluated;
+    ctx->stats.umma_levels++;
+    ctx->stats.fp32_regime_items += hs->fp32_regime;
+    float kernel_ms = 0.f;
+    if (lp->timed) {
+        for (uint32_t i = 0; i < lp->st.n_launches; ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev_pass[2 * i], ctx->ev_pass[2 * i + 1]);
+            kernel_ms += ms;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]);
+        ctx->stats.level_search_ms[io.stat_level] = kernel_ms;
+        ctx->stats.level_prep_ms[io.stat_level] = ms - kernel_ms;
+        ctx->stats.level_ranges[io.stat_level] = io.nR;
+        ctx->stats.level_matches[io.stat_level] = hs->matches;
+        ctx->stats.level_evaluated[io.stat_level] = hs->evaluated;
+        ctx->stats.level_passes[io.stat_level] = hs->passes;
+    }
+    if (hs->fp32_regime) {
+        // re-rank of the flagged range blocks on the exact kernel: every domain of the block's class in scan order
+        *redo = true;
+        const uint32_t nD = io.nD, nR = io.nR;
+        if (p.use_classifier) {
+            uint32_t doff[8], roff[8] = {0};
+            FE_TRY(bucket_by_class(ctx, ctx->b_dom_cls.as<int32_t>(), nD, ctx->b_dom_order, doff));
+            std::vector<uint32_t> lr(FE_MAX_TOTAL + 1);
+            FE_CUDA(ctx, cudaMemcpy(lr.data(), reinterpret_cast<const uint8_t*>(ctx->b_plan.p) + offsetof(LevelPlan, roff), lr.size() * 4, cudaMemcpyDeviceToHost));
+            for (int c = 0; c <= 7; ++c) roff[c] = lr[(size_t)c * lp->st.nbins];
+            FE_TRY(rerank_fp32_regime(ctx, io, p, ctx->b_dom_order.as<uint32_t>(), lp->st.rng_order, doff, roff, 7));
+        } else {
+            const uint32_t d1[8] = {0, nD, nD, nD, nD, nD, nD, nD}, r1[8] = {0, nR, nR, nR, nR, nR, nR, nR};
+            FE_TRY(rerank_fp32_regime(ctx, io, p, nullptr, lp->st.rng_order, d1, r1, 1));
+        }
+    }
+    return FE_OK;
+}
+
+static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
+    LevelPending lp;
+    bool redo = false;
+    FE_TRY(run_level_enqueue(ctx, io, p, &lp));
+    if (lp.device) FE_TRY(run_level_complete(ctx, io, p, &lp, nullptr, nullptr, nullptr, &redo));
+    return FE_OK;
+}
+
 static int make_geom(fe_ctx* ctx, uint32_t S, uint32_t T, bool even_origins, LevelGeom* g) {
     if (T < 2 || S <= T || S % T) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "geometry: need S a multiple of T, S > T >= 2 (got S=%u T=%u)", S, T);
     if (T > 64) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "geometry: range size %u > 64 (32-bit score arithmetic)", T);
@@ -1005,6 +1154,7 @@ extern "C" int fe_encode_quadtree_slice_device(fe_ctx* ctx, uint32_t t_max, uint
                (uint32_t)first_block);
     for (int l = 0; l < 8; ++l) {
         ctx->stats.level_items[l] = ctx->stats.level_ranges[l] = ctx->stats.level_matches[l] = 0;
+        ctx->stats.level_evaluated[l] = ctx->stats.level_passes[l] = 0;
         ctx->stats.level_search_ms[l] = ctx->stats.level_prep_ms[l] = 0.f;
     }
     size_t offset = 0;
@@ -1027,23 +1177,42 @@ extern "C" int fe_encode_quadtree_slice_device(fe_ctx* ctx, uint32_t t_max, uint
         io.can_split = (T / 2 >= t_min) ? 1 : 0;
         io.d_split = ctx->b_split.as<uint32_t>();
         io.stat_level = level;
-        FE_TRY(run_level(ctx, io, *params));
+        LevelPending lp;
+        FE_TRY(run_level_enqueue(ctx, io, *params, &lp));
         size_t n_split = 0;
         if (io.can_split) {
             FE_CUDA(ctx, ctx->b_scan.ensure(n_pending * 4 + 4));
-            size_t tmp_bytes = 0;
-            FE_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, io.d_split, ctx->b_scan.as<uint32_t>(), (int)n_pending, ctx->stream));
-            FE_CUDA(ctx, ctx->b_scan_tmp.ensure(tmp_bytes));
-            FE_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_scan_tmp.p, tmp_bytes, io.d_split, ctx->b_scan.as<uint32_t>(), (int)n_pending, ctx->stream));
-            ctx->stats.kernel_launches += 2;
-            uint32_t last_scan = 0, last_flag = 0;
-            FE_CUDA(ctx, cudaMemcpyAsync(&last_scan, ctx->b_scan.as<uint32_t>() + (n_pending - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-            FE_CUDA(ctx, cudaMemcpyAsync(&last_flag, io.d_split + (n_pending - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-            FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            n_split = (size_t)last_scan + last_flag;
+            auto scan_and_count = [&](bool sync_here) -> int {
+                size_t tmp_bytes = 0;
+                FE_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, io.d_split, ctx->b_scan.as<uint32_t>(), (int)n_pending, ctx->stream));
+                FE_CUDA(ctx, ctx->b_scan_tmp.ensure(tmp_bytes));
+                FE_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_scan_tmp.p, tmp_bytes, io.d_split, ctx->b_scan.as<uint32_t>(), (int)n_pending, ctx->stream));
+                ctx->stats.kernel_launches += 2;
+                if (sync_here) {
+                    uint32_t last_scan = 0, last_flag = 0;
+                    FE_CUDA(ctx, cudaMemcpyAsync(&last_scan, ctx->b_scan.as<uint32_t>() + (n_pending - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+                    FE_CUDA(ctx, cudaMemcpyAsync(&last_flag, io.d_split + (n_pending - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+                    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                    n_split = (size_t)last_scan + last_flag;
+                }
+                return FE_OK;
+            };
+            if (lp.device) {
+                // one synchronisation per level: the level's summary and the split count come back together
+                bool redo = false;
+                FE_TRY(scan_and_count(false));
+                FE_TRY(run_level_complete(ctx, io, *params, &lp, ctx->b_scan.as<uint32_t>() + (n_pending - 1), io.d_split + (n_pending - 1), &n_split, &redo));
+                if (redo) FE_TRY(scan_and_count(true));
+            } else {
+                FE_TRY(scan_and_count(true));
+            }
             LAUNCH(ctx, k_quadtree_scatter, cdiv(n_pending, 256), 256, ctx->b_rng.as<fe_grid_item>(), io.d_out, io.d_split, ctx->b_scan.as<uint32_t>(),
                    (uint32_t)n_pending, ctx->b_rng_next.as<fe_grid_item>(), ctx->b_items.as<fe_encode_item>() + offset);
         } else {
+            if (lp.device) {
+                bool redo = false;
+                FE_TRY(run_level_complete(ctx, io, *params, &lp, nullptr, nullptr, nullptr, &redo));
+            }
             FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_items.as<fe_encode_item>() + offset, io.d_out, n_pending * sizeof(fe_encode_item), cudaMemcpyDeviceToDevice, ctx->stream));
         }
         const size_t kept = n_pending - n_split;

@@ -96,6 +96,11 @@ struct fe_ctx {
     DevBuf b_dom_order2, b_rng_order2;
     // tcgen05 path operands
     DevBuf b_A16, b_B16, b_tmaps, b_blob_dom, b_tileseg;
+    // device-scheduled levels (fe_plan.cuh): plan, slice state, the two lists of open range blocks, work items, bucket of every
+    // level position, and the per-level summary the host reads back (device record + pinned host copy)
+    DevBuf b_plan, b_ctl, b_list[2], b_itemrec, b_posb, b_summary;
+    void* h_summary = nullptr;
+    int n_sm = 148;                 // multiProcessorCount of the device
     // results
     DevBuf b_items;
     size_t n_items = 0;

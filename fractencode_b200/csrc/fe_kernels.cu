@@ -244,7 +244,7 @@ __global__ void k_bin_prefix(const uint32_t* __restrict__ dom_order, const uint3
     const uint32_t c = cut.v[k];
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (dom_order[mid] < c) lo = mid + 1; else hi = mid;
+        if ((dom_order ? dom_order[mid] : mid) < c) lo = mid + 1; else hi = mid;   // NULL order: one bucket, position = index
     }
     out[t] = lo - beg;
 }

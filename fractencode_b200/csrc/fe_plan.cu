@@ -1,0 +1,497 @@
+// fe_plan.cu -- device-side planning of a search level (see fe_plan.cuh): bucket layout, slice schedule, survivor
+// compaction and work-item expansion, all from device memory; and the host code that enqueues one level.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "fe_kernels.cuh"
+#include "fe_plan.cuh"
+#include "fe_umma.cuh"
+
+namespace {
+
+constexpr uint32_t GR = 128;   // slice granularity in columns: whole tiles of both kinds
+
+__device__ __forceinline__ uint32_t grp_lo(const LevelPlan* p, uint32_t c, bool whole) {
+    const uint32_t g0 = (c / p->nbins) * p->nbins, b = c - g0;
+    return whole ? g0 : g0 + (b > p->span ? b - p->span : 0u);
+}
+__device__ __forceinline__ uint32_t grp_hi(const LevelPlan* p, uint32_t c, bool whole) {
+    const uint32_t g0 = (c / p->nbins) * p->nbins, b = c - g0;
+    return whole ? g0 + p->nbins - 1 : g0 + min(p->nbins - 1, b + p->span);
+}
+
+// block-wide sums over 256 threads
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sh) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long t = 0;
+    for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t += sh[w];
+    return t;
+}
+__device__ __forceinline__ uint32_t block_max_u32(uint32_t v, unsigned long long* sh) {
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t t = 0;
+    for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t = max(t, (uint32_t)sh[w]);
+    return t;
+}
+
+} // namespace
+
+// key = (class + 1) * nbins + bin (class 0 when cls is NULL, bin 0 when bins is NULL); hist[key] counts.
+__global__ void k_bucket_keys(const int32_t* __restrict__ cls, const uint8_t* __restrict__ bins, uint32_t n, uint32_t nbins,
+                              uint16_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = (cls ? (uint32_t)(cls[i] + 1) : 0u) * nbins + (bins ? (uint32_t)bins[i] : 0u);
+    keys[i] = (uint16_t)k;
+    atomicAdd(&hist[k], 1u);
+}
+
+// One CTA of 512 threads: bucket offsets, the interval ends of every bucket, the tile layout of the operand blob and the
+// initial slice state.  pre[b * 8 + k] = positions of bucket b with a domain index below cut[k] (k_bin_prefix).
+__global__ void __launch_bounds__(512) k_level_plan(PlanArgs a, const uint32_t* __restrict__ dom_hist, const uint32_t* __restrict__ rng_hist,
+                                                    const uint32_t* __restrict__ pre, uint32_t nb, uint32_t nbins, uint32_t ngroups, uint32_t span,
+                                                    uint32_t nD, uint32_t nR, uint32_t nt) {
+    __shared__ uint32_t s_scan[512];
+    LevelPlan* p = a.plan;
+    SliceCtl* ctl = a.ctl;
+    const uint32_t t = threadIdx.x;
+    const uint32_t dc = t < nb ? dom_hist[t] : 0u, rc = t < nb ? rng_hist[t] : 0u;
+    // exclusive scans of the two histograms
+    for (int pass = 0; pass < 2; ++pass) {
+        const uint32_t v = pass ? rc : dc;
+        s_scan[t] = v;
+        __syncthreads();
+        for (uint32_t o = 1; o < 512; o <<= 1) {
+            const uint32_t x = t >= o ? s_scan[t - o] : 0u;
+            __syncthreads();
+            s_scan[t] += x;
+            __syncthreads();
+        }
+        uint32_t* dst = pass ? p->roff : p->doff;
+        if (t < nb) dst[t + 1] = s_scan[t];
+        if (t == 0) dst[0] = 0;
+        __syncthreads();
+    }
+    // interval ends of my bucket
+    const uint32_t min_step = a.min_tiles * GR;
+    uint32_t tiles[FE_NK];
+    uint32_t done = 0;
+#pragma unroll
+    for (int k = 0; k < FE_NK; ++k) {
+        uint32_t hi = dc;
+        if (a.multipass && k < FE_NK - 1) {
+            const uint32_t target = pre[t < nb ? t * 8 + k : 0];
+            const uint64_t up = ((uint64_t)max(min_step, target) + GR - 1) / GR * GR;
+            hi = (uint32_t)min((uint64_t)dc, max(up, (uint64_t)done + min_step));
+            if (dc - hi < min_step / 2) hi = dc;     // no slivers at the end of the scan
+        }
+        if (t < nb) p->dend[k][t] = hi;
+        tiles[k] = t < nb ? (hi - done + nt - 1) / nt : 0u;
+        done = hi;
+    }
+    // tile layout, interval-major: exclusive scan over (k, b)
+    uint32_t base = 0;
+    const uint32_t nk = a.multipass ? FE_NK : 1;
+    for (uint32_t k = 0; k < nk; ++k) {
+        s_scan[t] = tiles[k];
+        __syncthreads();
+        for (uint32_t o = 1; o < 512; o <<= 1) {
+            const uint32_t x = t >= o ? s_scan[t - o] : 0u;
+            __syncthreads();
+            s_scan[t] += x;
+            __syncthreads();
+        }
+        if (t < nb) p->tile0[k * nb + t] = base + s_scan[t] - tiles[k];
+        base += s_scan[511];
+        __syncthreads();
+    }
+    if (t == 0) {
+        p->tile0[nk * nb] = base;
+        p->n_tiles = base;
+        p->nb = nb; p->nbins = nbins; p->ngroups = ngroups; p->span = span;
+        p->nD = nD; p->nR = nR; p->nt = nt; p->nk = nk;
+        for (int k = 0; k < FE_NK; ++k)
+            p->cut[k] = !a.multipass ? FE_NONE32 : (k == FE_NK - 1 ? nD : (uint32_t)((((uint64_t)nD) << k) / 128 + 1));
+        ctl->list = 0; ctl->k_done = 0; ctl->done = 0; ctl->open = 1; ctl->passes = 0; ctl->ticket = 0;
+        ctl->cutoff = FE_NONE32; ctl->evaluated = 0ull; ctl->active = FE_NONE32; ctl->n_items = 0; ctl->no_min = 0;
+        ctl->overflow = 0;
+    }
+    for (uint32_t b = t; b < FE_MAX_TOTAL; b += 512) {
+        ctl->cnt[0][b] = b < nb ? rng_hist[b] : 0u;
+        ctl->cnt[1][b] = 0;
+    }
+}
+
+// Per level position: the first list (every range block open), sum a^2 of the block (centred: a = 4 r - 510, f16 kind;
+// else 16 sum r^2, i8 kind) and the bucket of the position.
+__global__ void k_level_ranges(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
+                               const uint32_t* __restrict__ order, const LevelPlan* __restrict__ plan, uint32_t T, int centred,
+                               ListEntry* __restrict__ list0, uint32_t* __restrict__ rowA2, uint16_t* __restrict__ pos_bucket) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= plan->nR) return;
+    const fe_grid_item r = rng[order ? order[p] : p];
+    const uint8_t* base = img + (size_t)r.y * stride + r.x;
+    uint32_t s2 = 0;
+    for (uint32_t y = 0; y < T; ++y)
+        for (uint32_t x = 0; x < T; ++x) {
+            const int v = centred ? 4 * (int)base[(size_t)y * stride + x] - 510 : 4 * (int)base[(size_t)y * stride + x];
+            s2 += (uint32_t)(v * v);
+        }
+    rowA2[p] = s2;
+    ListEntry e;
+    e.slot = p;
+    e.xy = r.x | (r.y << 16);
+    list0[p] = e;
+    uint32_t lo = 0, hi = plan->nb - 1;               // bucket b with roff[b] <= p < roff[b + 1]
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (plan->roff[mid] <= p) lo = mid; else hi = mid - 1;
+    }
+    pos_bucket[p] = (uint16_t)lo;
+}
+
+// Survivors of the slice that just ran, then the plan of the next one.
+//  phase SLICE (ordinal s): no-op once the slicing is over.  First call: every range block is open.
+//  phase MIN: after the slicing, the range blocks still without a proven first hit get one pass over every domain of their
+//             class (first hit and minimum) -- only threshold searches with brightness bins that want the minimum.
+// A range block stays open while none of its four rows has a hit below the cutoff the last slice scanned to.
+__global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint32_t ordinal) {
+    LevelPlan* p = a.plan;
+    SliceCtl* ctl = a.ctl;
+    __shared__ unsigned long long s_red[8];
+    __shared__ uint32_t s_last;
+    __shared__ uint32_t s_cnt[FE_MAX_TOTAL], s_tiles[FE_MAX_TOTAL];
+    __shared__ uint32_t s_k0, s_k1, s_go;
+    if (phase == FE_PHASE_SLICE && ctl->done) return;
+    if (phase == FE_PHASE_MIN && !(ctl->open && a.use_thr && a.bins && a.need_min)) return;
+    const uint32_t cur = ctl->list;
+    const bool first = phase == FE_PHASE_SLICE && ctl->passes == 0;
+    const uint32_t nxt = first ? cur : cur ^ 1u;
+    if (!first) {
+        // ---- compaction: the open range blocks of list `cur` that stay open go to list `nxt`, bucket regions kept ----
+        const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+        bool alive = false;
+        uint32_t b = 0;
+        ListEntry e{};
+        if (pos < p->nR) {
+            b = a.pos_bucket[pos];
+            if (pos - p->roff[b] < ctl->cnt[cur][b]) {
+                e = a.list[cur][pos];
+                const uint4 h = reinterpret_cast<const uint4*>(a.rowhit)[e.slot];
+                alive = min(min(h.x, h.y), min(h.z, h.w)) >= ctl->cutoff;
+            }
+        }
+        // warp-aggregated append per bucket (positions are sorted by bucket: a warp holds one or two)
+        const uint32_t key = alive ? b : 0xFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (alive) {
+            const uint32_t lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&ctl->cnt[nxt][b], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            a.list[nxt][p->roff[b] + base + __popc(peers & ((1u << lane) - 1))] = e;
+        }
+    }
+    // ---- last CTA plans ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const uint32_t t = threadIdx.x, nb = p->nb, nk = p->nk;
+    unsigned long long before = 0, S = 0;
+    for (uint32_t b = t; b < nb; b += 256) {
+        const uint32_t c = __ldcg(&ctl->cnt[nxt][b]);
+        s_cnt[b] = c;
+        S += c;
+        before += __ldcg(&ctl->cnt[cur][b]);
+    }
+    S = block_sum_u64(S, s_red);
+    before = block_sum_u64(before, s_red);
+    const uint32_t kd = ctl->k_done;
+    const bool whole = phase == FE_PHASE_MIN;
+    // work left for the open range blocks if everything that remains were scanned now
+    unsigned long long left = 0;
+    for (uint32_t c = t; c < nb; c += 256) {
+        if (!s_cnt[c]) continue;
+        unsigned long long cols = 0;
+        for (uint32_t b = grp_lo(p, c, whole); b <= grp_hi(p, c, whole); ++b)
+            cols += (p->doff[b + 1] - p->doff[b]) - ((kd && !whole) ? p->dend[kd - 1][b] : 0u);
+        left += cols * s_cnt[c];
+    }
+    left = block_sum_u64(left, s_red);
+    if (t == 0) {
+        uint32_t go = 1, k0 = 0, k1 = nk - 1;
+        if (phase == FE_PHASE_SLICE) {
+            if (!first) {
+                const double resolved = 1.0 - (double)S / (double)max(before, 1ull);
+                if (S == 0) { go = 0; ctl->open = 0; }
+                // Bins only pay when ranges end on a hit: first slices that close next to nothing say "no hits on this
+                // level" -- the minimum pass will scan everything anyway, go there now.
+                else if (a.bins && a.need_min && ctl->passes <= 2 && resolved < 0.05) go = 0;
+                else if (kd >= nk) go = 0;
+                else {
+                    // slices that close little grow faster; one that closes nothing says early-out will not pay
+                    const uint32_t step = resolved >= 0.03 ? 1u : (resolved >= 0.002 ? 2u : 8u);
+                    k0 = kd;
+                    k1 = min(nk - 1, kd + step - 1);
+                    // what is left is small: one more slice for all of it costs less than several
+                    if ((double)left * 4.0 * 2.0 * (double)a.N <= 1.5e11) k1 = nk - 1;
+                }
+            } else {
+                k0 = 0;
+                k1 = a.multipass ? 0u : nk - 1;
+                if ((double)left * 4.0 * 2.0 * (double)a.N <= 1.5e11) k1 = nk - 1;
+            }
+            if (!go) ctl->done = 1;
+        } else {
+            if (S == 0) go = 0;
+            ctl->open = 0;
+        }
+        s_go = go; s_k0 = k0; s_k1 = k1;
+    }
+    __syncthreads();
+    const uint32_t k0 = s_k0, k1 = s_k1;
+    if (s_go) {
+        // ---- row tiles, candidates and the longest run of the slice ----
+        unsigned long long work = 0;
+        uint32_t maxrun = 0;
+        for (uint32_t c = t; c < nb; c += 256) {
+            unsigned long long cols = 0;
+            if (s_cnt[c]) {
+                const uint32_t lo = grp_lo(p, c, whole), hi = grp_hi(p, c, whole);
+                for (uint32_t b = lo; b <= hi; ++b) cols += p->dend[k1][b] - (k0 ? p->dend[k0 - 1][b] : 0u);
+                for (uint32_t k = k0; k <= k1; ++k) maxrun = max(maxrun, p->tile0[k * nb + hi + 1] - p->tile0[k * nb + lo]);
+            }
+            s_tiles[c] = cols ? (s_cnt[c] + 31) / 32 : 0u;
+            work += cols * s_cnt[c] * 4ull;
+        }
+        work = block_sum_u64(work, s_red);
+        maxrun = block_max_u32(maxrun, s_red);
+        __syncthreads();
+        if (t == 0) {
+            uint32_t acc = 0;
+            for (uint32_t c = 0; c < nb; ++c) { ctl->tile_prefix[c] = acc; acc += s_tiles[c]; }
+            ctl->tile_prefix[nb] = acc;
+            const uint32_t nkk = k1 - k0 + 1;
+            // column chunks: aim at >= 4 work items per SM when there are few row tiles, chunks of >= 4 tiles
+            uint32_t Q = 1;
+            const uint64_t base_items = (uint64_t)acc * nkk;
+            if (base_items && base_items < 4ull * 148) Q = (uint32_t)((4ull * 148 + base_items - 1) / base_items);
+            Q = max(1u, min(Q, min(64u, maxrun / 4)));
+            uint64_t n_items = base_items * Q;
+            if (n_items > a.max_items) { Q = 1; n_items = base_items; }
+            if (n_items > a.max_items) ctl->overflow = 1;
+            ctl->n_row_tiles = acc;
+            ctl->k0 = k0; ctl->k1 = k1; ctl->Q = Q;
+            ctl->whole_group = whole ? 1u : 0u;
+            ctl->no_min = (a.use_thr && (!a.need_min || (a.bins && !whole))) ? 1u : 0u;
+            ctl->n_items = (uint32_t)min(n_items, (uint64_t)a.max_items);
+            ctl->evaluated += work;
+            ctl->passes += 1;
+            ctl->active = ordinal;
+            if (phase == FE_PHASE_SLICE) {
+                ctl->k_done = k1 + 1;
+                ctl->cutoff = (k1 == nk - 1) ? FE_NONE32 : p->cut[k1];
+                if (k1 == nk - 1) ctl->done = 1;       // nothing left to slice (the launches of later ordinals return at once)
+            }
+        }
+    }
+    // the list that was read becomes the target of the next compaction
+    if (!first)
+        for (uint32_t b = t; b < FE_MAX_TOTAL; b += 256) ctl->cnt[cur][b] = 0;
+    if (t == 0) { ctl->list = nxt; ctl->ticket = 0; }
+}
+
+// Work items of the planned slice: (bucket c, row tile, interval k, column chunk q), one record each, in that order.
+__global__ void k_expand_items(PlanArgs a, uint32_t ordinal) {
+    const LevelPlan* p = a.plan;
+    const SliceCtl* ctl = a.ctl;
+    if (ctl->active != ordinal) return;
+    const uint32_t n = ctl->n_items, Q = ctl->Q, k0 = ctl->k0, nkk = ctl->k1 - k0 + 1, nb = p->nb, nt = p->nt;
+    const bool whole = ctl->whole_group != 0;
+    const uint32_t cur = ctl->list;
+    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+        const uint32_t per = nkk * Q, tl = id / per, rem = id - tl * per, k = k0 + rem / Q, q = rem % Q;
+        uint32_t lo = 0, hi = nb - 1;                 // bucket c with tile_prefix[c] <= tl < tile_prefix[c + 1]
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (ctl->tile_prefix[mid] <= tl) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t c = lo, rt = tl - ctl->tile_prefix[c];
+        const uint32_t blo = grp_lo(p, c, whole), bhi = grp_hi(p, c, whole);
+        const uint32_t T0 = p->tile0[k * nb + blo], T1 = p->tile0[k * nb + bhi + 1], nrun = T1 - T0;
+        const uint32_t qe = max(1u, min(Q, nrun / 4));   // short runs are not chunked
+        ItemRec r{};
+        if (q < qe && nrun) {
+            r.t0 = T0 + (uint32_t)(((uint64_t)q * nrun) / qe);
+            r.t1 = T0 + (uint32_t)(((uint64_t)(q + 1) * nrun) / qe);
+            r.pos0 = p->roff[c] + 32 * rt;
+            r.nrows = 4 * min(32u, ctl->cnt[cur][c] - 32 * rt);
+            r.cols_left = (p->dend[k][blo] - (k ? p->dend[k - 1][blo] : 0u)) - (r.t0 - T0) * nt;
+            r.a_tile = tl;
+        }
+        a.items[id] = r;
+    }
+}
+
+__global__ void k_level_summary(const SliceCtl* ctl, const LevelPlan* plan, const uint32_t* counters, const uint32_t* scan_last,
+                                const uint32_t* split_last, LevelSummary* out) {
+    LevelSummary s{};
+    s.mismatch = counters[0]; s.fp32_regime = counters[1]; s.flags = counters[2];
+    if (ctl) { s.passes = ctl->passes; s.evaluated = ctl->evaluated; s.overflow = ctl->overflow; }
+    if (plan)
+        for (uint32_t g = 0; g < plan->ngroups; ++g) {
+            const uint32_t b0 = g * plan->nbins, b1 = b0 + plan->nbins;
+            s.matches += (unsigned long long)(plan->roff[b1] - plan->roff[b0]) * (plan->doff[b1] - plan->doff[b0]) * 4ull;
+        }
+    if (scan_last) { s.last_scan = *scan_last; s.last_flag = *split_last; }
+    *out = s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side: enqueue one level
+// ---------------------------------------------------------------------------------------------------
+static inline uint32_t cdiv_u(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+void fe_plan_bins(uint32_t N, uint32_t thr16, fe_threshold_plan* pl);   // fe_api.cu
+
+#define PLAUNCH(ctx, kernel, grid, block, ...)                         \
+    do {                                                               \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);    \
+        (ctx)->stats.kernel_launches++;                                \
+        FE_CUDA(ctx, cudaGetLastError());                              \
+    } while (0)
+
+int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, DeviceLevelState* st) {
+    const LevelGeom& g = lv.g;
+    const uint32_t nD = lv.nD, nR = lv.nR;
+    const uint32_t nt = kind == 0 ? (uint32_t)UM_NT : (uint32_t)I8_NT;
+    const bool multipass = lv.use_thr && !getenv("FE_SINGLE_PASS");
+    *st = DeviceLevelState{};
+    // ---- brightness bins (host arithmetic only) ----
+    uint32_t width = 0;
+    if (multipass && !getenv("FE_NO_BINS")) {
+        fe_threshold_plan pl{};
+        fe_plan_bins(g.N, lv.thr16, &pl);
+        if (pl.n_bins) { st->bins = true; st->nbins = pl.n_bins; st->span = pl.bin_span; width = pl.bin_width; }
+    }
+    st->ngroups = lv.dom_cls ? 7u : 1u;
+    const uint32_t nb = st->ngroups * st->nbins;
+    if (nb > (uint32_t)FE_MAX_TOTAL) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "internal: %u buckets", nb);
+    const bool sorted = nb > 1;
+    const uint32_t max_tiles = cdiv_u(nD, nt) + nb + 1;
+    const uint32_t max_items = std::max<uint32_t>((nR / 32 + nb) * FE_NK, 4 * 148 * 2);
+
+    // ---- buffers ----
+    const size_t n = (size_t)nD + nR;
+    FE_CUDA(ctx, ctx->b_keys_tmp.ensure(n * 6 + 512));
+    FE_CUDA(ctx, ctx->b_vals_tmp.ensure((size_t)std::max(nD, nR) * 4));
+    FE_CUDA(ctx, ctx->b_dom_order2.ensure((size_t)nD * 4 + 16));
+    FE_CUDA(ctx, ctx->b_rng_order2.ensure((size_t)nR * 4 + 16));
+    FE_CUDA(ctx, ctx->b_hist.ensure((size_t)FE_MAX_TOTAL * 10 * 4 + 2 * FE_MAX_BUCKETS * 4));
+    FE_CUDA(ctx, ctx->b_plan.ensure(sizeof(LevelPlan)));
+    FE_CUDA(ctx, ctx->b_ctl.ensure(sizeof(SliceCtl)));
+    FE_CUDA(ctx, ctx->b_list[0].ensure((size_t)nR * sizeof(ListEntry) + 16));
+    FE_CUDA(ctx, ctx->b_list[1].ensure((size_t)nR * sizeof(ListEntry) + 16));
+    FE_CUDA(ctx, ctx->b_itemrec.ensure((size_t)max_items * sizeof(ItemRec)));
+    FE_CUDA(ctx, ctx->b_posb.ensure((size_t)nR * 2 + 16));
+    FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)nR * 4 + 16));
+    uint8_t* bins8 = ctx->b_keys_tmp.as<uint8_t>();
+    uint16_t* keys = reinterpret_cast<uint16_t*>(bins8 + ((n + 255) & ~(size_t)255));
+    uint16_t* keys_out = keys + n;
+    uint32_t* hist_d = ctx->b_hist.as<uint32_t>();
+    uint32_t* hist_r = hist_d + FE_MAX_TOTAL;
+    uint32_t* pre = hist_d + 2 * FE_MAX_TOTAL;
+    uint32_t* scratch = pre + FE_MAX_TOTAL * 8;
+    FE_CUDA(ctx, cudaMemsetAsync(hist_d, 0, ((size_t)FE_MAX_TOTAL * 10 + 2 * FE_MAX_BUCKETS) * 4, ctx->stream));
+
+    // ---- bucket keys, orders ----
+    if (st->bins) {
+        launch_brightness_bins(ctx->stream, ctx->src.px, ctx->src.stride, lv.d_dom, nD, g.S, 1u, width, bins8, scratch);
+        launch_brightness_bins(ctx->stream, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, nR, g.T, 4u, width, bins8 + nD, scratch + FE_MAX_BUCKETS);
+        ctx->stats.kernel_launches += 2;
+        FE_CUDA(ctx, cudaGetLastError());
+    }
+    PLAUNCH(ctx, k_bucket_keys, cdiv_u(nD, 256), 256, lv.dom_cls, st->bins ? bins8 : nullptr, nD, st->nbins, keys, hist_d);
+    PLAUNCH(ctx, k_bucket_keys, cdiv_u(nR, 256), 256, lv.rng_cls, st->bins ? bins8 + nD : nullptr, nR, st->nbins, keys + nD, hist_r);
+    if (sorted) {
+        int bits = 1;
+        while ((1u << bits) < nb) ++bits;
+        PLAUNCH(ctx, k_iota, cdiv_u(std::max(nD, nR), 256), 256, ctx->b_vals_tmp.as<uint32_t>(), std::max(nD, nR));
+        size_t tmp_d = 0, tmp_r = 0;
+        FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_d, keys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order2.as<uint32_t>(), (int)nD, 0, bits, ctx->stream));
+        FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_r, keys + nD, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order2.as<uint32_t>(), (int)nR, 0, bits, ctx->stream));
+        FE_CUDA(ctx, ctx->b_sort_tmp.ensure(std::max(tmp_d, tmp_r)));
+        FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_d, keys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order2.as<uint32_t>(), (int)nD, 0, bits, ctx->stream));
+        FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_r, keys + nD, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order2.as<uint32_t>(), (int)nR, 0, bits, ctx->stream));
+        ctx->stats.kernel_launches += 6;
+        st->dom_order = ctx->b_dom_order2.as<uint32_t>();
+        st->rng_order = ctx->b_rng_order2.as<uint32_t>();
+    }
+    BucketOff c8{};
+    for (int k = 0; k < FE_NK; ++k) c8.v[k] = !multipass ? FE_NONE32 : (k == FE_NK - 1 ? nD : (uint32_t)((((uint64_t)nD) << k) / 128 + 1));
+    PLAUNCH(ctx, k_bin_prefix, cdiv_u((uint64_t)nb * 8, 128), 128, st->dom_order, hist_d, (int)nb, c8, pre);
+
+    // ---- the level's plan, first list, operand blob ----
+    PlanArgs pa{};
+    pa.plan = ctx->b_plan.as<LevelPlan>();
+    pa.ctl = ctx->b_ctl.as<SliceCtl>();
+    pa.list[0] = ctx->b_list[0].as<ListEntry>();
+    pa.list[1] = ctx->b_list[1].as<ListEntry>();
+    pa.items = ctx->b_itemrec.as<ItemRec>();
+    pa.rowhit = ctx->b_rowhit.as<uint32_t>();
+    pa.pos_bucket = ctx->b_posb.as<uint16_t>();
+    pa.N = g.N;
+    pa.use_thr = lv.use_thr; pa.need_min = lv.need_min; pa.bins = st->bins; pa.multipass = multipass;
+    const char* ms_env = getenv("FE_MIN_STEP");      // tuning: column tiles (of 128) a bucket advances per interval at least
+    pa.min_tiles = ms_env ? (uint32_t)std::max(1, atoi(ms_env)) : (st->bins ? (uint32_t)std::max(2, 10 / (2 * (int)st->span + 1)) : 16u);
+    pa.max_items = max_items;
+    PLAUNCH(ctx, k_level_plan, 1, 512, pa, hist_d, hist_r, pre, nb, st->nbins, st->ngroups, st->span, nD, nR, nt);
+    PLAUNCH(ctx, k_level_ranges, cdiv_u(nR, 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T, kind == 0 ? 1 : 0,
+            pa.list[0], ctx->b_rowc.as<uint32_t>(), ctx->b_posb.as<uint16_t>());
+    PLAUNCH(ctx, k_fill_u64, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
+    PLAUNCH(ctx, k_fill_u32, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
+    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));
+    if (kind != 0) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "internal: device-scheduled i8 kind not built");
+    FE_TRY(f16_build_pool(ctx, g, lv.d_dom, st->dom_order, pa.plan, max_tiles));
+
+    F16Args fa{};
+    fa.img = ctx->tgt.px; fa.stride = ctx->tgt.stride;
+    fa.B16 = ctx->b_B16.p;
+    fa.colmeta = ctx->b_tmaps.as<uint4>();
+    fa.blob_dom = ctx->b_blob_dom.as<uint32_t>();
+    fa.list[0] = pa.list[0]; fa.list[1] = pa.list[1];
+    fa.items = pa.items;
+    fa.ctl = pa.ctl;
+    fa.rowA2 = ctx->b_rowc.as<uint32_t>();
+    fa.rowbest = ctx->b_rowbest.as<unsigned long long>();
+    fa.rowhit = ctx->b_rowhit.as<uint32_t>();
+    fa.flags = ctx->b_counters.as<uint32_t>() + 2;
+    fa.thr16 = lv.thr16; fa.use_thr = lv.use_thr ? 1u : 0u;
+    const bool retire = lv.use_thr && g.T == 4;
+    const uint32_t plan_grid = cdiv_u(nR, 256);
+    const uint32_t n_slices = multipass ? (uint32_t)FE_NK : 1u;
+    auto slice = [&](int phase, uint32_t ordinal, bool meta) -> int {
+        PLAUNCH(ctx, k_slice_plan, plan_grid, 256, pa, phase, ordinal);
+        PLAUNCH(ctx, k_expand_items, 2 * 148, 256, pa, ordinal);
+        fa.ordinal = ordinal;
+        cudaEvent_t e0 = lv.timed ? ctx->ev_pass[2 * st->n_launches] : nullptr, e1 = lv.timed ? ctx->ev_pass[2 * st->n_launches + 1] : nullptr;
+        FE_TRY(f16_launch_search(ctx, g, fa, retire, meta, e0, e1));
+        ++st->n_launches;
+        return FE_OK;
+    };
+    for (uint32_t s = 0; s < n_slices; ++s) FE_TRY(slice(FE_PHASE_SLICE, s, st->span > 0));
+    if (st->bins && lv.need_min) FE_TRY(slice(FE_PHASE_MIN, FE_NK, true));
+    return FE_OK;
+}

@@ -1,5 +1,7 @@
 // fe_umma_dev.cuh -- device-side PTX wrappers shared by the tcgen05 search kernels (fp16 and int8 kinds).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "fe_umma.cuh"
 
 namespace umma_dev {
@@ -106,6 +108,28 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// T bytes at p as T/4 little-endian words
+template <int T>
+__device__ __forceinline__ void load_px(const uint8_t* __restrict__ p, uint32_t (&w)[T / 4]) {
+    if ((reinterpret_cast<uintptr_t>(p) & (T - 1)) == 0) {
+        if constexpr (T == 4) {
+            w[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+        } else {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+            w[0] = v.x; w[1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < T / 4; ++i)
+            w[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+    }
 }
 
 struct WorkItem {
