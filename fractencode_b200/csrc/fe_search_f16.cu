@@ -317,6 +317,18 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
                             atomicMin(&a.rowhit[srow], a.blob_dom[(size_t)item_t0 * UM_NT + st.hit]);
                             st.hit = FE_NONE32;
                         }
+                        // Same for the running minimum: "first column wins a tie" is only "smallest domain index wins" inside a
+                        // chunk.  Bank it (the 64-bit key settles ties by domain index) and go on from its score plus one, so
+                        // that an equal score in the next chunk is still looked at.
+                        if (st.bestcol != FE_NONE32) {
+                            if (st.bestp == 2) st.bestp = row_parity(st, st.bestcol);
+                            const long long d = 2ll * (long long)st.bestV + (long long)st.bestp;
+                            atomicMin(&a.rowbest[srow], ((unsigned long long)(uint32_t)((long long)a2 + d) << 32) |
+                                                            (unsigned long long)a.blob_dom[(size_t)item_t0 * UM_NT + st.bestcol]);
+                            if (st.bestV >= 16777216.0f - 64.0f) atomicOr(a.flags, 1u);
+                            const long long V = (d + 1) >= 0 ? (d + 1) / 2 : -((-(d + 1) + 1) / 2);
+                            st.bestV = (float)V; st.bestp = (uint32_t)(d + 1 - 2 * V); st.bestcol = FE_NONE32;
+                        }
                         cur_seg = meta.w;
                         if (RETIRE) { retired = !row_ok; warp_done = false; }
                     }
