@@ -1032,6 +1032,7 @@ static int run_level_complete(fe_ctx* ctx, const LevelIO& io, const fe_params& p
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->ev_pass[2 * i], ctx->ev_pass[2 * i + 1]);
             kernel_ms += ms;
+            if (getenv("FE_PASS_TIMES")) fprintf(stderr, "[level] T=%u search launch %u: %.3f ms\n", g.T, i, ms);
         }
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]);

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "fe_kernels.cuh"
@@ -33,16 +34,6 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
     for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t += sh[w];
     return t;
 }
-__device__ __forceinline__ uint32_t block_max_u32(uint32_t v, unsigned long long* sh) {
-    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    uint32_t t = 0;
-    for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t = max(t, (uint32_t)sh[w]);
-    return t;
-}
-
 } // namespace
 
 // key = (class + 1) * nbins + bin (class 0 when cls is NULL, bin 0 when bins is NULL); hist[key] counts.
@@ -135,7 +126,7 @@ __global__ void __launch_bounds__(512) k_level_plan(PlanArgs a, const uint32_t* 
 // else 16 sum r^2, i8 kind) and the bucket of the position.
 __global__ void k_level_ranges(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
                                const uint32_t* __restrict__ order, const LevelPlan* __restrict__ plan, uint32_t T, int centred,
-                               ListEntry* __restrict__ list0, uint32_t* __restrict__ rowA2, uint16_t* __restrict__ pos_bucket) {
+                               ListEntry* __restrict__ list0, uint16_t* __restrict__ pos_bucket) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= plan->nR) return;
     const fe_grid_item r = rng[order ? order[p] : p];
@@ -146,10 +137,11 @@ __global__ void k_level_ranges(const uint8_t* __restrict__ img, uint32_t stride,
             const int v = centred ? 4 * (int)base[(size_t)y * stride + x] - 510 : 4 * (int)base[(size_t)y * stride + x];
             s2 += (uint32_t)(v * v);
         }
-    rowA2[p] = s2;
     ListEntry e;
     e.slot = p;
     e.xy = r.x | (r.y << 16);
+    e.a2 = s2;
+    e.pad_ = 0;
     list0[p] = e;
     uint32_t lo = 0, hi = plan->nb - 1;               // bucket b with roff[b] <= p < roff[b + 1]
     while (lo < hi) {
@@ -189,6 +181,9 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
                 const uint4 h = reinterpret_cast<const uint4*>(a.rowhit)[e.slot];
                 alive = min(min(h.x, h.y), min(h.z, h.w)) >= ctl->cutoff;
             }
+            // minimum pass: a range block meets every domain of its class, so the survivors of a class share row tiles --
+            // they are gathered in the region of the class's first bucket
+            if (phase == FE_PHASE_MIN) b = (b / p->nbins) * p->nbins;
         }
         // warp-aggregated append per bucket (positions are sorted by bucket: a warp holds one or two)
         const uint32_t key = alive ? b : 0xFFFFu;
@@ -263,40 +258,48 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
     __syncthreads();
     const uint32_t k0 = s_k0, k1 = s_k1;
     if (s_go) {
-        // ---- row tiles, candidates and the longest run of the slice ----
-        unsigned long long work = 0;
-        uint32_t maxrun = 0;
+        // ---- candidates and tile steps (row tiles x column tiles) of the slice ----
+        unsigned long long work = 0, steps = 0;
         for (uint32_t c = t; c < nb; c += 256) {
-            unsigned long long cols = 0;
+            unsigned long long cols = 0, run = 0;
             if (s_cnt[c]) {
                 const uint32_t lo = grp_lo(p, c, whole), hi = grp_hi(p, c, whole);
                 for (uint32_t b = lo; b <= hi; ++b) cols += p->dend[k1][b] - (k0 ? p->dend[k0 - 1][b] : 0u);
-                for (uint32_t k = k0; k <= k1; ++k) maxrun = max(maxrun, p->tile0[k * nb + hi + 1] - p->tile0[k * nb + lo]);
+                for (uint32_t k = k0; k <= k1; ++k) run += p->tile0[k * nb + hi + 1] - p->tile0[k * nb + lo];
             }
             s_tiles[c] = cols ? (s_cnt[c] + 31) / 32 : 0u;
             work += cols * s_cnt[c] * 4ull;
+            steps += run * s_tiles[c];
         }
         work = block_sum_u64(work, s_red);
-        maxrun = block_max_u32(maxrun, s_red);
+        steps = block_sum_u64(steps, s_red);
+        // Work items of about equal length: long runs are cut so that every SM gets eight items or more, short runs stay
+        // whole (an item pays for its A tile and for filling the pipeline: never below 16 column tiles).
+        const uint32_t run_len = (uint32_t)min(max(steps / (8ull * a.n_sm), 16ull), 1ull << 20);
+        __syncthreads();
+        for (uint32_t c = t; c < nb; c += 256) {
+            uint32_t per_tile = 0;
+            if (s_tiles[c]) {
+                const uint32_t lo = grp_lo(p, c, whole), hi = grp_hi(p, c, whole);
+                for (uint32_t k = k0; k <= k1; ++k) {
+                    const uint32_t nrun = p->tile0[k * nb + hi + 1] - p->tile0[k * nb + lo];
+                    per_tile += (nrun + run_len - 1) / run_len;
+                }
+            }
+            s_cnt[c] = s_tiles[c] * per_tile;          // work items of the bucket (s_cnt is not needed any more)
+        }
         __syncthreads();
         if (t == 0) {
-            uint32_t acc = 0;
-            for (uint32_t c = 0; c < nb; ++c) { ctl->tile_prefix[c] = acc; acc += s_tiles[c]; }
-            ctl->tile_prefix[nb] = acc;
-            const uint32_t nkk = k1 - k0 + 1;
-            // column chunks: aim at >= 4 work items per SM when there are few row tiles, chunks of >= 4 tiles
-            uint32_t Q = 1;
-            const uint64_t base_items = (uint64_t)acc * nkk;
-            if (base_items && base_items < 4ull * 148) Q = (uint32_t)((4ull * 148 + base_items - 1) / base_items);
-            Q = max(1u, min(Q, min(64u, maxrun / 4)));
-            uint64_t n_items = base_items * Q;
-            if (n_items > a.max_items) { Q = 1; n_items = base_items; }
-            if (n_items > a.max_items) ctl->overflow = 1;
-            ctl->n_row_tiles = acc;
-            ctl->k0 = k0; ctl->k1 = k1; ctl->Q = Q;
+            uint64_t acc = 0;
+            uint32_t tiles = 0;
+            for (uint32_t c = 0; c < nb; ++c) { ctl->item_prefix[c] = (uint32_t)min(acc, (uint64_t)0xFFFFFFFFull); acc += s_cnt[c]; tiles += s_tiles[c]; }
+            ctl->item_prefix[nb] = (uint32_t)min(acc, (uint64_t)0xFFFFFFFFull);
+            if (acc > a.max_items) ctl->overflow = 1;
+            ctl->n_row_tiles = tiles;
+            ctl->k0 = k0; ctl->k1 = k1; ctl->run_len = run_len;
             ctl->whole_group = whole ? 1u : 0u;
             ctl->no_min = (a.use_thr && (!a.need_min || (a.bins && !whole))) ? 1u : 0u;
-            ctl->n_items = (uint32_t)min(n_items, (uint64_t)a.max_items);
+            ctl->n_items = (uint32_t)min(acc, (uint64_t)a.max_items);
             ctl->evaluated += work;
             ctl->passes += 1;
             ctl->active = ordinal;
@@ -313,33 +316,39 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
     if (t == 0) { ctl->list = nxt; ctl->ticket = 0; }
 }
 
-// Work items of the planned slice: (bucket c, row tile, interval k, column chunk q), one record each, in that order.
+// Work items of the planned slice: (bucket c, row tile, interval k, piece of the run), one record each, in that order.
 __global__ void k_expand_items(PlanArgs a, uint32_t ordinal) {
     const LevelPlan* p = a.plan;
     const SliceCtl* ctl = a.ctl;
     if (ctl->active != ordinal) return;
-    const uint32_t n = ctl->n_items, Q = ctl->Q, k0 = ctl->k0, nkk = ctl->k1 - k0 + 1, nb = p->nb, nt = p->nt;
+    const uint32_t n = ctl->n_items, L = ctl->run_len, k0 = ctl->k0, k1 = ctl->k1, nb = p->nb, nt = p->nt;
     const bool whole = ctl->whole_group != 0;
     const uint32_t cur = ctl->list;
     for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
-        const uint32_t per = nkk * Q, tl = id / per, rem = id - tl * per, k = k0 + rem / Q, q = rem % Q;
-        uint32_t lo = 0, hi = nb - 1;                 // bucket c with tile_prefix[c] <= tl < tile_prefix[c + 1]
+        uint32_t lo = 0, hi = nb - 1;                 // bucket c with item_prefix[c] <= id < item_prefix[c + 1]
         while (lo < hi) {
             const uint32_t mid = (lo + hi + 1) >> 1;
-            if (ctl->tile_prefix[mid] <= tl) lo = mid; else hi = mid - 1;
+            if (ctl->item_prefix[mid] <= id) lo = mid; else hi = mid - 1;
         }
-        const uint32_t c = lo, rt = tl - ctl->tile_prefix[c];
-        const uint32_t blo = grp_lo(p, c, whole), bhi = grp_hi(p, c, whole);
-        const uint32_t T0 = p->tile0[k * nb + blo], T1 = p->tile0[k * nb + bhi + 1], nrun = T1 - T0;
-        const uint32_t qe = max(1u, min(Q, nrun / 4));   // short runs are not chunked
+        const uint32_t c = lo, blo = grp_lo(p, c, whole), bhi = grp_hi(p, c, whole);
+        const uint32_t cnt = ctl->cnt[cur][c], ntile = (cnt + 31) / 32;
+        const uint32_t per_tile = (ctl->item_prefix[c + 1] - ctl->item_prefix[c]) / ntile;
+        uint32_t rem = id - ctl->item_prefix[c];
+        const uint32_t rt = rem / per_tile;
+        rem -= rt * per_tile;
         ItemRec r{};
-        if (q < qe && nrun) {
-            r.t0 = T0 + (uint32_t)(((uint64_t)q * nrun) / qe);
-            r.t1 = T0 + (uint32_t)(((uint64_t)(q + 1) * nrun) / qe);
-            r.pos0 = p->roff[c] + 32 * rt;
-            r.nrows = 4 * min(32u, ctl->cnt[cur][c] - 32 * rt);
-            r.cols_left = (p->dend[k][blo] - (k ? p->dend[k - 1][blo] : 0u)) - (r.t0 - T0) * nt;
-            r.a_tile = tl;
+        for (uint32_t k = k0; k <= k1; ++k) {
+            const uint32_t T0 = p->tile0[k * nb + blo], nrun = p->tile0[k * nb + bhi + 1] - T0, q = (nrun + L - 1) / L;
+            if (rem < q) {
+                r.t0 = T0 + (uint32_t)(((uint64_t)rem * nrun) / q);
+                r.t1 = T0 + (uint32_t)(((uint64_t)(rem + 1) * nrun) / q);
+                r.pos0 = p->roff[c] + 32 * rt;
+                r.nrows = 4 * min(32u, cnt - 32 * rt);
+                r.cols_left = (p->dend[k][blo] - (k ? p->dend[k - 1][blo] : 0u)) - (r.t0 - T0) * nt;
+                r.a_tile = 0;
+                break;
+            }
+            rem -= q;
         }
         a.items[id] = r;
     }
@@ -391,7 +400,7 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, DeviceLeve
     if (nb > (uint32_t)FE_MAX_TOTAL) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "internal: %u buckets", nb);
     const bool sorted = nb > 1;
     const uint32_t max_tiles = cdiv_u(nD, nt) + nb + 1;
-    const uint32_t max_items = std::max<uint32_t>((nR / 32 + nb) * FE_NK, 4 * 148 * 2);
+    const uint32_t max_items = (nR / 32 + nb) * FE_NK + 8 * (uint32_t)ctx->n_sm + 64;   // row tiles x intervals + pieces of long runs
 
     // ---- buffers ----
     const size_t n = (size_t)nD + nR;
@@ -406,7 +415,6 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, DeviceLeve
     FE_CUDA(ctx, ctx->b_list[1].ensure((size_t)nR * sizeof(ListEntry) + 16));
     FE_CUDA(ctx, ctx->b_itemrec.ensure((size_t)max_items * sizeof(ItemRec)));
     FE_CUDA(ctx, ctx->b_posb.ensure((size_t)nR * 2 + 16));
-    FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)nR * 4 + 16));
     uint8_t* bins8 = ctx->b_keys_tmp.as<uint8_t>();
     uint16_t* keys = reinterpret_cast<uint16_t*>(bins8 + ((n + 255) & ~(size_t)255));
     uint16_t* keys_out = keys + n;
@@ -457,9 +465,10 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, DeviceLeve
     const char* ms_env = getenv("FE_MIN_STEP");      // tuning: column tiles (of 128) a bucket advances per interval at least
     pa.min_tiles = ms_env ? (uint32_t)std::max(1, atoi(ms_env)) : (st->bins ? (uint32_t)std::max(2, 10 / (2 * (int)st->span + 1)) : 16u);
     pa.max_items = max_items;
+    pa.n_sm = (uint32_t)ctx->n_sm;
     PLAUNCH(ctx, k_level_plan, 1, 512, pa, hist_d, hist_r, pre, nb, st->nbins, st->ngroups, st->span, nD, nR, nt);
     PLAUNCH(ctx, k_level_ranges, cdiv_u(nR, 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T, kind == 0 ? 1 : 0,
-            pa.list[0], ctx->b_rowc.as<uint32_t>(), ctx->b_posb.as<uint16_t>());
+            pa.list[0], ctx->b_posb.as<uint16_t>());
     PLAUNCH(ctx, k_fill_u64, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
     PLAUNCH(ctx, k_fill_u32, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));
@@ -474,12 +483,12 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, DeviceLeve
     fa.list[0] = pa.list[0]; fa.list[1] = pa.list[1];
     fa.items = pa.items;
     fa.ctl = pa.ctl;
-    fa.rowA2 = ctx->b_rowc.as<uint32_t>();
     fa.rowbest = ctx->b_rowbest.as<unsigned long long>();
     fa.rowhit = ctx->b_rowhit.as<uint32_t>();
     fa.flags = ctx->b_counters.as<uint32_t>() + 2;
     fa.thr16 = lv.thr16; fa.use_thr = lv.use_thr ? 1u : 0u;
     const bool retire = lv.use_thr && g.T == 4;
+    const bool pass_dbg = getenv("FE_PASS_DBG") != nullptr;
     const uint32_t plan_grid = cdiv_u(nR, 256);
     const uint32_t n_slices = multipass ? (uint32_t)FE_NK : 1u;
     auto slice = [&](int phase, uint32_t ordinal, bool meta) -> int {
@@ -489,6 +498,16 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, DeviceLeve
         cudaEvent_t e0 = lv.timed ? ctx->ev_pass[2 * st->n_launches] : nullptr, e1 = lv.timed ? ctx->ev_pass[2 * st->n_launches + 1] : nullptr;
         FE_TRY(f16_launch_search(ctx, g, fa, retire, meta, e0, e1));
         ++st->n_launches;
+        if (pass_dbg) {                                // debugging aid: synchronises after every launch
+            SliceCtl* h = new SliceCtl;
+            cudaStreamSynchronize(ctx->stream);
+            cudaMemcpy(h, pa.ctl, sizeof(SliceCtl), cudaMemcpyDeviceToHost);
+            float ms = 0;
+            if (e0) cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "[slice] T=%u ordinal=%u ran=%d k=%u..%u run_len=%u items=%u row_tiles=%u passes=%u evaluated=%.3e done=%u open=%u kernel %.3f ms\n", g.T,
+                    ordinal, h->active == ordinal, h->k0, h->k1, h->run_len, h->n_items, h->n_row_tiles, h->passes, (double)h->evaluated, h->done, h->open, ms);
+            delete h;
+        }
         return FE_OK;
     };
     for (uint32_t s = 0; s < n_slices; ++s) FE_TRY(slice(FE_PHASE_SLICE, s, st->span > 0));

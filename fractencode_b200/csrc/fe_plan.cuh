@@ -31,10 +31,13 @@ struct LevelPlan {
     uint32_t tile0[FE_NK * FE_MAX_TOTAL + 1];   // first blob tile of chunk k * nb + b; [nk * nb] = n_tiles
 };
 
-// One open range block of the level: its result slot (level position) and its origin.
-struct ListEntry {
+// One open range block of the level: its result slot (level position), its origin and its norm -- everything a search
+// item needs about the block in one 16-byte load.
+struct __align__(16) ListEntry {
     uint32_t slot;
     uint32_t xy;                          // x | y << 16
+    uint32_t a2;                          // f16 kind: sum (4 r - 510)^2; i8 kind: 16 sum r^2
+    uint32_t pad_;
 };
 
 // One work item of a slice: a row tile (up to 32 range blocks = 128 rows) against a run of blob tiles.
@@ -61,12 +64,13 @@ struct SliceCtl {
     // ---- the slice about to run ----
     uint32_t active;                      // ordinal of the planned slice: the expand / search launches of that ordinal run it
     uint32_t overflow;                    // the item buffer was too small (host sizing bug): the level is invalid
-    uint32_t k0, k1, Q;                   // intervals of the slice, column chunks per run
+    uint32_t k0, k1;                      // intervals of the slice
+    uint32_t run_len;                     // runs are cut into work items of about this many column tiles
     uint32_t whole_group;                 // runs cover every bucket of the group (minimum pass)
     uint32_t no_min;
     uint32_t n_items;
     uint32_t n_row_tiles;
-    uint32_t tile_prefix[FE_MAX_TOTAL + 1];   // row tiles of the buckets before b
+    uint32_t item_prefix[FE_MAX_TOTAL + 1];   // work items of the buckets before b
 };
 
 // Level constants the planner needs (kernel parameter).
@@ -81,6 +85,7 @@ struct PlanArgs {
     uint32_t use_thr, need_min, bins, multipass;
     uint32_t min_tiles;                   // column tiles a bucket advances per interval at least
     uint32_t max_items;
+    uint32_t n_sm;
 };
 
 enum { FE_PHASE_SLICE = 0, FE_PHASE_MIN = 1 };
@@ -88,7 +93,7 @@ enum { FE_PHASE_SLICE = 0, FE_PHASE_MIN = 1 };
 __global__ void k_level_plan(PlanArgs a, const uint32_t* dom_hist, const uint32_t* rng_hist, const uint32_t* pre, uint32_t nb, uint32_t nbins,
                              uint32_t ngroups, uint32_t span, uint32_t nD, uint32_t nR, uint32_t nt);
 __global__ void k_level_ranges(const uint8_t* img, uint32_t stride, const fe_grid_item* rng, const uint32_t* order, const LevelPlan* plan,
-                               uint32_t T, int centred, ListEntry* list0, uint32_t* rowA2, uint16_t* pos_bucket);
+                               uint32_t T, int centred, ListEntry* list0, uint16_t* pos_bucket);
 __global__ void k_slice_plan(PlanArgs a, int phase, uint32_t ordinal);
 __global__ void k_expand_items(PlanArgs a, uint32_t ordinal);
 
@@ -131,7 +136,6 @@ struct F16Args {
     const ListEntry* list[2];
     const ItemRec* items;
     const SliceCtl* ctl;
-    const uint32_t* rowA2;
     unsigned long long* rowbest;
     uint32_t* rowhit;
     uint32_t* flags;

@@ -29,24 +29,24 @@ using namespace umma_dev;
 
 constexpr int F16_THREADS = 768;
 constexpr int F16_STAGES = 8;              // two B stages per issuer
+constexpr int F16_ABUFS = 3;               // A tiles in shared memory (T = 8: 3 x 20 KB + 8 x 20 KB of B stages = 220 KB)
 constexpr int F16_ISSUERS = 4;
 constexpr int F16_BUILDERS = 4;
 
 // Rows 4 r + k (k = 0..3) of the A tile: range block r of the item under the inverse of rotation k, values 510 - 4 p, then
 // the constant columns [1, 2048, 2048].  Lane = (r, k); the four lanes of a block read the same 64 pixels.
 template <int T>
-__device__ __forceinline__ void build_rows(uint8_t* sAbuf, const uint8_t* __restrict__ img, uint32_t stride, const ListEntry* __restrict__ list,
-                                           uint32_t pos0, uint32_t nrows, uint32_t bw, uint32_t lane) {
+__device__ __forceinline__ void build_rows(uint8_t* sAbuf, const uint8_t* __restrict__ img, uint32_t stride, uint32_t xy, bool valid, uint32_t bw,
+                                           uint32_t lane) {
     constexpr int N = T * T, KPAD = (N + 3 + 15) & ~15, NCH = KPAD / 8, W = T / 4;
     const uint32_t r = bw * 8 + (lane >> 2), k = lane & 3u;
     uint4* out = reinterpret_cast<uint4*>(sAbuf) + (4 * r + k);          // K chunk ch of this row: out[ch * UM_ROWS]
-    if (4 * r >= nrows) {
+    if (!valid) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) out[ch * UM_ROWS] = make_uint4(0, 0, 0, 0);
         return;
     }
-    const uint2 ent = __ldg(reinterpret_cast<const uint2*>(list + pos0 + r));
-    const uint8_t* base = img + (size_t)(ent.y >> 16) * stride + (ent.y & 0xFFFFu);
+    const uint8_t* base = img + (size_t)(xy >> 16) * stride + (xy & 0xFFFFu);
     uint32_t o[T][W];
 #pragma unroll
     for (int y = 0; y < T; ++y) load_px<T>(base + (size_t)y * stride, o[y]);
@@ -96,6 +96,7 @@ template <int T, bool RETIRE, bool META>
 __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) {
     constexpr uint32_t N = T * T, KPAD = (N + 3 + 15) & ~15u;
     constexpr uint32_t bytesA = UM_ROWS * KPAD * 2, bytesB = UM_NT * KPAD * 2;
+    constexpr uint32_t NA = F16_ABUFS;                     // A tiles in flight: the builders run up to NA - 1 items ahead
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SliceCtl* __restrict__ ctl = a.ctl;
@@ -105,25 +106,25 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
     const uint32_t no_min = ctl->no_min;
     const ListEntry* __restrict__ list = a.list[ctl->list];
 
-    uint8_t* sA = smem;                                    // 2 buffers
-    uint8_t* sB = smem + 2 * bytesA;                       // F16_STAGES stages
+    uint8_t* sA = smem;                                    // NA buffers
+    uint8_t* sB = smem + NA * bytesA;                      // F16_STAGES stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)F16_STAGES * bytesB);
     const uint32_t bar0 = smem_u32(bars);
-    auto A_FULL = [&](uint32_t i) { return bar0 + 8 * (0 + i); };
-    auto A_EMPTY = [&](uint32_t i) { return bar0 + 8 * (2 + i); };
-    auto ACC_FULL = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (4 + 2 * g + b); };
-    auto ACC_EMPTY = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (8 + 2 * g + b); };
-    auto B_FULL = [&](uint32_t i) { return bar0 + 8 * (12 + i); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + F16_STAGES);
+    auto ACC_FULL = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (0 + 2 * g + b); };
+    auto ACC_EMPTY = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (4 + 2 * g + b); };
+    auto B_FULL = [&](uint32_t i) { return bar0 + 8 * (8 + i); };
+    auto A_FULL = [&](uint32_t i) { return bar0 + 8 * (8 + F16_STAGES + i); };
+    auto A_EMPTY = [&](uint32_t i) { return bar0 + 8 * (8 + F16_STAGES + NA + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + F16_STAGES + 2 * NA);
 
     if (threadIdx.x == 0) {
-        for (uint32_t i = 0; i < 2; ++i) {
+        for (uint32_t i = 0; i < NA; ++i) {
             mbar_init(A_FULL(i), F16_BUILDERS);            // one arrive per builder warp
             mbar_init(A_EMPTY(i), F16_ISSUERS);
         }
         for (uint32_t i = 0; i < 4; ++i) {
-            mbar_init(bar0 + 8 * (4 + i), 1);              // ACC_FULL: one tcgen05.commit
-            mbar_init(bar0 + 8 * (8 + i), 8);              // ACC_EMPTY: one arrive per compute warp of the warpgroup
+            mbar_init(bar0 + 8 * (0 + i), 1);              // ACC_FULL: one tcgen05.commit
+            mbar_init(bar0 + 8 * (4 + i), 8);              // ACC_EMPTY: one arrive per compute warp of the warpgroup
         }
         for (uint32_t i = 0; i < (uint32_t)F16_STAGES; ++i) mbar_init(B_FULL(i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -166,10 +167,10 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
             auto next_item = [&](Cursor& c, bool is_mm) {
                 if (is_mm) {
                     // An issuer without a tile in this item must not sign it off before the item's A tile exists: it could run
-                    // two items ahead and arrive twice on the same A_EMPTY phase.  Waiting for A_FULL orders it behind the
-                    // completion of the item two back, like the issuers that do have tiles.
-                    if (!mm_had_tiles) mbar_wait(A_FULL(c.wi & 1), (c.wi >> 1) & 1);
-                    if (mm_had_tiles) tc_commit(A_EMPTY(c.wi & 1)); else mbar_arrive(A_EMPTY(c.wi & 1));
+                    // NA items ahead and arrive twice on the same A_EMPTY phase.  Waiting for A_FULL orders it behind the
+                    // completion of the item NA back (the builders wait for that), like the issuers that do have tiles.
+                    if (!mm_had_tiles) mbar_wait(A_FULL(c.wi % NA), (c.wi / NA) & 1);
+                    if (mm_had_tiles) tc_commit(A_EMPTY(c.wi % NA)); else mbar_arrive(A_EMPTY(c.wi % NA));
                     mm_had_tiles = false;
                 }
                 c.it0 += c.n; c.w += gridDim.x; ++c.wi;
@@ -204,8 +205,8 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
                 if (m >= 1 && ld.valid) load_B();          // tile m+1 goes into the stage of tile m-1
                 if (mm.wi != cur_wi) {                      // first tile of this issuer in a new item: its A tile must be built
                     cur_wi = mm.wi;
-                    mbar_wait(A_FULL(cur_wi & 1), (cur_wi >> 1) & 1);
-                    a_addr = smem_u32(sA + (cur_wi & 1) * bytesA);
+                    mbar_wait(A_FULL(cur_wi % NA), (cur_wi / NA) & 1);
+                    a_addr = smem_u32(sA + (cur_wi % NA) * bytesA);
                 }
                 const uint32_t s = sb + (m & 1);
                 mbar_wait(B_FULL(s), (m >> 1) & 1);
@@ -228,16 +229,37 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
     } else if (warp < F16_ISSUERS + F16_BUILDERS) {
         // ================= A builders =================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // Lane = (range block lane >> 2 of this warp's eight, rotation lane & 3).  The chain item record -> list entry ->
+        // pixels is three dependent loads; it is software-pipelined: the entry of the NEXT item is fetched while this item is
+        // built and its pixel rows are prefetched into L1, so an item costs one L1 round trip plus the arithmetic.
         const uint32_t bw = warp - F16_ISSUERS;
+        const uint32_t r = bw * 8 + (lane >> 2);
+        auto fetch = [&](uint32_t w, uint4& ent, bool& valid) {
+            valid = false;
+            if (w < n_items) {
+                const uint4 rec = __ldg(reinterpret_cast<const uint4*>(a.items + w));
+                valid = 4 * r < rec.y;
+                if (valid) {
+                    ent = __ldg(reinterpret_cast<const uint4*>(list + rec.x + r));
+                    const uint8_t* base = a.img + (size_t)(ent.y >> 16) * a.stride + (ent.y & 0xFFFFu);
+#pragma unroll
+                    for (int y = 0; y < T; ++y) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)y * a.stride));
+                }
+            }
+        };
+        uint4 ent = make_uint4(0, 0, 0, 0), ent_next = make_uint4(0, 0, 0, 0);
+        bool valid = false, valid_next = false;
+        fetch(blockIdx.x, ent, valid);
         uint32_t wi = 0;
         for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++wi) {
-            const uint4 rec = __ldg(reinterpret_cast<const uint4*>(a.items + w));
-            const uint32_t ab = wi & 1;
-            if (wi >= 2) mbar_wait(A_EMPTY(ab), ((wi >> 1) & 1) ^ 1);   // all four issuers are done with item wi - 2
-            if (rec.y) build_rows<T>(sA + ab * bytesA, a.img, a.stride, list, rec.x, rec.y, bw, lane);
+            const uint32_t ab = wi % NA;
+            fetch(w + gridDim.x, ent_next, valid_next);
+            if (wi >= NA) mbar_wait(A_EMPTY(ab), ((wi / NA) & 1) ^ 1);   // all four issuers are done with item wi - NA
+            build_rows<T>(sA + ab * bytesA, a.img, a.stride, ent.y, valid, bw, lane);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) mbar_arrive(A_FULL(ab));
+            ent = ent_next; valid = valid_next;
         }
     } else {
         // ================= compute warps: TMEM -> registers -> row argmin =================
@@ -256,8 +278,8 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
             const bool row_ok = lrow < rec.y;
             uint32_t slot = 0, a2 = 0;
             if (row_ok) {
-                slot = __ldg(&list[rec.x + (lrow >> 2)].slot);
-                a2 = __ldg(&a.rowA2[slot]);
+                const uint4 ent = __ldg(reinterpret_cast<const uint4*>(list + rec.x + (lrow >> 2)));
+                slot = ent.x; a2 = ent.z;
             }
             const uint32_t srow = 4u * slot + (lrow & 3u);     // result row of the level
             RowState st;
@@ -482,7 +504,7 @@ int f16_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, c
 template <int T>
 static int launch_T(fe_ctx* ctx, const F16Args& a, bool retire, bool meta, cudaEvent_t ev0, cudaEvent_t ev1) {
     constexpr uint32_t Kpad = (T * T + 3 + 15u) & ~15u;
-    const size_t smem = (size_t)2 * UM_ROWS * Kpad * 2 + (size_t)F16_STAGES * UM_NT * Kpad * 2 + (12 + F16_STAGES) * 8 + 64;
+    const size_t smem = (size_t)F16_ABUFS * UM_ROWS * Kpad * 2 + (size_t)F16_STAGES * UM_NT * Kpad * 2 + (8 + F16_STAGES + 2 * F16_ABUFS) * 8 + 64;
     auto kern = retire ? (meta ? k_search_f16<T, true, true> : k_search_f16<T, true, false>)
                        : (meta ? k_search_f16<T, false, true> : k_search_f16<T, false, false>);
     FE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
