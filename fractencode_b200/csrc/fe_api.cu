@@ -284,6 +284,13 @@ static int bucket_by_class(fe_ctx* ctx, const int32_t* d_cls, uint32_t n, DevBuf
     return FE_OK;
 }
 
+static int launch_finalize(fe_ctx* ctx, const FinalizeArgs& f, uint32_t T) {
+    launch_k_finalize(ctx->stream, f, T);
+    ctx->stats.kernel_launches++;
+    FE_CUDA(ctx, cudaGetLastError());
+    return FE_OK;
+}
+
 // fp32-regime re-rank (SURVEY hard part 2): ranges whose best SSE is >= 2^20 are re-scored with the reference's
 // rounded fp32 running sum over every candidate inside the rounding band of the exact minimum.  Rare (noise-like or
 // saturated blocks at T >= 16); runs the exact integer kernel on the flagged ranges only.
@@ -366,7 +373,7 @@ static int rerank_fp32_regime(fe_ctx* ctx, const LevelIO& io, const fe_params& p
     f.fp32_regime = ctx->b_counters.as<uint32_t>() + 9;
     f.bound_out = nullptr;
     f.rerank = 1;
-    LAUNCH(ctx, k_finalize, cdiv((uint64_t)nF * 32, 256), 256, f);
+    FE_TRY(launch_finalize(ctx, f, g.T));
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FE_OK;
 }
@@ -895,7 +902,7 @@ static int run_level_host(fe_ctx* ctx, const LevelIO& io, const fe_params& p, bo
     f.hit_is_domain = searched ? 1 : 0;
     if (searched) f.dom_order = nullptr;   // the tcgen05 paths report domain indices (keys and hits), not sorted columns
     f.no_min = (searched && use_thr && io.can_split) ? 1 : 0;   // a range without a hit splits: its minimum was not even tracked
-    LAUNCH(ctx, k_finalize, cdiv((uint64_t)nR * 32, 256), 256, f);
+    FE_TRY(launch_finalize(ctx, f, g.T));
     if (timed) cudaEventRecord(ctx->ev[3], ctx->stream);
 
     uint32_t counters[4];
@@ -938,18 +945,24 @@ static int run_level_host(fe_ctx* ctx, const LevelIO& io, const fe_params& p, bo
 // ---------------------------------------------------------------------------------------------------
 struct LevelPending {
     bool device = false;
+    int kind = 0;                         // 0: kind::f16 (T = 4, 8), 1: kind::i8
     DeviceLevelState st;
     uint32_t thr16 = 0;
     bool use_thr = false, timed = false;
+    FinalizeArgs fin{};
 };
 
-static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p, LevelPending* lp) {
+static inline int hint_slot(uint32_t T) { int l = 0; while ((1u << l) < T && l < 7) ++l; return l; }
+
+static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p, LevelPending* lp, bool skip_f16 = false) {
     const LevelGeom& g = io.g;
     const uint32_t nR = io.nR, nD = io.nD;
     *lp = LevelPending{};
     if (nR == 0) return FE_OK;
-    const bool device = nD && umma_level_supported(g) && p.search_impl != FE_SEARCH_EXACT && !getenv("FE_HOST_SLICES");
-    if (!device) return run_level_host(ctx, io, p);
+    const bool f16_ok = nD && umma_level_supported(g) && !skip_f16, i8_ok = nD && umma_i8_level_supported(g);
+    const bool device = (f16_ok || i8_ok) && p.search_impl != FE_SEARCH_EXACT && !getenv("FE_HOST_SLICES");
+    if (!device) return run_level_host(ctx, io, p, skip_f16);
+    lp->kind = f16_ok ? 0 : 1;
     if (p.rms_threshold * (double)(g.S * g.S) >= 1048576.0)
         return fe_fail(ctx, FE_ERR_UNSUPPORTED, "rms_threshold %g reaches the fp32-rounding regime of the reference distance (SSE >= 2^20) at S=%u", p.rms_threshold, g.S);
     lp->device = true;
@@ -971,9 +984,14 @@ static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p,
         lv.rng_cls = ctx->b_rng_cls.as<int32_t>();
     }
     lv.thr16 = lp->thr16; lv.use_thr = lp->use_thr; lv.need_min = !io.can_split; lv.timed = lp->timed;
-    FE_TRY(search_level_device(ctx, lv, 0, &lp->st));
+    // How many slices the level will need is only known on the device.  The host enqueues as many as the same kind of level
+    // needed last time (a launch past the end costs a few microseconds, a missing one a second synchronisation) -- the whole
+    // train when nothing is known yet.
+    const fe_ctx::SliceHint& hint = ctx->hint[lp->kind][hint_slot(g.T)];
+    const bool use_hint = hint.known && !getenv("FE_NO_HINT");
+    FE_TRY(search_level_device(ctx, lv, lp->kind, use_hint ? hint.slices : 0u, use_hint ? hint.with_min != 0 : true, &lp->st));
     if (lp->timed) cudaEventRecord(ctx->ev[2], ctx->stream);
-    FinalizeArgs f{};
+    FinalizeArgs& f = lp->fin;
     f.src = ctx->src.px; f.src_stride = ctx->src.stride;
     f.tgt = ctx->tgt.px; f.tgt_stride = ctx->tgt.stride;
     f.dom = io.d_dom; f.rng = io.d_rng;
@@ -993,41 +1011,65 @@ static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p,
     f.rerank = 0;
     f.hit_is_domain = 1;
     f.no_min = (lp->use_thr && io.can_split) ? 1 : 0;   // a range without a hit splits: its minimum was not even tracked
-    LAUNCH(ctx, k_finalize, cdiv((uint64_t)nR * 32, 256), 256, f);
+    FE_TRY(launch_finalize(ctx, f, g.T));
     if (lp->timed) cudaEventRecord(ctx->ev[3], ctx->stream);
     return FE_OK;
 }
 
-// Second half: one D2H copy + synchronisation.  scan_last / split_last (device, may be NULL): last entries of the quadtree's
-// exclusive scan of the split flags and of the flags; *n_split gets their sum.  *redo is set when the level's items were
-// rewritten after the scan had been enqueued (rare paths: inexact fp16 band, fp32-regime re-rank).
-static int run_level_complete(fe_ctx* ctx, const LevelIO& io, const fe_params& p, LevelPending* lp, const uint32_t* scan_last,
-                              const uint32_t* split_last, size_t* n_split, bool* redo) {
-    *redo = false;
-    if (io.nR == 0) { if (n_split) *n_split = 0; return FE_OK; }
+// Second half: the quadtree's scan of the split flags (do_scan), ONE D2H copy + synchronisation for the level's summary
+// and the split count, and the rare follow-ups (more slices than were enqueued, the inexact fp16 band, the fp32-regime
+// re-rank), each of which costs another round.
+static int run_level_complete(fe_ctx* ctx, const LevelIO& io, const fe_params& p, LevelPending* lp, bool do_scan, size_t* n_split) {
+    if (n_split) *n_split = 0;
+    if (io.nR == 0) return FE_OK;
+    do_scan = do_scan && io.can_split;
+    if (!lp->device && !do_scan) return FE_OK;
     FE_CUDA(ctx, ctx->b_summary.ensure(sizeof(LevelSummary)));
     FE_CUDA(ctx, ctx->b_counters.ensure(16 * sizeof(uint32_t)));
+    if (do_scan) FE_CUDA(ctx, ctx->b_scan.ensure((size_t)io.nR * 4 + 4));
     LevelSummary* hs = reinterpret_cast<LevelSummary*>(ctx->h_summary);
-    LAUNCH(ctx, k_level_summary, 1, 1, lp->device ? ctx->b_ctl.as<SliceCtl>() : nullptr, lp->device ? ctx->b_plan.as<LevelPlan>() : nullptr,
-           ctx->b_counters.as<uint32_t>(), scan_last, split_last, ctx->b_summary.as<LevelSummary>());
-    FE_CUDA(ctx, cudaMemcpyAsync(hs, ctx->b_summary.p, sizeof(LevelSummary), cudaMemcpyDeviceToHost, ctx->stream));
-    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (n_split) *n_split = (size_t)hs->last_scan + hs->last_flag;
-    if (!lp->device) return FE_OK;
     const LevelGeom& g = io.g;
-    if (hs->overflow) return fe_fail(ctx, FE_ERR_CUDA, "internal: work-item buffer of the level too small (T=%u)", g.T);
-    if (hs->flags & 1u) {
-        // a winner of the kind::f16 search sits in the fp32-inexact band: the level is searched again on the integer kind
-        *redo = true;
-        return run_level_host(ctx, io, p, true);
+    for (int round = 0;; ++round) {
+        if (round > 4) return fe_fail(ctx, FE_ERR_CUDA, "internal: level T=%u does not settle", g.T);
+        if (do_scan) {
+            size_t tmp_bytes = 0;
+            FE_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, io.d_split, ctx->b_scan.as<uint32_t>(), (int)io.nR, ctx->stream));
+            FE_CUDA(ctx, ctx->b_scan_tmp.ensure(tmp_bytes));
+            FE_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_scan_tmp.p, tmp_bytes, io.d_split, ctx->b_scan.as<uint32_t>(), (int)io.nR, ctx->stream));
+            ctx->stats.kernel_launches += 2;
+        }
+        LAUNCH(ctx, k_level_summary, 1, 1, lp->device ? ctx->b_ctl.as<SliceCtl>() : nullptr, lp->device ? ctx->b_plan.as<LevelPlan>() : nullptr,
+               ctx->b_counters.as<uint32_t>(), do_scan ? ctx->b_scan.as<uint32_t>() + (io.nR - 1) : nullptr, do_scan ? io.d_split + (io.nR - 1) : nullptr,
+               lp->device && lp->st.wants_min_pass ? 1u : 0u, ctx->b_summary.as<LevelSummary>());
+        FE_CUDA(ctx, cudaMemcpyAsync(hs, ctx->b_summary.p, sizeof(LevelSummary), cudaMemcpyDeviceToHost, ctx->stream));
+        FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (n_split) *n_split = (size_t)hs->last_scan + hs->last_flag;
+        if (!lp->device) return FE_OK;
+        if (hs->overflow) return fe_fail(ctx, FE_ERR_CUDA, "internal: work-item buffer of the level too small (T=%u)", g.T);
+        if (hs->flags & 1u) {
+            // a winner of the kind::f16 search sits in the fp32-inexact band: the level is searched again on the integer kind
+            FE_TRY(run_level_enqueue(ctx, io, p, lp, true));
+            continue;
+        }
+        if (!hs->done) {
+            // the level needed more slices (or a minimum pass) than were enqueued: the rest of the train, winners again
+            FE_TRY(search_level_more(ctx, &lp->st));
+            if (lp->timed) cudaEventRecord(ctx->ev[2], ctx->stream);
+            FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+            FE_TRY(launch_finalize(ctx, lp->fin, g.T));
+            continue;
+        }
+        break;
     }
     if (hs->mismatch) return fe_fail(ctx, FE_ERR_CUDA, "internal: %u winners whose search score disagrees with the direct recomputation (T=%u)", hs->mismatch, g.T);
+    fe_ctx::SliceHint& hint = ctx->hint[lp->kind][hint_slot(g.T)];
+    hint.known = 1; hint.slices = (uint8_t)std::max(1u, hs->slices); hint.with_min = hs->min_ran ? 1 : 0;
     ctx->stats.matches += hs->matches;
     ctx->stats.evaluated += hs->evaluated;
     ctx->stats.umma_levels++;
     ctx->stats.fp32_regime_items += hs->fp32_regime;
-    float kernel_ms = 0.f;
     if (lp->timed) {
+        float kernel_ms = 0.f;
         for (uint32_t i = 0; i < lp->st.n_launches; ++i) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->ev_pass[2 * i], ctx->ev_pass[2 * i + 1]);
@@ -1045,7 +1087,6 @@ static int run_level_complete(fe_ctx* ctx, const LevelIO& io, const fe_params& p
     }
     if (hs->fp32_regime) {
         // re-rank of the flagged range blocks on the exact kernel: every domain of the block's class in scan order
-        *redo = true;
         const uint32_t nD = io.nD, nR = io.nR;
         if (p.use_classifier) {
             uint32_t doff[8], roff[8] = {0};
@@ -1058,16 +1099,18 @@ static int run_level_complete(fe_ctx* ctx, const LevelIO& io, const fe_params& p
             const uint32_t d1[8] = {0, nD, nD, nD, nD, nD, nD, nD}, r1[8] = {0, nR, nR, nR, nR, nR, nR, nR};
             FE_TRY(rerank_fp32_regime(ctx, io, p, nullptr, lp->st.rng_order, d1, r1, 1));
         }
+        if (do_scan) {   // the re-rank rewrote items and split flags: scan again
+            LevelPending none;
+            FE_TRY(run_level_complete(ctx, io, p, &none, true, n_split));
+        }
     }
     return FE_OK;
 }
 
 static int run_level(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     LevelPending lp;
-    bool redo = false;
     FE_TRY(run_level_enqueue(ctx, io, p, &lp));
-    if (lp.device) FE_TRY(run_level_complete(ctx, io, p, &lp, nullptr, nullptr, nullptr, &redo));
-    return FE_OK;
+    return run_level_complete(ctx, io, p, &lp, false, nullptr);
 }
 
 static int make_geom(fe_ctx* ctx, uint32_t S, uint32_t T, bool even_origins, LevelGeom* g) {
@@ -1181,39 +1224,12 @@ extern "C" int fe_encode_quadtree_slice_device(fe_ctx* ctx, uint32_t t_max, uint
         LevelPending lp;
         FE_TRY(run_level_enqueue(ctx, io, *params, &lp));
         size_t n_split = 0;
+        // one synchronisation per level: the level's summary and the split count come back together
+        FE_TRY(run_level_complete(ctx, io, *params, &lp, true, &n_split));
         if (io.can_split) {
-            FE_CUDA(ctx, ctx->b_scan.ensure(n_pending * 4 + 4));
-            auto scan_and_count = [&](bool sync_here) -> int {
-                size_t tmp_bytes = 0;
-                FE_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, io.d_split, ctx->b_scan.as<uint32_t>(), (int)n_pending, ctx->stream));
-                FE_CUDA(ctx, ctx->b_scan_tmp.ensure(tmp_bytes));
-                FE_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->b_scan_tmp.p, tmp_bytes, io.d_split, ctx->b_scan.as<uint32_t>(), (int)n_pending, ctx->stream));
-                ctx->stats.kernel_launches += 2;
-                if (sync_here) {
-                    uint32_t last_scan = 0, last_flag = 0;
-                    FE_CUDA(ctx, cudaMemcpyAsync(&last_scan, ctx->b_scan.as<uint32_t>() + (n_pending - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-                    FE_CUDA(ctx, cudaMemcpyAsync(&last_flag, io.d_split + (n_pending - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
-                    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                    n_split = (size_t)last_scan + last_flag;
-                }
-                return FE_OK;
-            };
-            if (lp.device) {
-                // one synchronisation per level: the level's summary and the split count come back together
-                bool redo = false;
-                FE_TRY(scan_and_count(false));
-                FE_TRY(run_level_complete(ctx, io, *params, &lp, ctx->b_scan.as<uint32_t>() + (n_pending - 1), io.d_split + (n_pending - 1), &n_split, &redo));
-                if (redo) FE_TRY(scan_and_count(true));
-            } else {
-                FE_TRY(scan_and_count(true));
-            }
             LAUNCH(ctx, k_quadtree_scatter, cdiv(n_pending, 256), 256, ctx->b_rng.as<fe_grid_item>(), io.d_out, io.d_split, ctx->b_scan.as<uint32_t>(),
                    (uint32_t)n_pending, ctx->b_rng_next.as<fe_grid_item>(), ctx->b_items.as<fe_encode_item>() + offset);
         } else {
-            if (lp.device) {
-                bool redo = false;
-                FE_TRY(run_level_complete(ctx, io, *params, &lp, nullptr, nullptr, nullptr, &redo));
-            }
             FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_items.as<fe_encode_item>() + offset, io.d_out, n_pending * sizeof(fe_encode_item), cudaMemcpyDeviceToDevice, ctx->stream));
         }
         const size_t kept = n_pending - n_split;

@@ -101,6 +101,8 @@ struct fe_ctx {
     DevBuf b_plan, b_ctl, b_list[2], b_itemrec, b_posb, b_summary;
     void* h_summary = nullptr;
     int n_sm = 148;                 // multiProcessorCount of the device
+    // slices the last level of this kind (f16 / i8) and block size needed: how many the next one gets enqueued up front
+    struct SliceHint { uint8_t known = 0, slices = 0, with_min = 0; } hint[2][8];
     // results
     DevBuf b_items;
     size_t n_items = 0;

@@ -494,11 +494,14 @@ cudaError_t launch_search_exact(fe_ctx* ctx, const SearchArgs& a, bool rerank) {
 // ---------------------------------------------------------------------------------------------
 // winner finalisation: TransformEstimator2::estimate's net rule over the four
 // rotation rows of a range, then s/o for the winner only (transformmatcher.h:98-108).
-// One warp per range position j.
+// LPR lanes per range position j (launch_k_finalize).
 // ---------------------------------------------------------------------------------------------
-__global__ void k_finalize(FinalizeArgs f) {
-    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (j >= f.n) return;
+template <int LPR>
+__global__ void k_finalize_t(FinalizeArgs f) {
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = gt / LPR, lane = gt % LPR;              // range position, lane inside the block's group of LPR lanes
+    const uint32_t gmask = LPR == 32 ? 0xFFFFFFFFu : (((1u << LPR) - 1u) << ((threadIdx.x & 31u) / LPR * LPR));
+    if (j >= f.n) return;                                      // whole groups leave together
     const uint32_t ri = f.rng_order ? f.rng_order[j] : j;
     const fe_grid_item r = f.rng[ri];
     // ---- pick the winner (identical on all lanes) ----
@@ -554,18 +557,18 @@ __global__ void k_finalize(FinalizeArgs f) {
     // ---- exact sums for the winner ----
     const uint32_t T = r.w, N = T * T, rho = dm.w / T;
     uint32_t sA = 0, sA2 = 0, sB = 0, sAB = 0, sB2 = 0;
-    for (uint32_t e = lane; e < N; e += 32) {
+    for (uint32_t e = lane; e < N; e += LPR) {
         const uint32_t ty = e / T, tx = e % T;
         const uint32_t a = f.tgt[(size_t)(r.y + ty) * f.tgt_stride + r.x + tx];
         const uint32_t D = (uint32_t)sample_sum4(f.src, f.src_stride, dm.x, dm.y, dm.w, tx * rho, ty * rho, wk);
         sA += a; sA2 += a * a; sB += D; sAB += a * D; sB2 += D * D;
     }
-    for (int o = 16; o; o >>= 1) {
-        sA += __shfl_xor_sync(0xFFFFFFFFu, sA, o);
-        sA2 += __shfl_xor_sync(0xFFFFFFFFu, sA2, o);
-        sB += __shfl_xor_sync(0xFFFFFFFFu, sB, o);
-        sAB += __shfl_xor_sync(0xFFFFFFFFu, sAB, o);
-        sB2 += __shfl_xor_sync(0xFFFFFFFFu, sB2, o);
+    for (int o = LPR / 2; o; o >>= 1) {
+        sA += __shfl_xor_sync(gmask, sA, o);
+        sA2 += __shfl_xor_sync(gmask, sA2, o);
+        sB += __shfl_xor_sync(gmask, sB, o);
+        sAB += __shfl_xor_sync(gmask, sAB, o);
+        sB2 += __shfl_xor_sync(gmask, sB2, o);
     }
     wn16 = 16u * sA2 - 8u * sAB + sB2; // exact for T <= 64
     if (lane != 0) return;
@@ -621,6 +624,15 @@ __global__ void k_finalize(FinalizeArgs f) {
     out.match_x = dm.x; out.match_y = dm.y; out.src_w = dm.w; out.src_h = dm.h;
     f.out[ri] = out;
     if (f.split) f.split[ri] = (f.can_split && !(distance <= f.thr)) ? 1u : 0u;
+}
+
+// Lanes per range block: a warp per block leaves most lanes idle on the small blocks (64 pixels at T = 8) and the kernel
+// is a chain of dependent loads per block, so small blocks share a warp.
+void launch_k_finalize(cudaStream_t stream, const FinalizeArgs& f, uint32_t T) {
+    const uint32_t N = T * T;
+    if (N <= 16) k_finalize_t<4><<<(unsigned)(((uint64_t)f.n * 4 + 255) / 256), 256, 0, stream>>>(f);
+    else if (N <= 64) k_finalize_t<8><<<(unsigned)(((uint64_t)f.n * 8 + 255) / 256), 256, 0, stream>>>(f);
+    else k_finalize_t<32><<<(unsigned)(((uint64_t)f.n * 32 + 255) / 256), 256, 0, stream>>>(f);
 }
 
 // ---------------------------------------------------------------------------------------------

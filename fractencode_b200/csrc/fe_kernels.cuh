@@ -48,7 +48,7 @@ __global__ void k_build_rows(const uint8_t* img, uint32_t stride, const fe_grid_
                              uint32_t T, uint32_t Npad, int fast, uint8_t* A, uint32_t* rowc);
 __global__ void k_build_pool(const uint8_t* img, uint32_t stride, const fe_grid_item* dom, const uint32_t* order, uint32_t n,
                              uint32_t npool, uint32_t T, uint32_t rho, uint32_t Npad, uint8_t* Blo, uint8_t* Bhi, uint32_t* coln);
-__global__ void k_finalize(FinalizeArgs f);
+void launch_k_finalize(cudaStream_t stream, const FinalizeArgs& f, uint32_t T);
 __global__ void k_decode_step(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items,
                               const uint32_t* pix_off, uint32_t n_items, uint32_t total_pix, int use_fma);
 __global__ void k_decode_step_uniform(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items,

@@ -36,14 +36,21 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 }
 } // namespace
 
-// key = (class + 1) * nbins + bin (class 0 when cls is NULL, bin 0 when bins is NULL); hist[key] counts.
-__global__ void k_bucket_keys(const int32_t* __restrict__ cls, const uint8_t* __restrict__ bins, uint32_t n, uint32_t nbins,
-                              uint16_t* __restrict__ keys, uint32_t* __restrict__ hist) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t k = (cls ? (uint32_t)(cls[i] + 1) : 0u) * nbins + (bins ? (uint32_t)bins[i] : 0u);
-    keys[i] = (uint16_t)k;
-    atomicAdd(&hist[k], 1u);
+// key = (class + 1) * nbins + bin (class 0 when cls is NULL, bin 0 when bins is NULL); hist[key] counts (per-block
+// histogram in shared memory first: a few dozen hot global addresses would serialise the whole grid).
+__global__ void __launch_bounds__(256) k_bucket_keys(const int32_t* __restrict__ cls, const uint8_t* __restrict__ bins, uint32_t n, uint32_t nbins,
+                                                     uint32_t nb, uint16_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[FE_MAX_TOTAL];
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t k = (cls ? (uint32_t)(cls[i] + 1) : 0u) * nbins + (bins ? (uint32_t)bins[i] : 0u);
+        keys[i] = (uint16_t)k;
+        atomicAdd(&sh[k], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x)
+        if (sh[b]) atomicAdd(&hist[b], sh[b]);
 }
 
 // One CTA of 512 threads: bucket offsets, the interval ends of every bucket, the tile layout of the operand blob and the
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(512) k_level_plan(PlanArgs a, const uint32_t* 
         p->nD = nD; p->nR = nR; p->nt = nt; p->nk = nk;
         for (int k = 0; k < FE_NK; ++k)
             p->cut[k] = !a.multipass ? FE_NONE32 : (k == FE_NK - 1 ? nD : (uint32_t)((((uint64_t)nD) << k) / 128 + 1));
-        ctl->list = 0; ctl->k_done = 0; ctl->done = 0; ctl->open = 1; ctl->passes = 0; ctl->ticket = 0;
+        ctl->list = 0; ctl->k_done = 0; ctl->done = 0; ctl->open = 1; ctl->passes = 0; ctl->ticket = 0; ctl->slices = 0; ctl->min_ran = 0;
         ctl->cutoff = FE_NONE32; ctl->evaluated = 0ull; ctl->active = FE_NONE32; ctl->n_items = 0; ctl->no_min = 0;
         ctl->overflow = 0;
     }
@@ -127,16 +134,21 @@ __global__ void __launch_bounds__(512) k_level_plan(PlanArgs a, const uint32_t* 
 __global__ void k_level_ranges(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
                                const uint32_t* __restrict__ order, const LevelPlan* __restrict__ plan, uint32_t T, int centred,
                                ListEntry* __restrict__ list0, uint16_t* __restrict__ pos_bucket) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    // a warp per block from T = 16 on (coalesced rows), a thread per block below
+    const uint32_t lanes = T >= 16 ? 32u : 1u;
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x, p = gt / lanes, lane = gt % lanes;
     if (p >= plan->nR) return;
     const fe_grid_item r = rng[order ? order[p] : p];
     const uint8_t* base = img + (size_t)r.y * stride + r.x;
     uint32_t s2 = 0;
-    for (uint32_t y = 0; y < T; ++y)
-        for (uint32_t x = 0; x < T; ++x) {
-            const int v = centred ? 4 * (int)base[(size_t)y * stride + x] - 510 : 4 * (int)base[(size_t)y * stride + x];
-            s2 += (uint32_t)(v * v);
-        }
+    for (uint32_t e = lane; e < T * T; e += lanes) {
+        const uint32_t y = e / T, x = e - y * T;
+        const int v = centred ? 4 * (int)base[(size_t)y * stride + x] - 510 : 4 * (int)base[(size_t)y * stride + x];
+        s2 += (uint32_t)(v * v);
+    }
+    if (lanes == 32)
+        for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+    if (lane) return;
     ListEntry e;
     e.slot = p;
     e.xy = r.x | (r.y << 16);
@@ -164,9 +176,9 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
     __shared__ uint32_t s_cnt[FE_MAX_TOTAL], s_tiles[FE_MAX_TOTAL];
     __shared__ uint32_t s_k0, s_k1, s_go;
     if (phase == FE_PHASE_SLICE && ctl->done) return;
-    if (phase == FE_PHASE_MIN && !(ctl->open && a.use_thr && a.bins && a.need_min)) return;
+    if (phase == FE_PHASE_MIN && !(ctl->done && ctl->open && a.use_thr && a.bins && a.need_min)) return;
     const uint32_t cur = ctl->list;
-    const bool first = phase == FE_PHASE_SLICE && ctl->passes == 0;
+    const bool first = phase == FE_PHASE_SLICE && ctl->slices == 0;
     const uint32_t nxt = first ? cur : cur ^ 1u;
     if (!first) {
         // ---- compaction: the open range blocks of list `cur` that stay open go to list `nxt`, bucket regions kept ----
@@ -185,16 +197,24 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
             // they are gathered in the region of the class's first bucket
             if (phase == FE_PHASE_MIN) b = (b / p->nbins) * p->nbins;
         }
-        // warp-aggregated append per bucket (positions are sorted by bucket: a warp holds one or two)
-        const uint32_t key = alive ? b : 0xFFFFu;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-        if (alive) {
-            const uint32_t lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(&ctl->cnt[nxt][b], (uint32_t)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            a.list[nxt][p->roff[b] + base + __popc(peers & ((1u << lane) - 1))] = e;
+        // Append per bucket, aggregated per block: positions are sorted by bucket, so a block holds one or two buckets -- ranks
+        // come from shared-memory counters, one global atomic per block and bucket reserves the space.
+        __shared__ uint32_t s_bmin, s_n[32], s_base[32];
+        if (threadIdx.x == 0) {
+            const uint32_t p0 = min(blockIdx.x * blockDim.x, p->nR - 1);
+            uint32_t b0 = a.pos_bucket[p0];
+            if (phase == FE_PHASE_MIN) b0 = (b0 / p->nbins) * p->nbins;
+            s_bmin = b0;
         }
+        if (threadIdx.x < 32) s_n[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t d = b - s_bmin;
+        uint32_t rank = 0;
+        if (alive) rank = d < 32 ? atomicAdd(&s_n[d], 1u) : atomicAdd(&ctl->cnt[nxt][b], 1u);
+        __syncthreads();
+        if (threadIdx.x < 32 && s_n[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&ctl->cnt[nxt][s_bmin + threadIdx.x], s_n[threadIdx.x]);
+        __syncthreads();
+        if (alive) a.list[nxt][p->roff[b] + (d < 32 ? s_base[d] : 0u) + rank] = e;
     }
     // ---- last CTA plans ----
     __threadfence();
@@ -275,7 +295,7 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
         steps = block_sum_u64(steps, s_red);
         // Work items of about equal length: long runs are cut so that every SM gets eight items or more, short runs stay
         // whole (an item pays for its A tile and for filling the pipeline: never below 16 column tiles).
-        const uint32_t run_len = (uint32_t)min(max(steps / (8ull * a.n_sm), 16ull), 1ull << 20);
+        const uint32_t run_len = (uint32_t)min(max(steps / ((unsigned long long)a.items_per_sm * a.n_sm), (unsigned long long)a.min_run), 1ull << 20);
         __syncthreads();
         for (uint32_t c = t; c < nb; c += 256) {
             uint32_t per_tile = 0;
@@ -292,8 +312,14 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
         if (t == 0) {
             uint64_t acc = 0;
             uint32_t tiles = 0;
-            for (uint32_t c = 0; c < nb; ++c) { ctl->item_prefix[c] = (uint32_t)min(acc, (uint64_t)0xFFFFFFFFull); acc += s_cnt[c]; tiles += s_tiles[c]; }
+            for (uint32_t c = 0; c < nb; ++c) {
+                ctl->item_prefix[c] = (uint32_t)min(acc, (uint64_t)0xFFFFFFFFull);
+                ctl->tile_prefix[c] = tiles;
+                acc += s_cnt[c];
+                tiles += s_tiles[c];
+            }
             ctl->item_prefix[nb] = (uint32_t)min(acc, (uint64_t)0xFFFFFFFFull);
+            ctl->tile_prefix[nb] = tiles;
             if (acc > a.max_items) ctl->overflow = 1;
             ctl->n_row_tiles = tiles;
             ctl->k0 = k0; ctl->k1 = k1; ctl->run_len = run_len;
@@ -303,7 +329,9 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
             ctl->evaluated += work;
             ctl->passes += 1;
             ctl->active = ordinal;
+            if (phase == FE_PHASE_MIN) ctl->min_ran = 1;
             if (phase == FE_PHASE_SLICE) {
+                ctl->slices += 1;
                 ctl->k_done = k1 + 1;
                 ctl->cutoff = (k1 == nk - 1) ? FE_NONE32 : p->cut[k1];
                 if (k1 == nk - 1) ctl->done = 1;       // nothing left to slice (the launches of later ordinals return at once)
@@ -345,7 +373,7 @@ __global__ void k_expand_items(PlanArgs a, uint32_t ordinal) {
                 r.pos0 = p->roff[c] + 32 * rt;
                 r.nrows = 4 * min(32u, cnt - 32 * rt);
                 r.cols_left = (p->dend[k][blo] - (k ? p->dend[k - 1][blo] : 0u)) - (r.t0 - T0) * nt;
-                r.a_tile = 0;
+                r.a_tile = ctl->tile_prefix[c] + rt;
                 break;
             }
             rem -= q;
@@ -355,10 +383,15 @@ __global__ void k_expand_items(PlanArgs a, uint32_t ordinal) {
 }
 
 __global__ void k_level_summary(const SliceCtl* ctl, const LevelPlan* plan, const uint32_t* counters, const uint32_t* scan_last,
-                                const uint32_t* split_last, LevelSummary* out) {
+                                const uint32_t* split_last, uint32_t wants_min_pass, LevelSummary* out) {
     LevelSummary s{};
     s.mismatch = counters[0]; s.fp32_regime = counters[1]; s.flags = counters[2];
-    if (ctl) { s.passes = ctl->passes; s.evaluated = ctl->evaluated; s.overflow = ctl->overflow; }
+    s.done = 1;
+    if (ctl) {
+        s.passes = ctl->passes; s.evaluated = ctl->evaluated; s.overflow = ctl->overflow;
+        s.slices = ctl->slices; s.min_ran = ctl->min_ran;
+        s.done = (ctl->done && !(ctl->open && wants_min_pass)) ? 1u : 0u;
+    }
     if (plan)
         for (uint32_t g = 0; g < plan->ngroups; ++g) {
             const uint32_t b0 = g * plan->nbins, b1 = b0 + plan->nbins;
@@ -382,7 +415,50 @@ void fe_plan_bins(uint32_t N, uint32_t thr16, fe_threshold_plan* pl);   // fe_ap
         FE_CUDA(ctx, cudaGetLastError());                              \
     } while (0)
 
-int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, DeviceLevelState* st) {
+static int enqueue_slice(fe_ctx* ctx, DeviceLevelState* st, int phase, uint32_t ordinal, bool meta) {
+    const PlanArgs& pa = st->pa;
+    const LevelGeom& g = st->g;
+    PLAUNCH(ctx, k_slice_plan, cdiv_u(st->nR, 256), 256, pa, phase, ordinal);
+    PLAUNCH(ctx, k_expand_items, 2 * ctx->n_sm, 256, pa, ordinal);
+    cudaEvent_t e0 = st->timed ? ctx->ev_pass[2 * st->n_launches] : nullptr, e1 = st->timed ? ctx->ev_pass[2 * st->n_launches + 1] : nullptr;
+    if (st->kind == 0) {
+        st->fa.ordinal = ordinal;
+        FE_TRY(f16_launch_search(ctx, g, st->fa, st->retire, meta, e0, e1));
+    } else {
+        const ListEntry* lists[2] = {pa.list[0], pa.list[1]};
+        FE_TRY(i8_build_rows(ctx, g, pa.plan, pa.ctl, lists, ordinal, st->max_row_tiles));
+        st->ia.ordinal = ordinal;
+        st->ia.meta = meta ? 1u : 0u;
+        FE_TRY(i8_launch_search(ctx, g, st->ia, e0, e1));
+    }
+    ++st->n_launches;
+    if (getenv("FE_PASS_DBG")) {                      // debugging aid: synchronises after every launch
+        SliceCtl* h = new SliceCtl;
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, pa.ctl, sizeof(SliceCtl), cudaMemcpyDeviceToHost);
+        float ms = 0;
+        if (e0) cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "[slice] T=%u kind=%d ordinal=%u ran=%d k=%u..%u run_len=%u items=%u row_tiles=%u passes=%u evaluated=%.3e done=%u open=%u kernel %.3f ms\n",
+                g.T, st->kind, ordinal, h->active == ordinal, h->k0, h->k1, h->run_len, h->n_items, h->n_row_tiles, h->passes, (double)h->evaluated, h->done,
+                h->open, ms);
+        delete h;
+    }
+    return FE_OK;
+}
+
+// What the level still needs after the host has seen that the enqueued slices did not finish it: the rest of the slice
+// train and the minimum pass.
+int search_level_more(fe_ctx* ctx, DeviceLevelState* st) {
+    if ((size_t)st->n_launches + FE_NK + 1 > (size_t)FE_MAX_LAUNCHES) return fe_fail(ctx, FE_ERR_CUDA, "internal: search launch budget exceeded");
+    const uint32_t n_slices = st->multipass ? (uint32_t)FE_NK : 1u;
+    for (uint32_t s = st->slices_enqueued; s < n_slices; ++s) FE_TRY(enqueue_slice(ctx, st, FE_PHASE_SLICE, s, st->span > 0));
+    st->slices_enqueued = n_slices;
+    if (st->wants_min_pass) FE_TRY(enqueue_slice(ctx, st, FE_PHASE_MIN, FE_NK + (st->min_enqueued ? 1u : 0u), true));
+    st->min_enqueued = true;
+    return FE_OK;
+}
+
+int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n_slices_hint, bool with_min, DeviceLevelState* st) {
     const LevelGeom& g = lv.g;
     const uint32_t nD = lv.nD, nR = lv.nR;
     const uint32_t nt = kind == 0 ? (uint32_t)UM_NT : (uint32_t)I8_NT;
@@ -431,8 +507,8 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, DeviceLeve
         ctx->stats.kernel_launches += 2;
         FE_CUDA(ctx, cudaGetLastError());
     }
-    PLAUNCH(ctx, k_bucket_keys, cdiv_u(nD, 256), 256, lv.dom_cls, st->bins ? bins8 : nullptr, nD, st->nbins, keys, hist_d);
-    PLAUNCH(ctx, k_bucket_keys, cdiv_u(nR, 256), 256, lv.rng_cls, st->bins ? bins8 + nD : nullptr, nR, st->nbins, keys + nD, hist_r);
+    PLAUNCH(ctx, k_bucket_keys, std::min(cdiv_u(nD, 1024), 4u * ctx->n_sm), 256, lv.dom_cls, st->bins ? bins8 : nullptr, nD, st->nbins, nb, keys, hist_d);
+    PLAUNCH(ctx, k_bucket_keys, std::min(cdiv_u(nR, 1024), 4u * ctx->n_sm), 256, lv.rng_cls, st->bins ? bins8 + nD : nullptr, nR, st->nbins, nb, keys + nD, hist_r);
     if (sorted) {
         int bits = 1;
         while ((1u << bits) < nb) ++bits;
@@ -452,7 +528,8 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, DeviceLeve
     PLAUNCH(ctx, k_bin_prefix, cdiv_u((uint64_t)nb * 8, 128), 128, st->dom_order, hist_d, (int)nb, c8, pre);
 
     // ---- the level's plan, first list, operand blob ----
-    PlanArgs pa{};
+    PlanArgs& pa = st->pa;
+    pa = PlanArgs{};
     pa.plan = ctx->b_plan.as<LevelPlan>();
     pa.ctl = ctx->b_ctl.as<SliceCtl>();
     pa.list[0] = ctx->b_list[0].as<ListEntry>();
@@ -466,51 +543,62 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, DeviceLeve
     pa.min_tiles = ms_env ? (uint32_t)std::max(1, atoi(ms_env)) : (st->bins ? (uint32_t)std::max(2, 10 / (2 * (int)st->span + 1)) : 16u);
     pa.max_items = max_items;
     pa.n_sm = (uint32_t)ctx->n_sm;
+    // work items: the i8 kind reloads its A tile per item (128 KB at T = 32, one buffer): longer and fewer items there
+    pa.min_run = kind == 0 ? 16u : (g.T >= 32 ? 48u : 24u);
+    pa.items_per_sm = kind == 0 ? 8u : (g.T >= 32 ? 4u : 6u);
     PLAUNCH(ctx, k_level_plan, 1, 512, pa, hist_d, hist_r, pre, nb, st->nbins, st->ngroups, st->span, nD, nR, nt);
-    PLAUNCH(ctx, k_level_ranges, cdiv_u(nR, 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T, kind == 0 ? 1 : 0,
+    PLAUNCH(ctx, k_level_ranges, cdiv_u((uint64_t)nR * (g.T >= 16 ? 32 : 1), 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T, kind == 0 ? 1 : 0,
             pa.list[0], ctx->b_posb.as<uint16_t>());
     PLAUNCH(ctx, k_fill_u64, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
     PLAUNCH(ctx, k_fill_u32, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));
-    if (kind != 0) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "internal: device-scheduled i8 kind not built");
-    FE_TRY(f16_build_pool(ctx, g, lv.d_dom, st->dom_order, pa.plan, max_tiles));
-
-    F16Args fa{};
-    fa.img = ctx->tgt.px; fa.stride = ctx->tgt.stride;
-    fa.B16 = ctx->b_B16.p;
-    fa.colmeta = ctx->b_tmaps.as<uint4>();
-    fa.blob_dom = ctx->b_blob_dom.as<uint32_t>();
-    fa.list[0] = pa.list[0]; fa.list[1] = pa.list[1];
-    fa.items = pa.items;
-    fa.ctl = pa.ctl;
-    fa.rowbest = ctx->b_rowbest.as<unsigned long long>();
-    fa.rowhit = ctx->b_rowhit.as<uint32_t>();
-    fa.flags = ctx->b_counters.as<uint32_t>() + 2;
-    fa.thr16 = lv.thr16; fa.use_thr = lv.use_thr ? 1u : 0u;
-    const bool retire = lv.use_thr && g.T == 4;
-    const bool pass_dbg = getenv("FE_PASS_DBG") != nullptr;
-    const uint32_t plan_grid = cdiv_u(nR, 256);
-    const uint32_t n_slices = multipass ? (uint32_t)FE_NK : 1u;
-    auto slice = [&](int phase, uint32_t ordinal, bool meta) -> int {
-        PLAUNCH(ctx, k_slice_plan, plan_grid, 256, pa, phase, ordinal);
-        PLAUNCH(ctx, k_expand_items, 2 * 148, 256, pa, ordinal);
-        fa.ordinal = ordinal;
-        cudaEvent_t e0 = lv.timed ? ctx->ev_pass[2 * st->n_launches] : nullptr, e1 = lv.timed ? ctx->ev_pass[2 * st->n_launches + 1] : nullptr;
-        FE_TRY(f16_launch_search(ctx, g, fa, retire, meta, e0, e1));
-        ++st->n_launches;
-        if (pass_dbg) {                                // debugging aid: synchronises after every launch
-            SliceCtl* h = new SliceCtl;
-            cudaStreamSynchronize(ctx->stream);
-            cudaMemcpy(h, pa.ctl, sizeof(SliceCtl), cudaMemcpyDeviceToHost);
-            float ms = 0;
-            if (e0) cudaEventElapsedTime(&ms, e0, e1);
-            fprintf(stderr, "[slice] T=%u ordinal=%u ran=%d k=%u..%u run_len=%u items=%u row_tiles=%u passes=%u evaluated=%.3e done=%u open=%u kernel %.3f ms\n", g.T,
-                    ordinal, h->active == ordinal, h->k0, h->k1, h->run_len, h->n_items, h->n_row_tiles, h->passes, (double)h->evaluated, h->done, h->open, ms);
-            delete h;
-        }
-        return FE_OK;
-    };
-    for (uint32_t s = 0; s < n_slices; ++s) FE_TRY(slice(FE_PHASE_SLICE, s, st->span > 0));
-    if (st->bins && lv.need_min) FE_TRY(slice(FE_PHASE_MIN, FE_NK, true));
+    F16Args& fa = st->fa;
+    I8Args& ia = st->ia;
+    fa = F16Args{};
+    ia = I8Args{};
+    const uint32_t max_row_tiles = nR / 32 + nb;
+    if (kind == 0) {
+        FE_TRY(f16_build_pool(ctx, g, lv.d_dom, st->dom_order, pa.plan, max_tiles));
+        fa.img = ctx->tgt.px; fa.stride = ctx->tgt.stride;
+        fa.B16 = ctx->b_B16.p;
+        fa.colmeta = ctx->b_tmaps.as<uint4>();
+        fa.blob_dom = ctx->b_blob_dom.as<uint32_t>();
+        fa.list[0] = pa.list[0]; fa.list[1] = pa.list[1];
+        fa.items = pa.items;
+        fa.ctl = pa.ctl;
+        fa.rowbest = ctx->b_rowbest.as<unsigned long long>();
+        fa.rowhit = ctx->b_rowhit.as<uint32_t>();
+        fa.flags = ctx->b_counters.as<uint32_t>() + 2;
+        fa.thr16 = lv.thr16; fa.use_thr = lv.use_thr ? 1u : 0u;
+    } else {
+        FE_TRY(i8_build_pool(ctx, g, lv.d_dom, st->dom_order, pa.plan, nD, max_tiles));
+        FE_CUDA(ctx, ctx->b_A16.ensure((size_t)max_row_tiles * UM_ROWS * i8_kpad(g) + 256));
+        ia.A8 = ctx->b_A16.p;
+        ia.B8 = ctx->b_B16.p;
+        ia.tileseg = ctx->b_tileseg.as<uint32_t>();
+        ia.blob_dom = ctx->b_blob_dom.as<uint32_t>();
+        ia.coln = ctx->b_coln.as<uint32_t>();
+        ia.list[0] = pa.list[0]; ia.list[1] = pa.list[1];
+        ia.items = pa.items;
+        ia.ctl = pa.ctl;
+        ia.rowbest = ctx->b_rowbest.as<unsigned long long>();
+        ia.rowhit = ctx->b_rowhit.as<uint32_t>();
+        ia.thr16 = lv.thr16; ia.use_thr = lv.use_thr ? 1u : 0u;
+    }
+    st->kind = kind;
+    st->multipass = multipass;
+    st->retire = lv.use_thr && g.T == 4;
+    st->timed = lv.timed;
+    st->wants_min_pass = st->bins && lv.need_min;
+    st->max_row_tiles = max_row_tiles;
+    st->nR = nR;
+    st->g = g;
+    const uint32_t n_slices = multipass ? (n_slices_hint ? std::min(n_slices_hint, (uint32_t)FE_NK) : (uint32_t)FE_NK) : 1u;
+    for (uint32_t s = 0; s < n_slices; ++s) FE_TRY(enqueue_slice(ctx, st, FE_PHASE_SLICE, s, st->span > 0));
+    st->slices_enqueued = n_slices;
+    if (st->wants_min_pass && with_min) {
+        FE_TRY(enqueue_slice(ctx, st, FE_PHASE_MIN, FE_NK, true));
+        st->min_enqueued = true;
+    }
     return FE_OK;
 }

@@ -57,7 +57,9 @@ struct SliceCtl {
     uint32_t k_done;                      // intervals 0 .. k_done-1 have been scanned
     uint32_t done;                        // the slicing is over
     uint32_t open;                        // range blocks may still be without their first hit
-    uint32_t passes;                      // slices run so far
+    uint32_t passes;                      // search launches planned so far (slices + minimum pass)
+    uint32_t slices;                      // of those, slices of the scan
+    uint32_t min_ran;                     // the minimum pass was planned
     uint32_t ticket;
     uint32_t cutoff;                      // hits at domain indices below this are final
     unsigned long long evaluated;         // (range, domain, rotation) candidates scored
@@ -71,6 +73,7 @@ struct SliceCtl {
     uint32_t n_items;
     uint32_t n_row_tiles;
     uint32_t item_prefix[FE_MAX_TOTAL + 1];   // work items of the buckets before b
+    uint32_t tile_prefix[FE_MAX_TOTAL + 1];   // row tiles of the buckets before b (i8 kind: index into the slice's A blob)
 };
 
 // Level constants the planner needs (kernel parameter).
@@ -86,6 +89,7 @@ struct PlanArgs {
     uint32_t min_tiles;                   // column tiles a bucket advances per interval at least
     uint32_t max_items;
     uint32_t n_sm;
+    uint32_t min_run, items_per_sm;       // work items: never shorter than min_run column tiles, about items_per_sm per SM
 };
 
 enum { FE_PHASE_SLICE = 0, FE_PHASE_MIN = 1 };
@@ -107,25 +111,20 @@ struct DeviceLevel {
     uint32_t thr16;
     bool use_thr, need_min, timed;
 };
-struct DeviceLevelState {
-    bool bins = false;                    // brightness bins are on (inside the classes when there are classes)
-    uint32_t nbins = 1, span = 0, ngroups = 1;
-    uint32_t n_launches = 0;              // search launches enqueued (events ctx->ev_pass[2 i], [2 i + 1] when timed)
-    const uint32_t* dom_order = nullptr;  // sorted position -> domain index (NULL: identity)
-    const uint32_t* rng_order = nullptr;  // level position -> range index (NULL: identity)
-};
-int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, DeviceLevelState* st);
+struct DeviceLevelState;
+
 
 // Everything the host reads back after a level, in one record (one D2H copy, one synchronisation per level).
 struct LevelSummary {
     uint32_t mismatch, fp32_regime, flags, passes;
     unsigned long long evaluated;
     uint32_t last_scan, last_flag;
-    uint32_t overflow, pad_;
+    uint32_t slices, min_ran;
+    uint32_t overflow, done;              // done: the slicing is over and no minimum pass is outstanding
     unsigned long long matches;           // nominal candidates of the level: sum over classes of ranges x domains x 4
 };
 __global__ void k_level_summary(const SliceCtl* ctl, const LevelPlan* plan, const uint32_t* counters, const uint32_t* scan_last,
-                                const uint32_t* split_last, LevelSummary* out);
+                                const uint32_t* split_last, uint32_t wants_min_pass, LevelSummary* out);
 
 // kind::f16 kernel, device-scheduled (fe_search_f16.cu)
 struct F16Args {
@@ -144,3 +143,48 @@ struct F16Args {
 };
 int f16_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const uint32_t* dom_order, const LevelPlan* plan, uint32_t max_tiles);
 int f16_launch_search(fe_ctx* ctx, const LevelGeom& g, const F16Args& a, bool retire, bool meta, cudaEvent_t ev0, cudaEvent_t ev1);
+
+// kind::i8 kernel, device-scheduled (fe_search_i8.cu)
+struct I8Args {
+    const void* A8;                       // A blob of the slice: [row tile][K / 16][128 rows][16 B]
+    const void* B8;                       // B blob of the level: [tile][K stage][plane lo, hi][kc / 16][64 columns][16 B]
+    const uint32_t* tileseg;              // [tile] chunk of the tile
+    const uint32_t* blob_dom;             // [tile][64] domain index of every blob column
+    const uint32_t* coln;                 // [tile][64] sum D^2 (INT_MAX: padding column)
+    const ListEntry* list[2];
+    const ItemRec* items;
+    const SliceCtl* ctl;
+    unsigned long long* rowbest;
+    uint32_t* rowhit;
+    uint32_t thr16, use_thr, meta;
+    uint32_t Kpad, stages, n_abuf;
+    uint32_t ordinal;
+};
+int i8_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const uint32_t* dom_order, const LevelPlan* plan, uint32_t nD,
+                  uint32_t max_tiles);
+int i8_build_rows(fe_ctx* ctx, const LevelGeom& g, const LevelPlan* plan, const SliceCtl* ctl, const ListEntry* const list[2], uint32_t ordinal,
+                  uint32_t max_row_tiles);
+int i8_launch_search(fe_ctx* ctx, const LevelGeom& g, I8Args a, cudaEvent_t ev0, cudaEvent_t ev1);
+uint32_t i8_kpad(const LevelGeom& g);
+
+// State of one device-scheduled level between its enqueue calls.
+struct DeviceLevelState {
+    bool bins = false;                    // brightness bins are on (inside the classes when there are classes)
+    uint32_t nbins = 1, span = 0, ngroups = 1;
+    uint32_t n_launches = 0;              // search launches enqueued (events ctx->ev_pass[2 i], [2 i + 1] when timed)
+    const uint32_t* dom_order = nullptr;  // sorted position -> domain index (NULL: identity)
+    const uint32_t* rng_order = nullptr;  // level position -> range index (NULL: identity)
+    // continuation
+    int kind = 0;
+    bool multipass = false, retire = false, timed = false, wants_min_pass = false;
+    uint32_t slices_enqueued = 0, max_row_tiles = 0, nR = 0;
+    bool min_enqueued = false;
+    LevelGeom g;
+    PlanArgs pa{};
+    F16Args fa{};
+    I8Args ia{};
+};
+// Prepares the level (buckets, plan, operand blob) and enqueues `n_slices` slices (0: as many as the scan can need) and, when
+// `with_min`, the minimum pass.  search_level_more enqueues what a level turned out to need beyond that.
+int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n_slices, bool with_min, DeviceLevelState* st);
+int search_level_more(fe_ctx* ctx, DeviceLevelState* st);
