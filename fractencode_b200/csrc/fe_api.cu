@@ -14,7 +14,6 @@
 
 #include "fe_kernels.cuh"
 #include "fe_plan.cuh"
-#include "fe_umma.cuh"
 
 static thread_local std::string g_create_error;   // error of the last failed fe_create on this thread
 
@@ -141,7 +140,7 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
                       &ctx->b_rowc, &ctx->b_coln, &ctx->b_rowbest, &ctx->b_rowhit, &ctx->b_hist, &ctx->b_level_items, &ctx->b_split,
                       &ctx->b_scan, &ctx->b_scan_tmp, &ctx->b_rng_next, &ctx->b_counters, &ctx->b_A16, &ctx->b_B16, &ctx->b_tmaps,
                       &ctx->b_items, &ctx->b_dec_a, &ctx->b_dec_b, &ctx->b_dec_items, &ctx->b_dec_sum, &ctx->b_q, &ctx->b_bound,
-                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_act[0], &ctx->b_act[1], &ctx->b_act_items, &ctx->b_act_flags, &ctx->b_act_tmp, &ctx->b_dom_order2, &ctx->b_rng_order2};
+                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_dom_order2, &ctx->b_rng_order2};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
@@ -378,368 +377,14 @@ static int rerank_fp32_regime(fe_ctx* ctx, const LevelIO& io, const fe_params& p
     return FE_OK;
 }
 
-// tcgen05 search of one level (kind 0: f16 operands, T = 4, 8; kind 1: i8 operands, T <= 32).
-//
-// Without a threshold: one pass, every range against every admissible domain.
-//
-// With a threshold two exact prunings apply, both leaving k_finalize with what it needs to reproduce the reference's
-// estimate() (TransformEstimator2.hpp:29-47): the first candidate in scan order under the threshold, else the minimum.
-//  * Early-out: the scan is cut into growing slices of the domain order; after each slice the ranges whose first hit is
-//    known are final (the reference breaks there too, :40-41) and only the survivors go on, compacted into fresh row tiles.
-//  * Brightness bins: by Cauchy-Schwarz (sum(4r) - sum(D))^2 <= N * n16, so a candidate can only be under the threshold
-//    when the two block sums differ by at most R = floor(sqrt(N * thr16)).  Blocks are bucketed by sum / width (width about
-//    R / 2, plan_bins), so a range of bin c finds every possible hit in the domain bins c-span .. c+span: adjacent in the
-//    operand blob, one work item per row tile.  With the classifier on the bins run inside every class (groups): one
-//    launch per class and slice, back to back.  Ranges that never hit get their minimum from one plain pass over all their
-//    admissible domains at the end -- unless the level can split, where a range without a hit is split and its minimum is
-//    never looked at (Encoder2 quadtree rule): those levels do not even track it (no_min).
-// Hits are recorded as DOMAIN indices (atomicMin), so "first in scan order" holds across bins, slices and column chunks.
-struct TcBuckets {
-    int nb = 1;                            // buckets of one group (one search launch)
-    int ngroups = 1;                       // groups: 1, or the classifier classes when brightness bins run inside every class
-    const uint32_t* dom_order = nullptr;   // position -> domain index, ascending inside a bucket
-    const uint32_t* rng_order = nullptr;   // position -> range index
-    uint32_t doff[FE_MAX_TOTAL + 1] = {0}, roff[FE_MAX_TOTAL + 1] = {0};   // bucket (group g, c) = entry g * nb + c
-    bool bins = false;                     // brightness bins: range bucket c pairs with the domain buckets c-span .. c+span of its group
-    int span = 0;
-    uint32_t cut[8] = {0};                 // bins: domain-index cutoffs of the slice schedule (fractions 2^k / 128 of the scan)
-    uint32_t pre[FE_MAX_TOTAL][8] = {};    // bins: positions of a bucket below cut[k]
-    // bins inside classifier classes: the class-only order (domain index ascending inside a class) for the minimum pass
-    const uint32_t* grp_dom_order = nullptr;
-    uint32_t grp_doff[FE_MAX_GROUPS + 1] = {0};
-};
-
-struct TcSearchResult {
-    bool inexact = false;      // kind 0 only: a winner sits in the fp32-inexact band, redo on kind 1
-    uint64_t evaluated = 0;    // (range, domain, rotation) candidates actually scored
-    uint32_t passes = 0;       // slices
-    uint32_t launches = 0;     // search kernel launches
-    float kernel_ms = 0.f;     // search launches only (CUDA events), when timed
-};
-
-static int search_tc(fe_ctx* ctx, const LevelIO& io, int kind, const TcBuckets& tb, uint32_t thr16, bool use_thr, bool need_min, bool timed,
-                     TcSearchResult* res) {
-    const LevelGeom& g = io.g;
-    const uint32_t nR = io.nR, nD = io.nD;
-    const int nb = tb.nb, nbt = tb.nb * tb.ngroups;                      // buckets per group / of the level
-    const bool single_pass = getenv("FE_SINGLE_PASS") != nullptr;         // tuning / A-B switch: never slice the scan
-    const bool pass_dbg = getenv("FE_PASS_DBG") != nullptr;
-    const bool multipass = use_thr && !single_pass;
-    const uint32_t GR = 128;                                              // slice granularity: whole column tiles of both kinds
-    const char* ms_env = getenv("FE_MIN_STEP");                          // tuning: column tiles a bucket advances per pass at least
-    const uint32_t min_step = (ms_env ? (uint32_t)std::max(1, atoi(ms_env)) : (tb.bins ? std::max(2, 10 / (2 * tb.span + 1)) : 16)) * GR;   // columns a bucket advances per pass at
-                                                                          // least (a work item spans 2*span+1 buckets with bins)
-    LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
-    LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
-    FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));
-    FE_CUDA(ctx, ctx->b_hist.ensure((FE_MAX_TOTAL + 8) * sizeof(uint32_t)));
-    uint32_t* d_cnt = ctx->b_hist.as<uint32_t>();
-    uint32_t* d_nsel = d_cnt + FE_MAX_TOTAL;
-
-    std::vector<uint32_t> dc(nbt), done(nbt, 0), aoff(nbt + 1), lo(nbt), hi(nbt), host(FE_MAX_TOTAL + 1);
-    for (int c = 0; c < nbt; ++c) dc[c] = tb.doff[c + 1] - tb.doff[c];
-    for (int c = 0; c <= nbt; ++c) aoff[c] = tb.roff[c];
-    // neighbours of bucket idx inside its group: [nlo(idx), nhi(idx)]
-    auto nlo = [&](int idx) { return (idx / nb) * nb + std::max(0, idx % nb - tb.span); };
-    auto nhi = [&](int idx) { return (idx / nb) * nb + std::min(nb - 1, idx % nb + tb.span); };
-    const uint32_t* items = tb.rng_order; // range position of the pass -> range item
-    const uint32_t* slots = nullptr;      // range position of the pass -> range position of the level
-    uint32_t nA = nR;
-    int gen = 0, kF = 0;                  // F = 2^kF / 128: cumulative fraction of the scan after this pass
-    double F = multipass ? 1.0 / 128.0 : 1.0;
-    bool reuse_rows = false;              // the operand rows of the current range list are already built
-    bool open_left = true;                // some range may still be without a hit
-    uint32_t done_cutoff = 0;             // every admissible domain below this index has been scored for the ranges still listed
-    *res = TcSearchResult{};
-
-    // survivors of the current list (positions whose best hit is not below `cutoff`), compacted; updates the list state
-    auto survivors = [&](uint32_t cutoff, bool read_inexact, bool* inexact, uint32_t* n_left) -> int {
-        FE_CUDA(ctx, ctx->b_act_flags.ensure((size_t)nA + 16));
-        FE_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)nbt * sizeof(uint32_t), ctx->stream));
-        TotalOff o;
-        for (int c = 0; c <= FE_MAX_TOTAL; ++c) o.v[c] = aoff[std::min(c, nbt)];
-        LAUNCH(ctx, k_unresolved, cdiv(nA, 256), 256, slots, ctx->b_rowhit.as<uint32_t>(), nA, o, nbt, cutoff, ctx->b_act_flags.as<uint8_t>(), d_cnt);
-        FE_CUDA(ctx, cudaMemcpyAsync(host.data(), d_cnt, (size_t)nbt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        if (read_inexact)
-            FE_CUDA(ctx, cudaMemcpyAsync(host.data() + FE_MAX_TOTAL, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        *inexact = read_inexact && (host[FE_MAX_TOTAL] & 1u);
-        uint32_t S = 0;
-        for (int c = 0; c < nbt; ++c) S += host[c];
-        *n_left = S;
-        if (*inexact || S == 0 || S == nA) return FE_OK;
-        // stable compaction of the surviving positions (bucket grouping is kept), then their item indices
-        DevBuf& out = ctx->b_act[gen];
-        FE_CUDA(ctx, out.ensure((size_t)S * 4 + 16));
-        FE_CUDA(ctx, ctx->b_act_items.ensure((size_t)S * 4 + 16));
-        size_t tmp_bytes = 0;
-        if (slots) {
-            FE_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, slots, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
-            FE_CUDA(ctx, ctx->b_act_tmp.ensure(tmp_bytes));
-            FE_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_act_tmp.p, tmp_bytes, slots, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
-        } else {
-            thrust::counting_iterator<uint32_t> iota(0u);
-            FE_CUDA(ctx, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
-            FE_CUDA(ctx, ctx->b_act_tmp.ensure(tmp_bytes));
-            FE_CUDA(ctx, cub::DeviceSelect::Flagged(ctx->b_act_tmp.p, tmp_bytes, iota, ctx->b_act_flags.as<uint8_t>(), out.as<uint32_t>(), d_nsel, (int)nA, ctx->stream));
-        }
-        ctx->stats.kernel_launches += 2;
-        slots = out.as<uint32_t>();
-        gen ^= 1;
-        if (tb.rng_order) {
-            LAUNCH(ctx, k_gather_u32, cdiv(S, 256), 256, slots, tb.rng_order, S, ctx->b_act_items.as<uint32_t>());
-            items = ctx->b_act_items.as<uint32_t>();
-        } else {
-            items = slots;
-        }
-        aoff[0] = 0;
-        for (int c = 0; c < nbt; ++c) aoff[c + 1] = aoff[c] + host[c];
-        nA = S;
-        reuse_rows = false;
-        return FE_OK;
-    };
-    auto launch = [&](SearchPass& sp) -> int {
-        if (res->launches >= (uint32_t)FE_MAX_LAUNCHES) return fe_fail(ctx, FE_ERR_CUDA, "internal: search launch budget exceeded");
-        if (timed) { sp.ev0 = ctx->ev_pass[2 * res->launches]; sp.ev1 = ctx->ev_pass[2 * res->launches + 1]; }
-        sp.reuse_rows = reuse_rows;
-        if (kind == 0) FE_TRY(umma_prepare_and_search(ctx, g, io.d_dom, io.d_rng, sp, thr16, use_thr));
-        else FE_TRY(umma_i8_prepare_and_search(ctx, g, io.d_dom, io.d_rng, sp, thr16, use_thr));
-        ++res->launches;
-        reuse_rows = true;
-        return FE_OK;
-    };
-
-    for (;;) {
-        if (res->passes >= (uint32_t)FE_MAX_PASSES - 2) F = 1.0;
-        // ---- domain slice of every bucket for this pass ----
-        bool all_done = true, any_work = false;
-        for (int b = 0; b < nbt; ++b) {
-            bool wanted = false;
-            for (int c = nlo(b); c <= nhi(b); ++c)
-                if (aoff[c + 1] > aoff[c]) wanted = true;                 // some range bucket that meets this domain bucket is alive
-            lo[b] = done[b];
-            hi[b] = dc[b];
-            if (!wanted) { lo[b] = hi[b] = done[b] = dc[b]; continue; }   // its ranges are all closed: never needed again
-            if (F < 1.0) {
-                const uint64_t target = tb.bins ? tb.pre[b][kF] : (uint64_t)std::ceil((double)dc[b] * F);
-                const uint64_t up = (std::max<uint64_t>(min_step, target) + GR - 1) / GR * GR;
-                hi[b] = (uint32_t)std::min<uint64_t>(dc[b], std::max<uint64_t>(up, (uint64_t)done[b] + min_step));   // every pass advances
-                if (dc[b] - hi[b] < min_step / 2) hi[b] = dc[b];         // no slivers at the end of the scan
-            }
-            if (hi[b] > lo[b]) any_work = true;
-            if (hi[b] < dc[b]) all_done = false;
-        }
-        if (!any_work) break;
-        // every admissible domain with an index below `cutoff` has been scored once this pass is through
-        const uint32_t cutoff = (tb.bins && !all_done) ? tb.cut[kF] : FE_NONE32;
-        for (int grp = 0; grp < tb.ngroups; ++grp) {                      // one launch per group, back to back (no round trip between)
-            const int g0 = grp * nb;
-            SearchPass sp{};
-            sp.dom_order = tb.dom_order; sp.rng_items = items; sp.rowslot = slots;
-            sp.nbuckets = nb; sp.n_dom = nD;
-            sp.span = tb.span;
-            sp.no_min = use_thr && !need_min;
-            sp.reuse_dom_norms = res->launches > 0;
-            uint64_t cols = 0, work = 0;
-            for (int b = 0; b < nb; ++b) {
-                sp.dbeg[b] = tb.doff[g0 + b] + lo[g0 + b];
-                sp.dend[b] = tb.doff[g0 + b] + hi[g0 + b];
-                cols += hi[g0 + b] - lo[g0 + b];
-            }
-            for (int c = 0; c < nb; ++c) {
-                const uint32_t rc = aoff[g0 + c + 1] - aoff[g0 + c];
-                for (int b = nlo(g0 + c); rc && b <= nhi(g0 + c); ++b) work += (uint64_t)rc * (hi[b] - lo[b]) * 4;
-            }
-            for (int c = 0; c <= nb; ++c) sp.roff[c] = aoff[g0 + c];
-            if (!work) continue;
-            if (tb.ngroups > 1) reuse_rows = false;                       // the groups share the operand buffers
-            if (pass_dbg)
-                fprintf(stderr, "[pass] T=%u kind=%d pass=%u group=%d ranges=%u of %u cols=%llu candidates=%.3e (scan fraction %.4f) rebuild_rows=%d\n", g.T,
-                        kind, res->passes, grp, aoff[g0 + nb] - aoff[g0], nA, (unsigned long long)cols, (double)work, F, reuse_rows ? 0 : 1);
-            FE_TRY(launch(sp));
-            res->evaluated += work;
-        }
-        for (int b = 0; b < nbt; ++b) done[b] = hi[b];
-        ++res->passes;
-        done_cutoff = cutoff;
-
-        if (all_done) {
-            if (kind == 0) {
-                FE_CUDA(ctx, cudaMemcpyAsync(host.data() + FE_MAX_TOTAL, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-                FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                res->inexact = (host[FE_MAX_TOTAL] & 1u) != 0;
-            }
-            break;
-        }
-        const uint32_t before = nA;
-        uint32_t S = 0;
-        FE_TRY(survivors(cutoff, kind == 0, &res->inexact, &S));
-        if (res->inexact) break;
-        if (S == 0) { open_left = false; break; }                         // every range has its first hit
-        const double resolved = 1.0 - (double)S / (double)before;
-        // Bins only pay when ranges end on a hit: a range without one still needs the plain pass over every domain for its
-        // minimum, and the bins (about a third of the scan) come on top.  Hits come early in the scan where they come at
-        // all -- first slices that close next to nothing say "no hits on this level": go plain now.
-        if (tb.bins && need_min && res->passes <= 2 && resolved < 0.05) break;
-        // slices that close little grow faster; one that closes nothing at all says early-out will not pay: finish in one go
-        const int step = resolved >= 0.03 ? 1 : (resolved >= 0.002 ? 2 : 8);
-        kF += step;
-        F *= (double)(1 << step);
-        // what is left is small: one more launch for all of it costs less than the round trips of several slices
-        uint64_t left = 0;
-        for (int c = 0; c < nbt; ++c) {
-            const uint64_t rc = aoff[c + 1] - aoff[c];
-            for (int b = nlo(c); rc && b <= nhi(c); ++b) left += rc * (dc[b] - done[b]) * 4;
-        }
-        if ((double)left * 2.0 * g.N <= 1.5e11) F = 1.0;
-        if (kF > 7) { kF = 7; F = 1.0; }
-    }
-
-    if (tb.bins && need_min && open_left && !res->inexact) {
-        // ---- ranges whose first hit is not known yet: one plain pass over ALL domains in scan order (first hit and minimum) ----
-        uint32_t S = 0;
-        bool inex = false;
-        FE_TRY(survivors(done_cutoff, false, &inex, &S));
-        if (S) {
-            LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
-            SearchPass sp{};
-            sp.rng_items = items; sp.rowslot = slots;
-            sp.n_dom = nD;
-            sp.reuse_dom_norms = false;
-            uint64_t work = 0;
-            if (tb.ngroups == 1) {
-                sp.dom_order = nullptr;
-                sp.nbuckets = 1;
-                sp.dbeg[0] = 0; sp.dend[0] = nD;
-                sp.roff[0] = 0; sp.roff[1] = S;
-                work = (uint64_t)S * nD * 4;
-            } else {                                                      // every class against its own domains, in scan order
-                sp.dom_order = tb.grp_dom_order;
-                sp.nbuckets = tb.ngroups;
-                for (int grp = 0; grp < tb.ngroups; ++grp) {
-                    sp.dbeg[grp] = tb.grp_doff[grp]; sp.dend[grp] = tb.grp_doff[grp + 1];
-                    sp.roff[grp] = aoff[grp * nb];
-                    work += (uint64_t)(aoff[(grp + 1) * nb] - aoff[grp * nb]) * (tb.grp_doff[grp + 1] - tb.grp_doff[grp]) * 4;
-                }
-                sp.roff[tb.ngroups] = aoff[nbt];
-            }
-            reuse_rows = false;                                           // other buckets now: different row tiles
-            if (pass_dbg) fprintf(stderr, "[pass] T=%u kind=%d minimum pass: ranges=%u candidates=%.3e\n", g.T, kind, S, (double)work);
-            FE_TRY(launch(sp));
-            res->evaluated += work;
-            ++res->passes;
-            if (kind == 0) {
-                FE_CUDA(ctx, cudaMemcpyAsync(host.data() + FE_MAX_TOTAL, ctx->b_counters.as<uint32_t>() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-                FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                res->inexact = (host[FE_MAX_TOTAL] & 1u) != 0;
-            }
-        }
-    }
-    if (timed && res->launches) {
-        cudaEventSynchronize(ctx->ev_pass[2 * res->launches - 1]);
-        for (uint32_t i = 0; i < res->launches; ++i) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, ctx->ev_pass[2 * i], ctx->ev_pass[2 * i + 1]);
-            res->kernel_ms += ms;
-            if (pass_dbg) fprintf(stderr, "[pass] T=%u kind=%d launch=%u kernel %.3f ms\n", g.T, kind, i, ms);
-        }
-    }
-    return FE_OK;
-}
-
-// Stable bucketing of the level's two uniform block lists by brightness bin (see search_tc); order[pos] = item index.
-// Keys and histograms of both lists first, ONE host round trip for the two histograms, then the two sorts.
-static int bucket_by_brightness(fe_ctx* ctx, const LevelIO& io, uint32_t width, int nbins, uint32_t doff[FE_MAX_BUCKETS + 1],
-                                uint32_t roff[FE_MAX_BUCKETS + 1], const uint32_t cut[8], uint32_t pre[FE_MAX_BUCKETS][8]) {
-    const uint32_t nD = io.nD, nR = io.nR;
-    const size_t n = (size_t)nD + nR;
-    FE_CUDA(ctx, ctx->b_dom_order.ensure((size_t)nD * sizeof(uint32_t)));
-    FE_CUDA(ctx, ctx->b_rng_order.ensure((size_t)nR * sizeof(uint32_t)));
-    FE_CUDA(ctx, ctx->b_keys_tmp.ensure(n * 2 + 64));
-    FE_CUDA(ctx, ctx->b_vals_tmp.ensure((size_t)std::max(nD, nR) * sizeof(uint32_t)));
-    FE_CUDA(ctx, ctx->b_hist.ensure((size_t)FE_MAX_BUCKETS * 10 * sizeof(uint32_t)));
-    uint8_t* dkeys = ctx->b_keys_tmp.as<uint8_t>();
-    uint8_t* rkeys = dkeys + nD;
-    uint8_t* keys_out = dkeys + n;
-    uint32_t* hist = ctx->b_hist.as<uint32_t>();
-    FE_CUDA(ctx, cudaMemsetAsync(hist, 0, 2 * FE_MAX_BUCKETS * sizeof(uint32_t), ctx->stream));
-    launch_brightness_bins(ctx->stream, ctx->src.px, ctx->src.stride, io.d_dom, nD, io.g.S, 1u, width, dkeys, hist);
-    launch_brightness_bins(ctx->stream, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, io.g.T, 4u, width, rkeys, hist + FE_MAX_BUCKETS);
-    FE_CUDA(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches += 2;
-    LAUNCH(ctx, k_iota, cdiv(std::max(nD, nR), 256), 256, ctx->b_vals_tmp.as<uint32_t>(), std::max(nD, nR));
-    size_t tmp_d = 0, tmp_r = 0;
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_d, dkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order.as<uint32_t>(), (int)nD, 0, 6, ctx->stream));
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_r, rkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order.as<uint32_t>(), (int)nR, 0, 6, ctx->stream));
-    FE_CUDA(ctx, ctx->b_sort_tmp.ensure(std::max(tmp_d, tmp_r)));
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_d, dkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order.as<uint32_t>(), (int)nD, 0, 6, ctx->stream));
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_r, rkeys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order.as<uint32_t>(), (int)nR, 0, 6, ctx->stream));
-    ctx->stats.kernel_launches += 6;
-    // prefix lengths of every domain bucket at the slice cutoffs (device-side offsets: no host round trip in between)
-    BucketOff c8{};
-    for (int k = 0; k < 8; ++k) c8.v[k] = cut[k];
-    LAUNCH(ctx, k_bin_prefix, cdiv((uint64_t)nbins * 8, 128), 128, ctx->b_dom_order.as<uint32_t>(), hist, nbins, c8, hist + 2 * FE_MAX_BUCKETS);
-    uint32_t h[FE_MAX_BUCKETS * 10];
-    FE_CUDA(ctx, cudaMemcpyAsync(h, hist, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    doff[0] = roff[0] = 0;
-    for (int c = 0; c < nbins; ++c) { doff[c + 1] = doff[c] + h[c]; roff[c + 1] = roff[c] + h[FE_MAX_BUCKETS + c]; }
-    for (int b = 0; b < nbins; ++b)
-        for (int k = 0; k < 8; ++k) pre[b][k] = h[2 * FE_MAX_BUCKETS + b * 8 + k];
-    return FE_OK;
-}
-
-// Classifier classes x brightness bins (a threshold search with the classifier on): both lists are ordered by
-// (class, bin, index); bucket (class c, bin b) = entry (c + 1) * nbins + b of the offset arrays.  The class-only orders
-// (bucket_by_class) must already sit in b_dom_order / b_rng_order with the classes in b_dom_cls / b_rng_cls.
-static int bucket_by_class_and_brightness(fe_ctx* ctx, const LevelIO& io, uint32_t width, int nbins, TcBuckets* tb) {
-    const uint32_t nD = io.nD, nR = io.nR;
-    const int nbt = 7 * nbins;
-    const size_t n = (size_t)nD + nR;
-    FE_CUDA(ctx, ctx->b_dom_order2.ensure((size_t)nD * sizeof(uint32_t)));
-    FE_CUDA(ctx, ctx->b_rng_order2.ensure((size_t)nR * sizeof(uint32_t)));
-    FE_CUDA(ctx, ctx->b_keys_tmp.ensure(n * 7 + 256));
-    FE_CUDA(ctx, ctx->b_vals_tmp.ensure((size_t)std::max(nD, nR) * sizeof(uint32_t)));
-    FE_CUDA(ctx, ctx->b_hist.ensure((size_t)FE_MAX_TOTAL * 10 * sizeof(uint32_t)));
-    uint8_t* bins8 = ctx->b_keys_tmp.as<uint8_t>();                              // [nD + nR] brightness bins
-    uint16_t* keys = reinterpret_cast<uint16_t*>(bins8 + ((n + 63) & ~(size_t)63)); // [nD + nR] composite keys, then the sorted copies
-    uint16_t* keys_out = keys + n;
-    uint32_t* hist = ctx->b_hist.as<uint32_t>();                                 // [FE_MAX_TOTAL] domains, [FE_MAX_TOTAL] ranges, [FE_MAX_TOTAL * 8] prefixes
-    FE_CUDA(ctx, cudaMemsetAsync(hist, 0, 2 * FE_MAX_TOTAL * sizeof(uint32_t), ctx->stream));
-    uint32_t* scratch = hist + 2 * FE_MAX_TOTAL;                                 // bin histograms nobody reads (filled before the prefixes)
-    FE_CUDA(ctx, cudaMemsetAsync(scratch, 0, 2 * FE_MAX_BUCKETS * sizeof(uint32_t), ctx->stream));
-    launch_brightness_bins(ctx->stream, ctx->src.px, ctx->src.stride, io.d_dom, nD, io.g.S, 1u, width, bins8, scratch);
-    launch_brightness_bins(ctx->stream, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, io.g.T, 4u, width, bins8 + nD, scratch + FE_MAX_BUCKETS);
-    LAUNCH(ctx, k_composite_keys, cdiv(nD, 256), 256, ctx->b_dom_cls.as<int32_t>(), bins8, nD, (uint32_t)nbins, keys, hist);
-    LAUNCH(ctx, k_composite_keys, cdiv(nR, 256), 256, ctx->b_rng_cls.as<int32_t>(), bins8 + nD, nR, (uint32_t)nbins, keys + nD, hist + FE_MAX_TOTAL);
-    LAUNCH(ctx, k_iota, cdiv(std::max(nD, nR), 256), 256, ctx->b_vals_tmp.as<uint32_t>(), std::max(nD, nR));
-    size_t tmp_d = 0, tmp_r = 0;
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_d, keys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order2.as<uint32_t>(), (int)nD, 0, 9, ctx->stream));
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_r, keys + nD, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order2.as<uint32_t>(), (int)nR, 0, 9, ctx->stream));
-    FE_CUDA(ctx, ctx->b_sort_tmp.ensure(std::max(tmp_d, tmp_r)));
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_d, keys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order2.as<uint32_t>(), (int)nD, 0, 9, ctx->stream));
-    FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_r, keys + nD, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order2.as<uint32_t>(), (int)nR, 0, 9, ctx->stream));
-    ctx->stats.kernel_launches += 10;
-    BucketOff c8{};
-    for (int k = 0; k < 8; ++k) c8.v[k] = tb->cut[k];
-    LAUNCH(ctx, k_bin_prefix, cdiv((uint64_t)nbt * 8, 128), 128, ctx->b_dom_order2.as<uint32_t>(), hist, nbt, c8, hist + 2 * FE_MAX_TOTAL);
-    std::vector<uint32_t> h((size_t)FE_MAX_TOTAL * 10);
-    FE_CUDA(ctx, cudaMemcpyAsync(h.data(), hist, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    tb->doff[0] = tb->roff[0] = 0;
-    for (int c = 0; c < nbt; ++c) { tb->doff[c + 1] = tb->doff[c] + h[c]; tb->roff[c + 1] = tb->roff[c] + h[FE_MAX_TOTAL + c]; }
-    for (int b = 0; b < nbt; ++b)
-        for (int k = 0; k < 8; ++k) tb->pre[b][k] = h[2 * FE_MAX_TOTAL + b * 8 + k];
-    return FE_OK;
-}
-
-static int run_level_host(fe_ctx* ctx, const LevelIO& io, const fe_params& p, bool skip_f16 = false) {
+// One level on the exact integer path (CUDA cores, dp4a): u8 rows, low/high byte pools.  Every geometry the tensor paths do
+// not take -- rho != 2, odd domain origins, T = 2 or 64 -- and FE_SEARCH_EXACT.  Runs to completion (synchronises).
+static int run_level_exact(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     const LevelGeom& g = io.g;
     const uint32_t nR = io.nR, nD = io.nD;
     if (nR == 0) return FE_OK;
     const bool timed = io.stat_level >= 0 && io.stat_level < 8;
     if (timed) cudaEventRecord(ctx->ev[0], ctx->stream);
-
     FE_CUDA(ctx, ctx->b_counters.ensure(16 * sizeof(uint32_t)));
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.p, 0, 16 * sizeof(uint32_t), ctx->stream));
 
@@ -759,7 +404,6 @@ static int run_level_host(fe_ctx* ctx, const LevelIO& io, const fe_params& p, bo
         rng_order = ctx->b_rng_order.as<uint32_t>();
         nbuckets = 7;
     }
-
     if (p.rms_threshold * (double)(g.S * g.S) >= 1048576.0)
         return fe_fail(ctx, FE_ERR_UNSUPPORTED, "rms_threshold %g reaches the fp32-rounding regime of the reference distance (SSE >= 2^20) at S=%u", p.rms_threshold, g.S);
     uint32_t thr16 = 0;
@@ -770,114 +414,42 @@ static int run_level_host(fe_ctx* ctx, const LevelIO& io, const fe_params& p, bo
     FE_CUDA(ctx, ctx->b_rowhit.ensure((size_t)nR * 4 * 4));
     FE_CUDA(ctx, ctx->b_rowc.ensure((size_t)nR * 4));
 
-    const bool f16_ok = nD && umma_level_supported(g) && !skip_f16, i8_ok = nD && umma_i8_level_supported(g);
-    if (p.search_impl == FE_SEARCH_UMMA && nD && !f16_ok && !i8_ok)
-        return fe_fail(ctx, FE_ERR_UNSUPPORTED, "tcgen05 paths need S == 2T, even domain origins and T <= 32 (got S=%u T=%u)", g.S, g.T);
-    bool searched = false;
-    uint64_t evaluated = matches;
-    uint32_t passes = 1;
-    float kernel_ms = -1.f;
-    bool bins = false;
-    const uint32_t* cls_dom_order = nullptr;   // bins inside classifier classes: class-only domain order and class offsets of the
-    uint32_t cls_roff[8] = {0};                // (class, bin)-ordered range list, for the re-rank
-    if (p.search_impl != FE_SEARCH_EXACT && (f16_ok || i8_ok)) {
-        TcBuckets tb;
-        tb.nb = nbuckets;
-        tb.dom_order = dom_order; tb.rng_order = rng_order;
-        for (int c = 0; c <= nbuckets; ++c) { tb.doff[c] = doff[c]; tb.roff[c] = roff[c]; }
-        // ---- brightness bins (threshold): see search_tc; with the classifier on they run inside every class ----
-        if (use_thr && nD && !getenv("FE_NO_BINS") && !getenv("FE_SINGLE_PASS")) {
-            fe_threshold_plan pl{};
-            fe_plan_bins(g.N, thr16, &pl);
-            const uint64_t width = pl.bin_width;
-            const int nbins = (int)pl.n_bins, span = (int)pl.bin_span;
-            // Inside classifier classes the bins cost seven launches per slice (the classes share the operand buffers): only
-            // worth it when the level is big -- below ~7 TFLOP of nominal work the plain class buckets finish sooner.
-            // On the last level most ranges close in the first slice anyway (everything that did not match further up ends
-            // there), so the extra launches buy little: levels that split only.
-            // Levels of small blocks run many slices (seven launches each): they need more work to pay (measured on config 4,
-            // whole and sharded over 8 GPUs).
-            const double nominal = (double)matches * 2.0 * g.N;
-            const bool cls_bins_pay = (io.can_split && nominal >= (g.T >= 16 ? 7e12 : 3e13)) || getenv("FE_CLASS_BINS") != nullptr;
-            if (nbins && (!p.use_classifier || cls_bins_pay)) {
-                tb.span = span;
-                for (int k = 0; k < 8; ++k) tb.cut[k] = k == 7 ? nD : (uint32_t)(((uint64_t)nD << k) / 128 + 1);
-                if (p.use_classifier) {
-                    tb.grp_dom_order = dom_order;                    // class-only order: the minimum pass and the re-rank use it
-                    for (int c = 0; c <= 7; ++c) tb.grp_doff[c] = doff[c];
-                    FE_TRY(bucket_by_class_and_brightness(ctx, io, (uint32_t)width, nbins, &tb));
-                    tb.ngroups = 7;
-                    tb.dom_order = ctx->b_dom_order2.as<uint32_t>();
-                    tb.rng_order = ctx->b_rng_order2.as<uint32_t>();
-                    for (int c = 0; c <= 7; ++c) cls_roff[c] = tb.roff[c * nbins];
-                    cls_dom_order = dom_order;
-                } else {
-                    FE_TRY(bucket_by_brightness(ctx, io, (uint32_t)width, nbins, tb.doff, tb.roff, tb.cut, tb.pre));
-                    tb.dom_order = ctx->b_dom_order.as<uint32_t>();
-                    tb.rng_order = ctx->b_rng_order.as<uint32_t>();
-                }
-                tb.nb = nbins;
-                tb.bins = bins = true;
-                dom_order = nullptr;                 // results come back as domain indices
-                rng_order = tb.rng_order;            // row slots follow the binned range order
-            }
-        }
-        const bool need_min = !io.can_split;
-        TcSearchResult r{};
-        r.inexact = !f16_ok;
-        evaluated = 0; passes = 0; kernel_ms = 0.f;
-        if (f16_ok) {
-            // ---- tcgen05 kind::f16 (T = 4, 8): fp16 operand blobs, integer-exact fp32 accumulators, fused argmin ----
-            FE_TRY(search_tc(ctx, io, 0, tb, thr16, use_thr, need_min, timed, &r));
-            evaluated += r.evaluated; passes += r.launches; kernel_ms += r.kernel_ms;
-        }
-        if (r.inexact) {
-            // ---- tcgen05 kind::i8 (T >= 16, or a winner of the f16 kind in the fp32-inexact band): exact s32 accumulators ----
-            FE_TRY(search_tc(ctx, io, 1, tb, thr16, use_thr, need_min, timed, &r));
-            evaluated += r.evaluated; passes += r.launches; kernel_ms += r.kernel_ms;
-        }
-        searched = true;
-        ctx->stats.umma_levels++;
+    const uint32_t npool = g.fast ? 1u : 4u;
+    FE_CUDA(ctx, ctx->b_A.ensure((size_t)nR * 4 * g.Npad));
+    LAUNCH(ctx, k_build_rows, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, rng_order, nR, g.T, g.Npad,
+           g.fast ? 1 : 0, ctx->b_A.as<uint8_t>(), ctx->b_rowc.as<uint32_t>());
+    if (nD) {
+        FE_CUDA(ctx, ctx->b_Blo.ensure((size_t)nD * npool * g.Npad));
+        FE_CUDA(ctx, ctx->b_Bhi.ensure((size_t)nD * npool * g.Npad));
+        FE_CUDA(ctx, ctx->b_coln.ensure((size_t)nD * npool * 4));
+        LAUNCH(ctx, k_build_pool, cdiv((uint64_t)nD * npool * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, dom_order, nD, npool,
+               g.T, g.rho, g.Npad, ctx->b_Blo.as<uint8_t>(), ctx->b_Bhi.as<uint8_t>(), ctx->b_coln.as<uint32_t>());
     }
-    if (!searched) {
-        // ---- exact integer path: u8 rows, low/high byte pools, dp4a ----
-        const uint32_t npool = g.fast ? 1u : 4u;
-        FE_CUDA(ctx, ctx->b_A.ensure((size_t)nR * 4 * g.Npad));
-        LAUNCH(ctx, k_build_rows, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, rng_order, nR, g.T, g.Npad,
-               g.fast ? 1 : 0, ctx->b_A.as<uint8_t>(), ctx->b_rowc.as<uint32_t>());
-        if (nD) {
-            FE_CUDA(ctx, ctx->b_Blo.ensure((size_t)nD * npool * g.Npad));
-            FE_CUDA(ctx, ctx->b_Bhi.ensure((size_t)nD * npool * g.Npad));
-            FE_CUDA(ctx, ctx->b_coln.ensure((size_t)nD * npool * 4));
-            LAUNCH(ctx, k_build_pool, cdiv((uint64_t)nD * npool * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, dom_order, nD, npool,
-                   g.T, g.rho, g.Npad, ctx->b_Blo.as<uint8_t>(), ctx->b_Bhi.as<uint8_t>(), ctx->b_coln.as<uint32_t>());
-        }
-        LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
-        LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
-        if (timed) cudaEventRecord(ctx->ev[1], ctx->stream);
-        for (int c = 0; c < nbuckets; ++c) {
-            const uint32_t rc = roff[c + 1] - roff[c], dc = doff[c + 1] - doff[c];
-            if (!rc || !dc) continue;
-            SearchArgs a{};
-            a.A = ctx->b_A.as<uint8_t>();
-            a.Blo = ctx->b_Blo.as<uint8_t>();
-            a.Bhi = ctx->b_Bhi.as<uint8_t>();
-            a.rowc = ctx->b_rowc.as<uint32_t>();
-            a.coln = ctx->b_coln.as<uint32_t>();
-            a.rowbest = ctx->b_rowbest.as<unsigned long long>();
-            a.rowhit = ctx->b_rowhit.as<uint32_t>();
-            a.row0 = roff[c] * 4; a.nrows = rc * 4;
-            a.col0 = doff[c]; a.ncols = dc;
-            a.Npad = g.Npad;
-            a.pool_stride_cols = g.fast ? 0 : nD;
-            a.thr16 = thr16;
-            a.use_thr = use_thr ? 1u : 0u;
-            FE_CUDA(ctx, launch_search_exact(ctx, a));
-        }
-        ctx->stats.exact_levels++;
+    LAUNCH(ctx, k_fill_u64, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
+    LAUNCH(ctx, k_fill_u32, cdiv((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
+    if (timed) cudaEventRecord(ctx->ev[1], ctx->stream);
+    for (int c = 0; c < nbuckets; ++c) {
+        const uint32_t rc = roff[c + 1] - roff[c], dc = doff[c + 1] - doff[c];
+        if (!rc || !dc) continue;
+        SearchArgs a{};
+        a.A = ctx->b_A.as<uint8_t>();
+        a.Blo = ctx->b_Blo.as<uint8_t>();
+        a.Bhi = ctx->b_Bhi.as<uint8_t>();
+        a.rowc = ctx->b_rowc.as<uint32_t>();
+        a.coln = ctx->b_coln.as<uint32_t>();
+        a.rowbest = ctx->b_rowbest.as<unsigned long long>();
+        a.rowhit = ctx->b_rowhit.as<uint32_t>();
+        a.row0 = roff[c] * 4; a.nrows = rc * 4;
+        a.col0 = doff[c]; a.ncols = dc;
+        a.Npad = g.Npad;
+        a.pool_stride_cols = g.fast ? 0 : nD;
+        a.thr16 = thr16;
+        a.use_thr = use_thr ? 1u : 0u;
+        FE_CUDA(ctx, launch_search_exact(ctx, a));
     }
+    ctx->stats.exact_levels++;
     ctx->stats.matches += matches;
-    ctx->stats.evaluated += evaluated;
+    ctx->stats.evaluated += matches;
     if (timed) cudaEventRecord(ctx->ev[2], ctx->stream);
 
     // ---- winners ----
@@ -899,9 +471,8 @@ static int run_level_host(fe_ctx* ctx, const LevelIO& io, const fe_params& p, bo
     FE_CUDA(ctx, ctx->b_bound.ensure((size_t)nR * 4 + 4));
     f.bound_out = ctx->b_bound.as<uint32_t>();
     f.rerank = 0;
-    f.hit_is_domain = searched ? 1 : 0;
-    if (searched) f.dom_order = nullptr;   // the tcgen05 paths report domain indices (keys and hits), not sorted columns
-    f.no_min = (searched && use_thr && io.can_split) ? 1 : 0;   // a range without a hit splits: its minimum was not even tracked
+    f.hit_is_domain = 0;                 // the exact path reports sorted column positions
+    f.no_min = 0;
     FE_TRY(launch_finalize(ctx, f, g.T));
     if (timed) cudaEventRecord(ctx->ev[3], ctx->stream);
 
@@ -910,30 +481,15 @@ static int run_level_host(fe_ctx* ctx, const LevelIO& io, const fe_params& p, bo
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (counters[0]) return fe_fail(ctx, FE_ERR_CUDA, "internal: %u winners whose search score disagrees with the direct recomputation (T=%u)", counters[0], g.T);
     ctx->stats.fp32_regime_items += counters[1];
-    if (counters[1]) {
-        if (bins && cls_dom_order) { // bins inside classes: a class's domains in scan order, rows in the (class, bin) range order
-            FE_TRY(rerank_fp32_regime(ctx, io, p, cls_dom_order, rng_order, doff, cls_roff, 7));
-        } else if (bins) { // every domain is admissible for the minimum: one bucket in scan order, rows in the binned range order
-            const uint32_t d1[8] = {0, nD, nD, nD, nD, nD, nD, nD}, r1[8] = {0, nR, nR, nR, nR, nR, nR, nR};
-            FE_TRY(rerank_fp32_regime(ctx, io, p, nullptr, rng_order, d1, r1, 1));
-        } else {
-            FE_TRY(rerank_fp32_regime(ctx, io, p, dom_order, rng_order, doff, roff, nbuckets));
-        }
-    }
+    if (counters[1]) FE_TRY(rerank_fp32_regime(ctx, io, p, dom_order, rng_order, doff, roff, nbuckets));
     if (timed) {
         float ms = 0;
-        if (kernel_ms >= 0.f) { // tcgen05 path: the search launches were timed one by one; the rest of the level is preparation
-            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]);
-            ctx->stats.level_search_ms[io.stat_level] = kernel_ms;
-            ctx->stats.level_prep_ms[io.stat_level] = ms - kernel_ms;
-        } else {
-            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.level_prep_ms[io.stat_level] = ms;
-            cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.level_search_ms[io.stat_level] = ms;
-        }
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stats.level_prep_ms[io.stat_level] = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.level_search_ms[io.stat_level] = ms;
         ctx->stats.level_ranges[io.stat_level] = nR;
         ctx->stats.level_matches[io.stat_level] = matches;
-        ctx->stats.level_evaluated[io.stat_level] = evaluated;
-        ctx->stats.level_passes[io.stat_level] = passes;
+        ctx->stats.level_evaluated[io.stat_level] = matches;
+        ctx->stats.level_passes[io.stat_level] = 1;
     }
     return FE_OK;
 }
@@ -941,7 +497,7 @@ static int run_level_host(fe_ctx* ctx, const LevelIO& io, const fe_params& p, bo
 // ---------------------------------------------------------------------------------------------------
 // A level in two halves: everything is enqueued, then ONE synchronisation reads the level's summary back (together with
 // the quadtree's split count).  Levels of the device-scheduled tcgen05 path (fe_plan.cu) never synchronise in between;
-// the other paths (exact integer search, host-scheduled i8 kind) still run to completion inside the first half.
+// the exact integer path (generic geometries) still runs to completion inside the first half.
 // ---------------------------------------------------------------------------------------------------
 struct LevelPending {
     bool device = false;
@@ -959,9 +515,13 @@ static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p,
     const uint32_t nR = io.nR, nD = io.nD;
     *lp = LevelPending{};
     if (nR == 0) return FE_OK;
-    const bool f16_ok = nD && umma_level_supported(g) && !skip_f16, i8_ok = nD && umma_i8_level_supported(g);
-    const bool device = (f16_ok || i8_ok) && p.search_impl != FE_SEARCH_EXACT && !getenv("FE_HOST_SLICES");
-    if (!device) return run_level_host(ctx, io, p, skip_f16);
+    const bool f16_ok = nD && f16_level_supported(g) && !skip_f16, i8_ok = nD && i8_level_supported(g);
+    const bool device = (f16_ok || i8_ok) && p.search_impl != FE_SEARCH_EXACT;
+    if (!device) {
+        if (p.search_impl == FE_SEARCH_UMMA && nD)
+            return fe_fail(ctx, FE_ERR_UNSUPPORTED, "tcgen05 paths need S == 2T, even domain origins and T <= 32 (got S=%u T=%u)", g.S, g.T);
+        return run_level_exact(ctx, io, p);
+    }
     lp->kind = f16_ok ? 0 : 1;
     if (p.rms_threshold * (double)(g.S * g.S) >= 1048576.0)
         return fe_fail(ctx, FE_ERR_UNSUPPORTED, "rms_threshold %g reaches the fp32-rounding regime of the reference distance (SSE >= 2^20) at S=%u", p.rms_threshold, g.S);

@@ -72,8 +72,7 @@ struct SearchArgs {
     uint32_t rho;
 };
 
-constexpr int FE_MAX_PASSES = 32;
-constexpr int FE_MAX_LAUNCHES = 3 * FE_MAX_PASSES + 4;   // search launches of one level (three brightness-bin shifts per slice)
+constexpr int FE_MAX_LAUNCHES = 40;  // search launches of one level: the slice train, the minimum pass, and once more after a re-run
 constexpr int FE_MAX_BUCKETS = 64;   // buckets of one search launch: classifier classes (7) or brightness bins (<= 64)
 constexpr int FE_MAX_GROUPS = 8;     // groups of buckets searched by separate launches of a slice: classifier classes when bins are on
 constexpr int FE_MAX_TOTAL = FE_MAX_GROUPS * FE_MAX_BUCKETS;
@@ -89,9 +88,6 @@ struct fe_ctx {
     DevBuf b_dom, b_rng, b_dom_cls, b_rng_cls, b_dom_order, b_rng_order, b_sort_tmp, b_keys_tmp, b_vals_tmp;
     DevBuf b_A, b_Blo, b_Bhi, b_rowc, b_coln, b_rowbest, b_rowhit, b_hist, b_level_items, b_split, b_scan, b_scan_tmp;
     DevBuf b_rng_next, b_counters, b_bound, b_flag_idx;
-    // multi-pass search: range positions still without a candidate under the threshold (two generations), their item
-    // indices, survivor flags, select scratch
-    DevBuf b_act[2], b_act_items, b_act_flags, b_act_tmp;
     // classifier classes x brightness bins: the composite orders (the class-only orders stay in b_dom_order / b_rng_order)
     DevBuf b_dom_order2, b_rng_order2;
     // tcgen05 path operands
@@ -133,5 +129,4 @@ int fe_fail(fe_ctx* ctx, int code, const char* fmt, ...);
 
 // ---- kernels' host launchers (each returns a cudaError_t from cudaGetLastError) ----
 cudaError_t launch_search_exact(fe_ctx* ctx, const SearchArgs& a, bool rerank = false);
-// tcgen05 path (fe_search_umma.cu). Returns FE_OK / FE_ERR_*.
-int umma_level_supported(const LevelGeom& g);
+

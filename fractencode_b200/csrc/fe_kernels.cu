@@ -147,45 +147,6 @@ __global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-// Multi-pass search: flags[i] = 1 when the range at position i (result slot slots[i]) is still open: none of its four rotation
-// rows has a candidate under the threshold at a domain index below `cutoff` (every admissible domain below the cutoff has
-// been scored, so a recorded hit below it is the first in scan order; 0xFFFFFFFF = "any hit closes the range").
-// cnt[b] += survivors of bucket b (roff = prefix offsets of the pass's positions).
-__global__ void k_unresolved(const uint32_t* __restrict__ slots, const uint32_t* __restrict__ rowhit, uint32_t n, TotalOff roff, int nb,
-                             uint32_t cutoff, uint8_t* __restrict__ flags, uint32_t* __restrict__ cnt) {
-    __shared__ uint32_t sc[FE_MAX_TOTAL];
-    for (uint32_t i = threadIdx.x; i < (uint32_t)nb; i += blockDim.x) sc[i] = 0;
-    __syncthreads();
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const uint32_t s = slots ? slots[i] : i;
-        const uint4 h = reinterpret_cast<const uint4*>(rowhit)[s];
-        const bool alive = min(min(h.x, h.y), min(h.z, h.w)) >= cutoff;
-        flags[i] = alive ? 1 : 0;
-        if (alive) {
-            int lo = 0, hi = nb - 1;                       // bucket b with roff[b] <= i < roff[b + 1]
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (roff.v[mid] <= i) lo = mid; else hi = mid - 1;
-            }
-            atomicAdd(&sc[lo], 1u);
-        }
-    }
-    __syncthreads();
-    for (uint32_t b = threadIdx.x; b < (uint32_t)nb; b += blockDim.x)
-        if (sc[b]) atomicAdd(&cnt[b], sc[b]);
-}
-
-// Classifier classes x brightness bins: key = (class + 1) * nbins + bin, hist[key] counts.
-__global__ void k_composite_keys(const int32_t* __restrict__ cls, const uint8_t* __restrict__ bins, uint32_t n, uint32_t nbins,
-                                 uint16_t* __restrict__ keys, uint32_t* __restrict__ hist) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t k = (uint32_t)(cls[i] + 1) * nbins + bins[i];
-    keys[i] = (uint16_t)k;
-    atomicAdd(&hist[k], 1u);
-}
-
 // Brightness bin of every block of a uniform list: key = (mul * sum of the block's edge x edge pixels) / width.  For a range
 // block mul = 4 (sum of 4 r); for a domain block mul = 1 and edge = S (the sum of its 2x2 box sums D is the sum of its pixels).
 // hist[key] counts.  WARP = true: one warp per block (large blocks); false: one thread per block (edge <= 16; neighbouring
@@ -247,11 +208,6 @@ __global__ void k_bin_prefix(const uint32_t* __restrict__ dom_order, const uint3
         if ((dom_order ? dom_order[mid] : mid) < c) lo = mid + 1; else hi = mid;   // NULL order: one bucket, position = index
     }
     out[t] = lo - beg;
-}
-
-__global__ void k_gather_u32(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ table, uint32_t n, uint32_t* __restrict__ out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = table ? table[idx[i]] : idx[i];
 }
 
 __global__ void k_iota(uint32_t* p, uint32_t n) {

@@ -35,14 +35,9 @@ __global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n);
 __global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n);
 __global__ void k_iota(uint32_t* p, uint32_t n);
 struct BucketOff { uint32_t v[FE_MAX_BUCKETS + 1]; };
-struct TotalOff { uint32_t v[FE_MAX_TOTAL + 1]; };   // all buckets of all groups of a level
-__global__ void k_unresolved(const uint32_t* slots, const uint32_t* rowhit, uint32_t n, TotalOff roff, int nb, uint32_t cutoff, uint8_t* flags,
-                             uint32_t* cnt);
 void launch_brightness_bins(cudaStream_t stream, const uint8_t* img, uint32_t stride, const fe_grid_item* items, uint32_t n, uint32_t edge,
                             uint32_t mul, uint32_t width, uint8_t* keys, uint32_t* hist);
 __global__ void k_bin_prefix(const uint32_t* dom_order, const uint32_t* hist, int nb, BucketOff cut, uint32_t* out);
-__global__ void k_composite_keys(const int32_t* cls, const uint8_t* bins, uint32_t n, uint32_t nbins, uint16_t* keys, uint32_t* hist);
-__global__ void k_gather_u32(const uint32_t* idx, const uint32_t* table, uint32_t n, uint32_t* out);
 __global__ void k_class_keys(const int32_t* cls, uint32_t n, uint8_t* keys, uint32_t* hist);
 __global__ void k_build_rows(const uint8_t* img, uint32_t stride, const fe_grid_item* rng, const uint32_t* order, uint32_t n,
                              uint32_t T, uint32_t Npad, int fast, uint8_t* A, uint32_t* rowc);

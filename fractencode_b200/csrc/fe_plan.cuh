@@ -12,7 +12,7 @@
 // bucket meets (bins c-span .. c+span of its class) are adjacent inside an interval, so a work item is one row tile of
 // 32 range blocks x one contiguous run of column tiles.
 #pragma once
-#include "fe_internal.cuh"
+#include "fe_umma.cuh"
 
 constexpr int FE_NK = 8;                  // base intervals of the scan
 
@@ -141,6 +141,7 @@ struct F16Args {
     uint32_t thr16, use_thr;
     uint32_t ordinal;                     // slice ordinal this launch belongs to
 };
+int f16_level_supported(const LevelGeom& g);   // fast geometry (S = 2T, even domain origins), T = 4 or 8
 int f16_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const uint32_t* dom_order, const LevelPlan* plan, uint32_t max_tiles);
 int f16_launch_search(fe_ctx* ctx, const LevelGeom& g, const F16Args& a, bool retire, bool meta, cudaEvent_t ev0, cudaEvent_t ev1);
 
@@ -160,6 +161,7 @@ struct I8Args {
     uint32_t Kpad, stages, n_abuf;
     uint32_t ordinal;
 };
+int i8_level_supported(const LevelGeom& g);    // fast geometry, 4 <= T <= 32
 int i8_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const uint32_t* dom_order, const LevelPlan* plan, uint32_t nD,
                   uint32_t max_tiles);
 int i8_build_rows(fe_ctx* ctx, const LevelGeom& g, const LevelPlan* plan, const SliceCtl* ctl, const ListEntry* const list[2], uint32_t ordinal,

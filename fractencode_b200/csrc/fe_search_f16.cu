@@ -485,6 +485,8 @@ __global__ void __launch_bounds__(128) k_build_pool16_level(const uint8_t* __res
 
 } // namespace
 
+int f16_level_supported(const LevelGeom& g) { return g.fast && (g.T == 4 || g.T == 8); }
+
 int f16_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const uint32_t* dom_order, const LevelPlan* plan, uint32_t max_tiles) {
     const uint32_t Kpad = (g.N + 3 + 15u) & ~15u;
     FE_CUDA(ctx, ctx->b_B16.ensure((size_t)max_tiles * UM_NT * Kpad * 2 + 256));

@@ -452,7 +452,35 @@ __global__ void k_build_pool_i8_level(const uint8_t* __restrict__ img, uint32_t 
 
 } // namespace
 
+// Per-block second moments, one warp per block (sorted position p -> item order[p]).
+// mode 0: range, sum (4 r - 510)^2   mode 1: range, 16 sum r^2   mode 2: domain, sum (D - 510)^2   mode 3: domain, sum D^2
+__global__ void k_block_norms(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ items,
+                              const uint32_t* __restrict__ order, uint32_t n, uint32_t T, int mode, uint32_t* __restrict__ out) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n) return;
+    const fe_grid_item it = items[order ? order[p] : p];
+    const uint8_t* base = img + (size_t)it.y * stride + it.x;
+    const uint32_t N = T * T;
+    uint32_t s2 = 0;
+    for (uint32_t e = lane; e < N; e += 32) {
+        int v;
+        if (mode < 2) {
+            const int r = base[(size_t)(e / T) * stride + (e % T)];
+            v = mode == 0 ? 4 * r - 510 : 4 * r;              // (4r)^2 = 16 r^2
+        } else {
+            const uint8_t* q = base + (size_t)(2 * (e / T)) * stride + 2 * (e % T);
+            const int D = (int)q[0] + (int)q[1] + (int)q[stride] + (int)q[stride + 1];
+            v = mode == 2 ? D - 510 : D;
+        }
+        s2 += (uint32_t)(v * v);
+    }
+    for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+    if (lane == 0) out[p] = s2;
+}
+
 uint32_t i8_kpad(const LevelGeom& g) { return g.N <= (uint32_t)I8_KC ? ((g.N + 31u) & ~31u) : ((g.N + I8_KC - 1) / I8_KC) * I8_KC; }
+
+int i8_level_supported(const LevelGeom& g) { return g.fast && g.T >= 4 && g.T <= 32; }
 
 int i8_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const uint32_t* dom_order, const LevelPlan* plan, uint32_t nD,
                   uint32_t max_tiles) {

@@ -132,37 +132,6 @@ __device__ __forceinline__ void load_px(const uint8_t* __restrict__ p, uint32_t 
     }
 }
 
-struct WorkItem {
-    uint32_t a_blob;   // row-tile index (A blob)
-    uint32_t row0;     // first global row of the tile
-    uint32_t nrows;    // valid rows in the tile (<= 128)
-    uint32_t t0, t1;   // column-tile range [t0, t1) of the B blob (may run over several adjacent domain buckets)
-    uint32_t cols_left;// span 0 only: valid columns from tile t0 to the end of the bucket's slice
-};
-
-__device__ __forceinline__ WorkItem decode_item(const UmmaArgs& a, uint32_t w) {
-    WorkItem it{};
-    int bi = 0;
-    while (bi + 1 < a.nb && w >= a.item_end[bi]) ++bi;       // running totals: two instructions per bucket passed
-    if (bi) w -= a.item_end[bi - 1];
-    const UmmaBucket& b = a.b[bi];
-    uint32_t rt = w, lt0 = 0, lt1 = b.n_col_tiles;
-    if (b.chunks != 1) {                                      // column chunking (few row tiles): divisions only here
-        rt = w / b.chunks;
-        const uint32_t q = w - rt * b.chunks;
-        lt0 = (uint32_t)(((uint64_t)q * b.n_col_tiles) / b.chunks);
-        lt1 = (uint32_t)(((uint64_t)(q + 1) * b.n_col_tiles) / b.chunks);
-    }
-    it.a_blob = b.row_tile0 + rt;
-    it.row0 = b.row0 + rt * UM_ROWS;
-    it.nrows = min((uint32_t)UM_ROWS, b.nrows - rt * UM_ROWS);
-    it.t0 = b.col_tile0 + lt0;
-    it.t1 = b.col_tile0 + lt1;
-    it.cols_left = b.ncols - lt0 * a.nt;
-    return it;
-}
-
-
 } // namespace umma_dev
 
 // Per-block second moments for the operand builders, one warp per block (sorted position p -> item order[p]).
