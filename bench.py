@@ -7,7 +7,7 @@ A "step" is one pass of the hot path over one synthetic image per GPU: the whole
 (BASELINE config 3: 4096x4096 "natural" image, quadtree 32->4, full search) -- operand preparation,
 the (range, domain x rotation) search on every level, winner finalisation with the least-squares
 (s, o), and the split/compaction between levels.  `value` times it with the image already in HBM and
-the transform list left in HBM (+ the NCCL gather of the per-rank lists for N > 1); `e2e` times the
+the transform list left in HBM (+ the NCCL gather of the per-rank lists, as packed 8-byte records, to rank 0 for N > 1); `e2e` times the
 reference-facing C-ABI call with HOST buffers (pinned image in, transform list out).
 
 matches = sum over levels of (range blocks searched) x (domains) x 4 rotations: the FULL candidate
@@ -30,8 +30,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram bytes (read + write) of all search launches of a level of the default workload, from ncu (None: not captured yet)
-TRAFFIC_BY_T = {32: 178.5e6, 16: 177.8e6, 8: 735.0e6, 4: 166.9e6}   # profiles/search_kernels_r1b.md
+
+def measured_traffic(a, T):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the level's search launches from the committed ncu --set full capture of
+    exactly this workload (profiles/traffic_r2.json, written by tools/traffic_from_ncu.py); (None, reason) when there is none."""
+    path = os.path.join(ROOT, "profiles", "traffic_r2.json")
+    key = "%d/%d/%d/%g/%d" % (a.size, a.tmax, a.tmin, a.thr, a.classifier)
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d[key]["dram_bytes_by_T"][str(T)]), d[key].get("source", "profiles/traffic_r2.json")
+    except Exception:
+        return None, "no ncu capture committed for this workload"
+
 
 METRIC = "range_block_matches_per_s"
 UNIT = "matches/s"
@@ -51,6 +62,7 @@ def parse():
     ap.add_argument("--search", type=int, default=0, help="0 auto, 1 exact integer path, 2 tcgen05 path")
     ap.add_argument("--cpu-blocks", type=int, default=0, help="range blocks per level in the CPU sample (0: 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-measurement (config 4)")
     ap.add_argument("--shard", default="images", choices=["images", "ranges"],
                     help="N > 1: one image per GPU (weak scaling, default) or the range blocks of ONE image sharded over the GPUs "
                          "(strong scaling, BASELINE config 4 in shape; the domain pool is rebuilt on every GPU)")
@@ -83,17 +95,22 @@ def peaks():
 # the sampled blocks that split are the sample of the next level; per-level cost and split fraction are
 # scaled to the whole image.  Cost per block is independent of the other blocks.
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(a, img, blocks_per_level=0):
+def cpu_sample(a, img, blocks_per_level=0, offset=0):
+    """One bounded sample of the reference's CPU path: `m` range blocks per quadtree level (every (n/m)-th block of the level,
+    shifted by `offset` so that successive samples take different blocks) against the FULL domain grid."""
     from oracle import pyoracle as po
-    lib, kind = po.reference(fma=False), "reference"
+    # the reference as its own CMake builds it: -mavx2 + FMA, -DFRAC_WITH_AVX=1 (oracle/Makefile: -march=x86-64-v3, portable to
+    # the GPU box's host); all host threads (OpenMP over range blocks, TransformEstimator2::estimate per block)
+    lib, kind = po.reference(fma=True), "reference"
     if lib is None:
         lib, kind = po.restatement(), "port"
     cores = lib.hardware_threads()
-    m = blocks_per_level or 2 * cores
+    m = blocks_per_level or 4 * cores
     W = H = a.size
-    p = lib.params(a.thr, -1.0, bool(a.classifier), False)
+    p = lib.params(a.thr, -1.0, bool(a.classifier), True)
     top = lib.uniform_grid(W, H, a.tmax, a.tmax)
-    sample = top[:: max(1, len(top) // m)][:m]
+    stride = max(1, len(top) // m)
+    sample = top[offset % stride:: stride][:m]
     pending_est = float(len(top))
     tot_time = tot_matches = 0.0
     per_level = []
@@ -129,7 +146,11 @@ def cpu_sample(a, img, blocks_per_level=0):
     value = tot_matches / tot_time if tot_time > 0 else 0.0
     return {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": "%d range blocks per quadtree level vs the full domain grid, children of split sampled blocks feed the next level; "
-                      "scaled per level by (estimated pending blocks)/(sampled blocks); %.1f s of CPU wall on %d threads" % (m, cpu_work, cores),
+                      "scaled per level by (estimated pending blocks)/(sampled blocks); %.1f s of CPU wall on %d threads (nproc %d); "
+                      "build: g++ -O2 -march=x86-64-v3 -DFRAC_WITH_AVX=1 (AVX2+FMA, the reference's CMake flags), OpenMP over range blocks "
+                      "around TransformEstimator2::estimate (EncodingEngineCore2's own thread pool deadlocks, SURVEY S9)" % (
+                          m, cpu_work, cores, os.cpu_count() or cores),
+            "cpu_work_s": cpu_work, "tot_matches": tot_matches,
             "est_image_seconds": tot_time, "est_mpix_per_s": W * H / 1e6 / tot_time if tot_time > 0 else 0.0, "levels": per_level}
 
 
@@ -143,19 +164,29 @@ def run_reference(a):
     img = fo.synth_image(a.size, a.size, 1234, 0)
     res = []
     for step in range(a.warmup + a.steps):
-        r = cpu_sample(a, img, a.cpu_blocks)
+        # every step samples DIFFERENT range blocks: the K timed steps together are one sample of K x m blocks per level
+        r = cpu_sample(a, img, a.cpu_blocks, offset=step)
         if step >= a.warmup:
             res.append(r)
-    vals = [r["value"] for r in res]
-    v = float(np.mean(vals))
+    # aggregate: whole-image time = mean of the per-step estimates; matches/s = nominal candidates / that time
+    est_s = float(np.mean([r["est_image_seconds"] for r in res]))
+    matches = float(np.mean([r["tot_matches"] for r in res]))
+    v = matches / est_s if est_s > 0 else 0.0
     last = res[-1]
-    ms = float(np.mean([r["est_image_seconds"] for r in res])) * 1e3
+    work = float(sum(r["cpu_work_s"] for r in res))
+    per_level_work = {}
+    for r in res:
+        for l in r["levels"]:
+            per_level_work[l["T"]] = per_level_work.get(l["T"], 0.0) + l["sec"]
+    sample = ("%d timed steps x (%s); each step takes different blocks: %.1f s of CPU wall in total, per level %s" % (
+        len(res), last["sample"], work, ", ".join("T=%d %.1f s" % (t, w) for t, w in sorted(per_level_work.items(), reverse=True))))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32 (CPU scalar+SSE)",
-            "data": "synthetic", "config": {"workload": workload_name(a), "note": "whole-image time extrapolated from a bounded sample; ms_per_step is that estimate"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "ms_per_step": est_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32 (CPU AVX2)",
+            "data": "synthetic", "config": {"workload": workload_name(a), "note": "whole-image time extrapolated from a bounded sample (cost per range "
+                                            "block is independent of the other blocks); ms_per_step is that estimate; value = nominal candidates / it"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "mpix_per_s": last["est_mpix_per_s"], "levels": last["levels"], "gpu_launches": 0}
+            "mpix_per_s": a.size * a.size / 1e6 / est_s if est_s > 0 else 0.0, "levels": last["levels"], "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -198,11 +229,51 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-class DevArray:
-    """__cuda_array_interface__ view of a raw device pointer (the library's result list)."""
+def strong_config4(a, ctx, fb, rank, world, sync_all, size=8192, steps=3):
+    """BASELINE config 4 in the same run: ONE 8192 x 8192 image with Classifier2, its top-level range blocks sharded over the N
+    GPUs (domain pool rebuilt on every GPU, per-rank lists gathered to rank 0), against the same image encoded by rank 0 alone."""
+    import torch
+    import torch.distributed as dist
+    from fractencode_b200.dist import PackedGather, shard_slice
+    params = fb.Params(a.thr, -1.0, True, False, a.search)
+    ctx.set_synthetic_image(size, size, 4321, 0)
+    n_top = (size // a.tmax) ** 2
+    mine = shard_slice(n_top, rank, world)
+    stream = torch.cuda.current_stream()
+    per_top = (a.tmax // a.tmin) ** 2
+    pg = PackedGather(-(-n_top // world) * per_top, torch.device("cuda"))      # the largest shard's worst case, equal on every rank
 
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+    def run(fn, n):
+        ts = []
+        for _ in range(n):
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return ts
+
+    def sharded():
+        n = ctx.encode_quadtree_slice_device(a.tmax, a.tmin, params, mine.start, mine.stop - mine.start)
+        return pg.gather(ctx, n, a.tmax, shared_image=True)
+
+    def whole():
+        if rank == 0:
+            ctx.encode_quadtree_device(a.tmax, a.tmin, params)
+
+    run(sharded, 1)
+    t_n = run(sharded, steps)
+    run(whole, 1)
+    t_1 = run(whole, steps)
+    v = torch.tensor([float(np.mean(t_n)), float(np.mean(t_1))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    tn, t1 = v[0].item(), v[1].item()
+    return {"workload": "natural %dx%d u8 seed 4321, quadtree %d->%d, Classifier2, rms_threshold %g (BASELINE config 4)" % (size, size, a.tmax, a.tmin, a.thr),
+            "scaling": "strong", "n_gpus": world, "sharding": "top-level range blocks over the GPUs (fe_encode_quadtree_slice_device), packed 8-byte records "
+            "gathered to rank 0", "ms_per_image_n_gpus": tn, "ms_per_image_1_gpu": t1, "speedup": t1 / tn if tn > 0 else None,
+            "mpix_per_s": size * size / 1e6 / (tn * 1e-3), "steps": steps}
 
 
 def run_b200(a):
@@ -210,7 +281,7 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
     import fractencode_b200 as fb
-    from fractencode_b200.dist import gather_item_lists, shard_slice
+    from fractencode_b200.dist import PackedGather, shard_slice
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -230,30 +301,22 @@ def run_b200(a):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     host_img = torch.empty((H, W), dtype=torch.uint8).pin_memory()
     host_items = torch.empty(cap * 64, dtype=torch.uint8).pin_memory()
-    counts_t = torch.zeros(world, dtype=torch.int64, device="cuda")
-    gather_buf = torch.empty(world * cap * 64, dtype=torch.uint8, device="cuda") if world > 1 else None
 
     by_ranges = a.shard == "ranges" and world > 1
     ctx.set_synthetic_image(W, H, 1234 + (0 if by_ranges else rank), 0)
     host_img.copy_(torch.from_numpy(ctx.get_image()))
     n_top = (W // a.tmax) * (H // a.tmax)
     mine = shard_slice(n_top, rank, world)          # this rank's top-level range blocks when sharding by ranges
-    my_items = torch.empty(cap * 64, dtype=torch.uint8, device="cuda") if by_ranges else None
+    per_top = (a.tmax // a.tmin) ** 2
+    pg = PackedGather(-(-n_top // world) * per_top if by_ranges else cap, torch.device("cuda")) if world > 1 else None
 
     def step_resident():
         if by_ranges:
             n = ctx.encode_quadtree_slice_device(a.tmax, a.tmin, params, mine.start, mine.stop - mine.start)
         else:
             n = ctx.encode_quadtree_device(a.tmax, a.tmin, params)
-        if world > 1:  # gather the per-rank transform lists (the only collective of the path)
-            nptr = C.c_size_t(0)
-            ptr = lib.fe_device_items(ctx.h, C.byref(nptr))
-            if by_ranges:   # the shard's list lives in a buffer sized for the shard: stage it in a full-capacity one
-                my_items[: n * 64].copy_(torch.as_tensor(DevArray(ptr, max(n, 1) * 64), device="cuda")[: n * 64])
-                items = my_items
-            else:
-                items = torch.as_tensor(DevArray(ptr, cap * 64), device="cuda")
-            gather_item_lists(items, n, cap, counts_t, gather_buf)
+        if world > 1:  # gather the per-rank transform lists on rank 0 (the only collective of the path): packed 8-byte records
+            pg.gather(ctx, n, a.tmax, shared_image=by_ranges)
         return n
 
     def step_e2e():
@@ -360,28 +423,39 @@ def run_b200(a):
         tot_ms, e_ms, all_matches, all_items = tmax[0].item(), tmax[1].item(), tsum[2].item(), tsum[3].item()
     else:
         tot_ms, e_ms, all_matches, all_items = my[0].item(), my[1].item(), my[2].item(), my[3].item()
+    strong = strong_config4(a, ctx, fb, rank, world, sync_all) if (world > 1 and not by_ranges and not a.no_strong) else None
     if rank == 0:
         pk = peaks()
         ms_per_step = tot_ms / a.steps
         value = all_matches / (ms_per_step * 1e-3)
         e_value = all_matches / (e_ms / a.steps * 1e-3)
         ach = flops / (search_ms * 1e-3) / 1e12 if search_ms > 0 else 0.0
-        # dominant kernel = the search launch with the largest share of the step
+        # dominant kernel = the search kernel of the level with the largest share of the step
         dom = max(levels, key=lambda l: l["search_ms"])
         dom_ach = 2.0 * dom["T"] ** 2 * dom["evaluated"] / (dom["search_ms"] * 1e-3) / 1e12 if dom["search_ms"] > 0 else 0.0
-        # dram__bytes_read.sum + dram__bytes_write.sum summed over the level's search launches, ncu --set full of this workload
-        # (profiles/search_kernels_r1.md)
-        traffic_by_T = TRAFFIC_BY_T if (a.size, a.tmax, a.tmin, a.thr, a.classifier) == (4096, 32, 4, 25.0, 0) else {}
+        # Peak: MEASURED_PEAKS.json holds a burst figure (best of 10 single GEMMs) and a sustained one (back to back for 4 s).
+        # A timed region of a fraction of a second at maximum clock is burst conditions; both fractions are printed.
+        burst = wall < 2.0
+        peak = pk["tflops_burst"] if burst else pk["tflops_sustained"]
+        for l in levels:
+            if l["tflops"]:
+                l["frac_burst"] = round(l["tflops"] / pk["tflops_burst"], 3)
+        traffic, traffic_src = measured_traffic(a, dom["T"])
+        kname = "k_search_f16<%d>" % dom["T"] if dom["T"] <= 8 else "k_search_i8"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if by_ranges else "weak", "vs_baseline": None,
-            "dtype": "u8 in, fp16 operands / fp32 (integer-exact) accumulate, int32 scores, f64 s/o",
+            "dtype": "u8 in; T<=8: fp16 operands, fp32 (integer-exact) accumulate; T>=16: u8 x u8 -> s32; int32 scores, f64 s/o",
             "data": "synthetic",
             "config": {"workload": workload_name(a), "images_per_step": 1 if by_ranges else world,
                        "sharding": "top-level range blocks of one image over the GPUs, pool rebuilt per GPU" if by_ranges else "one image per GPU",
                        "l2": "flushed between timed steps (512 MiB fill)",
-                       "search_impl": ["auto", "exact-int (dp4a)", "tcgen05"][a.search], "pruning": PRUNING_NOTE},
+                       "search_impl": ["auto", "exact-int (dp4a)", "tcgen05"][a.search], "pruning": PRUNING_NOTE,
+                       "value_counts": "NOMINAL candidates (SURVEY 8d: the full candidate count of the workload, what the reference scores without "
+                                       "its break) per second -- a time ratio, not device work; evaluated_matches_per_s and mpix_per_s are the "
+                                       "device-work and end-user figures"},
             "mpix_per_s": (1 if by_ranges else world) * W * H / 1e6 / (ms_per_step * 1e-3),
+            "evaluated_matches_per_s": evaluated_step * (1 if by_ranges else world) / (ms_per_step * 1e-3),
             "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": W * H, "d2h_bytes_per_step": int(e_items) * 64,
                     "ms_per_step": e_ms / a.steps, "mpix_per_s": (1 if by_ranges else world) * W * H / 1e6 / (e_ms / a.steps * 1e-3)},
             "gpu_launches": launches,
@@ -389,19 +463,24 @@ def run_b200(a):
             "evaluated_matches_per_step": evaluated_step,
             "levels": levels,
             "umma_levels": int(st.umma_levels), "exact_levels": int(st.exact_levels),
-            "roofline": {"bound": "tensor", "achieved": dom_ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": dom_ach / pk["tflops_sustained"], "traffic": traffic_by_T.get(dom["T"]),
+            "roofline": {"bound": "tensor", "achieved": dom_ach, "peak": peak, "unit": "TFLOP/s", "frac": dom_ach / peak,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_kind": "burst" if burst else "sustained",
+                         "frac_burst": dom_ach / pk["tflops_burst"], "frac_sustained": dom_ach / pk["tflops_sustained"],
                          "kernel": "%s, level T=%d: 2*T^2 FLOP x %d candidates scored by the level's %d search launches / their summed CUDA-event "
-                                   "durations (ctx stream); peak = sustained bf16 (kernel timed inside a long step), %s" % (
-                             "k_search_umma<f16>" if dom["T"] <= 8 else "k_search_umma_i8", dom["T"], dom["evaluated"], dom["passes"], pk["source"]),
-                         "all_levels": {"achieved": ach, "frac": ach / pk["tflops_sustained"]},
-                         "steady_state": dict(steady, frac=steady["achieved"] / pk["tflops_sustained"]) if steady else None,
-                         "peak_burst": pk["tflops_burst"]},
+                                   "durations (ctx stream); peak = %s bf16 dense (timed region %.2f s), %s" % (
+                             kname, dom["T"], dom["evaluated"], dom["passes"], "burst" if burst else "sustained", wall, pk["source"]),
+                         "all_levels": {"achieved": ach, "frac_burst": ach / pk["tflops_burst"], "frac_sustained": ach / pk["tflops_sustained"]},
+                         "steady_state": dict(steady, frac_burst=steady["achieved"] / pk["tflops_burst"],
+                                              frac_sustained=steady["achieved"] / pk["tflops_sustained"]) if steady else None,
+                         "peak_burst": pk["tflops_burst"], "peak_sustained": pk["tflops_sustained"]},
             "hbm_kernels": {"peak_gbs": pk["hbm_gbs"], "decode": decode_info,
                             "prep_ms_per_level": {str(l["T"]): l["prep_ms"] for l in levels}},
             "clocks": sampler.summary(),
             "wall_s_timed_region": wall,
         }
+        if strong:
+            line["strong"] = strong
         if world == 1 and not a.no_cpu_baseline:
             from oracle import pyoracle as po
             po.build(ref=os.path.isdir("/root/reference/encode"))

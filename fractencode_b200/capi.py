@@ -76,7 +76,7 @@ _LIB = None
 EXPORTS = [
     "fe_abi_version", "fe_create", "fe_destroy", "fe_last_error", "fe_set_image", "fe_set_images", "fe_set_image_device",
     "fe_classify", "fe_encode_level", "fe_encode_quadtree", "fe_encode_quadtree_device", "fe_encode_quadtree_slice_device", "fe_fetch_items", "fe_device_items",
-    "fe_decode", "fe_copy_items", "fe_quantize", "fe_pack_items", "fe_unpack_items", "fe_get_stats", "fe_stats_reset", "fe_synchronize", "fe_set_synthetic_image", "fe_get_image", "fe_plan_threshold",
+    "fe_decode", "fe_copy_items", "fe_quantize", "fe_pack_items", "fe_unpack_items", "fe_items_minmax_device", "fe_pack_items_device", "fe_pack_errors", "fe_get_stats", "fe_stats_reset", "fe_synchronize", "fe_set_synthetic_image", "fe_get_image", "fe_plan_threshold",
 ]
 
 
@@ -111,6 +111,9 @@ def load_library():
         "fe_quantize": (i32, [vp, vp, sz, i32, i32, vp, vp, vp]),
         "fe_pack_items": (i32, [vp, vp, sz, u32, i32, i32, vp, vp]),
         "fe_unpack_items": (i32, [vp, vp, sz, u32, i32, i32, vp, i32, vp]),
+        "fe_items_minmax_device": (i32, [vp, vp]),
+        "fe_pack_items_device": (i32, [vp, u32, i32, i32, vp, vp, sz, C.POINTER(sz)]),
+        "fe_pack_errors": (i32, [vp, C.POINTER(u32)]),
         "fe_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "fe_stats_reset": (i32, [vp]),
         "fe_synchronize": (i32, [vp]),
@@ -286,6 +289,20 @@ class Context:
         out = np.zeros(len(packed), ENCODE_ITEM)
         self._check(self.lib.fe_unpack_items(self.h, packed.ctypes.data, len(packed), t_max, bits_s, bits_o, mm.ctypes.data, int(fma), out.ctypes.data))
         return out
+
+    # ---- device-resident post-pass (no synchronisation): minmax and packed records of the last quadtree result ----
+    def items_minmax_device(self, minmax_dev_ptr: int):
+        self._check(self.lib.fe_items_minmax_device(self.h, minmax_dev_ptr))
+
+    def pack_items_device(self, t_max: int, minmax_dev_ptr: int, packed_dev_ptr: int, cap: int, bits_s: int = 5, bits_o: int = 7) -> int:
+        n = C.c_size_t(0)
+        self._check(self.lib.fe_pack_items_device(self.h, t_max, bits_s, bits_o, minmax_dev_ptr, packed_dev_ptr, cap, C.byref(n)))
+        return n.value
+
+    def pack_errors(self) -> int:
+        n = C.c_uint32(0)
+        self._check(self.lib.fe_pack_errors(self.h, C.byref(n)))
+        return n.value
 
     # ---- misc ----
     def stats(self) -> Stats:

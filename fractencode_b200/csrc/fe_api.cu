@@ -35,6 +35,10 @@ int fe_fail(fe_ctx* ctx, int code, const char* fmt, ...) {
     } while (0)
 
 static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+// block [x, x + w) x [y, y + h) inside a W x H plane, without 32-bit wrap-around (the C ABI is a trust boundary)
+static inline bool inside(uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint32_t W, uint32_t H) {
+    return (uint64_t)x + w <= W && (uint64_t)y + h <= H;
+}
 
 // Largest n16 (16 * SSE) whose reference distance double(float(n16/16)) / (S*S) is <= thr, looked
 // for in the exact regime n16 < 2^24 (SURVEY hard part 4).  Returns false when no n16 qualifies.
@@ -234,7 +238,7 @@ extern "C" int fe_classify(fe_ctx* ctx, int which, const fe_grid_item* items, si
     if (!pl.px) return fe_fail(ctx, FE_ERR_STATE, "fe_classify: no image set");
     if (n == 0) return FE_OK;
     for (size_t i = 0; i < n; ++i)
-        if (items[i].w < 2 || items[i].h < 2 || items[i].x + items[i].w > pl.w || items[i].y + items[i].h > pl.h)
+        if (items[i].w < 2 || items[i].h < 2 || !inside(items[i].x, items[i].y, items[i].w, items[i].h, pl.w, pl.h))
             return fe_fail(ctx, FE_ERR_INVALID, "fe_classify: item %zu outside the image or smaller than 2x2", i);
     FE_CUDA(ctx, cudaSetDevice(ctx->device));
     FE_CUDA(ctx, ctx->b_dom.ensure(n * sizeof(fe_grid_item)));
@@ -694,7 +698,10 @@ extern "C" int fe_encode_level(fe_ctx* ctx, const fe_grid_item* domains, size_t 
     for (size_t i = 0; i < n_rng; ++i) {
         const fe_grid_item& r = ranges[i];
         if (r.w != T || r.h != T) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_encode_level: range %zu is %ux%u, expected square %u", i, r.w, r.h, T);
-        if (r.x + T > ctx->tgt.w || r.y + T > ctx->tgt.h) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_level: range %zu outside the target image", i);
+        if (!inside(r.x, r.y, T, T, ctx->tgt.w, ctx->tgt.h)) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_level: range %zu outside the target image", i);
+        if (params->use_classifier && (r.bin < -1 || r.bin > 5))
+            return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_level: range %zu has classifier bin %d; bins are -1 (not classified) or the classes 0..5 of "
+                                                "BrightnessBlocksClassifier2::getCategory", i, r.bin);
     }
     FE_CUDA(ctx, cudaSetDevice(ctx->device));
     FE_CUDA(ctx, ctx->b_level_items.ensure(n_rng * sizeof(fe_encode_item)));
@@ -709,7 +716,10 @@ extern "C" int fe_encode_level(fe_ctx* ctx, const fe_grid_item* domains, size_t 
         for (size_t i = 0; i < n_dom; ++i) {
             const fe_grid_item& d = domains[i];
             if (d.w != S || d.h != S) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_encode_level: domain %zu is %ux%u, expected square %u", i, d.w, d.h, S);
-            if (d.x + S > ctx->src.w || d.y + S > ctx->src.h) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_level: domain %zu outside the source image", i);
+            if (!inside(d.x, d.y, S, S, ctx->src.w, ctx->src.h)) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_level: domain %zu outside the source image", i);
+            if (params->use_classifier && (d.bin < -1 || d.bin > 5))
+                return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_level: domain %zu has classifier bin %d; bins are -1 (not classified) or the classes 0..5 of "
+                                                    "BrightnessBlocksClassifier2::getCategory", i, d.bin);
             even = even && !(d.x & 1) && !(d.y & 1);
         }
         FE_TRY(make_geom(ctx, S, T, even, &io.g));
@@ -863,8 +873,8 @@ extern "C" int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uin
     std::vector<uint32_t> sizes;   // distinct fast sizes
     for (size_t i = 0; i < n; ++i) {
         const fe_encode_item& e = items[i];
-        if (!e.w || !e.h || e.x + e.w > width || e.y + e.h > height) return fe_fail(ctx, FE_ERR_INVALID, "fe_decode: item %zu outside the image", i);
-        if (e.src_w && (e.src_w != e.src_h || e.match_x + e.src_w > width || e.match_y + e.src_h > height || e.transform < 0 || e.transform > 7 || e.src_w < 2))
+        if (!e.w || !e.h || !inside(e.x, e.y, e.w, e.h, width, height)) return fe_fail(ctx, FE_ERR_INVALID, "fe_decode: item %zu outside the image", i);
+        if (e.src_w && (e.src_w != e.src_h || !inside(e.match_x, e.match_y, e.src_w, e.src_h, width, height) || e.transform < 0 || e.transform > 7 || e.src_w < 2))
             return fe_fail(ctx, FE_ERR_INVALID, "fe_decode: item %zu has an invalid source block", i);
         area += (uint64_t)e.w * e.h;
         if (!e.src_w || !e.src_h) has_default = true;
@@ -898,68 +908,99 @@ extern "C" int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uin
     }
     pix_off.push_back((uint32_t)slow_area);
     const size_t n_slow = n - n_fast;
-    const bool covered = !has_default && area == (uint64_t)width * height; // non-overlapping full cover -> ping-pong needs no copy
-    const bool fused_sq = covered && n_slow == 0;                          // convergence sum inside the gather kernel
     const int iters = max_iters < 0 ? 300 : max_iters;
     const size_t bytes = (size_t)height * stride;
     FE_CUDA(ctx, cudaSetDevice(ctx->device));
     FE_CUDA(ctx, ctx->b_dec_a.ensure(bytes + 64));
     FE_CUDA(ctx, ctx->b_dec_b.ensure(bytes + 64));
     FE_CUDA(ctx, ctx->b_dec_items.ensure(n * sizeof(fe_encode_item) + (n_slow + 1) * 4 + 64));
-    FE_CUDA(ctx, ctx->b_dec_sum.ensure(64 * 8));
+    FE_CUDA(ctx, ctx->b_dec_sum.ensure(64 * 8 + 64));
     fe_encode_item* d_items = ctx->b_dec_items.as<fe_encode_item>();
     uint32_t* d_off = reinterpret_cast<uint32_t*>(d_items + n);
     if (n) {
         FE_CUDA(ctx, cudaMemcpyAsync(d_items, grouped.data(), n * sizeof(fe_encode_item), cudaMemcpyHostToDevice, ctx->stream));
         FE_CUDA(ctx, cudaMemcpyAsync(d_off, pix_off.data(), (n_slow + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    uint8_t* src = ctx->b_dec_a.as<uint8_t>();
-    uint8_t* dst = ctx->b_dec_b.as<uint8_t>();
-    FE_CUDA(ctx, cudaMemsetAsync(src, 100, bytes, ctx->stream)); // Encoder2.hpp:69
-    FE_CUDA(ctx, cudaMemcpyAsync(dst, target, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    cudaEventRecord(ctx->ev[0], ctx->stream);
-    int i = 0;
-    double rms = 0.0;
     unsigned long long* d_sum = ctx->b_dec_sum.as<unsigned long long>();
-    for (; i < iters; ++i) {
-        FE_CUDA(ctx, cudaMemsetAsync(d_sum, 0, 64 * 8, ctx->stream));
-        for (size_t gidx = 0; gidx < sizes.size(); ++gidx) {
-            const uint32_t T = sizes[gidx];
-            const size_t cnt = goff[gidx + 1] - goff[gidx];
-            if (!cnt) continue;
-            if (tiled[gidx]) {
-                if (!launch_decode_step_small(ctx->stream, src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T, use_fma, fused_sq ? d_sum : nullptr))
-                    k_decode_step_tiled<<<cdiv(cnt, 8), 256, 8 * T * T * sizeof(uint16_t), ctx->stream>>>(src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T,
-                                                                                                        use_fma, fused_sq ? d_sum : nullptr);
-                ctx->stats.kernel_launches++;
-                FE_CUDA(ctx, cudaGetLastError());
-            } else {
-                LAUNCH(ctx, k_decode_step_uniform, cdiv((uint64_t)cnt * T * (T / 4), 256), 256, src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T,
-                       use_fma, fused_sq ? d_sum : nullptr);
-            }
-        }
-        if (n_slow)
-            LAUNCH(ctx, k_decode_step, cdiv(slow_area, 256), 256, src, dst, stride, d_items + n_fast, d_off, (uint32_t)n_slow, (uint32_t)slow_area, use_fma);
-        if (!fused_sq) LAUNCH(ctx, k_sqdiff, 148 * 8, 256, src, dst, width, height, stride, d_sum);
-        unsigned long long slots[64];
-        FE_CUDA(ctx, cudaMemcpyAsync(slots, d_sum, sizeof(slots), cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t* d_state = reinterpret_cast<uint32_t*>(d_sum + 64);       // {done, iterations, rms bits lo, hi} ... [8..] coverage scratch
+    FE_CUDA(ctx, cudaMemsetAsync(d_sum, 0, 64 * 8 + 64, ctx->stream));
+
+    // ---- do the items tile the plane?  Equal area does not prove it: every pixel must be written exactly once (bitmap). ----
+    bool covered = false;
+    if (n) {
+        const bool maybe = !has_default && area == (uint64_t)width * height;
+        const uint32_t wpr = (width + 31) / 32;
+        std::vector<uint32_t> row_off(n + 1, 0);
+        for (size_t i = 0; i < n; ++i) row_off[i + 1] = row_off[i] + grouped[i].h;
+        FE_CUDA(ctx, ctx->b_q.ensure((size_t)wpr * height * 4 + (n + 1) * 4 + 64));
+        uint32_t* d_bm = ctx->b_q.as<uint32_t>();
+        uint32_t* d_rows = d_bm + (size_t)wpr * height;
+        FE_CUDA(ctx, cudaMemsetAsync(d_bm, 0, (size_t)wpr * height * 4, ctx->stream));
+        FE_CUDA(ctx, cudaMemcpyAsync(d_rows, row_off.data(), (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(ctx, k_cover_bitmap, cdiv(row_off[n], 256), 256, d_items, (uint32_t)n, d_rows, row_off[n], wpr, d_bm, d_state + 8);
+        if (maybe) LAUNCH(ctx, k_popcount, ctx->n_sm * 4, 256, d_bm, (size_t)wpr * height, reinterpret_cast<unsigned long long*>(d_state + 10));
+        uint32_t cov[4] = {0, 0, 0, 0};                                    // overlap flag, -, covered pixels (u64)
+        FE_CUDA(ctx, cudaMemcpyAsync(cov, d_state + 8, sizeof(cov), cudaMemcpyDeviceToHost, ctx->stream));
         FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        unsigned long long sum64 = 0;
-        for (unsigned long long v : slots) sum64 += v;
-        const int32_t wrapped = (int32_t)(uint32_t)(sum64 & 0xFFFFFFFFull); // the reference's int32 accumulator (metrics.h:27)
-        rms = (double)wrapped / (double)(uint32_t)(width * height);
-        if (rms < rms_eps) break;
-        if (covered) std::swap(src, dst); // source = target.copy(): every pixel is rewritten next step anyway
-        else FE_CUDA(ctx, cudaMemcpyAsync(src, dst, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        // gaps are fine (the copy path below); overlaps are not: the reference applies its items in list order
+        if (cov[0])
+            return fe_fail(ctx, FE_ERR_INVALID, "fe_decode: items overlap (Decoder2 applies its items in list order, the last one wins; "
+                                                "overlapping lists are not supported)");
+        covered = maybe && (((uint64_t)cov[3] << 32) | cov[2]) == (uint64_t)width * height;
     }
-    // after a swap the freshest plane is `src` unless we broke out before swapping
-    const uint8_t* result = dst;
-    if (covered && i == iters && iters > 0) result = src;
+    const bool fused_sq = covered && n_slow == 0;                          // convergence sum inside the gather kernel
+    uint8_t* buf[2] = {ctx->b_dec_a.as<uint8_t>(), ctx->b_dec_b.as<uint8_t>()};
+    FE_CUDA(ctx, cudaMemsetAsync(buf[0], 100, bytes, ctx->stream)); // Encoder2.hpp:69
+    FE_CUDA(ctx, cudaMemcpy2DAsync(buf[1], stride, target, stride, width, height, cudaMemcpyHostToDevice, ctx->stream));
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    // ---- the iteration train: BATCH iterations per host look; once `done` is up the rest of a batch are no-ops ----
+    const int BATCH = 8;
+    uint32_t state[4] = {0, 0, 0, 0};
+    const uint32_t npix = (uint32_t)(width * height);
+    for (int i0 = 0; i0 < iters && !state[0]; i0 += BATCH) {
+        for (int i = i0; i < std::min(iters, i0 + BATCH); ++i) {
+            // tiled plane: the two buffers ping-pong (every pixel is rewritten); else buffer 0 is the source, refreshed by a copy
+            const uint8_t* src = covered ? buf[i & 1] : buf[0];
+            uint8_t* dst = covered ? buf[(i + 1) & 1] : buf[1];
+            for (size_t gidx = 0; gidx < sizes.size(); ++gidx) {
+                const uint32_t T = sizes[gidx];
+                const size_t cnt = goff[gidx + 1] - goff[gidx];
+                if (!cnt) continue;
+                if (tiled[gidx]) {
+                    if (!launch_decode_step_small(ctx->stream, src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T, use_fma, fused_sq ? d_sum : nullptr, d_state))
+                        k_decode_step_tiled<<<cdiv(cnt, 8), 256, 8 * T * T * sizeof(uint16_t), ctx->stream>>>(src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T,
+                                                                                                            use_fma, fused_sq ? d_sum : nullptr, d_state);
+                    ctx->stats.kernel_launches++;
+                    FE_CUDA(ctx, cudaGetLastError());
+                } else {
+                    LAUNCH(ctx, k_decode_step_uniform, cdiv((uint64_t)cnt * T * (T / 4), 256), 256, src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T,
+                           use_fma, fused_sq ? d_sum : nullptr, d_state);
+                }
+            }
+            if (n_slow)
+                LAUNCH(ctx, k_decode_step, cdiv(slow_area, 256), 256, src, dst, stride, d_items + n_fast, d_off, (uint32_t)n_slow, (uint32_t)slow_area, use_fma,
+                       d_state);
+            if (!fused_sq) LAUNCH(ctx, k_sqdiff, ctx->n_sm * 8, 256, src, dst, width, height, stride, d_sum, d_state);
+            LAUNCH(ctx, k_decode_check, 1, 32, d_sum, d_state, npix, rms_eps, (uint32_t)i);
+            if (!covered)   // source = target.copy() (Encoder2.hpp:86), unless this iteration converged
+                LAUNCH(ctx, k_copy_plane_if_running, ctx->n_sm * 4, 256, reinterpret_cast<const uint4*>(buf[1]), reinterpret_cast<uint4*>(buf[0]), (bytes + 15) / 16,
+                       d_state);
+        }
+        FE_CUDA(ctx, cudaMemcpyAsync(state, d_state, sizeof(state), cudaMemcpyDeviceToHost, ctx->stream));
+        FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    const int done_iter = (int)state[1];                                     // index of the converged iteration, or `iters`
+    const unsigned long long rbits = ((unsigned long long)state[3] << 32) | state[2];
+    double rms = 0.0;
+    memcpy(&rms, &rbits, 8);
+    // freshest plane: the destination of the last iteration that ran
+    const int last = state[0] ? done_iter : iters - 1;
+    const uint8_t* result = (covered && last >= 0) ? buf[(last + 1) & 1] : buf[1];
     cudaEventRecord(ctx->ev[1], ctx->stream);
-    FE_CUDA(ctx, cudaMemcpyAsync(target, result, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaMemcpy2DAsync(target, stride, result, stride, width, height, cudaMemcpyDeviceToHost, ctx->stream));   // never the caller's padding
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->stats.last_decode_ms, ctx->ev[0], ctx->ev[1]);
-    if (iterations) *iterations = i;
+    if (iterations) *iterations = done_iter;
     if (rms_out) *rms_out = rms;
     return FE_OK;
 }
@@ -973,8 +1014,8 @@ extern "C" int fe_copy_items(fe_ctx* ctx, const uint8_t* source, uint8_t* target
     uint64_t area = 0;
     for (size_t i = 0; i < n; ++i) {
         const fe_encode_item& e = items[i];
-        if (!e.w || !e.h || e.x + e.w > width || e.y + e.h > height) return fe_fail(ctx, FE_ERR_INVALID, "fe_copy_items: item %zu outside the image", i);
-        if (e.src_w && (e.src_w != e.src_h || e.match_x + e.src_w > width || e.match_y + e.src_h > height || e.transform < 0 || e.transform > 7 || e.src_w < 2))
+        if (!e.w || !e.h || !inside(e.x, e.y, e.w, e.h, width, height)) return fe_fail(ctx, FE_ERR_INVALID, "fe_copy_items: item %zu outside the image", i);
+        if (e.src_w && (e.src_w != e.src_h || !inside(e.match_x, e.match_y, e.src_w, e.src_h, width, height) || e.transform < 0 || e.transform > 7 || e.src_w < 2))
             return fe_fail(ctx, FE_ERR_INVALID, "fe_copy_items: item %zu has an invalid source block", i);
         pix_off[i] = (uint32_t)area;
         area += (uint64_t)e.w * e.h;
@@ -994,7 +1035,7 @@ extern "C" int fe_copy_items(fe_ctx* ctx, const uint8_t* source, uint8_t* target
         FE_CUDA(ctx, cudaMemcpyAsync(d_items, items, n * sizeof(fe_encode_item), cudaMemcpyHostToDevice, ctx->stream));
         FE_CUDA(ctx, cudaMemcpyAsync(d_off, pix_off.data(), (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
         LAUNCH(ctx, k_decode_step, cdiv(area, 256), 256, ctx->b_dec_a.as<uint8_t>(), ctx->b_dec_b.as<uint8_t>(), stride, d_items, d_off, (uint32_t)n,
-               (uint32_t)area, use_fma);
+               (uint32_t)area, use_fma, nullptr);
     }
     FE_CUDA(ctx, cudaMemcpyAsync(target, ctx->b_dec_b.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1071,15 +1112,54 @@ extern "C" int fe_pack_items(fe_ctx* ctx, const fe_encode_item* items, size_t n,
     if (!(minmax_out[1] > minmax_out[0]) || !(minmax_out[3] > minmax_out[2]))
         return fe_fail(ctx, FE_ERR_INVALID, "fe_pack_items: degenerate value range (Quantizer asserts max > min)");
     uint32_t* d_bad = reinterpret_cast<uint32_t*>(ctx->b_q.as<uint8_t>() + 64);
+    double* d_mm = reinterpret_cast<double*>(ctx->b_q.as<uint8_t>() + 96);
     unsigned long long* d_out = reinterpret_cast<unsigned long long*>(ctx->b_q.as<uint8_t>() + 128);
     FE_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
-    LAUNCH(ctx, k_pack, cdiv(n, 256), 256, ctx->b_dec_items.as<fe_encode_item>(), (uint32_t)n, t_max, minmax_out[0], minmax_out[1], minmax_out[2],
-           minmax_out[3], bits_s, bits_o, d_out, d_bad);
+    FE_CUDA(ctx, cudaMemcpyAsync(d_mm, minmax_out, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_pack, cdiv(n, 256), 256, ctx->b_dec_items.as<fe_encode_item>(), (uint32_t)n, t_max, d_mm, bits_s, bits_o, d_out, d_bad);
     uint32_t bad = 0;
     FE_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
     FE_CUDA(ctx, cudaMemcpyAsync(packed_out, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (bad) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "fe_pack_items: %u items are not power-of-two lattice blocks with S = 2T below t_max=%u", bad, t_max);
+    return FE_OK;
+}
+
+extern "C" int fe_items_minmax_device(fe_ctx* ctx, double* minmax_dev) {
+    if (!ctx || !minmax_dev) return fe_fail(ctx, FE_ERR_INVALID, "fe_items_minmax_device: null argument");
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    FE_CUDA(ctx, ctx->b_q.ensure(256));
+    unsigned long long mm[4] = {FE_INF64, 0, FE_INF64, 0};
+    unsigned long long* d_keys = reinterpret_cast<unsigned long long*>(ctx->b_q.as<uint8_t>());
+    FE_CUDA(ctx, cudaMemcpyAsync(d_keys, mm, sizeof(mm), cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->n_items) LAUNCH(ctx, k_minmax, ctx->n_sm * 4, 256, ctx->b_items.as<fe_encode_item>(), (uint32_t)ctx->n_items, d_keys);
+    LAUNCH(ctx, k_minmax_finish, 1, 32, d_keys, minmax_dev);
+    return FE_OK;
+}
+
+extern "C" int fe_pack_items_device(fe_ctx* ctx, uint32_t t_max, int bits_s, int bits_o, const double* minmax_dev, uint64_t* packed_dev,
+                                    size_t cap, size_t* n_out) {
+    if (!ctx || !minmax_dev || (!packed_dev && ctx->n_items)) return fe_fail(ctx, FE_ERR_INVALID, "fe_pack_items_device: null argument");
+    if (bits_s < 2 || bits_s > 5 || bits_o < 2 || bits_o > 7) return fe_fail(ctx, FE_ERR_INVALID, "fe_pack_items_device: bits_s in 2..5, bits_o in 2..7");
+    if (!t_max || (t_max & (t_max - 1))) return fe_fail(ctx, FE_ERR_INVALID, "fe_pack_items_device: t_max must be a power of two");
+    if (cap < ctx->n_items) return fe_fail(ctx, FE_ERR_CAPACITY, "fe_pack_items_device: %zu items, capacity %zu", ctx->n_items, cap);
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    FE_CUDA(ctx, ctx->b_counters.ensure(16 * sizeof(uint32_t)));
+    uint32_t* d_bad = ctx->b_counters.as<uint32_t>() + 12;     // read by fe_pack_errors
+    FE_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    if (ctx->n_items)
+        LAUNCH(ctx, k_pack, cdiv(ctx->n_items, 256), 256, ctx->b_items.as<fe_encode_item>(), (uint32_t)ctx->n_items, t_max, minmax_dev, bits_s, bits_o,
+               reinterpret_cast<unsigned long long*>(packed_dev), d_bad);
+    if (n_out) *n_out = ctx->n_items;
+    return FE_OK;
+}
+
+extern "C" int fe_pack_errors(fe_ctx* ctx, uint32_t* n_bad) {
+    if (!ctx || !n_bad) return FE_ERR_INVALID;
+    *n_bad = 0;
+    if (!ctx->b_counters.p) return FE_OK;
+    FE_CUDA(ctx, cudaMemcpyAsync(n_bad, ctx->b_counters.as<uint32_t>() + 12, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FE_OK;
 }
 

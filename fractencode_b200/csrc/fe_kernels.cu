@@ -597,7 +597,8 @@ void launch_k_finalize(cudaStream_t stream, const FinalizeArgs& f, uint32_t T) {
 // One thread per target pixel of an item list with prefix offsets (pix_off[i] = first pixel id of item i).
 __global__ void k_decode_step(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t stride,
                               const fe_encode_item* __restrict__ items, const uint32_t* __restrict__ pix_off, uint32_t n_items,
-                              uint32_t total_pix, int use_fma) {
+                              uint32_t total_pix, int use_fma, const uint32_t* __restrict__ done) {
+    if (done && *done) return;            // the iteration already converged: every later launch is a no-op
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= total_pix) return;
     // binary search the owning item
@@ -620,7 +621,8 @@ __global__ void k_decode_step(const uint8_t* __restrict__ src, uint8_t* __restri
 // of Decoder2 (metrics.h:26-36) without a second pass over both planes -- valid when the items tile the plane.
 __global__ void k_decode_step_uniform(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t stride,
                                       const fe_encode_item* __restrict__ items, uint32_t n_items, uint32_t T, int use_fma,
-                                      unsigned long long* __restrict__ sq_out) {
+                                      unsigned long long* __restrict__ sq_out, const uint32_t* __restrict__ done) {
+    if (done && *done) return;            // the iteration already converged: every later launch is a no-op
     const uint32_t segs = T / 4, per_item = T * segs;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long sq = 0;
@@ -672,7 +674,8 @@ __global__ void k_decode_step_uniform(const uint8_t* __restrict__ src, uint8_t* 
 // write of the plane (+ one read of the old plane for the fused convergence sum).
 __global__ void __launch_bounds__(256) k_decode_step_tiled(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t stride,
                                                            const fe_encode_item* __restrict__ items, uint32_t n_items, uint32_t T, int use_fma,
-                                                           unsigned long long* __restrict__ sq_out) {
+                                                           unsigned long long* __restrict__ sq_out, const uint32_t* __restrict__ done) {
+    if (done && *done) return;            // the iteration already converged: every later launch is a no-op
     extern __shared__ uint16_t sh_box[];                       // [warps per block][T*T]
     const uint32_t warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t i = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
@@ -739,7 +742,8 @@ __global__ void __launch_bounds__(256) k_decode_step_tiled(const uint8_t* __rest
 template <int T, int IPW>
 __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t stride,
                                                            const fe_encode_item* __restrict__ items, uint32_t n_items, int use_fma,
-                                                           unsigned long long* __restrict__ sq_out) {
+                                                           unsigned long long* __restrict__ sq_out, const uint32_t* __restrict__ done) {
+    if (done && *done) return;            // the iteration already converged: every later launch is a no-op
     constexpr int N = T * T, S = 2 * T, WPR = S / 4, UNITS = T * WPR;       // row-pair words per item
     constexpr int U = (IPW * UNITS + 31) / 32;                                // load units per lane
     constexpr int SEGS = T / 4, OUT = T * SEGS, Q = (IPW * OUT + 31) / 32;    // 4-pixel output segments per item / per lane
@@ -824,17 +828,66 @@ __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __rest
 }
 
 bool launch_decode_step_small(cudaStream_t stream, const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items, uint32_t n,
-                              uint32_t T, int use_fma, unsigned long long* sq_out) {
-    if (T == 4) k_decode_step_small<4, 8><<<(n + 63) / 64, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out);
-    else if (T == 8) k_decode_step_small<8, 4><<<(n + 31) / 32, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out);
+                              uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done) {
+    if (T == 4) k_decode_step_small<4, 8><<<(n + 63) / 64, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done);
+    else if (T == 8) k_decode_step_small<8, 4><<<(n + 31) / 32, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done);
     else return false;
     return true;
+}
+
+// Coverage proof for the ping-pong decode: every pixel must be written by exactly one item.  One thread per (item, row):
+// the row's pixels are OR-ed into a bitmap (wpr words per image row); a bit that was already set means two items overlap.
+__global__ void k_cover_bitmap(const fe_encode_item* __restrict__ items, uint32_t n, const uint32_t* __restrict__ row_off, uint32_t total_rows,
+                               uint32_t wpr, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ overlap) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_rows) return;
+    uint32_t lo = 0, hi = n;                       // item whose rows contain t
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (row_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    const fe_encode_item e = items[lo];
+    if (e.src_w == 0 || e.src_h == 0) return;      // default item: writes nothing
+    const uint32_t y = e.y + (t - row_off[lo]), x0 = e.x, x1 = e.x + e.w;   // [x0, x1)
+    for (uint32_t w = x0 / 32; w <= (x1 - 1) / 32; ++w) {
+        const uint32_t a = max(x0, w * 32) - w * 32, b = min(x1, w * 32 + 32) - w * 32;   // bits [a, b)
+        const uint32_t mask = (b - a == 32 ? 0xFFFFFFFFu : ((1u << (b - a)) - 1u) << a);
+        const uint32_t old = atomicOr(&bitmap[(size_t)y * wpr + w], mask);
+        if (old & mask) atomicExch(overlap, 1u);
+    }
+}
+__global__ void k_popcount(const uint32_t* __restrict__ words, size_t n, unsigned long long* __restrict__ out) {
+    unsigned long long s = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += __popc(words[i]);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+// Decoder2's convergence test (encode/Encoder2.hpp:83-85) on the device, once per iteration: the int32-wrapped sum of
+// squared differences over the pixel count; the first iteration below eps raises `done`, which turns every later launch of the
+// train into a no-op, so the host only looks every few iterations.  state = {done, iterations, rms bits lo, hi}; one warp.
+__global__ void k_decode_check(unsigned long long* __restrict__ sums, uint32_t* __restrict__ state, uint32_t npix, double eps, uint32_t iter) {
+    if (state[0]) return;
+    unsigned long long v = sums[threadIdx.x] + sums[threadIdx.x + 32];
+    sums[threadIdx.x] = 0; sums[threadIdx.x + 32] = 0;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (threadIdx.x) return;
+    const int32_t wrapped = (int32_t)(uint32_t)(v & 0xFFFFFFFFull);      // the reference's int32 accumulator (metrics.h:27)
+    const double rms = __ddiv_rn((double)wrapped, (double)npix);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(rms);
+    state[2] = (uint32_t)bits; state[3] = (uint32_t)(bits >> 32);
+    if (rms < eps) { state[0] = 1; state[1] = iter; } else state[1] = iter + 1;
+}
+// source = target.copy() of a decode that does not tile the plane (Encoder2.hpp:86), skipped once converged
+__global__ void k_copy_plane_if_running(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16, const uint32_t* __restrict__ done) {
+    if (*done) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 // sum over the plane of (a-b)^2 as uint64 (the reference accumulates in int32, metrics.h:27; the
 // host wraps the 64-bit sum to int32 to reproduce it).
 __global__ void k_sqdiff(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t w, uint32_t h, uint32_t stride,
-                         unsigned long long* __restrict__ out) {
+                         unsigned long long* __restrict__ out, const uint32_t* __restrict__ done) {
+    if (done && *done) return;            // the iteration already converged: every later launch is a no-op
     unsigned long long s = 0;
     const size_t n = (size_t)w * h;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -879,6 +932,15 @@ __global__ void k_minmax(const fe_encode_item* __restrict__ items, uint32_t n, u
         atomicMin(&mm[0], mns); atomicMax(&mm[1], mxs); atomicMin(&mm[2], mno); atomicMax(&mm[3], mxo);
     }
 }
+// order-preserving keys of k_minmax -> the doubles main.cpp:109-118 ends up with (max starts at -1, min at DBL_MAX)
+__global__ void k_minmax_finish(const unsigned long long* __restrict__ keys, double* __restrict__ out) {
+    const int i = threadIdx.x;
+    if (i >= 4) return;
+    const unsigned long long k = keys[i];
+    const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    const double d = __longlong_as_double((long long)b);
+    out[i] = (i & 1) ? fmax(-1.0, d) : fmin(1.7976931348623157e308, d);
+}
 __global__ void k_quantize(const fe_encode_item* __restrict__ items, uint32_t n, double min_s, double max_s, double min_o,
                            double max_o, int bits_s, int bits_o, uint32_t* __restrict__ qs, uint32_t* __restrict__ qo) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -893,10 +955,11 @@ __global__ void k_quantize(const fe_encode_item* __restrict__ items, uint32_t n,
 }
 
 // packed 64-bit records (layout in include/fractencode_b200.h)
-__global__ void k_pack(const fe_encode_item* __restrict__ items, uint32_t n, uint32_t t_max, double min_s, double max_s, double min_o,
-                       double max_o, int bits_s, int bits_o, unsigned long long* __restrict__ out, uint32_t* __restrict__ bad) {
+__global__ void k_pack(const fe_encode_item* __restrict__ items, uint32_t n, uint32_t t_max, const double* __restrict__ mm, int bits_s,
+                       int bits_o, unsigned long long* __restrict__ out, uint32_t* __restrict__ bad) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const double min_s = mm[0], max_s = mm[1], min_o = mm[2], max_o = mm[3];   // device memory: may come from an all-reduce
     const fe_encode_item e = items[i];
     const uint32_t T = e.w;
     uint32_t level = 0;

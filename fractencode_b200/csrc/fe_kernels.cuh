@@ -45,19 +45,25 @@ __global__ void k_build_pool(const uint8_t* img, uint32_t stride, const fe_grid_
                              uint32_t npool, uint32_t T, uint32_t rho, uint32_t Npad, uint8_t* Blo, uint8_t* Bhi, uint32_t* coln);
 void launch_k_finalize(cudaStream_t stream, const FinalizeArgs& f, uint32_t T);
 __global__ void k_decode_step(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items,
-                              const uint32_t* pix_off, uint32_t n_items, uint32_t total_pix, int use_fma);
+                              const uint32_t* pix_off, uint32_t n_items, uint32_t total_pix, int use_fma, const uint32_t* done);
 __global__ void k_decode_step_uniform(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items,
-                                      uint32_t n_items, uint32_t T, int use_fma, unsigned long long* sq_out);
+                                      uint32_t n_items, uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done);
 bool launch_decode_step_small(cudaStream_t stream, const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items, uint32_t n,
-                              uint32_t T, int use_fma, unsigned long long* sq_out);
+                              uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done);
 __global__ void k_decode_step_tiled(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items, uint32_t n_items,
-                                    uint32_t T, int use_fma, unsigned long long* sq_out);
-__global__ void k_sqdiff(const uint8_t* a, const uint8_t* b, uint32_t w, uint32_t h, uint32_t stride, unsigned long long* out);
+                                    uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done);
+__global__ void k_sqdiff(const uint8_t* a, const uint8_t* b, uint32_t w, uint32_t h, uint32_t stride, unsigned long long* out, const uint32_t* done);
+__global__ void k_cover_bitmap(const fe_encode_item* items, uint32_t n, const uint32_t* row_off, uint32_t total_rows, uint32_t wpr, uint32_t* bitmap,
+                               uint32_t* overlap);
+__global__ void k_popcount(const uint32_t* words, size_t n, unsigned long long* out);
+__global__ void k_decode_check(unsigned long long* sums, uint32_t* state, uint32_t npix, double eps, uint32_t iter);
+__global__ void k_copy_plane_if_running(const uint4* src, uint4* dst, size_t n16, const uint32_t* done);
 __global__ void k_minmax(const fe_encode_item* items, uint32_t n, unsigned long long* mm);
 __global__ void k_quantize(const fe_encode_item* items, uint32_t n, double min_s, double max_s, double min_o, double max_o,
                            int bits_s, int bits_o, uint32_t* qs, uint32_t* qo);
 __global__ void k_synth(uint8_t* out, uint32_t w, uint32_t h, uint32_t stride, unsigned long long seed, int kind);
-__global__ void k_pack(const fe_encode_item* items, uint32_t n, uint32_t t_max, double min_s, double max_s, double min_o, double max_o,
-                       int bits_s, int bits_o, unsigned long long* out, uint32_t* bad);
+__global__ void k_pack(const fe_encode_item* items, uint32_t n, uint32_t t_max, const double* mm, int bits_s, int bits_o,
+                       unsigned long long* out, uint32_t* bad);
+__global__ void k_minmax_finish(const unsigned long long* keys, double* out);
 __global__ void k_unpack(const unsigned long long* in, uint32_t n, uint32_t t_max, double min_s, double max_s, double min_o, double max_o,
                          int bits_s, int bits_o, int use_fma, fe_encode_item* out);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FE_ABI_VERSION 2
+#define FE_ABI_VERSION 3
 
 typedef enum {
     FE_OK = 0,
@@ -190,6 +190,18 @@ int fe_quantize(fe_ctx* ctx, const fe_encode_item* items, size_t n, int bits_s, 
  * together with (t_max, bits_s, bits_o).  Requires square power-of-two blocks with S = 2T on their lattice. */
 int fe_pack_items(fe_ctx* ctx, const fe_encode_item* items, size_t n, uint32_t t_max, int bits_s, int bits_o,
                   uint64_t* packed_out, double minmax_out[4]);
+/* The same post-pass on the DEVICE-RESIDENT result list of the last quadtree encode, for pipelines that never bring the 64-byte
+ * records to the host (multi-GPU gathers ship the 8-byte records: SURVEY 8e/8f-1).  Nothing here synchronises.
+ *   fe_items_minmax_device: minmax_dev[4] (device memory) = {min_s, max_s, min_o, max_o} over the list as main.cpp:109-118
+ *                           computes them (max starts at -1, min at DBL_MAX).  When one image is sharded over several GPUs
+ *                           the caller reduces the four values across ranks (min / max) before packing.
+ *   fe_pack_items_device:   packed_dev[0 .. n) (device memory, capacity `cap` words) = packed records of the list, quantised
+ *                           with minmax_dev.  *n_out = n.  Items outside the format are written as 0 and counted:
+ *   fe_pack_errors:         synchronises and returns that count (0 = every record is valid). */
+int fe_items_minmax_device(fe_ctx* ctx, double* minmax_dev);
+int fe_pack_items_device(fe_ctx* ctx, uint32_t t_max, int bits_s, int bits_o, const double* minmax_dev, uint64_t* packed_dev,
+                         size_t cap, size_t* n_out);
+int fe_pack_errors(fe_ctx* ctx, uint32_t* n_bad);
 /* Inverse: contrast = Quantizer::value(q_s), brightness = Quantizer::value(q_o) (fma: q*step+min fused as an
  * FMA-contracting build of the reference would), distance = 0.  The result feeds fe_decode. */
 int fe_unpack_items(fe_ctx* ctx, const uint64_t* packed, size_t n, uint32_t t_max, int bits_s, int bits_o,

@@ -37,7 +37,7 @@ def test_python_binding_covers_header():
 
 def test_abi_version_and_struct_sizes(lib):
     import fractencode_b200 as fb
-    assert lib.fe_abi_version() == 2
+    assert lib.fe_abi_version() == 3
     assert fb.GRID_ITEM.itemsize == 20      # sizeof(Frac2::UniformGridItem), gpu/opencl/common.hpp:18
     assert fb.ENCODE_ITEM.itemsize == 64    # sizeof(Frac::encode_item_t)
     assert ctypes.sizeof(fb.Params) == 32

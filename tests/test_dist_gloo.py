@@ -13,32 +13,33 @@ WORKER = textwrap.dedent("""
     import torch
     import torch.distributed as dist
     sys.path.insert(0, %r)
-    from fractencode_b200.capi import ENCODE_ITEM
-    from fractencode_b200.dist import gather_item_lists, shard_slice, unpack_gathered
+    from fractencode_b200.dist import HEADER_WORDS, PackedGather, shard_slice, split_gathered
 
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    # 37 range blocks sharded over the ranks, every rank "encodes" its slice into fake records
+    # 37 range blocks sharded over the ranks, every rank "encodes" its slice into fake packed records
     units = np.arange(37)
     sl = shard_slice(len(units), rank, world)
-    mine = np.zeros(sl.stop - sl.start, ENCODE_ITEM)
-    mine["x"] = units[sl] * 4
-    mine["y"] = rank
-    mine["distance"] = units[sl] * 0.5
-    cap = 2048
-    buf = torch.zeros(cap * 64, dtype=torch.uint8)
-    buf[: mine.nbytes] = torch.from_numpy(np.frombuffer(mine.tobytes(), np.uint8).copy())
-    counts, gathered = gather_item_lists(buf, len(mine), cap)
-    lists = unpack_gathered(counts, gathered, ENCODE_ITEM)
-    allitems = np.concatenate(lists)
-    assert counts.tolist() == [19, 18], counts
-    assert tuple(gathered.shape) == (2, 1024 * 64), gathered.shape   # blocks of the largest count (rounded), not of the capacity
-    assert (allitems["x"] == units * 4).all()
-    assert (allitems["distance"] == units * 0.5).all()
-    assert [int(l["y"][0]) for l in lists] == [0, 1]
+    mine = (units[sl].astype(np.uint64) << np.uint64(22)) | np.uint64(rank)
+    pg = PackedGather(64, torch.device("cpu"))
+    pg.send[HEADER_WORDS: HEADER_WORDS + len(mine)] = torch.from_numpy(mine.view(np.int64).copy())
+    # per-rank min/max of (s, o), reduced like the Quantizer header of one image sharded over the ranks
+    pg.send[1:5] = torch.tensor([-1.0 - rank, 2.0 + rank, 10.0 * (rank + 1), 50.0 - rank], dtype=torch.float64).view(torch.int64)
+    pg.reduce_minmax()
+    got = pg.exchange(len(mine))
+    if rank == 0:
+        lists = split_gathered(got)
+        assert [len(p) for p, _ in lists] == [19, 18]
+        allrec = np.concatenate([p for p, _ in lists])
+        assert ((allrec >> np.uint64(22)) == units.astype(np.uint64)).all()
+        assert [int(p[0] & np.uint64(1)) for p, _ in lists] == [0, 1]
+        assert lists[0][1].tolist() == [-2.0, 3.0, 10.0, 50.0]        # min_s, max_s, min_o, max_o over both ranks
+        assert tuple(got.shape) == (2, HEADER_WORDS + 64)
+    else:
+        assert got is None
     # slices tile the unit range exactly
-    got = [shard_slice(37, r, world) for r in range(world)]
-    assert got[0].start == 0 and got[-1].stop == 37 and all(got[i].stop == got[i + 1].start for i in range(world - 1))
+    sls = [shard_slice(37, r, world) for r in range(world)]
+    assert sls[0].start == 0 and sls[-1].stop == 37 and all(sls[i].stop == sls[i + 1].start for i in range(world - 1))
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")
@@ -63,7 +64,7 @@ def test_bench_reference_arm_small():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "256", "--tmax", "16", "--steps", "1",
                         "--warmup", "0", "--cpu-blocks", "4"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
-    line = json.loads(p.stdout.strip().split("\\n")[-1])
+    line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "matches/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0

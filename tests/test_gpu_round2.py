@@ -1,0 +1,157 @@
+"""Round-2 GPU tests: C-ABI hardening (trust-boundary checks), decode coverage proof and device-side convergence,
+device-scheduled levels (slice hints + continuation), device-resident packed records."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.cases import assert_items_equal
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def test_classifier_bins_out_of_range_are_rejected(ctx, fo):
+    """Bins are -1 or Classifier2's classes 0..5; anything else is refused (it would index outside the bucket tables)."""
+    import fractencode_b200 as fb
+    img = fo.synth_image(64, 64, 5, 0)
+    ctx.set_image(img)
+    for bad in (6, 100, -2):
+        for which in ("dom", "rng"):
+            dom, rng = fb.uniform_grid(64, 64, 16, 8), fb.uniform_grid(64, 64, 8, 8)
+            (dom if which == "dom" else rng)["bin"][3] = bad
+            with pytest.raises(fb.FractencodeError) as e:
+                ctx.encode_level(dom, rng, fb.Params(0.0, -1.0, True))
+            assert e.value.code == -1, (bad, which)
+            # without the classifier the field is ignored, as DummyClassifier does
+            got = ctx.encode_level(dom, rng, fb.Params(0.0, -1.0, False))
+            assert_items_equal(got, fo.encode_level(img, img, dom, rng, fo.params(0.0, -1.0, False)))
+
+
+def test_bounds_checks_do_not_wrap_around(ctx, fo):
+    """x + w is checked without 32-bit wrap-around at every entry point that takes block lists."""
+    import fractencode_b200 as fb
+    img = fo.synth_image(64, 64, 5, 0)
+    ctx.set_image(img)
+    dom, rng = fb.uniform_grid(64, 64, 16, 8), fb.uniform_grid(64, 64, 8, 8)
+    for fld in ("x", "y"):
+        r2 = rng.copy()
+        r2[fld][1] = 0xFFFFFFFE
+        with pytest.raises(fb.FractencodeError) as e:
+            ctx.encode_level(dom, r2, fb.Params())
+        assert e.value.code == -1
+        d2 = dom.copy()
+        d2[fld][1] = 0xFFFFFFF8
+        with pytest.raises(fb.FractencodeError) as e:
+            ctx.encode_level(d2, rng, fb.Params())
+        assert e.value.code == -1
+        with pytest.raises(fb.FractencodeError):
+            ctx.classify(d2)
+    items = ctx.encode_level(dom, rng, fb.Params())
+    for fld in ("x", "y", "match_x", "match_y"):
+        bad = items.copy()
+        bad[fld][2] = 0xFFFFFFFC
+        with pytest.raises(fb.FractencodeError) as e:
+            ctx.decode(bad, 64, 64, max_iters=1)
+        assert e.value.code == -1
+        with pytest.raises(fb.FractencodeError):
+            ctx.copy_items(img, img.copy(), bad)
+
+
+def test_decode_equal_area_is_not_a_tiling(ctx, fo):
+    """A list whose areas sum to the plane but which overlaps (and leaves a gap) must not take the ping-pong path."""
+    import fractencode_b200 as fb
+    img = fo.synth_image(64, 64, 9, 0)
+    ctx.set_image(img)
+    dom, rng = fb.uniform_grid(64, 64, 16, 8), fb.uniform_grid(64, 64, 8, 8)
+    items = ctx.encode_level(dom, rng, fb.Params())
+    dup = items.copy()
+    dup[5] = dup[4]                               # item 4 twice, block 5 never written: same total area
+    with pytest.raises(fb.FractencodeError) as e:
+        ctx.decode(dup, 64, 64, max_iters=4)
+    assert e.value.code == -1
+    # a list with gaps only (no overlap) decodes like the reference: uncovered pixels keep the target's content
+    gaps = np.delete(items, [3, 17, 40])
+    for iters in (1, 2, 5, -1):
+        a, ia, ra = ctx.decode(gaps, 64, 64, max_iters=iters, init=33)
+        b, ib, rb = fo.decode(gaps, 64, 64, max_iters=iters, init=33)
+        assert (a == b).all() and ia == ib and ra == rb, iters
+
+
+def test_decode_leaves_the_callers_padding_alone(ctx, fo):
+    import ctypes as C
+    import fractencode_b200 as fb
+    z = np.load(os.path.join(GOLDEN, "items_lenna_16_8.npz"))["items"]
+    W = H = 512
+    stride = 544
+    tgt = np.full((H, stride), 7, np.uint8)
+    it, rms = C.c_int(0), C.c_double(0)
+    rc = ctx.lib.fe_decode(ctx.h, z.ctypes.data, len(z), tgt.ctypes.data, W, H, stride, 5, 1e-5, 0, C.byref(it), C.byref(rms))
+    assert rc == 0
+    assert (tgt[:, W:] == 7).all(), "padding bytes of the caller's plane were overwritten"
+    ref, _, _ = fo.decode(z, W, H, stride=stride, max_iters=5, init=7)
+    assert (tgt[:, :W] == ref).all()
+
+
+def test_decode_converges_on_the_same_iteration_as_the_reference(ctx, fo, lenna):
+    """Device-side convergence test in batches of eight iterations: iteration count, rms and image are the reference's
+    whether the stop falls at the start, in the middle or at the end of a batch."""
+    z = np.load(os.path.join(GOLDEN, "items_lenna_qt_16_4_cls_thr5.npz"))["items"]
+    for eps in (1e-5, 0.5, 3.0, 40.0, 1e9):
+        a, ia, ra = ctx.decode(z, 512, 512, eps=eps)
+        b, ib, rb = fo.decode(z, 512, 512, eps=eps)
+        assert ia == ib and ra == rb and (a == b).all(), (eps, ia, ib)
+    for iters in (0, 1, 7, 8, 9, 16, 17):
+        a, ia, ra = ctx.decode(z, 512, 512, max_iters=iters, eps=-1.0)
+        b, ib, rb = fo.decode(z, 512, 512, max_iters=iters, eps=-1.0)
+        assert ia == ib and ra == rb and (a == b).all(), iters
+
+
+def test_slice_hints_and_continuation(fo):
+    """The number of slices a level gets enqueued up front comes from the previous level of its kind; a level that needs
+    more is continued after its synchronisation.  Results never depend on what ran before on the context."""
+    import fractencode_b200 as fb
+    imgs = [fo.synth_image(256, 256, 1234, 2), fo.synth_image(256, 256, 1234, 0), fo.synth_image(256, 256, 7, 1),
+            fo.synth_image(256, 256, 1234, 0)]
+    params = [fb.Params(3.0), fb.Params(8.0), fb.Params(40.0, -1.0, True), fb.Params(8.0)]
+    fresh = []
+    for img, p in zip(imgs, params):
+        with fb.Context(0) as c:
+            c.set_image(img)
+            fresh.append(c.encode_quadtree(32, 4, p))
+    with fb.Context(0) as c:                      # one context: the hints of one image meet the next
+        for rep in range(2):
+            for (img, p), (want, wcounts) in zip(zip(imgs, params), fresh):
+                c.set_image(img)
+                got, counts = c.encode_quadtree(32, 4, p)
+                assert counts == wcounts
+                assert_items_equal(got, want)
+    ref, rcounts = fo.encode_quadtree(imgs[1], 32, 4, fo.params(8.0))
+    assert rcounts == fresh[1][1]
+    assert_items_equal(fresh[1][0], ref)
+
+
+def test_device_resident_pack_matches_the_host_pack(ctx, fo):
+    """fe_items_minmax_device + fe_pack_items_device on the result list in HBM == fe_pack_items on the fetched list."""
+    import torch
+    import fractencode_b200 as fb
+    img = fo.synth_image(256, 256, 1234, 0)
+    ctx.set_image(img)
+    n = ctx.encode_quadtree_device(32, 4, fb.Params(8.0))
+    items = ctx.fetch_items()
+    assert len(items) == n
+    mm = torch.zeros(4, dtype=torch.float64, device="cuda")
+    packed = torch.zeros(n + 5, dtype=torch.int64, device="cuda")
+    ctx.items_minmax_device(mm.data_ptr())
+    assert ctx.pack_items_device(32, mm.data_ptr(), packed.data_ptr(), n + 5) == n
+    assert ctx.pack_errors() == 0
+    want, wmm = ctx.pack_items(items, 32)
+    assert (mm.cpu().numpy() == wmm).all()
+    assert (packed.cpu().numpy()[:n].view(np.uint64) == want).all()
+    # the decoder accepts what the packed stream carries
+    back = ctx.unpack_items(want, 32, wmm)
+    dec, it, rms = ctx.decode(back, 256, 256, max_iters=10, eps=-1.0)
+    odec, oit, orms = fo.decode(back, 256, 256, max_iters=10, eps=-1.0)
+    assert (dec == odec).all() and it == oit and rms == orms
+    with pytest.raises(fb.FractencodeError):
+        ctx.pack_items_device(32, mm.data_ptr(), packed.data_ptr(), n - 1)      # capacity
