@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--search", type=int, default=0, help="0 auto, 1 exact integer path, 2 tcgen05 path")
     ap.add_argument("--cpu-blocks", type=int, default=0, help="range blocks per level in the CPU sample (0: 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch", action="store_true", help="skip the batch-mode sub-measurement (config 5)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-measurement (config 4)")
     ap.add_argument("--shard", default="images", choices=["images", "ranges"],
                     help="N > 1: one image per GPU (weak scaling, default) or the range blocks of ONE image sharded over the GPUs "
@@ -227,6 +228,57 @@ class ClockSampler(threading.Thread):
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def batch_config5(a, ctx, fb, rank, world, sync_all, size=1024, per_rank=32):
+    """BASELINE config 5 in shape: a batch of 1024 x 1024 images, 8x8 grid + quadtree split to 4x4, image-parallel: every
+    rank encodes `per_rank` images from pinned host memory through fe_encode_batch (two pipelined streams) into pinned
+    host records.  Also the same images one call at a time (fe_encode_quadtree), to show what the pipelining buys."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    params = fb.Params(a.thr, -1.0, False, False, a.search)
+    cap = (size // 4) ** 2
+    host = torch.empty((per_rank, size, size), dtype=torch.uint8).pin_memory()
+    for i in range(per_rank):
+        ctx.set_synthetic_image(size, size, 5000 + rank * per_rank + i, 0)
+        host[i].copy_(torch.from_numpy(ctx.get_image()))
+    out = torch.empty(per_rank * cap * 64, dtype=torch.uint8).pin_memory()
+    ptrs = (C.c_void_p * per_rank)(*[host[i].data_ptr() for i in range(per_rank)])
+    counts = (C.c_size_t * per_rank)()
+
+    def batched():
+        rc = ctx.lib.fe_encode_batch(ctx.h, ptrs, per_rank, size, size, size, 8, 4, C.byref(params), out.data_ptr(), cap, counts)
+        if rc != 0:
+            raise fb.FractencodeError(rc, ctx.lib.fe_last_error(ctx.h).decode())
+
+    def one_by_one():
+        n = C.c_size_t(0)
+        for i in range(per_rank):
+            ctx.set_image(host[i].numpy())
+            rc = ctx.lib.fe_encode_quadtree(ctx.h, 8, 4, C.byref(params), out.data_ptr() + i * cap * 64, cap, C.byref(n), None)
+            if rc != 0:
+                raise fb.FractencodeError(rc, ctx.lib.fe_last_error(ctx.h).decode())
+
+    res = {}
+    for name, fn in (("batched", batched), ("one_by_one", one_by_one)):
+        fn()                                       # warm-up (allocations, slice hints)
+        sync_all()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        v = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        res[name] = v.item()
+    n_img = per_rank * world
+    return {"workload": "%d natural %dx%d images per GPU (seeds 5000+), 8x8 grid + quadtree split to 4x4, full search, rms_threshold %g "
+                        "(BASELINE config 5 in shape), pinned host images in, pinned host records out" % (per_rank, size, size, a.thr),
+            "n_gpus": world, "images": n_img, "images_per_s": n_img / res["batched"], "ms_per_image": res["batched"] / per_rank * 1e3,
+            "mpix_per_s": n_img * size * size / 1e6 / res["batched"],
+            "one_call_per_image": {"images_per_s": n_img / res["one_by_one"], "ms_per_image": res["one_by_one"] / per_rank * 1e3},
+            "timing": "host wall clock around the call(s) + device synchronise, max over ranks (the call is synchronous)"}
 
 
 def strong_config4(a, ctx, fb, rank, world, sync_all, size=8192, steps=3):
@@ -424,6 +476,7 @@ def run_b200(a):
     else:
         tot_ms, e_ms, all_matches, all_items = my[0].item(), my[1].item(), my[2].item(), my[3].item()
     strong = strong_config4(a, ctx, fb, rank, world, sync_all) if (world > 1 and not by_ranges and not a.no_strong) else None
+    batch = batch_config5(a, ctx, fb, rank, world, sync_all) if (not by_ranges and not a.no_batch) else None
     if rank == 0:
         pk = peaks()
         ms_per_step = tot_ms / a.steps
@@ -481,6 +534,8 @@ def run_b200(a):
         }
         if strong:
             line["strong"] = strong
+        if batch:
+            line["batch"] = batch
         if world == 1 and not a.no_cpu_baseline:
             from oracle import pyoracle as po
             po.build(ref=os.path.isdir("/root/reference/encode"))

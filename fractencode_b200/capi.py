@@ -75,7 +75,7 @@ def build_library() -> str:
 _LIB = None
 EXPORTS = [
     "fe_abi_version", "fe_create", "fe_destroy", "fe_last_error", "fe_set_image", "fe_set_images", "fe_set_image_device",
-    "fe_classify", "fe_encode_level", "fe_encode_quadtree", "fe_encode_quadtree_device", "fe_encode_quadtree_slice_device", "fe_fetch_items", "fe_device_items",
+    "fe_classify", "fe_encode_level", "fe_encode_quadtree", "fe_encode_quadtree_device", "fe_encode_quadtree_slice_device", "fe_fetch_items", "fe_device_items", "fe_encode_batch",
     "fe_decode", "fe_copy_items", "fe_quantize", "fe_pack_items", "fe_unpack_items", "fe_items_minmax_device", "fe_pack_items_device", "fe_pack_errors", "fe_get_stats", "fe_stats_reset", "fe_synchronize", "fe_set_synthetic_image", "fe_get_image", "fe_plan_threshold",
 ]
 
@@ -105,6 +105,7 @@ def load_library():
         "fe_encode_quadtree_device": (i32, [vp, u32, u32, C.POINTER(Params), C.POINTER(sz)]),
         "fe_encode_quadtree_slice_device": (i32, [vp, u32, u32, C.POINTER(Params), sz, sz, C.POINTER(sz)]),
         "fe_fetch_items": (i32, [vp, vp, sz, C.POINTER(sz)]),
+        "fe_encode_batch": (i32, [vp, vp, sz, u32, u32, u32, u32, u32, C.POINTER(Params), vp, sz, vp]),
         "fe_device_items": (vp, [vp, C.POINTER(sz)]),
         "fe_decode": (i32, [vp, vp, sz, vp, u32, u32, u32, i32, dbl, i32, C.POINTER(C.c_int), C.POINTER(dbl)]),
         "fe_copy_items": (i32, [vp, vp, vp, u32, u32, u32, vp, sz, i32]),
@@ -238,6 +239,21 @@ class Context:
         n = C.c_size_t(0)
         self._check(self.lib.fe_encode_quadtree_slice_device(self.h, t_max, t_min, C.byref(params), first_block, n_blocks, C.byref(n)))
         return n.value
+
+    def encode_batch(self, images, t_max: int, t_min: int, params: Params, out: np.ndarray | None = None):
+        """Quadtree-encode a batch of equally sized planes (list of 2-D uint8 arrays, or one [n, H, W] array), pipelined.
+        Returns one transform list per image."""
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        n = len(imgs)
+        H, W = imgs[0].shape
+        assert all(im.shape == (H, W) for im in imgs)
+        cap = (W // t_min) * (H // t_min)
+        if out is None:
+            out = np.zeros(n * cap, ENCODE_ITEM)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        counts = (C.c_size_t * n)()
+        self._check(self.lib.fe_encode_batch(self.h, ptrs, n, W, H, W, t_max, t_min, C.byref(params), out.ctypes.data, cap, counts))
+        return [out[i * cap: i * cap + counts[i]] for i in range(n)]
 
     def fetch_items(self, out: np.ndarray | None = None) -> np.ndarray:
         n = C.c_size_t(0)

@@ -17,6 +17,8 @@
 
 static thread_local std::string g_create_error;   // error of the last failed fe_create on this thread
 
+void fe_free_job(fe_ctx* ctx);
+
 int fe_fail(fe_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -150,6 +152,8 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& ev : ctx->ev_pass) if (ev) cudaEventDestroy(ev);
+    for (auto& c : ctx->sub) { if (c) fe_destroy(c); c = nullptr; }
+    fe_free_job(ctx);
     if (ctx->h_summary) cudaFreeHost(ctx->h_summary);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -742,9 +746,28 @@ extern "C" int fe_encode_quadtree_device(fe_ctx* ctx, uint32_t t_max, uint32_t t
     return fe_encode_quadtree_slice_device(ctx, t_max, t_min, params, 0, (size_t)-1, n_out);
 }
 
-extern "C" int fe_encode_quadtree_slice_device(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params, size_t first_block,
-                                               size_t n_blocks, size_t* n_out) {
-    if (!ctx) return FE_ERR_INVALID;
+// The quadtree encode of one image as a resumable job: begin, then (enqueue level, complete level) until finished.  Between
+// the two halves of a level the host is free -- fe_encode_batch uses that to keep a second image's level in flight.
+struct QuadJob {
+    uint32_t t_max = 0, t_min = 0, T = 0;
+    int level = 0;
+    size_t n_pending = 0, offset = 0;
+    fe_params params{};
+    LevelIO io;
+    LevelPending lp;
+    bool level_open = false;
+};
+
+static QuadJob* job_of(fe_ctx* ctx) {
+    if (!ctx->job) ctx->job = new QuadJob();
+    return reinterpret_cast<QuadJob*>(ctx->job);
+}
+void fe_free_job(fe_ctx* ctx) {
+    delete reinterpret_cast<QuadJob*>(ctx->job);
+    ctx->job = nullptr;
+}
+
+static int quad_begin(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params, size_t first_block, size_t n_blocks) {
     if (!params) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_quadtree: params is NULL");
     if (!ctx->src.px) return fe_fail(ctx, FE_ERR_STATE, "fe_encode_quadtree: call fe_set_image first");
     if (ctx->tgt.px != ctx->src.px) return fe_fail(ctx, FE_ERR_STATE, "fe_encode_quadtree: needs a single image (fe_set_image)");
@@ -760,64 +783,162 @@ extern "C" int fe_encode_quadtree_slice_device(fe_ctx* ctx, uint32_t t_max, uint
     const size_t per_top = (size_t)(t_max / t_min) * (t_max / t_min);
     const size_t cap = std::max<size_t>(n_blocks * per_top, 1);
     FE_CUDA(ctx, ctx->b_items.ensure(cap * sizeof(fe_encode_item)));
-    size_t n_pending = n_blocks;
     FE_CUDA(ctx, ctx->b_rng.ensure(cap * sizeof(fe_grid_item)));
     FE_CUDA(ctx, ctx->b_rng_next.ensure(cap * sizeof(fe_grid_item)));
-    if (n_pending)
-        LAUNCH(ctx, k_uniform_grid, cdiv(n_pending, 256), 256, ctx->b_rng.as<fe_grid_item>(), W / t_max, (uint32_t)n_pending, t_max, t_max,
+    if (n_blocks)
+        LAUNCH(ctx, k_uniform_grid, cdiv(n_blocks, 256), 256, ctx->b_rng.as<fe_grid_item>(), W / t_max, (uint32_t)n_blocks, t_max, t_max,
                (uint32_t)first_block);
     for (int l = 0; l < 8; ++l) {
         ctx->stats.level_items[l] = ctx->stats.level_ranges[l] = ctx->stats.level_matches[l] = 0;
         ctx->stats.level_evaluated[l] = ctx->stats.level_passes[l] = 0;
         ctx->stats.level_search_ms[l] = ctx->stats.level_prep_ms[l] = 0.f;
     }
-    size_t offset = 0;
-    int level = 0;
-    for (uint32_t T = t_max; T >= t_min && n_pending; T /= 2, ++level) {
-        const uint32_t S = 2 * T;
-        const uint32_t dnx = W >= S ? W / T - 1 : 0, dny = H >= S ? H / T - 1 : 0;
-        const size_t nD = (size_t)dnx * dny;
-        LevelIO io;
-        FE_TRY(make_geom(ctx, S, T, true, &io.g));
-        if (nD) {
-            FE_CUDA(ctx, ctx->b_dom.ensure(nD * sizeof(fe_grid_item)));
-            LAUNCH(ctx, k_uniform_grid, cdiv(nD, 256), 256, ctx->b_dom.as<fe_grid_item>(), dnx, (uint32_t)nD, S, T, 0u);
-        }
-        FE_CUDA(ctx, ctx->b_level_items.ensure(n_pending * sizeof(fe_encode_item)));
-        FE_CUDA(ctx, ctx->b_split.ensure(n_pending * 4 + 4));
-        io.d_dom = ctx->b_dom.as<fe_grid_item>(); io.nD = (uint32_t)nD;
-        io.d_rng = ctx->b_rng.as<fe_grid_item>(); io.nR = (uint32_t)n_pending;
-        io.d_out = ctx->b_level_items.as<fe_encode_item>();
-        io.can_split = (T / 2 >= t_min) ? 1 : 0;
-        io.d_split = ctx->b_split.as<uint32_t>();
-        io.stat_level = level;
-        LevelPending lp;
-        FE_TRY(run_level_enqueue(ctx, io, *params, &lp));
-        size_t n_split = 0;
-        // one synchronisation per level: the level's summary and the split count come back together
-        FE_TRY(run_level_complete(ctx, io, *params, &lp, true, &n_split));
-        if (io.can_split) {
-            LAUNCH(ctx, k_quadtree_scatter, cdiv(n_pending, 256), 256, ctx->b_rng.as<fe_grid_item>(), io.d_out, io.d_split, ctx->b_scan.as<uint32_t>(),
-                   (uint32_t)n_pending, ctx->b_rng_next.as<fe_grid_item>(), ctx->b_items.as<fe_encode_item>() + offset);
-        } else {
-            FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_items.as<fe_encode_item>() + offset, io.d_out, n_pending * sizeof(fe_encode_item), cudaMemcpyDeviceToDevice, ctx->stream));
-        }
-        const size_t kept = n_pending - n_split;
-        ctx->stats.level_items[level] = kept;
-        if (ctx->host_out && kept && offset + kept <= ctx->host_cap && ctx->host_copied == offset) {
-            // the level's items are final: send them to the caller's buffer behind the next level's work
-            FE_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
-            FE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
-            FE_CUDA(ctx, cudaMemcpyAsync(ctx->host_out + offset, ctx->b_items.as<fe_encode_item>() + offset, kept * sizeof(fe_encode_item),
-                                         cudaMemcpyDeviceToHost, ctx->copy_stream));
-            ctx->host_copied = offset + kept;
-        }
-        offset += kept;
-        std::swap(ctx->b_rng, ctx->b_rng_next);
-        n_pending = 4 * n_split;
+    QuadJob* j = job_of(ctx);
+    *j = QuadJob{};
+    j->t_max = t_max; j->t_min = t_min; j->T = t_max;
+    j->n_pending = n_blocks;
+    j->params = *params;
+    ctx->n_items = 0;
+    return FE_OK;
+}
+
+static bool quad_finished(const QuadJob* j) { return !j->level_open && (j->T < j->t_min || j->n_pending == 0); }
+
+// first half of the current level: grids, search, winners -- nothing here waits for the device (tensor paths)
+static int quad_enqueue(fe_ctx* ctx) {
+    QuadJob* j = job_of(ctx);
+    if (quad_finished(j)) return FE_OK;
+    const uint32_t W = ctx->src.w, H = ctx->src.h, T = j->T, S = 2 * T;
+    const uint32_t dnx = W >= S ? W / T - 1 : 0, dny = H >= S ? H / T - 1 : 0;
+    const size_t nD = (size_t)dnx * dny, n_pending = j->n_pending;
+    LevelIO& io = j->io;
+    io = LevelIO{};
+    FE_TRY(make_geom(ctx, S, T, true, &io.g));
+    if (nD) {
+        FE_CUDA(ctx, ctx->b_dom.ensure(nD * sizeof(fe_grid_item)));
+        LAUNCH(ctx, k_uniform_grid, cdiv(nD, 256), 256, ctx->b_dom.as<fe_grid_item>(), dnx, (uint32_t)nD, S, T, 0u);
     }
-    ctx->n_items = offset;
-    if (n_out) *n_out = offset;
+    FE_CUDA(ctx, ctx->b_level_items.ensure(n_pending * sizeof(fe_encode_item)));
+    FE_CUDA(ctx, ctx->b_split.ensure(n_pending * 4 + 4));
+    io.d_dom = ctx->b_dom.as<fe_grid_item>(); io.nD = (uint32_t)nD;
+    io.d_rng = ctx->b_rng.as<fe_grid_item>(); io.nR = (uint32_t)n_pending;
+    io.d_out = ctx->b_level_items.as<fe_encode_item>();
+    io.can_split = (T / 2 >= j->t_min) ? 1 : 0;
+    io.d_split = ctx->b_split.as<uint32_t>();
+    io.stat_level = j->level;
+    FE_TRY(run_level_enqueue(ctx, io, j->params, &j->lp));
+    j->level_open = true;
+    return FE_OK;
+}
+
+// second half: ONE synchronisation (level summary + split count), then the children / the emitted items
+static int quad_complete(fe_ctx* ctx) {
+    QuadJob* j = job_of(ctx);
+    if (!j->level_open) return FE_OK;
+    const LevelIO& io = j->io;
+    const size_t n_pending = j->n_pending, offset = j->offset;
+    size_t n_split = 0;
+    FE_TRY(run_level_complete(ctx, io, j->params, &j->lp, true, &n_split));
+    if (io.can_split) {
+        LAUNCH(ctx, k_quadtree_scatter, cdiv(n_pending, 256), 256, ctx->b_rng.as<fe_grid_item>(), io.d_out, io.d_split, ctx->b_scan.as<uint32_t>(),
+               (uint32_t)n_pending, ctx->b_rng_next.as<fe_grid_item>(), ctx->b_items.as<fe_encode_item>() + offset);
+    } else {
+        FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_items.as<fe_encode_item>() + offset, io.d_out, n_pending * sizeof(fe_encode_item), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    const size_t kept = n_pending - n_split;
+    ctx->stats.level_items[j->level] = kept;
+    if (ctx->host_out && kept && offset + kept <= ctx->host_cap && ctx->host_copied == offset) {
+        // the level's items are final: send them to the caller's buffer behind the next level's work
+        FE_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
+        FE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+        FE_CUDA(ctx, cudaMemcpyAsync(ctx->host_out + offset, ctx->b_items.as<fe_encode_item>() + offset, kept * sizeof(fe_encode_item),
+                                     cudaMemcpyDeviceToHost, ctx->copy_stream));
+        ctx->host_copied = offset + kept;
+    }
+    j->offset = offset + kept;
+    std::swap(ctx->b_rng, ctx->b_rng_next);
+    j->n_pending = 4 * n_split;
+    j->T /= 2;
+    j->level += 1;
+    j->level_open = false;
+    ctx->n_items = j->offset;
+    return FE_OK;
+}
+
+extern "C" int fe_encode_quadtree_slice_device(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params, size_t first_block,
+                                               size_t n_blocks, size_t* n_out) {
+    if (!ctx) return FE_ERR_INVALID;
+    FE_TRY(quad_begin(ctx, t_max, t_min, params, first_block, n_blocks));
+    QuadJob* j = job_of(ctx);
+    while (!quad_finished(j)) {
+        FE_TRY(quad_enqueue(ctx));
+        FE_TRY(quad_complete(ctx));
+    }
+    if (n_out) *n_out = ctx->n_items;
+    return FE_OK;
+}
+
+// Batch mode (BASELINE config 5; the reference encodes one plane after the other, main.cpp:142-181,193-200): the images
+// alternate between two child contexts with their own streams and scratch.  A level is enqueued without waiting and
+// completed with one synchronisation, so while the host waits for image A's level, image B's level (and the H2D of its
+// pixels, the D2H of a finished list) is already queued on the other stream: the GPU never idles on the host.
+extern "C" int fe_encode_batch(fe_ctx* ctx, const uint8_t* const* images, size_t n_images, uint32_t width, uint32_t height, uint32_t stride,
+                               uint32_t t_max, uint32_t t_min, const fe_params* params, fe_encode_item* out, size_t cap_per_image, size_t* n_out) {
+    if (!ctx) return FE_ERR_INVALID;
+    if (!params || (!images && n_images) || (!out && n_images) || !n_out) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_batch: null argument");
+    if (!width || !height || stride < width) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_batch: zero size or stride < width");
+    for (int k = 0; k < 2; ++k)
+        if (!ctx->sub[k]) {
+            const int rc = fe_create(&ctx->sub[k], ctx->device, nullptr);
+            if (rc != FE_OK) return fe_fail(ctx, rc, "fe_encode_batch: %s", fe_last_error(nullptr));
+        }
+    size_t next = 0;
+    int image_of[2] = {-1, -1};
+    auto fail_from = [&](int k, int rc) { return fe_fail(ctx, rc, "fe_encode_batch (image %d): %s", image_of[k], ctx->sub[k]->err.c_str()); };
+    auto start_next = [&](int k) -> int {
+        image_of[k] = -1;
+        if (next >= n_images) return FE_OK;
+        fe_ctx* c = ctx->sub[k];
+        image_of[k] = (int)next;
+        if (!images[next]) { c->err = "null image"; return FE_ERR_INVALID; }
+        int rc = fe_set_image(c, images[next], width, height, stride);
+        ++next;
+        if (rc == FE_OK) rc = quad_begin(c, t_max, t_min, params, 0, (size_t)-1);
+        if (rc == FE_OK) rc = quad_enqueue(c);
+        return rc;
+    };
+    for (int k = 0; k < 2; ++k) {
+        const int rc = start_next(k);
+        if (rc != FE_OK) return fail_from(k, rc);
+    }
+    while (image_of[0] >= 0 || image_of[1] >= 0) {
+        for (int k = 0; k < 2; ++k) {
+            if (image_of[k] < 0) continue;
+            fe_ctx* c = ctx->sub[k];
+            int rc = quad_complete(c);
+            if (rc != FE_OK) return fail_from(k, rc);
+            if (!quad_finished(job_of(c))) {
+                rc = quad_enqueue(c);
+                if (rc != FE_OK) return fail_from(k, rc);
+                continue;
+            }
+            const size_t n = c->n_items, img = (size_t)image_of[k];
+            if (n > cap_per_image) return fe_fail(ctx, FE_ERR_CAPACITY, "fe_encode_batch: image %zu has %zu items, capacity %zu", img, n, cap_per_image);
+            if (n) FE_CUDA(ctx, cudaMemcpyAsync(out + img * cap_per_image, c->b_items.p, n * sizeof(fe_encode_item), cudaMemcpyDeviceToHost, c->stream));
+            n_out[img] = n;
+            rc = start_next(k);        // the child's stream orders the copy before the next image's kernels touch b_items
+            if (rc != FE_OK) return fail_from(k, rc);
+        }
+    }
+    for (int k = 0; k < 2; ++k) {
+        FE_CUDA(ctx, cudaStreamSynchronize(ctx->sub[k]->stream));
+        ctx->stats.kernel_launches += ctx->sub[k]->stats.kernel_launches;
+        ctx->stats.matches += ctx->sub[k]->stats.matches;
+        ctx->stats.evaluated += ctx->sub[k]->stats.evaluated;
+        ctx->stats.umma_levels += ctx->sub[k]->stats.umma_levels;
+        ctx->stats.exact_levels += ctx->sub[k]->stats.exact_levels;
+        fe_stats_reset(ctx->sub[k]);
+    }
     return FE_OK;
 }
 

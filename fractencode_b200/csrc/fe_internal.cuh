@@ -96,6 +96,8 @@ struct fe_ctx {
     // level position, and the per-level summary the host reads back (device record + pinned host copy)
     DevBuf b_plan, b_ctl, b_list[2], b_itemrec, b_posb, b_summary;
     void* h_summary = nullptr;
+    void* job = nullptr;            // QuadJob (fe_api.cu): the quadtree encode in progress
+    fe_ctx* sub[2] = {nullptr, nullptr};   // fe_encode_batch: two child contexts (own stream and scratch) the images alternate between
     int n_sm = 148;                 // multiProcessorCount of the device
     // slices the last level of this kind (f16 / i8) and block size needed: how many the next one gets enqueued up front
     struct SliceHint { uint8_t known = 0, slices = 0, with_min = 0; } hint[2][8];

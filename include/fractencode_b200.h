@@ -155,6 +155,13 @@ int fe_encode_quadtree_device(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const
  * give exactly the transform list of fe_encode_quadtree (range blocks are independent). */
 int fe_encode_quadtree_slice_device(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_params* params,
                                     size_t first_block, size_t n_blocks, size_t* n_out);
+/* Batch mode (BASELINE config 5): n_images planes of the same size, each encoded like fe_encode_quadtree does -- what the
+ * reference does plane after plane (main.cpp:142-181; the three planes of --color, main.cpp:193-200).  Image i's items
+ * go to out[i * cap_per_image ...], its count to n_out[i].  The images are pipelined over two internal streams (the upload
+ * and the levels of one overlap the other's), so pinned host buffers pay; results are identical to n single calls. */
+int fe_encode_batch(fe_ctx* ctx, const uint8_t* const* images, size_t n_images, uint32_t width, uint32_t height, uint32_t stride,
+                    uint32_t t_max, uint32_t t_min, const fe_params* params, fe_encode_item* out, size_t cap_per_image,
+                    size_t* n_out);
 int fe_fetch_items(fe_ctx* ctx, fe_encode_item* out, size_t cap, size_t* n_out);
 /* Device pointer to the last result list (n items of 64 bytes), valid until the next encode. */
 const void* fe_device_items(const fe_ctx* ctx, size_t* n_out);

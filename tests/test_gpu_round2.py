@@ -155,3 +155,44 @@ def test_device_resident_pack_matches_the_host_pack(ctx, fo):
     assert (dec == odec).all() and it == oit and rms == orms
     with pytest.raises(fb.FractencodeError):
         ctx.pack_items_device(32, mm.data_ptr(), packed.data_ptr(), n - 1)      # capacity
+
+
+def test_batch_entry_point_small_images_vs_oracle(ctx, fo):
+    """fe_encode_batch == the oracle's quadtree on every image (whole lists), incl. an odd batch size and a batch of one."""
+    import fractencode_b200 as fb
+    p = fb.Params(8.0, -1.0, True)
+    for n in (1, 5):
+        imgs = [fo.synth_image(256, 256, 100 + i, i % 2) for i in range(n)]
+        lists = ctx.encode_batch(imgs, 32, 4, p)
+        assert len(lists) == n
+        for img, got in zip(imgs, lists):
+            want, _ = fo.encode_quadtree(img, 32, 4, fo.params(8.0, -1.0, True))
+            assert_items_equal(got, want)
+
+
+def test_batch_of_16_images_1024(ctx, fo):
+    """BASELINE config 5 in shape: sixteen 1024^2 images, 8x8 grid + quadtree split to 4x4, through fe_encode_batch.
+    Every list equals the single-image call; image 0 is compared WHOLE with the oracle, the others on a sample."""
+    import fractencode_b200 as fb
+    from oracle import pyoracle as po
+    thr = 25.0
+    p = fb.Params(thr)
+    imgs = [fo.synth_image(1024, 1024, 1234 + i, 0) for i in range(16)]
+    lists = ctx.encode_batch(imgs, 8, 4, p)
+    assert len(lists) == 16
+    rs = np.random.default_rng(3)
+    for i, (img, got) in enumerate(zip(imgs, lists)):
+        ctx.set_image(img)
+        single, _ = ctx.encode_quadtree(8, 4, p)
+        assert po.sort_items(got).tobytes() == po.sort_items(single).tobytes(), i
+        if i == 0:
+            want, _ = fo.encode_quadtree(img, 8, 4, fo.params(thr))
+            assert_items_equal(got, want, "image 0 whole")
+        else:
+            for T in (8, 4):
+                sel = got[got["w"] == T]
+                pick = sel[rs.choice(len(sel), size=min(24, len(sel)), replace=False)]
+                dom = fo.uniform_grid(1024, 1024, 2 * T, T)
+                rng = np.zeros(len(pick), dom.dtype)
+                rng["x"], rng["y"], rng["w"], rng["h"], rng["bin"] = pick["x"], pick["y"], T, T, -1
+                assert_items_equal(pick, fo.encode_level(img, img, dom, rng, fo.params(thr)), "image %d T=%d" % (i, T))
