@@ -75,7 +75,7 @@ def build_library() -> str:
 _LIB = None
 EXPORTS = [
     "fe_abi_version", "fe_create", "fe_destroy", "fe_last_error", "fe_set_image", "fe_set_images", "fe_set_image_device",
-    "fe_classify", "fe_encode_level", "fe_encode_quadtree", "fe_encode_quadtree_device", "fe_encode_quadtree_slice_device", "fe_fetch_items", "fe_device_items", "fe_encode_batch",
+    "fe_classify", "fe_encode_level", "fe_encode_quadtree", "fe_encode_quadtree_device", "fe_encode_quadtree_slice_device", "fe_fetch_items", "fe_device_items", "fe_encode_batch", "fe_encode_planes", "fe_rgb_to_yuv420", "fe_yuv420_to_rgb",
     "fe_decode", "fe_copy_items", "fe_quantize", "fe_pack_items", "fe_unpack_items", "fe_items_minmax_device", "fe_pack_items_device", "fe_pack_errors", "fe_get_stats", "fe_stats_reset", "fe_synchronize", "fe_set_synthetic_image", "fe_get_image", "fe_plan_threshold",
 ]
 
@@ -106,6 +106,9 @@ def load_library():
         "fe_encode_quadtree_slice_device": (i32, [vp, u32, u32, C.POINTER(Params), sz, sz, C.POINTER(sz)]),
         "fe_fetch_items": (i32, [vp, vp, sz, C.POINTER(sz)]),
         "fe_encode_batch": (i32, [vp, vp, sz, u32, u32, u32, u32, u32, C.POINTER(Params), vp, sz, vp]),
+        "fe_encode_planes": (i32, [vp, vp, sz, vp, vp, vp, u32, u32, C.POINTER(Params), vp, vp, vp, vp]),
+        "fe_rgb_to_yuv420": (i32, [vp, vp, u32, u32, u32, vp, u32, vp, u32, vp, u32, i32]),
+        "fe_yuv420_to_rgb": (i32, [vp, vp, u32, u32, u32, vp, u32, vp, u32, vp, u32, i32]),
         "fe_device_items": (vp, [vp, C.POINTER(sz)]),
         "fe_decode": (i32, [vp, vp, sz, vp, u32, u32, u32, i32, dbl, i32, C.POINTER(C.c_int), C.POINTER(dbl)]),
         "fe_copy_items": (i32, [vp, vp, vp, u32, u32, u32, vp, sz, i32]),
@@ -254,6 +257,38 @@ class Context:
         counts = (C.c_size_t * n)()
         self._check(self.lib.fe_encode_batch(self.h, ptrs, n, W, H, W, t_max, t_min, C.byref(params), out.ctypes.data, cap, counts))
         return [out[i * cap: i * cap + counts[i]] for i in range(n)]
+
+    def encode_planes(self, planes, t_max: int, t_min: int, params: Params):
+        """Quadtree-encode planes of different sizes (the colour path: Y and the two half-size chroma planes)."""
+        pl = [np.ascontiguousarray(p, np.uint8) for p in planes]
+        n = len(pl)
+        caps = [(p.shape[1] // t_min) * (p.shape[0] // t_min) for p in pl]
+        offs = np.concatenate([[0], np.cumsum(caps)[:-1]]).astype(np.uint64)
+        out = np.zeros(int(sum(caps)), ENCODE_ITEM)
+        ptrs = (C.c_void_p * n)(*[p.ctypes.data for p in pl])
+        ws = np.array([p.shape[1] for p in pl], np.uint32)
+        hs = np.array([p.shape[0] for p in pl], np.uint32)
+        capsa = np.array(caps, np.uint64)
+        counts = (C.c_size_t * n)()
+        self._check(self.lib.fe_encode_planes(self.h, ptrs, n, ws.ctypes.data, hs.ctypes.data, ws.ctypes.data, t_max, t_min, C.byref(params),
+                                              out.ctypes.data, offs.ctypes.data, capsa.ctypes.data, counts))
+        return [out[int(offs[i]): int(offs[i]) + counts[i]] for i in range(n)]
+
+    def rgb_to_yuv420(self, rgb: np.ndarray, fma: bool = False):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        H, W, _ = rgb.shape
+        y = np.zeros((H, W), np.uint8)
+        u = np.zeros((H // 2, W // 2), np.uint8)
+        v = np.zeros_like(u)
+        self._check(self.lib.fe_rgb_to_yuv420(self.h, rgb.ctypes.data, W, H, 3 * W, y.ctypes.data, W, u.ctypes.data, W // 2, v.ctypes.data, W // 2, int(fma)))
+        return y, u, v
+
+    def yuv420_to_rgb(self, y: np.ndarray, u: np.ndarray, v: np.ndarray, fma: bool = False) -> np.ndarray:
+        y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+        H, W = y.shape
+        rgb = np.zeros((H, W, 3), np.uint8)
+        self._check(self.lib.fe_yuv420_to_rgb(self.h, y.ctypes.data, W, H, W, u.ctypes.data, W // 2, v.ctypes.data, W // 2, rgb.ctypes.data, W, int(fma)))
+        return rgb
 
     def fetch_items(self, out: np.ndarray | None = None) -> np.ndarray:
         n = C.c_size_t(0)

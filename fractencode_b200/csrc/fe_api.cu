@@ -882,26 +882,29 @@ extern "C" int fe_encode_quadtree_slice_device(fe_ctx* ctx, uint32_t t_max, uint
 // alternate between two child contexts with their own streams and scratch.  A level is enqueued without waiting and
 // completed with one synchronisation, so while the host waits for image A's level, image B's level (and the H2D of its
 // pixels, the D2H of a finished list) is already queued on the other stream: the GPU never idles on the host.
-extern "C" int fe_encode_batch(fe_ctx* ctx, const uint8_t* const* images, size_t n_images, uint32_t width, uint32_t height, uint32_t stride,
-                               uint32_t t_max, uint32_t t_min, const fe_params* params, fe_encode_item* out, size_t cap_per_image, size_t* n_out) {
+extern "C" int fe_encode_planes(fe_ctx* ctx, const uint8_t* const* images, size_t n_images, const uint32_t* widths, const uint32_t* heights,
+                                const uint32_t* strides, uint32_t t_max, uint32_t t_min, const fe_params* params, fe_encode_item* out,
+                                const size_t* out_offsets, const size_t* caps, size_t* n_out) {
     if (!ctx) return FE_ERR_INVALID;
-    if (!params || (!images && n_images) || (!out && n_images) || !n_out) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_batch: null argument");
-    if (!width || !height || stride < width) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_batch: zero size or stride < width");
+    if (!params || (n_images && (!images || !out || !widths || !heights || !strides || !out_offsets || !caps)) || !n_out)
+        return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_planes: null argument");
+    for (size_t i = 0; i < n_images; ++i)
+        if (!widths[i] || !heights[i] || strides[i] < widths[i]) return fe_fail(ctx, FE_ERR_INVALID, "fe_encode_planes: plane %zu: zero size or stride < width", i);
     for (int k = 0; k < 2; ++k)
         if (!ctx->sub[k]) {
             const int rc = fe_create(&ctx->sub[k], ctx->device, nullptr);
-            if (rc != FE_OK) return fe_fail(ctx, rc, "fe_encode_batch: %s", fe_last_error(nullptr));
+            if (rc != FE_OK) return fe_fail(ctx, rc, "fe_encode_planes: %s", fe_last_error(nullptr));
         }
     size_t next = 0;
     int image_of[2] = {-1, -1};
-    auto fail_from = [&](int k, int rc) { return fe_fail(ctx, rc, "fe_encode_batch (image %d): %s", image_of[k], ctx->sub[k]->err.c_str()); };
+    auto fail_from = [&](int k, int rc) { return fe_fail(ctx, rc, "fe_encode_planes (plane %d): %s", image_of[k], ctx->sub[k]->err.c_str()); };
     auto start_next = [&](int k) -> int {
         image_of[k] = -1;
         if (next >= n_images) return FE_OK;
         fe_ctx* c = ctx->sub[k];
         image_of[k] = (int)next;
         if (!images[next]) { c->err = "null image"; return FE_ERR_INVALID; }
-        int rc = fe_set_image(c, images[next], width, height, stride);
+        int rc = fe_set_image(c, images[next], widths[next], heights[next], strides[next]);
         ++next;
         if (rc == FE_OK) rc = quad_begin(c, t_max, t_min, params, 0, (size_t)-1);
         if (rc == FE_OK) rc = quad_enqueue(c);
@@ -923,8 +926,8 @@ extern "C" int fe_encode_batch(fe_ctx* ctx, const uint8_t* const* images, size_t
                 continue;
             }
             const size_t n = c->n_items, img = (size_t)image_of[k];
-            if (n > cap_per_image) return fe_fail(ctx, FE_ERR_CAPACITY, "fe_encode_batch: image %zu has %zu items, capacity %zu", img, n, cap_per_image);
-            if (n) FE_CUDA(ctx, cudaMemcpyAsync(out + img * cap_per_image, c->b_items.p, n * sizeof(fe_encode_item), cudaMemcpyDeviceToHost, c->stream));
+            if (n > caps[img]) return fe_fail(ctx, FE_ERR_CAPACITY, "fe_encode_planes: plane %zu has %zu items, capacity %zu", img, n, caps[img]);
+            if (n) FE_CUDA(ctx, cudaMemcpyAsync(out + out_offsets[img], c->b_items.p, n * sizeof(fe_encode_item), cudaMemcpyDeviceToHost, c->stream));
             n_out[img] = n;
             rc = start_next(k);        // the child's stream orders the copy before the next image's kernels touch b_items
             if (rc != FE_OK) return fail_from(k, rc);
@@ -939,6 +942,61 @@ extern "C" int fe_encode_batch(fe_ctx* ctx, const uint8_t* const* images, size_t
         ctx->stats.exact_levels += ctx->sub[k]->stats.exact_levels;
         fe_stats_reset(ctx->sub[k]);
     }
+    return FE_OK;
+}
+
+extern "C" int fe_encode_batch(fe_ctx* ctx, const uint8_t* const* images, size_t n_images, uint32_t width, uint32_t height, uint32_t stride,
+                               uint32_t t_max, uint32_t t_min, const fe_params* params, fe_encode_item* out, size_t cap_per_image, size_t* n_out) {
+    if (!ctx) return FE_ERR_INVALID;
+    std::vector<uint32_t> w(n_images, width), h(n_images, height), st(n_images, stride);
+    std::vector<size_t> off(n_images), caps(n_images, cap_per_image);
+    for (size_t i = 0; i < n_images; ++i) off[i] = i * cap_per_image;
+    return fe_encode_planes(ctx, images, n_images, w.data(), h.data(), st.data(), t_max, t_min, params, out, off.data(), caps.data(), n_out);
+}
+
+// ImageIO::rgb2yuv / yuv2rgb (image/ImageIO.cpp:40-84) on host buffers through the device.
+extern "C" int fe_rgb_to_yuv420(fe_ctx* ctx, const uint8_t* rgb, uint32_t width, uint32_t height, uint32_t rgb_stride_bytes, uint8_t* y, uint32_t y_stride,
+                                uint8_t* u, uint32_t u_stride, uint8_t* v, uint32_t v_stride, int fma) {
+    if (!ctx || !rgb || !y || !u || !v) return fe_fail(ctx, FE_ERR_INVALID, "fe_rgb_to_yuv420: null argument");
+    if (!width || !height || (width & 1) || (height & 1)) return fe_fail(ctx, FE_ERR_INVALID, "fe_rgb_to_yuv420: width and height must be even and non-zero");
+    if (rgb_stride_bytes < 3 * width || y_stride < width || u_stride < width / 2 || v_stride < width / 2) return fe_fail(ctx, FE_ERR_INVALID, "fe_rgb_to_yuv420: stride too small");
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nrgb = (size_t)rgb_stride_bytes * height, ny = (size_t)width * height, nc = ny / 4;
+    FE_CUDA(ctx, ctx->b_dec_a.ensure(nrgb + 64));
+    FE_CUDA(ctx, ctx->b_dec_b.ensure(ny + 2 * nc + 64));
+    uint8_t* d_y = ctx->b_dec_b.as<uint8_t>();
+    uint8_t* d_u = d_y + ny;
+    uint8_t* d_v = d_u + nc;
+    FE_CUDA(ctx, cudaMemcpyAsync(ctx->b_dec_a.p, rgb, nrgb, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 block(32, 8), grid(cdiv(width / 2, 32), cdiv(height / 2, 8));
+    LAUNCH(ctx, k_rgb2yuv420, grid, block, ctx->b_dec_a.as<uint8_t>(), width, height, rgb_stride_bytes, d_y, width, d_u, width / 2, d_v, width / 2, fma);
+    FE_CUDA(ctx, cudaMemcpy2DAsync(y, y_stride, d_y, width, width, height, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaMemcpy2DAsync(u, u_stride, d_u, width / 2, width / 2, height / 2, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaMemcpy2DAsync(v, v_stride, d_v, width / 2, width / 2, height / 2, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FE_OK;
+}
+
+extern "C" int fe_yuv420_to_rgb(fe_ctx* ctx, const uint8_t* y, uint32_t width, uint32_t height, uint32_t y_stride, const uint8_t* u, uint32_t u_stride,
+                                const uint8_t* v, uint32_t v_stride, uint8_t* rgb, uint32_t rgb_stride_pixels, int fma) {
+    if (!ctx || !rgb || !y || !u || !v) return fe_fail(ctx, FE_ERR_INVALID, "fe_yuv420_to_rgb: null argument");
+    if (!width || !height || (width & 1) || (height & 1)) return fe_fail(ctx, FE_ERR_INVALID, "fe_yuv420_to_rgb: width and height must be even and non-zero");
+    if (rgb_stride_pixels < width || y_stride < width || u_stride < width / 2 || v_stride < width / 2) return fe_fail(ctx, FE_ERR_INVALID, "fe_yuv420_to_rgb: stride too small");
+    FE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nrgb = (size_t)rgb_stride_pixels * 3 * height, ny = (size_t)width * height, nc = ny / 4;
+    FE_CUDA(ctx, ctx->b_dec_a.ensure(nrgb + 64));
+    FE_CUDA(ctx, ctx->b_dec_b.ensure(ny + 2 * nc + 64));
+    uint8_t* d_y = ctx->b_dec_b.as<uint8_t>();
+    uint8_t* d_u = d_y + ny;
+    uint8_t* d_v = d_u + nc;
+    FE_CUDA(ctx, cudaMemcpy2DAsync(d_y, width, y, y_stride, width, height, cudaMemcpyHostToDevice, ctx->stream));
+    FE_CUDA(ctx, cudaMemcpy2DAsync(d_u, width / 2, u, u_stride, width / 2, height / 2, cudaMemcpyHostToDevice, ctx->stream));
+    FE_CUDA(ctx, cudaMemcpy2DAsync(d_v, width / 2, v, v_stride, width / 2, height / 2, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 block(32, 8), grid(cdiv(width, 32), cdiv(height, 8));
+    LAUNCH(ctx, k_yuv420_to_rgb, grid, block, d_y, width, height, width, d_u, width / 2, d_v, width / 2, ctx->b_dec_a.as<uint8_t>(), rgb_stride_pixels, fma);
+    // only the pixels of every row go back: the caller's row padding is left alone
+    FE_CUDA(ctx, cudaMemcpy2DAsync(rgb, (size_t)rgb_stride_pixels * 3, ctx->b_dec_a.p, (size_t)rgb_stride_pixels * 3, (size_t)width * 3, height, cudaMemcpyDeviceToHost, ctx->stream));
+    FE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FE_OK;
 }
 

@@ -1012,6 +1012,52 @@ __global__ void k_unpack(const unsigned long long* __restrict__ in, uint32_t n, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// colour path: ImageIO::rgb2yuv / yuv2rgb (image/ImageIO.cpp:40-57, 68-84).  fp64 with explicit roundings; fma = the contraction
+// GCC applies under -march=native (middle product plain, first and last fused onto it: oracle/frac_oracle.c:fo_rgb2yuv).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t clamp_u8_dev(double x) { return x < 0.0 ? 0 : (x > 255.0 ? 255 : (uint8_t)x); }
+__device__ __forceinline__ double mix3(double c0, double r, double c1, double g, double c2, double b, int fma) {
+    return fma ? __fma_rn(c2, b, __fma_rn(c0, r, __dmul_rn(c1, g))) : __dadd_rn(__dadd_rn(__dmul_rn(c0, r), __dmul_rn(c1, g)), __dmul_rn(c2, b));
+}
+// one thread per 2x2 cell: four luma values; the chroma of the cell is that of its LAST pixel (odd x, odd y), as the reference's
+// overwriting loop leaves it
+__global__ void k_rgb2yuv420(const uint8_t* __restrict__ rgb, uint32_t w, uint32_t h, uint32_t stride, uint8_t* __restrict__ yb, uint32_t ys,
+                             uint8_t* __restrict__ ub, uint32_t us, uint8_t* __restrict__ vb, uint32_t vs, int fma) {
+    const uint32_t cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (cx >= w / 2 || cy >= h / 2) return;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const uint32_t x = 2 * cx + dx, y = 2 * cy + dy;
+            const uint8_t* p = rgb + (size_t)y * stride + 3 * (size_t)x;
+            const double r = p[0], g = p[1], b = p[2];
+            yb[(size_t)y * ys + x] = clamp_u8_dev(mix3(0.299, r, 0.587, g, 0.114, b, fma));
+            if (dx && dy) {
+                ub[(size_t)cy * us + cx] = clamp_u8_dev(__dadd_rn(mix3(-0.169, r, -0.331, g, 0.499, b, fma), 128.0));
+                vb[(size_t)cy * vs + cx] = clamp_u8_dev(__dadd_rn(mix3(0.499, r, -0.418, g, -0.0813, b, fma), 128.0));
+            }
+        }
+}
+__global__ void k_yuv420_to_rgb(const uint8_t* __restrict__ yb, uint32_t w, uint32_t h, uint32_t ys, const uint8_t* __restrict__ ub, uint32_t us,
+                                const uint8_t* __restrict__ vb, uint32_t vs, uint8_t* __restrict__ rgb, uint32_t rgb_stride, int fma) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const double yp = yb[(size_t)y * ys + x], du = __dsub_rn((double)ub[(size_t)(y / 2) * us + x / 2], 128.0),
+                 dv = __dsub_rn((double)vb[(size_t)(y / 2) * vs + x / 2], 128.0);
+    uint8_t* p = rgb + 3 * ((size_t)y * rgb_stride + x);
+    if (fma) {
+        p[0] = clamp_u8_dev(__fma_rn(1.402, dv, yp));
+        p[1] = clamp_u8_dev(__fma_rn(-0.714, dv, __fma_rn(-0.344, du, yp)));
+        p[2] = clamp_u8_dev(__fma_rn(1.772, du, yp));
+    } else {
+        p[0] = clamp_u8_dev(__dadd_rn(yp, __dmul_rn(1.402, dv)));
+        p[1] = clamp_u8_dev(__dsub_rn(__dsub_rn(yp, __dmul_rn(0.344, du)), __dmul_rn(0.714, dv)));
+        p[2] = clamp_u8_dev(__dadd_rn(yp, __dmul_rn(1.772, du)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // synthetic images: same integer formulas as oracle/frac_oracle.c:fo_synth_image
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {

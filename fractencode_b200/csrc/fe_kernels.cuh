@@ -61,6 +61,10 @@ __global__ void k_copy_plane_if_running(const uint4* src, uint4* dst, size_t n16
 __global__ void k_minmax(const fe_encode_item* items, uint32_t n, unsigned long long* mm);
 __global__ void k_quantize(const fe_encode_item* items, uint32_t n, double min_s, double max_s, double min_o, double max_o,
                            int bits_s, int bits_o, uint32_t* qs, uint32_t* qo);
+__global__ void k_rgb2yuv420(const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t stride, uint8_t* yb, uint32_t ys, uint8_t* ub, uint32_t us,
+                             uint8_t* vb, uint32_t vs, int fma);
+__global__ void k_yuv420_to_rgb(const uint8_t* yb, uint32_t w, uint32_t h, uint32_t ys, const uint8_t* ub, uint32_t us, const uint8_t* vb, uint32_t vs,
+                                uint8_t* rgb, uint32_t rgb_stride, int fma);
 __global__ void k_synth(uint8_t* out, uint32_t w, uint32_t h, uint32_t stride, unsigned long long seed, int kind);
 __global__ void k_pack(const fe_encode_item* items, uint32_t n, uint32_t t_max, const double* mm, int bits_s, int bits_o,
                        unsigned long long* out, uint32_t* bad);

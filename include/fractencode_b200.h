@@ -162,6 +162,19 @@ int fe_encode_quadtree_slice_device(fe_ctx* ctx, uint32_t t_max, uint32_t t_min,
 int fe_encode_batch(fe_ctx* ctx, const uint8_t* const* images, size_t n_images, uint32_t width, uint32_t height, uint32_t stride,
                     uint32_t t_max, uint32_t t_min, const fe_params* params, fe_encode_item* out, size_t cap_per_image,
                     size_t* n_out);
+/* The same for planes of DIFFERENT sizes -- the colour path: main.cpp:193-200 encodes the luma plane and the two half-size chroma
+ * planes of a YUV 4:2:0 image with the same parameters.  Plane i's items go to out[out_offsets[i] ...] (capacity caps[i]). */
+int fe_encode_planes(fe_ctx* ctx, const uint8_t* const* planes, size_t n_planes, const uint32_t* widths, const uint32_t* heights,
+                     const uint32_t* strides, uint32_t t_max, uint32_t t_min, const fe_params* params, fe_encode_item* out,
+                     const size_t* out_offsets, const size_t* caps, size_t* n_out);
+/* Replaces: ImageIO::rgb2yuv / ImageIO::yuv2rgb (image/ImageIO.cpp:40-57, 68-84): interleaved 8-bit RGB <-> Y (width x height)
+ * and U, V (width/2 x height/2; the chroma of a 2x2 cell is that of its last pixel, as the reference's loop leaves it).  Host
+ * buffers; width and height even.  rgb_stride_bytes = bytes per RGB row (rgb2yuv indexes x*3 + y*stride); rgb_stride_pixels =
+ * pixels per RGB row (yuv2rgb indexes 3*(x + y*stride)) -- the reference's own two conventions.  fma as in fe_params. */
+int fe_rgb_to_yuv420(fe_ctx* ctx, const uint8_t* rgb, uint32_t width, uint32_t height, uint32_t rgb_stride_bytes, uint8_t* y,
+                     uint32_t y_stride, uint8_t* u, uint32_t u_stride, uint8_t* v, uint32_t v_stride, int fma);
+int fe_yuv420_to_rgb(fe_ctx* ctx, const uint8_t* y, uint32_t width, uint32_t height, uint32_t y_stride, const uint8_t* u,
+                     uint32_t u_stride, const uint8_t* v, uint32_t v_stride, uint8_t* rgb, uint32_t rgb_stride_pixels, int fma);
 int fe_fetch_items(fe_ctx* ctx, fe_encode_item* out, size_t cap, size_t* n_out);
 /* Device pointer to the last result list (n items of 64 bytes), valid until the next encode. */
 const void* fe_device_items(const fe_ctx* ctx, size_t* n_out);

@@ -449,3 +449,49 @@ void fo_synth_image(uint8_t* out, uint32_t w, uint32_t h, uint32_t stride, uint6
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * colour path: ImageIO::rgb2yuv (image/ImageIO.cpp:40-57) and yuv2rgb (:68-84); main.cpp:193-200 encodes the three planes.
+ * Chroma is "subsampled" by overwriting: the last pixel of every 2x2 cell (odd x, odd y) wins.
+ * ------------------------------------------------------------------------------------------------ */
+static uint8_t clamp_u8(double x) { return x < 0.0 ? 0 : x > 255 ? 255 : (uint8_t)x; }   /* ImageIO.cpp:11-13 */
+
+void fo_rgb2yuv(const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t stride, uint8_t* yb, uint32_t ys, uint8_t* ub, uint32_t us, uint8_t* vb,
+                uint32_t vs, int use_fma) {
+    for (size_t y = 0; y < h; ++y)
+        for (size_t x = 0; x < w; ++x) {
+            const double r = rgb[x * 3 + y * stride + 0], g = rgb[x * 3 + y * stride + 1], b = rgb[x * 3 + y * stride + 2];
+            double yp, up, vp;
+            if (use_fma) {   /* what GCC -O2 -march=x86-64-v3 emits for a*r + b*g + c*b: the middle product stays a product, the first
+                                and the last are fused onto it (checked against the compiled reference on every input that differs) */
+                yp = fma(0.114, b, fma(0.299, r, 0.587 * g));
+                up = fma(0.499, b, fma(-0.169, r, -0.331 * g)) + 128;
+                vp = fma(-0.0813, b, fma(0.499, r, -0.418 * g)) + 128;
+            } else {
+                yp = 0.299 * r + 0.587 * g + 0.114 * b;
+                up = -0.169 * r - 0.331 * g + 0.499 * b + 128;
+                vp = 0.499 * r - 0.418 * g - 0.0813 * b + 128;
+            }
+            yb[x + y * ys] = clamp_u8(yp);
+            ub[(x / 2) + (y / 2) * us] = clamp_u8(up);
+            vb[(x / 2) + (y / 2) * vs] = clamp_u8(vp);
+        }
+}
+
+void fo_yuv2rgb(const uint8_t* yb, uint32_t w, uint32_t h, uint32_t ys, const uint8_t* ub, uint32_t us, const uint8_t* vb, uint32_t vs,
+                uint8_t* rgb, uint32_t rgb_stride, int use_fma) {
+    for (size_t y = 0; y < h; ++y)
+        for (size_t x = 0; x < w; ++x) {
+            uint8_t* p = rgb + (x * 3 + y * rgb_stride * 3);
+            const double yp = yb[x + y * ys], up = ub[(x / 2) + (y / 2) * us], vp = vb[(x / 2) + (y / 2) * vs];
+            if (use_fma) {
+                p[0] = clamp_u8(fma(1.402, vp - 128, yp));
+                p[1] = clamp_u8(fma(-0.714, vp - 128, fma(-0.344, up - 128, yp)));
+                p[2] = clamp_u8(fma(1.772, up - 128, yp));
+            } else {
+                p[0] = clamp_u8(yp + 1.402 * (vp - 128));
+                p[1] = clamp_u8(yp - 0.344 * (up - 128) - 0.714 * (vp - 128));
+                p[2] = clamp_u8(yp + 1.772 * (up - 128));
+            }
+        }
+}

@@ -125,6 +125,13 @@ double fo_dequantize(uint64_t q, double vmin, double vmax, int bits);
 
 /* Synthetic images of SURVEY 8d (ours; identical generator in the product's bench). */
 void fo_synth_image(uint8_t* out, uint32_t w, uint32_t h, uint32_t stride, uint64_t seed, int kind);
+/* image/ImageIO.cpp:40-57 and :68-84.  `stride` of rgb2yuv is in BYTES per row (the reference indexes x*3 + y*stride);
+ * `rgb_stride` of yuv2rgb is in PIXELS per row (the reference indexes x*3 + y*rgbStride*3).  fma: the contraction GCC applies
+ * under -march=native. */
+void fo_rgb2yuv(const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t stride, uint8_t* y, uint32_t ys, uint8_t* u, uint32_t us, uint8_t* v,
+                uint32_t vs, int fma);
+void fo_yuv2rgb(const uint8_t* y, uint32_t w, uint32_t h, uint32_t ys, const uint8_t* u, uint32_t us, const uint8_t* v, uint32_t vs,
+                uint8_t* rgb, uint32_t rgb_stride, int fma);
 
 int fo_hardware_threads(void);
 const char* fo_version(void);

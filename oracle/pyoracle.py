@@ -66,6 +66,8 @@ class Oracle:
         self._sig("decode", None, [vp, sz, vp, u32, u32, u32, i32, dbl, i32, C.POINTER(C.c_int), C.POINTER(C.c_double)])
         self._sig("quantize", C.c_uint64, [dbl, dbl, dbl, i32])
         self._sig("dequantize", dbl, [C.c_uint64, dbl, dbl, i32])
+        self._sig("rgb2yuv", None, [vp, u32, u32, u32, vp, u32, vp, u32, vp, u32, i32])
+        self._sig("yuv2rgb", None, [vp, u32, u32, u32, vp, u32, vp, u32, vp, u32, i32])
         self._sig("hardware_threads", i32, [])
         self._sig("version", C.c_char_p, [])
         if prefix == "fo_":
@@ -156,6 +158,23 @@ class Oracle:
         it, rms = C.c_int(0), C.c_double(0)
         self._decode(items.ctypes.data, len(items), tgt.ctypes.data, W, H, stride, max_iters, eps, int(fma), C.byref(it), C.byref(rms))
         return tgt[:, :W], it.value, rms.value
+
+    def rgb2yuv(self, rgb: np.ndarray, fma=False):
+        """[H, W, 3] uint8 -> (Y [H, W], U, V [ceil(H/2), ceil(W/2)]) like ImageIO::rgb2yuv (tightly packed planes)."""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        H, W, _ = rgb.shape
+        y = np.zeros((H, W), np.uint8)
+        u = np.zeros(((H + 1) // 2, (W + 1) // 2), np.uint8)
+        v = np.zeros_like(u)
+        self._rgb2yuv(rgb.ctypes.data, W, H, W * 3, y.ctypes.data, W, u.ctypes.data, u.shape[1], v.ctypes.data, v.shape[1], int(fma))
+        return y, u, v
+
+    def yuv2rgb(self, y: np.ndarray, u: np.ndarray, v: np.ndarray, fma=False) -> np.ndarray:
+        H, W = y.shape
+        y, u, v = (np.ascontiguousarray(a, np.uint8) for a in (y, u, v))
+        rgb = np.zeros((H, W, 3), np.uint8)
+        self._yuv2rgb(y.ctypes.data, W, H, W, u.ctypes.data, u.shape[1], v.ctypes.data, v.shape[1], rgb.ctypes.data, W, int(fma))
+        return rgb
 
     def quantize(self, v, vmin, vmax, bits):
         return self._quantize(v, vmin, vmax, bits)

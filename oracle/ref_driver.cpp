@@ -321,4 +321,18 @@ int fr_load_luma(const char* path, uint8_t* out, size_t cap, uint32_t* w, uint32
     return 0;
 }
 
+/* ImageIO::rgb2yuv / yuv2rgb (image/ImageIO.cpp:40-84) on caller buffers: the colour path of main.cpp:193-200. */
+void fr_rgb2yuv(const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t stride, uint8_t* y, uint32_t ys, uint8_t* u, uint32_t us, uint8_t* v,
+                uint32_t vs, int fma) {
+    (void)fma; /* decided by this library's build flags */
+    ImageIO::rgb2yuv({rgb, (std::ptrdiff_t)((size_t)stride * h)}, w, h, stride, {y, (std::ptrdiff_t)((size_t)ys * h)}, ys,
+                     {u, (std::ptrdiff_t)((size_t)us * ((h + 1) / 2))}, us, {v, (std::ptrdiff_t)((size_t)vs * ((h + 1) / 2))}, vs);
+}
+void fr_yuv2rgb(const uint8_t* y, uint32_t w, uint32_t h, uint32_t ys, const uint8_t* u, uint32_t us, const uint8_t* v, uint32_t vs,
+                uint8_t* rgb, uint32_t rgb_stride, int fma) {
+    (void)fma;
+    ImageIO::yuv2rgb({y, (std::ptrdiff_t)((size_t)ys * h)}, w, h, ys, {u, (std::ptrdiff_t)((size_t)us * ((h + 1) / 2))}, us,
+                     {v, (std::ptrdiff_t)((size_t)vs * ((h + 1) / 2))}, vs, {rgb, (std::ptrdiff_t)((size_t)rgb_stride * 3 * h)}, rgb_stride);
+}
+
 } // extern "C"

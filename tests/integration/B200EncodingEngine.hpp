@@ -17,8 +17,10 @@
 namespace Frac2 {
 class B200EncodingEngine : public AbstractEncodingEngine2 {
 public:
-    B200EncodingEngine(const encode_parameters_t& p, const ImagePlane& image, const UniformGrid& source, bool useClassifier, int device = 0)
-        : AbstractEncodingEngine2(p, image, source), _useClassifier(useClassifier), _device(device) {}
+    // same constructor shape as the OpenCLEncodingEngine the reference left commented out (encode/EncodingEngine2.cpp:23);
+    // the classifier choice travels in encode_parameters_t::noclassifier like it does for main.cpp:152-154
+    B200EncodingEngine(const encode_parameters_t& p, const ImagePlane& image, const UniformGrid& source, int device = 0)
+        : AbstractEncodingEngine2(p, image, source), _useClassifier(!p.noclassifier), _device(device) {}
     ~B200EncodingEngine() override { fe_destroy(_ctx); }
 
     void init() override {

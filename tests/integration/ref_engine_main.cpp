@@ -17,10 +17,11 @@ int main(int argc, char** argv) {
     Frac::encode_parameters_t params;
     params.sourceGridSize = S;
     params.targetGridSize = T;
+    params.noclassifier = std::atoi(argv[6]) == 0;
     auto sourceGrid = createUniformGrid(image.size(), Size32u(S, S), Size32u(S / 2, S / 2));
     auto targetGrid = createUniformGrid(image.size(), Size32u(T, T), Size32u(T, T));
     try {
-        B200EncodingEngine engine(params, image, sourceGrid, std::atoi(argv[6]) != 0);
+        B200EncodingEngine engine(params, image, sourceGrid);
         engine.setName("B200");
         engine.init();
         for (const auto& item : targetGrid.items()) engine.encode(item);
