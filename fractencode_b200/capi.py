@@ -28,10 +28,10 @@ SEARCH_AUTO, SEARCH_EXACT, SEARCH_UMMA = 0, 1, 2
 class Params(C.Structure):
     """fe_params: TransformMatcher(rmsThreshold, sMax) + classifier choice + FMA mode + engine."""
     _fields_ = [("rms_threshold", C.c_double), ("s_max", C.c_double), ("use_classifier", C.c_int32),
-                ("fma", C.c_int32), ("search_impl", C.c_int32), ("reserved_", C.c_int32)]
+                ("fma", C.c_int32), ("search_impl", C.c_int32), ("isometries", C.c_int32)]
 
-    def __init__(self, rms_threshold=0.0, s_max=-1.0, use_classifier=False, fma=False, search_impl=SEARCH_AUTO):
-        super().__init__(float(rms_threshold), float(s_max), int(bool(use_classifier)), int(bool(fma)), int(search_impl), 0)
+    def __init__(self, rms_threshold=0.0, s_max=-1.0, use_classifier=False, fma=False, search_impl=SEARCH_AUTO, isometries=4):
+        super().__init__(float(rms_threshold), float(s_max), int(bool(use_classifier)), int(bool(fma)), int(search_impl), int(isometries))
 
 
 class Stats(C.Structure):

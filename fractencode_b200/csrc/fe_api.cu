@@ -146,7 +146,7 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
                       &ctx->b_rowc, &ctx->b_coln, &ctx->b_rowbest, &ctx->b_rowhit, &ctx->b_hist, &ctx->b_level_items, &ctx->b_split,
                       &ctx->b_scan, &ctx->b_scan_tmp, &ctx->b_rng_next, &ctx->b_counters, &ctx->b_A16, &ctx->b_B16, &ctx->b_tmaps,
                       &ctx->b_items, &ctx->b_dec_a, &ctx->b_dec_b, &ctx->b_dec_items, &ctx->b_dec_sum, &ctx->b_q, &ctx->b_bound,
-                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_dom_order2, &ctx->b_rng_order2};
+                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_dom_order2, &ctx->b_rng_order2, &ctx->b_rng2, &ctx->b_pos_of};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
@@ -525,9 +525,12 @@ static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p,
     if (nR == 0) return FE_OK;
     const bool f16_ok = nD && f16_level_supported(g) && !skip_f16, i8_ok = nD && i8_level_supported(g);
     const bool device = (f16_ok || i8_ok) && p.search_impl != FE_SEARCH_EXACT;
+    const bool flips = p.isometries == 8;
+    if (p.isometries != 0 && p.isometries != 4 && p.isometries != 8) return fe_fail(ctx, FE_ERR_INVALID, "isometries must be 0, 4 or 8 (got %d)", p.isometries);
     if (!device) {
         if (p.search_impl == FE_SEARCH_UMMA && nD)
             return fe_fail(ctx, FE_ERR_UNSUPPORTED, "tcgen05 paths need S == 2T, even domain origins and T <= 32 (got S=%u T=%u)", g.S, g.T);
+        if (flips && nD) return fe_fail(ctx, FE_ERR_UNSUPPORTED, "the flip isometries run on the tensor paths only (S == 2T, even domain origins, 4 <= T <= 32)");
         return run_level_exact(ctx, io, p);
     }
     lp->kind = f16_ok ? 0 : 1;
@@ -539,15 +542,24 @@ static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p,
     if (lp->timed) cudaEventRecord(ctx->ev[0], ctx->stream);
     FE_CUDA(ctx, ctx->b_counters.ensure(16 * sizeof(uint32_t)));
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.p, 0, 16 * sizeof(uint32_t), ctx->stream));
-    FE_CUDA(ctx, ctx->b_rowbest.ensure((size_t)nR * 4 * 8));
-    FE_CUDA(ctx, ctx->b_rowhit.ensure((size_t)nR * 4 * 4));
+    // flip isometries: every range block is searched twice, the second copy mirrored left-right (its four rotation rows are
+    // the four flip isometries of the block); the list the search sees has 2 nR entries
+    const uint32_t nS = flips ? 2 * nR : nR;
+    const fe_grid_item* d_rng = io.d_rng;
+    if (flips) {
+        FE_CUDA(ctx, ctx->b_rng2.ensure((size_t)nS * sizeof(fe_grid_item)));
+        LAUNCH(ctx, k_dup_items, cdiv(nS, 256), 256, io.d_rng, nR, ctx->b_rng2.as<fe_grid_item>());
+        d_rng = ctx->b_rng2.as<fe_grid_item>();
+    }
+    FE_CUDA(ctx, ctx->b_rowbest.ensure((size_t)nS * 4 * 8));
+    FE_CUDA(ctx, ctx->b_rowhit.ensure((size_t)nS * 4 * 4));
     DeviceLevel lv{};
-    lv.d_dom = io.d_dom; lv.nD = nD; lv.d_rng = io.d_rng; lv.nR = nR; lv.g = g;
+    lv.d_dom = io.d_dom; lv.nD = nD; lv.d_rng = d_rng; lv.nR = nS; lv.g = g; lv.flips = flips;
     if (p.use_classifier) {
         FE_CUDA(ctx, ctx->b_dom_cls.ensure((size_t)nD * 4));
-        FE_CUDA(ctx, ctx->b_rng_cls.ensure((size_t)nR * 4));
+        FE_CUDA(ctx, ctx->b_rng_cls.ensure((size_t)nS * 4));
         LAUNCH(ctx, k_classify, cdiv((uint64_t)nD * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, nD, ctx->b_dom_cls.as<int32_t>(), 0);
-        LAUNCH(ctx, k_classify, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, ctx->b_rng_cls.as<int32_t>(), 0);
+        LAUNCH(ctx, k_classify, cdiv((uint64_t)nS * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, d_rng, nS, ctx->b_rng_cls.as<int32_t>(), 0);
         lv.dom_cls = ctx->b_dom_cls.as<int32_t>();
         lv.rng_cls = ctx->b_rng_cls.as<int32_t>();
     }
@@ -562,8 +574,14 @@ static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p,
     FinalizeArgs& f = lp->fin;
     f.src = ctx->src.px; f.src_stride = ctx->src.stride;
     f.tgt = ctx->tgt.px; f.tgt_stride = ctx->tgt.stride;
-    f.dom = io.d_dom; f.rng = io.d_rng;
+    f.dom = io.d_dom; f.rng = d_rng;
     f.dom_order = nullptr; f.rng_order = lp->st.rng_order;        // keys and hits are domain indices
+    if (flips) {
+        FE_CUDA(ctx, ctx->b_pos_of.ensure((size_t)nS * 4));
+        LAUNCH(ctx, k_pos_of, cdiv(nS, 256), 256, lp->st.rng_order, nS, ctx->b_pos_of.as<uint32_t>());
+        f.flips = 1;
+        f.pos_of = ctx->b_pos_of.as<uint32_t>();
+    }
     f.rowbest = ctx->b_rowbest.as<unsigned long long>();
     f.rowhit = ctx->b_rowhit.as<uint32_t>();
     f.n = nR;
@@ -653,6 +671,9 @@ static int run_level_complete(fe_ctx* ctx, const LevelIO& io, const fe_params& p
         ctx->stats.level_evaluated[io.stat_level] = hs->evaluated;
         ctx->stats.level_passes[io.stat_level] = hs->passes;
     }
+    if (hs->fp32_regime && lp->fin.flips)
+        return fe_fail(ctx, FE_ERR_UNSUPPORTED, "flip isometries: %u winners in the fp32-rounding regime of the reference distance (SSE >= 2^20, T=%u); "
+                                                "the re-rank pass covers the four rotations only", hs->fp32_regime, g.T);
     if (hs->fp32_regime) {
         // re-rank of the flagged range blocks on the exact kernel: every domain of the block's class in scan order
         const uint32_t nD = io.nD, nR = io.nR;

@@ -90,6 +90,8 @@ struct fe_ctx {
     DevBuf b_rng_next, b_counters, b_bound, b_flag_idx;
     // classifier classes x brightness bins: the composite orders (the class-only orders stay in b_dom_order / b_rng_order)
     DevBuf b_dom_order2, b_rng_order2;
+    // flip isometries: the doubled range list and the position of every copy after bucketing
+    DevBuf b_rng2, b_pos_of;
     // tcgen05 path operands
     DevBuf b_A16, b_B16, b_tmaps, b_blob_dom, b_tileseg;
     // device-scheduled levels (fe_plan.cuh): plan, slice state, the two lists of open range blocks, work items, bucket of every

@@ -210,6 +210,17 @@ __global__ void k_bin_prefix(const uint32_t* __restrict__ dom_order, const uint3
     out[t] = lo - beg;
 }
 
+// flip isometries: every range block twice (the odd copy is searched mirrored), and the position of every copy after sorting
+__global__ void k_dup_items(const fe_grid_item* __restrict__ in, uint32_t n, fe_grid_item* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    out[i] = in[i >> 1];
+}
+__global__ void k_pos_of(const uint32_t* __restrict__ order, uint32_t n, uint32_t* __restrict__ pos_of) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    pos_of[order ? order[p] : p] = p;
+}
 __global__ void k_iota(uint32_t* p, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
@@ -458,37 +469,56 @@ __global__ void k_finalize_t(FinalizeArgs f) {
     const uint32_t j = gt / LPR, lane = gt % LPR;              // range position, lane inside the block's group of LPR lanes
     const uint32_t gmask = LPR == 32 ? 0xFFFFFFFFu : (((1u << LPR) - 1u) << ((threadIdx.x & 31u) / LPR * LPR));
     if (j >= f.n) return;                                      // whole groups leave together
-    const uint32_t ri = f.rng_order ? f.rng_order[j] : j;
-    const fe_grid_item r = f.rng[ri];
+    // Rows of this range block and the isometry each one stands for.  Rotations only: rows 4 j + k.  With the flip
+    // isometries the block was searched twice (f.rng holds it at 2 j and, mirrored, at 2 j + 1): the mirrored copy under the
+    // inverse of rotation q is the block under Flip_Rotate_180, Flip_Rotate_90, Flip, Flip_Rotate_270 for q = 0..3
+    // (image/transform.h:37-40 worked out on the decimated grid).
+    const int nrow = f.flips ? 8 : 4;
+    uint32_t rowidx[8];
+    int kof[8];
+    uint32_t ri;
+    if (!f.flips) {
+        ri = f.rng_order ? f.rng_order[j] : j;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { rowidx[k] = 4 * j + k; kof[k] = k; rowidx[4 + k] = 0; kof[4 + k] = 0; }
+    } else {
+        ri = j;
+        const uint32_t pa = f.pos_of[2 * j], pb = f.pos_of[2 * j + 1];
+        const int km[4] = {6, 5, 4, 7};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { rowidx[k] = 4 * pa + k; kof[k] = k; rowidx[4 + k] = 4 * pb + k; kof[4 + k] = km[k]; }
+    }
+    const fe_grid_item r = f.rng[f.flips ? 2 * ri : ri];
     // ---- pick the winner (identical on all lanes) ----
-    int wk = -1;
+    int wk = -1, wrow = -1;
     uint32_t wd = 0, wn16 = 0;
     bool from_min = false;
-    if (f.use_thr) { // first candidate in scan order c = 4*d + k with distance <= threshold
+    if (f.use_thr) { // first candidate in scan order c = 8*d + k with distance <= threshold
         unsigned long long bestscan = FE_INF64;
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t h = f.rowhit[4 * j + k];
+        for (int q = 0; q < nrow; ++q) {
+            const uint32_t h = f.rowhit[rowidx[q]];
             if (h != FE_NONE32) {
                 const uint32_t d = (f.dom_order && !f.hit_is_domain) ? f.dom_order[h] : h;
-                const unsigned long long scan = (unsigned long long)d * 4 + k;
-                if (scan < bestscan) bestscan = scan;
+                const unsigned long long scan = (unsigned long long)d * 8 + (unsigned)kof[q];
+                if (scan < bestscan) { bestscan = scan; wrow = q; }
             }
         }
         if (bestscan != FE_INF64) {
-            wk = (int)(bestscan & 3);
-            wd = (uint32_t)(bestscan >> 2);
+            wk = (int)(bestscan & 7);
+            wd = (uint32_t)(bestscan >> 3);
         }
     }
     if (wk < 0 && !f.no_min) { // minimum n16; ties -> smallest domain index, then LARGEST k
         uint32_t bn = 0, bd = 0;
-        for (int k = 0; k < 4; ++k) {
-            const unsigned long long key = f.rowbest[4 * j + k];
+        for (int q = 0; q < nrow; ++q) {
+            const unsigned long long key = f.rowbest[rowidx[q]];
             if (key == FE_INF64) continue;
             // normal pass: n16; re-rank pass: bits of the emulated fp32 sum (monotone for non-negative floats)
             const uint32_t n16 = (uint32_t)(key >> 32), col = (uint32_t)key;
             const uint32_t d = f.dom_order ? f.dom_order[col] : col;
-            if (wk < 0 || n16 < bn || (n16 == bn && d <= bd)) {
-                wk = k;
+            if (wk < 0 || n16 < bn || (n16 == bn && (d < bd || (d == bd && kof[q] > wk)))) {
+                wk = kof[q];
+                wrow = q;
                 bn = n16;
                 bd = d;
             }
@@ -505,7 +535,7 @@ __global__ void k_finalize_t(FinalizeArgs f) {
         if (lane == 0) {
             f.out[ri] = out;
             if (f.split) f.split[ri] = (f.can_split && !(100000.0 <= f.thr)) ? 1u : 0u;
-            if (f.bound_out) f.bound_out[j] = 0;
+            if (f.bound_out && !f.flips) f.bound_out[j] = 0;
         }
         return;
     }
@@ -532,12 +562,12 @@ __global__ void k_finalize_t(FinalizeArgs f) {
     if (f.rerank) {
         // keys are float sums here; nothing to cross-check against the integer recomputation
     } else if (from_min) {
-        const unsigned long long key = f.rowbest[4 * j + wk];
+        const unsigned long long key = f.rowbest[rowidx[wrow]];
         if ((uint32_t)(key >> 32) != wn16) atomicAdd(f.mismatch, 1u);
     } else if (wn16 > f.thr16) {
         atomicAdd(f.mismatch, 1u);
     }
-    if (f.bound_out) {
+    if (f.bound_out && !f.flips) {
         // fp32 regime (SSE >= 2^20): the reference ranks candidates by a ROUNDED running sum, so every candidate whose
         // exact score lies within the worst-case rounding band of the exact minimum must be re-scored.
         // |fl_seq(S) - S| <= N * ulp(S) / 2; band = 2 * N * ulp(S_min) in SSE units = 32 * N * ulp in n16 units.

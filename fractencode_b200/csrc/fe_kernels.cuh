@@ -25,6 +25,8 @@ struct FinalizeArgs {
     int rerank;                     // rowbest keys hold float bits (re-rank pass)
     int no_min;                     // the minimum is not wanted: a range without a hit gets the default item (and splits)
     int hit_is_domain;              // rowhit holds domain indices (tcgen05 paths), not sorted column positions (exact path)
+    int flips;                      // eight isometries: rng holds every block twice, n counts blocks, pos_of[copy] = its row position
+    const uint32_t* pos_of;
 };
 
 __global__ void k_uniform_grid(fe_grid_item* out, uint32_t nx, uint32_t n, uint32_t size, uint32_t step, uint32_t first);
@@ -34,6 +36,8 @@ __global__ void k_classify(const uint8_t* img, uint32_t stride, const fe_grid_it
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n);
 __global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n);
 __global__ void k_iota(uint32_t* p, uint32_t n);
+__global__ void k_dup_items(const fe_grid_item* in, uint32_t n, fe_grid_item* out);
+__global__ void k_pos_of(const uint32_t* order, uint32_t n, uint32_t* pos_of);
 struct BucketOff { uint32_t v[FE_MAX_BUCKETS + 1]; };
 void launch_brightness_bins(cudaStream_t stream, const uint8_t* img, uint32_t stride, const fe_grid_item* items, uint32_t n, uint32_t edge,
                             uint32_t mul, uint32_t width, uint8_t* keys, uint32_t* hist);

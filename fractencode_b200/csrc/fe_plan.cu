@@ -132,13 +132,14 @@ __global__ void __launch_bounds__(512) k_level_plan(PlanArgs a, const uint32_t* 
 // Per level position: the first list (every range block open), sum a^2 of the block (centred: a = 4 r - 510, f16 kind;
 // else 16 sum r^2, i8 kind) and the bucket of the position.
 __global__ void k_level_ranges(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
-                               const uint32_t* __restrict__ order, const LevelPlan* __restrict__ plan, uint32_t T, int centred,
+                               const uint32_t* __restrict__ order, const LevelPlan* __restrict__ plan, uint32_t T, int centred, int flips,
                                ListEntry* __restrict__ list0, uint16_t* __restrict__ pos_bucket) {
     // a warp per block from T = 16 on (coalesced rows), a thread per block below
     const uint32_t lanes = T >= 16 ? 32u : 1u;
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x, p = gt / lanes, lane = gt % lanes;
     if (p >= plan->nR) return;
-    const fe_grid_item r = rng[order ? order[p] : p];
+    const uint32_t idx = order ? order[p] : p;
+    const fe_grid_item r = rng[idx];
     const uint8_t* base = img + (size_t)r.y * stride + r.x;
     uint32_t s2 = 0;
     for (uint32_t e = lane; e < T * T; e += lanes) {
@@ -153,7 +154,7 @@ __global__ void k_level_ranges(const uint8_t* __restrict__ img, uint32_t stride,
     e.slot = p;
     e.xy = r.x | (r.y << 16);
     e.a2 = s2;
-    e.pad_ = 0;
+    e.mirror = flips ? (idx & 1u) : 0u;
     list0[p] = e;
     uint32_t lo = 0, hi = plan->nb - 1;               // bucket b with roff[b] <= p < roff[b + 1]
     while (lo < hi) {
@@ -548,7 +549,7 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
     pa.items_per_sm = kind == 0 ? 8u : (g.T >= 32 ? 4u : 6u);
     PLAUNCH(ctx, k_level_plan, 1, 512, pa, hist_d, hist_r, pre, nb, st->nbins, st->ngroups, st->span, nD, nR, nt);
     PLAUNCH(ctx, k_level_ranges, cdiv_u((uint64_t)nR * (g.T >= 16 ? 32 : 1), 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T, kind == 0 ? 1 : 0,
-            pa.list[0], ctx->b_posb.as<uint16_t>());
+            lv.flips ? 1 : 0, pa.list[0], ctx->b_posb.as<uint16_t>());
     PLAUNCH(ctx, k_fill_u64, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
     PLAUNCH(ctx, k_fill_u32, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));

@@ -37,7 +37,7 @@ struct __align__(16) ListEntry {
     uint32_t slot;
     uint32_t xy;                          // x | y << 16
     uint32_t a2;                          // f16 kind: sum (4 r - 510)^2; i8 kind: 16 sum r^2
-    uint32_t pad_;
+    uint32_t mirror;                      // 1: the block is read mirrored left-right (flip isometries: the second copy of a range block)
 };
 
 // One work item of a slice: a row tile (up to 32 range blocks = 128 rows) against a run of blob tiles.
@@ -97,7 +97,7 @@ enum { FE_PHASE_SLICE = 0, FE_PHASE_MIN = 1 };
 __global__ void k_level_plan(PlanArgs a, const uint32_t* dom_hist, const uint32_t* rng_hist, const uint32_t* pre, uint32_t nb, uint32_t nbins,
                              uint32_t ngroups, uint32_t span, uint32_t nD, uint32_t nR, uint32_t nt);
 __global__ void k_level_ranges(const uint8_t* img, uint32_t stride, const fe_grid_item* rng, const uint32_t* order, const LevelPlan* plan,
-                               uint32_t T, int centred, ListEntry* list0, uint16_t* pos_bucket);
+                               uint32_t T, int centred, int flips, ListEntry* list0, uint16_t* pos_bucket);
 __global__ void k_slice_plan(PlanArgs a, int phase, uint32_t ordinal);
 __global__ void k_expand_items(PlanArgs a, uint32_t ordinal);
 
@@ -110,6 +110,7 @@ struct DeviceLevel {
     const int32_t* rng_cls;
     uint32_t thr16;
     bool use_thr, need_min, timed;
+    bool flips;                           // d_rng holds every range block twice (2 i, 2 i + 1): the odd copy is searched mirrored
 };
 struct DeviceLevelState;
 

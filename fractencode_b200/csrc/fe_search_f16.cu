@@ -36,8 +36,8 @@ constexpr int F16_BUILDERS = 4;
 // Rows 4 r + k (k = 0..3) of the A tile: range block r of the item under the inverse of rotation k, values 510 - 4 p, then
 // the constant columns [1, 2048, 2048].  Lane = (r, k); the four lanes of a block read the same 64 pixels.
 template <int T>
-__device__ __forceinline__ void build_rows(uint8_t* sAbuf, const uint8_t* __restrict__ img, uint32_t stride, uint32_t xy, bool valid, uint32_t bw,
-                                           uint32_t lane) {
+__device__ __forceinline__ void build_rows(uint8_t* sAbuf, const uint8_t* __restrict__ img, uint32_t stride, uint32_t xy, bool mirror, bool valid,
+                                           uint32_t bw, uint32_t lane) {
     constexpr int N = T * T, KPAD = (N + 3 + 15) & ~15, NCH = KPAD / 8, W = T / 4;
     const uint32_t r = bw * 8 + (lane >> 2), k = lane & 3u;
     uint4* out = reinterpret_cast<uint4*>(sAbuf) + (4 * r + k);          // K chunk ch of this row: out[ch * UM_ROWS]
@@ -50,6 +50,16 @@ __device__ __forceinline__ void build_rows(uint8_t* sAbuf, const uint8_t* __rest
     uint32_t o[T][W];
 #pragma unroll
     for (int y = 0; y < T; ++y) load_px<T>(base + (size_t)y * stride, o[y]);
+    if (mirror) {                              // flip isometries: the block read right to left
+#pragma unroll
+        for (int y = 0; y < T; ++y) {
+            uint32_t m[W];
+#pragma unroll
+            for (int wq = 0; wq < W; ++wq) m[wq] = __byte_perm(o[y][W - 1 - wq], 0, 0x0123);
+#pragma unroll
+            for (int wq = 0; wq < W; ++wq) o[y][wq] = m[wq];
+        }
+    }
     // transpose: tr[c] byte y = o[y] byte c
     uint32_t tr[T][W];
 #pragma unroll
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
             const uint32_t ab = wi % NA;
             fetch(w + gridDim.x, ent_next, valid_next);
             if (wi >= NA) mbar_wait(A_EMPTY(ab), ((wi / NA) & 1) ^ 1);   // all four issuers are done with item wi - NA
-            build_rows<T>(sA + ab * bytesA, a.img, a.stride, ent.y, valid, bw, lane);
+            build_rows<T>(sA + ab * bytesA, a.img, a.stride, ent.y, ent.w != 0, valid, bw, lane);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) mbar_arrive(A_FULL(ab));

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) k_build_rows_i8(const uint8_t* __restrict
                                                        uint4* __restrict__ A8) {
     const uint32_t T = TT ? TT : T_rt;
     extern __shared__ __align__(16) uint8_t sblk[];            // [32][N + 16]
-    __shared__ uint32_t sxy[32];
+    __shared__ uint32_t sxy[32], smir[32];
     __shared__ uint32_t s_pos0, s_nvalid;
     if (ctl->active != ordinal) return;
     const uint32_t N = T * T, NS = N + 16;                     // T a template parameter: the index arithmetic below is shifts
@@ -309,7 +309,11 @@ __global__ void __launch_bounds__(256) k_build_rows_i8(const uint8_t* __restrict
     }
     __syncthreads();
     const uint32_t nvalid = s_nvalid;
-    if (threadIdx.x < nvalid) sxy[threadIdx.x] = list[s_pos0 + threadIdx.x].xy;
+    if (threadIdx.x < nvalid) {
+        const ListEntry e = list[s_pos0 + threadIdx.x];
+        sxy[threadIdx.x] = e.xy;
+        smir[threadIdx.x] = e.mirror;
+    }
     __syncthreads();
     // ---- stage the blocks ----
     const bool words = (T & 3u) == 0 && (stride & 3u) == 0 && (reinterpret_cast<uintptr_t>(img) & 3u) == 0;
@@ -322,13 +326,14 @@ __global__ void __launch_bounds__(256) k_build_rows_i8(const uint8_t* __restrict
             uint32_t v;
             if ((x & 3u) == 0) v = __ldg(reinterpret_cast<const uint32_t*>(p));
             else v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-            reinterpret_cast<uint32_t*>(sblk + lr * NS)[e] = v;
+            if (smir[lr]) reinterpret_cast<uint32_t*>(sblk + lr * NS)[y * wpr + (wpr - 1 - xw)] = __byte_perm(v, 0, 0x0123);   // read right to left
+            else reinterpret_cast<uint32_t*>(sblk + lr * NS)[e] = v;
         }
     } else {
         for (uint32_t idx = threadIdx.x; idx < nvalid * N; idx += blockDim.x) {
             const uint32_t lr = idx / N, e = idx - lr * N, y = e / T, x = e - y * T;
             const uint32_t xy = sxy[lr];
-            sblk[lr * NS + e] = img[(size_t)((xy >> 16) + y) * stride + (xy & 0xFFFFu) + x];
+            sblk[lr * NS + y * T + (smir[lr] ? T - 1 - x : x)] = img[(size_t)((xy >> 16) + y) * stride + (xy & 0xFFFFu) + x];
         }
     }
     __syncthreads();

@@ -466,7 +466,7 @@ public:
     QuadtreeEncoder2(const ImagePlane& image, const encode_parameters_t& p, uint32_t tMax, uint32_t tMin, int device = 0) {
         Frac::b200::Context c(device);
         c.check(fe_set_image(c.get(), image.data(), image.width(), image.height(), image.stride()));
-        fe_params fp{p.rmsThreshold, p.sMax, p.noclassifier ? 0 : 1, p.fma ? 1 : 0, p.searchImpl, 0};
+        fe_params fp{p.rmsThreshold, p.sMax, p.noclassifier ? 0 : 1, p.fma ? 1 : 0, p.searchImpl, 4};
         std::vector<fe_encode_item> out((size_t)(image.width() / tMin) * (image.height() / tMin));
         size_t n = 0;
         size_t counts[8] = {0};

@@ -74,7 +74,10 @@ typedef struct {
                              without FMA); 1: fused, as GCC emits for the reference's -march=native
                              build.  Same switch for decode's s*v+o. */
     int32_t search_impl;  /* fe_search_impl */
-    int32_t reserved_;
+    int32_t isometries;   /* 0 or 4: the four rotations TransformMatcher::match tries (transformmatcher.h:38-46) -- the reference's
+                             results.  8: the chain goes on through Flip, Flip_Rotate_90/180/270 (image/transform.h:20-24, 37-40)
+                             with the same rules (first isometry under the threshold, else the minimum, ties to the later one):
+                             an extension, results differ from the reference by design; tensor paths only. */
 } fe_params;
 
 typedef struct {

@@ -225,7 +225,8 @@ static score_t match_type(const fo_plane* src, const fo_grid_item* d, const fo_p
 static score_t match_chain(const fo_plane* src, const fo_grid_item* d, const fo_plane* tgt,
                            const fo_grid_item* r, const fo_params* p) {
     score_t prev = kDefaultScore;
-    for (int t = 0; t < 4; ++t) {
+    const int n_iso = p->isometries == 8 ? 8 : 4;
+    for (int t = 0; t < n_iso; ++t) {
         const score_t res = match_type(src, d, tgt, r, p, t, prev);
         if (res.distance <= p->rms_threshold) return res; /* checkDistance :32-34 */
         prev = res.distance <= prev.distance ? res : prev;

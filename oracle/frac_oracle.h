@@ -60,6 +60,10 @@ typedef struct {
     double s_max;
     int use_classifier; /* 0 = DummyClassifier, 1 = BrightnessBlocksClassifier2 */
     int fma;
+    int isometries;     /* 0 / 4: the four rotations TransformMatcher::match tries (transformmatcher.h:38-46); 8: the chain goes on
+                           through Flip .. Flip_Rotate_270 (image/transform.h:20-24) with the same rules -- OURS, the
+                           compiled reference ignores it */
+    int reserved_;
 } fo_params;
 
 /* image/sampler.h:22-38 + image/transform.h:96-109.  Returns the 2x2 box SUM

@@ -32,7 +32,8 @@ class Plane(C.Structure):
 
 
 class Params(C.Structure):
-    _fields_ = [("rms_threshold", C.c_double), ("s_max", C.c_double), ("use_classifier", C.c_int), ("fma", C.c_int)]
+    _fields_ = [("rms_threshold", C.c_double), ("s_max", C.c_double), ("use_classifier", C.c_int), ("fma", C.c_int),
+                ("isometries", C.c_int), ("reserved_", C.c_int)]
 
 
 def build(ref: bool = True) -> None:
@@ -123,8 +124,8 @@ class Oracle:
         return items
 
     @staticmethod
-    def params(thr=0.0, smax=-1.0, classifier=False, fma=False) -> Params:
-        return Params(float(thr), float(smax), int(bool(classifier)), int(bool(fma)))
+    def params(thr=0.0, smax=-1.0, classifier=False, fma=False, isometries=4) -> Params:
+        return Params(float(thr), float(smax), int(bool(classifier)), int(bool(fma)), int(isometries), 0)
 
     def match(self, src, dom, tgt, rng, p: Params) -> np.ndarray:
         d = np.array([tuple(dom) + (-1,)], GRID_ITEM)

@@ -31,7 +31,7 @@ public:
     void finalize() override {
         static_assert(sizeof(UniformGridItem) == sizeof(fe_grid_item), "20-byte layout");
         static_assert(sizeof(encode_item_t) == sizeof(fe_encode_item), "64-byte layout");
-        fe_params fp{_parameters.rmsThreshold, _parameters.sMax, _useClassifier ? 1 : 0, FRAC_FMA_BUILD, FE_SEARCH_AUTO, 0};
+        fe_params fp{_parameters.rmsThreshold, _parameters.sMax, _useClassifier ? 1 : 0, FRAC_FMA_BUILD, FE_SEARCH_AUTO, 4};
         _batch.resize(_queue.size());
         check(fe_encode_level(_ctx, reinterpret_cast<const fe_grid_item*>(_source.items().data()), _source.items().size(),
                               reinterpret_cast<const fe_grid_item*>(_queue.data()), _queue.size(), &fp,

@@ -196,3 +196,57 @@ def test_batch_of_16_images_1024(ctx, fo):
                 rng = np.zeros(len(pick), dom.dtype)
                 rng["x"], rng["y"], rng["w"], rng["h"], rng["bin"] = pick["x"], pick["y"], T, T, -1
                 assert_items_equal(pick, fo.encode_level(img, img, dom, rng, fo.params(thr)), "image %d T=%d" % (i, T))
+
+
+@pytest.mark.parametrize("kind,S,T,thr,cls", [(0, 16, 8, 0.0, False), (0, 8, 4, 0.0, True), (0, 32, 16, 0.0, False), (2, 16, 8, 0.0, False),
+                                               (2, 16, 8, 3.0, True), (0, 16, 8, 30.0, False), (0, 32, 16, 60.0, True)])
+def test_flip_isometries_fixed_grid(ctx, fo, kind, S, T, thr, cls):
+    """the match chain extended through the four flip isometries (image/transform.h:20-24,37-40), behind
+    fe_params.isometries = 8.  Oracle = the same chain rules over eight isometries (oracle/frac_oracle.c:match_chain)."""
+    import fractencode_b200 as fb
+    img = fo.synth_image(128, 128, 77, kind)
+    dom, rng = fb.uniform_grid(128, 128, S, S // 2), fb.uniform_grid(128, 128, T, T)
+    ctx.set_image(img)
+    for fma in (False, True):
+        got = ctx.encode_level(dom, rng, fb.Params(thr, -1.0, cls, fma, isometries=8))
+        want = fo.encode_level(img, img, dom, rng, fo.params(thr, -1.0, cls, fma, isometries=8))
+        assert_items_equal(got, want, "flips S=%d T=%d" % (S, T))
+    if kind != 2:   # (the pattern image matches exactly under the identity)
+        assert (got["transform"] > 3).any(), "no flip isometry was ever selected: the test would prove nothing"
+    # and the reference's four-rotation answer is untouched by the extension
+    got4 = ctx.encode_level(dom, rng, fb.Params(thr, -1.0, cls))
+    assert_items_equal(got4, fo.encode_level(img, img, dom, rng, fo.params(thr, -1.0, cls)))
+
+
+def test_flip_isometries_quadtree_and_decode(ctx, fo):
+    import fractencode_b200 as fb
+    img = fo.synth_image(256, 256, 1234, 0)
+    ctx.set_image(img)
+    for cls in (False, True):
+        got, counts = ctx.encode_quadtree(32, 4, fb.Params(8.0, -1.0, cls, isometries=8))
+        want, wcounts = fo.encode_quadtree(img, 32, 4, fo.params(8.0, -1.0, cls, isometries=8))
+        assert counts == wcounts
+        assert_items_equal(got, want)
+        dec, it, rms = ctx.decode(got, 256, 256)
+        odec, oit, orms = fo.decode(want, 256, 256)
+        assert (dec == odec).all() and it == oit and rms == orms
+    # more isometries can only find hits earlier: never more items than with rotations alone... not guaranteed by the first-hit
+    # rule, but the candidate count doubles
+    ctx.stats_reset()
+    ctx.encode_quadtree(32, 4, fb.Params(8.0, isometries=8))
+    m8 = int(ctx.stats().level_matches[0])
+    ctx.stats_reset()
+    ctx.encode_quadtree(32, 4, fb.Params(8.0))
+    assert m8 == 2 * int(ctx.stats().level_matches[0])
+    # the fp32-rounding regime (noise-like blocks at T >= 16) is re-ranked over the four rotations only: refused with flips
+    noise = fo.synth_image(128, 128, 77, 1)
+    ctx.set_image(noise)
+    with pytest.raises(fb.FractencodeError) as e:
+        ctx.encode_level(fb.uniform_grid(128, 128, 32, 16), fb.uniform_grid(128, 128, 16, 16), fb.Params(0.0, isometries=8))
+    assert e.value.code == -2
+    ctx.set_image(img)
+    # generic geometries (exact integer path) do not take the flag
+    dom, rng = fb.uniform_grid(256, 256, 16, 8), fb.uniform_grid(256, 256, 4, 4)
+    with pytest.raises(fb.FractencodeError) as e:
+        ctx.encode_level(dom, rng, fb.Params(0.0, isometries=8))
+    assert e.value.code == -2
