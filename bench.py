@@ -423,10 +423,11 @@ def run_b200(a):
     for l in range(nlev):
         T = a.tmax >> l
         lm, le, ms = int(st.level_matches[l]), int(st.level_evaluated[l]), float(st.level_search_ms[l])
-        lf = 2.0 * T * T * le
+        lp_ = int(st.level_prefiltered[l])
+        lf = 2.0 * T * T * le + 2.0 * 64 * lp_      # prefilter pairs: an 8 x 8 bound, 64 products each
         flops += lf
         search_ms += ms
-        levels.append({"T": T, "ranges": int(st.level_ranges[l]), "items": int(st.level_items[l]), "matches": lm, "evaluated": le,
+        levels.append({"T": T, "ranges": int(st.level_ranges[l]), "items": int(st.level_items[l]), "matches": lm, "evaluated": le, "prefiltered": lp_,
                        "passes": int(st.level_passes[l]), "search_ms": round(ms, 3), "prep_ms": round(float(st.level_prep_ms[l]), 3),
                        "tflops": round(lf / (ms * 1e-3) / 1e12, 2) if ms > 0 else None})
     # e2e through the C ABI with host buffers

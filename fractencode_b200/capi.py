@@ -39,7 +39,8 @@ class Stats(C.Structure):
                 ("umma_levels", C.c_uint64), ("exact_levels", C.c_uint64),
                 ("level_items", C.c_uint64 * 8), ("level_ranges", C.c_uint64 * 8), ("level_matches", C.c_uint64 * 8),
                 ("level_search_ms", C.c_float * 8), ("level_prep_ms", C.c_float * 8), ("last_decode_ms", C.c_float), ("reserved_", C.c_uint32),
-                ("evaluated", C.c_uint64), ("level_evaluated", C.c_uint64 * 8), ("level_passes", C.c_uint64 * 8)]
+                ("evaluated", C.c_uint64), ("level_evaluated", C.c_uint64 * 8), ("level_passes", C.c_uint64 * 8),
+                ("prefiltered", C.c_uint64), ("level_prefiltered", C.c_uint64 * 8)]
 
 
 class ThresholdPlan(C.Structure):

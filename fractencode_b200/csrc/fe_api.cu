@@ -146,7 +146,7 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
                       &ctx->b_rowc, &ctx->b_coln, &ctx->b_rowbest, &ctx->b_rowhit, &ctx->b_hist, &ctx->b_level_items, &ctx->b_split,
                       &ctx->b_scan, &ctx->b_scan_tmp, &ctx->b_rng_next, &ctx->b_counters, &ctx->b_A16, &ctx->b_B16, &ctx->b_tmaps,
                       &ctx->b_items, &ctx->b_dec_a, &ctx->b_dec_b, &ctx->b_dec_items, &ctx->b_dec_sum, &ctx->b_q, &ctx->b_bound,
-                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_dom_order2, &ctx->b_rng_order2, &ctx->b_rng2, &ctx->b_pos_of};
+                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_dom_order2, &ctx->b_rng_order2, &ctx->b_rng2, &ctx->b_pos_of, &ctx->b_lbq, &ctx->b_lbcand};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
@@ -264,6 +264,7 @@ struct LevelIO {
     fe_encode_item* d_out = nullptr; // [nR], by range index
     uint32_t* d_split = nullptr;     // [nR] or NULL
     int can_split = 0;
+    int lattice = 0;                 // the blocks lie on the quadtree's lattices (range origins multiples of T, domain origins of T)
     int stat_level = -1;             // quadtree level index for the per-level stats, -1 = none
 };
 
@@ -509,7 +510,8 @@ static int run_level_exact(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
 // ---------------------------------------------------------------------------------------------------
 struct LevelPending {
     bool device = false;
-    int kind = 0;                         // 0: kind::f16 (T = 4, 8), 1: kind::i8
+    int kind = 0;                         // 0: kind::f16 (T = 4, 8), 1: kind::i8, 2: lower-bound prefilter + exact check
+    int skip = 0;
     DeviceLevelState st;
     uint32_t thr16 = 0;
     bool use_thr = false, timed = false;
@@ -518,12 +520,14 @@ struct LevelPending {
 
 static inline int hint_slot(uint32_t T) { int l = 0; while ((1u << l) < T && l < 7) ++l; return l; }
 
-static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p, LevelPending* lp, bool skip_f16 = false) {
+// skip: bit 0 = not the kind::f16 search (a winner sat in its inexact band), bit 1 = not the lower-bound prefilter (its
+// candidate list overflowed) -- set when a level is redone
+static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p, LevelPending* lp, int skip = 0) {
     const LevelGeom& g = io.g;
     const uint32_t nR = io.nR, nD = io.nD;
     *lp = LevelPending{};
     if (nR == 0) return FE_OK;
-    const bool f16_ok = nD && f16_level_supported(g) && !skip_f16, i8_ok = nD && i8_level_supported(g);
+    const bool f16_ok = nD && f16_level_supported(g) && !(skip & 1), i8_ok = nD && i8_level_supported(g);
     const bool device = (f16_ok || i8_ok) && p.search_impl != FE_SEARCH_EXACT;
     const bool flips = p.isometries == 8;
     if (p.isometries != 0 && p.isometries != 4 && p.isometries != 8) return fe_fail(ctx, FE_ERR_INVALID, "isometries must be 0, 4 or 8 (got %d)", p.isometries);
@@ -534,11 +538,21 @@ static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p,
         return run_level_exact(ctx, io, p);
     }
     lp->kind = f16_ok ? 0 : 1;
+    lp->skip = skip;
     if (p.rms_threshold * (double)(g.S * g.S) >= 1048576.0)
         return fe_fail(ctx, FE_ERR_UNSUPPORTED, "rms_threshold %g reaches the fp32-rounding regime of the reference distance (SSE >= 2^20) at S=%u", p.rms_threshold, g.S);
     lp->device = true;
     lp->timed = io.stat_level >= 0 && io.stat_level < 8;
     lp->use_thr = threshold_n16(p.rms_threshold, g.S, &lp->thr16);
+    // Large blocks of a level that only looks for hits (it splits the range blocks that find none): lower-bound prefilter on
+    // the 8 x 8 grid of cell sums + exact check of the few candidates it lets through (fe_lb.cu)
+    {
+        const char* mt = getenv("FE_LB_MIN_T");
+        const uint32_t lb_min_t = mt ? (uint32_t)atoi(mt) : 32u;
+        if (lp->kind == 1 && !(skip & 2) && g.T >= lb_min_t && g.T >= 16 && lp->use_thr && io.can_split && !flips && ctx->src.px == ctx->tgt.px &&
+            ctx->src.w % (g.T / 8) == 0 && ctx->src.h % (g.T / 8) == 0 && io.lattice && !getenv("FE_NO_LB"))
+            lp->kind = 2;
+    }
     if (lp->timed) cudaEventRecord(ctx->ev[0], ctx->stream);
     FE_CUDA(ctx, ctx->b_counters.ensure(16 * sizeof(uint32_t)));
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.p, 0, 16 * sizeof(uint32_t), ctx->stream));
@@ -634,7 +648,12 @@ static int run_level_complete(fe_ctx* ctx, const LevelIO& io, const fe_params& p
         if (hs->overflow) return fe_fail(ctx, FE_ERR_CUDA, "internal: work-item buffer of the level too small (T=%u)", g.T);
         if (hs->flags & 1u) {
             // a winner of the kind::f16 search sits in the fp32-inexact band: the level is searched again on the integer kind
-            FE_TRY(run_level_enqueue(ctx, io, p, lp, true));
+            FE_TRY(run_level_enqueue(ctx, io, p, lp, lp->skip | 1));
+            continue;
+        }
+        if (hs->flags & 2u) {
+            // the candidate list of the lower-bound prefilter overflowed (everything matches everything): exact kind
+            FE_TRY(run_level_enqueue(ctx, io, p, lp, lp->skip | 2));
             continue;
         }
         if (!hs->done) {
@@ -650,8 +669,13 @@ static int run_level_complete(fe_ctx* ctx, const LevelIO& io, const fe_params& p
     if (hs->mismatch) return fe_fail(ctx, FE_ERR_CUDA, "internal: %u winners whose search score disagrees with the direct recomputation (T=%u)", hs->mismatch, g.T);
     fe_ctx::SliceHint& hint = ctx->hint[lp->kind][hint_slot(g.T)];
     hint.known = 1; hint.slices = (uint8_t)std::max(1u, hs->slices); hint.with_min = hs->min_ran ? 1 : 0;
+    // lower-bound prefilter levels: `evaluated` = candidates scored exactly (1024 products each at T = 32); the pairs the
+    // 8 x 8 bound looked at (64 products each) are counted apart
+    const unsigned long long evaluated = lp->kind == 2 ? hs->lb_candidates : hs->evaluated;
+    const unsigned long long prefiltered = lp->kind == 2 ? hs->evaluated : 0ull;
     ctx->stats.matches += hs->matches;
-    ctx->stats.evaluated += hs->evaluated;
+    ctx->stats.evaluated += evaluated;
+    ctx->stats.prefiltered += prefiltered;
     ctx->stats.umma_levels++;
     ctx->stats.fp32_regime_items += hs->fp32_regime;
     if (lp->timed) {
@@ -668,7 +692,8 @@ static int run_level_complete(fe_ctx* ctx, const LevelIO& io, const fe_params& p
         ctx->stats.level_prep_ms[io.stat_level] = ms - kernel_ms;
         ctx->stats.level_ranges[io.stat_level] = io.nR;
         ctx->stats.level_matches[io.stat_level] = hs->matches;
-        ctx->stats.level_evaluated[io.stat_level] = hs->evaluated;
+        ctx->stats.level_evaluated[io.stat_level] = evaluated;
+        ctx->stats.level_prefiltered[io.stat_level] = prefiltered;
         ctx->stats.level_passes[io.stat_level] = hs->passes;
     }
     if (hs->fp32_regime && lp->fin.flips)
@@ -811,7 +836,7 @@ static int quad_begin(fe_ctx* ctx, uint32_t t_max, uint32_t t_min, const fe_para
                (uint32_t)first_block);
     for (int l = 0; l < 8; ++l) {
         ctx->stats.level_items[l] = ctx->stats.level_ranges[l] = ctx->stats.level_matches[l] = 0;
-        ctx->stats.level_evaluated[l] = ctx->stats.level_passes[l] = 0;
+        ctx->stats.level_evaluated[l] = ctx->stats.level_passes[l] = ctx->stats.level_prefiltered[l] = 0;
         ctx->stats.level_search_ms[l] = ctx->stats.level_prep_ms[l] = 0.f;
     }
     QuadJob* j = job_of(ctx);
@@ -845,6 +870,7 @@ static int quad_enqueue(fe_ctx* ctx) {
     io.d_rng = ctx->b_rng.as<fe_grid_item>(); io.nR = (uint32_t)n_pending;
     io.d_out = ctx->b_level_items.as<fe_encode_item>();
     io.can_split = (T / 2 >= j->t_min) ? 1 : 0;
+    io.lattice = 1;
     io.d_split = ctx->b_split.as<uint32_t>();
     io.stat_level = j->level;
     FE_TRY(run_level_enqueue(ctx, io, j->params, &j->lp));

@@ -92,6 +92,8 @@ struct fe_ctx {
     DevBuf b_dom_order2, b_rng_order2;
     // flip isometries: the doubled range list and the position of every copy after bucketing
     DevBuf b_rng2, b_pos_of;
+    // lower-bound prefilter: cell-sum plane, candidate list (+ its counter)
+    DevBuf b_lbq, b_lbcand;
     // tcgen05 path operands
     DevBuf b_A16, b_B16, b_tmaps, b_blob_dom, b_tileseg;
     // device-scheduled levels (fe_plan.cuh): plan, slice state, the two lists of open range blocks, work items, bucket of every
@@ -102,7 +104,7 @@ struct fe_ctx {
     fe_ctx* sub[2] = {nullptr, nullptr};   // fe_encode_batch: two child contexts (own stream and scratch) the images alternate between
     int n_sm = 148;                 // multiProcessorCount of the device
     // slices the last level of this kind (f16 / i8) and block size needed: how many the next one gets enqueued up front
-    struct SliceHint { uint8_t known = 0, slices = 0, with_min = 0; } hint[2][8];
+    struct SliceHint { uint8_t known = 0, slices = 0, with_min = 0; } hint[3][8];
     // results
     DevBuf b_items;
     size_t n_items = 0;

@@ -387,6 +387,7 @@ __global__ void k_level_summary(const SliceCtl* ctl, const LevelPlan* plan, cons
                                 const uint32_t* split_last, uint32_t wants_min_pass, LevelSummary* out) {
     LevelSummary s{};
     s.mismatch = counters[0]; s.fp32_regime = counters[1]; s.flags = counters[2];
+    s.lb_candidates = *reinterpret_cast<const unsigned long long*>(counters + 4);
     s.done = 1;
     if (ctl) {
         s.passes = ctl->passes; s.evaluated = ctl->evaluated; s.overflow = ctl->overflow;
@@ -425,6 +426,13 @@ static int enqueue_slice(fe_ctx* ctx, DeviceLevelState* st, int phase, uint32_t 
     if (st->kind == 0) {
         st->fa.ordinal = ordinal;
         FE_TRY(f16_launch_search(ctx, g, st->fa, st->retire, meta, e0, e1));
+    } else if (st->kind == 2) {
+        // lower-bound prefilter: cell-sum rows of the open range blocks, the 8 x 8 contraction emitting candidates, exact check
+        const ListEntry* lists[2] = {pa.list[0], pa.list[1]};
+        FE_TRY(lb_build_rows(ctx, st->lb, pa.plan, pa.ctl, lists, ordinal, st->max_row_tiles));
+        st->fa.ordinal = ordinal;
+        FE_TRY(f16_launch_search_lb(ctx, st->fa, e0, e1));
+        FE_TRY(lb_verify(ctx, st->lb, st->d_dom, st->d_rng, st->rng_order, st->thr16, pa.ctl, ordinal));
     } else {
         const ListEntry* lists[2] = {pa.list[0], pa.list[1]};
         FE_TRY(i8_build_rows(ctx, g, pa.plan, pa.ctl, lists, ordinal, st->max_row_tiles));
@@ -439,6 +447,11 @@ static int enqueue_slice(fe_ctx* ctx, DeviceLevelState* st, int phase, uint32_t 
         cudaMemcpy(h, pa.ctl, sizeof(SliceCtl), cudaMemcpyDeviceToHost);
         float ms = 0;
         if (e0) cudaEventElapsedTime(&ms, e0, e1);
+        if (st->kind == 2) {
+            uint32_t nc = 0;
+            cudaMemcpy(&nc, st->lb.cand_count, 4, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[slice] lower-bound prefilter: %u candidates\n", nc);
+        }
         fprintf(stderr, "[slice] T=%u kind=%d ordinal=%u ran=%d k=%u..%u run_len=%u items=%u row_tiles=%u passes=%u evaluated=%.3e done=%u open=%u kernel %.3f ms\n",
                 g.T, st->kind, ordinal, h->active == ordinal, h->k0, h->k1, h->run_len, h->n_items, h->n_row_tiles, h->passes, (double)h->evaluated, h->done,
                 h->open, ms);
@@ -462,7 +475,7 @@ int search_level_more(fe_ctx* ctx, DeviceLevelState* st) {
 int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n_slices_hint, bool with_min, DeviceLevelState* st) {
     const LevelGeom& g = lv.g;
     const uint32_t nD = lv.nD, nR = lv.nR;
-    const uint32_t nt = kind == 0 ? (uint32_t)UM_NT : (uint32_t)I8_NT;
+    const uint32_t nt = kind == 1 ? (uint32_t)I8_NT : (uint32_t)UM_NT;
     const bool multipass = lv.use_thr && !getenv("FE_SINGLE_PASS");
     *st = DeviceLevelState{};
     // ---- brightness bins (host arithmetic only) ----
@@ -545,10 +558,10 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
     pa.max_items = max_items;
     pa.n_sm = (uint32_t)ctx->n_sm;
     // work items: the i8 kind reloads its A tile per item (128 KB at T = 32, one buffer): longer and fewer items there
-    pa.min_run = kind == 0 ? 16u : (g.T >= 32 ? 48u : 24u);
-    pa.items_per_sm = kind == 0 ? 8u : (g.T >= 32 ? 4u : 6u);
+    pa.min_run = kind != 1 ? 16u : (g.T >= 32 ? 48u : 24u);
+    pa.items_per_sm = kind != 1 ? 8u : (g.T >= 32 ? 4u : 6u);
     PLAUNCH(ctx, k_level_plan, 1, 512, pa, hist_d, hist_r, pre, nb, st->nbins, st->ngroups, st->span, nD, nR, nt);
-    PLAUNCH(ctx, k_level_ranges, cdiv_u((uint64_t)nR * (g.T >= 16 ? 32 : 1), 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T, kind == 0 ? 1 : 0,
+    PLAUNCH(ctx, k_level_ranges, cdiv_u((uint64_t)nR * (g.T >= 16 ? 32 : 1), 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T, kind == 1 ? 0 : 1,
             lv.flips ? 1 : 0, pa.list[0], ctx->b_posb.as<uint16_t>());
     PLAUNCH(ctx, k_fill_u64, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
     PLAUNCH(ctx, k_fill_u32, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
@@ -558,8 +571,10 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
     fa = F16Args{};
     ia = I8Args{};
     const uint32_t max_row_tiles = nR / 32 + nb;
-    if (kind == 0) {
-        FE_TRY(f16_build_pool(ctx, g, lv.d_dom, st->dom_order, pa.plan, max_tiles));
+    st->d_dom = lv.d_dom; st->d_rng = lv.d_rng; st->thr16 = lv.thr16;
+    if (kind == 0 || kind == 2) {
+        if (kind == 0) FE_TRY(f16_build_pool(ctx, g, lv.d_dom, st->dom_order, pa.plan, max_tiles));
+        else FE_TRY(lb_prepare(ctx, g, lv.d_dom, st->dom_order, pa.plan, nR, pa.list[0], max_tiles, &st->lb));
         fa.img = ctx->tgt.px; fa.stride = ctx->tgt.stride;
         fa.B16 = ctx->b_B16.p;
         fa.colmeta = ctx->b_tmaps.as<uint4>();
@@ -571,6 +586,12 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
         fa.rowhit = ctx->b_rowhit.as<uint32_t>();
         fa.flags = ctx->b_counters.as<uint32_t>() + 2;
         fa.thr16 = lv.thr16; fa.use_thr = lv.use_thr ? 1u : 0u;
+        if (kind == 2) {
+            FE_CUDA(ctx, ctx->b_A16.ensure((size_t)max_row_tiles * UM_ROWS * 80 * 2 + 256));
+            fa.A16 = ctx->b_A16.p;
+            fa.cand = st->lb.cand; fa.cand_count = st->lb.cand_count; fa.cand_cap = st->lb.cand_cap;
+            fa.thr16 = lb_threshold(lv.thr16);
+        }
     } else {
         FE_TRY(i8_build_pool(ctx, g, lv.d_dom, st->dom_order, pa.plan, nD, max_tiles));
         FE_CUDA(ctx, ctx->b_A16.ensure((size_t)max_row_tiles * UM_ROWS * i8_kpad(g) + 256));

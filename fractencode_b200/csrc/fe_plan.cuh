@@ -123,6 +123,7 @@ struct LevelSummary {
     uint32_t slices, min_ran;
     uint32_t overflow, done;              // done: the slicing is over and no minimum pass is outstanding
     unsigned long long matches;           // nominal candidates of the level: sum over classes of ranges x domains x 4
+    unsigned long long lb_candidates;     // lower-bound prefilter: candidates it let through (scored exactly)
 };
 __global__ void k_level_summary(const SliceCtl* ctl, const LevelPlan* plan, const uint32_t* counters, const uint32_t* scan_last,
                                 const uint32_t* split_last, uint32_t wants_min_pass, LevelSummary* out);
@@ -141,10 +142,16 @@ struct F16Args {
     uint32_t* flags;
     uint32_t thr16, use_thr;
     uint32_t ordinal;                     // slice ordinal this launch belongs to
+    // lower-bound prefilter (fe_lb.cu): A tiles come from a blob, candidates go to a list
+    const void* A16;                      // [row tile][K / 8][128 rows][8 halves]
+    uint2* cand;                          // {result row, domain index}
+    uint32_t* cand_count;
+    uint32_t cand_cap;
 };
 int f16_level_supported(const LevelGeom& g);   // fast geometry (S = 2T, even domain origins), T = 4 or 8
 int f16_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const uint32_t* dom_order, const LevelPlan* plan, uint32_t max_tiles);
 int f16_launch_search(fe_ctx* ctx, const LevelGeom& g, const F16Args& a, bool retire, bool meta, cudaEvent_t ev0, cudaEvent_t ev1);
+int f16_launch_search_lb(fe_ctx* ctx, const F16Args& a, cudaEvent_t ev0, cudaEvent_t ev1);
 
 // kind::i8 kernel, device-scheduled (fe_search_i8.cu)
 struct I8Args {
@@ -170,6 +177,22 @@ int i8_build_rows(fe_ctx* ctx, const LevelGeom& g, const LevelPlan* plan, const 
 int i8_launch_search(fe_ctx* ctx, const LevelGeom& g, I8Args a, cudaEvent_t ev0, cudaEvent_t ev1);
 uint32_t i8_kpad(const LevelGeom& g);
 
+// lower-bound prefilter (fe_lb.cu)
+struct LbState {
+    const uint16_t* Q = nullptr;          // c x c cell sums of the image
+    uint32_t qw = 0, c = 0, s = 0;
+    uint2* cand = nullptr;
+    uint32_t* cand_count = nullptr;
+    uint32_t cand_cap = 0;
+};
+uint32_t lb_threshold(uint32_t thr16);
+int lb_prepare(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const uint32_t* dom_order, const LevelPlan* plan, uint32_t nR,
+               ListEntry* list0, uint32_t max_tiles, LbState* lb);
+int lb_build_rows(fe_ctx* ctx, const LbState& lb, const LevelPlan* plan, const SliceCtl* ctl, const ListEntry* const list[2], uint32_t ordinal,
+                  uint32_t max_row_tiles);
+int lb_verify(fe_ctx* ctx, const LbState& lb, const fe_grid_item* d_dom, const fe_grid_item* d_rng, const uint32_t* rng_order, uint32_t thr16,
+              const SliceCtl* ctl, uint32_t ordinal);
+
 // State of one device-scheduled level between its enqueue calls.
 struct DeviceLevelState {
     bool bins = false;                    // brightness bins are on (inside the classes when there are classes)
@@ -178,7 +201,11 @@ struct DeviceLevelState {
     const uint32_t* dom_order = nullptr;  // sorted position -> domain index (NULL: identity)
     const uint32_t* rng_order = nullptr;  // level position -> range index (NULL: identity)
     // continuation
-    int kind = 0;
+    int kind = 0;                         // 0: kind::f16, 1: kind::i8, 2: lower-bound prefilter on the f16 kernel + exact verification
+    LbState lb;
+    const fe_grid_item* d_dom = nullptr;
+    const fe_grid_item* d_rng = nullptr;
+    uint32_t thr16 = 0;
     bool multipass = false, retire = false, timed = false, wants_min_pass = false;
     uint32_t slices_enqueued = 0, max_row_tiles = 0, nR = 0;
     bool min_enqueued = false;

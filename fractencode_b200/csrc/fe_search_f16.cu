@@ -102,7 +102,9 @@ __device__ __forceinline__ void build_rows(uint8_t* sAbuf, const uint8_t* __rest
 
 // RETIRE: retire quads of rows after their first threshold hit (T = 4 threshold levels: ALU bound)
 // META: runs cross chunks of the blob (brightness-bin neighbourhoods, minimum pass): per-tile metadata is read
-template <int T, bool RETIRE, bool META>
+// MODE 1: lower-bound prefilter (fe_lb.cu) -- the A tile is bulk-copied from a blob (operands are 16-bit cell sums, not
+// pixels) and the epilogue emits every column under the threshold as a candidate instead of tracking first hit / minimum
+template <int T, bool RETIRE, bool META, int MODE>
 __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) {
     constexpr uint32_t N = T * T, KPAD = (N + 3 + 15) & ~15u;
     constexpr uint32_t bytesA = UM_ROWS * KPAD * 2, bytesB = UM_NT * KPAD * 2;
@@ -259,8 +261,23 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
         };
         uint4 ent = make_uint4(0, 0, 0, 0), ent_next = make_uint4(0, 0, 0, 0);
         bool valid = false, valid_next = false;
-        fetch(blockIdx.x, ent, valid);
+        if (MODE == 0) fetch(blockIdx.x, ent, valid);
         uint32_t wi = 0;
+        if (MODE == 1) {
+            // the A tile of the item is one bulk copy from the slice's blob; the other three builder warps only sign the barrier
+            if (lane == 0)
+                for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++wi) {
+                    const uint32_t ab = wi % NA;
+                    if (wi >= NA) mbar_wait(A_EMPTY(ab), ((wi / NA) & 1) ^ 1);
+                    if (bw == 0) {
+                        const uint32_t a_tile = __ldg(&a.items[w].a_tile);
+                        mbar_expect_tx(A_FULL(ab), bytesA);
+                        bulk_g2s(smem_u32(sA + ab * bytesA), reinterpret_cast<const uint8_t*>(a.A16) + (size_t)a_tile * bytesA, bytesA, A_FULL(ab));
+                    } else {
+                        mbar_arrive(A_FULL(ab));
+                    }
+                }
+        } else {
         for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++wi) {
             const uint32_t ab = wi % NA;
             fetch(w + gridDim.x, ent_next, valid_next);
@@ -270,6 +287,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
             __syncwarp();
             if (lane == 0) mbar_arrive(A_FULL(ab));
             ent = ent_next; valid = valid_next;
+        }
         }
     } else {
         // ================= compute warps: TMEM -> registers -> row argmin =================
@@ -301,10 +319,17 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
                 const long long tt = (long long)a.thr16 - (long long)a2;
                 long long f0 = tt >= 0 ? tt / 2 : -((-tt + 1) / 2);
                 long long f1 = (tt - 1) >= 0 ? (tt - 1) / 2 : -((-(tt - 1) + 1) / 2);
-                f0 = max(-16777216ll, min(16777215ll, f0));
-                f1 = max(-16777216ll, min(16777215ll, f1));
-                st.vthr0 = (float)f0;
-                st.vthr1 = (float)f1;
+                if (MODE == 1) {
+                    // prefilter operands are 12-bit: V runs to +-2^29 and is not exact -- the threshold is rounded UP, the test
+                    // stays conservative (fe_lb.cu)
+                    st.vthr0 = __ll2float_ru(f0);
+                    st.vthr1 = __ll2float_ru(f1);
+                } else {
+                    f0 = max(-16777216ll, min(16777215ll, f0));
+                    f1 = max(-16777216ll, min(16777215ll, f1));
+                    st.vthr0 = (float)f0;
+                    st.vthr1 = (float)f1;
+                }
             }
             if (row_ok && !no_min) {
                 // Seed the running minimum with what earlier slices / column chunks already found for this row, plus one:
@@ -379,7 +404,13 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ACC_EMPTY(g, buf));
                 if (!RETIRE) chunk_change();
-                if (!(RETIRE && warp_done)) {
+                if (MODE == 1) {
+                    const size_t col0 = (size_t)item_t0 * UM_NT + colbase;
+                    candidates_half<META>(v, st.vthr0, st.vthr1, row_ok, nvalid, par, [&](uint32_t c) {
+                        const uint32_t idx = atomicAdd(a.cand_count, 1u);
+                        if (idx < a.cand_cap) a.cand[idx] = make_uint2(srow, a.blob_dom[col0 + c]);
+                    });
+                } else if (!(RETIRE && warp_done)) {
                     process_half<META>(v, st, RETIRE ? !retired : row_ok, colbase, nvalid, par, no_min == 0);
                     if (RETIRE && (j & 3) == 3) {   // every 4th tile is enough: retirement only saves work
                         uint32_t hm = __ballot_sync(0xFFFFFFFFu, st.hit != FE_NONE32);
@@ -517,8 +548,8 @@ template <int T>
 static int launch_T(fe_ctx* ctx, const F16Args& a, bool retire, bool meta, cudaEvent_t ev0, cudaEvent_t ev1) {
     constexpr uint32_t Kpad = (T * T + 3 + 15u) & ~15u;
     const size_t smem = (size_t)F16_ABUFS * UM_ROWS * Kpad * 2 + (size_t)F16_STAGES * UM_NT * Kpad * 2 + (8 + F16_STAGES + 2 * F16_ABUFS) * 8 + 64;
-    auto kern = retire ? (meta ? k_search_f16<T, true, true> : k_search_f16<T, true, false>)
-                       : (meta ? k_search_f16<T, false, true> : k_search_f16<T, false, false>);
+    auto kern = retire ? (meta ? k_search_f16<T, true, true, 0> : k_search_f16<T, true, false, 0>)
+                       : (meta ? k_search_f16<T, false, true, 0> : k_search_f16<T, false, false, 0>);
     FE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (ev0) cudaEventRecord(ev0, ctx->stream);
     kern<<<ctx->n_sm, F16_THREADS, smem, ctx->stream>>>(a);
@@ -530,4 +561,18 @@ static int launch_T(fe_ctx* ctx, const F16Args& a, bool retire, bool meta, cudaE
 
 int f16_launch_search(fe_ctx* ctx, const LevelGeom& g, const F16Args& a, bool retire, bool meta, cudaEvent_t ev0, cudaEvent_t ev1) {
     return g.T == 4 ? launch_T<4>(ctx, a, retire, meta, ev0, ev1) : launch_T<8>(ctx, a, retire, meta, ev0, ev1);
+}
+
+// lower-bound prefilter launch: the T' = 8 contraction on cell sums, candidates out (fe_lb.cu)
+int f16_launch_search_lb(fe_ctx* ctx, const F16Args& a, cudaEvent_t ev0, cudaEvent_t ev1) {
+    constexpr uint32_t Kpad = (8 * 8 + 3 + 15u) & ~15u;
+    const size_t smem = (size_t)F16_ABUFS * UM_ROWS * Kpad * 2 + (size_t)F16_STAGES * UM_NT * Kpad * 2 + (8 + F16_STAGES + 2 * F16_ABUFS) * 8 + 64;
+    auto kern = k_search_f16<8, false, true, 1>;
+    FE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (ev0) cudaEventRecord(ev0, ctx->stream);
+    kern<<<ctx->n_sm, F16_THREADS, smem, ctx->stream>>>(a);
+    FE_CUDA(ctx, cudaGetLastError());
+    if (ev1) cudaEventRecord(ev1, ctx->stream);
+    ctx->stats.kernel_launches++;
+    return FE_OK;
 }

@@ -139,4 +139,39 @@ __device__ __forceinline__ void process_half(uint32_t (&v)[UM_HALF], RowState& s
     }
 }
 
+// Lower-bound prefilter (fe_lb.cu): every column of the half tile whose value is at or below the row's threshold is a
+// CANDIDATE and is handed to `emit` (column inside the half tile); nothing else is tracked.
+template <bool META, typename Emit>
+__device__ __forceinline__ void candidates_half(uint32_t (&v)[UM_HALF], float vthr0, float vthr1, bool row_ok, uint32_t nvalid, const ParitySrc& par,
+                                                Emit&& emit) {
+    if (nvalid < UM_HALF) {
+#pragma unroll
+        for (int i = 0; i < UM_HALF; ++i)
+            if ((uint32_t)i >= nvalid) v[i] = 0x7F61B1E6u; // 3.0e38f
+    }
+    float grp[UM_HALF / 8];
+#pragma unroll
+    for (int k = 0; k < UM_HALF / 8; ++k) {
+        const float a = fmin3(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1]), __uint_as_float(v[8 * k + 2]));
+        const float b = fmin3(__uint_as_float(v[8 * k + 3]), __uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5]));
+        grp[k] = fmin3(fminf(a, b), __uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7]));
+    }
+    float t0 = 3.0e38f, t1 = 3.0e38f;
+#pragma unroll
+    for (int k = 0; k < UM_HALF / 8; k += 4) {
+        t0 = fmin3(t0, grp[k], grp[k + 1]);
+        t1 = fmin3(t1, grp[k + 2], grp[k + 3]);
+    }
+    if (!(row_ok && fminf(t0, t1) <= vthr0)) return;
+#pragma unroll
+    for (int k = 0; k < UM_HALF / 8; ++k) {
+        if (grp[k] <= vthr0) {
+            const uint32_t pw = par_word<META>(par, (8 * k) >> 5) >> ((8 * k) & 31);
+#pragma unroll
+            for (int e2 = 0; e2 < 8; ++e2)
+                if (__uint_as_float(v[8 * k + e2]) <= (((pw >> e2) & 1u) ? vthr1 : vthr0)) emit((uint32_t)(8 * k + e2));
+        }
+    }
+}
+
 } // namespace umma_dev

@@ -98,6 +98,9 @@ typedef struct {
                                 * blocks stop at their first hit (the reference's break, TransformEstimator2.hpp:40-41) */
     uint64_t level_evaluated[8]; /* last quadtree: evaluated per level */
     uint64_t level_passes[8];  /* last quadtree: search passes (kernel launches) per level */
+    uint64_t prefiltered;      /* candidates only looked at by the lower-bound prefilter of the large-block levels (an 8 x 8 bound,
+                                * 64 products each; those it lets through are scored exactly and count as `evaluated`) */
+    uint64_t level_prefiltered[8];
 } fe_stats;
 
 typedef struct fe_ctx fe_ctx;

@@ -31,8 +31,10 @@ class _Env:
                 os.environ[k] = v
 
 
-# FE_CLASS_BINS forces the brightness bins inside classifier classes on levels too small for them to pay
-MODES = {"pruned": {"FE_CLASS_BINS": "1"}, "slices_only": {"FE_NO_BINS": "1"}, "one_pass": {"FE_SINGLE_PASS": "1"}}
+# default = slices + brightness bins (+ the lower-bound prefilter on the T = 32 level); "no_prefilter" takes the exact kind there;
+# "one_pass" = one full scan per level, no pruning of any kind
+MODES = {"pruned": {}, "no_prefilter": {"FE_NO_LB": "1"}, "slices_only": {"FE_NO_BINS": "1", "FE_NO_LB": "1"},
+         "one_pass": {"FE_SINGLE_PASS": "1", "FE_NO_LB": "1"}}
 
 
 @pytest.mark.parametrize("kind,cls,thr", [(0, False, 25.0), (0, False, 6.0), (0, True, 25.0), (1, False, 40.0), (2, False, 25.0)])
@@ -50,7 +52,7 @@ def test_quadtree_pruned_equals_one_pass(ctx, kind, cls, thr):
             out[name] = (items, counts, int(st.matches), int(st.evaluated))
     ref_items, ref_counts, ref_matches, ref_eval = out["one_pass"]
     assert ref_eval == ref_matches, "the one-pass search scores every admissible candidate"
-    for name in ("pruned", "slices_only"):
+    for name in ("pruned", "no_prefilter", "slices_only"):
         items, counts, matches, evaluated = out[name]
         assert counts == ref_counts and matches == ref_matches
         # worst case on the last level: the bins (about a third of the scan) found hits for some ranges only, the rest
