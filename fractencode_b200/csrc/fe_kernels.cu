@@ -543,11 +543,32 @@ __global__ void k_finalize_t(FinalizeArgs f) {
     // ---- exact sums for the winner ----
     const uint32_t T = r.w, N = T * T, rho = dm.w / T;
     uint32_t sA = 0, sA2 = 0, sB = 0, sAB = 0, sB2 = 0;
-    for (uint32_t e = lane; e < N; e += LPR) {
-        const uint32_t ty = e / T, tx = e % T;
-        const uint32_t a = f.tgt[(size_t)(r.y + ty) * f.tgt_stride + r.x + tx];
-        const uint32_t D = (uint32_t)sample_sum4(f.src, f.src_stride, dm.x, dm.y, dm.w, tx * rho, ty * rho, wk);
-        sA += a; sA2 += a * a; sB += D; sAB += a * D; sB2 += D * D;
+    if (rho == 2 && wk < 4 && (T & 1u) == 0 && ((dm.x | f.src_stride) & 3u) == 0 && (reinterpret_cast<uintptr_t>(f.src) & 3u) == 0) {
+        // The common case (S = 2T, a rotation): a lane takes whole rows of the decimated domain block -- two source rows read as
+        // words, two box sums per word pair -- against the range block under the INVERSE rotation (the same pairs as below).
+        for (uint32_t ty = lane; ty < T; ty += LPR) {
+            const uint32_t* q0 = reinterpret_cast<const uint32_t*>(f.src + (size_t)(dm.y + 2 * ty) * f.src_stride + dm.x);
+            const uint32_t* q1 = reinterpret_cast<const uint32_t*>(f.src + (size_t)(dm.y + 2 * ty + 1) * f.src_stride + dm.x);
+            for (uint32_t tx = 0; tx < T; tx += 2) {
+                const uint32_t w0 = __ldg(q0 + tx / 2), w1 = __ldg(q1 + tx / 2);
+                const uint32_t dd = (w0 & 0x00FF00FFu) + ((w0 >> 8) & 0x00FF00FFu) + (w1 & 0x00FF00FFu) + ((w1 >> 8) & 0x00FF00FFu);
+#pragma unroll
+                for (uint32_t j = 0; j < 2; ++j) {
+                    const uint32_t D = j ? dd >> 16 : dd & 0xFFFFu, x = tx + j;
+                    const uint32_t py = wk == 0 ? ty : wk == 1 ? x : wk == 2 ? T - 1 - ty : T - 1 - x;
+                    const uint32_t px = wk == 0 ? x : wk == 1 ? T - 1 - ty : wk == 2 ? T - 1 - x : ty;
+                    const uint32_t a = f.tgt[(size_t)(r.y + py) * f.tgt_stride + r.x + px];
+                    sA += a; sA2 += a * a; sB += D; sAB += a * D; sB2 += D * D;
+                }
+            }
+        }
+    } else {
+        for (uint32_t e = lane; e < N; e += LPR) {
+            const uint32_t ty = e / T, tx = e % T;
+            const uint32_t a = f.tgt[(size_t)(r.y + ty) * f.tgt_stride + r.x + tx];
+            const uint32_t D = (uint32_t)sample_sum4(f.src, f.src_stride, dm.x, dm.y, dm.w, tx * rho, ty * rho, wk);
+            sA += a; sA2 += a * a; sB += D; sAB += a * D; sB2 += D * D;
+        }
     }
     for (int o = LPR / 2; o; o >>= 1) {
         sA += __shfl_xor_sync(gmask, sA, o);

@@ -277,7 +277,7 @@ int lb_build_rows(fe_ctx* ctx, const LbState& lb, const LevelPlan* plan, const S
 
 int lb_verify(fe_ctx* ctx, const LbState& lb, const fe_grid_item* d_dom, const fe_grid_item* d_rng, const uint32_t* rng_order, uint32_t thr16,
               const SliceCtl* ctl, uint32_t ordinal) {
-    k_lb_verify<<<4 * ctx->n_sm, 256, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, ctx->tgt.px, ctx->tgt.stride, d_dom, d_rng, rng_order, lb.cand,
+    k_lb_verify<<<16 * ctx->n_sm, 256, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, ctx->tgt.px, ctx->tgt.stride, d_dom, d_rng, rng_order, lb.cand,
                                                        lb.cand_count, lb.cand_cap, thr16, ctl, ordinal, ctx->b_rowhit.as<uint32_t>(),
                                                        ctx->b_counters.as<uint32_t>() + 2, reinterpret_cast<unsigned long long*>(ctx->b_counters.as<uint32_t>() + 4));
     FE_CUDA(ctx, cudaGetLastError());
