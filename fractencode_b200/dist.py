@@ -34,6 +34,9 @@ class PackedGather:
         self.send = torch.zeros(self.words, dtype=torch.int64, device=device)
         self.recv = torch.zeros((self.world, self.words), dtype=torch.int64, device=device) if self.rank == 0 else None
         self.red = torch.zeros(4, dtype=torch.float64, device=device)
+        self.count_host = torch.zeros(1, dtype=torch.int64)
+        if torch.device(device).type == "cuda":
+            self.count_host = self.count_host.pin_memory()      # the count goes up with an asynchronous copy, no host stall
 
     def gather(self, ctx, n_items: int, t_max: int, shared_image: bool, bits=(5, 7)):
         """Pack this rank's device-resident result list and gather all lists on rank 0.
@@ -59,7 +62,8 @@ class PackedGather:
 
     def exchange(self, n_items: int):
         """Ship `send` (header + records) to rank 0; the count travels in word 0."""
-        self.send[0] = int(n_items)
+        self.count_host[0] = int(n_items)
+        self.send[0:1].copy_(self.count_host, non_blocking=True)
         if self.world == 1:
             return self.send.view(1, -1)
         dist.gather(self.send, [self.recv[r] for r in range(self.world)] if self.rank == 0 else None, dst=0, group=self.group)
