@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
             }
             s_tiles[c] = cols ? (s_cnt[c] + 31) / 32 : 0u;
             work += cols * s_cnt[c] * 4ull;
-            steps += run * s_tiles[c];
+            steps += run * ((s_tiles[c] + a.tiles_per_item - 1) / a.tiles_per_item);
         }
         work = block_sum_u64(work, s_red);
         steps = block_sum_u64(steps, s_red);
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
                     per_tile += (nrun + run_len - 1) / run_len;
                 }
             }
-            s_cnt[c] = s_tiles[c] * per_tile;          // work items of the bucket (s_cnt is not needed any more)
+            s_cnt[c] = ((s_tiles[c] + a.tiles_per_item - 1) / a.tiles_per_item) * per_tile;   // work items of the bucket (s_cnt is not needed any more)
         }
         __syncthreads();
         if (t == 0) {
@@ -360,7 +360,8 @@ __global__ void k_expand_items(PlanArgs a, uint32_t ordinal) {
             if (ctl->item_prefix[mid] <= id) lo = mid; else hi = mid - 1;
         }
         const uint32_t c = lo, blo = grp_lo(p, c, whole), bhi = grp_hi(p, c, whole);
-        const uint32_t cnt = ctl->cnt[cur][c], ntile = (cnt + 31) / 32;
+        const uint32_t tpi = a.tiles_per_item, rpi = 32 * tpi;          // row tiles / range blocks per work item
+        const uint32_t cnt = ctl->cnt[cur][c], ntile = (cnt + rpi - 1) / rpi;
         const uint32_t per_tile = (ctl->item_prefix[c + 1] - ctl->item_prefix[c]) / ntile;
         uint32_t rem = id - ctl->item_prefix[c];
         const uint32_t rt = rem / per_tile;
@@ -371,10 +372,10 @@ __global__ void k_expand_items(PlanArgs a, uint32_t ordinal) {
             if (rem < q) {
                 r.t0 = T0 + (uint32_t)(((uint64_t)rem * nrun) / q);
                 r.t1 = T0 + (uint32_t)(((uint64_t)(rem + 1) * nrun) / q);
-                r.pos0 = p->roff[c] + 32 * rt;
-                r.nrows = 4 * min(32u, cnt - 32 * rt);
+                r.pos0 = p->roff[c] + rpi * rt;
+                r.nrows = 4 * min(rpi, cnt - rpi * rt);
                 r.cols_left = (p->dend[k][blo] - (k ? p->dend[k - 1][blo] : 0u)) - (r.t0 - T0) * nt;
-                r.a_tile = ctl->tile_prefix[c] + rt;
+                r.a_tile = ctl->tile_prefix[c] + tpi * rt;
                 break;
             }
             rem -= q;
@@ -560,6 +561,9 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
     // work items: the i8 kind reloads its A tile per item (128 KB at T = 32, one buffer): longer and fewer items there
     pa.min_run = kind != 1 ? 16u : (g.T >= 32 ? 48u : 24u);
     pa.items_per_sm = kind != 1 ? 8u : (g.T >= 32 ? 4u : 6u);
+    // i8 kind up to T = 16: a work item is TWO row tiles (64 range blocks, M = 256 through two accumulator pairs) sharing every
+    // B stage -- halves the L2 -> shared-memory operand stream, which bounds the kernel before the tensor pipe does
+    pa.tiles_per_item = (kind == 1 && g.T <= 16 && !getenv("FE_NO_PAIR")) ? 2u : 1u;
     PLAUNCH(ctx, k_level_plan, 1, 512, pa, hist_d, hist_r, pre, nb, st->nbins, st->ngroups, st->span, nD, nR, nt);
     PLAUNCH(ctx, k_level_ranges, cdiv_u((uint64_t)nR * (g.T >= 16 ? 32 : 1), 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T, kind == 1 ? 0 : 1,
             lv.flips ? 1 : 0, pa.list[0], ctx->b_posb.as<uint16_t>());
@@ -594,7 +598,7 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
         }
     } else {
         FE_TRY(i8_build_pool(ctx, g, lv.d_dom, st->dom_order, pa.plan, nD, max_tiles));
-        FE_CUDA(ctx, ctx->b_A16.ensure((size_t)max_row_tiles * UM_ROWS * i8_kpad(g) + 256));
+        FE_CUDA(ctx, ctx->b_A16.ensure((size_t)(max_row_tiles + 2) * UM_ROWS * i8_kpad(g) + 256));
         ia.A8 = ctx->b_A16.p;
         ia.B8 = ctx->b_B16.p;
         ia.tileseg = ctx->b_tileseg.as<uint32_t>();
@@ -606,6 +610,7 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
         ia.rowbest = ctx->b_rowbest.as<unsigned long long>();
         ia.rowhit = ctx->b_rowhit.as<uint32_t>();
         ia.thr16 = lv.thr16; ia.use_thr = lv.use_thr ? 1u : 0u;
+        ia.pair = pa.tiles_per_item == 2 ? 1u : 0u;
     }
     st->kind = kind;
     st->multipass = multipass;

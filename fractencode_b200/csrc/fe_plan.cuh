@@ -90,6 +90,7 @@ struct PlanArgs {
     uint32_t max_items;
     uint32_t n_sm;
     uint32_t min_run, items_per_sm;       // work items: never shorter than min_run column tiles, about items_per_sm per SM
+    uint32_t tiles_per_item;              // row tiles of a work item: 1, or 2 (i8 kind, M = 256)
 };
 
 enum { FE_PHASE_SLICE = 0, FE_PHASE_MIN = 1 };
@@ -168,6 +169,7 @@ struct I8Args {
     uint32_t thr16, use_thr, meta;
     uint32_t Kpad, stages, n_abuf;
     uint32_t ordinal;
+    uint32_t pair;                        // work items are pairs of row tiles (rows 0-127 / 128-255 of the A tile): one compute warpgroup each
 };
 int i8_level_supported(const LevelGeom& g);    // fast geometry, 4 <= T <= 32
 int i8_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const uint32_t* dom_order, const LevelPlan* plan, uint32_t nD,

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_i8(const I8Args a) 
     const uint32_t Kpad = a.Kpad;
     const uint32_t kc = min(Kpad, (uint32_t)I8_KC);          // bytes of K per stage
     const uint32_t nch = Kpad / kc;                          // stages per tile
-    const uint32_t bytesA = UM_ROWS * Kpad, bytesB = 2 * I8_NT * kc;
+    const uint32_t pair = a.pair;                            // M = 256: two row tiles per item, warpgroup g owns row tile g
+    const uint32_t bytesA1 = UM_ROWS * Kpad, bytesA = (pair ? 2u : 1u) * bytesA1, bytesB = 2 * I8_NT * kc;
     const uint32_t S = a.stages, NA = a.n_abuf;
     uint8_t* sA = smem;
     uint8_t* sB = smem + NA * bytesA;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_i8(const I8Args a) 
         }
         for (uint32_t i = 0; i < S; ++i) {
             mbar_init(B_FULL(i), 1);
-            mbar_init(B_EMPTY(i), 1);
+            mbar_init(B_EMPTY(i), pair ? 2 : 1);          // pair: the issuers of both row tiles release a stage
         }
         tmem_slot[4] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_i8(const I8Args a) 
                 // the bulk copy engine takes at most ~1 MB per request; 128 KB tiles go as 32 KB pieces
                 for (uint32_t off = 0; off < bytesA; off += 32768) {
                     const uint32_t n = min(32768u, bytesA - off);
-                    bulk_g2s(smem_u32(sA + ab * bytesA + off), reinterpret_cast<const uint8_t*>(a.A8) + (size_t)a_tile * bytesA + off, n, A_FULL(ab));
+                    bulk_g2s(smem_u32(sA + ab * bytesA + off), reinterpret_cast<const uint8_t*>(a.A8) + (size_t)a_tile * bytesA1 + off, n, A_FULL(ab));
                 }
                 for (uint32_t t = rec.z; t < rec.w; ++t)
                     for (uint32_t c = 0; c < nch; ++c, ++ic) {
@@ -129,11 +130,12 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_i8(const I8Args a) 
             for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++wi) {
                 const uint4 rec = item_rec(w);
                 const uint32_t ab = wi % NA, n = rec.w - rec.z;
-                const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
+                // single tiles: the column tiles alternate between the warpgroups; pairs: every column tile goes to both (row tile g)
+                const uint32_t first = pair ? 0u : (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS, ustep = pair ? 1u : (uint32_t)UM_WGS;
                 mbar_wait(A_FULL(ab), (wi / NA) & 1);
-                const uint32_t a_addr = smem_u32(sA + ab * bytesA);
+                const uint32_t a_addr = smem_u32(sA + ab * bytesA) + (pair ? g * bytesA1 : 0u);
                 bool any = false;
-                for (uint32_t u = first; u < n; u += UM_WGS, ++jb) {
+                for (uint32_t u = first; u < n; u += ustep, ++jb) {
                     const uint32_t gi = it0 + u, buf = jb & 1;
                     if (buf != ib) continue;
                     const uint32_t d_lo = tmem_base + (g * 2 + buf) * 2 * I8_NT, d_hi = d_lo + I8_NT;
@@ -174,10 +176,11 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_i8(const I8Args a) 
         for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
             const uint4 rec = item_rec(w);
             const uint32_t item_t0 = rec.z, n = rec.w - rec.z;
-            const bool row_ok = lrow < rec.y;
+            const uint32_t irow = pair ? g * UM_ROWS + lrow : lrow;     // row inside the item (pairs: 256 rows, warpgroup g has rows 128 g ..)
+            const bool row_ok = irow < rec.y;
             uint32_t slot = 0, rc = 0;                // rc = 16 * sum r^2
             if (row_ok) {
-                const uint4 ent = __ldg(reinterpret_cast<const uint4*>(list + rec.x + (lrow >> 2)));
+                const uint4 ent = __ldg(reinterpret_cast<const uint4*>(list + rec.x + (irow >> 2)));
                 slot = ent.x; rc = ent.z;
             }
             const uint32_t srow = 4u * slot + (lrow & 3u);   // result row of the level
@@ -188,10 +191,10 @@ __global__ void __launch_bounds__(UM_THREADS_I8, 1) k_search_i8(const I8Args a) 
             int bestw = 0x7FFFFFFF;
             uint32_t bestcol = FE_NONE32, hit = FE_NONE32;
             uint32_t cur_seg = FE_NONE32;       // chunk of the tiles this thread is scanning
-            const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
-            const uint32_t my_tiles = first < n ? (n - first + UM_WGS - 1) / UM_WGS : 0;
+            const uint32_t first = pair ? 0u : (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS, ustep = pair ? 1u : (uint32_t)UM_WGS;
+            const uint32_t my_tiles = first < n ? (n - first + ustep - 1) / ustep : 0;
             for (uint32_t j = 0; j < my_tiles; ++j, ++jb) {
-                const uint32_t u = first + j * UM_WGS, buf = jb & 1;
+                const uint32_t u = first + j * ustep, buf = jb & 1;
                 const uint32_t colbase = u * I8_NT + h * 32;             // column inside the item
                 const uint32_t taddr = lane_addr + (g * 2 + buf) * 2 * I8_NT;
                 // runs that cross chunks of the blob (brightness-bin neighbourhoods, minimum pass): chunk id of the tile, loaded
@@ -530,7 +533,7 @@ int i8_build_rows(fe_ctx* ctx, const LevelGeom& g, const LevelPlan* plan, const 
 int i8_launch_search(fe_ctx* ctx, const LevelGeom& g, I8Args a, cudaEvent_t ev0, cudaEvent_t ev1) {
     const uint32_t Kpad = i8_kpad(g), kc = std::min(Kpad, (uint32_t)I8_KC);
     a.Kpad = Kpad;
-    const uint32_t stage_bytes = 2 * I8_NT * kc, a_bytes = UM_ROWS * Kpad;
+    const uint32_t stage_bytes = 2 * I8_NT * kc, a_bytes = (a.pair ? 2u : 1u) * UM_ROWS * Kpad;
     const uint32_t budget = 226 * 1024 - 512;
     a.n_abuf = (2 * a_bytes + 2 * stage_bytes <= budget) ? 2 : 1;
     uint32_t stages = (budget - a.n_abuf * a_bytes) / stage_bytes;
