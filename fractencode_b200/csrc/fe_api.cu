@@ -6,6 +6,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -146,7 +147,7 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
                       &ctx->b_rowc, &ctx->b_coln, &ctx->b_rowbest, &ctx->b_rowhit, &ctx->b_hist, &ctx->b_level_items, &ctx->b_split,
                       &ctx->b_scan, &ctx->b_scan_tmp, &ctx->b_rng_next, &ctx->b_counters, &ctx->b_A16, &ctx->b_B16, &ctx->b_tmaps,
                       &ctx->b_items, &ctx->b_dec_a, &ctx->b_dec_b, &ctx->b_dec_items, &ctx->b_dec_sum, &ctx->b_q, &ctx->b_bound,
-                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_dom_order2, &ctx->b_rng_order2, &ctx->b_rng2, &ctx->b_pos_of, &ctx->b_lbq, &ctx->b_lbcand};
+                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_dom_order2, &ctx->b_rng_order2, &ctx->b_rng2, &ctx->b_pos_of, &ctx->b_lbq, &ctx->b_lbcand, &ctx->b_cells};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
@@ -265,6 +266,7 @@ struct LevelIO {
     uint32_t* d_split = nullptr;     // [nR] or NULL
     int can_split = 0;
     int lattice = 0;                 // the blocks lie on the quadtree's lattices (range origins multiples of T, domain origins of T)
+    uint32_t dnx = 0;                // lattice: domains per row, domain d has its origin at (T (d % dnx), T (d / dnx))
     int stat_level = -1;             // quadtree level index for the per-level stats, -1 = none
 };
 
@@ -405,8 +407,10 @@ static int run_level_exact(fe_ctx* ctx, const LevelIO& io, const fe_params& p) {
     if (p.use_classifier && nD) {
         FE_CUDA(ctx, ctx->b_dom_cls.ensure((size_t)nD * 4));
         FE_CUDA(ctx, ctx->b_rng_cls.ensure((size_t)nR * 4));
-        LAUNCH(ctx, k_classify, cdiv((uint64_t)nD * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, nD, ctx->b_dom_cls.as<int32_t>(), 0);
-        LAUNCH(ctx, k_classify, cdiv((uint64_t)nR * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, ctx->b_rng_cls.as<int32_t>(), 0);
+        launch_classify(ctx->stream, ctx->src.px, ctx->src.stride, io.d_dom, nD, g.S, ctx->b_dom_cls.as<int32_t>(), 0);
+        launch_classify(ctx->stream, ctx->tgt.px, ctx->tgt.stride, io.d_rng, nR, g.T, ctx->b_rng_cls.as<int32_t>(), 0);
+        ctx->stats.kernel_launches += 2;
+        FE_CUDA(ctx, cudaGetLastError());
         FE_TRY(bucket_by_class(ctx, ctx->b_dom_cls.as<int32_t>(), nD, ctx->b_dom_order, doff));
         FE_TRY(bucket_by_class(ctx, ctx->b_rng_cls.as<int32_t>(), nR, ctx->b_rng_order, roff));
         dom_order = ctx->b_dom_order.as<uint32_t>();
@@ -569,11 +573,21 @@ static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p,
     FE_CUDA(ctx, ctx->b_rowhit.ensure((size_t)nS * 4 * 4));
     DeviceLevel lv{};
     lv.d_dom = io.d_dom; lv.nD = nD; lv.d_rng = d_rng; lv.nR = nS; lv.g = g; lv.flips = flips;
+    // lattice levels: the image's T x T cell sums give every domain its class and its brightness bin (fe_kernels.cu)
+    if (io.lattice && io.dnx && g.S == 2 * g.T && (p.use_classifier || lp->use_thr) && cell_grid_supported(ctx->src.px, ctx->src.stride, ctx->src.w, ctx->src.h, g.T) && !getenv("FE_NO_CELLS")) {
+        FE_CUDA(ctx, ctx->b_cells.ensure((size_t)(ctx->src.w / g.T) * (ctx->src.h / g.T) * 4));
+        launch_cell_grid(ctx->stream, ctx->src.px, ctx->src.stride, ctx->src.w, ctx->src.h, g.T, ctx->b_cells.as<uint32_t>());
+        ctx->stats.kernel_launches++;
+        lv.cells = ctx->b_cells.as<uint32_t>(); lv.cells_w = ctx->src.w / g.T; lv.dnx = io.dnx;
+    }
     if (p.use_classifier) {
         FE_CUDA(ctx, ctx->b_dom_cls.ensure((size_t)nD * 4));
         FE_CUDA(ctx, ctx->b_rng_cls.ensure((size_t)nS * 4));
-        LAUNCH(ctx, k_classify, cdiv((uint64_t)nD * 32, 256), 256, ctx->src.px, ctx->src.stride, io.d_dom, nD, ctx->b_dom_cls.as<int32_t>(), 0);
-        LAUNCH(ctx, k_classify, cdiv((uint64_t)nS * 32, 256), 256, ctx->tgt.px, ctx->tgt.stride, d_rng, nS, ctx->b_rng_cls.as<int32_t>(), 0);
+        if (lv.cells) launch_dom_from_cells(ctx->stream, lv.cells, lv.cells_w, lv.dnx, nD, ctx->b_dom_cls.as<int32_t>(), 1u, nullptr, nullptr);
+        else launch_classify(ctx->stream, ctx->src.px, ctx->src.stride, io.d_dom, nD, g.S, ctx->b_dom_cls.as<int32_t>(), 0);
+        launch_classify(ctx->stream, ctx->tgt.px, ctx->tgt.stride, d_rng, nS, g.T, ctx->b_rng_cls.as<int32_t>(), 0);
+        ctx->stats.kernel_launches += 2;
+        FE_CUDA(ctx, cudaGetLastError());
         lv.dom_cls = ctx->b_dom_cls.as<int32_t>();
         lv.rng_cls = ctx->b_rng_cls.as<int32_t>();
     }
@@ -871,9 +885,13 @@ static int quad_enqueue(fe_ctx* ctx) {
     io.d_out = ctx->b_level_items.as<fe_encode_item>();
     io.can_split = (T / 2 >= j->t_min) ? 1 : 0;
     io.lattice = 1;
+    io.dnx = dnx;
     io.d_split = ctx->b_split.as<uint32_t>();
     io.stat_level = j->level;
+    const auto h0 = std::chrono::steady_clock::now();
     FE_TRY(run_level_enqueue(ctx, io, j->params, &j->lp));
+    if (getenv("FE_PASS_TIMES"))
+        fprintf(stderr, "[level] T=%u host enqueue %.1f us\n", T, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count());
     j->level_open = true;
     return FE_OK;
 }

@@ -139,6 +139,73 @@ __global__ void k_classify(const uint8_t* __restrict__ img, uint32_t stride, con
     if (lane == 0) cls[warp] = category4(a[0], a[1], a[2], a[3]);
 }
 
+// The same classes for a list of square blocks of one power-of-two edge (every list of a search level): min(EDGE, 32) lanes per
+// block instead of a warp, a lane sums the left and the right half of its rows with 4-byte loads.  A block of another size or at
+// an unaligned origin is summed pixel by pixel by the group's first lane (same result, the slow way).
+template <int EDGE>
+__global__ void __launch_bounds__(256) k_classify_edge(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ items, uint32_t n,
+                                                       int32_t* __restrict__ cls, int force) {
+    constexpr int L = EDGE < 32 ? EDGE : 32, RPL = EDGE / L, HALF = EDGE / 2;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, item = t / L, lane = t % L;
+    const bool live = item < n;
+    fe_grid_item it{};
+    if (live) it = items[item];
+    const bool keep = live && !force && it.bin != -1;
+    const bool regular = it.w == EDGE && it.h == EDGE && (((uint32_t)it.x | stride | (uint32_t)(reinterpret_cast<uintptr_t>(img) & 3u)) & 3u) == 0;
+    uint32_t a[4] = {0, 0, 0, 0};
+    if (live && !keep) {
+        if (regular) {
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                const int r = (int)lane + k * L;
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(img + (size_t)(it.y + r) * stride + it.x);
+                uint32_t l = 0, rr = 0;
+                if (EDGE == 4) {
+                    const uint32_t v = __ldg(row);
+                    l = __dp4a(v, 0x00000101u, 0u); rr = __dp4a(v, 0x01010000u, 0u);
+                } else {
+#pragma unroll
+                    for (int w = 0; w < EDGE / 8; ++w) {
+                        l = __dp4a(__ldg(row + w), 0x01010101u, l);
+                        rr = __dp4a(__ldg(row + EDGE / 8 + w), 0x01010101u, rr);
+                    }
+                }
+                if (r < HALF) { a[0] += l; a[1] += rr; } else { a[2] += l; a[3] += rr; }
+            }
+        } else if (lane == 0) {
+            const uint32_t hw = it.w / 2, hh = it.h / 2;
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t qx = it.x + (q & 1) * hw, qy = it.y + (q >> 1) * hh;
+                uint32_t s = 0;
+                for (uint32_t p = 0; p < hw * hh; ++p) s += img[(size_t)(qy + p / hw) * stride + qx + p % hw];
+                a[q] = hw <= 16 ? (s & 0xFFFFu) : s;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = L / 2; o; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] += __shfl_xor_sync(0xFFFFFFFFu, a[q], o);
+    }
+    if (live && lane == 0) cls[item] = keep ? it.bin : category4(a[0], a[1], a[2], a[3]);
+}
+
+// classes of a list whose blocks are (expected to be) edge x edge
+void launch_classify(cudaStream_t stream, const uint8_t* img, uint32_t stride, const fe_grid_item* items, uint32_t n, uint32_t edge, int32_t* cls, int force) {
+    if (!n) return;
+    const uint64_t lanes = (uint64_t)n * (edge < 32 ? edge : 32);
+    const unsigned grid = (unsigned)((lanes + 255) / 256);
+    switch (edge) {
+    case 4: k_classify_edge<4><<<grid, 256, 0, stream>>>(img, stride, items, n, cls, force); break;
+    case 8: k_classify_edge<8><<<grid, 256, 0, stream>>>(img, stride, items, n, cls, force); break;
+    case 16: k_classify_edge<16><<<grid, 256, 0, stream>>>(img, stride, items, n, cls, force); break;
+    case 32: k_classify_edge<32><<<grid, 256, 0, stream>>>(img, stride, items, n, cls, force); break;
+    case 64: k_classify_edge<64><<<grid, 256, 0, stream>>>(img, stride, items, n, cls, force); break;
+    case 128: k_classify_edge<128><<<grid, 256, 0, stream>>>(img, stride, items, n, cls, force); break;
+    default: k_classify<<<(unsigned)(((uint64_t)n * 32 + 255) / 256), 256, 0, stream>>>(img, stride, items, n, cls, force);
+    }
+}
+
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -189,6 +256,64 @@ void launch_brightness_bins(cudaStream_t stream, const uint8_t* img, uint32_t st
     if (!n) return;
     if (edge <= 16) k_brightness_bins_t<false><<<(n + 127) / 128, 128, 0, stream>>>(img, stride, items, n, edge, mul, width, keys, hist);
     else k_brightness_bins_t<true><<<(unsigned)(((uint64_t)n * 32 + 255) / 256), 256, 0, stream>>>(img, stride, items, n, edge, mul, width, keys, hist);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the domain lattice of a quadtree level through cell sums
+// ---------------------------------------------------------------------------------------------
+// On the quadtree's lattice a domain block (origin (T i, T j), edge 2T) is 2 x 2 cells of T x T pixels: one coalesced pass over
+// the image gives every cell sum, and both the Classifier2 class (quadrant sums = the four cells) and the brightness bin (their
+// total) of every domain come from four 4-byte reads -- instead of every domain re-reading its own (overlapping) pixels.
+// cells[j][i] = sum of the C x C pixels at (C i, C j), C a power of two in 4..64: a thread adds up a 4-pixel wide column of a cell
+// row, C / 4 neighbouring lanes combine.
+__global__ void __launch_bounds__(256) k_cell_grid(const uint8_t* __restrict__ img, uint32_t stride, uint32_t wpr, uint32_t ch, uint32_t C,
+                                                   uint32_t* __restrict__ cells) {
+    const uint32_t wx = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y, lanes = C / 4;
+    const bool live = wx < wpr && j < ch;
+    uint32_t s = 0;
+    if (live) {
+        const uint8_t* p = img + (size_t)(C * j) * stride + 4 * (size_t)wx;
+        for (uint32_t y = 0; y < C; ++y) s = __dp4a(__ldg(reinterpret_cast<const uint32_t*>(p + (size_t)y * stride)), 0x01010101u, s);
+    }
+    for (uint32_t o = lanes / 2; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if (live && (wx & (lanes - 1)) == 0) cells[(size_t)j * (wpr / lanes) + wx / lanes] = s;
+}
+// domain d = (d % dnx, d / dnx) on the lattice (k_uniform_grid order); cls and/or keys + hist, whichever is asked for
+__global__ void __launch_bounds__(256) k_dom_from_cells(const uint32_t* __restrict__ cells, uint32_t cw, uint32_t dnx, uint32_t n, int32_t* __restrict__ cls,
+                                                        uint32_t width, uint8_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[FE_MAX_BUCKETS];
+    if (keys) {
+        for (uint32_t b = threadIdx.x; b < FE_MAX_BUCKETS; b += blockDim.x) sh[b] = 0;
+        __syncthreads();
+    }
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) {
+        const uint32_t i = d % dnx, j = d / dnx;
+        const uint32_t* c = cells + (size_t)j * cw + i;
+        const uint32_t a1 = __ldg(c), a2 = __ldg(c + 1), a3 = __ldg(c + cw), a4 = __ldg(c + cw + 1);
+        if (cls) cls[d] = category4(a1, a2, a3, a4);
+        if (keys) {
+            const uint32_t k = min((a1 + a2 + a3 + a4) / width, (uint32_t)FE_MAX_BUCKETS - 1);
+            keys[d] = (uint8_t)k;
+            atomicAdd(&sh[k], 1u);
+        }
+    }
+    if (keys) {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < FE_MAX_BUCKETS; b += blockDim.x)
+            if (sh[b]) atomicAdd(&hist[b], sh[b]);
+    }
+}
+bool cell_grid_supported(const uint8_t* img, uint32_t stride, uint32_t w, uint32_t h, uint32_t C) {
+    return C >= 4 && C <= 64 && (C & (C - 1)) == 0 && w % C == 0 && h % C == 0 && stride % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 3u) == 0;
+}
+void launch_cell_grid(cudaStream_t stream, const uint8_t* img, uint32_t stride, uint32_t w, uint32_t h, uint32_t C, uint32_t* cells) {
+    const uint32_t wpr = w / 4, ch = h / C;
+    k_cell_grid<<<dim3((wpr + 31) / 32, (ch + 7) / 8), dim3(32, 8), 0, stream>>>(img, stride, wpr, ch, C, cells);
+}
+void launch_dom_from_cells(cudaStream_t stream, const uint32_t* cells, uint32_t cw, uint32_t dnx, uint32_t n, int32_t* cls, uint32_t width, uint8_t* keys,
+                           uint32_t* hist) {
+    if (n) k_dom_from_cells<<<(n + 255) / 256, 256, 0, stream>>>(cells, cw, dnx, n, cls, width, keys, hist);
 }
 
 // out[b * 8 + k] = number of positions of domain bucket b whose domain index is below cut.v[k] (positions of a bucket are

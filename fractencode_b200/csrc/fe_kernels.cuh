@@ -33,6 +33,11 @@ __global__ void k_uniform_grid(fe_grid_item* out, uint32_t nx, uint32_t n, uint3
 __global__ void k_quadtree_scatter(const fe_grid_item* rng, const fe_encode_item* level_items, const uint32_t* split,
                                    const uint32_t* scan, uint32_t n, fe_grid_item* next, fe_encode_item* items_out);
 __global__ void k_classify(const uint8_t* img, uint32_t stride, const fe_grid_item* items, uint32_t n, int32_t* cls, int force);
+bool cell_grid_supported(const uint8_t* img, uint32_t stride, uint32_t w, uint32_t h, uint32_t C);
+void launch_cell_grid(cudaStream_t stream, const uint8_t* img, uint32_t stride, uint32_t w, uint32_t h, uint32_t C, uint32_t* cells);
+void launch_dom_from_cells(cudaStream_t stream, const uint32_t* cells, uint32_t cw, uint32_t dnx, uint32_t n, int32_t* cls, uint32_t width, uint8_t* keys,
+                           uint32_t* hist);
+void launch_classify(cudaStream_t stream, const uint8_t* img, uint32_t stride, const fe_grid_item* items, uint32_t n, uint32_t edge, int32_t* cls, int force);
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n);
 __global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n);
 __global__ void k_iota(uint32_t* p, uint32_t n);

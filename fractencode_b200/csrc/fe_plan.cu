@@ -517,7 +517,8 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
 
     // ---- bucket keys, orders ----
     if (st->bins) {
-        launch_brightness_bins(ctx->stream, ctx->src.px, ctx->src.stride, lv.d_dom, nD, g.S, 1u, width, bins8, scratch);
+        if (lv.cells) launch_dom_from_cells(ctx->stream, lv.cells, lv.cells_w, lv.dnx, nD, nullptr, width, bins8, scratch);
+        else launch_brightness_bins(ctx->stream, ctx->src.px, ctx->src.stride, lv.d_dom, nD, g.S, 1u, width, bins8, scratch);
         launch_brightness_bins(ctx->stream, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, nR, g.T, 4u, width, bins8 + nD, scratch + FE_MAX_BUCKETS);
         ctx->stats.kernel_launches += 2;
         FE_CUDA(ctx, cudaGetLastError());

@@ -112,6 +112,8 @@ struct DeviceLevel {
     uint32_t thr16;
     bool use_thr, need_min, timed;
     bool flips;                           // d_rng holds every range block twice (2 i, 2 i + 1): the odd copy is searched mirrored
+    const uint32_t* cells;                // lattice levels: sums of the T x T cells of the image ([h / T][cells_w]), else NULL
+    uint32_t cells_w, dnx;                // domain d sits at cell (d % dnx, d / dnx)
 };
 struct DeviceLevelState;
 
