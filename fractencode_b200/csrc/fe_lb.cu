@@ -208,15 +208,29 @@ __global__ void k_lb_verify(const uint8_t* __restrict__ src, uint32_t src_stride
                         D[j] = (t0 + j < T) ? (uint32_t)q[0] + q[1] + q[src_stride] + q[src_stride + 1] : 0u;
                     }
                 }
+                // row k = the range block under the INVERSE of rotation k against the unrotated domain.  k even: the eight pixels
+                // lie in ONE row of the range block (the lanes of the warp read 32 different rows: byte loads would be 32
+                // sectors per instruction) -- one 8-byte load, read backwards for k = 2; k odd: a column, which the lanes of the
+                // warp read as one row segment
+                if (vec && (k & 1u) == 0 && ((r.x | tgt_stride | (uint32_t)(reinterpret_cast<uintptr_t>(tgt) & 7u)) & 7u) == 0) {
+                    const uint32_t py = k == 0 ? ty : T - 1 - ty, px0 = k == 0 ? t0 : T - 8 - t0;
+                    const uint2 w = __ldg(reinterpret_cast<const uint2*>(tgt + (size_t)(r.y + py) * tgt_stride + r.x + px0));
+                    const uint32_t lo = k == 0 ? w.x : __byte_perm(w.y, 0, 0x0123), hi = k == 0 ? w.y : __byte_perm(w.x, 0, 0x0123);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t tx = t0 + j;
-                    if (tx < T) {
-                        // row k = the range block under the INVERSE of rotation k against the unrotated domain
-                        const uint32_t py = k == 0 ? ty : k == 1 ? tx : k == 2 ? T - 1 - ty : T - 1 - tx;
-                        const uint32_t px = k == 0 ? tx : k == 1 ? T - 1 - ty : k == 2 ? T - 1 - tx : ty;
-                        const uint32_t a = tgt[(size_t)(r.y + py) * tgt_stride + r.x + px];
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t a = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 255u;
                         sA2 += a * a; sAB += a * D[j]; sB2 += D[j] * D[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t tx = t0 + j;
+                        if (tx < T) {
+                            const uint32_t py = k == 0 ? ty : k == 1 ? tx : k == 2 ? T - 1 - ty : T - 1 - tx;
+                            const uint32_t px = k == 0 ? tx : k == 1 ? T - 1 - ty : k == 2 ? T - 1 - tx : ty;
+                            const uint32_t a = tgt[(size_t)(r.y + py) * tgt_stride + r.x + px];
+                            sA2 += a * a; sAB += a * D[j]; sB2 += D[j] * D[j];
+                        }
                     }
                 }
             }

@@ -564,7 +564,9 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
     pa.items_per_sm = kind != 1 ? 8u : (g.T >= 32 ? 4u : 6u);
     // i8 kind up to T = 16: a work item is TWO row tiles (64 range blocks, M = 256 through two accumulator pairs) sharing every
     // B stage -- halves the L2 -> shared-memory operand stream, which bounds the kernel before the tensor pipe does
-    pa.tiles_per_item = (kind == 1 && g.T <= 16 && !getenv("FE_NO_PAIR")) ? 2u : 1u;
+    // The kind::f16 search does the same at T = 8 (fe_search_f16.cu, PAIR; measured: T = 8 -2 %, T = 4 +14 % -- its short K makes
+    // the epilogue, not the operand stream, the bound, and half as many work items balance worse).
+    pa.tiles_per_item = (((kind == 1 && g.T <= 16) || (kind == 0 && g.T == 8)) && !getenv("FE_NO_PAIR")) ? 2u : 1u;
     PLAUNCH(ctx, k_level_plan, 1, 512, pa, hist_d, hist_r, pre, nb, st->nbins, st->ngroups, st->span, nD, nR, nt);
     PLAUNCH(ctx, k_level_ranges, cdiv_u((uint64_t)nR * (g.T >= 16 ? 32 : 1), 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T, kind == 1 ? 0 : 1,
             lv.flips ? 1 : 0, pa.list[0], ctx->b_posb.as<uint16_t>());
@@ -591,6 +593,7 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
         fa.rowhit = ctx->b_rowhit.as<uint32_t>();
         fa.flags = ctx->b_counters.as<uint32_t>() + 2;
         fa.thr16 = lv.thr16; fa.use_thr = lv.use_thr ? 1u : 0u;
+        fa.pair = (kind == 0 && pa.tiles_per_item == 2) ? 1u : 0u;
         if (kind == 2) {
             FE_CUDA(ctx, ctx->b_A16.ensure((size_t)max_row_tiles * UM_ROWS * 80 * 2 + 256));
             fa.A16 = ctx->b_A16.p;

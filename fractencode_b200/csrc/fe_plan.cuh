@@ -145,6 +145,7 @@ struct F16Args {
     uint32_t* flags;
     uint32_t thr16, use_thr;
     uint32_t ordinal;                     // slice ordinal this launch belongs to
+    uint32_t pair;                        // work items are two row tiles (PlanArgs::tiles_per_item == 2)
     // lower-bound prefilter (fe_lb.cu): A tiles come from a blob, candidates go to a list
     const void* A16;                      // [row tile][K / 8][128 rows][8 halves]
     uint2* cand;                          // {result row, domain index}

@@ -104,11 +104,18 @@ __device__ __forceinline__ void build_rows(uint8_t* sAbuf, const uint8_t* __rest
 // META: runs cross chunks of the blob (brightness-bin neighbourhoods, minimum pass): per-tile metadata is read
 // MODE 1: lower-bound prefilter (fe_lb.cu) -- the A tile is bulk-copied from a blob (operands are 16-bit cell sums, not
 // pixels) and the epilogue emits every column under the threshold as a candidate instead of tracking first hit / minimum
-template <int T, bool RETIRE, bool META, int MODE>
+// PAIR: a work item is TWO row tiles (64 range blocks, M = 256 as two MMAs per B tile into the accumulators of the two compute
+// groups): every B stage is used twice, which halves the operand stream into shared memory -- the stream, not the tensor pipe,
+// bounds the single-tile form.  Two issuers (tile parity = accumulator buffer) with three B stages each; group g drains row tile g.
+template <int T, bool RETIRE, bool META, int MODE, bool PAIR>
 __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) {
     constexpr uint32_t N = T * T, KPAD = (N + 3 + 15) & ~15u;
     constexpr uint32_t bytesA = UM_ROWS * KPAD * 2, bytesB = UM_NT * KPAD * 2;
-    constexpr uint32_t NA = F16_ABUFS;                     // A tiles in flight: the builders run up to NA - 1 items ahead
+    constexpr uint32_t AT = PAIR ? 2 : 1;                  // row tiles per item / per A buffer
+    constexpr uint32_t NA = PAIR ? 2 : F16_ABUFS;          // A buffers in flight: the builders run up to NA - 1 items ahead
+    constexpr uint32_t NST = PAIR ? 6 : F16_STAGES;        // B stages
+    constexpr uint32_t NISS = PAIR ? 2 : F16_ISSUERS;      // issuers with work; tiles are dealt to them round-robin
+    constexpr uint32_t SPI = NST / NISS;                   // B stages per issuer
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SliceCtl* __restrict__ ctl = a.ctl;
@@ -119,26 +126,26 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
     const ListEntry* __restrict__ list = a.list[ctl->list];
 
     uint8_t* sA = smem;                                    // NA buffers
-    uint8_t* sB = smem + NA * bytesA;                      // F16_STAGES stages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)F16_STAGES * bytesB);
+    uint8_t* sB = smem + NA * AT * bytesA;                 // NST stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)NST * bytesB);
     const uint32_t bar0 = smem_u32(bars);
     auto ACC_FULL = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (0 + 2 * g + b); };
     auto ACC_EMPTY = [&](uint32_t g, uint32_t b) { return bar0 + 8 * (4 + 2 * g + b); };
     auto B_FULL = [&](uint32_t i) { return bar0 + 8 * (8 + i); };
-    auto A_FULL = [&](uint32_t i) { return bar0 + 8 * (8 + F16_STAGES + i); };
-    auto A_EMPTY = [&](uint32_t i) { return bar0 + 8 * (8 + F16_STAGES + NA + i); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + F16_STAGES + 2 * NA);
+    auto A_FULL = [&](uint32_t i) { return bar0 + 8 * (8 + NST + i); };
+    auto A_EMPTY = [&](uint32_t i) { return bar0 + 8 * (8 + NST + NA + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + NST + 2 * NA);
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < NA; ++i) {
             mbar_init(A_FULL(i), F16_BUILDERS);            // one arrive per builder warp
-            mbar_init(A_EMPTY(i), F16_ISSUERS);
+            mbar_init(A_EMPTY(i), NISS);
         }
         for (uint32_t i = 0; i < 4; ++i) {
             mbar_init(bar0 + 8 * (0 + i), 1);              // ACC_FULL: one tcgen05.commit
             mbar_init(bar0 + 8 * (4 + i), 8);              // ACC_EMPTY: one arrive per compute warp of the warpgroup
         }
-        for (uint32_t i = 0; i < (uint32_t)F16_STAGES; ++i) mbar_init(B_FULL(i), 1);
+        for (uint32_t i = 0; i < NST; ++i) mbar_init(B_FULL(i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -153,20 +160,21 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
     if (warp < F16_ISSUERS) {
         // ================= issuers: one thread per accumulator (g, ib), each also the producer of its B tiles =================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (lane == 0) {
-            const uint32_t g = warp >> 1, ib = warp & 1, res = g + 2 * ib;
-            const uint32_t sb = 2 * warp;                  // first of this issuer's two stages
+        if (lane == 0 && warp < NISS) {
+            // single: tile t of the CTA's running count goes to group t % 2, buffer (t / 2) % 2; pair: to buffer t % 2 of both groups
+            const uint32_t g = PAIR ? 1u : warp >> 1, ib = PAIR ? warp : warp & 1, res = PAIR ? warp : g + 2 * ib;
+            const uint32_t sb = SPI * warp;                // first of this issuer's stages
             const uint32_t idesc = (1u << 4) | ((uint32_t)(UM_NT >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
             constexpr uint32_t nk = KPAD / 16;
             struct Cursor {
-                uint32_t w, wi, it0, u, n, t0;
+                uint32_t w, wi, it0, u, n, t0, nrows;
                 bool valid;
             };
             auto load_item = [&](Cursor& c) {
                 c.valid = c.w < n_items;
                 if (c.valid) {
                     const uint4 rec = __ldg(reinterpret_cast<const uint4*>(a.items + c.w));
-                    c.t0 = rec.z; c.n = rec.w - rec.z;
+                    c.t0 = rec.z; c.n = rec.w - rec.z; c.nrows = rec.y;
                     if (c.w + gridDim.x < n_items) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.items + c.w + gridDim.x));
                 }
             };
@@ -190,47 +198,54 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
             };
             auto seek = [&](Cursor& c, bool is_mm) {
                 while (c.valid) {
-                    c.u = (res + 4 - (c.it0 & 3)) & 3;
+                    c.u = (res + NISS - (c.it0 % NISS)) % NISS;
                     if (c.u < c.n) return;
                     next_item(c, is_mm);
                 }
             };
             auto advance = [&](Cursor& c, bool is_mm) {
-                c.u += 4;
+                c.u += NISS;
                 if (c.u >= c.n) { next_item(c, is_mm); seek(c, is_mm); }
             };
             seek(ld, false);
             seek(mm, true);
             uint32_t m_ld = 0, m = 0;                      // tiles loaded / issued by this issuer so far
             auto load_B = [&]() {                           // bulk copy of the load cursor's tile into stage sb + (m_ld & 1)
-                const uint32_t s = sb + (m_ld & 1);
-                if (m_ld >= 2) mbar_wait(ACC_FULL(g, ib), (m_ld - 2) & 1);   // the stage's previous tile: its MMAs have completed
+                const uint32_t s = sb + (m_ld % SPI);
+                if (m_ld >= SPI) mbar_wait(ACC_FULL(g, ib), (m_ld - SPI) & 1);   // the stage's previous tile: its MMAs have completed
                 mbar_expect_tx(B_FULL(s), bytesB);
                 bulk_g2s(smem_u32(sB + (size_t)s * bytesB), reinterpret_cast<const uint8_t*>(a.B16) + (size_t)(ld.t0 + ld.u) * bytesB, bytesB, B_FULL(s));
                 ++m_ld;
                 advance(ld, false);
             };
-            if (ld.valid) load_B();
-            if (ld.valid) load_B();
+#pragma unroll
+            for (uint32_t i = 0; i < SPI; ++i)
+                if (ld.valid) load_B();
             uint32_t cur_wi = 0xFFFFFFFFu, a_addr = 0;
             while (mm.valid) {
-                if (m >= 1 && ld.valid) load_B();          // tile m+1 goes into the stage of tile m-1
+                if (m >= 1 && ld.valid) load_B();          // tile m + SPI - 1 goes into the stage of tile m - 1
                 if (mm.wi != cur_wi) {                      // first tile of this issuer in a new item: its A tile must be built
                     cur_wi = mm.wi;
                     mbar_wait(A_FULL(cur_wi % NA), (cur_wi / NA) & 1);
-                    a_addr = smem_u32(sA + (cur_wi % NA) * bytesA);
+                    a_addr = smem_u32(sA + (cur_wi % NA) * (AT * bytesA));
                 }
-                const uint32_t s = sb + (m & 1);
-                mbar_wait(B_FULL(s), (m >> 1) & 1);
+                const uint32_t s = sb + (m % SPI);
+                mbar_wait(B_FULL(s), (m / SPI) & 1);
                 mbar_wait(ACC_EMPTY(g, ib), (m & 1) ^ 1);
+                if (PAIR) mbar_wait(ACC_EMPTY(0, ib), (m & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(sB + (size_t)s * bytesB);
-                const uint32_t d_tmem = tmem_base + (g * 2 + ib) * UM_NT;
 #pragma unroll
-                for (uint32_t kk = 0; kk < nk; ++kk) {
-                    const uint64_t adesc = make_desc(a_addr + kk * 2 * (UM_ROWS * 16), UM_ROWS * 16, 128);
-                    const uint64_t bdesc = make_desc(b_addr + kk * 2 * (UM_NT * 16), UM_NT * 16, 128);
-                    tc_mma<0>(d_tmem, adesc, bdesc, idesc, kk > 0 ? 1u : 0u);
+                for (uint32_t rt = 0; rt < AT; ++rt) {
+                    if (PAIR && rt == 1 && mm.nrows <= (uint32_t)UM_ROWS) break;     // a lone row tile at the end of a bucket
+                    const uint32_t d_tmem = tmem_base + ((PAIR ? rt : g) * 2 + ib) * UM_NT;
+#pragma unroll
+                    for (uint32_t kk = 0; kk < nk; ++kk) {
+                        const uint64_t adesc = make_desc(a_addr + rt * bytesA + kk * 2 * (UM_ROWS * 16), UM_ROWS * 16, 128);
+                        const uint64_t bdesc = make_desc(b_addr + kk * 2 * (UM_NT * 16), UM_NT * 16, 128);
+                        tc_mma<0>(d_tmem, adesc, bdesc, idesc, kk > 0 ? 1u : 0u);
+                    }
+                    if (PAIR && rt == 0) tc_commit(ACC_FULL(0, ib));   // group 0 starts while the second row tile multiplies
                 }
                 tc_commit(ACC_FULL(g, ib));
                 mm_had_tiles = true;
@@ -246,21 +261,29 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
         // built and its pixel rows are prefetched into L1, so an item costs one L1 round trip plus the arithmetic.
         const uint32_t bw = warp - F16_ISSUERS;
         const uint32_t r = bw * 8 + (lane >> 2);
-        auto fetch = [&](uint32_t w, uint4& ent, bool& valid) {
-            valid = false;
+        // entry = (pixel origin, mirror flag) of this lane's range block in each of the item's row tiles
+        auto fetch = [&](uint32_t w, uint2 (&ent)[AT], bool (&valid)[AT]) {
+#pragma unroll
+            for (uint32_t rt = 0; rt < AT; ++rt) valid[rt] = false;
             if (w < n_items) {
                 const uint4 rec = __ldg(reinterpret_cast<const uint4*>(a.items + w));
-                valid = 4 * r < rec.y;
-                if (valid) {
-                    ent = __ldg(reinterpret_cast<const uint4*>(list + rec.x + r));
-                    const uint8_t* base = a.img + (size_t)(ent.y >> 16) * a.stride + (ent.y & 0xFFFFu);
 #pragma unroll
-                    for (int y = 0; y < T; ++y) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)y * a.stride));
+                for (uint32_t rt = 0; rt < AT; ++rt) {
+                    valid[rt] = 4 * (r + 32 * rt) < rec.y;
+                    if (valid[rt]) {
+                        const uint4 e = __ldg(reinterpret_cast<const uint4*>(list + rec.x + r + 32 * rt));
+                        ent[rt] = make_uint2(e.y, e.w);
+                        const uint8_t* base = a.img + (size_t)(e.y >> 16) * a.stride + (e.y & 0xFFFFu);
+#pragma unroll
+                        for (int y = 0; y < T; ++y) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)y * a.stride));
+                    }
                 }
             }
         };
-        uint4 ent = make_uint4(0, 0, 0, 0), ent_next = make_uint4(0, 0, 0, 0);
-        bool valid = false, valid_next = false;
+        uint2 ent[AT], ent_next[AT];
+        bool valid[AT], valid_next[AT];
+#pragma unroll
+        for (uint32_t rt = 0; rt < AT; ++rt) { ent[rt] = ent_next[rt] = make_uint2(0, 0); valid[rt] = valid_next[rt] = false; }
         if (MODE == 0) fetch(blockIdx.x, ent, valid);
         uint32_t wi = 0;
         if (MODE == 1) {
@@ -282,11 +305,17 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
             const uint32_t ab = wi % NA;
             fetch(w + gridDim.x, ent_next, valid_next);
             if (wi >= NA) mbar_wait(A_EMPTY(ab), ((wi / NA) & 1) ^ 1);   // all four issuers are done with item wi - NA
-            build_rows<T>(sA + ab * bytesA, a.img, a.stride, ent.y, ent.w != 0, valid, bw, lane);
+#pragma unroll
+            for (uint32_t rt = 0; rt < AT; ++rt) {
+                // the second row tile of a lone-tile item is never multiplied: leave it as it is
+                if (rt == 0 || __any_sync(0xFFFFFFFFu, valid[rt]))
+                    build_rows<T>(sA + (ab * AT + rt) * bytesA, a.img, a.stride, ent[rt].x, ent[rt].y != 0, valid[rt], bw, lane);
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) mbar_arrive(A_FULL(ab));
-            ent = ent_next; valid = valid_next;
+#pragma unroll
+            for (uint32_t rt = 0; rt < AT; ++rt) { ent[rt] = ent_next[rt]; valid[rt] = valid_next[rt]; }
         }
         }
     } else {
@@ -303,10 +332,12 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
             const uint4 rec = __ldg(reinterpret_cast<const uint4*>(a.items + w));
             const uint32_t cols_left = __ldg(&a.items[w].cols_left);
             const uint32_t item_t0 = rec.z, n = rec.w - rec.z;
-            const bool row_ok = lrow < rec.y;
+            const uint32_t trow = PAIR ? g * UM_ROWS + lrow : lrow;          // row inside the item
+            const bool row_ok = trow < rec.y;
+            const bool tile_empty = PAIR && g * UM_ROWS >= rec.y;          // lone row tile: this group only keeps the hand-shake going
             uint32_t slot = 0, a2 = 0;
             if (row_ok) {
-                const uint4 ent = __ldg(reinterpret_cast<const uint4*>(list + rec.x + (lrow >> 2)));
+                const uint4 ent = __ldg(reinterpret_cast<const uint4*>(list + rec.x + (trow >> 2)));
                 slot = ent.x; a2 = ent.z;
             }
             const uint32_t srow = 4u * slot + (lrow & 3u);     // result row of the level
@@ -342,15 +373,17 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
                     if (V > -16777216ll && V < 16777216ll) { st.bestV = (float)V; st.bestp = (uint32_t)(d - 2 * V); }
                 }
             }
-            const uint32_t first = (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
-            const uint32_t my_tiles = first < n ? (n - first + UM_WGS - 1) / UM_WGS : 0;
+            // single: the two groups take alternate tiles of the item; pair: every tile, for their own row tile
+            const uint32_t tstep = PAIR ? 1u : (uint32_t)UM_WGS;
+            const uint32_t first = PAIR ? 0u : (g + UM_WGS - (it0 % UM_WGS)) % UM_WGS;
+            const uint32_t my_tiles = first < n ? (n - first + tstep - 1) / tstep : 0;
             // Threshold runs: a range is decided by its first hit in scan order, so once any of its four rotation rows
             // (four adjacent lanes) has crossed the threshold the whole quad is retired for the rest of the chunk, and a
             // warp whose 32 rows are all retired only keeps the accumulator hand-shake going.
             bool retired = !row_ok;
-            bool warp_done = false;
+            bool warp_done = tile_empty;
             for (uint32_t j = 0; j < my_tiles; ++j, ++jb) {
-                const uint32_t u = first + j * UM_WGS, buf = jb & 1;
+                const uint32_t u = first + j * tstep, buf = jb & 1;
                 const uint32_t colbase = u * UM_NT + h * UM_HALF;
                 static_assert(UM_HALF == 64, "two parity words per half tile");
                 const uint4* meta_p = a.colmeta + (size_t)(item_t0 + u) * 2 + h;
@@ -387,14 +420,14 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
                             st.bestV = (float)V; st.bestp = (uint32_t)(d + 1 - 2 * V); st.bestcol = FE_NONE32;
                         }
                         cur_seg = meta.w;
-                        if (RETIRE) { retired = !row_ok; warp_done = false; }
+                        if (RETIRE) { retired = !row_ok; warp_done = tile_empty; }
                     }
                 };
                 if (RETIRE) chunk_change();
                 uint32_t v[UM_HALF];
                 mbar_wait(ACC_FULL(g, buf), (jb >> 1) & 1);
                 tc_fence_after();
-                if (!(RETIRE && warp_done)) {
+                if (!((RETIRE || PAIR) && warp_done)) {
                     const uint32_t taddr = lane_addr + (g * 2 + buf) * UM_NT;
                     TMEM_LD32(taddr, (v + 0));
                     TMEM_LD32(taddr + 32, (v + 32));
@@ -410,7 +443,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) k_search_f16(const F16Args a) 
                         const uint32_t idx = atomicAdd(a.cand_count, 1u);
                         if (idx < a.cand_cap) a.cand[idx] = make_uint2(srow, a.blob_dom[col0 + c]);
                     });
-                } else if (!(RETIRE && warp_done)) {
+                } else if (!((RETIRE || PAIR) && warp_done)) {
                     process_half<META>(v, st, RETIRE ? !retired : row_ok, colbase, nvalid, par, no_min == 0);
                     if (RETIRE && (j & 3) == 3) {   // every 4th tile is enough: retirement only saves work
                         uint32_t hm = __ballot_sync(0xFFFFFFFFu, st.hit != FE_NONE32);
@@ -544,12 +577,13 @@ int f16_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, c
     return FE_OK;
 }
 
-template <int T>
+template <int T, bool PAIR>
 static int launch_T(fe_ctx* ctx, const F16Args& a, bool retire, bool meta, cudaEvent_t ev0, cudaEvent_t ev1) {
     constexpr uint32_t Kpad = (T * T + 3 + 15u) & ~15u;
-    const size_t smem = (size_t)F16_ABUFS * UM_ROWS * Kpad * 2 + (size_t)F16_STAGES * UM_NT * Kpad * 2 + (8 + F16_STAGES + 2 * F16_ABUFS) * 8 + 64;
-    auto kern = retire ? (meta ? k_search_f16<T, true, true, 0> : k_search_f16<T, true, false, 0>)
-                       : (meta ? k_search_f16<T, false, true, 0> : k_search_f16<T, false, false, 0>);
+    constexpr uint32_t na = PAIR ? 2 : F16_ABUFS, at = PAIR ? 2 : 1, nst = PAIR ? 6 : F16_STAGES;
+    const size_t smem = (size_t)na * at * UM_ROWS * Kpad * 2 + (size_t)nst * UM_NT * Kpad * 2 + (8 + nst + 2 * na) * 8 + 64;
+    auto kern = retire ? (meta ? k_search_f16<T, true, true, 0, PAIR> : k_search_f16<T, true, false, 0, PAIR>)
+                       : (meta ? k_search_f16<T, false, true, 0, PAIR> : k_search_f16<T, false, false, 0, PAIR>);
     FE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (ev0) cudaEventRecord(ev0, ctx->stream);
     kern<<<ctx->n_sm, F16_THREADS, smem, ctx->stream>>>(a);
@@ -560,14 +594,15 @@ static int launch_T(fe_ctx* ctx, const F16Args& a, bool retire, bool meta, cudaE
 }
 
 int f16_launch_search(fe_ctx* ctx, const LevelGeom& g, const F16Args& a, bool retire, bool meta, cudaEvent_t ev0, cudaEvent_t ev1) {
-    return g.T == 4 ? launch_T<4>(ctx, a, retire, meta, ev0, ev1) : launch_T<8>(ctx, a, retire, meta, ev0, ev1);
+    if (a.pair) return g.T == 4 ? launch_T<4, true>(ctx, a, retire, meta, ev0, ev1) : launch_T<8, true>(ctx, a, retire, meta, ev0, ev1);
+    return g.T == 4 ? launch_T<4, false>(ctx, a, retire, meta, ev0, ev1) : launch_T<8, false>(ctx, a, retire, meta, ev0, ev1);
 }
 
 // lower-bound prefilter launch: the T' = 8 contraction on cell sums, candidates out (fe_lb.cu)
 int f16_launch_search_lb(fe_ctx* ctx, const F16Args& a, cudaEvent_t ev0, cudaEvent_t ev1) {
     constexpr uint32_t Kpad = (8 * 8 + 3 + 15u) & ~15u;
     const size_t smem = (size_t)F16_ABUFS * UM_ROWS * Kpad * 2 + (size_t)F16_STAGES * UM_NT * Kpad * 2 + (8 + F16_STAGES + 2 * F16_ABUFS) * 8 + 64;
-    auto kern = k_search_f16<8, false, true, 1>;
+    auto kern = k_search_f16<8, false, true, 1, false>;
     FE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (ev0) cudaEventRecord(ev0, ctx->stream);
     kern<<<ctx->n_sm, F16_THREADS, smem, ctx->stream>>>(a);

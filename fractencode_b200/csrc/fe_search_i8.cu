@@ -342,6 +342,61 @@ __global__ void __launch_bounds__(256) k_build_rows_i8(const uint8_t* __restrict
     __syncthreads();
     // ---- chunks: [K/16][128 rows][16 B] ----
     uint4* out = A8 + (size_t)tile * nch * UM_ROWS;
+    if constexpr (TT >= 16) {
+        // A thread turns a 4 x 16 patch of a rotated block into four chunks.  A warp is one rotation of eight blocks x four
+        // patches: no divergence, and the word reads of the odd rotations (16 rows of 4 pixels, transposed with PRMT) fall into
+        // 32 different banks (block stride 68 words, patches one word apart).
+        constexpr uint32_t nY4 = TT / 4, nX16 = TT / 16, units = UM_ROWS * nY4 * nX16;
+        for (uint32_t idx = threadIdx.x; idx < units; idx += blockDim.x) {
+            const uint32_t lr8 = idx & 7u, ysub = (idx >> 3) & 3u, rest = idx >> 5;
+            const uint32_t k = rest & 3u, bg = (rest >> 2) & 3u, r2 = rest >> 4;
+            const uint32_t Y = ((r2 % (nY4 / 4)) * 4 + ysub) * 4, X0 = (r2 / (nY4 / 4)) * 16;
+            const uint32_t lr = bg * 8 + lr8, row = 4 * lr + k;
+            uint32_t o[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) o[i][m] = 0;
+            if (lr < nvalid) {
+                const uint8_t* sb = sblk + lr * NS;
+                if (k == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(sb + (Y + i) * TT + X0);
+                        o[i][0] = v.x; o[i][1] = v.y; o[i][2] = v.z; o[i][3] = v.w;
+                    }
+                } else if (k == 2) {                           // element e of the rotated block = element N-1-e of the block
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(sb + (TT - 1 - Y - i) * TT + (TT - 16 - X0));
+                        o[i][0] = __byte_perm(v.w, 0, 0x0123); o[i][1] = __byte_perm(v.z, 0, 0x0123);
+                        o[i][2] = __byte_perm(v.y, 0, 0x0123); o[i][3] = __byte_perm(v.x, 0, 0x0123);
+                    }
+                } else {
+                    // k = 1: out(Y + i, X0 + q) = blk[X0 + q][T - 1 - Y - i]; k = 3: blk[T - 1 - X0 - q][Y + i]
+                    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t q = 4 * m + j;
+                            w[j] = k == 1 ? sw[((X0 + q) * TT + (TT - 4 - Y)) >> 2] : sw[((TT - 1 - X0 - q) * TT + Y) >> 2];
+                        }
+                        const uint32_t ab_lo = __byte_perm(w[0], w[1], 0x5140), ab_hi = __byte_perm(w[0], w[1], 0x7362);
+                        const uint32_t cd_lo = __byte_perm(w[2], w[3], 0x5140), cd_hi = __byte_perm(w[2], w[3], 0x7362);
+                        const uint32_t t0 = __byte_perm(ab_lo, cd_lo, 0x5410), t1 = __byte_perm(ab_lo, cd_lo, 0x7632);
+                        const uint32_t t2 = __byte_perm(ab_hi, cd_hi, 0x5410), t3 = __byte_perm(ab_hi, cd_hi, 0x7632);
+                        o[0][m] = k == 1 ? t3 : t0; o[1][m] = k == 1 ? t2 : t1;
+                        o[2][m] = k == 1 ? t1 : t2; o[3][m] = k == 1 ? t0 : t3;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) out[(((Y + i) * TT + X0) >> 4) * UM_ROWS + row] = make_uint4(o[i][0], o[i][1], o[i][2], o[i][3]);
+        }
+        for (uint32_t idx = N / 16 * UM_ROWS + threadIdx.x; idx < nch * UM_ROWS; idx += blockDim.x) out[idx] = make_uint4(0, 0, 0, 0);
+    } else {
     for (uint32_t idx = threadIdx.x; idx < nch * UM_ROWS; idx += blockDim.x) {
         const uint32_t row = idx % UM_ROWS, ch = idx / UM_ROWS, lr = row >> 2, k = row & 3u;
         uint32_t w[4] = {0, 0, 0, 0};
@@ -371,6 +426,7 @@ __global__ void __launch_bounds__(256) k_build_rows_i8(const uint8_t* __restrict
             }
         }
         out[idx] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
     }
     }
 }
