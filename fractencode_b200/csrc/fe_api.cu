@@ -575,10 +575,14 @@ static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p,
     lv.d_dom = io.d_dom; lv.nD = nD; lv.d_rng = d_rng; lv.nR = nS; lv.g = g; lv.flips = flips;
     // lattice levels: the image's T x T cell sums give every domain its class and its brightness bin (fe_kernels.cu)
     if (io.lattice && io.dnx && g.S == 2 * g.T && (p.use_classifier || lp->use_thr) && cell_grid_supported(ctx->src.px, ctx->src.stride, ctx->src.w, ctx->src.h, g.T) && !getenv("FE_NO_CELLS")) {
-        FE_CUDA(ctx, ctx->b_cells.ensure((size_t)(ctx->src.w / g.T) * (ctx->src.h / g.T) * 4));
-        launch_cell_grid(ctx->stream, ctx->src.px, ctx->src.stride, ctx->src.w, ctx->src.h, g.T, ctx->b_cells.as<uint32_t>());
+        const size_t ncell = (size_t)(ctx->src.w / g.T) * (ctx->src.h / g.T);
+        FE_CUDA(ctx, ctx->b_cells.ensure(ncell * 12));
+        launch_cell_grid(ctx->stream, ctx->src.px, ctx->src.stride, ctx->src.w, ctx->src.h, g.T, ctx->b_cells.as<uint32_t>(), ctx->b_cells.as<uint32_t>() + ncell,
+                         ctx->b_cells.as<uint32_t>() + 2 * ncell);
+        lv.cellsD2 = ctx->b_cells.as<uint32_t>() + 2 * ncell;
         ctx->stats.kernel_launches++;
         lv.cells = ctx->b_cells.as<uint32_t>(); lv.cells_w = ctx->src.w / g.T; lv.dnx = io.dnx;
+        if (ctx->src.px == ctx->tgt.px && !flips) lv.cells2 = lv.cells + ncell;
     }
     if (p.use_classifier) {
         FE_CUDA(ctx, ctx->b_dom_cls.ensure((size_t)nD * 4));

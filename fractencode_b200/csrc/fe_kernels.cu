@@ -265,18 +265,48 @@ void launch_brightness_bins(cudaStream_t stream, const uint8_t* img, uint32_t st
 // the image gives every cell sum, and both the Classifier2 class (quadrant sums = the four cells) and the brightness bin (their
 // total) of every domain come from four 4-byte reads -- instead of every domain re-reading its own (overlapping) pixels.
 // cells[j][i] = sum of the C x C pixels at (C i, C j), C a power of two in 4..64: a thread adds up a 4-pixel wide column of a cell
-// row, C / 4 neighbouring lanes combine.
+// row, C / 4 neighbouring lanes combine.  cells2 = the same for the squared pixels (a range block on the lattice IS a cell: its
+// operand norm comes from the two sums, k_level_ranges).
 __global__ void __launch_bounds__(256) k_cell_grid(const uint8_t* __restrict__ img, uint32_t stride, uint32_t wpr, uint32_t ch, uint32_t C,
-                                                   uint32_t* __restrict__ cells) {
+                                                   uint32_t* __restrict__ cells, uint32_t* __restrict__ cells2, uint32_t* __restrict__ cellsD2) {
     const uint32_t wx = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y, lanes = C / 4;
     const bool live = wx < wpr && j < ch;
-    uint32_t s = 0;
+    uint32_t s = 0, s2 = 0, d2 = 0;
     if (live) {
         const uint8_t* p = img + (size_t)(C * j) * stride + 4 * (size_t)wx;
-        for (uint32_t y = 0; y < C; ++y) s = __dp4a(__ldg(reinterpret_cast<const uint32_t*>(p + (size_t)y * stride)), 0x01010101u, s);
+        for (uint32_t y = 0; y < C; y += 2) {
+            const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)y * stride));
+            const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)(y + 1) * stride));
+            s = __dp4a(w1, 0x01010101u, __dp4a(w0, 0x01010101u, s));
+            s2 = __dp4a(w1, w1, __dp4a(w0, w0, s2));
+            const uint32_t Da = __dp4a(w1, 0x00000101u, __dp4a(w0, 0x00000101u, 0u));   // the two 2 x 2 box sums of the row pair
+            const uint32_t Db = __dp4a(w1, 0x01010000u, __dp4a(w0, 0x01010000u, 0u));
+            d2 += Da * Da + Db * Db;
+        }
     }
-    for (uint32_t o = lanes / 2; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-    if (live && (wx & (lanes - 1)) == 0) cells[(size_t)j * (wpr / lanes) + wx / lanes] = s;
+    for (uint32_t o = lanes / 2; o; o >>= 1) {
+        s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+        d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, o);
+    }
+    if (live && (wx & (lanes - 1)) == 0) {
+        const size_t c = (size_t)j * (wpr / lanes) + wx / lanes;
+        cells[c] = s;
+        cells2[c] = s2;
+        cellsD2[c] = d2;
+    }
+}
+// sum D^2 of the lattice domains in sorted order (what k_block_norms mode 3 computes from the pixels)
+__global__ void k_dom_norms_from_cells(const uint32_t* __restrict__ cellsD2, uint32_t cw, uint32_t dnx, const uint32_t* __restrict__ order, uint32_t n,
+                                       uint32_t* __restrict__ out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t d = order ? order[p] : p;
+    const uint32_t* c = cellsD2 + (size_t)(d / dnx) * cw + d % dnx;
+    out[p] = __ldg(c) + __ldg(c + 1) + __ldg(c + cw) + __ldg(c + cw + 1);
+}
+void launch_dom_norms_from_cells(cudaStream_t stream, const uint32_t* cellsD2, uint32_t cw, uint32_t dnx, const uint32_t* order, uint32_t n, uint32_t* out) {
+    if (n) k_dom_norms_from_cells<<<(n + 255) / 256, 256, 0, stream>>>(cellsD2, cw, dnx, order, n, out);
 }
 // domain d = (d % dnx, d / dnx) on the lattice (k_uniform_grid order); cls and/or keys + hist, whichever is asked for
 __global__ void __launch_bounds__(256) k_dom_from_cells(const uint32_t* __restrict__ cells, uint32_t cw, uint32_t dnx, uint32_t n, int32_t* __restrict__ cls,
@@ -307,9 +337,10 @@ __global__ void __launch_bounds__(256) k_dom_from_cells(const uint32_t* __restri
 bool cell_grid_supported(const uint8_t* img, uint32_t stride, uint32_t w, uint32_t h, uint32_t C) {
     return C >= 4 && C <= 64 && (C & (C - 1)) == 0 && w % C == 0 && h % C == 0 && stride % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 3u) == 0;
 }
-void launch_cell_grid(cudaStream_t stream, const uint8_t* img, uint32_t stride, uint32_t w, uint32_t h, uint32_t C, uint32_t* cells) {
+void launch_cell_grid(cudaStream_t stream, const uint8_t* img, uint32_t stride, uint32_t w, uint32_t h, uint32_t C, uint32_t* cells, uint32_t* cells2,
+                      uint32_t* cellsD2) {
     const uint32_t wpr = w / 4, ch = h / C;
-    k_cell_grid<<<dim3((wpr + 31) / 32, (ch + 7) / 8), dim3(32, 8), 0, stream>>>(img, stride, wpr, ch, C, cells);
+    k_cell_grid<<<dim3((wpr + 31) / 32, (ch + 7) / 8), dim3(32, 8), 0, stream>>>(img, stride, wpr, ch, C, cells, cells2, cellsD2);
 }
 void launch_dom_from_cells(cudaStream_t stream, const uint32_t* cells, uint32_t cw, uint32_t dnx, uint32_t n, int32_t* cls, uint32_t width, uint8_t* keys,
                            uint32_t* hist) {

@@ -34,7 +34,9 @@ __global__ void k_quadtree_scatter(const fe_grid_item* rng, const fe_encode_item
                                    const uint32_t* scan, uint32_t n, fe_grid_item* next, fe_encode_item* items_out);
 __global__ void k_classify(const uint8_t* img, uint32_t stride, const fe_grid_item* items, uint32_t n, int32_t* cls, int force);
 bool cell_grid_supported(const uint8_t* img, uint32_t stride, uint32_t w, uint32_t h, uint32_t C);
-void launch_cell_grid(cudaStream_t stream, const uint8_t* img, uint32_t stride, uint32_t w, uint32_t h, uint32_t C, uint32_t* cells);
+void launch_cell_grid(cudaStream_t stream, const uint8_t* img, uint32_t stride, uint32_t w, uint32_t h, uint32_t C, uint32_t* cells, uint32_t* cells2,
+                      uint32_t* cellsD2);
+void launch_dom_norms_from_cells(cudaStream_t stream, const uint32_t* cellsD2, uint32_t cw, uint32_t dnx, const uint32_t* order, uint32_t n, uint32_t* out);
 void launch_dom_from_cells(cudaStream_t stream, const uint32_t* cells, uint32_t cw, uint32_t dnx, uint32_t n, int32_t* cls, uint32_t width, uint8_t* keys,
                            uint32_t* hist);
 void launch_classify(cudaStream_t stream, const uint8_t* img, uint32_t stride, const fe_grid_item* items, uint32_t n, uint32_t edge, int32_t* cls, int force);

@@ -131,24 +131,32 @@ __global__ void __launch_bounds__(512) k_level_plan(PlanArgs a, const uint32_t* 
 
 // Per level position: the first list (every range block open), sum a^2 of the block (centred: a = 4 r - 510, f16 kind;
 // else 16 sum r^2, i8 kind) and the bucket of the position.
+// cells / cells2 (lattice levels): the block is cell (x / T, y / T) of the image's T-cell sums -- no pixel is read, one thread per block.
 __global__ void k_level_ranges(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
                                const uint32_t* __restrict__ order, const LevelPlan* __restrict__ plan, uint32_t T, int centred, int flips,
+                               const uint32_t* __restrict__ cells, const uint32_t* __restrict__ cells2, uint32_t cells_w,
                                ListEntry* __restrict__ list0, uint16_t* __restrict__ pos_bucket) {
     // a warp per block from T = 16 on (coalesced rows), a thread per block below
-    const uint32_t lanes = T >= 16 ? 32u : 1u;
+    const uint32_t lanes = (T >= 16 && !cells2) ? 32u : 1u;
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x, p = gt / lanes, lane = gt % lanes;
     if (p >= plan->nR) return;
     const uint32_t idx = order ? order[p] : p;
     const fe_grid_item r = rng[idx];
-    const uint8_t* base = img + (size_t)r.y * stride + r.x;
     uint32_t s2 = 0;
-    for (uint32_t e = lane; e < T * T; e += lanes) {
-        const uint32_t y = e / T, x = e - y * T;
-        const int v = centred ? 4 * (int)base[(size_t)y * stride + x] - 510 : 4 * (int)base[(size_t)y * stride + x];
-        s2 += (uint32_t)(v * v);
+    if (cells2) {
+        const size_t c = (size_t)(r.y / T) * cells_w + r.x / T;
+        const uint32_t q = 16u * __ldg(cells2 + c);                     // 16 sum r^2 <= 16 * 1024 * 255^2 < 2^31
+        s2 = centred ? q - 4080u * __ldg(cells + c) + T * T * 260100u : q;   // sum (4 r - 510)^2
+    } else {
+        const uint8_t* base = img + (size_t)r.y * stride + r.x;
+        for (uint32_t e = lane; e < T * T; e += lanes) {
+            const uint32_t y = e / T, x = e - y * T;
+            const int v = centred ? 4 * (int)base[(size_t)y * stride + x] - 510 : 4 * (int)base[(size_t)y * stride + x];
+            s2 += (uint32_t)(v * v);
+        }
+        if (lanes == 32)
+            for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
     }
-    if (lanes == 32)
-        for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
     if (lane) return;
     ListEntry e;
     e.slot = p;
@@ -568,8 +576,8 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
     // the epilogue, not the operand stream, the bound, and half as many work items balance worse).
     pa.tiles_per_item = (((kind == 1 && g.T <= 16) || (kind == 0 && g.T == 8)) && !getenv("FE_NO_PAIR")) ? 2u : 1u;
     PLAUNCH(ctx, k_level_plan, 1, 512, pa, hist_d, hist_r, pre, nb, st->nbins, st->ngroups, st->span, nD, nR, nt);
-    PLAUNCH(ctx, k_level_ranges, cdiv_u((uint64_t)nR * (g.T >= 16 ? 32 : 1), 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T, kind == 1 ? 0 : 1,
-            lv.flips ? 1 : 0, pa.list[0], ctx->b_posb.as<uint16_t>());
+    PLAUNCH(ctx, k_level_ranges, cdiv_u((uint64_t)nR * ((g.T >= 16 && !lv.cells2) ? 32 : 1), 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T,
+            kind == 1 ? 0 : 1, lv.flips ? 1 : 0, lv.cells, lv.cells2, lv.cells_w, pa.list[0], ctx->b_posb.as<uint16_t>());
     PLAUNCH(ctx, k_fill_u64, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
     PLAUNCH(ctx, k_fill_u32, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));
@@ -601,7 +609,7 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
             fa.thr16 = lb_threshold(lv.thr16);
         }
     } else {
-        FE_TRY(i8_build_pool(ctx, g, lv.d_dom, st->dom_order, pa.plan, nD, max_tiles));
+        FE_TRY(i8_build_pool(ctx, g, lv, st->dom_order, pa.plan, nD, max_tiles));
         FE_CUDA(ctx, ctx->b_A16.ensure((size_t)(max_row_tiles + 2) * UM_ROWS * i8_kpad(g) + 256));
         ia.A8 = ctx->b_A16.p;
         ia.B8 = ctx->b_B16.p;

@@ -113,6 +113,8 @@ struct DeviceLevel {
     bool use_thr, need_min, timed;
     bool flips;                           // d_rng holds every range block twice (2 i, 2 i + 1): the odd copy is searched mirrored
     const uint32_t* cells;                // lattice levels: sums of the T x T cells of the image ([h / T][cells_w]), else NULL
+    const uint32_t* cells2;               // ... and of their squared pixels (src == tgt: a range block on the lattice is a cell)
+    const uint32_t* cellsD2;              // ... and of their squared 2 x 2 box sums (sum D^2 of a domain = its four cells)
     uint32_t cells_w, dnx;                // domain d sits at cell (d % dnx, d / dnx)
 };
 struct DeviceLevelState;
@@ -175,7 +177,8 @@ struct I8Args {
     uint32_t pair;                        // work items are pairs of row tiles (rows 0-127 / 128-255 of the A tile): one compute warpgroup each
 };
 int i8_level_supported(const LevelGeom& g);    // fast geometry, 4 <= T <= 32
-int i8_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const uint32_t* dom_order, const LevelPlan* plan, uint32_t nD,
+struct DeviceLevel;
+int i8_build_pool(fe_ctx* ctx, const LevelGeom& g, const DeviceLevel& lv, const uint32_t* dom_order, const LevelPlan* plan, uint32_t nD,
                   uint32_t max_tiles);
 int i8_build_rows(fe_ctx* ctx, const LevelGeom& g, const LevelPlan* plan, const SliceCtl* ctl, const ListEntry* const list[2], uint32_t ordinal,
                   uint32_t max_row_tiles);

@@ -546,16 +546,19 @@ uint32_t i8_kpad(const LevelGeom& g) { return g.N <= (uint32_t)I8_KC ? ((g.N + 3
 
 int i8_level_supported(const LevelGeom& g) { return g.fast && g.T >= 4 && g.T <= 32; }
 
-int i8_build_pool(fe_ctx* ctx, const LevelGeom& g, const fe_grid_item* d_dom, const uint32_t* dom_order, const LevelPlan* plan, uint32_t nD,
+int i8_build_pool(fe_ctx* ctx, const LevelGeom& g, const DeviceLevel& lv, const uint32_t* dom_order, const LevelPlan* plan, uint32_t nD,
                   uint32_t max_tiles) {
+    const fe_grid_item* d_dom = lv.d_dom;
     const uint32_t Kpad = i8_kpad(g), kc = std::min(Kpad, (uint32_t)I8_KC), nst = Kpad / kc, ncs = kc / 16;
     FE_CUDA(ctx, ctx->b_B16.ensure((size_t)max_tiles * 2 * I8_NT * Kpad + 256));
     FE_CUDA(ctx, ctx->b_coln.ensure((size_t)max_tiles * I8_NT * 4 + 64));
     FE_CUDA(ctx, ctx->b_blob_dom.ensure((size_t)max_tiles * I8_NT * 4 + 64));
     FE_CUDA(ctx, ctx->b_tileseg.ensure((size_t)max_tiles * 4 + 64));
     FE_CUDA(ctx, ctx->b_tmaps.ensure((size_t)nD * 4 + 64));
-    k_block_norms<<<(unsigned)(((uint64_t)nD * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order, nD, g.T, 3,
-                                                                                      ctx->b_tmaps.as<uint32_t>());
+    if (lv.cellsD2) launch_dom_norms_from_cells(ctx->stream, lv.cellsD2, lv.cells_w, lv.dnx, dom_order, nD, ctx->b_tmaps.as<uint32_t>());
+    else
+        k_block_norms<<<(unsigned)(((uint64_t)nD * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order, nD, g.T, 3,
+                                                                                          ctx->b_tmaps.as<uint32_t>());
     k_build_pool_i8_level<<<max_tiles * nst, ncs * I8_NT, 0, ctx->stream>>>(ctx->src.px, ctx->src.stride, d_dom, dom_order, plan, g.T, Kpad, kc,
                                                                            ctx->b_tmaps.as<uint32_t>(), ctx->b_B16.as<uint4>(), ctx->b_coln.as<uint32_t>(),
                                                                            ctx->b_blob_dom.as<uint32_t>(), ctx->b_tileseg.as<uint32_t>());
