@@ -38,19 +38,28 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 
 // key = (class + 1) * nbins + bin (class 0 when cls is NULL, bin 0 when bins is NULL); hist[key] counts (per-block
 // histogram in shared memory first: a few dozen hot global addresses would serialise the whole grid).
-__global__ void __launch_bounds__(256) k_bucket_keys(const int32_t* __restrict__ cls, const uint8_t* __restrict__ bins, uint32_t n, uint32_t nbins,
-                                                     uint32_t nb, uint16_t* __restrict__ keys, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sh[FE_MAX_TOTAL];
-    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0;
+// Both lists in one go (positions 0..nD-1 the domains, nD.. the range blocks; bins likewise): the range keys carry `list_bit`, so
+// ONE stable radix sort orders both lists, and vals = the index inside the own list.  hist_d / hist_r as before.
+__global__ void __launch_bounds__(256) k_bucket_keys(const int32_t* __restrict__ dom_cls, const int32_t* __restrict__ rng_cls, const uint8_t* __restrict__ bins,
+                                                     uint32_t nD, uint32_t nR, uint32_t nbins, uint32_t nb, uint32_t list_bit, uint16_t* __restrict__ keys,
+                                                     uint32_t* __restrict__ vals, uint32_t* __restrict__ hist_d, uint32_t* __restrict__ hist_r) {
+    __shared__ uint32_t sh[2 * FE_MAX_TOTAL];
+    for (uint32_t b = threadIdx.x; b < 2 * FE_MAX_TOTAL; b += blockDim.x) sh[b] = 0;
     __syncthreads();
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t k = (cls ? (uint32_t)(cls[i] + 1) : 0u) * nbins + (bins ? (uint32_t)bins[i] : 0u);
-        keys[i] = (uint16_t)k;
-        atomicAdd(&sh[k], 1u);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nD + nR; i += gridDim.x * blockDim.x) {
+        const bool is_rng = i >= nD;
+        const uint32_t j = is_rng ? i - nD : i;
+        const int32_t* cls = is_rng ? rng_cls : dom_cls;
+        const uint32_t k = (cls ? (uint32_t)(cls[j] + 1) : 0u) * nbins + (bins ? (uint32_t)bins[i] : 0u);
+        keys[i] = (uint16_t)(k | (is_rng ? list_bit : 0u));
+        vals[i] = j;
+        atomicAdd(&sh[k + (is_rng ? FE_MAX_TOTAL : 0)], 1u);
     }
     __syncthreads();
-    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x)
-        if (sh[b]) atomicAdd(&hist[b], sh[b]);
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+        if (sh[b]) atomicAdd(&hist_d[b], sh[b]);
+        if (sh[FE_MAX_TOTAL + b]) atomicAdd(&hist_r[b], sh[FE_MAX_TOTAL + b]);
+    }
 }
 
 // One CTA of 512 threads: bucket offsets, the interval ends of every bucket, the tile layout of the operand blob and the
@@ -504,9 +513,8 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
     // ---- buffers ----
     const size_t n = (size_t)nD + nR;
     FE_CUDA(ctx, ctx->b_keys_tmp.ensure(n * 6 + 512));
-    FE_CUDA(ctx, ctx->b_vals_tmp.ensure((size_t)std::max(nD, nR) * 4));
-    FE_CUDA(ctx, ctx->b_dom_order2.ensure((size_t)nD * 4 + 16));
-    FE_CUDA(ctx, ctx->b_rng_order2.ensure((size_t)nR * 4 + 16));
+    FE_CUDA(ctx, ctx->b_vals_tmp.ensure(n * 4));
+    FE_CUDA(ctx, ctx->b_dom_order2.ensure(n * 4 + 16));     // both orders: the domains', then the range blocks' 
     FE_CUDA(ctx, ctx->b_hist.ensure((size_t)FE_MAX_TOTAL * 10 * 4 + 2 * FE_MAX_BUCKETS * 4));
     FE_CUDA(ctx, ctx->b_plan.ensure(sizeof(LevelPlan)));
     FE_CUDA(ctx, ctx->b_ctl.ensure(sizeof(SliceCtl)));
@@ -531,21 +539,19 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
         ctx->stats.kernel_launches += 2;
         FE_CUDA(ctx, cudaGetLastError());
     }
-    PLAUNCH(ctx, k_bucket_keys, std::min(cdiv_u(nD, 1024), 4u * ctx->n_sm), 256, lv.dom_cls, st->bins ? bins8 : nullptr, nD, st->nbins, nb, keys, hist_d);
-    PLAUNCH(ctx, k_bucket_keys, std::min(cdiv_u(nR, 1024), 4u * ctx->n_sm), 256, lv.rng_cls, st->bins ? bins8 + nD : nullptr, nR, st->nbins, nb, keys + nD, hist_r);
+    int bits = 1;
+    while ((1u << bits) < nb) ++bits;
+    PLAUNCH(ctx, k_bucket_keys, std::min(cdiv_u(n, 1024), 4u * ctx->n_sm), 256, lv.dom_cls, lv.rng_cls, st->bins ? bins8 : nullptr, nD, nR, st->nbins, nb, 1u << bits, keys,
+            ctx->b_vals_tmp.as<uint32_t>(), hist_d, hist_r);
     if (sorted) {
-        int bits = 1;
-        while ((1u << bits) < nb) ++bits;
-        PLAUNCH(ctx, k_iota, cdiv_u(std::max(nD, nR), 256), 256, ctx->b_vals_tmp.as<uint32_t>(), std::max(nD, nR));
-        size_t tmp_d = 0, tmp_r = 0;
-        FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_d, keys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order2.as<uint32_t>(), (int)nD, 0, bits, ctx->stream));
-        FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_r, keys + nD, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order2.as<uint32_t>(), (int)nR, 0, bits, ctx->stream));
-        FE_CUDA(ctx, ctx->b_sort_tmp.ensure(std::max(tmp_d, tmp_r)));
-        FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_d, keys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order2.as<uint32_t>(), (int)nD, 0, bits, ctx->stream));
-        FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp_r, keys + nD, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_rng_order2.as<uint32_t>(), (int)nR, 0, bits, ctx->stream));
-        ctx->stats.kernel_launches += 6;
+        // one stable sort for both lists: the list bit is the top key bit
+        size_t tmp = 0;
+        FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order2.as<uint32_t>(), (int)n, 0, bits + 1, ctx->stream));
+        FE_CUDA(ctx, ctx->b_sort_tmp.ensure(tmp));
+        FE_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->b_sort_tmp.p, tmp, keys, keys_out, ctx->b_vals_tmp.as<uint32_t>(), ctx->b_dom_order2.as<uint32_t>(), (int)n, 0, bits + 1, ctx->stream));
+        ctx->stats.kernel_launches += 3;
         st->dom_order = ctx->b_dom_order2.as<uint32_t>();
-        st->rng_order = ctx->b_rng_order2.as<uint32_t>();
+        st->rng_order = ctx->b_dom_order2.as<uint32_t>() + nD;
     }
     BucketOff c8{};
     for (int k = 0; k < FE_NK; ++k) c8.v[k] = !multipass ? FE_NONE32 : (k == FE_NK - 1 ? nD : (uint32_t)((((uint64_t)nD) << k) / 128 + 1));
