@@ -34,6 +34,27 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
     for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t += sh[w];
     return t;
 }
+// exclusive prefix sums over the block (blockDim <= 1024, sh: 33 words); *total = sum of all; two barriers
+template <typename V>
+__device__ __forceinline__ V block_excl_scan(V v, V* sh, V* total) {
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    V inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const V x = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= (uint32_t)o) inc += x;
+    }
+    __syncthreads();                       // sh may still be read by the previous call
+    if (lane == 31) sh[w] = inc;
+    __syncthreads();
+    V base = 0, tot = 0;
+    for (uint32_t i = 0; i < nw; ++i) {
+        const V x = sh[i];
+        if (i < w) base += x;
+        tot += x;
+    }
+    if (total) *total = tot;
+    return base + inc - v;
+}
 } // namespace
 
 // key = (class + 1) * nbins + bin (class 0 when cls is NULL, bin 0 when bins is NULL); hist[key] counts (per-block
@@ -67,7 +88,7 @@ __global__ void __launch_bounds__(256) k_bucket_keys(const int32_t* __restrict__
 __global__ void __launch_bounds__(512) k_level_plan(PlanArgs a, const uint32_t* __restrict__ dom_hist, const uint32_t* __restrict__ rng_hist,
                                                     const uint32_t* __restrict__ pre, uint32_t nb, uint32_t nbins, uint32_t ngroups, uint32_t span,
                                                     uint32_t nD, uint32_t nR, uint32_t nt) {
-    __shared__ uint32_t s_scan[512];
+    __shared__ uint32_t s_scan[33];
     LevelPlan* p = a.plan;
     SliceCtl* ctl = a.ctl;
     const uint32_t t = threadIdx.x;
@@ -75,18 +96,10 @@ __global__ void __launch_bounds__(512) k_level_plan(PlanArgs a, const uint32_t* 
     // exclusive scans of the two histograms
     for (int pass = 0; pass < 2; ++pass) {
         const uint32_t v = pass ? rc : dc;
-        s_scan[t] = v;
-        __syncthreads();
-        for (uint32_t o = 1; o < 512; o <<= 1) {
-            const uint32_t x = t >= o ? s_scan[t - o] : 0u;
-            __syncthreads();
-            s_scan[t] += x;
-            __syncthreads();
-        }
+        const uint32_t ex = block_excl_scan(v, s_scan, (uint32_t*)nullptr);
         uint32_t* dst = pass ? p->roff : p->doff;
-        if (t < nb) dst[t + 1] = s_scan[t];
+        if (t < nb) dst[t + 1] = ex + v;
         if (t == 0) dst[0] = 0;
-        __syncthreads();
     }
     // interval ends of my bucket
     const uint32_t min_step = a.min_tiles * GR;
@@ -102,24 +115,25 @@ __global__ void __launch_bounds__(512) k_level_plan(PlanArgs a, const uint32_t* 
             if (dc - hi < min_step / 2) hi = dc;     // no slivers at the end of the scan
         }
         if (t < nb) p->dend[k][t] = hi;
+        {   // prefix over the buckets: the slice planner takes neighbourhood sums by difference
+            const uint32_t v = t < nb ? hi : 0u;
+            const uint32_t ex = block_excl_scan(v, s_scan, (uint32_t*)nullptr);
+            if (t < nb) p->dendP[k][t + 1] = ex + v;
+            if (t == 0) p->dendP[k][0] = 0;
+        }
         tiles[k] = t < nb ? (hi - done + nt - 1) / nt : 0u;
         done = hi;
     }
     // tile layout, interval-major: exclusive scan over (k, b)
     uint32_t base = 0;
     const uint32_t nk = a.multipass ? FE_NK : 1;
-    for (uint32_t k = 0; k < nk; ++k) {
-        s_scan[t] = tiles[k];
-        __syncthreads();
-        for (uint32_t o = 1; o < 512; o <<= 1) {
-            const uint32_t x = t >= o ? s_scan[t - o] : 0u;
-            __syncthreads();
-            s_scan[t] += x;
-            __syncthreads();
-        }
-        if (t < nb) p->tile0[k * nb + t] = base + s_scan[t] - tiles[k];
-        base += s_scan[511];
-        __syncthreads();
+#pragma unroll
+    for (uint32_t k = 0; k < FE_NK; ++k) {
+        if (k >= nk) break;
+        uint32_t tot = 0;
+        const uint32_t ex = block_excl_scan(tiles[k], s_scan, &tot);
+        if (t < nb) p->tile0[k * nb + t] = base + ex;
+        base += tot;
     }
     if (t == 0) {
         p->tile0[nk * nb] = base;
@@ -144,7 +158,8 @@ __global__ void __launch_bounds__(512) k_level_plan(PlanArgs a, const uint32_t* 
 __global__ void k_level_ranges(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
                                const uint32_t* __restrict__ order, const LevelPlan* __restrict__ plan, uint32_t T, int centred, int flips,
                                const uint32_t* __restrict__ cells, const uint32_t* __restrict__ cells2, uint32_t cells_w,
-                               ListEntry* __restrict__ list0, uint16_t* __restrict__ pos_bucket) {
+                               ListEntry* __restrict__ list0, uint16_t* __restrict__ pos_bucket, unsigned long long* __restrict__ rowbest,
+                               uint32_t* __restrict__ rowhit) {
     // a warp per block from T = 16 on (coalesced rows), a thread per block below
     const uint32_t lanes = (T >= 16 && !cells2) ? 32u : 1u;
     const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x, p = gt / lanes, lane = gt % lanes;
@@ -173,6 +188,10 @@ __global__ void k_level_ranges(const uint8_t* __restrict__ img, uint32_t stride,
     e.a2 = s2;
     e.mirror = flips ? (idx & 1u) : 0u;
     list0[p] = e;
+    // the four result rows of the position start empty
+    reinterpret_cast<ulonglong2*>(rowbest)[2 * p] = make_ulonglong2(FE_INF64, FE_INF64);
+    reinterpret_cast<ulonglong2*>(rowbest)[2 * p + 1] = make_ulonglong2(FE_INF64, FE_INF64);
+    reinterpret_cast<uint4*>(rowhit)[p] = make_uint4(FE_NONE32, FE_NONE32, FE_NONE32, FE_NONE32);
     uint32_t lo = 0, hi = plan->nb - 1;               // bucket b with roff[b] <= p < roff[b + 1]
     while (lo < hi) {
         const uint32_t mid = (lo + hi + 1) >> 1;
@@ -257,9 +276,8 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
     unsigned long long left = 0;
     for (uint32_t c = t; c < nb; c += 256) {
         if (!s_cnt[c]) continue;
-        unsigned long long cols = 0;
-        for (uint32_t b = grp_lo(p, c, whole); b <= grp_hi(p, c, whole); ++b)
-            cols += (p->doff[b + 1] - p->doff[b]) - ((kd && !whole) ? p->dend[kd - 1][b] : 0u);
+        const uint32_t lo = grp_lo(p, c, whole), hi = grp_hi(p, c, whole);     // neighbourhood sums by difference of prefixes
+        const unsigned long long cols = (p->doff[hi + 1] - p->doff[lo]) - ((kd && !whole) ? p->dendP[kd - 1][hi + 1] - p->dendP[kd - 1][lo] : 0u);
         left += cols * s_cnt[c];
     }
     left = block_sum_u64(left, s_red);
@@ -302,8 +320,10 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
             unsigned long long cols = 0, run = 0;
             if (s_cnt[c]) {
                 const uint32_t lo = grp_lo(p, c, whole), hi = grp_hi(p, c, whole);
-                for (uint32_t b = lo; b <= hi; ++b) cols += p->dend[k1][b] - (k0 ? p->dend[k0 - 1][b] : 0u);
-                for (uint32_t k = k0; k <= k1; ++k) run += p->tile0[k * nb + hi + 1] - p->tile0[k * nb + lo];
+                cols = (p->dendP[k1][hi + 1] - p->dendP[k1][lo]) - (k0 ? p->dendP[k0 - 1][hi + 1] - p->dendP[k0 - 1][lo] : 0u);
+#pragma unroll
+                for (uint32_t k = 0; k < FE_NK; ++k)      // unrolled and predicated: the loads of all intervals are in flight together
+                    if (k >= k0 && k <= k1) run += p->tile0[k * nb + hi + 1] - p->tile0[k * nb + lo];
             }
             s_tiles[c] = cols ? (s_cnt[c] + 31) / 32 : 0u;
             work += cols * s_cnt[c] * 4ull;
@@ -319,31 +339,37 @@ __global__ void __launch_bounds__(256) k_slice_plan(PlanArgs a, int phase, uint3
             uint32_t per_tile = 0;
             if (s_tiles[c]) {
                 const uint32_t lo = grp_lo(p, c, whole), hi = grp_hi(p, c, whole);
-                for (uint32_t k = k0; k <= k1; ++k) {
-                    const uint32_t nrun = p->tile0[k * nb + hi + 1] - p->tile0[k * nb + lo];
-                    per_tile += (nrun + run_len - 1) / run_len;
-                }
+#pragma unroll
+                for (uint32_t k = 0; k < FE_NK; ++k)
+                    if (k >= k0 && k <= k1) {
+                        const uint32_t nrun = p->tile0[k * nb + hi + 1] - p->tile0[k * nb + lo];
+                        per_tile += (nrun + run_len - 1) / run_len;
+                    }
             }
             s_cnt[c] = ((s_tiles[c] + a.tiles_per_item - 1) / a.tiles_per_item) * per_tile;   // work items of the bucket (s_cnt is not needed any more)
         }
         __syncthreads();
+        // prefixes of the work items and the row tiles over the buckets: thread t owns buckets 2 t and 2 t + 1
+        unsigned long long acc = 0;
+        uint32_t tiles = 0;
+        {
+            const uint32_t c0 = 2 * t, c1 = 2 * t + 1;
+            const unsigned long long i0 = c0 < nb ? s_cnt[c0] : 0u, i1 = c1 < nb ? s_cnt[c1] : 0u;
+            const uint32_t t0 = c0 < nb ? s_tiles[c0] : 0u, t1 = c1 < nb ? s_tiles[c1] : 0u;
+            const unsigned long long ei = block_excl_scan(i0 + i1, s_red, &acc);
+            const uint32_t et = block_excl_scan(t0 + t1, reinterpret_cast<uint32_t*>(s_red), &tiles);
+            if (c0 < nb) { ctl->item_prefix[c0] = (uint32_t)min(ei, (unsigned long long)0xFFFFFFFFull); ctl->tile_prefix[c0] = et; }
+            if (c1 < nb) { ctl->item_prefix[c1] = (uint32_t)min(ei + i0, (unsigned long long)0xFFFFFFFFull); ctl->tile_prefix[c1] = et + t0; }
+        }
         if (t == 0) {
-            uint64_t acc = 0;
-            uint32_t tiles = 0;
-            for (uint32_t c = 0; c < nb; ++c) {
-                ctl->item_prefix[c] = (uint32_t)min(acc, (uint64_t)0xFFFFFFFFull);
-                ctl->tile_prefix[c] = tiles;
-                acc += s_cnt[c];
-                tiles += s_tiles[c];
-            }
-            ctl->item_prefix[nb] = (uint32_t)min(acc, (uint64_t)0xFFFFFFFFull);
+            ctl->item_prefix[nb] = (uint32_t)min(acc, (unsigned long long)0xFFFFFFFFull);
             ctl->tile_prefix[nb] = tiles;
             if (acc > a.max_items) ctl->overflow = 1;
             ctl->n_row_tiles = tiles;
             ctl->k0 = k0; ctl->k1 = k1; ctl->run_len = run_len;
             ctl->whole_group = whole ? 1u : 0u;
             ctl->no_min = (a.use_thr && (!a.need_min || (a.bins && !whole))) ? 1u : 0u;
-            ctl->n_items = (uint32_t)min(acc, (uint64_t)a.max_items);
+            ctl->n_items = (uint32_t)min(acc, (unsigned long long)a.max_items);
             ctl->evaluated += work;
             ctl->passes += 1;
             ctl->active = ordinal;
@@ -583,9 +609,8 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
     pa.tiles_per_item = (((kind == 1 && g.T <= 16) || (kind == 0 && g.T == 8)) && !getenv("FE_NO_PAIR")) ? 2u : 1u;
     PLAUNCH(ctx, k_level_plan, 1, 512, pa, hist_d, hist_r, pre, nb, st->nbins, st->ngroups, st->span, nD, nR, nt);
     PLAUNCH(ctx, k_level_ranges, cdiv_u((uint64_t)nR * ((g.T >= 16 && !lv.cells2) ? 32 : 1), 128), 128, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, st->rng_order, pa.plan, g.T,
-            kind == 1 ? 0 : 1, lv.flips ? 1 : 0, lv.cells, lv.cells2, lv.cells_w, pa.list[0], ctx->b_posb.as<uint16_t>());
-    PLAUNCH(ctx, k_fill_u64, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowbest.as<unsigned long long>(), FE_INF64, (size_t)nR * 4);
-    PLAUNCH(ctx, k_fill_u32, cdiv_u((uint64_t)nR * 4, 256), 256, ctx->b_rowhit.as<uint32_t>(), FE_NONE32, (size_t)nR * 4);
+            kind == 1 ? 0 : 1, lv.flips ? 1 : 0, lv.cells, lv.cells2, lv.cells_w, pa.list[0], ctx->b_posb.as<uint16_t>(),
+            ctx->b_rowbest.as<unsigned long long>(), ctx->b_rowhit.as<uint32_t>());
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.as<uint32_t>() + 2, 0, 2 * sizeof(uint32_t), ctx->stream));
     F16Args& fa = st->fa;
     I8Args& ia = st->ia;

@@ -28,6 +28,7 @@ struct LevelPlan {
     uint32_t doff[FE_MAX_TOTAL + 1];      // domain positions (sorted order) of bucket b
     uint32_t roff[FE_MAX_TOTAL + 1];      // level positions of the range blocks of bucket b
     uint32_t dend[FE_NK][FE_MAX_TOTAL];   // bucket-relative end of interval k (columns)
+    uint32_t dendP[FE_NK][FE_MAX_TOTAL + 1];   // dendP[k][b] = sum of dend[k][b'] over b' < b: columns of a bucket neighbourhood by difference
     uint32_t tile0[FE_NK * FE_MAX_TOTAL + 1];   // first blob tile of chunk k * nb + b; [nk * nb] = n_tiles
 };
 
