@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __rest
 bool launch_decode_step_small(cudaStream_t stream, const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items, uint32_t n,
                               uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done) {
     if (T == 4) k_decode_step_small<4, 8><<<(n + 63) / 64, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done);
-    else if (T == 8) k_decode_step_small<8, 4><<<(n + 31) / 32, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done);
+    else if (T == 8) k_decode_step_small<8, 8><<<(n + 63) / 64, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done);
     else return false;
     return true;
 }
