@@ -198,6 +198,8 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        # an NVML query takes driver locks of the GPU it asks about: a few samples per timed region, not a busy poll
+        self.interval = float(os.environ.get("FE_BENCH_CLOCK_INTERVAL", "0.1"))
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -208,7 +210,7 @@ class ClockSampler(threading.Thread):
             self.nv = None
 
     def run(self):
-        if not self.nv:
+        if not self.nv or self.interval <= 0:
             return
         nv = self.nv
         names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
@@ -223,7 +225,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(self.interval)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -341,6 +343,15 @@ def run_b200(a):
     if not os.path.exists(fb.library_path()):
         raise SystemExit("libfractencode_b200.so missing: run __graft_entry__.build() (no fallback path exists)")
     torch.cuda.set_device(local)
+    if world > 1 and os.environ.get("FE_BENCH_PIN", "1") != "0" and hasattr(os, "sched_setaffinity"):
+        # one slice of the host cores per rank: the level driver is a latency-bound host thread (one synchronisation per quadtree
+        # level), and eight of them plus their NCCL / monitor threads migrating over each other show up as idle GPU time
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
+        except OSError:
+            pass
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -465,7 +476,7 @@ def run_b200(a):
         dms = float(ctx.stats().last_decode_ms) / dec_iters
         dbytes = 2.0 * W * H + 64.0 * len(items_host)       # read plane + write plane + item records per iteration
         decode_info = {"ms_per_iteration": dms, "algorithmic_bytes": dbytes, "achieved_gbs": dbytes / (dms * 1e-3) / 1e9,
-                       "note": "k_decode_step + k_sqdiff (convergence sum re-reads both planes: +2*W*H real traffic) + 8-byte D2H per iteration"}
+                       "note": "k_decode_step_small<8>/<4> with the convergence sum fused in (+ W*H re-read of the old plane) + k_decode_check per iteration; the planes (2 x 16 MB) and the items (21 MB) stay in L2 at this size, the kernels are bound by L1 wavefronts of the scattered 16-byte source rows (profiles/search_kernels_r2.md)"}
 
     my = torch.tensor([sum(times), sum(e_times), float(matches_step), float(n_items)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -474,8 +485,12 @@ def run_b200(a):
         tsum = my.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         tot_ms, e_ms, all_matches, all_items = tmax[0].item(), tmax[1].item(), tsum[2].item(), tsum[3].item()
+        every = [torch.zeros_like(my) for _ in range(world)]
+        dist.all_gather(every, my)
+        per_rank_ms = [round(t[0].item() / a.steps, 3) for t in every]
     else:
         tot_ms, e_ms, all_matches, all_items = my[0].item(), my[1].item(), my[2].item(), my[3].item()
+        per_rank_ms = [round(tot_ms / a.steps, 3)]
     strong = strong_config4(a, ctx, fb, rank, world, sync_all) if (world > 1 and not by_ranges and not a.no_strong) else None
     batch = batch_config5(a, ctx, fb, rank, world, sync_all) if (not by_ranges and not a.no_batch) else None
     if rank == 0:
@@ -513,6 +528,7 @@ def run_b200(a):
             "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": W * H, "d2h_bytes_per_step": int(e_items) * 64,
                     "ms_per_step": e_ms / a.steps, "mpix_per_s": (1 if by_ranges else world) * W * H / 1e6 / (e_ms / a.steps * 1e-3)},
             "gpu_launches": launches,
+            "per_rank_ms_per_step": per_rank_ms, "host_cores": os.cpu_count(),
             "items_per_step": all_items,
             "evaluated_matches_per_step": evaluated_step,
             "levels": levels,
