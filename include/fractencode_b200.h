@@ -116,7 +116,11 @@ int fe_abi_version(void);
 /* Replaces: the `const ImagePlane& sourceImage` the engine/estimator constructors
  * capture (encode/EncodingEngine2.hpp:52-59, encode/TransformEstimator2.hpp:14-27).
  * Host pixels are copied to the device; the caller keeps ownership.  `px` has
- * height*stride bytes, stride >= width (image/Image2.hpp:84-111). */
+ * height*stride bytes, stride >= width (image/Image2.hpp:84-111).
+ * The copy is enqueued on the context's stream (cudaMemcpyAsync): pageable memory has been
+ * read when the call returns; PAGE-LOCKED memory is read asynchronously and must stay
+ * unchanged until the next call on this context that returns results to the host (any
+ * fe_encode_*, fe_classify, fe_get_image ...), which orders itself behind the copy. */
 int fe_set_image(fe_ctx* ctx, const uint8_t* px, uint32_t width, uint32_t height, uint32_t stride);
 /* Separate source (domain) and target (range) planes, as TransformEstimator2's
  * (sourceImage, targetImage) pair allows (tests/TransformEstimatorTest.cpp:13-47). */
