@@ -33,8 +33,9 @@ class _Env:
 
 # default = slices + brightness bins (+ the lower-bound prefilter on the T = 32 level); "no_prefilter" takes the exact kind there;
 # "one_pass" = one full scan per level, no pruning of any kind
+# "plain_prep" = one row tile per work item and per-block class / bin / norm kernels instead of the level's cell sums
 MODES = {"pruned": {}, "no_prefilter": {"FE_NO_LB": "1"}, "slices_only": {"FE_NO_BINS": "1", "FE_NO_LB": "1"},
-         "one_pass": {"FE_SINGLE_PASS": "1", "FE_NO_LB": "1"}}
+         "plain_prep": {"FE_NO_PAIR": "1", "FE_NO_CELLS": "1"}, "one_pass": {"FE_SINGLE_PASS": "1", "FE_NO_LB": "1"}}
 
 
 @pytest.mark.parametrize("kind,cls,thr", [(0, False, 25.0), (0, False, 6.0), (0, True, 25.0), (1, False, 40.0), (2, False, 25.0)])
@@ -52,7 +53,7 @@ def test_quadtree_pruned_equals_one_pass(ctx, kind, cls, thr):
             out[name] = (items, counts, int(st.matches), int(st.evaluated))
     ref_items, ref_counts, ref_matches, ref_eval = out["one_pass"]
     assert ref_eval == ref_matches, "the one-pass search scores every admissible candidate"
-    for name in ("pruned", "no_prefilter", "slices_only"):
+    for name in ("pruned", "no_prefilter", "slices_only", "plain_prep"):
         items, counts, matches, evaluated = out[name]
         assert counts == ref_counts and matches == ref_matches
         # worst case on the last level: the bins (about a third of the scan) found hits for some ranges only, the rest
@@ -82,6 +83,7 @@ def test_single_level_with_threshold_keeps_the_minimum(ctx, fo, T, thr):
                 assert int(st.evaluated) == int(st.matches)
     assert_items_equal(got["pruned"], got["one_pass"], "T=%d pruned" % T)
     assert_items_equal(got["slices_only"], got["one_pass"], "T=%d slices" % T)
+    assert_items_equal(got["plain_prep"], got["one_pass"], "T=%d plain prep" % T)
     hits = np.count_nonzero(got["one_pass"]["distance"] <= thr)
     assert hits > 0 and (T == 32 or hits < len(rng)), "the case must mix ranges with and without a hit (%d of %d)" % (hits, len(rng))
     sub = rng[:: max(1, len(rng) // 16)][:16]
