@@ -13,7 +13,10 @@
  *
  * Threading: one fe_ctx per device and per host thread (the reference runs one
  * thread per engine, encode/EncodingEngine2.hpp:126-155).  A ctx is not
- * thread-safe.  All work is issued on the ctx's CUDA stream.
+ * thread-safe.  All work is issued on the ctx's CUDA stream.  Every call makes
+ * the ctx's device the calling thread's current CUDA device (cudaSetDevice) and
+ * leaves it so: a host that drives several devices from ONE thread restores its
+ * own current device after a call.
  *
  * There is NO CPU fallback: fe_create fails when no sm_100 device is present.
  */
@@ -126,7 +129,9 @@ int fe_set_image(fe_ctx* ctx, const uint8_t* px, uint32_t width, uint32_t height
  * (sourceImage, targetImage) pair allows (tests/TransformEstimatorTest.cpp:13-47). */
 int fe_set_images(fe_ctx* ctx, const uint8_t* src_px, uint32_t src_w, uint32_t src_h, uint32_t src_stride,
                   const uint8_t* tgt_px, uint32_t tgt_w, uint32_t tgt_h, uint32_t tgt_stride);
-/* Same, but `dev_px` already lives in this device's memory (copied device-to-device). */
+/* Same, but `dev_px` already lives in this device's memory (copied device-to-device ON THE
+ * CTX's STREAM: pixels written on another stream must be complete -- event or synchronise --
+ * before this call; with the caller's own stream passed to fe_create there is nothing to do). */
 int fe_set_image_device(fe_ctx* ctx, const void* dev_px, uint32_t width, uint32_t height, uint32_t stride);
 
 /* Replaces: BrightnessBlocksClassifier2::preclassify / getCategory
