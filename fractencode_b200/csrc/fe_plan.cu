@@ -602,6 +602,8 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
     // work items: the i8 kind reloads its A tile per item (128 KB at T = 32, one buffer): longer and fewer items there
     pa.min_run = kind != 1 ? 16u : (g.T >= 32 ? 48u : 24u);
     pa.items_per_sm = kind != 1 ? 8u : (g.T >= 32 ? 4u : 6u);
+    if (const char* e = getenv(kind == 1 ? "FE_I8_ITEMS" : "FE_F16_ITEMS")) pa.items_per_sm = (uint32_t)std::max(1, atoi(e));   // tuning
+    if (const char* e = getenv(kind == 1 ? "FE_I8_MIN_RUN" : "FE_F16_MIN_RUN")) pa.min_run = (uint32_t)std::max(1, atoi(e));
     // i8 kind up to T = 16: a work item is TWO row tiles (64 range blocks, M = 256 through two accumulator pairs) sharing every
     // B stage -- halves the L2 -> shared-memory operand stream, which bounds the kernel before the tensor pipe does
     // The kind::f16 search does the same at T = 8 (fe_search_f16.cu, PAIR; measured: T = 8 -2 %, T = 4 +14 % -- its short K makes
