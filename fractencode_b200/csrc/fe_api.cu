@@ -58,7 +58,7 @@ static bool threshold_n16(double thr, uint32_t S, uint32_t* out) {
     return true;
 }
 
-// Brightness bins of a threshold search (search_tc): radius of the Cauchy-Schwarz bound, bin width, bins, span.
+// Brightness bins of a threshold search (fe_plan.cu: search_level_device): radius of the Cauchy-Schwarz bound, bin width, bins, span.
 void fe_plan_bins(uint32_t N, uint32_t thr16, fe_threshold_plan* pl) {
     const uint64_t nt = (uint64_t)N * thr16;
     uint64_t R = (uint64_t)std::sqrt((double)nt);

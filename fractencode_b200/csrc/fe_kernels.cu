@@ -1,5 +1,5 @@
 // fe_kernels.cu -- CUDA kernels of the search path except the tcgen05 contraction
-// (fe_search_umma.cu): grids, classification, operand preparation, the exact integer
+// (fe_search_f16.cu, fe_search_i8.cu): grids, classification, cell sums, operand preparation, the exact integer
 // search, winner finalisation (least squares s/o), quadtree bookkeeping, decode gather,
 // quantizer and the synthetic image generator.  sm_100a only.
 //
@@ -396,7 +396,7 @@ __global__ void k_class_keys(const int32_t* __restrict__ cls, uint32_t n, uint8_
 // Range rows.  One warp per range position j (range index order[j]).  Writes the four rows
 // 4j+k: fast geometry -> the range block under the INVERSE of rotation k (so that one unrotated
 // domain pool serves all four isometries); generic geometry -> four copies of the block.
-// Also rowc[j] = 16*sum(r^2).  Optionally the fp16 rows of the tcgen05 path (A16, see fe_search_umma.cu).
+// Also rowc[j] = 16*sum(r^2).  (Exact dp4a path only: the tensor kinds build their own operands.)
 __global__ void k_build_rows(const uint8_t* __restrict__ img, uint32_t stride, const fe_grid_item* __restrict__ rng,
                              const uint32_t* __restrict__ order, uint32_t n, uint32_t T, uint32_t Npad, int fast,
                              uint8_t* __restrict__ A, uint32_t* __restrict__ rowc) {

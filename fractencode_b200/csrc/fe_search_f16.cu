@@ -1,7 +1,11 @@
 // fe_search_f16.cu -- tcgen05 kind::f16 search of the small range blocks (T = 4, 8), scheduled from device memory.
 //
-// Same contraction and epilogue as fe_search_umma.cu (operands centred at 510, the integer V = h - sum a b in fp32 TMEM
-// accumulators, FMNMX3 row argmin; see the header of that file for the exactness argument).  What differs:
+// Contraction: operands centred at 510 (a = 4 r - 510, b = D - 510); with sum b^2 = 2 h + p the score is
+// n16 = sum a^2 + 2 V + p, V = h - sum a b.  The MMA computes V itself: A row = [-a | 1 | 2048 | 2048 | 0...], B column =
+// [b | h0 | h1 | 2048 h2 | 0...] (limbs of h; every entry an integer <= 2048, exact in fp16).  Every product and partial sum is
+// an integer below 2^24 whenever the final V is, so the fp32 TMEM accumulator is exact; a winner with V >= 2^24 - 64 raises a
+// flag and the level is redone on the i8 kind.  Epilogue: FMNMX3 row argmin (fe_umma_epi.cuh).
+//
 //  * work items come from a record list in device memory (fe_plan.cu: k_expand_items) and the slice's parameters from
 //    SliceCtl, so the host launches the kernel without knowing what the previous slice left -- a launch whose ordinal was
 //    not planned returns at once;
@@ -12,7 +16,7 @@
 //
 // Kernel anatomy (one persistent CTA per SM, 768 threads, register budget re-split with setmaxnreg):
 //   warps 0-3   issuers (one thread each): B tile bulk copies two steps ahead, tcgen05.mma M128 x N128 x K16, one commit
-//               per tile; accumulator t % 4 of the 4 x 128 TMEM columns                                   (40 registers)
+//               per tile; accumulator t % 4 of the 4 x 128 TMEM columns (PAIR: two issuers, see below)   (40 registers)
 //   warps 4-7   A builders: 8 range blocks per warp, lane = (block, rotation)                              (56 registers)
 //   warps 8-23  two compute warpgroups of 8 warps: tcgen05.ld 32x32b.x32 x 2 -> release -> FMNMX3 argmin   (96 registers)
 #include <cuda_fp16.h>

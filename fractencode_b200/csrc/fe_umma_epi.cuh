@@ -1,5 +1,5 @@
 // fe_umma_epi.cuh -- row-argmin epilogue of the tcgen05 kind::f16 search kernels: one thread owns one row x UM_HALF
-// accumulator columns of a tile (fe_search_umma.cu: host-scheduled slices; fe_search_f16.cu: device-scheduled slices).
+// accumulator columns of a tile (fe_search_f16.cu).
 #pragma once
 #include "fe_umma_dev.cuh"
 
