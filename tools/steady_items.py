@@ -2,7 +2,8 @@
 """Short-item experiment: one full-scan launch of a T = 8 level (1024^2: 512 row tiles x 127 column tiles), work items cut to
 FE_F16_MIN_RUN column tiles (FE_F16_ITEMS work items per SM).  Prints the kernel time.  (With a build whose A builders only
 signed their barriers after the first tile of each buffer -- stale but real rows -- the same runs were 6-8 % faster at every
-run length from 21 to 87 tiles: the in-kernel A build costs that much, independent of the item length.)"""
+run length from 21 to 87 tiles -- proportional to time rather than to the number of items, so probably the epilogue's
+data-dependent paths on stale rows rather than the cost of the build.)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fractencode_b200 as fb  # noqa: E402
