@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--cpu-blocks", type=int, default=0, help="range blocks per level in the CPU sample (0: 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch", action="store_true", help="skip the batch-mode sub-measurement (config 5)")
+    ap.add_argument("--no-decode-large", action="store_true", help="N = 1: skip the 8192 x 8192 decode measurement")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-measurement (config 4)")
     ap.add_argument("--shard", default="images", choices=["images", "ranges"],
                     help="N > 1: one image per GPU (weak scaling, default) or the range blocks of ONE image sharded over the GPUs "
@@ -477,6 +478,19 @@ def run_b200(a):
         dbytes = 2.0 * W * H + 64.0 * len(items_host)       # read plane + write plane + item records per iteration
         decode_info = {"ms_per_iteration": dms, "algorithmic_bytes": dbytes, "achieved_gbs": dbytes / (dms * 1e-3) / 1e9,
                        "note": "k_decode_step_small<8>/<4> with the convergence sum fused in (+ W*H re-read of the old plane) + k_decode_check per iteration; the planes (2 x 16 MB) and the items (21 MB) stay in L2 at this size, the kernels are bound by L1 wavefronts of the scattered 16-byte source rows (profiles/search_kernels_r2.md)"}
+
+        if world == 1 and not a.no_decode_large and W * H < 8192 * 8192:
+            # the same at 8192 x 8192, where the two planes (2 x 67 MB) and the items leave the 126 MB L2
+            ctx.set_synthetic_image(8192, 8192, 4321, 0)
+            big, _ = ctx.encode_quadtree(a.tmax, a.tmin, params)
+            ctx.decode(big, 8192, 8192, max_iters=dec_iters, eps=-1e9)
+            ctx.decode(big, 8192, 8192, max_iters=dec_iters, eps=-1e9)
+            bms = float(ctx.stats().last_decode_ms) / dec_iters
+            bbytes = 2.0 * 8192 * 8192 + 64.0 * len(big)
+            decode_info["at_8192"] = {"ms_per_iteration": bms, "items": int(len(big)), "algorithmic_bytes": bbytes,
+                                      "achieved_gbs": bbytes / (bms * 1e-3) / 1e9, "frac_hbm": bbytes / (bms * 1e-3) / 1e9 / peaks()["hbm_gbs"]}
+            del big
+            ctx.set_synthetic_image(W, H, 1234, 0)
 
     my = torch.tensor([sum(times), sum(e_times), float(matches_step), float(n_items)], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -702,9 +702,30 @@ __global__ void k_finalize_t(FinalizeArgs f) {
     if (rho == 2 && wk < 4 && (T & 1u) == 0 && ((dm.x | f.src_stride) & 3u) == 0 && (reinterpret_cast<uintptr_t>(f.src) & 3u) == 0) {
         // The common case (S = 2T, a rotation): a lane takes whole rows of the decimated domain block -- two source rows read as
         // words, two box sums per word pair -- against the range block under the INVERSE rotation (the same pairs as below).
+        // even rotations: the range pixels of a decimated row lie in ONE row of the block (read forwards or backwards) -- words
+        const bool rowwise = (wk & 1) == 0 && (T & 3u) == 0 && ((r.x | f.tgt_stride) & 3u) == 0 && (reinterpret_cast<uintptr_t>(f.tgt) & 3u) == 0;
         for (uint32_t ty = lane; ty < T; ty += LPR) {
             const uint32_t* q0 = reinterpret_cast<const uint32_t*>(f.src + (size_t)(dm.y + 2 * ty) * f.src_stride + dm.x);
             const uint32_t* q1 = reinterpret_cast<const uint32_t*>(f.src + (size_t)(dm.y + 2 * ty + 1) * f.src_stride + dm.x);
+            if (rowwise) {
+                const uint8_t* arow = f.tgt + (size_t)(r.y + (wk == 0 ? ty : T - 1 - ty)) * f.tgt_stride + r.x;
+                for (uint32_t tx = 0; tx < T; tx += 4) {
+                    uint32_t aw = __ldg(reinterpret_cast<const uint32_t*>(arow + (wk == 0 ? tx : T - 4 - tx)));
+                    if (wk == 2) aw = __byte_perm(aw, 0, 0x0123);
+#pragma unroll
+                    for (uint32_t hlf = 0; hlf < 2; ++hlf) {
+                        const uint32_t w0 = __ldg(q0 + tx / 2 + hlf), w1 = __ldg(q1 + tx / 2 + hlf);
+                        const uint32_t dd = (w0 & 0x00FF00FFu) + ((w0 >> 8) & 0x00FF00FFu) + (w1 & 0x00FF00FFu) + ((w1 >> 8) & 0x00FF00FFu);
+#pragma unroll
+                        for (uint32_t j = 0; j < 2; ++j) {
+                            const uint32_t D = j ? dd >> 16 : dd & 0xFFFFu;
+                            const uint32_t a = (aw >> (8 * (2 * hlf + j))) & 255u;
+                            sA += a; sA2 += a * a; sB += D; sAB += a * D; sB2 += D * D;
+                        }
+                    }
+                }
+                continue;
+            }
             for (uint32_t tx = 0; tx < T; tx += 2) {
                 const uint32_t w0 = __ldg(q0 + tx / 2), w1 = __ldg(q1 + tx / 2);
                 const uint32_t dd = (w0 & 0x00FF00FFu) + ((w0 >> 8) & 0x00FF00FFu) + (w1 & 0x00FF00FFu) + ((w1 >> 8) & 0x00FF00FFu);
