@@ -477,7 +477,7 @@ def run_b200(a):
         dms = float(ctx.stats().last_decode_ms) / dec_iters
         dbytes = 2.0 * W * H + 64.0 * len(items_host)       # read plane + write plane + item records per iteration
         decode_info = {"ms_per_iteration": dms, "algorithmic_bytes": dbytes, "achieved_gbs": dbytes / (dms * 1e-3) / 1e9,
-                       "note": "k_decode_step_small<8>/<4> with the convergence sum fused in (+ W*H re-read of the old plane) + k_decode_check per iteration; the planes (2 x 16 MB) and the items (21 MB) stay in L2 at this size, the kernels are bound by L1 wavefronts of the scattered 16-byte source rows (profiles/search_kernels_r2.md)"}
+                       "note": "k_decode_step_small<8>/<4> (gather from the half-resolution box-sum plane the previous iteration wrote, convergence sum fused in: + W*H re-read of the old plane, + W*H/2 box sums written and read) + k_decode_check per iteration; the planes and the items stay in L2 at this size, the kernels are issue-bound (fp64 per pixel, as the reference computes) after the L1 wavefronts were cut (profiles/search_kernels_r2.md)"}
 
         if world == 1 and not a.no_decode_large and W * H < 8192 * 8192:
             # the same at 8192 x 8192, where the two planes (2 x 67 MB) and the items leave the 126 MB L2

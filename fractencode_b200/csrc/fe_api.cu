@@ -147,7 +147,7 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
                       &ctx->b_rowc, &ctx->b_coln, &ctx->b_rowbest, &ctx->b_rowhit, &ctx->b_hist, &ctx->b_level_items, &ctx->b_split,
                       &ctx->b_scan, &ctx->b_scan_tmp, &ctx->b_rng_next, &ctx->b_counters, &ctx->b_A16, &ctx->b_B16, &ctx->b_tmaps,
                       &ctx->b_items, &ctx->b_dec_a, &ctx->b_dec_b, &ctx->b_dec_items, &ctx->b_dec_sum, &ctx->b_q, &ctx->b_bound,
-                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_dom_order2, &ctx->b_rng_order2, &ctx->b_rng2, &ctx->b_pos_of, &ctx->b_lbq, &ctx->b_lbcand, &ctx->b_cells};
+                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_dom_order2, &ctx->b_rng_order2, &ctx->b_rng2, &ctx->b_pos_of, &ctx->b_lbq, &ctx->b_lbcand, &ctx->b_cells, &ctx->b_dq[0], &ctx->b_dq[1]};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
@@ -1133,6 +1133,7 @@ extern "C" int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uin
     grouped.reserve(n);
     std::vector<size_t> goff{0};
     std::vector<char> tiled;       // per size: every item has a 2T source block at a 4-byte aligned origin inside aligned rows
+    bool even_rows = true;         // every item of the fast sizes starts at an even row (its 2 x 2 boxes are its own)
     for (uint32_t T : sizes) {
         bool ok = (stride % 4 == 0) && T <= 32;
         for (size_t i = 0; i < n; ++i)
@@ -1140,6 +1141,7 @@ extern "C" int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uin
                 const fe_encode_item& e = items[i];
                 grouped.push_back(e);
                 ok = ok && e.src_w == 2 * T && e.src_h == 2 * T && e.match_x % 4 == 0 && e.match_y % 2 == 0 && e.x % 4 == 0;
+                even_rows = even_rows && e.y % 2 == 0;
             }
         goff.push_back(grouped.size());
         tiled.push_back(ok ? 1 : 0);
@@ -1199,6 +1201,21 @@ extern "C" int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uin
     const bool fused_sq = covered && n_slow == 0;                          // convergence sum inside the gather kernel
     uint8_t* buf[2] = {ctx->b_dec_a.as<uint8_t>(), ctx->b_dec_b.as<uint8_t>()};
     FE_CUDA(ctx, cudaMemsetAsync(buf[0], 100, bytes, ctx->stream)); // Encoder2.hpp:69
+    // The encoder's own lists (4- and 8-pixel blocks on the lattice, tiling the plane): the iterate carries its half-resolution
+    // plane of 2 x 2 box sums, the gather reads those (k_decode_step_small<.., DQ>)
+    bool with_dq = fused_sq && even_rows && width % 4 == 0 && height % 2 == 0 && !getenv("FE_NO_DQ");
+    for (size_t gidx = 0; gidx < sizes.size(); ++gidx) with_dq = with_dq && tiled[gidx] && (sizes[gidx] == 4 || sizes[gidx] == 8);
+    uint16_t* dq[2] = {nullptr, nullptr};
+    const uint32_t dq_stride = width / 2;
+    if (with_dq) {
+        const size_t qn = (size_t)(width / 2) * (height / 2);
+        FE_CUDA(ctx, ctx->b_dq[0].ensure(qn * 2 + 64));
+        FE_CUDA(ctx, ctx->b_dq[1].ensure(qn * 2 + 64));
+        dq[0] = ctx->b_dq[0].as<uint16_t>(); dq[1] = ctx->b_dq[1].as<uint16_t>();
+        launch_boxsum_plane(ctx->stream, buf[0], stride, width, height, dq[0]);
+        ctx->stats.kernel_launches++;
+        FE_CUDA(ctx, cudaGetLastError());
+    }
     FE_CUDA(ctx, cudaMemcpy2DAsync(buf[1], stride, target, stride, width, height, cudaMemcpyHostToDevice, ctx->stream));
     cudaEventRecord(ctx->ev[0], ctx->stream);
     // ---- the iteration train: BATCH iterations per host look; once `done` is up the rest of a batch are no-ops ----
@@ -1215,7 +1232,8 @@ extern "C" int fe_decode(fe_ctx* ctx, const fe_encode_item* items, size_t n, uin
                 const size_t cnt = goff[gidx + 1] - goff[gidx];
                 if (!cnt) continue;
                 if (tiled[gidx]) {
-                    if (!launch_decode_step_small(ctx->stream, src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T, use_fma, fused_sq ? d_sum : nullptr, d_state))
+                    if (!launch_decode_step_small(ctx->stream, src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T, use_fma, fused_sq ? d_sum : nullptr, d_state,
+                                                  with_dq ? dq[i & 1] : nullptr, with_dq ? dq[(i + 1) & 1] : nullptr, dq_stride))
                         k_decode_step_tiled<<<cdiv(cnt, 8), 256, 8 * T * T * sizeof(uint16_t), ctx->stream>>>(src, dst, stride, d_items + goff[gidx], (uint32_t)cnt, T,
                                                                                                             use_fma, fused_sq ? d_sum : nullptr, d_state);
                     ctx->stats.kernel_launches++;

@@ -93,7 +93,7 @@ struct fe_ctx {
     // flip isometries: the doubled range list and the position of every copy after bucketing
     DevBuf b_rng2, b_pos_of;
     // lower-bound prefilter: cell-sum plane, candidate list (+ its counter)
-    DevBuf b_lbq, b_lbcand, b_cells;
+    DevBuf b_lbq, b_lbcand, b_cells, b_dq[2];
     // tcgen05 path operands
     DevBuf b_A16, b_B16, b_tmaps, b_blob_dom, b_tileseg;
     // device-scheduled levels (fe_plan.cuh): plan, slice state, the two lists of open range blocks, work items, bucket of every

@@ -964,19 +964,28 @@ __global__ void __launch_bounds__(256) k_decode_step_tiled(const uint8_t* __rest
     }
 }
 
-// Same gather for the small blocks (T = 4: eight items per warp, T = 8: four): a warp per item leaves most lanes idle there and
+// Same gather for the small blocks (T = 4, T = 8: eight items per warp): a warp per item leaves most lanes idle there and
 // chains item load -> source loads -> store once per item; here a warp fetches IPW item records with one coalesced read,
 // issues all its source loads before it touches any of them, and every lane has output work.
-template <int T, int IPW>
+// DQ: the iterate travels with its half-resolution plane of 2 x 2 box sums (u16).  The gather reads the T x T box sums of an
+// item's source block from that plane (T rows of 2 T bytes instead of 2 T rows of 2 T bytes: half the lines), and writes the
+// box sums of its own output next to the pixels for the next iteration (items sit at even origins, so a box never straddles two).
+template <int T, int IPW, bool DQ>
 __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t stride,
                                                            const fe_encode_item* __restrict__ items, uint32_t n_items, int use_fma,
-                                                           unsigned long long* __restrict__ sq_out, const uint32_t* __restrict__ done) {
+                                                           unsigned long long* __restrict__ sq_out, const uint32_t* __restrict__ done,
+                                                           const uint16_t* __restrict__ dq_src, uint16_t* __restrict__ dq_dst, uint32_t dq_stride) {
     if (done && *done) return;            // the iteration already converged: every later launch is a no-op
-    constexpr int N = T * T, S = 2 * T, WPR = S / 4, UNITS = T * WPR;       // row-pair words per item
+    constexpr int N = T * T, S = 2 * T, WPR = S / 4, UNITS = DQ ? T * (T / 2) : T * WPR;   // words (DQ) / row-pair words per item
     constexpr int U = (IPW * UNITS + 31) / 32;                                // load units per lane
     constexpr int SEGS = T / 4, OUT = T * SEGS, Q = (IPW * OUT + 31) / 32;    // 4-pixel output segments per item / per lane
     __shared__ __align__(16) fe_encode_item sitem[8][IPW];
-    __shared__ __align__(16) uint16_t sbox[8][IPW][N];
+    // Box sums of the warp's items.  The lanes of an output instruction are (rows) x (items) x (segments): the items' slots are
+    // skewed so that an identity-oriented read of one instruction falls into 32 different banks (T = 8: slot k starts at word
+    // 32 k + 8 (k / 2) + k % 2; T = 4: 8 k + k / 4).
+    auto box_of = [](uint16_t* base, uint32_t k) { return base + 2 * (T == 8 ? 32 * k + 8 * (k >> 1) + (k & 1u) : (N / 2) * k + (k >> 2)); };
+    constexpr int WARP_U16 = 2 * (T == 8 ? 32 * (IPW - 1) + 8 * ((IPW - 1) >> 1) + 1 + 32 : (N / 2) * IPW + (IPW >> 2) + 1);
+    __shared__ __align__(16) uint16_t sbox_raw[8][(WARP_U16 + 7) & ~7];
     const uint32_t warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t first = (blockIdx.x * 8 + warp_in_block) * IPW;
     unsigned long long sq = 0;
@@ -987,57 +996,85 @@ __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __rest
             reinterpret_cast<uint4*>(&sitem[warp_in_block][0])[q] = __ldg(reinterpret_cast<const uint4*>(items + first) + q);
         __syncwarp();
         // all source loads first, then the box sums
-        uint32_t r0[U], r1[U];
+        uint32_t r0[U], r1[DQ ? 1 : U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t idx = lane + 32 * u, k = idx / UNITS, w = idx % UNITS;
-            r0[u] = r1[u] = 0;
+            r0[u] = 0;
+            if (!DQ) r1[u] = 0;
             if (k < cnt) {
                 const fe_encode_item& e = sitem[warp_in_block][k];
-                const uint8_t* p = src + (size_t)(e.match_y + 2 * (w / WPR)) * stride + e.match_x + 4 * (w % WPR);
-                r0[u] = __ldg(reinterpret_cast<const uint32_t*>(p));
-                r1[u] = __ldg(reinterpret_cast<const uint32_t*>(p + stride));
+                if (DQ) {
+                    r0[u] = __ldg(reinterpret_cast<const uint32_t*>(dq_src + (size_t)(e.match_y / 2 + w / (T / 2)) * dq_stride + e.match_x / 2) + w % (T / 2));
+                } else {
+                    const uint8_t* p = src + (size_t)(e.match_y + 2 * (w / WPR)) * stride + e.match_x + 4 * (w % WPR);
+                    r0[u] = __ldg(reinterpret_cast<const uint32_t*>(p));
+                    r1[u] = __ldg(reinterpret_cast<const uint32_t*>(p + stride));
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t idx = lane + 32 * u, k = idx / UNITS, w = idx % UNITS;
             if (k < cnt) {
-                const uint32_t dd = (r0[u] & 0x00FF00FFu) + ((r0[u] >> 8) & 0x00FF00FFu) + (r1[u] & 0x00FF00FFu) + ((r1[u] >> 8) & 0x00FF00FFu);
-                *reinterpret_cast<uint32_t*>(&sbox[warp_in_block][k][(w / WPR) * T + 2 * (w % WPR)]) = dd;
+                if (DQ) {
+                    *reinterpret_cast<uint32_t*>(box_of(sbox_raw[warp_in_block], k) + (w / (T / 2)) * T + 2 * (w % (T / 2))) = r0[u];
+                } else {
+                    const uint32_t dd = (r0[u] & 0x00FF00FFu) + ((r0[u] >> 8) & 0x00FF00FFu) + (r1[u] & 0x00FF00FFu) + ((r1[u] >> 8) & 0x00FF00FFu);
+                    *reinterpret_cast<uint32_t*>(box_of(sbox_raw[warp_in_block], k) + (w / WPR) * T + 2 * (w % WPR)) = dd;
+                }
             }
         }
         __syncwarp();
+        // Lanes run along an output row ACROSS the warp's items: consecutive items of a level list are neighbours in the plane
+        // (Z-order), so the segments of a row that lie side by side share a sector for the store and the old-value read.  A lane
+        // keeps its (item, segment) for all its rows: the item's fields are read once.
+        static_assert(32 % (IPW * SEGS) == 0 && (IPW * OUT) % 32 == 0, "rows of the warp's items per instruction");
+        constexpr uint32_t LPRW = IPW * SEGS, RPI = 32 / LPRW;       // lanes per output row of the warp, rows per instruction
+        static_assert(RPI % 2 == 0, "a lane and its box partner (the next row) sit in the same instruction");
+        const uint32_t k = (lane % LPRW) / SEGS, x0 = (lane % SEGS) * 4;
+        const bool live = k < cnt;
+        const fe_encode_item& e = sitem[warp_in_block][live ? k : 0];
+        const uint16_t* box = box_of(sbox_raw[warp_in_block], live ? k : 0);
+        const int t = e.transform;
+        const int m0 = kMapDev[t][0], m1 = kMapDev[t][1], m4 = kMapDev[t][4], m5 = kMapDev[t][5];
+        const int cx = (kMapDev[t][2] + kMapDev[t][3]) * (S - 1), cy = (kMapDev[t][6] + kMapDev[t][7]) * (S - 1);
+        const int ax = (m0 + m1) < 0 ? -1 : 0, ay = (m4 + m5) < 0 ? -1 : 0;     // min corner of the mapped 2x2 box
+        const double cs = e.contrast, br = e.brightness;
+        const uint32_t ex = e.x, ey = e.y;
 #pragma unroll
         for (int qq = 0; qq < Q; ++qq) {
-            const uint32_t idx = lane + 32 * qq, k = idx / OUT, q = idx % OUT;
-            if (k >= cnt) continue;
-            const fe_encode_item& e = sitem[warp_in_block][k];
-            const uint16_t* box = sbox[warp_in_block][k];
-            const int t = e.transform;
-            const int m0 = kMapDev[t][0], m1 = kMapDev[t][1], m4 = kMapDev[t][4], m5 = kMapDev[t][5];
-            const int cx = (kMapDev[t][2] + kMapDev[t][3]) * (S - 1), cy = (kMapDev[t][6] + kMapDev[t][7]) * (S - 1);
-            const int ax = (m0 + m1) < 0 ? -1 : 0, ay = (m4 + m5) < 0 ? -1 : 0;     // min corner of the mapped 2x2 box
-            const uint32_t y = q / SEGS, x0 = (q % SEGS) * 4;
-            const double cs = e.contrast, br = e.brightness;
+            const uint32_t y = lane / LPRW + qq * RPI;
             uint32_t packed = 0;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int lx = 2 * (int)(x0 + kk), ly = 2 * (int)y;
-                const int gx = m0 * lx + m1 * ly + cx + ax, gy = m4 * lx + m5 * ly + cy + ay;
-                const double smp = (double)box[(gy >> 1) * T + (gx >> 1)] * 0.25;
-                const double v = use_fma ? __fma_rn(cs, smp, br) : __dadd_rn(__dmul_rn(cs, smp), br);
-                const uint32_t b = v < 0.0 ? 0u : (v > 255.0 ? 255u : (uint32_t)(uint8_t)v);
-                packed |= b << (8 * kk);
-            }
-            const size_t off = (size_t)(e.y + y) * stride + e.x + x0;
-            *reinterpret_cast<uint32_t*>(dst + off) = packed;
-            if (sq_out) {
-                const uint32_t old = __ldg(reinterpret_cast<const uint32_t*>(src + off));
+            if (live) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    const int d = (int)((old >> (8 * kk)) & 255u) - (int)((packed >> (8 * kk)) & 255u);
-                    sq += (unsigned long long)(d * d);
+                    const int lx = 2 * (int)(x0 + kk), ly = 2 * (int)y;
+                    const int gx = m0 * lx + m1 * ly + cx + ax, gy = m4 * lx + m5 * ly + cy + ay;
+                    const double smp = (double)box[(gy >> 1) * T + (gx >> 1)] * 0.25;
+                    const double v = use_fma ? __fma_rn(cs, smp, br) : __dadd_rn(__dmul_rn(cs, smp), br);
+                    const uint32_t b = v < 0.0 ? 0u : (v > 255.0 ? 255u : (uint32_t)(uint8_t)v);
+                    packed |= b << (8 * kk);
+                }
+            }
+            if (DQ) {   // box sums of the output: this row and the next one (lane ^ LPRW), even rows write
+                const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, packed, LPRW);
+                if (live && (y & 1u) == 0) {
+                    const uint32_t lo = __dp4a(packed, 0x00000101u, __dp4a(other, 0x00000101u, 0u));
+                    const uint32_t hi = __dp4a(packed, 0x01010000u, __dp4a(other, 0x01010000u, 0u));
+                    *reinterpret_cast<uint32_t*>(dq_dst + (size_t)((ey + y) / 2) * dq_stride + (ex + x0) / 2) = lo | (hi << 16);
+                }
+            }
+            if (live) {
+                const size_t off = (size_t)(ey + y) * stride + ex + x0;
+                *reinterpret_cast<uint32_t*>(dst + off) = packed;
+                if (sq_out) {
+                    const uint32_t old = __ldg(reinterpret_cast<const uint32_t*>(src + off));
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int d = (int)((old >> (8 * kk)) & 255u) - (int)((packed >> (8 * kk)) & 255u);
+                        sq += (unsigned long long)(d * d);
+                    }
                 }
             }
         }
@@ -1056,11 +1093,28 @@ __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __rest
 }
 
 bool launch_decode_step_small(cudaStream_t stream, const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items, uint32_t n,
-                              uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done) {
-    if (T == 4) k_decode_step_small<4, 8><<<(n + 63) / 64, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done);
-    else if (T == 8) k_decode_step_small<8, 8><<<(n + 63) / 64, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done);
+                              uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done, const uint16_t* dq_src, uint16_t* dq_dst,
+                              uint32_t dq_stride) {
+    const unsigned grid = (n + 63) / 64;
+    if (T == 4 && dq_src) k_decode_step_small<4, 8, true><<<grid, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done, dq_src, dq_dst, dq_stride);
+    else if (T == 8 && dq_src) k_decode_step_small<8, 8, true><<<grid, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done, dq_src, dq_dst, dq_stride);
+    else if (T == 4) k_decode_step_small<4, 8, false><<<grid, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done, nullptr, nullptr, 0);
+    else if (T == 8) k_decode_step_small<8, 8, false><<<grid, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done, nullptr, nullptr, 0);
     else return false;
     return true;
+}
+// box-sum plane of a u8 plane (first iterate of a decode that carries one)
+__global__ void k_boxsum_plane(const uint8_t* __restrict__ src, uint32_t stride, uint32_t qw, uint32_t qh, uint16_t* __restrict__ dq) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;    // x: pairs of boxes
+    if (2 * x >= qw || y >= qh) return;
+    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(src + (size_t)(2 * y) * stride + 4 * x);
+    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(src + (size_t)(2 * y + 1) * stride + 4 * x);
+    const uint32_t lo = __dp4a(w0, 0x00000101u, __dp4a(w1, 0x00000101u, 0u)), hi = __dp4a(w0, 0x01010000u, __dp4a(w1, 0x01010000u, 0u));
+    *reinterpret_cast<uint32_t*>(dq + (size_t)y * qw + 2 * x) = lo | (hi << 16);
+}
+void launch_boxsum_plane(cudaStream_t stream, const uint8_t* src, uint32_t stride, uint32_t w, uint32_t h, uint16_t* dq) {
+    const uint32_t qw = w / 2, qh = h / 2;
+    k_boxsum_plane<<<dim3((qw / 2 + 31) / 32, (qh + 7) / 8), dim3(32, 8), 0, stream>>>(src, stride, qw, qh, dq);
 }
 
 // Coverage proof for the ping-pong decode: every pixel must be written by exactly one item.  One thread per (item, row):

@@ -60,7 +60,9 @@ __global__ void k_decode_step(const uint8_t* src, uint8_t* dst, uint32_t stride,
 __global__ void k_decode_step_uniform(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items,
                                       uint32_t n_items, uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done);
 bool launch_decode_step_small(cudaStream_t stream, const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items, uint32_t n,
-                              uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done);
+                              uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done, const uint16_t* dq_src, uint16_t* dq_dst,
+                              uint32_t dq_stride);
+void launch_boxsum_plane(cudaStream_t stream, const uint8_t* src, uint32_t stride, uint32_t w, uint32_t h, uint16_t* dq);
 __global__ void k_decode_step_tiled(const uint8_t* src, uint8_t* dst, uint32_t stride, const fe_encode_item* items, uint32_t n_items,
                                     uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done);
 __global__ void k_sqdiff(const uint8_t* a, const uint8_t* b, uint32_t w, uint32_t h, uint32_t stride, unsigned long long* out, const uint32_t* done);
