@@ -107,6 +107,42 @@ def test_decode_converges_on_the_same_iteration_as_the_reference(ctx, fo, lenna)
         assert ia == ib and ra == rb and (a == b).all(), iters
 
 
+def test_decode_box_sum_plane_path_equals_plain_path_and_oracle(ctx, fo):
+    """Lists of 4- and 8-pixel lattice blocks decode through the half-resolution box-sum plane (k_decode_step_small<.., DQ>);
+    FE_NO_DQ=1 takes the pixel gather.  Same image, iteration count and rms either way and as the oracle -- with and without
+    FMA, on a padded stride, for a list that also holds 16-pixel blocks (plane not used) and after a non-tiling call."""
+    import fractencode_b200 as fb
+    W, H = 384, 256
+    ctx.set_synthetic_image(W, H, 4242, 0)
+    img = ctx.get_image()
+    for tmax in (8, 16):
+        for thr in (25.0, 60.0, 120.0, 250.0):       # the first threshold that leaves both 8- and 4-pixel blocks
+            items, counts = ctx.encode_quadtree(tmax, 4, fb.Params(thr))
+            if counts[-1] > 0 and counts[-2] > 0:
+                break
+        assert counts[-1] > 0 and counts[-2] > 0, counts
+        for fma in (False, True):
+            for iters, eps in ((1, -1.0), (2, -1.0), (9, -1.0), (-1, 1e-5)):
+                want, iw, rw = fo.decode(items, W, H, max_iters=iters, eps=eps, fma=fma)
+                got = {}
+                for name, env in (("dq", None), ("plain", "1")):
+                    old = os.environ.pop("FE_NO_DQ", None)
+                    if env:
+                        os.environ["FE_NO_DQ"] = env
+                    try:
+                        got[name] = ctx.decode(items, W, H, max_iters=iters, eps=eps, fma=fma)
+                    finally:
+                        os.environ.pop("FE_NO_DQ", None)
+                        if old is not None:
+                            os.environ["FE_NO_DQ"] = old
+                for name, (a, ia, ra) in got.items():
+                    assert ia == iw and ra == rw and (a == want).all(), (tmax, fma, iters, name, ia, iw)
+        a, ia, ra = ctx.decode(items, W, H, stride=W + 36, max_iters=3, eps=-1.0, init=9)
+        b, ib, rb = fo.decode(items, W, H, stride=W + 36, max_iters=3, eps=-1.0, init=9)
+        assert ia == ib and ra == rb and (a == b).all(), "padded stride"
+    del img
+
+
 def test_slice_hints_and_continuation(fo):
     """The number of slices a level gets enqueued up front comes from the previous level of its kind; a level that needs
     more is continued after its synchronisation.  Results never depend on what ran before on the context."""
