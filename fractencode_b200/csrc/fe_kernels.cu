@@ -1038,23 +1038,27 @@ __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __rest
         const uint16_t* box = box_of(sbox_raw[warp_in_block], live ? k : 0);
         const int t = e.transform;
         const int m0 = kMapDev[t][0], m1 = kMapDev[t][1], m4 = kMapDev[t][4], m5 = kMapDev[t][5];
-        const int cx = (kMapDev[t][2] + kMapDev[t][3]) * (S - 1), cy = (kMapDev[t][6] + kMapDev[t][7]) * (S - 1);
-        const int ax = (m0 + m1) < 0 ? -1 : 0, ay = (m4 + m5) < 0 ? -1 : 0;     // min corner of the mapped 2x2 box
-        const double cs = e.contrast, br = e.brightness;
+        // Box of output pixel (x, y): the mapped 2 x 2 source box has its min corner at the even position
+        // (2 (m0 x + m1 y) + cx + ax, ...) with cx + ax in {0, S - 2}: box index = base0 + y * sy + kk * sk, all per lane.
+        const int cxh = (((kMapDev[t][2] + kMapDev[t][3]) * (S - 1)) + ((m0 + m1) < 0 ? -1 : 0)) >> 1;
+        const int cyh = (((kMapDev[t][6] + kMapDev[t][7]) * (S - 1)) + ((m4 + m5) < 0 ? -1 : 0)) >> 1;
+        const int base0 = (m4 * (int)x0 + cyh) * T + m0 * (int)x0 + cxh, sy = m5 * T + m1, sk = m4 * T + m0;
+        // s * (D / 4) + o: the scaling by a power of two commutes with the rounding of the product, so (s / 4) * D is the same double
+        const double cs4 = e.contrast * 0.25, br = e.brightness;
         const uint32_t ex = e.x, ey = e.y;
+        uint32_t sq32 = 0;                         // <= 16 pixels x 255^2 per lane
 #pragma unroll
         for (int qq = 0; qq < Q; ++qq) {
             const uint32_t y = lane / LPRW + qq * RPI;
             uint32_t packed = 0;
             if (live) {
+                const uint16_t* bp = box + base0 + (int)y * sy;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    const int lx = 2 * (int)(x0 + kk), ly = 2 * (int)y;
-                    const int gx = m0 * lx + m1 * ly + cx + ax, gy = m4 * lx + m5 * ly + cy + ay;
-                    const double smp = (double)box[(gy >> 1) * T + (gx >> 1)] * 0.25;
-                    const double v = use_fma ? __fma_rn(cs, smp, br) : __dadd_rn(__dmul_rn(cs, smp), br);
-                    const uint32_t b = v < 0.0 ? 0u : (v > 255.0 ? 255u : (uint32_t)(uint8_t)v);
-                    packed |= b << (8 * kk);
+                    const double D = (double)(uint32_t)bp[kk * sk];
+                    const double v = use_fma ? __fma_rn(cs4, D, br) : __dadd_rn(__dmul_rn(cs4, D), br);
+                    // v < 0 -> 0, v > 255 -> 255, else truncation (DecodeUtils.hpp:19-22): the saturating conversion and a minimum
+                    packed |= min(__double2uint_rz(v), 255u) << (8 * kk);
                 }
             }
             if (DQ) {   // box sums of the output: this row and the next one (lane ^ LPRW), even rows write
@@ -1069,15 +1073,12 @@ __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __rest
                 const size_t off = (size_t)(ey + y) * stride + ex + x0;
                 *reinterpret_cast<uint32_t*>(dst + off) = packed;
                 if (sq_out) {
-                    const uint32_t old = __ldg(reinterpret_cast<const uint32_t*>(src + off));
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const int d = (int)((old >> (8 * kk)) & 255u) - (int)((packed >> (8 * kk)) & 255u);
-                        sq += (unsigned long long)(d * d);
-                    }
+                    const uint32_t ad = __vabsdiffu4(__ldg(reinterpret_cast<const uint32_t*>(src + off)), packed);
+                    sq32 = __dp4a(ad, ad, sq32);
                 }
             }
         }
+        sq = sq32;
     }
     if (sq_out) { // one atomic per block, spread over 64 slots
         __shared__ unsigned long long wsum[8];
