@@ -970,16 +970,18 @@ __global__ void __launch_bounds__(256) k_decode_step_tiled(const uint8_t* __rest
 // DQ: the iterate travels with its half-resolution plane of 2 x 2 box sums (u16).  The gather reads the T x T box sums of an
 // item's source block from that plane (T rows of 2 T bytes instead of 2 T rows of 2 T bytes: half the lines), and writes the
 // box sums of its own output next to the pixels for the next iteration (items sit at even origins, so a box never straddles two).
-template <int T, int IPW, bool DQ>
+template <int T, int IPW, bool DQ, bool FMA>
 __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t stride,
-                                                           const fe_encode_item* __restrict__ items, uint32_t n_items, int use_fma,
+                                                           const fe_encode_item* __restrict__ items, uint32_t n_items,
                                                            unsigned long long* __restrict__ sq_out, const uint32_t* __restrict__ done,
                                                            const uint16_t* __restrict__ dq_src, uint16_t* __restrict__ dq_dst, uint32_t dq_stride) {
     if (done && *done) return;            // the iteration already converged: every later launch is a no-op
     constexpr int N = T * T, S = 2 * T, WPR = S / 4, UNITS = DQ ? T * (T / 2) : T * WPR;   // words (DQ) / row-pair words per item
     constexpr int U = (IPW * UNITS + 31) / 32;                                // load units per lane
     constexpr int SEGS = T / 4, OUT = T * SEGS, Q = (IPW * OUT + 31) / 32;    // 4-pixel output segments per item / per lane
-    __shared__ __align__(16) fe_encode_item sitem[8][IPW];
+    // item records, 80 bytes apart: the lanes of an output instruction read the same field of eight different records
+    __shared__ uint4 sitem_raw[8][IPW * 5];
+    auto item_of = [&](uint32_t w, uint32_t k) -> const fe_encode_item& { return *reinterpret_cast<const fe_encode_item*>(&sitem_raw[w][5 * k]); };
     // Box sums of the warp's items.  The lanes of an output instruction are (rows) x (items) x (segments): the items' slots are
     // skewed so that an identity-oriented read of one instruction falls into 32 different banks (T = 8: slot k starts at word
     // 32 k + 8 (k / 2) + k % 2; T = 4: 8 k + k / 4).
@@ -993,7 +995,7 @@ __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __rest
         const uint32_t cnt = min((uint32_t)IPW, n_items - first);
         // item records: 4 x 16 bytes each, one coalesced read
         for (uint32_t q = lane; q < cnt * 4; q += 32)
-            reinterpret_cast<uint4*>(&sitem[warp_in_block][0])[q] = __ldg(reinterpret_cast<const uint4*>(items + first) + q);
+            sitem_raw[warp_in_block][5 * (q >> 2) + (q & 3u)] = __ldg(reinterpret_cast<const uint4*>(items + first) + q);
         __syncwarp();
         // all source loads first, then the box sums
         uint32_t r0[U], r1[DQ ? 1 : U];
@@ -1003,7 +1005,7 @@ __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __rest
             r0[u] = 0;
             if (!DQ) r1[u] = 0;
             if (k < cnt) {
-                const fe_encode_item& e = sitem[warp_in_block][k];
+                const fe_encode_item& e = item_of(warp_in_block, k);
                 if (DQ) {
                     r0[u] = __ldg(reinterpret_cast<const uint32_t*>(dq_src + (size_t)(e.match_y / 2 + w / (T / 2)) * dq_stride + e.match_x / 2) + w % (T / 2));
                 } else {
@@ -1034,14 +1036,16 @@ __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __rest
         static_assert(RPI % 2 == 0, "a lane and its box partner (the next row) sit in the same instruction");
         const uint32_t k = (lane % LPRW) / SEGS, x0 = (lane % SEGS) * 4;
         const bool live = k < cnt;
-        const fe_encode_item& e = sitem[warp_in_block][live ? k : 0];
+        const fe_encode_item& e = item_of(warp_in_block, live ? k : 0);
         const uint16_t* box = box_of(sbox_raw[warp_in_block], live ? k : 0);
-        const int t = e.transform;
-        const int m0 = kMapDev[t][0], m1 = kMapDev[t][1], m4 = kMapDev[t][4], m5 = kMapDev[t][5];
+        // rows of kMapDev as bit fields (m + 1, two bits each: m0, m1, m4, m5), one byte per isometry: the lanes of a warp hold
+        // different isometries, and a constant-bank read with a divergent index is replayed once per distinct value
+        const uint32_t code = (uint32_t)(0x4194691661144996ull >> (8 * (e.transform & 7))) & 0xFFu;
+        const int m0 = (int)(code & 3u) - 1, m1 = (int)((code >> 2) & 3u) - 1, m4 = (int)((code >> 4) & 3u) - 1, m5 = (int)(code >> 6) - 1;
         // Box of output pixel (x, y): the mapped 2 x 2 source box has its min corner at the even position
-        // (2 (m0 x + m1 y) + cx + ax, ...) with cx + ax in {0, S - 2}: box index = base0 + y * sy + kk * sk, all per lane.
-        const int cxh = (((kMapDev[t][2] + kMapDev[t][3]) * (S - 1)) + ((m0 + m1) < 0 ? -1 : 0)) >> 1;
-        const int cyh = (((kMapDev[t][6] + kMapDev[t][7]) * (S - 1)) + ((m4 + m5) < 0 ? -1 : 0)) >> 1;
+        // (2 (m0 x + m1 y) + cx + ax, ...) with cx + ax = S - 2 where the coefficients sum to -1, else 0 (transform.h:32-41):
+        // box index = base0 + y * sy + kk * sk, all per lane.
+        const int cxh = (m0 + m1) < 0 ? T - 1 : 0, cyh = (m4 + m5) < 0 ? T - 1 : 0;
         const int base0 = (m4 * (int)x0 + cyh) * T + m0 * (int)x0 + cxh, sy = m5 * T + m1, sk = m4 * T + m0;
         // s * (D / 4) + o: the scaling by a power of two commutes with the rounding of the product, so (s / 4) * D is the same double
         const double cs4 = e.contrast * 0.25, br = e.brightness;
@@ -1056,7 +1060,7 @@ __global__ void __launch_bounds__(256) k_decode_step_small(const uint8_t* __rest
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     const double D = (double)(uint32_t)bp[kk * sk];
-                    const double v = use_fma ? __fma_rn(cs4, D, br) : __dadd_rn(__dmul_rn(cs4, D), br);
+                    const double v = FMA ? __fma_rn(cs4, D, br) : __dadd_rn(__dmul_rn(cs4, D), br);
                     // v < 0 -> 0, v > 255 -> 255, else truncation (DecodeUtils.hpp:19-22): the saturating conversion and a minimum
                     packed |= min(__double2uint_rz(v), 255u) << (8 * kk);
                 }
@@ -1097,11 +1101,21 @@ bool launch_decode_step_small(cudaStream_t stream, const uint8_t* src, uint8_t* 
                               uint32_t T, int use_fma, unsigned long long* sq_out, const uint32_t* done, const uint16_t* dq_src, uint16_t* dq_dst,
                               uint32_t dq_stride) {
     const unsigned grid = (n + 63) / 64;
-    if (T == 4 && dq_src) k_decode_step_small<4, 8, true><<<grid, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done, dq_src, dq_dst, dq_stride);
-    else if (T == 8 && dq_src) k_decode_step_small<8, 8, true><<<grid, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done, dq_src, dq_dst, dq_stride);
-    else if (T == 4) k_decode_step_small<4, 8, false><<<grid, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done, nullptr, nullptr, 0);
-    else if (T == 8) k_decode_step_small<8, 8, false><<<grid, 256, 0, stream>>>(src, dst, stride, items, n, use_fma, sq_out, done, nullptr, nullptr, 0);
-    else return false;
+    if (T != 4 && T != 8) return false;
+#define DEC_SMALL(TT, DQ_, FMA_) \
+    k_decode_step_small<TT, 8, DQ_, FMA_><<<grid, 256, 0, stream>>>(src, dst, stride, items, n, sq_out, done, dq_src, dq_dst, dq_stride)
+    const int sel = (T == 8 ? 4 : 0) | (dq_src ? 2 : 0) | (use_fma ? 1 : 0);
+    switch (sel) {
+    case 0: DEC_SMALL(4, false, false); break;
+    case 1: DEC_SMALL(4, false, true); break;
+    case 2: DEC_SMALL(4, true, false); break;
+    case 3: DEC_SMALL(4, true, true); break;
+    case 4: DEC_SMALL(8, false, false); break;
+    case 5: DEC_SMALL(8, false, true); break;
+    case 6: DEC_SMALL(8, true, false); break;
+    default: DEC_SMALL(8, true, true); break;
+    }
+#undef DEC_SMALL
     return true;
 }
 // box-sum plane of a u8 plane (first iterate of a decode that carries one)
