@@ -558,6 +558,7 @@ static int run_level_enqueue(fe_ctx* ctx, const LevelIO& io, const fe_params& p,
             lp->kind = 2;
     }
     if (lp->timed) cudaEventRecord(ctx->ev[0], ctx->stream);
+    ctx->level_host_t0 = std::chrono::steady_clock::now();
     FE_CUDA(ctx, ctx->b_counters.ensure(16 * sizeof(uint32_t)));
     FE_CUDA(ctx, cudaMemsetAsync(ctx->b_counters.p, 0, 16 * sizeof(uint32_t), ctx->stream));
     // flip isometries: every range block is searched twice, the second copy mirrored left-right (its four rotation rows are
@@ -705,6 +706,10 @@ static int run_level_complete(fe_ctx* ctx, const LevelIO& io, const fe_params& p
             if (getenv("FE_PASS_TIMES")) fprintf(stderr, "[level] T=%u search launch %u: %.3f ms\n", g.T, i, ms);
         }
         float ms = 0;
+        if (getenv("FE_PASS_TIMES") && lp->st.n_launches) {       // device time from the level's first launch to its first search launch
+            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev_pass[0]);
+            fprintf(stderr, "[level] T=%u device time before the first search launch %.1f us (host: %.1f us)\n", g.T, ms * 1e3, lp->st.host_us_first_search);
+        }
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]);
         ctx->stats.level_search_ms[io.stat_level] = kernel_ms;
         ctx->stats.level_prep_ms[io.stat_level] = ms - kernel_ms;

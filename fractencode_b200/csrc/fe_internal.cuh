@@ -1,5 +1,6 @@
 // fe_internal.cuh -- shared declarations of the B200 fractal-search library (not part of the C ABI).
 #pragma once
+#include <chrono>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -94,6 +95,7 @@ struct fe_ctx {
     DevBuf b_rng2, b_pos_of;
     // lower-bound prefilter: cell-sum plane, candidate list (+ its counter)
     DevBuf b_lbq, b_lbcand, b_cells, b_dq[2];
+    std::chrono::steady_clock::time_point level_host_t0;   // FE_PASS_TIMES: host clock at the level's first launch
     // tcgen05 path operands
     DevBuf b_A16, b_B16, b_tmaps, b_blob_dom, b_tileseg;
     // device-scheduled levels (fe_plan.cuh): plan, slice state, the two lists of open range blocks, work items, bucket of every

@@ -1,5 +1,6 @@
 // fe_plan.cu -- device-side planning of a search level (see fe_plan.cuh): bucket layout, slice schedule, survivor
 // compaction and work-item expansion, all from device memory; and the host code that enqueues one level.
+#include <chrono>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -467,6 +468,7 @@ static int enqueue_slice(fe_ctx* ctx, DeviceLevelState* st, int phase, uint32_t 
     PLAUNCH(ctx, k_slice_plan, cdiv_u(st->nR, 256), 256, pa, phase, ordinal);
     PLAUNCH(ctx, k_expand_items, 2 * ctx->n_sm, 256, pa, ordinal);
     cudaEvent_t e0 = st->timed ? ctx->ev_pass[2 * st->n_launches] : nullptr, e1 = st->timed ? ctx->ev_pass[2 * st->n_launches + 1] : nullptr;
+    if (st->n_launches == 0) st->host_us_first_search = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - ctx->level_host_t0).count();
     if (st->kind == 0) {
         st->fa.ordinal = ordinal;
         FE_TRY(f16_launch_search(ctx, g, st->fa, st->retire, meta, e0, e1));

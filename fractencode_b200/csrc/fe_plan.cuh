@@ -207,6 +207,7 @@ struct DeviceLevelState {
     bool bins = false;                    // brightness bins are on (inside the classes when there are classes)
     uint32_t nbins = 1, span = 0, ngroups = 1;
     uint32_t n_launches = 0;              // search launches enqueued (events ctx->ev_pass[2 i], [2 i + 1] when timed)
+    double host_us_first_search = 0;      // FE_PASS_TIMES: host time from the level's first launch to its first search launch
     const uint32_t* dom_order = nullptr;  // sorted position -> domain index (NULL: identity)
     const uint32_t* rng_order = nullptr;  // level position -> range index (NULL: identity)
     // continuation
