@@ -62,9 +62,13 @@ __device__ __forceinline__ V block_excl_scan(V v, V* sh, V* total) {
 // histogram in shared memory first: a few dozen hot global addresses would serialise the whole grid).
 // Both lists in one go (positions 0..nD-1 the domains, nD.. the range blocks; bins likewise): the range keys carry `list_bit`, so
 // ONE stable radix sort orders both lists, and vals = the index inside the own list.  hist_d / hist_r as before.
+// cells != NULL (lattice levels, one image): the brightness bin is computed here from the level's cell sums -- a domain is the
+// 2 x 2 cells at (i % dnx, i / dnx), a range block the cell at its origin (sum of 4 r = 4 x the cell) -- bin_width = the bin width.
 __global__ void __launch_bounds__(256) k_bucket_keys(const int32_t* __restrict__ dom_cls, const int32_t* __restrict__ rng_cls, const uint8_t* __restrict__ bins,
                                                      uint32_t nD, uint32_t nR, uint32_t nbins, uint32_t nb, uint32_t list_bit, uint16_t* __restrict__ keys,
-                                                     uint32_t* __restrict__ vals, uint32_t* __restrict__ hist_d, uint32_t* __restrict__ hist_r) {
+                                                     uint32_t* __restrict__ vals, uint32_t* __restrict__ hist_d, uint32_t* __restrict__ hist_r,
+                                                     const uint32_t* __restrict__ cells, uint32_t cells_w, uint32_t dnx, const fe_grid_item* __restrict__ rng,
+                                                     uint32_t T, uint32_t bin_width) {
     __shared__ uint32_t sh[2 * FE_MAX_TOTAL];
     for (uint32_t b = threadIdx.x; b < 2 * FE_MAX_TOTAL; b += blockDim.x) sh[b] = 0;
     __syncthreads();
@@ -72,7 +76,19 @@ __global__ void __launch_bounds__(256) k_bucket_keys(const int32_t* __restrict__
         const bool is_rng = i >= nD;
         const uint32_t j = is_rng ? i - nD : i;
         const int32_t* cls = is_rng ? rng_cls : dom_cls;
-        const uint32_t k = (cls ? (uint32_t)(cls[j] + 1) : 0u) * nbins + (bins ? (uint32_t)bins[i] : 0u);
+        uint32_t bin = bins ? (uint32_t)bins[i] : 0u;
+        if (cells) {
+            uint32_t s;
+            if (is_rng) {
+                const fe_grid_item r = rng[j];
+                s = 4u * __ldg(cells + (size_t)(r.y / T) * cells_w + r.x / T);
+            } else {
+                const uint32_t* c = cells + (size_t)(j / dnx) * cells_w + j % dnx;
+                s = __ldg(c) + __ldg(c + 1) + __ldg(c + cells_w) + __ldg(c + cells_w + 1);
+            }
+            bin = min(s / bin_width, (uint32_t)FE_MAX_BUCKETS - 1);
+        }
+        const uint32_t k = (cls ? (uint32_t)(cls[j] + 1) : 0u) * nbins + bin;
         keys[i] = (uint16_t)(k | (is_rng ? list_bit : 0u));
         vals[i] = j;
         atomicAdd(&sh[k + (is_rng ? FE_MAX_TOTAL : 0)], 1u);
@@ -560,7 +576,8 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
     FE_CUDA(ctx, cudaMemsetAsync(hist_d, 0, ((size_t)FE_MAX_TOTAL * 10 + 2 * FE_MAX_BUCKETS) * 4, ctx->stream));
 
     // ---- bucket keys, orders ----
-    if (st->bins) {
+    const bool bins_from_cells = st->bins && lv.cells && lv.cells2;       // both lists on the lattice of one image: bins inside k_bucket_keys
+    if (st->bins && !bins_from_cells) {
         if (lv.cells) launch_dom_from_cells(ctx->stream, lv.cells, lv.cells_w, lv.dnx, nD, nullptr, width, bins8, scratch);
         else launch_brightness_bins(ctx->stream, ctx->src.px, ctx->src.stride, lv.d_dom, nD, g.S, 1u, width, bins8, scratch);
         launch_brightness_bins(ctx->stream, ctx->tgt.px, ctx->tgt.stride, lv.d_rng, nR, g.T, 4u, width, bins8 + nD, scratch + FE_MAX_BUCKETS);
@@ -569,8 +586,8 @@ int search_level_device(fe_ctx* ctx, const DeviceLevel& lv, int kind, uint32_t n
     }
     int bits = 1;
     while ((1u << bits) < nb) ++bits;
-    PLAUNCH(ctx, k_bucket_keys, std::min(cdiv_u(n, 1024), 4u * ctx->n_sm), 256, lv.dom_cls, lv.rng_cls, st->bins ? bins8 : nullptr, nD, nR, st->nbins, nb, 1u << bits, keys,
-            ctx->b_vals_tmp.as<uint32_t>(), hist_d, hist_r);
+    PLAUNCH(ctx, k_bucket_keys, std::min(cdiv_u(n, 1024), 4u * ctx->n_sm), 256, lv.dom_cls, lv.rng_cls, (st->bins && !bins_from_cells) ? bins8 : nullptr, nD, nR, st->nbins,
+            nb, 1u << bits, keys, ctx->b_vals_tmp.as<uint32_t>(), hist_d, hist_r, bins_from_cells ? lv.cells : nullptr, lv.cells_w, lv.dnx, lv.d_rng, g.T, width);
     if (sorted) {
         // one stable sort for both lists: the list bit is the top key bit
         size_t tmp = 0;
