@@ -147,7 +147,8 @@ extern "C" void fe_destroy(fe_ctx* ctx) {
                       &ctx->b_rowc, &ctx->b_coln, &ctx->b_rowbest, &ctx->b_rowhit, &ctx->b_hist, &ctx->b_level_items, &ctx->b_split,
                       &ctx->b_scan, &ctx->b_scan_tmp, &ctx->b_rng_next, &ctx->b_counters, &ctx->b_A16, &ctx->b_B16, &ctx->b_tmaps,
                       &ctx->b_items, &ctx->b_dec_a, &ctx->b_dec_b, &ctx->b_dec_items, &ctx->b_dec_sum, &ctx->b_q, &ctx->b_bound,
-                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_dom_order2, &ctx->b_rng_order2, &ctx->b_rng2, &ctx->b_pos_of, &ctx->b_lbq, &ctx->b_lbcand, &ctx->b_cells, &ctx->b_dq[0], &ctx->b_dq[1]};
+                      &ctx->b_flag_idx, &ctx->b_blob_dom, &ctx->b_tileseg, &ctx->b_dom_order2, &ctx->b_rng_order2, &ctx->b_rng2, &ctx->b_pos_of, &ctx->b_lbq, &ctx->b_lbcand, &ctx->b_cells, &ctx->b_dq[0], &ctx->b_dq[1], &ctx->b_dom_lvl[0], &ctx->b_dom_lvl[1], &ctx->b_dom_lvl[2],
+                      &ctx->b_dom_lvl[3], &ctx->b_dom_lvl[4], &ctx->b_dom_lvl[5], &ctx->b_dom_lvl[6], &ctx->b_dom_lvl[7]};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
@@ -883,13 +884,18 @@ static int quad_enqueue(fe_ctx* ctx) {
     LevelIO& io = j->io;
     io = LevelIO{};
     FE_TRY(make_geom(ctx, S, T, true, &io.g));
-    if (nD) {
-        FE_CUDA(ctx, ctx->b_dom.ensure(nD * sizeof(fe_grid_item)));
-        LAUNCH(ctx, k_uniform_grid, cdiv(nD, 256), 256, ctx->b_dom.as<fe_grid_item>(), dnx, (uint32_t)nD, S, T, 0u);
+    // the level's domain grid depends on the image size only: kept per level across encodes
+    DevBuf& domb = ctx->b_dom_lvl[j->level & 7];
+    unsigned long long& dtag = ctx->dom_lvl_tag[j->level & 7];
+    const unsigned long long want = ((unsigned long long)W << 40) ^ ((unsigned long long)H << 16) ^ ((unsigned long long)S << 8) ^ T;
+    if (nD && dtag != want) {
+        FE_CUDA(ctx, domb.ensure(nD * sizeof(fe_grid_item)));
+        LAUNCH(ctx, k_uniform_grid, cdiv(nD, 256), 256, domb.as<fe_grid_item>(), dnx, (uint32_t)nD, S, T, 0u);
+        dtag = want;
     }
     FE_CUDA(ctx, ctx->b_level_items.ensure(n_pending * sizeof(fe_encode_item)));
     FE_CUDA(ctx, ctx->b_split.ensure(n_pending * 4 + 4));
-    io.d_dom = ctx->b_dom.as<fe_grid_item>(); io.nD = (uint32_t)nD;
+    io.d_dom = domb.as<fe_grid_item>(); io.nD = (uint32_t)nD;
     io.d_rng = ctx->b_rng.as<fe_grid_item>(); io.nR = (uint32_t)n_pending;
     io.d_out = ctx->b_level_items.as<fe_encode_item>();
     io.can_split = (T / 2 >= j->t_min) ? 1 : 0;

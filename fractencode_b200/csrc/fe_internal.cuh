@@ -95,6 +95,8 @@ struct fe_ctx {
     DevBuf b_rng2, b_pos_of;
     // lower-bound prefilter: cell-sum plane, candidate list (+ its counter)
     DevBuf b_lbq, b_lbcand, b_cells, b_dq[2];
+    DevBuf b_dom_lvl[8];                  // quadtree: the domain grid of level l (a function of the image size only)
+    unsigned long long dom_lvl_tag[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::chrono::steady_clock::time_point level_host_t0;   // FE_PASS_TIMES: host clock at the level's first launch
     // tcgen05 path operands
     DevBuf b_A16, b_B16, b_tmaps, b_blob_dom, b_tileseg;
